@@ -1,0 +1,90 @@
+/*
+ * wdg.h -- C ABI of libwdg.so, the B200 (sm_100a) implementation of the
+ * wind-downscaling-gan generator forward hot path.
+ *
+ * The reference (OpheliaMiralles/wind-downscaling-gan) has no FFI: its boundary for
+ * this path is the Keras object surface (`models.py:9-73`, `api.py:89-152`).  The
+ * entry points below are what a ctypes binding added to the reference would call in
+ * place of `make_generator(...)`, `generator.load_weights(...)` and
+ * `gen.predict([tensor, noise])` -- see INTEGRATION.md for that binding.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a
+ * non-zero code with a message available from wdg_last_error(); no exceptions
+ * cross the ABI; tensors are channels-last float32 exactly as the reference
+ * passes them ((B, T, S, S, C), `models.py:24-25`).  `*_dev` pointers are device
+ * memory owned by the caller; `stream` is a cudaStream_t (NULL = default stream).
+ * There is no CPU fallback: every call fails if no sm_100 device is present.
+ */
+#ifndef WDG_H
+#define WDG_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wdg_generator wdg_generator;
+
+/* Last error message of the calling thread ("" if none). */
+const char* wdg_last_error(void);
+
+/* Library / device probe: returns 0 and fills sm_major/sm_minor/sm_count of device `device`. */
+int wdg_device_info(int device, int* sm_major, int* sm_minor, int* sm_count);
+
+/* Replaces make_generator(image_size, in_channels, noise_channels, out_channels, n_timesteps,
+ * batch_size=None, feature_channels=128) -- models.py:9-17.  Asserts of models.py:19-20 are
+ * returned as errors.  n_timesteps is the default sequence length; forward() takes T per call. */
+int wdg_generator_create(wdg_generator** out, int image_size, int in_channels, int noise_channels,
+                         int out_channels, int n_timesteps, int feature_channels);
+void wdg_generator_destroy(wdg_generator* g);
+
+/* Number of weight tensors, and name/shape of the i-th one.  Names are the reference
+ * checkpoint's variable names (weights-55.ckpt/generator.index), e.g.
+ * "layer_with_weights-0/layer/w"; layouts are the reference's (Conv2D HWIO, Conv2DTranspose
+ * (kh, kw, out, in)).  dims must have room for 4 entries. */
+int wdg_generator_num_weights(const wdg_generator* g);
+int wdg_generator_weight_info(const wdg_generator* g, int index, const char** name, int64_t* dims, int* ndim);
+
+/* Replaces generator.load_weights / set_weights (ganbase.py:136-140): copies one fp32 HOST
+ * tensor, checked against the expected shape, into the handle. */
+int wdg_generator_set_weight(wdg_generator* g, const char* name, const float* host_data, const int64_t* dims,
+                             int ndim);
+/* Reads one tensor back (fp32 HOST), e.g. for save_weights (ganbase.py:132-134). */
+int wdg_generator_get_weight(const wdg_generator* g, const char* name, float* host_data, int64_t count);
+
+/* Re-packs the fp32 weights into the kernels' device layouts (bf16, K-major, gate-interleaved,
+ * BatchNorm folded to scale/shift).  Must be called after the last set_weight and before forward. */
+int wdg_generator_finalize(wdg_generator* g);
+
+/* Workspace (activation buffers) needed for a forward of B sequences x T timesteps. */
+int wdg_generator_workspace_bytes(const wdg_generator* g, int B, int T, size_t* bytes);
+/* Binds a caller-owned device workspace of at least that size and builds the TMA descriptors /
+ * launch plan for (B, T).  The workspace is zero-filled on `stream`. */
+int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspace_dev, size_t bytes, void* stream);
+
+/* Replaces gen.predict([image, noise]) / generator([image, noise], training=False) -- api.py:137.
+ * image_dev (B,T,S,S,Cin) fp32, noise_dev (B,T,S,S,Cnoise) fp32 -> out_dev (B,T,S,S,Cout) fp32,
+ * all device pointers; asynchronous on `stream`.  (B, T) must equal the bound plan. */
+int wdg_generator_forward(wdg_generator* g, const float* image_dev, const float* noise_dev, float* out_dev,
+                          void* stream);
+
+/* Same call with HOST buffers: copies inputs host->device, runs forward, copies the result
+ * back and synchronises.  io_dev is a caller-owned device staging buffer of at least
+ * wdg_generator_io_bytes() bytes. */
+int wdg_generator_io_bytes(const wdg_generator* g, int B, int T, size_t* bytes);
+int wdg_generator_predict_host(wdg_generator* g, const float* image_host, const float* noise_host,
+                               float* out_host, void* io_dev, void* stream);
+
+/* Number of kernels one forward() launches for the bound plan (bench.py's gpu_launches). */
+int wdg_generator_launches_per_forward(const wdg_generator* g);
+
+/* Debug / parity hooks: copies an intermediate activation of the last forward() to the host as
+ * fp32.  which: 0 res_2 (N,S/2,S/2,128)  1 res_4 (N,S/4,S/4,128)  2 lstm h (N,S/4,S/4,128)
+ * 3 g5 (N,S/4,S/4,64)  4 g7 (N,S/2,S/2,32)  5 g9 (N,S,S,16), N = B*T. */
+int wdg_generator_debug_read(const wdg_generator* g, int which, float* host_out, int64_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WDG_H */

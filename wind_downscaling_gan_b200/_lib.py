@@ -1,0 +1,69 @@
+"""ctypes binding of libwdg.so (C ABI in include/wdg.h).
+
+There is no CPU fallback: importing this module without the built library, or
+calling into it without an sm_100 device, raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libwdg.so")
+
+_lib = None
+
+
+class WdgError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
+    fp = C.POINTER(C.c_float)
+    i64p = C.POINTER(C.c_int64)
+    lib.wdg_last_error.restype = C.c_char_p
+    lib.wdg_last_error.argtypes = []
+    sigs = {
+        "wdg_device_info": [i, C.POINTER(i), C.POINTER(i), C.POINTER(i)],
+        "wdg_generator_create": [C.POINTER(vp), i, i, i, i, i, i],
+        "wdg_generator_num_weights": [vp],
+        "wdg_generator_weight_info": [vp, i, C.POINTER(C.c_char_p), i64p, C.POINTER(i)],
+        "wdg_generator_set_weight": [vp, C.c_char_p, vp, i64p, i],
+        "wdg_generator_get_weight": [vp, C.c_char_p, vp, C.c_int64],
+        "wdg_generator_finalize": [vp],
+        "wdg_generator_workspace_bytes": [vp, i, i, C.POINTER(sz)],
+        "wdg_generator_bind": [vp, i, i, vp, sz, vp],
+        "wdg_generator_forward": [vp, vp, vp, vp, vp],
+        "wdg_generator_io_bytes": [vp, i, i, C.POINTER(sz)],
+        "wdg_generator_predict_host": [vp, vp, vp, vp, vp, vp],
+        "wdg_generator_launches_per_forward": [vp],
+        "wdg_generator_debug_read": [vp, i, vp, C.c_int64],
+        "wdg_gather_normalise": [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, vp, vp],
+        "wdg_stitch": [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp],
+    }
+    for name, args in sigs.items():
+        if not hasattr(lib, name):
+            continue
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = i
+    lib.wdg_generator_destroy.argtypes = [vp]
+    lib.wdg_generator_destroy.restype = None
+    del fp
+
+
+def lib():
+    """Load libwdg.so (once).  Raises WdgError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise WdgError(
+                f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+                "This package has no CPU / PyTorch fallback.")
+        _lib = C.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise WdgError(lib().wdg_last_error().decode())

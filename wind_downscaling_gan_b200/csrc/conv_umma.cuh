@@ -1,0 +1,304 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+//   D[M = 128 output pixels, N = BN channels] = sum over K-blocks A[128, 64] * B[BN, 64]^T
+//
+// * A (activations, bf16 channels-last) is never im2col'ed in memory: every K-block is one
+//   TMA box {64 channels, tile_w, tile_h, (1,) tile_n} of a 5-D tensor map, shifted by the
+//   filter tap; out-of-bounds rows/cols are zero-filled by TMA (= SAME padding).  The box
+//   lands in shared memory as 128 rows x 128 B with SWIZZLE_128B, which is exactly the
+//   canonical K-major UMMA operand layout.  Strided convolutions use tensor maps with
+//   overlapping strides over a zero-padded image (window axis, ox, oy, row parity, n).
+// * B (weights, bf16) is a pre-packed [N_total][num_kb*64] K-major matrix, one 2-D TMA box
+//   {64, BN} per K-block.
+// * Accumulators live in TMEM (2 stages x BN fp32 columns) so the epilogue of tile i overlaps
+//   the main loop of tile i+1.  Persistent CTAs, static round-robin tile schedule.
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 = epilogue.
+#pragma once
+#include "ptx.cuh"
+
+namespace wdg {
+
+constexpr int MAX_KB = 80;
+constexpr int TILE_M = 128;
+constexpr int A_STAGE_BYTES = TILE_M * 128;
+
+enum { EPI_AFFINE = 0, EPI_LSTM = 1 };
+
+struct KBlock {        // one slice of the GEMM K axis
+  int8_t src;          // which A tensor map (0..2)
+  int8_t half;         // 1: 32-channel slice (64-byte rows, SWIZZLE_64B) -> 2 MMAs instead of 4
+  int16_t o0, o1, o2, o3;  // offsets added to the tile's base TMA coordinate (dims 0..3)
+};
+
+struct EpiParams {
+  // ---- EPI_AFFINE: v = (lrelu ? leaky(acc + bias) : acc + bias) * scale + shift  (per GEMM column)
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  void* out;                         // bf16, or fp32 when out_f32
+  long long out_sn, out_sy, out_sx;  // destination element strides for (image, row, col)
+  int out_c0;                        // first destination channel
+  int out_mul;                       // 1; 2 = 2x2 stride-2 transposed conv (pixel shuffle by column group)
+  int group_cols;                    // columns per (ky,kx) group when out_mul == 2
+  int lrelu;
+  int out_f32;
+  // ---- EPI_LSTM (BN = 256 = 4 gates x 64 channels per N tile)
+  float* c_state;                    // fp32 [n][H][W][F], updated in place
+  __nv_bfloat16* h_out;              // bf16, pixel (n,y,x) channel c at n*h_sn + h_off + (y*W+x)*F + c
+  long long h_sn, h_off;
+  int first_step;                    // c_{t-1} = 0: skip the state read
+  int F;
+};
+
+struct ConvParams {
+  int H, W, N;                 // GEMM M axis = N images of H x W output pixels
+  int tile_w, tile_h, tile_n;  // TMA box in pixels; tile_w * tile_h * tile_n == 128
+  int tiles_x, tiles_y, tiles_n;
+  int n_tiles_N;               // number of BN-wide column tiles
+  int num_kb;
+  int n_coord;                 // TMA coordinate (3 or 4) that carries the image index
+  EpiParams ep;
+  KBlock kb[MAX_KB];
+};
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float leaky02(float v) { return v >= 0.f ? v : 0.2f * v; }
+__device__ __forceinline__ float hard_sigmoid(float v) { return fminf(fmaxf(0.2f * v + 0.5f, 0.f), 1.f); }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(192, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int total_tiles = m_tiles * p.n_tiles_N;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmA2);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles_N;
+        const int m_tile = tile / p.n_tiles_N;
+        const int tx = m_tile % p.tiles_x;
+        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+        const int tn = m_tile / (p.tiles_x * p.tiles_y);
+        int base[5] = {0, tx * p.tile_w, ty * p.tile_h, 0, 0};
+        base[p.n_coord] = tn * p.tile_n;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          const KBlock k = p.kb[kb];
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t a_bytes = k.half ? (A_STAGE_BYTES / 2) : A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], a_bytes + Cfg::B_STAGE_BYTES);
+          const CUtensorMap* tm = (k.src == 0) ? &tmA0 : ((k.src == 1) ? &tmA1 : &tmA2);
+          tma_load_5d(smA + stage * A_STAGE_BYTES, tm, &full_bar[stage], base[0] + k.o0, base[1] + k.o1,
+                      base[2] + k.o2, base[3] + k.o3, base[4]);
+          tma_load_2d(smB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * 64, n_tile * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          const int half = p.kb[kb].half;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smA + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(smB + stage * Cfg::B_STAGE_BYTES);
+          const uint32_t a_row = half ? 64u : 128u;
+          const int nk = half ? 2 : 4;
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t da = umma_desc_kmajor(a_addr + k * 32, a_row);
+            const uint64_t db = umma_desc_kmajor(b_addr + k * 32, 128u);
+            umma_bf16(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);       // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5)
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;      // GEMM row == pixel within the tile
+    const int lx = row % p.tile_w;
+    const int ly = (row / p.tile_w) % p.tile_h;
+    const int ln = row / (p.tile_w * p.tile_h);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles_N;
+      const int m_tile = tile / p.n_tiles_N;
+      const int tx = m_tile % p.tiles_x;
+      const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+      const int tn = m_tile / (p.tiles_x * p.tiles_y);
+      const int x = tx * p.tile_w + lx;
+      const int y = ty * p.tile_h + ly;
+      const int n = tn * p.tile_n + ln;
+      const bool valid = (x < p.W) && (y < p.H) && (n < p.N);
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+
+      if constexpr (EPI == EPI_AFFINE) {
+        const EpiParams& e = p.ep;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+          if (valid) {
+            const int col = n_tile * BN + c0;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float a = __uint_as_float(r[i]) + __ldg(e.bias + col + i);
+              if (e.lrelu) a = leaky02(a);
+              v[i] = a * __ldg(e.scale + col + i) + __ldg(e.shift + col + i);
+            }
+            int oy = y, ox = x, oc = col;
+            if (e.out_mul == 2) {
+              const int g = col / e.group_cols;
+              oc = col - g * e.group_cols;
+              oy = 2 * y + (g >> 1);
+              ox = 2 * x + (g & 1);
+            }
+            const long long off = (long long)n * e.out_sn + (long long)oy * e.out_sy + (long long)ox * e.out_sx +
+                                  e.out_c0 + oc;
+            if (e.out_f32) {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off);
+              dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                  pack_bf16x2(v[6], v[7]));
+              dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                  pack_bf16x2(v[14], v[15]));
+            }
+          }
+        }
+      } else {
+        // ConvLSTM gate epilogue.  Column layout of this N tile: [i | f | c~ | o] x 64 channels.
+        static_assert(EPI != EPI_LSTM || BN == 256, "LSTM epilogue expects 4 gates x 64 channels");
+        const EpiParams& e = p.ep;
+        const long long pix = ((long long)n * p.H + y) * p.W + x;
+#pragma unroll 1
+        for (int s = 0; s < 4; ++s) {
+          uint32_t zi[16], zf[16], zc[16], zo[16];
+          tmem_ld16(taddr + 0 * 64 + s * 16, zi);
+          tmem_ld16(taddr + 1 * 64 + s * 16, zf);
+          tmem_ld16(taddr + 2 * 64 + s * 16, zc);
+          tmem_ld16(taddr + 3 * 64 + s * 16, zo);
+          tmem_ld_wait();
+          if (valid) {
+            const int ch0 = n_tile * 64 + s * 16;
+            const float* bias = e.bias + n_tile * 256 + s * 16;
+            float* cptr = e.c_state + pix * e.F + ch0;
+            float cprev[16];
+            if (e.first_step) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) cprev[i] = 0.f;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 t = reinterpret_cast<const float4*>(cptr)[i];
+                cprev[4 * i] = t.x; cprev[4 * i + 1] = t.y; cprev[4 * i + 2] = t.z; cprev[4 * i + 3] = t.w;
+              }
+            }
+            float cn[16], hn[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float gi = hard_sigmoid(__uint_as_float(zi[i]) + __ldg(bias + i));
+              const float gf = hard_sigmoid(__uint_as_float(zf[i]) + __ldg(bias + 64 + i));
+              const float gc = tanhf(__uint_as_float(zc[i]) + __ldg(bias + 128 + i));
+              const float go = hard_sigmoid(__uint_as_float(zo[i]) + __ldg(bias + 192 + i));
+              cn[i] = gf * cprev[i] + gi * gc;
+              hn[i] = go * tanhf(cn[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<float4*>(cptr)[i] = make_float4(cn[4 * i], cn[4 * i + 1], cn[4 * i + 2], cn[4 * i + 3]);
+            uint4* hdst = reinterpret_cast<uint4*>(e.h_out + (long long)n * e.h_sn + e.h_off +
+                                                   ((long long)y * p.W + x) * e.F + ch0);
+            hdst[0] = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]), pack_bf16x2(hn[4], hn[5]),
+                                 pack_bf16x2(hn[6], hn[7]));
+            hdst[1] = make_uint4(pack_bf16x2(hn[8], hn[9]), pack_bf16x2(hn[10], hn[11]), pack_bf16x2(hn[12], hn[13]),
+                                 pack_bf16x2(hn[14], hn[15]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace wdg

@@ -1,0 +1,701 @@
+// Host side of libwdg.so: weight packing, TMA descriptor / launch-plan construction and the
+// C ABI declared in include/wdg.h for the generator forward (reference models.py:9-73).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/wdg.h"
+#include "conv_umma.cuh"
+#include "stencil_kernels.cuh"
+
+using namespace wdg;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(const std::string& m) {
+  g_err = m;
+  return 1;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(_e));        \
+  } while (0)
+
+extern "C" const char* wdg_last_error(void) { return g_err.c_str(); }
+
+extern "C" int wdg_device_info(int device, int* sm_major, int* sm_minor, int* sm_count) {
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (sm_major) *sm_major = prop.major;
+  if (sm_minor) *sm_minor = prop.minor;
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  return 0;
+}
+
+// --------------------------------------------------------- TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor map of rank 2..5.  dims/box in elements (dim 0 innermost), strides in ELEMENTS for dims 1..rank-1.
+static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                     const uint32_t* box, int inner_bytes) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t gbox[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_el[i - 1] * 2;
+  }
+  CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                              : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, gbox, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu box %u %u %u", (int)r,
+             rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+             box[0], box[1], rank > 2 ? box[2] : 0);
+    return fail(buf);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------- the handle
+struct ConvLaunch {
+  CUtensorMap tmA[3];
+  CUtensorMap tmB;
+  ConvParams p;
+  int bn;
+  int epi;
+  int grid;
+};
+
+struct WeightDesc {
+  std::string name;
+  std::vector<int64_t> dims;
+  int64_t count() const {
+    int64_t c = 1;
+    for (auto d : dims) c *= d;
+    return c;
+  }
+};
+
+struct wdg_generator {
+  int S, cin, cnoise, cout, T_default, F;
+  int CP;                 // padded input channels of the packed image
+  int device = 0;
+  int sm_count = 148;
+  std::vector<WeightDesc> descs;
+  std::map<std::string, std::vector<float>> w;
+  std::map<std::string, bool> set_;
+  bool finalized = false;
+  // packed device weights
+  __nv_bfloat16 *B0 = nullptr, *B2 = nullptr, *BL = nullptr, *B5 = nullptr, *B7 = nullptr, *B9 = nullptr;
+  float* fparams = nullptr;  // all fp32 per-column vectors, see offsets
+  float *bias0, *sc0, *sh0, *bias2, *sc2, *sh2, *biasL, *bias5, *sc5, *sh5, *bias7, *sc7, *sh7, *bias9, *sc9, *sh9,
+      *w11, *b11;
+  // plan
+  int B = 0, T = 0;
+  uint8_t* ws = nullptr;
+  __nv_bfloat16 *xpad, *res2p, *res4, *hseq, *g5, *g7, *up, *g9;
+  float* cstate;
+  ConvLaunch L0, L2, L5, L7, L9;
+  std::vector<ConvLaunch> LS;  // one per timestep
+  int launches = 0;
+};
+
+static const char* LWF = "layer_with_weights-%d/%s";
+static std::string wname(int i, const char* leaf) {
+  char b[96];
+  snprintf(b, sizeof b, LWF, i, leaf);
+  return b;
+}
+
+extern "C" int wdg_generator_create(wdg_generator** out, int image_size, int in_channels, int noise_channels,
+                                    int out_channels, int n_timesteps, int feature_channels) {
+  if (!out) return fail("null out");
+  if (image_size % 4 != 0) return fail("image_size % 4 != 0 (models.py:19)");
+  if (feature_channels % 8 != 0) return fail("feature_channels % 8 != 0 (models.py:20)");
+  const int cin_total = in_channels + noise_channels;
+  const int f0 = cin_total * 8 <= feature_channels ? cin_total * 8 : feature_channels;  // models.py:31
+  if (feature_channels != 128 || f0 != 128)
+    return fail("sm_100a kernels are built for feature_channels == 128 and 8*(in+noise) >= 128 (api.py:22-28)");
+  if (feature_channels / 8 < out_channels) return fail("feature_channels/8 < out_channels: reference branch models.py:66-68 is broken; not built");
+  if (out_channels != 2) return fail("final convolution kernel is instantiated for out_channels == 2 (api.py:28)");
+  if (image_size % 32 != 0) return fail("image_size must be a multiple of 32 for the tile shapes used");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("no CUDA device: libwdg has no CPU fallback");
+  auto* g = new wdg_generator();
+  g->S = image_size; g->cin = in_channels; g->cnoise = noise_channels; g->cout = out_channels;
+  g->T_default = n_timesteps; g->F = feature_channels;
+  g->CP = (cin_total + 7) / 8 * 8;
+  cudaGetDevice(&g->device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, g->device) != cudaSuccess) { delete g; return fail("cudaGetDeviceProperties failed"); }
+  if (prop.major != 10) { delete g; return fail("libwdg requires an sm_100 (B200) device"); }
+  g->sm_count = prop.multiProcessorCount;
+  const int64_t F = feature_channels, C = cin_total, O = out_channels;
+  auto add = [&](int i, const char* leaf, std::vector<int64_t> d) { g->descs.push_back({wname(i, leaf), d}); };
+  auto bn = [&](int i, int64_t c) {
+    add(i, "gamma", {c}); add(i, "beta", {c}); add(i, "moving_mean", {c}); add(i, "moving_variance", {c});
+  };
+  add(0, "layer/w", {8, 8, C, f0}); add(0, "layer/layer/bias", {f0}); add(0, "layer/sn_u", {1, f0}); bn(1, f0);
+  add(2, "layer/w", {4, 4, f0, F}); add(2, "layer/layer/bias", {F}); add(2, "layer/sn_u", {1, F}); bn(3, F);
+  add(4, "cell/kernel", {3, 3, F, 4 * F}); add(4, "cell/recurrent_kernel", {3, 3, F, 4 * F}); add(4, "cell/bias", {4 * F});
+  add(5, "layer/w", {3, 3, F, F / 2}); add(5, "layer/layer/bias", {F / 2}); add(5, "layer/sn_u", {1, F / 2}); bn(6, F / 2);
+  add(7, "layer/w", {2, 2, F / 4, F / 2 + F}); add(7, "layer/layer/bias", {F / 4}); add(7, "layer/sn_u", {1, F / 2 + F}); bn(8, F / 4);
+  add(9, "layer/kernel", {5, 5, F / 8, F / 4 + f0}); add(9, "layer/bias", {F / 8}); bn(10, F / 8);
+  add(11, "layer/kernel", {3, 3, F / 8, O}); add(11, "layer/bias", {O});
+  for (auto& d : g->descs) g->w[d.name] = std::vector<float>((size_t)d.count(), 0.f);
+  *out = g;
+  return 0;
+}
+
+extern "C" void wdg_generator_destroy(wdg_generator* g) {
+  if (!g) return;
+  cudaFree(g->B0); cudaFree(g->B2); cudaFree(g->BL); cudaFree(g->B5); cudaFree(g->B7); cudaFree(g->B9);
+  cudaFree(g->fparams);
+  delete g;
+}
+
+extern "C" int wdg_generator_num_weights(const wdg_generator* g) { return g ? (int)g->descs.size() : 0; }
+
+extern "C" int wdg_generator_weight_info(const wdg_generator* g, int index, const char** name, int64_t* dims, int* ndim) {
+  if (!g || index < 0 || index >= (int)g->descs.size()) return fail("weight index out of range");
+  const WeightDesc& d = g->descs[index];
+  if (name) *name = d.name.c_str();
+  if (ndim) *ndim = (int)d.dims.size();
+  if (dims) for (size_t i = 0; i < d.dims.size(); ++i) dims[i] = d.dims[i];
+  return 0;
+}
+
+extern "C" int wdg_generator_set_weight(wdg_generator* g, const char* name, const float* host_data, const int64_t* dims, int ndim) {
+  if (!g || !name || !host_data) return fail("null argument");
+  for (auto& d : g->descs) {
+    if (d.name != name) continue;
+    if ((int)d.dims.size() != ndim) return fail(std::string("rank mismatch for ") + name);
+    for (int i = 0; i < ndim; ++i)
+      if (d.dims[i] != dims[i]) return fail(std::string("shape mismatch for ") + name);
+    std::memcpy(g->w[d.name].data(), host_data, sizeof(float) * (size_t)d.count());
+    g->set_[d.name] = true;
+    g->finalized = false;
+    return 0;
+  }
+  return fail(std::string("unknown weight name: ") + name);
+}
+
+extern "C" int wdg_generator_get_weight(const wdg_generator* g, const char* name, float* host_data, int64_t count) {
+  if (!g || !name || !host_data) return fail("null argument");
+  auto it = g->w.find(name);
+  if (it == g->w.end()) return fail(std::string("unknown weight name: ") + name);
+  if ((int64_t)it->second.size() != count) return fail(std::string("size mismatch for ") + name);
+  std::memcpy(host_data, it->second.data(), sizeof(float) * (size_t)count);
+  return 0;
+}
+
+// -------------------------------------------------------- weight packing
+static inline __nv_bfloat16 tobf(float v) { return __float2bfloat16_rn(v); }
+
+template <class Fn>
+static int upload_B(__nv_bfloat16** dev, int n_rows, int num_kb, Fn value /* (row, kb, j) -> float */) {
+  std::vector<__nv_bfloat16> h((size_t)n_rows * num_kb * 64);
+  for (int r = 0; r < n_rows; ++r)
+    for (int kb = 0; kb < num_kb; ++kb)
+      for (int j = 0; j < 64; ++j) h[((size_t)r * num_kb + kb) * 64 + j] = tobf(value(r, kb, j));
+  if (*dev) cudaFree(*dev);
+  *dev = nullptr;
+  CK(cudaMalloc(dev, h.size() * sizeof(__nv_bfloat16)));
+  CK(cudaMemcpy(*dev, h.data(), h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int wdg_generator_finalize(wdg_generator* g) {
+  if (!g) return fail("null handle");
+  const int F = g->F, C = g->cin + g->cnoise, CP = g->CP;
+  auto W = [&](int i, const char* leaf) -> const std::vector<float>& { return g->w[wname(i, leaf)]; };
+  // ---- L0: 8x8 s2 conv.  K index within a tap row = kx*CP + c (window over the padded image).
+  {
+    const auto& w = W(0, "layer/w");  // [8][8][C][128]
+    const int wk = 8 * CP;            // window elements per tap row
+    const int chunks = wk / 64;
+    if (wk % 64) return fail("8*CP not a multiple of 64");
+    if (upload_B(&g->B0, 128, 8 * chunks, [&](int n, int kb, int j) {
+          const int ky = kb / chunks, e = (kb % chunks) * 64 + j, kx = e / CP, c = e % CP;
+          return c < C ? w[(((size_t)ky * 8 + kx) * C + c) * 128 + n] : 0.f;
+        })) return 1;
+  }
+  // ---- L2: 4x4 s2 conv on the padded res_2.  K within tap row = kx*128 + c.
+  {
+    const auto& w = W(2, "layer/w");  // [4][4][128][128]
+    if (upload_B(&g->B2, 128, 4 * 8, [&](int n, int kb, int j) {
+          const int ky = kb / 8, e = (kb % 8) * 64 + j, kx = e / 128, c = e % 128;
+          return w[(((size_t)ky * 4 + kx) * 128 + c) * 128 + n];
+        })) return 1;
+  }
+  // ---- ConvLSTM: packed column = ntile*256 + gate*64 + cc  <->  original gate*F + ntile*64 + cc.
+  {
+    const auto& k = W(4, "cell/kernel");
+    const auto& r = W(4, "cell/recurrent_kernel");
+    if (upload_B(&g->BL, 4 * F, 36, [&](int n, int kb, int j) {
+          const int ntile = n / 256, gate = (n % 256) / 64, cc = n % 64;
+          const int orig = gate * F + ntile * 64 + cc;
+          const int kk = kb % 18, tap = kk / 2, c = (kk % 2) * 64 + j;
+          const auto& src = kb < 18 ? k : r;
+          return src[((size_t)tap * F + c) * (4 * F) + orig];
+        })) return 1;
+  }
+  // ---- L5: 3x3 same conv 128 -> 64
+  {
+    const auto& w = W(5, "layer/w");  // [3][3][128][64]
+    if (upload_B(&g->B5, F / 2, 18, [&](int n, int kb, int j) {
+          const int tap = kb / 2, c = (kb % 2) * 64 + j;
+          return w[((size_t)tap * F + c) * (F / 2) + n];
+        })) return 1;
+  }
+  // ---- L7: ConvT 2x2 s2, kernel (kh,kw,out,in); column = (ky*2+kx)*32 + o; K = in channel (g5 first, res_4 second)
+  {
+    const auto& w = W(7, "layer/w");  // [2][2][32][192]
+    const int O = F / 4, I = F / 2 + F;
+    if (upload_B(&g->B7, 4 * O, I / 64, [&](int n, int kb, int j) {
+          const int grp = n / O, o = n % O, i = kb * 64 + j;
+          return w[((size_t)grp * O + o) * I + i];
+        })) return 1;
+  }
+  // ---- L9: ConvT 5x5 same s1 == SAME correlation with flipped kernel, channels swapped.
+  {
+    const auto& w = W(9, "layer/kernel");  // [5][5][16][160]
+    const int O = F / 8, I = F / 4 + 128;
+    const int chunks = (I + 63) / 64;
+    if (upload_B(&g->B9, O, 25 * chunks, [&](int n, int kb, int j) {
+          const int tap = kb / chunks, ty = tap / 5, tx = tap % 5, i = (kb % chunks) * 64 + j;
+          return i < I ? w[(((size_t)(4 - ty) * 5 + (4 - tx)) * O + n) * I + i] : 0.f;
+        })) return 1;
+  }
+  // ---- fp32 per-column vectors
+  std::vector<float> fp;
+  auto push = [&](const std::vector<float>& v) { size_t o = fp.size(); fp.insert(fp.end(), v.begin(), v.end()); return o; };
+  auto bn_fold = [&](int i, int c, std::vector<float>& sc, std::vector<float>& sh) {
+    const auto &ga = W(i, "gamma"), &be = W(i, "beta"), &mu = W(i, "moving_mean"), &va = W(i, "moving_variance");
+    sc.resize(c); sh.resize(c);
+    for (int k = 0; k < c; ++k) {
+      const double s = (double)ga[k] / std::sqrt((double)va[k] + 1e-3);
+      sc[k] = (float)s;
+      sh[k] = (float)((double)be[k] - (double)mu[k] * s);
+    }
+  };
+  std::vector<float> sc, sh;
+  size_t o_b0 = push(W(0, "layer/layer/bias")); bn_fold(1, 128, sc, sh); size_t o_sc0 = push(sc), o_sh0 = push(sh);
+  size_t o_b2 = push(W(2, "layer/layer/bias")); bn_fold(3, F, sc, sh); size_t o_sc2 = push(sc), o_sh2 = push(sh);
+  std::vector<float> bl(4 * F);
+  {
+    const auto& b = W(4, "cell/bias");
+    for (int n = 0; n < 4 * F; ++n) {
+      const int ntile = n / 256, gate = (n % 256) / 64, cc = n % 64;
+      bl[n] = b[gate * F + ntile * 64 + cc];
+    }
+  }
+  size_t o_bl = push(bl);
+  size_t o_b5 = push(W(5, "layer/layer/bias")); bn_fold(6, F / 2, sc, sh); size_t o_sc5 = push(sc), o_sh5 = push(sh);
+  {
+    const auto& b = W(7, "layer/layer/bias");
+    bn_fold(8, F / 4, sc, sh);
+    std::vector<float> b4, sc4, sh4;
+    for (int grp = 0; grp < 4; ++grp) {
+      b4.insert(b4.end(), b.begin(), b.end()); sc4.insert(sc4.end(), sc.begin(), sc.end()); sh4.insert(sh4.end(), sh.begin(), sh.end());
+    }
+    size_t o_b7 = push(b4), o_sc7 = push(sc4), o_sh7 = push(sh4);
+    size_t o_b9 = push(W(9, "layer/bias")); bn_fold(10, F / 8, sc, sh); size_t o_sc9 = push(sc), o_sh9 = push(sh);
+    size_t o_w11 = push(W(11, "layer/kernel")), o_b11 = push(W(11, "layer/bias"));
+    if (g->fparams) cudaFree(g->fparams);
+    g->fparams = nullptr;
+    CK(cudaMalloc(&g->fparams, fp.size() * sizeof(float)));
+    CK(cudaMemcpy(g->fparams, fp.data(), fp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    float* f = g->fparams;
+    g->bias0 = f + o_b0; g->sc0 = f + o_sc0; g->sh0 = f + o_sh0;
+    g->bias2 = f + o_b2; g->sc2 = f + o_sc2; g->sh2 = f + o_sh2;
+    g->biasL = f + o_bl;
+    g->bias5 = f + o_b5; g->sc5 = f + o_sc5; g->sh5 = f + o_sh5;
+    g->bias7 = f + o_b7; g->sc7 = f + o_sc7; g->sh7 = f + o_sh7;
+    g->bias9 = f + o_b9; g->sc9 = f + o_sc9; g->sh9 = f + o_sh9;
+    g->w11 = f + o_w11; g->b11 = f + o_b11;
+  }
+  (void)C;
+  g->finalized = true;
+  g->B = 0;  // any previous plan referenced old buffers
+  return 0;
+}
+
+// ------------------------------------------------------------- workspace
+struct WsLayout {
+  size_t xpad, res2p, res4, hseq, cstate, g5, g7, up, g9, total;
+};
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
+  const size_t N = (size_t)B * T, S = g->S, S2 = S / 2, S4 = S / 4, F = g->F;
+  WsLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return r; };
+  L.xpad = take(N * (S + 6) * (S + 6) * g->CP * 2);
+  L.res2p = take(N * (S2 + 2) * (S2 + 2) * 128 * 2);
+  L.res4 = take(N * S4 * S4 * F * 2);
+  L.hseq = take(N * S4 * S4 * F * 2);
+  L.cstate = take((size_t)B * S4 * S4 * F * 4);
+  L.g5 = take(N * S4 * S4 * (F / 2) * 2);
+  L.g7 = take(N * S2 * S2 * (F / 4) * 2);
+  L.up = take(N * S * S * (F / 4 + 128) * 2);
+  L.g9 = take(N * S * S * (F / 8) * 2);
+  L.total = o;
+  return L;
+}
+
+extern "C" int wdg_generator_workspace_bytes(const wdg_generator* g, int B, int T, size_t* bytes) {
+  if (!g || !bytes || B <= 0 || T <= 0) return fail("bad argument");
+  *bytes = ws_layout(g, B, T).total;
+  return 0;
+}
+
+extern "C" int wdg_generator_io_bytes(const wdg_generator* g, int B, int T, size_t* bytes) {
+  if (!g || !bytes || B <= 0 || T <= 0) return fail("bad argument");
+  const size_t px = (size_t)B * T * g->S * g->S;
+  *bytes = align_up(px * g->cin * 4, 256) + align_up(px * g->cnoise * 4, 256) + align_up(px * g->cout * 4, 256);
+  return 0;
+}
+
+static void set_tiles(ConvParams& p, int H, int W, int N, int tw, int th, int tn, int n_tiles_N, int n_coord) {
+  p.H = H; p.W = W; p.N = N;
+  p.tile_w = tw; p.tile_h = th; p.tile_n = tn;
+  p.tiles_x = (W + tw - 1) / tw; p.tiles_y = (H + th - 1) / th; p.tiles_n = (N + tn - 1) / tn;
+  p.n_tiles_N = n_tiles_N;
+  p.n_coord = n_coord;
+}
+static void affine_epi(EpiParams& e, const float* bias, const float* sc, const float* sh, void* out, long long sn,
+                       long long sy, long long sx, int c0, int lrelu) {
+  std::memset(&e, 0, sizeof e);
+  e.bias = bias; e.scale = sc; e.shift = sh; e.out = out;
+  e.out_sn = sn; e.out_sy = sy; e.out_sx = sx; e.out_c0 = c0;
+  e.out_mul = 1; e.group_cols = 1 << 30; e.lrelu = lrelu; e.out_f32 = 0;
+}
+
+extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspace_dev, size_t bytes, void* stream_) {
+  if (!g || !workspace_dev || B <= 0 || T <= 0) return fail("bad argument");
+  if (!g->finalized) return fail("wdg_generator_finalize must be called before bind");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const WsLayout L = ws_layout(g, B, T);
+  if (bytes < L.total) return fail("workspace too small");
+  if ((uintptr_t)workspace_dev % 1024) return fail("workspace must be 1024-byte aligned");
+  CK(cudaMemsetAsync(workspace_dev, 0, L.total, stream));
+  uint8_t* ws = (uint8_t*)workspace_dev;
+  g->ws = ws;
+  g->xpad = (__nv_bfloat16*)(ws + L.xpad); g->res2p = (__nv_bfloat16*)(ws + L.res2p);
+  g->res4 = (__nv_bfloat16*)(ws + L.res4); g->hseq = (__nv_bfloat16*)(ws + L.hseq);
+  g->cstate = (float*)(ws + L.cstate); g->g5 = (__nv_bfloat16*)(ws + L.g5); g->g7 = (__nv_bfloat16*)(ws + L.g7);
+  g->up = (__nv_bfloat16*)(ws + L.up); g->g9 = (__nv_bfloat16*)(ws + L.g9);
+  const uint64_t N = (uint64_t)B * T, S = g->S, S2 = S / 2, S4 = S / 4, F = g->F, CP = g->CP;
+  const int sms = g->sm_count;
+  auto grid_for = [&](const ConvParams& p) {
+    const int total = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_N;
+    return total < sms ? total : sms;
+  };
+  // dummy map for unused A slots: reuse slot 0
+  // ---------------- L0: 8x8 s2 on xpad [N][S+6][S+6][CP]; dims (window 8*CP, ox S2, oy S2, parity 2, n)
+  {
+    ConvLaunch& c = g->L0;
+    std::memset(&c.p, 0, sizeof c.p);
+    const uint64_t SP = S + 6;
+    uint64_t dims[5] = {8 * CP, S2, SP / 2, 2, N};  // oy + ky/2 reaches SP/2 - 1
+    uint64_t str[4] = {2 * CP, 2 * SP * CP, SP * CP, SP * SP * CP};
+    uint32_t box[5] = {64, 16, 8, 1, 1};
+    if (make_tmap(&c.tmA[0], g->xpad, 5, dims, str, box, 128)) return 1;
+    c.tmA[1] = c.tmA[0]; c.tmA[2] = c.tmA[0];
+    const int chunks = (int)(8 * CP / 64);
+    uint64_t bd[2] = {(uint64_t)8 * chunks * 64, 128};
+    uint64_t bs[1] = {(uint64_t)8 * chunks * 64};
+    uint32_t bb[2] = {64, 128};
+    if (make_tmap(&c.tmB, g->B0, 2, bd, bs, bb, 128)) return 1;
+    set_tiles(c.p, (int)S2, (int)S2, (int)N, 16, 8, 1, 1, 4);
+    c.p.num_kb = 8 * chunks;
+    for (int ky = 0; ky < 8; ++ky)
+      for (int ch = 0; ch < chunks; ++ch) {
+        KBlock& k = c.p.kb[ky * chunks + ch];
+        k.src = 0; k.half = 0; k.o0 = (int16_t)(ch * 64); k.o1 = 0; k.o2 = (int16_t)(ky / 2); k.o3 = (int16_t)(ky % 2);
+      }
+    const long long sy = (long long)(S2 + 2) * 128, sn = (long long)(S2 + 2) * sy;
+    affine_epi(c.p.ep, g->bias0, g->sc0, g->sh0, g->res2p + sy + 128, sn, sy, 128, 0, 1);
+    c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
+  }
+  // ---------------- L2: 4x4 s2 on res2p [N][S2+2][S2+2][128]; dims (window 512, ox S4, oy S4, parity 2, n)
+  {
+    ConvLaunch& c = g->L2;
+    std::memset(&c.p, 0, sizeof c.p);
+    const uint64_t SP = S2 + 2;
+    uint64_t dims[5] = {512, S4, SP / 2, 2, N};  // oy + ky/2 reaches SP/2 - 1
+    uint64_t str[4] = {256, 2 * SP * 128, SP * 128, SP * SP * 128};
+    uint32_t box[5] = {64, 8, 8, 1, 2};
+    if (make_tmap(&c.tmA[0], g->res2p, 5, dims, str, box, 128)) return 1;
+    c.tmA[1] = c.tmA[0]; c.tmA[2] = c.tmA[0];
+    uint64_t bd[2] = {32 * 64, 128};
+    uint64_t bs[1] = {32 * 64};
+    uint32_t bb[2] = {64, 128};
+    if (make_tmap(&c.tmB, g->B2, 2, bd, bs, bb, 128)) return 1;
+    set_tiles(c.p, (int)S4, (int)S4, (int)N, 8, 8, 2, 1, 4);
+    c.p.num_kb = 32;
+    for (int ky = 0; ky < 4; ++ky)
+      for (int ch = 0; ch < 8; ++ch) {
+        KBlock& k = c.p.kb[ky * 8 + ch];
+        k.src = 0; k.half = 0; k.o0 = (int16_t)(ch * 64); k.o1 = 0; k.o2 = (int16_t)(ky / 2); k.o3 = (int16_t)(ky % 2);
+      }
+    affine_epi(c.p.ep, g->bias2, g->sc2, g->sh2, g->res4, (long long)S4 * S4 * F, (long long)S4 * F, F, 0, 1);
+    c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
+  }
+  // ---------------- ConvLSTM steps: A maps over (c, x, y, t, b) of res4 (x_t) and hseq (h_{t-1})
+  {
+    CUtensorMap tmX, tmH, tmB;
+    uint64_t dims[5] = {F, S4, S4, (uint64_t)T, (uint64_t)B};
+    uint64_t str[4] = {F, S4 * F, S4 * S4 * F, (uint64_t)T * S4 * S4 * F};
+    uint32_t box[5] = {64, 8, 8, 1, 2};
+    if (make_tmap(&tmX, g->res4, 5, dims, str, box, 128)) return 1;
+    if (make_tmap(&tmH, g->hseq, 5, dims, str, box, 128)) return 1;
+    uint64_t bd[2] = {36 * 64, 4 * F};
+    uint64_t bs[1] = {36 * 64};
+    uint32_t bb[2] = {64, 256};
+    if (make_tmap(&tmB, g->BL, 2, bd, bs, bb, 128)) return 1;
+    g->LS.assign(T, ConvLaunch());
+    for (int t = 0; t < T; ++t) {
+      ConvLaunch& c = g->LS[t];
+      std::memset(&c.p, 0, sizeof c.p);
+      c.tmA[0] = tmX; c.tmA[1] = tmH; c.tmA[2] = tmX; c.tmB = tmB;
+      set_tiles(c.p, (int)S4, (int)S4, B, 8, 8, 2, (int)(4 * F / 256), 4);
+      c.p.num_kb = t == 0 ? 18 : 36;
+      for (int kb = 0; kb < c.p.num_kb; ++kb) {
+        KBlock& k = c.p.kb[kb];
+        const int kk = kb % 18, tap = kk / 2;
+        k.src = kb < 18 ? 0 : 1; k.half = 0;
+        k.o0 = (int16_t)((kk % 2) * 64); k.o1 = (int16_t)(tap % 3 - 1); k.o2 = (int16_t)(tap / 3 - 1);
+        k.o3 = (int16_t)(kb < 18 ? t : t - 1);
+      }
+      EpiParams& e = c.p.ep;
+      std::memset(&e, 0, sizeof e);
+      e.bias = g->biasL; e.c_state = g->cstate; e.h_out = g->hseq;
+      e.h_sn = (long long)T * S4 * S4 * F; e.h_off = (long long)t * S4 * S4 * F;
+      e.first_step = t == 0; e.F = (int)F;
+      c.bn = 256; c.epi = EPI_LSTM; c.grid = grid_for(c.p);
+    }
+  }
+  // ---------------- L5: 3x3 same 128 -> 64 on hseq (c, x, y, n)
+  {
+    ConvLaunch& c = g->L5;
+    std::memset(&c.p, 0, sizeof c.p);
+    uint64_t dims[5] = {F, S4, S4, N, 1};
+    uint64_t str[4] = {F, S4 * F, S4 * S4 * F, N * S4 * S4 * F};
+    uint32_t box[5] = {64, 8, 8, 2, 1};
+    if (make_tmap(&c.tmA[0], g->hseq, 5, dims, str, box, 128)) return 1;
+    c.tmA[1] = c.tmA[0]; c.tmA[2] = c.tmA[0];
+    uint64_t bd[2] = {18 * 64, F / 2};
+    uint64_t bs[1] = {18 * 64};
+    uint32_t bb[2] = {64, 64};
+    if (make_tmap(&c.tmB, g->B5, 2, bd, bs, bb, 128)) return 1;
+    set_tiles(c.p, (int)S4, (int)S4, (int)N, 8, 8, 2, 1, 3);
+    c.p.num_kb = 18;
+    for (int kb = 0; kb < 18; ++kb) {
+      KBlock& k = c.p.kb[kb];
+      const int tap = kb / 2;
+      k.src = 0; k.half = 0; k.o0 = (int16_t)((kb % 2) * 64); k.o1 = (int16_t)(tap % 3 - 1); k.o2 = (int16_t)(tap / 3 - 1); k.o3 = 0;
+    }
+    affine_epi(c.p.ep, g->bias5, g->sc5, g->sh5, g->g5, (long long)S4 * S4 * (F / 2), (long long)S4 * (F / 2), F / 2, 0, 1);
+    c.bn = 64; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
+  }
+  // ---------------- L7: ConvT 2x2 s2 on concat(g5, res4) -> g7 [N][S2][S2][32] (pixel shuffle)
+  {
+    ConvLaunch& c = g->L7;
+    std::memset(&c.p, 0, sizeof c.p);
+    uint64_t d0[5] = {F / 2, S4, S4, N, 1};
+    uint64_t s0[4] = {F / 2, S4 * (F / 2), S4 * S4 * (F / 2), N * S4 * S4 * (F / 2)};
+    uint64_t d1[5] = {F, S4, S4, N, 1};
+    uint64_t s1[4] = {F, S4 * F, S4 * S4 * F, N * S4 * S4 * F};
+    uint32_t box[5] = {64, 8, 8, 2, 1};
+    if (make_tmap(&c.tmA[0], g->g5, 5, d0, s0, box, 128)) return 1;
+    if (make_tmap(&c.tmA[1], g->res4, 5, d1, s1, box, 128)) return 1;
+    c.tmA[2] = c.tmA[0];
+    uint64_t bd[2] = {3 * 64, 128};
+    uint64_t bs[1] = {3 * 64};
+    uint32_t bb[2] = {64, 128};
+    if (make_tmap(&c.tmB, g->B7, 2, bd, bs, bb, 128)) return 1;
+    set_tiles(c.p, (int)S4, (int)S4, (int)N, 8, 8, 2, 1, 3);
+    c.p.num_kb = 3;
+    for (int kb = 0; kb < 3; ++kb) {
+      KBlock& k = c.p.kb[kb];
+      k.src = kb == 0 ? 0 : 1; k.half = 0; k.o0 = (int16_t)(kb <= 1 ? 0 : 64); k.o1 = 0; k.o2 = 0; k.o3 = 0;
+    }
+    const long long O = F / 4;
+    affine_epi(c.p.ep, g->bias7, g->sc7, g->sh7, g->g7, (long long)S2 * S2 * O, (long long)S2 * O, O, 0, 1);
+    c.p.ep.out_mul = 2; c.p.ep.group_cols = (int)O;
+    c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
+  }
+  // ---------------- L9: 5x5 same on up [N][S][S][160] -> g9 [N][S][S][16]
+  {
+    ConvLaunch& c = g->L9;
+    std::memset(&c.p, 0, sizeof c.p);
+    const uint64_t I = F / 4 + 128, O = F / 8;
+    uint64_t dims[5] = {I, S, S, N, 1};
+    uint64_t str[4] = {I, S * I, S * S * I, N * S * S * I};
+    uint32_t box[5] = {64, 16, 8, 1, 1};
+    if (make_tmap(&c.tmA[0], g->up, 5, dims, str, box, 128)) return 1;
+    c.tmA[1] = c.tmA[0]; c.tmA[2] = c.tmA[0];
+    const int chunks = (int)((I + 63) / 64);
+    uint64_t bd[2] = {(uint64_t)25 * chunks * 64, O};
+    uint64_t bs[1] = {(uint64_t)25 * chunks * 64};
+    uint32_t bb[2] = {64, (uint32_t)O};
+    if (make_tmap(&c.tmB, g->B9, 2, bd, bs, bb, 128)) return 1;
+    set_tiles(c.p, (int)S, (int)S, (int)N, 16, 8, 1, 1, 3);
+    c.p.num_kb = 25 * chunks;
+    if (c.p.num_kb > MAX_KB) return fail("too many K blocks");
+    for (int tap = 0; tap < 25; ++tap)
+      for (int ch = 0; ch < chunks; ++ch) {
+        KBlock& k = c.p.kb[tap * chunks + ch];
+        k.src = 0; k.half = 0; k.o0 = (int16_t)(ch * 64); k.o1 = (int16_t)(tap % 5 - 2); k.o2 = (int16_t)(tap / 5 - 2); k.o3 = 0;
+      }
+    affine_epi(c.p.ep, g->bias9, g->sc9, g->sh9, g->g9, (long long)S * S * O, (long long)S * O, O, 0, 1);
+    c.bn = 16; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
+  }
+  g->B = B; g->T = T;
+  g->launches = 1 + 2 + T + 2 + 1 + 1 + 1;
+  return 0;
+}
+
+// ---------------------------------------------------------------- launch
+template <int BN, int EPI>
+static int launch_conv_t(const ConvLaunch& c, cudaStream_t stream) {
+  auto kern = conv_umma_kernel<BN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::SMEM_BYTES));
+    attr_set = true;
+  }
+  kern<<<c.grid, 192, ConvCfg<BN>::SMEM_BYTES, stream>>>(c.tmA[0], c.tmA[1], c.tmA[2], c.tmB, c.p);
+  CK(cudaGetLastError());
+  return 0;
+}
+static int launch_conv(const ConvLaunch& c, cudaStream_t stream) {
+  if (c.epi == EPI_LSTM) return launch_conv_t<256, EPI_LSTM>(c, stream);
+  switch (c.bn) {
+    case 128: return launch_conv_t<128, EPI_AFFINE>(c, stream);
+    case 64: return launch_conv_t<64, EPI_AFFINE>(c, stream);
+    case 16: return launch_conv_t<16, EPI_AFFINE>(c, stream);
+  }
+  return fail("no kernel instantiated for this BN");
+}
+
+extern "C" int wdg_generator_forward(wdg_generator* g, const float* image_dev, const float* noise_dev, float* out_dev,
+                                     void* stream_) {
+  if (!g || !image_dev || !noise_dev || !out_dev) return fail("null argument");
+  if (g->B == 0) return fail("wdg_generator_bind must be called before forward");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const long long N = (long long)g->B * g->T, S = g->S;
+  const long long npix = N * S * S;
+  pack_input_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(image_dev, noise_dev, g->xpad, npix, (int)S,
+                                                                        g->cin, g->cnoise, g->CP);
+  CK(cudaGetLastError());
+  if (launch_conv(g->L0, stream)) return 1;
+  if (launch_conv(g->L2, stream)) return 1;
+  for (int t = 0; t < g->T; ++t)
+    if (launch_conv(g->LS[t], stream)) return 1;
+  if (launch_conv(g->L5, stream)) return 1;
+  if (launch_conv(g->L7, stream)) return 1;
+  {
+    const int C0 = g->F / 4, C1 = 128;
+    const long long total = npix * ((C0 + C1) / 8);
+    upsample_concat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(g->g7, g->res2p, g->up, total,
+                                                                               (int)(S / 2), (int)(S / 2), C0, C1);
+    CK(cudaGetLastError());
+  }
+  if (launch_conv(g->L9, stream)) return 1;
+  final_conv3x3_kernel<16, 2><<<(unsigned)((npix + 127) / 128), 128, 0, stream>>>(g->g9, g->w11, g->b11, out_dev, npix,
+                                                                                  (int)S);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int wdg_generator_predict_host(wdg_generator* g, const float* image_host, const float* noise_host,
+                                          float* out_host, void* io_dev, void* stream_) {
+  if (!g || !image_host || !noise_host || !out_host || !io_dev) return fail("null argument");
+  if (g->B == 0) return fail("wdg_generator_bind must be called before predict_host");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t px = (size_t)g->B * g->T * g->S * g->S;
+  const size_t b_img = px * g->cin * 4, b_noise = px * g->cnoise * 4, b_out = px * g->cout * 4;
+  uint8_t* io = (uint8_t*)io_dev;
+  float* d_img = (float*)io;
+  float* d_noise = (float*)(io + align_up(b_img, 256));
+  float* d_out = (float*)(io + align_up(b_img, 256) + align_up(b_noise, 256));
+  CK(cudaMemcpyAsync(d_img, image_host, b_img, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(d_noise, noise_host, b_noise, cudaMemcpyHostToDevice, stream));
+  if (wdg_generator_forward(g, d_img, d_noise, d_out, stream_)) return 1;
+  CK(cudaMemcpyAsync(out_host, d_out, b_out, cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+extern "C" int wdg_generator_launches_per_forward(const wdg_generator* g) { return g ? g->launches : 0; }
+
+// --------------------------------------------------------------- debug
+__global__ void bf16_to_f32_strided(const __nv_bfloat16* src, float* dst, long long n_img, int H, int W, int C,
+                                    long long sn, long long sy, long long sx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = n_img * H * W * C;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long long pix = i / C;
+  const int x = (int)(pix % W);
+  const int y = (int)((pix / W) % H);
+  const long long n = pix / ((long long)W * H);
+  dst[i] = __bfloat162float(src[n * sn + y * sy + x * sx + c]);
+}
+
+extern "C" int wdg_generator_debug_read(const wdg_generator* g, int which, float* host_out, int64_t count) {
+  if (!g || g->B == 0 || !host_out) return fail("bad argument");
+  const long long N = (long long)g->B * g->T, S = g->S, S2 = S / 2, S4 = S / 4, F = g->F;
+  const __nv_bfloat16* src;
+  int H, W, C;
+  long long sn, sy, sx;
+  switch (which) {
+    case 0: H = W = (int)S2; C = 128; sx = 128; sy = (S2 + 2) * 128; sn = (S2 + 2) * sy; src = g->res2p + sy + sx; break;
+    case 1: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = g->res4; break;
+    case 2: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = g->hseq; break;
+    case 3: H = W = (int)S4; C = (int)(F / 2); sx = C; sy = S4 * sx; sn = S4 * sy; src = g->g5; break;
+    case 4: H = W = (int)S2; C = (int)(F / 4); sx = C; sy = S2 * sx; sn = S2 * sy; src = g->g7; break;
+    case 5: H = W = (int)S; C = (int)(F / 8); sx = C; sy = S * sx; sn = S * sy; src = g->g9; break;
+    default: return fail("unknown intermediate");
+  }
+  const long long total = N * H * W * C;
+  if (count != total) return fail("count mismatch");
+  float* d = nullptr;
+  CK(cudaMalloc(&d, total * sizeof(float)));
+  bf16_to_f32_strided<<<(unsigned)((total + 255) / 256), 256>>>(src, d, N, H, W, C, sn, sy, sx);
+  cudaError_t e = cudaMemcpy(host_out, d, total * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(std::string("debug_read: ") + cudaGetErrorString(e));
+  return 0;
+}
