@@ -79,6 +79,13 @@ int wdg_generator_predict_host(wdg_generator* g, const float* image_host, const 
 /* Number of kernels one forward() launches for the bound plan (bench.py's gpu_launches). */
 int wdg_generator_launches_per_forward(const wdg_generator* g);
 
+/* Per-stage device timing of forward() with CUDA events recorded on the caller's stream
+ * (bench.py's roofline).  Stages, in launch order: 0 pack_input, 1 conv 8x8 s2, 2 conv 4x4 s2,
+ * 3 ConvLSTM (T launches), 4 conv 3x3, 5 convT 2x2 s2, 6 border lines + border-correction GEMM, 7 fused bilinear x2 + convT 5x5, 8 conv 3x3 out. */
+#define WDG_NUM_STAGES 9
+int wdg_generator_profile(wdg_generator* g, int enable);
+int wdg_generator_stage_ms(wdg_generator* g, float* ms, int n);
+
 /* Debug / parity hooks: copies an intermediate activation of the last forward() to the host as
  * fp32.  which: 0 res_2 (N,S/2,S/2,128)  1 res_4 (N,S/4,S/4,128)  2 lstm h (N,S/4,S/4,128)
  * 3 g5 (N,S/4,S/4,64)  4 g7 (N,S/2,S/2,32)  5 g9 (N,S,S,16), N = B*T. */

@@ -37,6 +37,8 @@ def _declare(lib):
         "wdg_generator_predict_host": [vp, vp, vp, vp, vp, vp],
         "wdg_generator_launches_per_forward": [vp],
         "wdg_generator_debug_read": [vp, i, vp, C.c_int64],
+        "wdg_generator_profile": [vp, i],
+        "wdg_generator_stage_ms": [vp, vp, i],
         "wdg_gather_normalise": [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, vp, vp],
         "wdg_stitch": [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp],
     }

@@ -22,7 +22,7 @@ constexpr int MAX_KB = 80;
 constexpr int TILE_M = 128;
 constexpr int A_STAGE_BYTES = TILE_M * 128;
 
-enum { EPI_AFFINE = 0, EPI_LSTM = 1 };
+enum { EPI_AFFINE = 0, EPI_LSTM = 1, EPI_UPCONV = 2 };
 
 struct KBlock {        // one slice of the GEMM K axis
   int8_t src;          // which A tensor map (0..2)
@@ -42,6 +42,14 @@ struct EpiParams {
   int group_cols;                    // columns per (ky,kx) group when out_mul == 2
   int lrelu;
   int out_f32;
+  void* out2;                        // optional second bf16 destination (same values), own strides
+  long long out2_sn, out2_sy, out2_sx;
+  int out2_c0;
+  // ---- EPI_UPCONV (BN = 64 = 2x2 output phases x 16 channels; GEMM rows are window anchors on the
+  //      flattened zero-padded low-res image, see wdg_generator.cu)
+  int up_pw, up_ph;                  // padded low-res width / height (anchor grid pitch)
+  int up_S;                          // high-res size
+  const float* up_delta;             // fp32 border corrections [n][S][4 edges * 48]
   // ---- EPI_LSTM (BN = 256 = 4 gates x 64 channels per N tile)
   float* c_state;                    // fp32 [n][H][W][F], updated in place
   __nv_bfloat16* h_out;              // bf16, pixel (n,y,x) channel c at n*h_sn + h_off + (y*W+x)*F + c
@@ -57,6 +65,7 @@ struct ConvParams {
   int n_tiles_N;               // number of BN-wide column tiles
   int num_kb;
   int n_coord;                 // TMA coordinate (3 or 4) that carries the image index
+  int ntile_coord;             // TMA coordinate that additionally receives the N-tile index (-1: none)
   EpiParams ep;
   KBlock kb[MAX_KB];
 };
@@ -130,6 +139,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int tn = m_tile / (p.tiles_x * p.tiles_y);
         int base[5] = {0, tx * p.tile_w, ty * p.tile_h, 0, 0};
         base[p.n_coord] = tn * p.tile_n;
+        if (p.ntile_coord >= 0) base[p.ntile_coord] += n_tile;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           const KBlock k = p.kb[kb];
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -233,7 +243,68 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                   pack_bf16x2(v[6], v[7]));
               dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
                                   pack_bf16x2(v[14], v[15]));
+              if (e.out2) {
+                uint4* d2 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out2) + (long long)n * e.out2_sn +
+                                                     (long long)oy * e.out2_sy + (long long)ox * e.out2_sx + e.out2_c0 + oc);
+                d2[0] = dst[0];
+                d2[1] = dst[1];
+              }
             }
+          }
+        }
+      } else if constexpr (EPI == EPI_UPCONV) {
+        // Fused bilinear-x2 + 5x5 transposed conv: row = anchor (r, s) of a 4x4 low-res window, the
+        // 64 columns are the 2x2 high-res pixels (2r+3+py, 2s+3+px) x 16 channels.
+        static_assert(EPI != EPI_UPCONV || BN == 64, "UPCONV epilogue expects 4 phases x 16 channels");
+        const EpiParams& e = p.ep;
+        const long long f = (long long)m_tile * TILE_M + row;      // flattened padded position
+        const int per_img = e.up_pw * e.up_ph;
+        const int img = (int)(f / per_img);
+        const int rem = (int)(f - (long long)img * per_img);
+        const int pr = rem / e.up_pw, ps = rem - pr * e.up_pw;
+        const int S = e.up_S;
+        const bool arow = img < p.N;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t r[16];
+          tmem_ld16(taddr + g * 16, r);
+          tmem_ld_wait();
+          const int Y = 2 * pr - 1 + (g >> 1);   // 2*(pr-2)+3+py
+          const int X = 2 * ps - 1 + (g & 1);
+          if (arow && Y >= 0 && Y < S && X >= 0 && X < S) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+            const float* D = e.up_delta + (long long)img * S * 192;
+            if (Y < 3) {
+              const float* d = D + X * 192 + Y * 16;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += d[i];
+            } else if (Y > S - 4) {
+              const float* d = D + X * 192 + 48 + (S - 1 - Y) * 16;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += d[i];
+            }
+            if (X < 3) {
+              const float* d = D + Y * 192 + 96 + X * 16;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += d[i];
+            } else if (X > S - 4) {
+              const float* d = D + Y * 192 + 144 + (S - 1 - X) * 16;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += d[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a = leaky02(v[i] + __ldg(e.bias + i));
+              v[i] = a * __ldg(e.scale + i) + __ldg(e.shift + i);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) +
+                                                  (((long long)img * S + Y) * S + X) * 16);
+            dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                pack_bf16x2(v[6], v[7]));
+            dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                pack_bf16x2(v[14], v[15]));
           }
         }
       } else {

@@ -29,60 +29,60 @@ __global__ void pack_input_kernel(const float* __restrict__ image, const float* 
   }
 }
 
-// K7: Concatenate([g7, res_2]) + UpSampling2D(2, 'bilinear') (models.py:60-62), half-pixel centres
-// with edge clamp.  One thread per (output pixel, 8-channel group); fp32 blend, bf16 store.
-// g7: [n][h][w][C0] plain; res2: zero-padded [n][h+2][w+2][C1] (interior at +1,+1).
-__global__ void upsample_concat_kernel(const __nv_bfloat16* __restrict__ g7, const __nv_bfloat16* __restrict__ res2,
-                                       __nv_bfloat16* __restrict__ up, long long total, int h, int w, int C0, int C1) {
+// K7 border lines.  The fused upsample + 5x5 transposed convolution (conv_umma EPI_UPCONV) works on the
+// zero-padded low-res concat image `catp` [n][h+4][w+4][C] (interior at +2,+2), i.e. it sees the bilinear
+// interpolation continued with zeros beyond the border.  The reference instead clamps the interpolation at the
+// border and zero-pads the UPSAMPLED image (models.py:62-63).  The difference is confined to high-res rows/cols
+// {-1, 0, 2h-1, 2h}: +-0.25 x the edge row/column upsampled along the edge ("border dipole").
+// This kernel writes those four upsampled edge lines, E[n][edge][P = 2h+8][C], position p = j + 4:
+//   edge 0/1 (top/bottom): clamped x-upsample of low-res row 0 / h-1,       j in [0, 2w)
+//   edge 2/3 (left/right): zero-extended y-upsample of low-res col 0 / w-1, j in [-1, 2h]
+// One thread per (n, edge, p, 8-channel group).
+__global__ void edge_lines_kernel(const __nv_bfloat16* __restrict__ catp, __nv_bfloat16* __restrict__ E,
+                                  long long total, int h, int C) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int C = C0 + C1;
   const int groups = C / 8;
+  const int P = 2 * h + 8;
   const int g = (int)(i % groups);
-  const long long pix = i / groups;
-  const int X = (int)(pix % (2 * w));
-  const int Y = (int)((pix / (2 * w)) % (2 * h));
-  const long long n = pix / ((long long)4 * w * h);
-  // source taps: out[2k] = .25 in[k-1] + .75 in[k]; out[2k+1] = .75 in[k] + .25 in[k+1] (clamped)
-  const int ky = Y >> 1, kx = X >> 1;
-  const int y0 = (Y & 1) ? ky : max(ky - 1, 0);
-  const int y1 = (Y & 1) ? min(ky + 1, h - 1) : ky;
-  const float wy0 = (Y & 1) ? 0.75f : 0.25f;
-  const int x0 = (X & 1) ? kx : max(kx - 1, 0);
-  const int x1 = (X & 1) ? min(kx + 1, w - 1) : kx;
-  const float wx0 = (X & 1) ? 0.75f : 0.25f;
-  const int c = g * 8;
-  const __nv_bfloat16* src;
-  long long sy, sx, base;
-  if (c < C0) {
-    src = g7 + c; sx = C0; sy = (long long)w * C0; base = n * h * sy;
-  } else {
-    src = res2 + (c - C0); sx = C1; sy = (long long)(w + 2) * C1; base = n * (h + 2) * sy + sy + sx;
-  }
+  const int p = (int)((i / groups) % P);
+  const int edge = (int)((i / ((long long)groups * P)) % 4);
+  const long long n = i / ((long long)groups * P * 4);
+  const int j = p - 4;
+  const int PW = h + 4;
+  const __nv_bfloat16* img = catp + n * (long long)PW * PW * C + g * 8;
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  const int ys[2] = {y0, y1};
-  const int xs[2] = {x0, x1};
-  const float wys[2] = {wy0, 1.f - wy0};
-  const float wxs[2] = {wx0, 1.f - wx0};
+  const bool clamped = edge < 2;
+  const bool in_range = clamped ? (j >= 0 && j < 2 * h) : (j >= -1 && j <= 2 * h);
+  if (in_range) {
+    const int odd = j & 1;
+    const int k0 = (j - odd) / 2;                 // floor(j / 2)
+    int ka = odd ? k0 : k0 - 1, kb = odd ? k0 + 1 : k0;
+    const float wa = odd ? 0.75f : 0.25f;
+    if (clamped) { ka = max(ka, 0); kb = min(kb, h - 1); }
+    const int fixed = (edge == 0 || edge == 2) ? 0 : h - 1;
+    const int ks[2] = {ka, kb};
+    const float ws[2] = {wa, 1.f - wa};
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const uint4 v = *reinterpret_cast<const uint4*>(src + base + ys[a] * sy + xs[b] * sx);
+    for (int t = 0; t < 2; ++t) {
+      // padded coordinates (+2): positions outside [0, h) read the physical zero ring
+      const int y = (edge < 2) ? fixed : ks[t];
+      const int x = (edge < 2) ? ks[t] : fixed;
+      const uint4 v = *reinterpret_cast<const uint4*>(img + ((long long)(y + 2) * PW + (x + 2)) * C);
       const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&v);
-      const float wgt = wys[a] * wxs[b];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 f = __bfloat1622float2(hv[k]);
-        acc[2 * k] += wgt * f.x;
-        acc[2 * k + 1] += wgt * f.y;
+        acc[2 * k] += ws[t] * f.x;
+        acc[2 * k + 1] += ws[t] * f.y;
       }
     }
-  uint4 o = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                       pack_bf16x2(acc[6], acc[7]));
-  *reinterpret_cast<uint4*>(up + pix * C + c) = o;
+  }
+  *reinterpret_cast<uint4*>(E + ((n * 4 + edge) * P + p) * C + g * 8) =
+      make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                 pack_bf16x2(acc[6], acc[7]));
 }
 
 // K9: Conv2D(out_channels, 3x3, 'same', linear) on the post-BatchNorm 16-channel tensor

@@ -114,18 +114,22 @@ struct wdg_generator {
   std::map<std::string, bool> set_;
   bool finalized = false;
   // packed device weights
-  __nv_bfloat16 *B0 = nullptr, *B2 = nullptr, *BL = nullptr, *B5 = nullptr, *B7 = nullptr, *B9 = nullptr;
+  __nv_bfloat16 *B0 = nullptr, *B2 = nullptr, *BL = nullptr, *B5 = nullptr, *B7 = nullptr, *B9 = nullptr, *BE = nullptr;
   float* fparams = nullptr;  // all fp32 per-column vectors, see offsets
   float *bias0, *sc0, *sh0, *bias2, *sc2, *sh2, *biasL, *bias5, *sc5, *sh5, *bias7, *sc7, *sh7, *bias9, *sc9, *sh9,
       *w11, *b11;
   // plan
   int B = 0, T = 0;
   uint8_t* ws = nullptr;
-  __nv_bfloat16 *xpad, *res2p, *res4, *hseq, *g5, *g7, *up, *g9;
-  float* cstate;
-  ConvLaunch L0, L2, L5, L7, L9;
+  __nv_bfloat16 *xpad, *res2p, *res4, *hseq, *g5, *catp, *edgeE, *g9;
+  float *cstate, *deltaD;
+  float *zero48, *one48;
+  ConvLaunch L0, L2, L5, L7, LE, L9;
   std::vector<ConvLaunch> LS;  // one per timestep
   int launches = 0;
+  // optional per-stage CUDA-event timing (bench.py roofline)
+  bool profiling = false;
+  cudaEvent_t ev[WDG_NUM_STAGES + 1] = {};
 };
 
 static const char* LWF = "layer_with_weights-%d/%s";
@@ -177,7 +181,8 @@ extern "C" int wdg_generator_create(wdg_generator** out, int image_size, int in_
 
 extern "C" void wdg_generator_destroy(wdg_generator* g) {
   if (!g) return;
-  cudaFree(g->B0); cudaFree(g->B2); cudaFree(g->BL); cudaFree(g->B5); cudaFree(g->B7); cudaFree(g->B9);
+  for (auto& e : g->ev) if (e) cudaEventDestroy(e);
+  cudaFree(g->B0); cudaFree(g->B2); cudaFree(g->BL); cudaFree(g->B5); cudaFree(g->B7); cudaFree(g->B9); cudaFree(g->BE);
   cudaFree(g->fparams);
   delete g;
 }
@@ -285,14 +290,45 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
           return w[((size_t)grp * O + o) * I + i];
         })) return 1;
   }
-  // ---- L9: ConvT 5x5 same s1 == SAME correlation with flipped kernel, channels swapped.
+  // ---- L9: UpSampling2D(2, bilinear) + ConvT 5x5 same s1, fused.  The ConvT is a SAME correlation with
+  //      Wf[ty][tx][c][o] = W[4-ty][4-tx][o][c].  GEMM row = anchor (r, s) of a 4x4 low-res window (rows r..r+3),
+  //      column = (py, px, o): high-res pixel (2r+3+py, 2s+3+px).  High-res row 2r+1+m (m = py+ty) is the bilinear
+  //      blend U[m][dy] of window rows, so  comp[py,px,o][dy,dx,c] = sum_{ty,tx} U[py+ty][dy] U[px+tx][dx] Wf[ty][tx][c][o].
   {
     const auto& w = W(9, "layer/kernel");  // [5][5][16][160]
     const int O = F / 8, I = F / 4 + 128;
-    const int chunks = (I + 63) / 64;
-    if (upload_B(&g->B9, O, 25 * chunks, [&](int n, int kb, int j) {
-          const int tap = kb / chunks, ty = tap / 5, tx = tap % 5, i = (kb % chunks) * 64 + j;
-          return i < I ? w[(((size_t)(4 - ty) * 5 + (4 - tx)) * O + n) * I + i] : 0.f;
+    if (O != 16 || I != 160) return fail("fused upsample conv expects 160 -> 16 channels");
+    static const double U[6][4] = {{.75, .25, 0, 0}, {.25, .75, 0, 0}, {0, .75, .25, 0},
+                                   {0, .25, .75, 0}, {0, 0, .75, .25}, {0, 0, .25, .75}};
+    auto Wf = [&](int ty, int tx, int c, int o) { return (double)w[(((size_t)(4 - ty) * 5 + (4 - tx)) * O + o) * I + c]; };
+    if (upload_B(&g->B9, 4 * O, 16 * 3, [&](int n, int kb, int j) {
+          const int py = n / (2 * O), px = (n / O) % 2, o = n % O;
+          const int tap = kb / 3, chunk = kb % 3, dy = tap / 4, dx = tap % 4;
+          if (chunk == 2 && j >= 32) return 0.f;
+          const int c = chunk * 64 + j;
+          double acc = 0;
+          for (int ty = 0; ty < 5; ++ty) {
+            const double uy = U[py + ty][dy];
+            if (uy == 0) continue;
+            for (int tx = 0; tx < 5; ++tx) acc += uy * U[px + tx][dx] * Wf(ty, tx, c, o);
+          }
+          return (float)acc;
+        })) return 1;
+    // Border "dipole" corrections (see stencil_kernels.cuh: edge_lines_kernel): 1-D 5-tap convolutions of the four
+    // upsampled edge lines; row = edge*48 + e*16 + o, where e is the distance of the output row/col from that edge.
+    if (upload_B(&g->BE, 4 * 48, 5 * 3, [&](int n, int kb, int j) {
+          const int edge = n / 48, e = (n % 48) / 16, o = n % 16;
+          const int t = kb / 3, chunk = kb % 3;
+          if (chunk == 2 && j >= 32) return 0.f;
+          const int c = chunk * 64 + j;
+          double v = 0;
+          switch (edge) {
+            case 0: v = Wf(2 - e, t, c, o) - (e <= 1 ? Wf(1 - e, t, c, o) : 0.0); break;
+            case 1: v = Wf(2 + e, t, c, o) - (e <= 1 ? Wf(3 + e, t, c, o) : 0.0); break;
+            case 2: v = Wf(t, 2 - e, c, o) - (e <= 1 ? Wf(t, 1 - e, c, o) : 0.0); break;
+            default: v = Wf(t, 2 + e, c, o) - (e <= 1 ? Wf(t, 3 + e, c, o) : 0.0); break;
+          }
+          return (float)(0.25 * v);
         })) return 1;
   }
   // ---- fp32 per-column vectors
@@ -330,6 +366,7 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
     size_t o_b7 = push(b4), o_sc7 = push(sc4), o_sh7 = push(sh4);
     size_t o_b9 = push(W(9, "layer/bias")); bn_fold(10, F / 8, sc, sh); size_t o_sc9 = push(sc), o_sh9 = push(sh);
     size_t o_w11 = push(W(11, "layer/kernel")), o_b11 = push(W(11, "layer/bias"));
+    size_t o_zero = push(std::vector<float>(192, 0.f)), o_one = push(std::vector<float>(192, 1.f));
     if (g->fparams) cudaFree(g->fparams);
     g->fparams = nullptr;
     CK(cudaMalloc(&g->fparams, fp.size() * sizeof(float)));
@@ -342,6 +379,7 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
     g->bias7 = f + o_b7; g->sc7 = f + o_sc7; g->sh7 = f + o_sh7;
     g->bias9 = f + o_b9; g->sc9 = f + o_sc9; g->sh9 = f + o_sh9;
     g->w11 = f + o_w11; g->b11 = f + o_b11;
+    g->zero48 = f + o_zero; g->one48 = f + o_one;
   }
   (void)C;
   g->finalized = true;
@@ -351,7 +389,7 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
 
 // ------------------------------------------------------------- workspace
 struct WsLayout {
-  size_t xpad, res2p, res4, hseq, cstate, g5, g7, up, g9, total;
+  size_t xpad, res2p, res4, hseq, cstate, g5, catp, edgeE, deltaD, g9, total;
 };
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
@@ -365,8 +403,9 @@ static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
   L.hseq = take(N * S4 * S4 * F * 2);
   L.cstate = take((size_t)B * S4 * S4 * F * 4);
   L.g5 = take(N * S4 * S4 * (F / 2) * 2);
-  L.g7 = take(N * S2 * S2 * (F / 4) * 2);
-  L.up = take(N * S * S * (F / 4 + 128) * 2);
+  L.catp = take(N * (S2 + 4) * (S2 + 4) * (F / 4 + 128) * 2 + 4096);
+  L.edgeE = take(N * 4 * (S + 8) * (F / 4 + 128) * 2);
+  L.deltaD = take(N * S * 192 * 4);
   L.g9 = take(N * S * S * (F / 8) * 2);
   L.total = o;
   return L;
@@ -391,6 +430,7 @@ static void set_tiles(ConvParams& p, int H, int W, int N, int tw, int th, int tn
   p.tiles_x = (W + tw - 1) / tw; p.tiles_y = (H + th - 1) / th; p.tiles_n = (N + tn - 1) / tn;
   p.n_tiles_N = n_tiles_N;
   p.n_coord = n_coord;
+  p.ntile_coord = -1;
 }
 static void affine_epi(EpiParams& e, const float* bias, const float* sc, const float* sh, void* out, long long sn,
                        long long sy, long long sx, int c0, int lrelu) {
@@ -412,8 +452,8 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
   g->ws = ws;
   g->xpad = (__nv_bfloat16*)(ws + L.xpad); g->res2p = (__nv_bfloat16*)(ws + L.res2p);
   g->res4 = (__nv_bfloat16*)(ws + L.res4); g->hseq = (__nv_bfloat16*)(ws + L.hseq);
-  g->cstate = (float*)(ws + L.cstate); g->g5 = (__nv_bfloat16*)(ws + L.g5); g->g7 = (__nv_bfloat16*)(ws + L.g7);
-  g->up = (__nv_bfloat16*)(ws + L.up); g->g9 = (__nv_bfloat16*)(ws + L.g9);
+  g->cstate = (float*)(ws + L.cstate); g->g5 = (__nv_bfloat16*)(ws + L.g5); g->catp = (__nv_bfloat16*)(ws + L.catp);
+  g->edgeE = (__nv_bfloat16*)(ws + L.edgeE); g->deltaD = (float*)(ws + L.deltaD); g->g9 = (__nv_bfloat16*)(ws + L.g9);
   const uint64_t N = (uint64_t)B * T, S = g->S, S2 = S / 2, S4 = S / 4, F = g->F, CP = g->CP;
   const int sms = g->sm_count;
   auto grid_for = [&](const ConvParams& p) {
@@ -445,6 +485,11 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
       }
     const long long sy = (long long)(S2 + 2) * 128, sn = (long long)(S2 + 2) * sy;
     affine_epi(c.p.ep, g->bias0, g->sc0, g->sh0, g->res2p + sy + 128, sn, sy, 128, 0, 1);
+    {  // res_2 also goes to channels 32.. of the zero-padded concat image read by the fused upsample conv
+      const long long CI = F / 4 + 128, PW = S2 + 4;
+      c.p.ep.out2 = g->catp + (2 * PW + 2) * CI;
+      c.p.ep.out2_sn = PW * PW * CI; c.p.ep.out2_sy = PW * CI; c.p.ep.out2_sx = CI; c.p.ep.out2_c0 = (int)(F / 4);
+    }
     c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
   }
   // ---------------- L2: 4x4 s2 on res2p [N][S2+2][S2+2][128]; dims (window 512, ox S4, oy S4, parity 2, n)
@@ -550,39 +595,72 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
       KBlock& k = c.p.kb[kb];
       k.src = kb == 0 ? 0 : 1; k.half = 0; k.o0 = (int16_t)(kb <= 1 ? 0 : 64); k.o1 = 0; k.o2 = 0; k.o3 = 0;
     }
-    const long long O = F / 4;
-    affine_epi(c.p.ep, g->bias7, g->sc7, g->sh7, g->g7, (long long)S2 * S2 * O, (long long)S2 * O, O, 0, 1);
+    const long long O = F / 4, CI = F / 4 + 128, PW = S2 + 4;
+    affine_epi(c.p.ep, g->bias7, g->sc7, g->sh7, g->catp + (2 * PW + 2) * CI, PW * PW * CI, PW * CI, CI, 0, 1);
     c.p.ep.out_mul = 2; c.p.ep.group_cols = (int)O;
     c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
   }
-  // ---------------- L9: 5x5 same on up [N][S][S][160] -> g9 [N][S][S][16]
+  // ---------------- LE: border corrections, 1-D 5-tap conv over the 4 edge lines E[N][4][S+8][160] -> D[N][S][4*48] fp32
+  {
+    ConvLaunch& c = g->LE;
+    std::memset(&c.p, 0, sizeof c.p);
+    const uint64_t I = F / 4 + 128, P = S + 8;
+    uint64_t dims[5] = {I, P, 4, N, 1};
+    uint64_t str[4] = {I, P * I, 4 * P * I, N * 4 * P * I};
+    uint32_t box[5] = {64, 16, 1, 8, 1};
+    uint32_t boxh[5] = {32, 16, 1, 8, 1};
+    if (make_tmap(&c.tmA[0], g->edgeE, 5, dims, str, box, 128)) return 1;
+    if (make_tmap(&c.tmA[1], g->edgeE, 5, dims, str, boxh, 64)) return 1;
+    c.tmA[2] = c.tmA[0];
+    uint64_t bd[2] = {15 * 64, 192};
+    uint64_t bs[1] = {15 * 64};
+    uint32_t bb[2] = {64, 48};
+    if (make_tmap(&c.tmB, g->BE, 2, bd, bs, bb, 128)) return 1;
+    set_tiles(c.p, 1, (int)S, (int)N, 16, 1, 8, 4, 3);
+    c.p.ntile_coord = 2;
+    c.p.num_kb = 15;
+    for (int t = 0; t < 5; ++t)
+      for (int ch = 0; ch < 3; ++ch) {
+        KBlock& k = c.p.kb[t * 3 + ch];
+        k.src = ch == 2 ? 1 : 0; k.half = ch == 2; k.o0 = (int16_t)(ch * 64); k.o1 = (int16_t)(t + 2); k.o2 = 0; k.o3 = 0;
+      }
+    affine_epi(c.p.ep, g->zero48, g->one48, g->zero48, g->deltaD, (long long)S * 192, 0, 192, 0, 0);
+    c.p.ep.out_f32 = 1;
+    c.bn = 48; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
+  }
+  // ---------------- L9: fused bilinear x2 + ConvT 5x5 on the flattened zero-padded concat image catp
   {
     ConvLaunch& c = g->L9;
     std::memset(&c.p, 0, sizeof c.p);
-    const uint64_t I = F / 4 + 128, O = F / 8;
-    uint64_t dims[5] = {I, S, S, N, 1};
-    uint64_t str[4] = {I, S * I, S * S * I, N * S * S * I};
-    uint32_t box[5] = {64, 16, 8, 1, 1};
-    if (make_tmap(&c.tmA[0], g->up, 5, dims, str, box, 128)) return 1;
-    c.tmA[1] = c.tmA[0]; c.tmA[2] = c.tmA[0];
-    const int chunks = (int)((I + 63) / 64);
-    uint64_t bd[2] = {(uint64_t)25 * chunks * 64, O};
-    uint64_t bs[1] = {(uint64_t)25 * chunks * 64};
-    uint32_t bb[2] = {64, (uint32_t)O};
+    const uint64_t I = F / 4 + 128, PW = S2 + 4, flat = N * PW * PW;
+    uint64_t dims[5] = {I, flat, 1, 1, 1};
+    uint64_t str[4] = {I, flat * I, flat * I, flat * I};
+    uint32_t box[5] = {64, 128, 1, 1, 1};
+    uint32_t boxh[5] = {32, 128, 1, 1, 1};
+    if (make_tmap(&c.tmA[0], g->catp, 5, dims, str, box, 128)) return 1;
+    if (make_tmap(&c.tmA[1], g->catp, 5, dims, str, boxh, 64)) return 1;
+    c.tmA[2] = c.tmA[0];
+    uint64_t bd[2] = {48 * 64, 64};
+    uint64_t bs[1] = {48 * 64};
+    uint32_t bb[2] = {64, 64};
     if (make_tmap(&c.tmB, g->B9, 2, bd, bs, bb, 128)) return 1;
-    set_tiles(c.p, (int)S, (int)S, (int)N, 16, 8, 1, 1, 3);
-    c.p.num_kb = 25 * chunks;
-    if (c.p.num_kb > MAX_KB) return fail("too many K blocks");
-    for (int tap = 0; tap < 25; ++tap)
-      for (int ch = 0; ch < chunks; ++ch) {
-        KBlock& k = c.p.kb[tap * chunks + ch];
-        k.src = 0; k.half = 0; k.o0 = (int16_t)(ch * 64); k.o1 = (int16_t)(tap % 5 - 2); k.o2 = (int16_t)(tap / 5 - 2); k.o3 = 0;
+    set_tiles(c.p, 1, (int)flat, 1, 128, 1, 1, 1, 3);
+    c.p.N = (int)N;  // images, for the epilogue's row decode
+    c.p.num_kb = 48;
+    for (int tap = 0; tap < 16; ++tap)
+      for (int ch = 0; ch < 3; ++ch) {
+        KBlock& k = c.p.kb[tap * 3 + ch];
+        k.src = ch == 2 ? 1 : 0; k.half = ch == 2; k.o0 = (int16_t)(ch * 64);
+        k.o1 = (int16_t)((tap / 4) * PW + (tap % 4)); k.o2 = 0; k.o3 = 0;
       }
-    affine_epi(c.p.ep, g->bias9, g->sc9, g->sh9, g->g9, (long long)S * S * O, (long long)S * O, O, 0, 1);
-    c.bn = 16; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
+    EpiParams& e = c.p.ep;
+    std::memset(&e, 0, sizeof e);
+    e.bias = g->bias9; e.scale = g->sc9; e.shift = g->sh9; e.out = g->g9;
+    e.up_pw = (int)PW; e.up_ph = (int)PW; e.up_S = (int)S; e.up_delta = g->deltaD;
+    c.bn = 64; c.epi = EPI_UPCONV; c.grid = grid_for(c.p);
   }
   g->B = B; g->T = T;
-  g->launches = 1 + 2 + T + 2 + 1 + 1 + 1;
+  g->launches = 1 + 2 + T + 2 + 2 + 1 + 1;
   return 0;
 }
 
@@ -601,10 +679,11 @@ static int launch_conv_t(const ConvLaunch& c, cudaStream_t stream) {
 }
 static int launch_conv(const ConvLaunch& c, cudaStream_t stream) {
   if (c.epi == EPI_LSTM) return launch_conv_t<256, EPI_LSTM>(c, stream);
+  if (c.epi == EPI_UPCONV) return launch_conv_t<64, EPI_UPCONV>(c, stream);
   switch (c.bn) {
     case 128: return launch_conv_t<128, EPI_AFFINE>(c, stream);
     case 64: return launch_conv_t<64, EPI_AFFINE>(c, stream);
-    case 16: return launch_conv_t<16, EPI_AFFINE>(c, stream);
+    case 48: return launch_conv_t<48, EPI_AFFINE>(c, stream);
   }
   return fail("no kernel instantiated for this BN");
 }
@@ -616,26 +695,55 @@ extern "C" int wdg_generator_forward(wdg_generator* g, const float* image_dev, c
   cudaStream_t stream = (cudaStream_t)stream_;
   const long long N = (long long)g->B * g->T, S = g->S;
   const long long npix = N * S * S;
+  int stage_i = 0;
+  auto mark = [&]() { if (g->profiling) cudaEventRecord(g->ev[stage_i++], stream); };
+  mark();
   pack_input_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(image_dev, noise_dev, g->xpad, npix, (int)S,
                                                                         g->cin, g->cnoise, g->CP);
   CK(cudaGetLastError());
+  mark();
   if (launch_conv(g->L0, stream)) return 1;
+  mark();
   if (launch_conv(g->L2, stream)) return 1;
+  mark();
   for (int t = 0; t < g->T; ++t)
     if (launch_conv(g->LS[t], stream)) return 1;
+  mark();
   if (launch_conv(g->L5, stream)) return 1;
+  mark();
   if (launch_conv(g->L7, stream)) return 1;
+  mark();
   {
-    const int C0 = g->F / 4, C1 = 128;
-    const long long total = npix * ((C0 + C1) / 8);
-    upsample_concat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(g->g7, g->res2p, g->up, total,
-                                                                               (int)(S / 2), (int)(S / 2), C0, C1);
+    const int CI = g->F / 4 + 128;
+    const long long total = N * 4 * (S + 8) * (CI / 8);
+    edge_lines_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(g->catp, g->edgeE, total, (int)(S / 2), CI);
     CK(cudaGetLastError());
+    if (launch_conv(g->LE, stream)) return 1;
   }
+  mark();
   if (launch_conv(g->L9, stream)) return 1;
+  mark();
   final_conv3x3_kernel<16, 2><<<(unsigned)((npix + 127) / 128), 128, 0, stream>>>(g->g9, g->w11, g->b11, out_dev, npix,
                                                                                   (int)S);
   CK(cudaGetLastError());
+  mark();
+  return 0;
+}
+
+extern "C" int wdg_generator_profile(wdg_generator* g, int enable) {
+  if (!g) return fail("null handle");
+  if (enable)
+    for (auto& e : g->ev)
+      if (!e) CK(cudaEventCreate(&e));
+  g->profiling = enable != 0;
+  return 0;
+}
+
+extern "C" int wdg_generator_stage_ms(wdg_generator* g, float* ms, int n) {
+  if (!g || !ms || n != WDG_NUM_STAGES) return fail("bad argument");
+  if (!g->profiling) return fail("profiling is off");
+  CK(cudaEventSynchronize(g->ev[WDG_NUM_STAGES]));
+  for (int i = 0; i < WDG_NUM_STAGES; ++i) CK(cudaEventElapsedTime(&ms[i], g->ev[i], g->ev[i + 1]));
   return 0;
 }
 
@@ -685,7 +793,7 @@ extern "C" int wdg_generator_debug_read(const wdg_generator* g, int which, float
     case 1: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = g->res4; break;
     case 2: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = g->hseq; break;
     case 3: H = W = (int)S4; C = (int)(F / 2); sx = C; sy = S4 * sx; sn = S4 * sy; src = g->g5; break;
-    case 4: H = W = (int)S2; C = (int)(F / 4); sx = C; sy = S2 * sx; sn = S2 * sy; src = g->g7; break;
+    case 4: H = W = (int)S2; C = (int)(F / 4); sx = F / 4 + 128; sy = (S2 + 4) * sx; sn = (S2 + 4) * sy; src = g->catp + 2 * sy + 2 * sx; break;
     case 5: H = W = (int)S; C = (int)(F / 8); sx = C; sy = S * sx; sn = S * sy; src = g->g9; break;
     default: return fail("unknown intermediate");
   }

@@ -251,6 +251,18 @@ class Generator(_NativeModel):
         self.optimizer, self.compiled_loss, self.compiled_metrics = optimizer, loss, metrics
         self.metrics = list(metrics or [])
 
+    STAGES = ("pack_input", "conv8x8s2", "conv4x4s2", "convlstm", "conv3x3", "convT2x2s2", "border_fix",
+              "upconvT5x5", "conv3x3_out")
+
+    def set_profiling(self, enable=True):
+        _lib.check(_lib.lib().wdg_generator_profile(self._h, int(enable)))
+
+    def stage_ms(self):
+        """Device time (ms) of each stage of the last forward, from CUDA events on the launch stream."""
+        ms = (C.c_float * len(self.STAGES))()
+        _lib.check(_lib.lib().wdg_generator_stage_ms(self._h, ms, len(self.STAGES)))
+        return dict(zip(self.STAGES, (float(v) for v in ms)))
+
     def debug_intermediate(self, which):
         """Intermediate activation of the last forward as fp32 numpy (parity tests)."""
         B, T = self._plan
