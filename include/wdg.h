@@ -91,6 +91,27 @@ int wdg_generator_stage_ms(wdg_generator* g, float* ms, int n);
  * 3 g5 (N,S/4,S/4,64)  4 g7 (N,S/2,S/2,32)  5 g9 (N,S,S,16), N = B*T. */
 int wdg_generator_debug_read(const wdg_generator* g, int which, float* host_out, int64_t count);
 
+/* ---- Tiling driver of predict() (api.py:98-151), device side.  All pointers are device memory.
+ * Patch order is the reference's: index = (ix * ny + iy) * ntimeseq + k (api.py:117-124); patch row p maps to
+ * domain row sy+img-1-p, or img-p when sy == 0 (api.py:119). */
+
+/* Scratch needed by wdg_gather_normalise. */
+int wdg_patch_scratch_bytes(int nx, int ny, int ntimeseq, int img, size_t* bytes);
+
+/* Replaces api.py:117-129: slices u10/v10 (T_total,H,W) and elevation_km (H,W) into patches, computes
+ * nanmean / nanstd over axes (0,1,2) of the (N,seq,img,img,3) stack -- i.e. per (patch column, channel), written to
+ * mean_dev/std_dev as fp64 [img][3] -- and writes the normalised fp32 tensor out_dev (N,seq,img,img,3). */
+int wdg_gather_normalise(const float* u10_dev, const float* v10_dev, const float* elev_km_dev, int T_total, int H,
+                         int W, const int* starts_x_dev, int nx, const int* starts_y_dev, int ny, int seq, int img,
+                         double* mean_dev, double* std_dev, float* out_dev, void* scratch_dev, void* stream);
+
+/* Replaces api.py:140-151: crops `crop` pixels off every patch side and averages overlapping predictions.
+ * pred_dev (N,seq,img,img,channels) fp32; rows_dev/cols_dev: sorted covered domain rows/cols;
+ * out_dev (channels, ntimeseq*seq, nrows, ncols) fp32.  Contributions are summed in fp64 in patch order. */
+int wdg_stitch(const float* pred_dev, const int* starts_x_dev, int nx, const int* starts_y_dev, int ny, int ntimeseq,
+               int seq, int img, int crop, int channels, const int* rows_dev, int nrows, const int* cols_dev, int ncols,
+               float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,80 @@
+"""CPU tests of the host-side mirror of api.py: regridding, template, tiling logic, error behaviour."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from wind_downscaling_gan_b200 import api, tiling
+from wind_downscaling_gan_b200.grid import GridDataset, nearest_index
+from tests.synth import synthetic_dem, synthetic_era5
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "patch_grid.json")))
+
+
+def test_constants_match_reference():
+    # api.py:22-28
+    assert (api.SEQUENCE_LENGTH, api.IMG_SIZE, api.BATCH_SIZE, api.NOISE_CHANNELS, api.NOISE_STD, api.NB_INPUTS,
+            api.NB_OUTPUTS) == (24, 96, 8, 20, 0.1, 3, 2)
+    assert api.WEIGHTS_PATH.name == "weights-55.ckpt"
+
+
+@pytest.mark.parametrize("name", [k for k in GOLD if not k.startswith("_")])
+def test_product_tiling_matches_reference_lines(name):
+    g = GOLD[name]
+    sx, sy = tiling.patch_grid(g["pixels_lat"], g["pixels_lon"], g["overlap_factor"], 96)
+    assert sx == g["slices_start_x"] and sy == g["slices_start_y"]
+    lat_cov = set()
+    for p in g["patches"]:
+        lo, hi = sorted((p["lat_first"], p["lat_last"]))
+        lat_cov.update(range(lo + 2, hi - 1))
+    assert sorted(lat_cov) == list(tiling.covered_rows(sy, 96, 2))
+    lon_cov = set()
+    for p in g["patches"]:
+        lon_cov.update(range(p["lon_first"] + 2, p["lon_last"] - 1))
+    assert sorted(lon_cov) == list(tiling.covered_cols(sx, 96, 2))
+
+
+def test_tiling_errors():
+    with pytest.raises(RuntimeError, match="Lon dimension too small"):
+        tiling.patch_grid(300, 96, 0.05, 96)
+    with pytest.raises(ZeroDivisionError):
+        tiling.patch_grid(97, 300, 0.05, 96)
+    with pytest.raises(AssertionError):
+        tiling.patch_grid(300, 300, 1.5, 96)
+
+
+def test_nearest_index_matches_pandas():
+    pd = pytest.importorskip("pandas")
+    rng = np.random.default_rng(0)
+    for labels in (np.arange(48.0, 50.01, 0.25), np.arange(50.0, 47.99, -0.25), np.array([1.0, 2.0, 4.0, 8.0])):
+        targets = np.concatenate([rng.uniform(labels.min() - 1, labels.max() + 1, 200),
+                                  (labels[:-1] + labels[1:]) / 2, labels])
+        ref = pd.Index(labels).get_indexer(targets, method="nearest")
+        assert np.array_equal(nearest_index(labels, targets), ref)
+
+
+def test_template_and_regrid_cfg1():
+    era = synthetic_era5()
+    dem = synthetic_dem()
+    tpl = api.build_high_res_template_from_era5(era, range_lon=(-1.0, 3.0), range_lat=(48.0, 50.0))
+    assert len(tpl.coords["lon_1"]) == 18 * 17 == 306 and len(tpl.coords["lat_1"]) == 26 * 9 == 234
+    e = api.process_era5(era, tpl)
+    assert e["u10"].shape == (24, 234, 306)
+    # nearest neighbour: template point -> closest ERA5 node
+    j = int(np.argmin(np.abs(era.coords["latitude"] - tpl.coords["lat_1"][100])))
+    i = int(np.argmin(np.abs(era.coords["longitude"] - tpl.coords["lon_1"][200])))
+    assert e["u10"][5, 100, 200] == era["u10"][5, j, i]
+    t = api.process_topo(dem, tpl)
+    assert t["elevation"].shape == (234, 306)
+    jj = int(np.argmin(np.abs(dem.coords["y"] - tpl.coords["lat_1"][7])))
+    ii = int(np.argmin(np.abs(dem.coords["x"] - tpl.coords["lon_1"][9])))
+    assert t["elevation"][7, 9] == dem["elevation"][0, jj, ii]
+
+
+def test_grid_dataset_npz_roundtrip(tmp_path):
+    era = synthetic_era5(hours=2)
+    era.to_npz(tmp_path / "a.npz")
+    back = GridDataset.from_npz(tmp_path / "a.npz")
+    assert np.array_equal(back["u10"], era["u10"]) and back.var_dims("v10") == ("time", "latitude", "longitude")
+    assert np.array_equal(back.coords["time"], era.coords["time"])

@@ -39,8 +39,9 @@ def _declare(lib):
         "wdg_generator_debug_read": [vp, i, vp, C.c_int64],
         "wdg_generator_profile": [vp, i],
         "wdg_generator_stage_ms": [vp, vp, i],
-        "wdg_gather_normalise": [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, vp, vp],
-        "wdg_stitch": [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp],
+        "wdg_patch_scratch_bytes": [i, i, i, i, C.POINTER(sz)],
+        "wdg_gather_normalise": [vp, vp, vp, i, i, i, vp, i, vp, i, i, i, vp, vp, vp, vp, vp],
+        "wdg_stitch": [vp, vp, i, vp, i, i, i, i, i, i, vp, i, vp, i, vp, vp],
     }
     for name, args in sigs.items():
         if not hasattr(lib, name):

@@ -28,6 +28,8 @@ static int fail(const std::string& m) {
     if (_e != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(_e));        \
   } while (0)
 
+int wdg_set_error(const std::string& m) { return fail(m); }  // shared with wdg_patches.cu
+
 extern "C" const char* wdg_last_error(void) { return g_err.c_str(); }
 
 extern "C" int wdg_device_info(int device, int* sm_major, int* sm_minor, int* sm_count) {
