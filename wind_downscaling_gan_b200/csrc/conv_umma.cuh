@@ -126,64 +126,71 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA loops are executed by the WHOLE warp (warp-uniform control flow, so addresses and
+  // descriptors stay in uniform registers); only the TMA / tcgen05 instructions themselves are issued by
+  // one elected lane.
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles_N;
-        const int m_tile = tile / p.n_tiles_N;
-        const int tx = m_tile % p.tiles_x;
-        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-        const int tn = m_tile / (p.tiles_x * p.tiles_y);
-        int base[5] = {0, tx * p.tile_w, ty * p.tile_h, 0, 0};
-        base[p.n_coord] = tn * p.tile_n;
-        if (p.ntile_coord >= 0) base[p.ntile_coord] += n_tile;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          const KBlock k = p.kb[kb];
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles_N;
+      const int m_tile = tile / p.n_tiles_N;
+      const int tx = m_tile % p.tiles_x;
+      const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+      const int tn = m_tile / (p.tiles_x * p.tiles_y);
+      const int n0 = tn * p.tile_n;
+      const int b0 = 0 + (p.ntile_coord == 0 ? n_tile : 0);
+      const int b1 = tx * p.tile_w + (p.ntile_coord == 1 ? n_tile : 0);
+      const int b2 = ty * p.tile_h + (p.ntile_coord == 2 ? n_tile : 0);
+      const int b3 = (p.n_coord == 3 ? n0 : 0) + (p.ntile_coord == 3 ? n_tile : 0);
+      const int b4 = (p.n_coord == 4 ? n0 : 0);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const KBlock k = p.kb[kb];
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           const uint32_t a_bytes = k.half ? (A_STAGE_BYTES / 2) : A_STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], a_bytes + Cfg::B_STAGE_BYTES);
           const CUtensorMap* tm = (k.src == 0) ? &tmA0 : ((k.src == 1) ? &tmA1 : &tmA2);
-          tma_load_5d(smA + stage * A_STAGE_BYTES, tm, &full_bar[stage], base[0] + k.o0, base[1] + k.o1,
-                      base[2] + k.o2, base[3] + k.o3, base[4]);
+          tma_load_5d(smA + stage * A_STAGE_BYTES, tm, &full_bar[stage], b0 + k.o0, b1 + k.o1, b2 + k.o2, b3 + k.o3, b4);
           tma_load_2d(smB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * 64, n_tile * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+    constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int half = p.kb[kb].half;
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          const int half = p.kb[kb].half;
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smA + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(smB + stage * Cfg::B_STAGE_BYTES);
-          const uint32_t a_row = half ? 64u : 128u;
-          const int nk = half ? 2 : 4;
-          for (int k = 0; k < nk; ++k) {
-            const uint64_t da = umma_desc_kmajor(a_addr + k * 32, a_row);
-            const uint64_t db = umma_desc_kmajor(b_addr + k * 32, 128u);
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+        if (elect_one()) {
+          const uint64_t da = umma_desc_kmajor(smem_u32(smA + stage * A_STAGE_BYTES), half ? 64u : 128u);
+          const uint64_t db = umma_desc_kmajor(smem_u32(smB + stage * Cfg::B_STAGE_BYTES), 128u);
+          // advancing K by 16 elements = +32 bytes = +2 in the descriptor's (address >> 4) field
+          umma_bf16(d_tmem, da, db, idesc, kb ? 1u : 0u);
+          umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+          if (!half) {
+            umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
+            umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(&empty_bar[stage]);                        // frees the smem slot once these MMAs have read it
+          if (kb == p.num_kb - 1) umma_commit(&tfull_bar[as]);   // accumulator complete -> epilogue
         }
-        umma_commit(&tfull_bar[as]);       // accumulator complete -> epilogue
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
     // ===================================================== epilogue (warps 2..5)

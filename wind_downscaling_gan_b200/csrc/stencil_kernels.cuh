@@ -39,7 +39,7 @@ __global__ void pack_input_kernel(const float* __restrict__ image, const float* 
 //   edge 2/3 (left/right): zero-extended y-upsample of low-res col 0 / w-1, j in [-1, 2h]
 // One thread per (n, edge, p, 8-channel group).
 __global__ void edge_lines_kernel(const __nv_bfloat16* __restrict__ catp, __nv_bfloat16* __restrict__ E,
-                                  long long total, int h, int C) {
+                                  long long total, int h, int C, int pitch) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int groups = C / 8;
@@ -50,7 +50,7 @@ __global__ void edge_lines_kernel(const __nv_bfloat16* __restrict__ catp, __nv_b
   const long long n = i / ((long long)groups * P * 4);
   const int j = p - 4;
   const int PW = h + 4;
-  const __nv_bfloat16* img = catp + n * (long long)PW * PW * C + g * 8;
+  const __nv_bfloat16* img = catp + n * (long long)PW * PW * pitch + g * 8;
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
@@ -70,7 +70,7 @@ __global__ void edge_lines_kernel(const __nv_bfloat16* __restrict__ catp, __nv_b
       // padded coordinates (+2): positions outside [0, h) read the physical zero ring
       const int y = (edge < 2) ? fixed : ks[t];
       const int x = (edge < 2) ? ks[t] : fixed;
-      const uint4 v = *reinterpret_cast<const uint4*>(img + ((long long)(y + 2) * PW + (x + 2)) * C);
+      const uint4 v = *reinterpret_cast<const uint4*>(img + ((long long)(y + 2) * PW + (x + 2)) * pitch);
       const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {

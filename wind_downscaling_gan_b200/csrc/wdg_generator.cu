@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -12,6 +13,7 @@
 
 #include "../../include/wdg.h"
 #include "conv_umma.cuh"
+#include "upconv_halo.cuh"
 #include "stencil_kernels.cuh"
 
 using namespace wdg;
@@ -116,7 +118,7 @@ struct wdg_generator {
   std::map<std::string, bool> set_;
   bool finalized = false;
   // packed device weights
-  __nv_bfloat16 *B0 = nullptr, *B2 = nullptr, *BL = nullptr, *B5 = nullptr, *B7 = nullptr, *B9 = nullptr, *BE = nullptr;
+  __nv_bfloat16 *B0 = nullptr, *B2 = nullptr, *BL = nullptr, *B5 = nullptr, *B7 = nullptr, *B9 = nullptr, *B9h = nullptr, *BE = nullptr;
   float* fparams = nullptr;  // all fp32 per-column vectors, see offsets
   float *bias0, *sc0, *sh0, *bias2, *sc2, *sh2, *biasL, *bias5, *sc5, *sh5, *bias7, *sc7, *sh7, *bias9, *sc9, *sh9,
       *w11, *b11;
@@ -127,6 +129,10 @@ struct wdg_generator {
   float *cstate, *deltaD;
   float *zero48, *one48;
   ConvLaunch L0, L2, L5, L7, LE, L9;
+  bool use_halo = false;
+  CUtensorMap hA, hB;
+  UpHaloParams hp;
+  int hgrid = 0;
   std::vector<ConvLaunch> LS;  // one per timestep
   int launches = 0;
   // optional per-stage CUDA-event timing (bench.py roofline)
@@ -184,7 +190,7 @@ extern "C" int wdg_generator_create(wdg_generator** out, int image_size, int in_
 extern "C" void wdg_generator_destroy(wdg_generator* g) {
   if (!g) return;
   for (auto& e : g->ev) if (e) cudaEventDestroy(e);
-  cudaFree(g->B0); cudaFree(g->B2); cudaFree(g->BL); cudaFree(g->B5); cudaFree(g->B7); cudaFree(g->B9); cudaFree(g->BE);
+  cudaFree(g->B0); cudaFree(g->B2); cudaFree(g->BL); cudaFree(g->B5); cudaFree(g->B7); cudaFree(g->B9); cudaFree(g->B9h); cudaFree(g->BE);
   cudaFree(g->fparams);
   delete g;
 }
@@ -303,19 +309,22 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
     static const double U[6][4] = {{.75, .25, 0, 0}, {.25, .75, 0, 0}, {0, .75, .25, 0},
                                    {0, .25, .75, 0}, {0, 0, .75, .25}, {0, 0, .25, .75}};
     auto Wf = [&](int ty, int tx, int c, int o) { return (double)w[(((size_t)(4 - ty) * 5 + (4 - tx)) * O + o) * I + c]; };
-    if (upload_B(&g->B9, 4 * O, 16 * 3, [&](int n, int kb, int j) {
-          const int py = n / (2 * O), px = (n / O) % 2, o = n % O;
-          const int tap = kb / 3, chunk = kb % 3, dy = tap / 4, dx = tap % 4;
-          if (chunk == 2 && j >= 32) return 0.f;
-          const int c = chunk * 64 + j;
-          double acc = 0;
-          for (int ty = 0; ty < 5; ++ty) {
-            const double uy = U[py + ty][dy];
-            if (uy == 0) continue;
-            for (int tx = 0; tx < 5; ++tx) acc += uy * U[px + tx][dx] * Wf(ty, tx, c, o);
-          }
-          return (float)acc;
-        })) return 1;
+    auto comp = [&](int n, int tap, int chunk, int j) {
+      const int py = n / (2 * O), px = (n / O) % 2, o = n % O;
+      const int dy = tap / 4, dx = tap % 4;
+      if (chunk == 2 && j >= 32) return 0.f;
+      const int c = chunk * 64 + j;
+      double acc = 0;
+      for (int ty = 0; ty < 5; ++ty) {
+        const double uy = U[py + ty][dy];
+        if (uy == 0) continue;
+        for (int tx = 0; tx < 5; ++tx) acc += uy * U[px + tx][dx] * Wf(ty, tx, c, o);
+      }
+      return (float)acc;
+    };
+    // generic kernel: K-block = tap*3 + chunk;  halo kernel: K-block = chunk*16 + tap
+    if (upload_B(&g->B9, 4 * O, 16 * 3, [&](int n, int kb, int j) { return comp(n, kb / 3, kb % 3, j); })) return 1;
+    if (upload_B(&g->B9h, 4 * O, 16 * 3, [&](int n, int kb, int j) { return comp(n, kb % 16, kb / 16, j); })) return 1;
     // Border "dipole" corrections (see stencil_kernels.cuh: edge_lines_kernel): 1-D 5-tap convolutions of the four
     // upsampled edge lines; row = edge*48 + e*16 + o, where e is the distance of the output row/col from that edge.
     if (upload_B(&g->BE, 4 * 48, 5 * 3, [&](int n, int kb, int j) {
@@ -393,6 +402,7 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
 struct WsLayout {
   size_t xpad, res2p, res4, hseq, cstate, g5, catp, edgeE, deltaD, g9, total;
 };
+static const int CATP_PITCH = 192;  // 160 concat channels padded to 3 x 64 (pad channels stay zero)
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
   const size_t N = (size_t)B * T, S = g->S, S2 = S / 2, S4 = S / 4, F = g->F;
@@ -405,7 +415,7 @@ static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
   L.hseq = take(N * S4 * S4 * F * 2);
   L.cstate = take((size_t)B * S4 * S4 * F * 4);
   L.g5 = take(N * S4 * S4 * (F / 2) * 2);
-  L.catp = take(N * (S2 + 4) * (S2 + 4) * (F / 4 + 128) * 2 + 4096);
+  L.catp = take(N * (S2 + 4) * (S2 + 4) * CATP_PITCH * 2 + 4096);
   L.edgeE = take(N * 4 * (S + 8) * (F / 4 + 128) * 2);
   L.deltaD = take(N * S * 192 * 4);
   L.g9 = take(N * S * S * (F / 8) * 2);
@@ -488,7 +498,7 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
     const long long sy = (long long)(S2 + 2) * 128, sn = (long long)(S2 + 2) * sy;
     affine_epi(c.p.ep, g->bias0, g->sc0, g->sh0, g->res2p + sy + 128, sn, sy, 128, 0, 1);
     {  // res_2 also goes to channels 32.. of the zero-padded concat image read by the fused upsample conv
-      const long long CI = F / 4 + 128, PW = S2 + 4;
+      const long long CI = CATP_PITCH, PW = S2 + 4;
       c.p.ep.out2 = g->catp + (2 * PW + 2) * CI;
       c.p.ep.out2_sn = PW * PW * CI; c.p.ep.out2_sy = PW * CI; c.p.ep.out2_sx = CI; c.p.ep.out2_c0 = (int)(F / 4);
     }
@@ -597,7 +607,7 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
       KBlock& k = c.p.kb[kb];
       k.src = kb == 0 ? 0 : 1; k.half = 0; k.o0 = (int16_t)(kb <= 1 ? 0 : 64); k.o1 = 0; k.o2 = 0; k.o3 = 0;
     }
-    const long long O = F / 4, CI = F / 4 + 128, PW = S2 + 4;
+    const long long O = F / 4, CI = CATP_PITCH, PW = S2 + 4;
     affine_epi(c.p.ep, g->bias7, g->sc7, g->sh7, g->catp + (2 * PW + 2) * CI, PW * PW * CI, PW * CI, CI, 0, 1);
     c.p.ep.out_mul = 2; c.p.ep.group_cols = (int)O;
     c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
@@ -634,9 +644,9 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
   {
     ConvLaunch& c = g->L9;
     std::memset(&c.p, 0, sizeof c.p);
-    const uint64_t I = F / 4 + 128, PW = S2 + 4, flat = N * PW * PW;
+    const uint64_t I = F / 4 + 128, PW = S2 + 4, flat = N * PW * PW, CI = CATP_PITCH;
     uint64_t dims[5] = {I, flat, 1, 1, 1};
-    uint64_t str[4] = {I, flat * I, flat * I, flat * I};
+    uint64_t str[4] = {CI, flat * CI, flat * CI, flat * CI};
     uint32_t box[5] = {64, 128, 1, 1, 1};
     uint32_t boxh[5] = {32, 128, 1, 1, 1};
     if (make_tmap(&c.tmA[0], g->catp, 5, dims, str, box, 128)) return 1;
@@ -660,6 +670,21 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
     e.bias = g->bias9; e.scale = g->sc9; e.shift = g->sh9; e.out = g->g9;
     e.up_pw = (int)PW; e.up_ph = (int)PW; e.up_S = (int)S; e.up_delta = g->deltaD;
     c.bn = 64; c.epi = EPI_UPCONV; c.grid = grid_for(c.p);
+    // halo-reuse variant (upconv_halo.cuh): needs 256 + 3*PW + 3 <= 416 rows of shared memory
+    g->use_halo = (3 * PW + 3 + UH_TILES * TILE_M) <= (uint64_t)UH_ROWS;
+    if (g->use_halo) {
+      uint64_t hd[2] = {CI, flat};
+      uint64_t hs[1] = {CI};
+      uint32_t hb[2] = {64, UH_BOX_ROWS};
+      if (make_tmap(&g->hA, g->catp, 2, hd, hs, hb, 128)) return 1;
+      if (make_tmap(&g->hB, g->B9h, 2, bd, bs, bb, 128)) return 1;
+      UpHaloParams& h = g->hp;
+      h.num_passes = (int)((flat + UH_TILES * TILE_M - 1) / (UH_TILES * TILE_M));
+      h.n_img = (int)N; h.pw = (int)PW; h.ph = (int)PW; h.S = (int)S; h.delta = g->deltaD;
+      h.bias = g->bias9; h.scale = g->sc9; h.shift = g->sh9; h.out = g->g9;
+      if (getenv("WDG_NO_HALO")) g->use_halo = false;
+      g->hgrid = h.num_passes < sms ? h.num_passes : sms;
+    }
   }
   g->B = B; g->T = T;
   g->launches = 1 + 2 + T + 2 + 2 + 1 + 1;
@@ -718,12 +743,20 @@ extern "C" int wdg_generator_forward(wdg_generator* g, const float* image_dev, c
   {
     const int CI = g->F / 4 + 128;
     const long long total = N * 4 * (S + 8) * (CI / 8);
-    edge_lines_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(g->catp, g->edgeE, total, (int)(S / 2), CI);
+    edge_lines_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(g->catp, g->edgeE, total, (int)(S / 2), CI, CATP_PITCH);
     CK(cudaGetLastError());
     if (launch_conv(g->LE, stream)) return 1;
   }
   mark();
-  if (launch_conv(g->L9, stream)) return 1;
+  if (g->use_halo) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CK(cudaFuncSetAttribute(upconv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UH_SMEM));
+      attr_set = true;
+    }
+    upconv_halo_kernel<<<g->hgrid, 224, UH_SMEM, stream>>>(g->hA, g->hB, g->hp);
+    CK(cudaGetLastError());
+  } else if (launch_conv(g->L9, stream)) return 1;
   mark();
   final_conv3x3_kernel<16, 2><<<(unsigned)((npix + 127) / 128), 128, 0, stream>>>(g->g9, g->w11, g->b11, out_dev, npix,
                                                                                   (int)S);
@@ -795,7 +828,7 @@ extern "C" int wdg_generator_debug_read(const wdg_generator* g, int which, float
     case 1: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = g->res4; break;
     case 2: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = g->hseq; break;
     case 3: H = W = (int)S4; C = (int)(F / 2); sx = C; sy = S4 * sx; sn = S4 * sy; src = g->g5; break;
-    case 4: H = W = (int)S2; C = (int)(F / 4); sx = F / 4 + 128; sy = (S2 + 4) * sx; sn = (S2 + 4) * sy; src = g->catp + 2 * sy + 2 * sx; break;
+    case 4: H = W = (int)S2; C = (int)(F / 4); sx = CATP_PITCH; sy = (S2 + 4) * sx; sn = (S2 + 4) * sy; src = g->catp + 2 * sy + 2 * sx; break;
     case 5: H = W = (int)S; C = (int)(F / 8); sx = C; sy = S * sx; sn = S * sy; src = g->g9; break;
     default: return fail("unknown intermediate");
   }
