@@ -1,0 +1,286 @@
+// Implicit-GEMM convolution with shared-memory HALO REUSE on tcgen05 (sm_100a).
+//
+// The image is addressed as a flat list of rows (one row = one pixel, or one sliding window of pixels);
+// a GEMM tile is 128 CONSECUTIVE flat positions and filter tap `t` reads the same rows shifted by
+// tap_shift[t] (= dy * pitch + dx).  So the A operand of every tap is the same block of shared memory:
+//
+//   pass  = 256 consecutive flat positions (2 GEMM tiles)
+//   A     = NCHUNK channel chunks x 416 rows x 128 B (SWIZZLE_128B), loaded ONCE per pass by two TMA boxes per
+//           chunk; the operand of (tile, tap) is the plain UMMA descriptor that starts `tile*128 + shift` rows into
+//           the chunk buffer -- SWIZZLE_128B is applied on absolute smem address bits, so any 128-byte row of the
+//           1024-byte aligned buffer is a valid start (verified on B200)
+//   B     = packed weights [BN][NCHUNK*NTAP*64] (K-block = chunk*NTAP + tap), streamed through a ring of
+//           TPS-tap stages; each stage feeds both tiles (2*4*TPS MMAs per barrier round trip)
+//   D     = 2 tiles x BN fp32 columns in TMEM, double buffered
+//
+// Positions whose window crosses an image row/edge compute garbage and are masked by the epilogue.
+// Warp roles: 0 = A producer, 1 = MMA issuer (+TMEM alloc), 2-5 = epilogue, 6 = B producer.
+#pragma once
+#include "conv_umma.cuh"
+
+namespace wdg {
+
+enum { HEPI_UPCONV = 0, HEPI_AFFINE = 1 };
+
+struct HaloParams {
+  int num_passes;        // ceil(total flat positions / 256)
+  int n_img;             // images
+  int pw, ph;            // flat positions per image = pw * ph (row pitch pw)
+  int tap_shift[16];     // row shift of each tap
+  const float* bias;     // [BN] (HEPI_UPCONV: [16])
+  const float* scale;
+  const float* shift;
+  // ---- HEPI_UPCONV: anchors of the fused bilinear x2 + 5x5 transposed conv
+  int S;                 // high-res size
+  const float* delta;    // fp32 border corrections [n][S][192]
+  __nv_bfloat16* out;    // [n][S][S][16]
+  // ---- HEPI_AFFINE: valid outputs are (y < vh, x < vw); v = leaky(acc + bias) * scale + shift -> bf16, two destinations
+  int vw, vh;
+  __nv_bfloat16* out1;
+  long long o1_sn, o1_sy, o1_sx;
+  __nv_bfloat16* out2;
+  long long o2_sn, o2_sy, o2_sx;
+  int o2_c0;
+};
+
+constexpr int H_TILES = 2;
+constexpr int H_ROWS = 416;                      // 256 + max tap shift (<= 160), two TMA boxes of 208 rows
+constexpr int H_BOX_ROWS = 208;
+constexpr int H_A_BYTES = H_ROWS * 128;          // one channel chunk
+
+template <int BN, int NCHUNK, int TPS>
+struct HaloCfg {
+  static constexpr int B_STAGE_BYTES = TPS * BN * 128;
+  static constexpr int A_BYTES = NCHUNK * H_A_BYTES;
+  static constexpr int BSTAGES = (226 * 1024 - 1024 - 512 - A_BYTES) / B_STAGE_BYTES > 8
+                                     ? 8 : (226 * 1024 - 1024 - 512 - A_BYTES) / B_STAGE_BYTES;
+  static constexpr int SMEM = A_BYTES + BSTAGES * B_STAGE_BYTES + 1024 + 512;
+  static constexpr int TMEM_COLS = (2 * H_TILES * BN <= 256) ? 256 : 512;
+  static_assert(BSTAGES >= 2, "not enough shared memory for the B ring");
+  static_assert(2 * H_TILES * BN <= 512, "accumulators exceed TMEM");
+};
+
+template <int BN, int NCHUNK, int NTAP, int TPS, int EPI>
+__global__ void __launch_bounds__(224, 1)
+halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ HaloParams p) {
+  using Cfg = HaloCfg<BN, NCHUNK, TPS>;
+  constexpr int BSTAGES = Cfg::BSTAGES;
+  static_assert(NTAP % TPS == 0, "taps per stage must divide the tap count");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + BSTAGES * Cfg::B_STAGE_BYTES);
+  uint64_t* a_full = bars;                      // [NCHUNK]
+  uint64_t* a_empty = a_full + NCHUNK;          // [NCHUNK]
+  uint64_t* b_full = a_empty + NCHUNK;          // [BSTAGES]
+  uint64_t* b_empty = b_full + BSTAGES;         // [BSTAGES]
+  uint64_t* tfull = b_empty + BSTAGES;          // [2]
+  uint64_t* tempty = tfull + 2;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < NCHUNK; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < BSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Producer / MMA loops run warp-uniformly; one elected lane issues the TMA / tcgen05 instructions.
+  if (warp == 0) {
+    // ================================================= A producer: NCHUNK buffers, one fill per pass
+    uint32_t phase = 0;
+    for (int pass = blockIdx.x; pass < p.num_passes; pass += gridDim.x) {
+      const int f0 = pass * (H_TILES * TILE_M);
+      for (int c = 0; c < NCHUNK; ++c) {
+        mbar_wait(&a_empty[c], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&a_full[c], H_A_BYTES);
+          tma_load_2d(smA + c * H_A_BYTES, &tmA, &a_full[c], c * 64, f0);
+          tma_load_2d(smA + c * H_A_BYTES + H_BOX_ROWS * 128, &tmA, &a_full[c], c * 64, f0 + H_BOX_ROWS);
+        }
+        __syncwarp();
+      }
+      phase ^= 1;
+    }
+  } else if (warp == 6) {
+    // ================================================= B producer: ring over (pass, stage of TPS K-blocks)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pass = blockIdx.x; pass < p.num_passes; pass += gridDim.x) {
+      for (int g = 0; g < NCHUNK * NTAP / TPS; ++g) {
+        mbar_wait(&b_empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&b_full[stage], Cfg::B_STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < TPS; ++j)
+            tma_load_2d(smB + stage * Cfg::B_STAGE_BYTES + j * BN * 128, &tmB, &b_full[stage], (g * TPS + j) * 64, 0);
+        }
+        __syncwarp();
+        if (++stage == BSTAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================= MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+    int stage = 0;
+    uint32_t bphase = 0, aphase = 0, tphase = 0;
+    int as = 0;
+    for (int pass = blockIdx.x; pass < p.num_passes; pass += gridDim.x) {
+      mbar_wait(&tempty[as], tphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * (H_TILES * BN);
+      for (int c = 0; c < NCHUNK; ++c) {
+        mbar_wait(&a_full[c], aphase);
+        tc_fence_after();
+        const uint64_t a_desc0 = umma_desc_kmajor(smem_u32(smA + c * H_A_BYTES), 128u);
+        for (int g = 0; g < NTAP / TPS; ++g) {
+          mbar_wait(&b_full[stage], bphase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t b_desc0 = umma_desc_kmajor(smem_u32(smB + stage * Cfg::B_STAGE_BYTES), 128u);
+#pragma unroll
+            for (int j = 0; j < TPS; ++j) {
+              const int tap = g * TPS + j;
+              const uint32_t shift_rows = (uint32_t)p.tap_shift[tap];
+              const uint64_t db = b_desc0 + (uint64_t)(j * BN * 8);                          // BN rows * 128 B >> 4
+#pragma unroll
+              for (int t = 0; t < H_TILES; ++t) {
+                const uint64_t da = a_desc0 + (uint64_t)((t * TILE_M + shift_rows) * 8);     // rows * 128 B >> 4
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d_tmem + t * BN, da + 2 * k, db + 2 * k, idesc, (c | tap | k) ? 1u : 0u);
+              }
+            }
+            umma_commit(&b_empty[stage]);
+            if (g == NTAP / TPS - 1) {
+              umma_commit(&a_empty[c]);
+              if (c == NCHUNK - 1) umma_commit(&tfull[as]);
+            }
+          }
+          __syncwarp();
+          if (++stage == BSTAGES) { stage = 0; bphase ^= 1; }
+        }
+      }
+      aphase ^= 1;
+      if (++as == 2) { as = 0; tphase ^= 1; }
+    }
+  } else {
+    // ================================================= epilogue (warps 2..5)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int per_img = p.pw * p.ph;
+    int as = 0;
+    uint32_t tphase = 0;
+    for (int pass = blockIdx.x; pass < p.num_passes; pass += gridDim.x) {
+      mbar_wait(&tfull[as], tphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < H_TILES; ++t) {
+        const long long f = (long long)pass * (H_TILES * TILE_M) + t * TILE_M + row;
+        const int img = (int)(f / per_img);
+        const int rem = (int)(f - (long long)img * per_img);
+        const int pr = rem / p.pw, ps = rem - pr * p.pw;
+        const bool arow = img < p.n_img;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (H_TILES * BN) + t * BN;
+        if constexpr (EPI == HEPI_UPCONV) {
+          static_assert(EPI != HEPI_UPCONV || BN == 64, "UPCONV expects 2x2 phases x 16 channels");
+          const int S = p.S;
+#pragma unroll 1
+          for (int g = 0; g < 4; ++g) {
+            uint32_t r[16];
+            tmem_ld16(taddr + g * 16, r);
+            tmem_ld_wait();
+            const int Y = 2 * pr - 1 + (g >> 1);
+            const int X = 2 * ps - 1 + (g & 1);
+            if (arow && Y >= 0 && Y < S && X >= 0 && X < S) {
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+              const float* D = p.delta + (long long)img * S * 192;
+              if (Y < 3 || Y > S - 4) {
+                const float4* d = reinterpret_cast<const float4*>(D + X * 192 + (Y < 3 ? Y * 16 : 48 + (S - 1 - Y) * 16));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 q = __ldg(d + i);
+                  v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+                }
+              }
+              if (X < 3 || X > S - 4) {
+                const float4* d = reinterpret_cast<const float4*>(D + Y * 192 + (X < 3 ? 96 + X * 16 : 144 + (S - 1 - X) * 16));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 q = __ldg(d + i);
+                  v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float a = leaky02(v[i] + __ldg(p.bias + i));
+                v[i] = a * __ldg(p.scale + i) + __ldg(p.shift + i);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(p.out + (((long long)img * S + Y) * S + X) * 16);
+              dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                  pack_bf16x2(v[6], v[7]));
+              dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                  pack_bf16x2(v[14], v[15]));
+            }
+          }
+        } else {
+          const bool valid = arow && pr < p.vh && ps < p.vw;
+          __nv_bfloat16* d1 = p.out1 + (long long)img * p.o1_sn + (long long)pr * p.o1_sy + (long long)ps * p.o1_sx;
+          __nv_bfloat16* d2 = p.out2 + (long long)img * p.o2_sn + (long long)pr * p.o2_sy + (long long)ps * p.o2_sx + p.o2_c0;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r0[16], r1[16];
+            tmem_ld16(taddr + c0, r0);
+            tmem_ld16(taddr + c0 + 16, r1);
+            tmem_ld_wait();
+            if (valid) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                const float a0 = leaky02(__uint_as_float(r0[i]) + __ldg(p.bias + c0 + i)) * __ldg(p.scale + c0 + i) + __ldg(p.shift + c0 + i);
+                const float a1 = leaky02(__uint_as_float(r0[i + 1]) + __ldg(p.bias + c0 + i + 1)) * __ldg(p.scale + c0 + i + 1) + __ldg(p.shift + c0 + i + 1);
+                pk[i / 2] = pack_bf16x2(a0, a1);
+                const float b0 = leaky02(__uint_as_float(r1[i]) + __ldg(p.bias + c0 + 16 + i)) * __ldg(p.scale + c0 + 16 + i) + __ldg(p.shift + c0 + 16 + i);
+                const float b1 = leaky02(__uint_as_float(r1[i + 1]) + __ldg(p.bias + c0 + 17 + i)) * __ldg(p.scale + c0 + 17 + i) + __ldg(p.shift + c0 + 17 + i);
+                pk[8 + i / 2] = pack_bf16x2(b0, b1);
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 v4 = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                reinterpret_cast<uint4*>(d1 + c0)[q] = v4;
+                if (p.out2) reinterpret_cast<uint4*>(d2 + c0)[q] = v4;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; tphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace wdg

@@ -5,27 +5,41 @@
 
 namespace wdg {
 
-// K1: Concatenate([image, noise]) + ZeroPadding2D(3) + cast (models.py:28,32), written as the
-// zero-padded bf16 image [n][S+6][S+6][CP] that the 8x8 stride-2 implicit GEMM reads through an
-// overlapping-stride tensor map.  One thread per pixel; border and pad channels stay zero.
-__global__ void pack_input_kernel(const float* __restrict__ image, const float* __restrict__ noise,
-                                  __nv_bfloat16* __restrict__ xpad, long long npix, int S, int cin, int cnoise,
-                                  int CP) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npix) return;
-  const int x = (int)(i % S);
-  const int y = (int)((i / S) % S);
-  const long long n = i / ((long long)S * S);
-  const int SP = S + 6;
-  __nv_bfloat16* dst = xpad + (((n * SP) + (y + 3)) * SP + (x + 3)) * CP;
-  const float* ip = image + i * cin;
-  const float* np = noise + i * cnoise;
-  for (int c = 0; c < CP; c += 2) {
-    float a = 0.f, b = 0.f;
-    if (c < cin) a = ip[c]; else if (c < cin + cnoise) a = np[c - cin];
-    const int c1 = c + 1;
-    if (c1 < cin) b = ip[c1]; else if (c1 < cin + cnoise) b = np[c1 - cin];
-    *reinterpret_cast<uint32_t*>(dst + c) = pack_bf16x2(a, b);
+// K1: Concatenate([image, noise]) + ZeroPadding2D(3) + cast (models.py:28,32), written as the space-to-depth
+// bf16 image X2[n][Q][Q][(p, q, c)], Q = (S+6)/2: padded pixel (y+3, x+3) = (2Y+p, 2X+q), CP channels per pixel
+// (pad channels and the zero ring are never written).  One block per image row: the row's fp32 image and noise
+// are staged in shared memory with coalesced float4 loads, then each thread emits one 2*CP-byte pixel.
+__global__ void __launch_bounds__(128)
+pack_input_s2d_kernel(const float* __restrict__ image, const float* __restrict__ noise, __nv_bfloat16* __restrict__ x2,
+                      int S, int cin, int cnoise, int CP) {
+  extern __shared__ float row[];          // [S*cin image | S*cnoise noise]
+  const long long r = blockIdx.x;         // n * S + y
+  const int y = (int)(r % S);
+  const long long n = r / S;
+  const float4* img4 = reinterpret_cast<const float4*>(image + r * S * cin);
+  const float4* noi4 = reinterpret_cast<const float4*>(noise + r * S * cnoise);
+  const int n_img4 = S * cin / 4, n_noi4 = S * cnoise / 4;
+  float4* row4 = reinterpret_cast<float4*>(row);
+  for (int i = threadIdx.x; i < n_img4; i += blockDim.x) row4[i] = __ldg(img4 + i);
+  for (int i = threadIdx.x; i < n_noi4; i += blockDim.x) row4[n_img4 + i] = __ldg(noi4 + i);
+  __syncthreads();
+  const int Q = (S + 6) / 2;
+  const int py = y + 3, Y = py >> 1, p = py & 1;
+  for (int x = threadIdx.x; x < S; x += blockDim.x) {
+    const int px = x + 3, X = px >> 1, q = px & 1;
+    __nv_bfloat16* dst = x2 + ((((n * Q + Y) * Q + X) * 2 + p) * 2 + q) * CP;
+    const float* ip = row + x * cin;
+    const float* np = row + S * cin + x * cnoise;
+    for (int c = 0; c < CP; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int cc = c + k;
+        v[k] = cc < cin ? ip[cc] : (cc < cin + cnoise ? np[cc - cin] : 0.f);
+      }
+      *reinterpret_cast<uint4*>(dst + c) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                      pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
   }
 }
 
@@ -85,14 +99,20 @@ __global__ void edge_lines_kernel(const __nv_bfloat16* __restrict__ catp, __nv_b
                  pack_bf16x2(acc[6], acc[7]));
 }
 
-// K9: Conv2D(out_channels, 3x3, 'same', linear) on the post-BatchNorm 16-channel tensor
-// (models.py:70-71).  CUDA cores: K = 144, N = 2 is a bandwidth-bound stencil.  One thread per pixel.
+// K9: Conv2D(out_channels, 3x3, 'same', linear) on the post-BatchNorm 16-channel tensor (models.py:70-71).
+// CUDA cores: K = 144, N = 2 is a bandwidth-bound stencil.  The 288 weights travel as a kernel parameter, i.e. in
+// the constant bank, so every FFMA takes its weight as a constant operand (no shared-memory or global loads).
+// One thread per output pixel.
 template <int CIN, int COUT>
-__global__ void final_conv3x3_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ wgt /*[3][3][CIN][COUT]*/,
-                                     const float* __restrict__ bias, float* __restrict__ out, long long npix, int S) {
-  __shared__ float ws[9 * CIN * COUT];
-  for (int i = threadIdx.x; i < 9 * CIN * COUT; i += blockDim.x) ws[i] = wgt[i];
-  __syncthreads();
+struct FinalConvW {
+  float w[9 * CIN * COUT];  // [3][3][CIN][COUT]
+  float b[COUT];
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(128)
+final_conv3x3_kernel(const __nv_bfloat16* __restrict__ in, const __grid_constant__ FinalConvW<CIN, COUT> W,
+                     float* __restrict__ out, long long npix, int S) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
   const int x = (int)(i % S);
@@ -100,7 +120,7 @@ __global__ void final_conv3x3_kernel(const __nv_bfloat16* __restrict__ in, const
   const long long n = i / ((long long)S * S);
   float acc[COUT];
 #pragma unroll
-  for (int o = 0; o < COUT; ++o) acc[o] = bias[o];
+  for (int o = 0; o < COUT; ++o) acc[o] = W.b[o];
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
     const int yy = y + dy - 1;
@@ -109,26 +129,29 @@ __global__ void final_conv3x3_kernel(const __nv_bfloat16* __restrict__ in, const
     for (int dx = 0; dx < 3; ++dx) {
       const int xx = x + dx - 1;
       if (xx < 0 || xx >= S) continue;
-      const __nv_bfloat16* p = in + ((n * S + yy) * S + xx) * CIN;
-      const float* wk = ws + (dy * 3 + dx) * CIN * COUT;
+      const uint4* p = reinterpret_cast<const uint4*>(in + ((n * S + yy) * S + xx) * CIN);
 #pragma unroll
       for (int c8 = 0; c8 < CIN; c8 += 8) {
-        const uint4 v = *reinterpret_cast<const uint4*>(p + c8);
+        const uint4 v = __ldg(p + c8 / 8);
         const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 f = __bfloat1622float2(hv[k]);
 #pragma unroll
           for (int o = 0; o < COUT; ++o) {
-            acc[o] += f.x * wk[(c8 + 2 * k) * COUT + o];
-            acc[o] += f.y * wk[(c8 + 2 * k + 1) * COUT + o];
+            acc[o] = fmaf(f.x, W.w[((dy * 3 + dx) * CIN + c8 + 2 * k) * COUT + o], acc[o]);
+            acc[o] = fmaf(f.y, W.w[((dy * 3 + dx) * CIN + c8 + 2 * k + 1) * COUT + o], acc[o]);
           }
         }
       }
     }
   }
+  if (COUT == 2) {
+    *reinterpret_cast<float2*>(out + i * 2) = make_float2(acc[0], acc[1]);
+  } else {
 #pragma unroll
-  for (int o = 0; o < COUT; ++o) out[i * COUT + o] = acc[o];
+    for (int o = 0; o < COUT; ++o) out[i * COUT + o] = acc[o];
+  }
 }
 
 }  // namespace wdg

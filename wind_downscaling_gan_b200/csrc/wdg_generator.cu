@@ -13,7 +13,7 @@
 
 #include "../../include/wdg.h"
 #include "conv_umma.cuh"
-#include "upconv_halo.cuh"
+#include "halo_conv.cuh"
 #include "stencil_kernels.cuh"
 
 using namespace wdg;
@@ -129,12 +129,13 @@ struct wdg_generator {
   float *cstate, *deltaD;
   float *zero48, *one48;
   ConvLaunch L0, L2, L5, L7, LE, L9;
-  bool use_halo = false;
-  CUtensorMap hA, hB;
-  UpHaloParams hp;
-  int hgrid = 0;
+  bool use_halo = false;       // halo-reuse kernels (halo_conv.cuh) for the 8x8 s2 conv and the fused upsample conv
+  CUtensorMap hA, hB, h0A, h0B;
+  HaloParams hp, h0p;
+  int hgrid = 0, h0grid = 0;
   std::vector<ConvLaunch> LS;  // one per timestep
   int launches = 0;
+  FinalConvW<16, 2> w11h;      // final 3x3 conv weights, passed by value (constant bank)
   // optional per-stage CUDA-event timing (bench.py roofline)
   bool profiling = false;
   cudaEvent_t ev[WDG_NUM_STAGES + 1] = {};
@@ -250,14 +251,17 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
   if (!g) return fail("null handle");
   const int F = g->F, C = g->cin + g->cnoise, CP = g->CP;
   auto W = [&](int i, const char* leaf) -> const std::vector<float>& { return g->w[wname(i, leaf)]; };
-  // ---- L0: 8x8 s2 conv.  K index within a tap row = kx*CP + c (window over the padded image).
+  // ---- L0: 8x8 s2 conv on the space-to-depth image X2[n][Y][X][(p,q,c)] (padded pixel (2Y+p, 2X+q), CP channels).
+  //      It becomes a 4x4 stride-1 conv over 4*CP channels; two horizontally adjacent s2d pixels are contiguous
+  //      (8*CP = 192 elements = 3 chunks of 64), so tap (a, w) = rows +a, window starting at pixel +2w, and
+  //      K-block = chunk*8 + (a*2 + w).  Window element e: pixel w' = e / (4*CP), parity (p,q), channel c.
   {
     const auto& w = W(0, "layer/w");  // [8][8][C][128]
-    const int wk = 8 * CP;            // window elements per tap row
-    const int chunks = wk / 64;
-    if (wk % 64) return fail("8*CP not a multiple of 64");
-    if (upload_B(&g->B0, 128, 8 * chunks, [&](int n, int kb, int j) {
-          const int ky = kb / chunks, e = (kb % chunks) * 64 + j, kx = e / CP, c = e % CP;
+    if (8 * CP != 192) return fail("8x8 s2 conv kernel expects 8*CP == 192 (CP == 24)");
+    if (upload_B(&g->B0, 128, 24, [&](int n, int kb, int j) {
+          const int chunk = kb / 8, tap = kb % 8, a = tap / 2, ww = tap % 2;
+          const int e = chunk * 64 + j, wp = e / (4 * CP), rem = e % (4 * CP), pq = rem / CP, c = rem % CP;
+          const int ky = 2 * a + pq / 2, kx = 2 * (2 * ww + wp) + pq % 2;
           return c < C ? w[(((size_t)ky * 8 + kx) * C + c) * 128 + n] : 0.f;
         })) return 1;
   }
@@ -390,6 +394,8 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
     g->bias7 = f + o_b7; g->sc7 = f + o_sc7; g->sh7 = f + o_sh7;
     g->bias9 = f + o_b9; g->sc9 = f + o_sc9; g->sh9 = f + o_sh9;
     g->w11 = f + o_w11; g->b11 = f + o_b11;
+    std::memcpy(g->w11h.w, W(11, "layer/kernel").data(), sizeof g->w11h.w);
+    std::memcpy(g->w11h.b, W(11, "layer/bias").data(), sizeof g->w11h.b);
     g->zero48 = f + o_zero; g->one48 = f + o_one;
   }
   (void)C;
@@ -409,7 +415,7 @@ static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
   WsLayout L;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return r; };
-  L.xpad = take(N * (S + 6) * (S + 6) * g->CP * 2);
+  L.xpad = take(N * (S + 6) * (S + 6) * g->CP * 2 + 1024);   // s2d image [N][(S+6)/2][(S+6)/2][4*CP] (+ window slack)
   L.res2p = take(N * (S2 + 2) * (S2 + 2) * 128 * 2);
   L.res4 = take(N * S4 * S4 * F * 2);
   L.hseq = take(N * S4 * S4 * F * 2);
@@ -473,36 +479,55 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
     return total < sms ? total : sms;
   };
   // dummy map for unused A slots: reuse slot 0
-  // ---------------- L0: 8x8 s2 on xpad [N][S+6][S+6][CP]; dims (window 8*CP, ox S2, oy S2, parity 2, n)
+  // ---------------- L0: 8x8 s2 as 4x4 s1 on the s2d image X2 [N][Q][Q][4*CP], Q = (S+6)/2; dims (window 8*CP, X, Y, n)
   {
     ConvLaunch& c = g->L0;
     std::memset(&c.p, 0, sizeof c.p);
-    const uint64_t SP = S + 6;
-    uint64_t dims[5] = {8 * CP, S2, SP / 2, 2, N};  // oy + ky/2 reaches SP/2 - 1
-    uint64_t str[4] = {2 * CP, 2 * SP * CP, SP * CP, SP * SP * CP};
+    const uint64_t Q = (S + 6) / 2, PC = 4 * CP;
+    uint64_t dims[5] = {2 * PC, Q, Q, N, 1};
+    uint64_t str[4] = {PC, Q * PC, Q * Q * PC, N * Q * Q * PC};
     uint32_t box[5] = {64, 16, 8, 1, 1};
     if (make_tmap(&c.tmA[0], g->xpad, 5, dims, str, box, 128)) return 1;
     c.tmA[1] = c.tmA[0]; c.tmA[2] = c.tmA[0];
-    const int chunks = (int)(8 * CP / 64);
-    uint64_t bd[2] = {(uint64_t)8 * chunks * 64, 128};
-    uint64_t bs[1] = {(uint64_t)8 * chunks * 64};
+    uint64_t bd[2] = {24 * 64, 128};
+    uint64_t bs[1] = {24 * 64};
     uint32_t bb[2] = {64, 128};
     if (make_tmap(&c.tmB, g->B0, 2, bd, bs, bb, 128)) return 1;
-    set_tiles(c.p, (int)S2, (int)S2, (int)N, 16, 8, 1, 1, 4);
-    c.p.num_kb = 8 * chunks;
-    for (int ky = 0; ky < 8; ++ky)
-      for (int ch = 0; ch < chunks; ++ch) {
-        KBlock& k = c.p.kb[ky * chunks + ch];
-        k.src = 0; k.half = 0; k.o0 = (int16_t)(ch * 64); k.o1 = 0; k.o2 = (int16_t)(ky / 2); k.o3 = (int16_t)(ky % 2);
+    set_tiles(c.p, (int)S2, (int)S2, (int)N, 16, 8, 1, 1, 3);
+    c.p.num_kb = 24;
+    for (int ch = 0; ch < 3; ++ch)
+      for (int tap = 0; tap < 8; ++tap) {
+        KBlock& k = c.p.kb[ch * 8 + tap];
+        k.src = 0; k.half = 0; k.o0 = (int16_t)(ch * 64); k.o1 = (int16_t)(2 * (tap % 2)); k.o2 = (int16_t)(tap / 2); k.o3 = 0;
       }
     const long long sy = (long long)(S2 + 2) * 128, sn = (long long)(S2 + 2) * sy;
     affine_epi(c.p.ep, g->bias0, g->sc0, g->sh0, g->res2p + sy + 128, sn, sy, 128, 0, 1);
-    {  // res_2 also goes to channels 32.. of the zero-padded concat image read by the fused upsample conv
-      const long long CI = CATP_PITCH, PW = S2 + 4;
-      c.p.ep.out2 = g->catp + (2 * PW + 2) * CI;
-      c.p.ep.out2_sn = PW * PW * CI; c.p.ep.out2_sy = PW * CI; c.p.ep.out2_sx = CI; c.p.ep.out2_c0 = (int)(F / 4);
-    }
+    const long long CI = CATP_PITCH, PW = S2 + 4;
+    // res_2 also goes to channels 32.. of the zero-padded concat image read by the fused upsample conv
+    c.p.ep.out2 = g->catp + (2 * PW + 2) * CI;
+    c.p.ep.out2_sn = PW * PW * CI; c.p.ep.out2_sy = PW * CI; c.p.ep.out2_sx = CI; c.p.ep.out2_c0 = (int)(F / 4);
     c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
+    // halo-reuse variant: flat positions of X2 (pitch Q), taps shift by a*Q + 2w rows
+    const bool fits = (3 * Q + 2 + H_TILES * TILE_M) <= (uint64_t)H_ROWS;
+    if (fits) {
+      const uint64_t flat = N * Q * Q;
+      uint64_t hd[2] = {2 * PC, flat};
+      uint64_t hs[1] = {PC};
+      uint32_t hb[2] = {64, H_BOX_ROWS};
+      if (make_tmap(&g->h0A, g->xpad, 2, hd, hs, hb, 128)) return 1;
+      g->h0B = c.tmB;
+      HaloParams& h = g->h0p;
+      std::memset(&h, 0, sizeof h);
+      h.num_passes = (int)((flat + H_TILES * TILE_M - 1) / (H_TILES * TILE_M));
+      h.n_img = (int)N; h.pw = (int)Q; h.ph = (int)Q;
+      for (int tap = 0; tap < 8; ++tap) h.tap_shift[tap] = (tap / 2) * (int)Q + 2 * (tap % 2);
+      h.bias = g->bias0; h.scale = g->sc0; h.shift = g->sh0;
+      h.vw = (int)S2; h.vh = (int)S2;
+      h.out1 = g->res2p + sy + 128; h.o1_sn = sn; h.o1_sy = sy; h.o1_sx = 128;
+      h.out2 = g->catp + (2 * PW + 2) * CI; h.o2_sn = PW * PW * CI; h.o2_sy = PW * CI; h.o2_sx = CI; h.o2_c0 = (int)(F / 4);
+      g->h0grid = h.num_passes < sms ? h.num_passes : sms;
+    }
+    g->use_halo = fits;
   }
   // ---------------- L2: 4x4 s2 on res2p [N][S2+2][S2+2][128]; dims (window 512, ox S4, oy S4, parity 2, n)
   {
@@ -670,19 +695,20 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
     e.bias = g->bias9; e.scale = g->sc9; e.shift = g->sh9; e.out = g->g9;
     e.up_pw = (int)PW; e.up_ph = (int)PW; e.up_S = (int)S; e.up_delta = g->deltaD;
     c.bn = 64; c.epi = EPI_UPCONV; c.grid = grid_for(c.p);
-    // halo-reuse variant (upconv_halo.cuh): needs 256 + 3*PW + 3 <= 416 rows of shared memory
-    g->use_halo = (3 * PW + 3 + UH_TILES * TILE_M) <= (uint64_t)UH_ROWS;
+    // halo-reuse variant (halo_conv.cuh): needs 256 + 3*PW + 3 <= 416 rows of shared memory
+    g->use_halo = g->use_halo && (3 * PW + 3 + H_TILES * TILE_M) <= (uint64_t)H_ROWS && !getenv("WDG_NO_HALO");
     if (g->use_halo) {
       uint64_t hd[2] = {CI, flat};
       uint64_t hs[1] = {CI};
-      uint32_t hb[2] = {64, UH_BOX_ROWS};
+      uint32_t hb[2] = {64, H_BOX_ROWS};
       if (make_tmap(&g->hA, g->catp, 2, hd, hs, hb, 128)) return 1;
       if (make_tmap(&g->hB, g->B9h, 2, bd, bs, bb, 128)) return 1;
-      UpHaloParams& h = g->hp;
-      h.num_passes = (int)((flat + UH_TILES * TILE_M - 1) / (UH_TILES * TILE_M));
+      HaloParams& h = g->hp;
+      std::memset(&h, 0, sizeof h);
+      h.num_passes = (int)((flat + H_TILES * TILE_M - 1) / (H_TILES * TILE_M));
       h.n_img = (int)N; h.pw = (int)PW; h.ph = (int)PW; h.S = (int)S; h.delta = g->deltaD;
+      for (int tap = 0; tap < 16; ++tap) h.tap_shift[tap] = (tap / 4) * (int)PW + tap % 4;
       h.bias = g->bias9; h.scale = g->sc9; h.shift = g->sh9; h.out = g->g9;
-      if (getenv("WDG_NO_HALO")) g->use_halo = false;
       g->hgrid = h.num_passes < sms ? h.num_passes : sms;
     }
   }
@@ -725,11 +751,18 @@ extern "C" int wdg_generator_forward(wdg_generator* g, const float* image_dev, c
   int stage_i = 0;
   auto mark = [&]() { if (g->profiling) cudaEventRecord(g->ev[stage_i++], stream); };
   mark();
-  pack_input_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(image_dev, noise_dev, g->xpad, npix, (int)S,
-                                                                        g->cin, g->cnoise, g->CP);
+  pack_input_s2d_kernel<<<(unsigned)(N * S), 128, (size_t)S * (g->cin + g->cnoise) * sizeof(float), stream>>>(
+      image_dev, noise_dev, g->xpad, (int)S, g->cin, g->cnoise, g->CP);
   CK(cudaGetLastError());
   mark();
-  if (launch_conv(g->L0, stream)) return 1;
+  if (g->use_halo) {
+    auto kern = halo_conv_kernel<128, 3, 8, 1, HEPI_AFFINE>;
+    constexpr int smem = HaloCfg<128, 3, 1>::SMEM;
+    static bool attr0 = false;
+    if (!attr0) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr0 = true; }
+    kern<<<g->h0grid, 224, smem, stream>>>(g->h0A, g->h0B, g->h0p);
+    CK(cudaGetLastError());
+  } else if (launch_conv(g->L0, stream)) return 1;
   mark();
   if (launch_conv(g->L2, stream)) return 1;
   mark();
@@ -749,17 +782,15 @@ extern "C" int wdg_generator_forward(wdg_generator* g, const float* image_dev, c
   }
   mark();
   if (g->use_halo) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      CK(cudaFuncSetAttribute(upconv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UH_SMEM));
-      attr_set = true;
-    }
-    upconv_halo_kernel<<<g->hgrid, 224, UH_SMEM, stream>>>(g->hA, g->hB, g->hp);
+    auto kern = halo_conv_kernel<64, 3, 16, 2, HEPI_UPCONV>;
+    constexpr int smem = HaloCfg<64, 3, 2>::SMEM;
+    static bool attr9 = false;
+    if (!attr9) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr9 = true; }
+    kern<<<g->hgrid, 224, smem, stream>>>(g->hA, g->hB, g->hp);
     CK(cudaGetLastError());
   } else if (launch_conv(g->L9, stream)) return 1;
   mark();
-  final_conv3x3_kernel<16, 2><<<(unsigned)((npix + 127) / 128), 128, 0, stream>>>(g->g9, g->w11, g->b11, out_dev, npix,
-                                                                                  (int)S);
+  final_conv3x3_kernel<16, 2><<<(unsigned)((npix + 127) / 128), 128, 0, stream>>>(g->g9, g->w11h, out_dev, npix, (int)S);
   CK(cudaGetLastError());
   mark();
   return 0;
