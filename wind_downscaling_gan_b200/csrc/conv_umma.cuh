@@ -224,13 +224,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           tmem_ld_wait();
           if (valid) {
             const int col = n_tile * BN + c0;
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float a = __uint_as_float(r[i]) + __ldg(e.bias + col + i);
-              if (e.lrelu) a = leaky02(a);
-              v[i] = a * __ldg(e.scale + col + i) + __ldg(e.shift + col + i);
-            }
             int oy = y, ox = x, oc = col;
             if (e.out_mul == 2) {
               const int g = col / e.group_cols;
@@ -243,19 +236,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (e.out_f32) {
               float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            } else {
-              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off);
-              dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                  pack_bf16x2(v[6], v[7]));
-              dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                                  pack_bf16x2(v[14], v[15]));
-              if (e.out2) {
-                uint4* d2 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out2) + (long long)n * e.out2_sn +
-                                                     (long long)oy * e.out2_sy + (long long)ox * e.out2_sx + e.out2_c0 + oc);
-                d2[0] = dst[0];
-                d2[1] = dst[1];
+              for (int i = 0; i < 4; ++i) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + col) + i);
+                const float4 ss = __ldg(reinterpret_cast<const float4*>(e.scale + col) + i);
+                const float4 tt = __ldg(reinterpret_cast<const float4*>(e.shift + col) + i);
+                float a0 = __uint_as_float(r[4 * i]) + bb.x, a1 = __uint_as_float(r[4 * i + 1]) + bb.y;
+                float a2 = __uint_as_float(r[4 * i + 2]) + bb.z, a3 = __uint_as_float(r[4 * i + 3]) + bb.w;
+                if (e.lrelu) { a0 = leaky02(a0); a1 = leaky02(a1); a2 = leaky02(a2); a3 = leaky02(a3); }
+                dst[i] = make_float4(a0 * ss.x + tt.x, a1 * ss.y + tt.y, a2 * ss.z + tt.z, a3 * ss.w + tt.w);
               }
+            } else {
+              uint32_t pk[8];
+              affine16_pack(r, e.bias + col, e.scale + col, e.shift + col, e.lrelu != 0, pk);
+              st_global_v8(reinterpret_cast<__nv_bfloat16*>(e.out) + off, pk);
+              if (e.out2)
+                st_global_v8(reinterpret_cast<__nv_bfloat16*>(e.out2) + (long long)n * e.out2_sn + (long long)oy * e.out2_sy +
+                                 (long long)ox * e.out2_sx + e.out2_c0 + oc, pk);
             }
           }
         }
@@ -306,12 +302,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               const float a = leaky02(v[i] + __ldg(e.bias + i));
               v[i] = a * __ldg(e.scale + i) + __ldg(e.shift + i);
             }
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) +
-                                                  (((long long)img * S + Y) * S + X) * 16);
-            dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                pack_bf16x2(v[6], v[7]));
-            dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                                pack_bf16x2(v[14], v[15]));
+            const uint32_t pk[8] = {pack_bf16x2(v[0], v[1]),   pack_bf16x2(v[2], v[3]),   pack_bf16x2(v[4], v[5]),
+                                    pack_bf16x2(v[6], v[7]),   pack_bf16x2(v[8], v[9]),   pack_bf16x2(v[10], v[11]),
+                                    pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])};
+            st_global_v8(reinterpret_cast<__nv_bfloat16*>(e.out) + (((long long)img * S + Y) * S + X) * 16, pk);
           }
         }
       } else {
@@ -355,12 +349,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               reinterpret_cast<float4*>(cptr)[i] = make_float4(cn[4 * i], cn[4 * i + 1], cn[4 * i + 2], cn[4 * i + 3]);
-            uint4* hdst = reinterpret_cast<uint4*>(e.h_out + (long long)n * e.h_sn + e.h_off +
-                                                   ((long long)y * p.W + x) * e.F + ch0);
-            hdst[0] = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]), pack_bf16x2(hn[4], hn[5]),
-                                 pack_bf16x2(hn[6], hn[7]));
-            hdst[1] = make_uint4(pack_bf16x2(hn[8], hn[9]), pack_bf16x2(hn[10], hn[11]), pack_bf16x2(hn[12], hn[13]),
-                                 pack_bf16x2(hn[14], hn[15]));
+            const uint32_t pk[8] = {pack_bf16x2(hn[0], hn[1]),   pack_bf16x2(hn[2], hn[3]),   pack_bf16x2(hn[4], hn[5]),
+                                    pack_bf16x2(hn[6], hn[7]),   pack_bf16x2(hn[8], hn[9]),   pack_bf16x2(hn[10], hn[11]),
+                                    pack_bf16x2(hn[12], hn[13]), pack_bf16x2(hn[14], hn[15])};
+            st_global_v8(e.h_out + (long long)n * e.h_sn + e.h_off + ((long long)y * p.W + x) * e.F + ch0, pk);
           }
         }
       }

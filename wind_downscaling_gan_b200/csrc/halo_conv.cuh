@@ -230,11 +230,10 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const float a = leaky02(v[i] + __ldg(p.bias + i));
                 v[i] = a * __ldg(p.scale + i) + __ldg(p.shift + i);
               }
-              uint4* dst = reinterpret_cast<uint4*>(p.out + (((long long)img * S + Y) * S + X) * 16);
-              dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                  pack_bf16x2(v[6], v[7]));
-              dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                                  pack_bf16x2(v[14], v[15]));
+              const uint32_t pk[8] = {pack_bf16x2(v[0], v[1]),   pack_bf16x2(v[2], v[3]),   pack_bf16x2(v[4], v[5]),
+                                      pack_bf16x2(v[6], v[7]),   pack_bf16x2(v[8], v[9]),   pack_bf16x2(v[10], v[11]),
+                                      pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])};
+              st_global_v8(p.out + (((long long)img * S + Y) * S + X) * 16, pk);
             }
           }
         } else {
@@ -248,21 +247,14 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tmem_ld16(taddr + c0 + 16, r1);
             tmem_ld_wait();
             if (valid) {
-              uint32_t pk[16];
-#pragma unroll
-              for (int i = 0; i < 16; i += 2) {
-                const float a0 = leaky02(__uint_as_float(r0[i]) + __ldg(p.bias + c0 + i)) * __ldg(p.scale + c0 + i) + __ldg(p.shift + c0 + i);
-                const float a1 = leaky02(__uint_as_float(r0[i + 1]) + __ldg(p.bias + c0 + i + 1)) * __ldg(p.scale + c0 + i + 1) + __ldg(p.shift + c0 + i + 1);
-                pk[i / 2] = pack_bf16x2(a0, a1);
-                const float b0 = leaky02(__uint_as_float(r1[i]) + __ldg(p.bias + c0 + 16 + i)) * __ldg(p.scale + c0 + 16 + i) + __ldg(p.shift + c0 + 16 + i);
-                const float b1 = leaky02(__uint_as_float(r1[i + 1]) + __ldg(p.bias + c0 + 17 + i)) * __ldg(p.scale + c0 + 17 + i) + __ldg(p.shift + c0 + 17 + i);
-                pk[8 + i / 2] = pack_bf16x2(b0, b1);
-              }
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 v4 = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                reinterpret_cast<uint4*>(d1 + c0)[q] = v4;
-                if (p.out2) reinterpret_cast<uint4*>(d2 + c0)[q] = v4;
+              uint32_t pk0[8], pk1[8];
+              affine16_pack(r0, p.bias + c0, p.scale + c0, p.shift + c0, true, pk0);
+              affine16_pack(r1, p.bias + c0 + 16, p.scale + c0 + 16, p.shift + c0 + 16, true, pk1);
+              st_global_v8(d1 + c0, pk0);
+              st_global_v8(d1 + c0 + 16, pk1);
+              if (p.out2) {
+                st_global_v8(d2 + c0, pk0);
+                st_global_v8(d2 + c0 + 16, pk1);
               }
             }
           }

@@ -147,5 +147,32 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// 256-bit global store (sm_100+): one full 32-byte sector per lane and instruction.
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// bias -> LeakyReLU(0.2) -> folded BatchNorm for 16 consecutive GEMM columns, packed to 8 x bf16x2.
+// The per-column vectors are read as warp-uniform float4 loads.
+__device__ __forceinline__ void affine16_pack(const uint32_t (&acc)[16], const float* __restrict__ bias,
+                                              const float* __restrict__ scale, const float* __restrict__ shift,
+                                              bool lrelu, uint32_t (&out)[8]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q);
+    const float4 s = __ldg(reinterpret_cast<const float4*>(scale) + q);
+    const float4 t = __ldg(reinterpret_cast<const float4*>(shift) + q);
+    float a0 = __uint_as_float(acc[4 * q]) + b.x, a1 = __uint_as_float(acc[4 * q + 1]) + b.y;
+    float a2 = __uint_as_float(acc[4 * q + 2]) + b.z, a3 = __uint_as_float(acc[4 * q + 3]) + b.w;
+    if (lrelu) {
+      a0 = a0 >= 0.f ? a0 : 0.2f * a0; a1 = a1 >= 0.f ? a1 : 0.2f * a1;
+      a2 = a2 >= 0.f ? a2 : 0.2f * a2; a3 = a3 >= 0.f ? a3 : 0.2f * a3;
+    }
+    out[2 * q] = pack_bf16x2(a0 * s.x + t.x, a1 * s.y + t.y);
+    out[2 * q + 1] = pack_bf16x2(a2 * s.z + t.z, a3 * s.w + t.w);
+  }
+}
+
 
 }  // namespace wdg

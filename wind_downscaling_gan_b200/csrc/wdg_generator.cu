@@ -125,7 +125,7 @@ struct wdg_generator {
   // plan
   int B = 0, T = 0;
   uint8_t* ws = nullptr;
-  __nv_bfloat16 *xpad, *res2p, *res4, *hseq, *g5, *catp, *edgeE, *g9;
+  __nv_bfloat16 *xpad, *res4, *hseq, *g5, *catp, *edgeE, *g9;
   float *cstate, *deltaD;
   float *zero48, *one48;
   ConvLaunch L0, L2, L5, L7, LE, L9;
@@ -348,7 +348,9 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
   }
   // ---- fp32 per-column vectors
   std::vector<float> fp;
-  auto push = [&](const std::vector<float>& v) { size_t o = fp.size(); fp.insert(fp.end(), v.begin(), v.end()); return o; };
+  auto push = [&](const std::vector<float>& v) {  // 16-byte aligned so the kernels can use float4 loads
+    while (fp.size() % 4) fp.push_back(0.f);
+    size_t o = fp.size(); fp.insert(fp.end(), v.begin(), v.end()); return o; };
   auto bn_fold = [&](int i, int c, std::vector<float>& sc, std::vector<float>& sh) {
     const auto &ga = W(i, "gamma"), &be = W(i, "beta"), &mu = W(i, "moving_mean"), &va = W(i, "moving_variance");
     sc.resize(c); sh.resize(c);
@@ -406,7 +408,7 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
 
 // ------------------------------------------------------------- workspace
 struct WsLayout {
-  size_t xpad, res2p, res4, hseq, cstate, g5, catp, edgeE, deltaD, g9, total;
+  size_t xpad, res4, hseq, cstate, g5, catp, edgeE, deltaD, g9, total;
 };
 static const int CATP_PITCH = 192;  // 160 concat channels padded to 3 x 64 (pad channels stay zero)
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -416,7 +418,6 @@ static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return r; };
   L.xpad = take(N * (S + 6) * (S + 6) * g->CP * 2 + 1024);   // s2d image [N][(S+6)/2][(S+6)/2][4*CP] (+ window slack)
-  L.res2p = take(N * (S2 + 2) * (S2 + 2) * 128 * 2);
   L.res4 = take(N * S4 * S4 * F * 2);
   L.hseq = take(N * S4 * S4 * F * 2);
   L.cstate = take((size_t)B * S4 * S4 * F * 4);
@@ -468,7 +469,7 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
   CK(cudaMemsetAsync(workspace_dev, 0, L.total, stream));
   uint8_t* ws = (uint8_t*)workspace_dev;
   g->ws = ws;
-  g->xpad = (__nv_bfloat16*)(ws + L.xpad); g->res2p = (__nv_bfloat16*)(ws + L.res2p);
+  g->xpad = (__nv_bfloat16*)(ws + L.xpad);
   g->res4 = (__nv_bfloat16*)(ws + L.res4); g->hseq = (__nv_bfloat16*)(ws + L.hseq);
   g->cstate = (float*)(ws + L.cstate); g->g5 = (__nv_bfloat16*)(ws + L.g5); g->catp = (__nv_bfloat16*)(ws + L.catp);
   g->edgeE = (__nv_bfloat16*)(ws + L.edgeE); g->deltaD = (float*)(ws + L.deltaD); g->g9 = (__nv_bfloat16*)(ws + L.g9);
@@ -500,12 +501,10 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
         KBlock& k = c.p.kb[ch * 8 + tap];
         k.src = 0; k.half = 0; k.o0 = (int16_t)(ch * 64); k.o1 = (int16_t)(2 * (tap % 2)); k.o2 = (int16_t)(tap / 2); k.o3 = 0;
       }
-    const long long sy = (long long)(S2 + 2) * 128, sn = (long long)(S2 + 2) * sy;
-    affine_epi(c.p.ep, g->bias0, g->sc0, g->sh0, g->res2p + sy + 128, sn, sy, 128, 0, 1);
+    // res_2 is written once, as channels 32..159 of the zero-padded concat image `catp` (ring 2): it is read there
+    // by the 4x4 s2 conv (through an overlapping-stride window map) and by the fused upsample conv.
     const long long CI = CATP_PITCH, PW = S2 + 4;
-    // res_2 also goes to channels 32.. of the zero-padded concat image read by the fused upsample conv
-    c.p.ep.out2 = g->catp + (2 * PW + 2) * CI;
-    c.p.ep.out2_sn = PW * PW * CI; c.p.ep.out2_sy = PW * CI; c.p.ep.out2_sx = CI; c.p.ep.out2_c0 = (int)(F / 4);
+    affine_epi(c.p.ep, g->bias0, g->sc0, g->sh0, g->catp + (2 * PW + 2) * CI, PW * PW * CI, PW * CI, CI, (int)(F / 4), 1);
     c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
     // halo-reuse variant: flat positions of X2 (pitch Q), taps shift by a*Q + 2w rows
     const bool fits = (3 * Q + 2 + H_TILES * TILE_M) <= (uint64_t)H_ROWS;
@@ -523,21 +522,22 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
       for (int tap = 0; tap < 8; ++tap) h.tap_shift[tap] = (tap / 2) * (int)Q + 2 * (tap % 2);
       h.bias = g->bias0; h.scale = g->sc0; h.shift = g->sh0;
       h.vw = (int)S2; h.vh = (int)S2;
-      h.out1 = g->res2p + sy + 128; h.o1_sn = sn; h.o1_sy = sy; h.o1_sx = 128;
-      h.out2 = g->catp + (2 * PW + 2) * CI; h.o2_sn = PW * PW * CI; h.o2_sy = PW * CI; h.o2_sx = CI; h.o2_c0 = (int)(F / 4);
+      h.out1 = g->catp + (2 * PW + 2) * CI + F / 4; h.o1_sn = PW * PW * CI; h.o1_sy = PW * CI; h.o1_sx = CI;
+      h.out2 = nullptr;
       g->h0grid = h.num_passes < sms ? h.num_passes : sms;
     }
     g->use_halo = fits;
   }
-  // ---------------- L2: 4x4 s2 on res2p [N][S2+2][S2+2][128]; dims (window 512, ox S4, oy S4, parity 2, n)
+  // ---------------- L2: ZeroPadding2D(1) + 4x4 s2 on res_2 = channels 32..159 of catp [N][S2+4][S2+4][192] (ring 2,
+  //                  so the pad-1 image starts at (1,1)); dims (window of 4 pixels, ox, oy, row parity, n)
   {
     ConvLaunch& c = g->L2;
     std::memset(&c.p, 0, sizeof c.p);
-    const uint64_t SP = S2 + 2;
-    uint64_t dims[5] = {512, S4, SP / 2, 2, N};  // oy + ky/2 reaches SP/2 - 1
-    uint64_t str[4] = {256, 2 * SP * 128, SP * 128, SP * SP * 128};
+    const uint64_t PW = S2 + 4, CI = CATP_PITCH;
+    uint64_t dims[5] = {3 * CI + 128, S4, PW / 2 - 1, 2, N};
+    uint64_t str[4] = {2 * CI, 2 * PW * CI, PW * CI, PW * PW * CI};
     uint32_t box[5] = {64, 8, 8, 1, 2};
-    if (make_tmap(&c.tmA[0], g->res2p, 5, dims, str, box, 128)) return 1;
+    if (make_tmap(&c.tmA[0], g->catp + (PW + 1) * CI + F / 4, 5, dims, str, box, 128)) return 1;
     c.tmA[1] = c.tmA[0]; c.tmA[2] = c.tmA[0];
     uint64_t bd[2] = {32 * 64, 128};
     uint64_t bs[1] = {32 * 64};
@@ -546,9 +546,9 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
     set_tiles(c.p, (int)S4, (int)S4, (int)N, 8, 8, 2, 1, 4);
     c.p.num_kb = 32;
     for (int ky = 0; ky < 4; ++ky)
-      for (int ch = 0; ch < 8; ++ch) {
+      for (int ch = 0; ch < 8; ++ch) {   // ch = kx*2 + half
         KBlock& k = c.p.kb[ky * 8 + ch];
-        k.src = 0; k.half = 0; k.o0 = (int16_t)(ch * 64); k.o1 = 0; k.o2 = (int16_t)(ky / 2); k.o3 = (int16_t)(ky % 2);
+        k.src = 0; k.half = 0; k.o0 = (int16_t)((ch / 2) * CI + (ch % 2) * 64); k.o1 = 0; k.o2 = (int16_t)(ky / 2); k.o3 = (int16_t)(ky % 2);
       }
     affine_epi(c.p.ep, g->bias2, g->sc2, g->sh2, g->res4, (long long)S4 * S4 * F, (long long)S4 * F, F, 0, 1);
     c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
@@ -855,7 +855,7 @@ extern "C" int wdg_generator_debug_read(const wdg_generator* g, int which, float
   int H, W, C;
   long long sn, sy, sx;
   switch (which) {
-    case 0: H = W = (int)S2; C = 128; sx = 128; sy = (S2 + 2) * 128; sn = (S2 + 2) * sy; src = g->res2p + sy + sx; break;
+    case 0: H = W = (int)S2; C = 128; sx = CATP_PITCH; sy = (S2 + 4) * sx; sn = (S2 + 4) * sy; src = g->catp + 2 * sy + 2 * sx + F / 4; break;
     case 1: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = g->res4; break;
     case 2: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = g->hseq; break;
     case 3: H = W = (int)S4; C = (int)(F / 2); sx = C; sy = S4 * sx; sn = S4 * sy; src = g->g5; break;
