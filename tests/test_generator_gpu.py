@@ -84,6 +84,21 @@ def test_device_and_host_entry_points_agree_bitwise(mk):
     assert np.array_equal(a, b) and np.array_equal(a, c)
 
 
+def test_pipelined_host_path_is_bitwise_equal(mk):
+    """B >= 32 goes through the chunked H2D | forward | D2H pipeline (chunks of 16 + a tail plan)."""
+    import torch
+    from oracle.generator import synthetic_generator_weights
+    B, T, S = 37, 2, 32
+    gen = mk(S, 3, 20, 2, T)
+    gen.set_weights(synthetic_generator_weights(4))
+    image, noise = inputs(B, T, S, 8)
+    host = gen.predict_host(torch.from_numpy(image).pin_memory(), torch.from_numpy(noise).pin_memory()).numpy()
+    dev = gen.forward_device(torch.from_numpy(image).cuda(), torch.from_numpy(noise).cuda()).cpu().numpy()
+    assert np.array_equal(host, dev)
+    again = gen.predict_host(image, noise).numpy()       # pageable buffers, second call
+    assert np.array_equal(again, dev)
+
+
 def test_full_size_properties(mk):
     """BASELINE configs[1] size (64 x 8 x 96 x 96): size-independent properties instead of the oracle.
     (1) sequences are independent: a sequence computed inside the batch of 64 equals the same sequence

@@ -108,6 +108,19 @@ struct WeightDesc {
   }
 };
 
+struct Plan {
+  int B = 0, T = 0;
+  __nv_bfloat16 *xpad, *res4, *hseq, *g5, *catp, *edgeE, *g9;
+  float *cstate, *deltaD;
+  ConvLaunch L0, L2, L5, L7, LE, L9;
+  std::vector<ConvLaunch> LS;  // one per timestep
+  bool use_halo = false;       // halo-reuse kernels (halo_conv.cuh) for the 8x8 s2 conv and the fused upsample conv
+  CUtensorMap hA, hB, h0A, h0B;
+  HaloParams hp, h0p;
+  int hgrid = 0, h0grid = 0;
+  int launches = 0;
+};
+
 struct wdg_generator {
   int S, cin, cnoise, cout, T_default, F;
   int CP;                 // padded input channels of the packed image
@@ -122,20 +135,14 @@ struct wdg_generator {
   float* fparams = nullptr;  // all fp32 per-column vectors, see offsets
   float *bias0, *sc0, *sh0, *bias2, *sc2, *sh2, *biasL, *bias5, *sc5, *sh5, *bias7, *sc7, *sh7, *bias9, *sc9, *sh9,
       *w11, *b11;
-  // plan
-  int B = 0, T = 0;
-  uint8_t* ws = nullptr;
-  __nv_bfloat16 *xpad, *res4, *hseq, *g5, *catp, *edgeE, *g9;
-  float *cstate, *deltaD;
-  float *zero48, *one48;
-  ConvLaunch L0, L2, L5, L7, LE, L9;
-  bool use_halo = false;       // halo-reuse kernels (halo_conv.cuh) for the 8x8 s2 conv and the fused upsample conv
-  CUtensorMap hA, hB, h0A, h0B;
-  HaloParams hp, h0p;
-  int hgrid = 0, h0grid = 0;
-  std::vector<ConvLaunch> LS;  // one per timestep
-  int launches = 0;
+  // plans: [0] = the bound (B, T); [1], [2] = chunk / tail plans used by the pipelined host entry point.
+  // Every plan owns a disjoint region of the caller's workspace, so the zero rings of its padded buffers stay zero.
+  Plan plans[3];
+  int chunk_B = 0, tail_B = 0;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_h2d[2] = {}, ev_fwd[2] = {}, ev_d2h[2] = {};
   FinalConvW<16, 2> w11h;      // final 3x3 conv weights, passed by value (constant bank)
+  float *zero48 = nullptr, *one48 = nullptr;
   // optional per-stage CUDA-event timing (bench.py roofline)
   bool profiling = false;
   cudaEvent_t ev[WDG_NUM_STAGES + 1] = {};
@@ -191,6 +198,13 @@ extern "C" int wdg_generator_create(wdg_generator** out, int image_size, int in_
 extern "C" void wdg_generator_destroy(wdg_generator* g) {
   if (!g) return;
   for (auto& e : g->ev) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (g->ev_h2d[i]) cudaEventDestroy(g->ev_h2d[i]);
+    if (g->ev_fwd[i]) cudaEventDestroy(g->ev_fwd[i]);
+    if (g->ev_d2h[i]) cudaEventDestroy(g->ev_d2h[i]);
+  }
+  if (g->copy_in) cudaStreamDestroy(g->copy_in);
+  if (g->copy_out) cudaStreamDestroy(g->copy_out);
   cudaFree(g->B0); cudaFree(g->B2); cudaFree(g->BL); cudaFree(g->B5); cudaFree(g->B7); cudaFree(g->B9); cudaFree(g->B9h); cudaFree(g->BE);
   cudaFree(g->fparams);
   delete g;
@@ -402,7 +416,7 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
   }
   (void)C;
   g->finalized = true;
-  g->B = 0;  // any previous plan referenced old buffers
+  for (auto& pl : g->plans) pl.B = 0;  // any previous plan referenced old buffers
   return 0;
 }
 
@@ -430,9 +444,18 @@ static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
   return L;
 }
 
+// The pipelined host entry point splits B into chunks of CHUNK_B sequences (plus a tail); each plan gets its own region.
+static const int CHUNK_B = 16;
+static void chunking(int B, int* chunk_B, int* tail_B) {
+  if (B >= 2 * CHUNK_B) { *chunk_B = CHUNK_B; *tail_B = B % CHUNK_B; }
+  else { *chunk_B = 0; *tail_B = 0; }
+}
+
 extern "C" int wdg_generator_workspace_bytes(const wdg_generator* g, int B, int T, size_t* bytes) {
   if (!g || !bytes || B <= 0 || T <= 0) return fail("bad argument");
-  *bytes = ws_layout(g, B, T).total;
+  int cb, tb;
+  chunking(B, &cb, &tb);
+  *bytes = ws_layout(g, B, T).total + (cb ? ws_layout(g, cb, T).total : 0) + (tb ? ws_layout(g, tb, T).total : 0);
   return 0;
 }
 
@@ -459,20 +482,12 @@ static void affine_epi(EpiParams& e, const float* bias, const float* sc, const f
   e.out_mul = 1; e.group_cols = 1 << 30; e.lrelu = lrelu; e.out_f32 = 0;
 }
 
-extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspace_dev, size_t bytes, void* stream_) {
-  if (!g || !workspace_dev || B <= 0 || T <= 0) return fail("bad argument");
-  if (!g->finalized) return fail("wdg_generator_finalize must be called before bind");
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
   const WsLayout L = ws_layout(g, B, T);
-  if (bytes < L.total) return fail("workspace too small");
-  if ((uintptr_t)workspace_dev % 1024) return fail("workspace must be 1024-byte aligned");
-  CK(cudaMemsetAsync(workspace_dev, 0, L.total, stream));
-  uint8_t* ws = (uint8_t*)workspace_dev;
-  g->ws = ws;
-  g->xpad = (__nv_bfloat16*)(ws + L.xpad);
-  g->res4 = (__nv_bfloat16*)(ws + L.res4); g->hseq = (__nv_bfloat16*)(ws + L.hseq);
-  g->cstate = (float*)(ws + L.cstate); g->g5 = (__nv_bfloat16*)(ws + L.g5); g->catp = (__nv_bfloat16*)(ws + L.catp);
-  g->edgeE = (__nv_bfloat16*)(ws + L.edgeE); g->deltaD = (float*)(ws + L.deltaD); g->g9 = (__nv_bfloat16*)(ws + L.g9);
+  pl.xpad = (__nv_bfloat16*)(ws + L.xpad);
+  pl.res4 = (__nv_bfloat16*)(ws + L.res4); pl.hseq = (__nv_bfloat16*)(ws + L.hseq);
+  pl.cstate = (float*)(ws + L.cstate); pl.g5 = (__nv_bfloat16*)(ws + L.g5); pl.catp = (__nv_bfloat16*)(ws + L.catp);
+  pl.edgeE = (__nv_bfloat16*)(ws + L.edgeE); pl.deltaD = (float*)(ws + L.deltaD); pl.g9 = (__nv_bfloat16*)(ws + L.g9);
   const uint64_t N = (uint64_t)B * T, S = g->S, S2 = S / 2, S4 = S / 4, F = g->F, CP = g->CP;
   const int sms = g->sm_count;
   auto grid_for = [&](const ConvParams& p) {
@@ -482,13 +497,13 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
   // dummy map for unused A slots: reuse slot 0
   // ---------------- L0: 8x8 s2 as 4x4 s1 on the s2d image X2 [N][Q][Q][4*CP], Q = (S+6)/2; dims (window 8*CP, X, Y, n)
   {
-    ConvLaunch& c = g->L0;
+    ConvLaunch& c = pl.L0;
     std::memset(&c.p, 0, sizeof c.p);
     const uint64_t Q = (S + 6) / 2, PC = 4 * CP;
     uint64_t dims[5] = {2 * PC, Q, Q, N, 1};
     uint64_t str[4] = {PC, Q * PC, Q * Q * PC, N * Q * Q * PC};
     uint32_t box[5] = {64, 16, 8, 1, 1};
-    if (make_tmap(&c.tmA[0], g->xpad, 5, dims, str, box, 128)) return 1;
+    if (make_tmap(&c.tmA[0], pl.xpad, 5, dims, str, box, 128)) return 1;
     c.tmA[1] = c.tmA[0]; c.tmA[2] = c.tmA[0];
     uint64_t bd[2] = {24 * 64, 128};
     uint64_t bs[1] = {24 * 64};
@@ -504,7 +519,7 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
     // res_2 is written once, as channels 32..159 of the zero-padded concat image `catp` (ring 2): it is read there
     // by the 4x4 s2 conv (through an overlapping-stride window map) and by the fused upsample conv.
     const long long CI = CATP_PITCH, PW = S2 + 4;
-    affine_epi(c.p.ep, g->bias0, g->sc0, g->sh0, g->catp + (2 * PW + 2) * CI, PW * PW * CI, PW * CI, CI, (int)(F / 4), 1);
+    affine_epi(c.p.ep, g->bias0, g->sc0, g->sh0, pl.catp + (2 * PW + 2) * CI, PW * PW * CI, PW * CI, CI, (int)(F / 4), 1);
     c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
     // halo-reuse variant: flat positions of X2 (pitch Q), taps shift by a*Q + 2w rows
     const bool fits = (3 * Q + 2 + H_TILES * TILE_M) <= (uint64_t)H_ROWS;
@@ -513,31 +528,31 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
       uint64_t hd[2] = {2 * PC, flat};
       uint64_t hs[1] = {PC};
       uint32_t hb[2] = {64, H_BOX_ROWS};
-      if (make_tmap(&g->h0A, g->xpad, 2, hd, hs, hb, 128)) return 1;
-      g->h0B = c.tmB;
-      HaloParams& h = g->h0p;
+      if (make_tmap(&pl.h0A, pl.xpad, 2, hd, hs, hb, 128)) return 1;
+      pl.h0B = c.tmB;
+      HaloParams& h = pl.h0p;
       std::memset(&h, 0, sizeof h);
       h.num_passes = (int)((flat + H_TILES * TILE_M - 1) / (H_TILES * TILE_M));
       h.n_img = (int)N; h.pw = (int)Q; h.ph = (int)Q;
       for (int tap = 0; tap < 8; ++tap) h.tap_shift[tap] = (tap / 2) * (int)Q + 2 * (tap % 2);
       h.bias = g->bias0; h.scale = g->sc0; h.shift = g->sh0;
       h.vw = (int)S2; h.vh = (int)S2;
-      h.out1 = g->catp + (2 * PW + 2) * CI + F / 4; h.o1_sn = PW * PW * CI; h.o1_sy = PW * CI; h.o1_sx = CI;
+      h.out1 = pl.catp + (2 * PW + 2) * CI + F / 4; h.o1_sn = PW * PW * CI; h.o1_sy = PW * CI; h.o1_sx = CI;
       h.out2 = nullptr;
-      g->h0grid = h.num_passes < sms ? h.num_passes : sms;
+      pl.h0grid = h.num_passes < sms ? h.num_passes : sms;
     }
-    g->use_halo = fits;
+    pl.use_halo = fits;
   }
   // ---------------- L2: ZeroPadding2D(1) + 4x4 s2 on res_2 = channels 32..159 of catp [N][S2+4][S2+4][192] (ring 2,
   //                  so the pad-1 image starts at (1,1)); dims (window of 4 pixels, ox, oy, row parity, n)
   {
-    ConvLaunch& c = g->L2;
+    ConvLaunch& c = pl.L2;
     std::memset(&c.p, 0, sizeof c.p);
     const uint64_t PW = S2 + 4, CI = CATP_PITCH;
     uint64_t dims[5] = {3 * CI + 128, S4, PW / 2 - 1, 2, N};
     uint64_t str[4] = {2 * CI, 2 * PW * CI, PW * CI, PW * PW * CI};
     uint32_t box[5] = {64, 8, 8, 1, 2};
-    if (make_tmap(&c.tmA[0], g->catp + (PW + 1) * CI + F / 4, 5, dims, str, box, 128)) return 1;
+    if (make_tmap(&c.tmA[0], pl.catp + (PW + 1) * CI + F / 4, 5, dims, str, box, 128)) return 1;
     c.tmA[1] = c.tmA[0]; c.tmA[2] = c.tmA[0];
     uint64_t bd[2] = {32 * 64, 128};
     uint64_t bs[1] = {32 * 64};
@@ -550,7 +565,7 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
         KBlock& k = c.p.kb[ky * 8 + ch];
         k.src = 0; k.half = 0; k.o0 = (int16_t)((ch / 2) * CI + (ch % 2) * 64); k.o1 = 0; k.o2 = (int16_t)(ky / 2); k.o3 = (int16_t)(ky % 2);
       }
-    affine_epi(c.p.ep, g->bias2, g->sc2, g->sh2, g->res4, (long long)S4 * S4 * F, (long long)S4 * F, F, 0, 1);
+    affine_epi(c.p.ep, g->bias2, g->sc2, g->sh2, pl.res4, (long long)S4 * S4 * F, (long long)S4 * F, F, 0, 1);
     c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
   }
   // ---------------- ConvLSTM steps: A maps over (c, x, y, t, b) of res4 (x_t) and hseq (h_{t-1})
@@ -559,15 +574,15 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
     uint64_t dims[5] = {F, S4, S4, (uint64_t)T, (uint64_t)B};
     uint64_t str[4] = {F, S4 * F, S4 * S4 * F, (uint64_t)T * S4 * S4 * F};
     uint32_t box[5] = {64, 8, 8, 1, 2};
-    if (make_tmap(&tmX, g->res4, 5, dims, str, box, 128)) return 1;
-    if (make_tmap(&tmH, g->hseq, 5, dims, str, box, 128)) return 1;
+    if (make_tmap(&tmX, pl.res4, 5, dims, str, box, 128)) return 1;
+    if (make_tmap(&tmH, pl.hseq, 5, dims, str, box, 128)) return 1;
     uint64_t bd[2] = {36 * 64, 4 * F};
     uint64_t bs[1] = {36 * 64};
     uint32_t bb[2] = {64, 256};
     if (make_tmap(&tmB, g->BL, 2, bd, bs, bb, 128)) return 1;
-    g->LS.assign(T, ConvLaunch());
+    pl.LS.assign(T, ConvLaunch());
     for (int t = 0; t < T; ++t) {
-      ConvLaunch& c = g->LS[t];
+      ConvLaunch& c = pl.LS[t];
       std::memset(&c.p, 0, sizeof c.p);
       c.tmA[0] = tmX; c.tmA[1] = tmH; c.tmA[2] = tmX; c.tmB = tmB;
       set_tiles(c.p, (int)S4, (int)S4, B, 8, 8, 2, (int)(4 * F / 256), 4);
@@ -581,7 +596,7 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
       }
       EpiParams& e = c.p.ep;
       std::memset(&e, 0, sizeof e);
-      e.bias = g->biasL; e.c_state = g->cstate; e.h_out = g->hseq;
+      e.bias = g->biasL; e.c_state = pl.cstate; e.h_out = pl.hseq;
       e.h_sn = (long long)T * S4 * S4 * F; e.h_off = (long long)t * S4 * S4 * F;
       e.first_step = t == 0; e.F = (int)F;
       c.bn = 256; c.epi = EPI_LSTM; c.grid = grid_for(c.p);
@@ -589,12 +604,12 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
   }
   // ---------------- L5: 3x3 same 128 -> 64 on hseq (c, x, y, n)
   {
-    ConvLaunch& c = g->L5;
+    ConvLaunch& c = pl.L5;
     std::memset(&c.p, 0, sizeof c.p);
     uint64_t dims[5] = {F, S4, S4, N, 1};
     uint64_t str[4] = {F, S4 * F, S4 * S4 * F, N * S4 * S4 * F};
     uint32_t box[5] = {64, 8, 8, 2, 1};
-    if (make_tmap(&c.tmA[0], g->hseq, 5, dims, str, box, 128)) return 1;
+    if (make_tmap(&c.tmA[0], pl.hseq, 5, dims, str, box, 128)) return 1;
     c.tmA[1] = c.tmA[0]; c.tmA[2] = c.tmA[0];
     uint64_t bd[2] = {18 * 64, F / 2};
     uint64_t bs[1] = {18 * 64};
@@ -607,20 +622,20 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
       const int tap = kb / 2;
       k.src = 0; k.half = 0; k.o0 = (int16_t)((kb % 2) * 64); k.o1 = (int16_t)(tap % 3 - 1); k.o2 = (int16_t)(tap / 3 - 1); k.o3 = 0;
     }
-    affine_epi(c.p.ep, g->bias5, g->sc5, g->sh5, g->g5, (long long)S4 * S4 * (F / 2), (long long)S4 * (F / 2), F / 2, 0, 1);
+    affine_epi(c.p.ep, g->bias5, g->sc5, g->sh5, pl.g5, (long long)S4 * S4 * (F / 2), (long long)S4 * (F / 2), F / 2, 0, 1);
     c.bn = 64; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
   }
   // ---------------- L7: ConvT 2x2 s2 on concat(g5, res4) -> g7 [N][S2][S2][32] (pixel shuffle)
   {
-    ConvLaunch& c = g->L7;
+    ConvLaunch& c = pl.L7;
     std::memset(&c.p, 0, sizeof c.p);
     uint64_t d0[5] = {F / 2, S4, S4, N, 1};
     uint64_t s0[4] = {F / 2, S4 * (F / 2), S4 * S4 * (F / 2), N * S4 * S4 * (F / 2)};
     uint64_t d1[5] = {F, S4, S4, N, 1};
     uint64_t s1[4] = {F, S4 * F, S4 * S4 * F, N * S4 * S4 * F};
     uint32_t box[5] = {64, 8, 8, 2, 1};
-    if (make_tmap(&c.tmA[0], g->g5, 5, d0, s0, box, 128)) return 1;
-    if (make_tmap(&c.tmA[1], g->res4, 5, d1, s1, box, 128)) return 1;
+    if (make_tmap(&c.tmA[0], pl.g5, 5, d0, s0, box, 128)) return 1;
+    if (make_tmap(&c.tmA[1], pl.res4, 5, d1, s1, box, 128)) return 1;
     c.tmA[2] = c.tmA[0];
     uint64_t bd[2] = {3 * 64, 128};
     uint64_t bs[1] = {3 * 64};
@@ -633,21 +648,21 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
       k.src = kb == 0 ? 0 : 1; k.half = 0; k.o0 = (int16_t)(kb <= 1 ? 0 : 64); k.o1 = 0; k.o2 = 0; k.o3 = 0;
     }
     const long long O = F / 4, CI = CATP_PITCH, PW = S2 + 4;
-    affine_epi(c.p.ep, g->bias7, g->sc7, g->sh7, g->catp + (2 * PW + 2) * CI, PW * PW * CI, PW * CI, CI, 0, 1);
+    affine_epi(c.p.ep, g->bias7, g->sc7, g->sh7, pl.catp + (2 * PW + 2) * CI, PW * PW * CI, PW * CI, CI, 0, 1);
     c.p.ep.out_mul = 2; c.p.ep.group_cols = (int)O;
     c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
   }
   // ---------------- LE: border corrections, 1-D 5-tap conv over the 4 edge lines E[N][4][S+8][160] -> D[N][S][4*48] fp32
   {
-    ConvLaunch& c = g->LE;
+    ConvLaunch& c = pl.LE;
     std::memset(&c.p, 0, sizeof c.p);
     const uint64_t I = F / 4 + 128, P = S + 8;
     uint64_t dims[5] = {I, P, 4, N, 1};
     uint64_t str[4] = {I, P * I, 4 * P * I, N * 4 * P * I};
     uint32_t box[5] = {64, 16, 1, 8, 1};
     uint32_t boxh[5] = {32, 16, 1, 8, 1};
-    if (make_tmap(&c.tmA[0], g->edgeE, 5, dims, str, box, 128)) return 1;
-    if (make_tmap(&c.tmA[1], g->edgeE, 5, dims, str, boxh, 64)) return 1;
+    if (make_tmap(&c.tmA[0], pl.edgeE, 5, dims, str, box, 128)) return 1;
+    if (make_tmap(&c.tmA[1], pl.edgeE, 5, dims, str, boxh, 64)) return 1;
     c.tmA[2] = c.tmA[0];
     uint64_t bd[2] = {15 * 64, 192};
     uint64_t bs[1] = {15 * 64};
@@ -661,21 +676,21 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
         KBlock& k = c.p.kb[t * 3 + ch];
         k.src = ch == 2 ? 1 : 0; k.half = ch == 2; k.o0 = (int16_t)(ch * 64); k.o1 = (int16_t)(t + 2); k.o2 = 0; k.o3 = 0;
       }
-    affine_epi(c.p.ep, g->zero48, g->one48, g->zero48, g->deltaD, (long long)S * 192, 0, 192, 0, 0);
+    affine_epi(c.p.ep, g->zero48, g->one48, g->zero48, pl.deltaD, (long long)S * 192, 0, 192, 0, 0);
     c.p.ep.out_f32 = 1;
     c.bn = 48; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
   }
   // ---------------- L9: fused bilinear x2 + ConvT 5x5 on the flattened zero-padded concat image catp
   {
-    ConvLaunch& c = g->L9;
+    ConvLaunch& c = pl.L9;
     std::memset(&c.p, 0, sizeof c.p);
     const uint64_t I = F / 4 + 128, PW = S2 + 4, flat = N * PW * PW, CI = CATP_PITCH;
     uint64_t dims[5] = {I, flat, 1, 1, 1};
     uint64_t str[4] = {CI, flat * CI, flat * CI, flat * CI};
     uint32_t box[5] = {64, 128, 1, 1, 1};
     uint32_t boxh[5] = {32, 128, 1, 1, 1};
-    if (make_tmap(&c.tmA[0], g->catp, 5, dims, str, box, 128)) return 1;
-    if (make_tmap(&c.tmA[1], g->catp, 5, dims, str, boxh, 64)) return 1;
+    if (make_tmap(&c.tmA[0], pl.catp, 5, dims, str, box, 128)) return 1;
+    if (make_tmap(&c.tmA[1], pl.catp, 5, dims, str, boxh, 64)) return 1;
     c.tmA[2] = c.tmA[0];
     uint64_t bd[2] = {48 * 64, 64};
     uint64_t bs[1] = {48 * 64};
@@ -692,28 +707,51 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
       }
     EpiParams& e = c.p.ep;
     std::memset(&e, 0, sizeof e);
-    e.bias = g->bias9; e.scale = g->sc9; e.shift = g->sh9; e.out = g->g9;
-    e.up_pw = (int)PW; e.up_ph = (int)PW; e.up_S = (int)S; e.up_delta = g->deltaD;
+    e.bias = g->bias9; e.scale = g->sc9; e.shift = g->sh9; e.out = pl.g9;
+    e.up_pw = (int)PW; e.up_ph = (int)PW; e.up_S = (int)S; e.up_delta = pl.deltaD;
     c.bn = 64; c.epi = EPI_UPCONV; c.grid = grid_for(c.p);
     // halo-reuse variant (halo_conv.cuh): needs 256 + 3*PW + 3 <= 416 rows of shared memory
-    g->use_halo = g->use_halo && (3 * PW + 3 + H_TILES * TILE_M) <= (uint64_t)H_ROWS && !getenv("WDG_NO_HALO");
-    if (g->use_halo) {
+    pl.use_halo = pl.use_halo && (3 * PW + 3 + H_TILES * TILE_M) <= (uint64_t)H_ROWS && !getenv("WDG_NO_HALO");
+    if (pl.use_halo) {
       uint64_t hd[2] = {CI, flat};
       uint64_t hs[1] = {CI};
       uint32_t hb[2] = {64, H_BOX_ROWS};
-      if (make_tmap(&g->hA, g->catp, 2, hd, hs, hb, 128)) return 1;
-      if (make_tmap(&g->hB, g->B9h, 2, bd, bs, bb, 128)) return 1;
-      HaloParams& h = g->hp;
+      if (make_tmap(&pl.hA, pl.catp, 2, hd, hs, hb, 128)) return 1;
+      if (make_tmap(&pl.hB, g->B9h, 2, bd, bs, bb, 128)) return 1;
+      HaloParams& h = pl.hp;
       std::memset(&h, 0, sizeof h);
       h.num_passes = (int)((flat + H_TILES * TILE_M - 1) / (H_TILES * TILE_M));
-      h.n_img = (int)N; h.pw = (int)PW; h.ph = (int)PW; h.S = (int)S; h.delta = g->deltaD;
+      h.n_img = (int)N; h.pw = (int)PW; h.ph = (int)PW; h.S = (int)S; h.delta = pl.deltaD;
       for (int tap = 0; tap < 16; ++tap) h.tap_shift[tap] = (tap / 4) * (int)PW + tap % 4;
-      h.bias = g->bias9; h.scale = g->sc9; h.shift = g->sh9; h.out = g->g9;
-      g->hgrid = h.num_passes < sms ? h.num_passes : sms;
+      h.bias = g->bias9; h.scale = g->sc9; h.shift = g->sh9; h.out = pl.g9;
+      pl.hgrid = h.num_passes < sms ? h.num_passes : sms;
     }
   }
-  g->B = B; g->T = T;
-  g->launches = 1 + 2 + T + 2 + 2 + 1 + 1;
+  pl.B = B; pl.T = T;
+  pl.launches = 1 + 2 + T + 2 + 2 + 1 + 1;
+  return 0;
+}
+
+
+extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspace_dev, size_t bytes, void* stream_) {
+  if (!g || !workspace_dev || B <= 0 || T <= 0) return fail("bad argument");
+  if (!g->finalized) return fail("wdg_generator_finalize must be called before bind");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  size_t need = 0;
+  if (wdg_generator_workspace_bytes(g, B, T, &need)) return 1;
+  if (bytes < need) return fail("workspace too small");
+  if ((uintptr_t)workspace_dev % 1024) return fail("workspace must be 1024-byte aligned");
+  CK(cudaMemsetAsync(workspace_dev, 0, need, stream));
+  uint8_t* ws = (uint8_t*)workspace_dev;
+  for (auto& pl : g->plans) pl.B = 0;
+  chunking(B, &g->chunk_B, &g->tail_B);
+  if (build_plan(g, g->plans[0], B, T, ws)) return 1;
+  ws += ws_layout(g, B, T).total;
+  if (g->chunk_B) {
+    if (build_plan(g, g->plans[1], g->chunk_B, T, ws)) return 1;
+    ws += ws_layout(g, g->chunk_B, T).total;
+  }
+  if (g->tail_B && build_plan(g, g->plans[2], g->tail_B, T, ws)) return 1;
   return 0;
 }
 
@@ -741,59 +779,64 @@ static int launch_conv(const ConvLaunch& c, cudaStream_t stream) {
   return fail("no kernel instantiated for this BN");
 }
 
-extern "C" int wdg_generator_forward(wdg_generator* g, const float* image_dev, const float* noise_dev, float* out_dev,
-                                     void* stream_) {
-  if (!g || !image_dev || !noise_dev || !out_dev) return fail("null argument");
-  if (g->B == 0) return fail("wdg_generator_bind must be called before forward");
-  cudaStream_t stream = (cudaStream_t)stream_;
-  const long long N = (long long)g->B * g->T, S = g->S;
+static int run_plan(wdg_generator* g, const Plan& pl, const float* image_dev, const float* noise_dev, float* out_dev,
+                    cudaStream_t stream, bool profile) {
+  const long long N = (long long)pl.B * pl.T, S = g->S;
   const long long npix = N * S * S;
   int stage_i = 0;
-  auto mark = [&]() { if (g->profiling) cudaEventRecord(g->ev[stage_i++], stream); };
+  auto mark = [&]() { if (g->profiling && profile) cudaEventRecord(g->ev[stage_i++], stream); };
   mark();
   pack_input_s2d_kernel<<<(unsigned)(N * S), 128, (size_t)S * (g->cin + g->cnoise) * sizeof(float), stream>>>(
-      image_dev, noise_dev, g->xpad, (int)S, g->cin, g->cnoise, g->CP);
+      image_dev, noise_dev, pl.xpad, (int)S, g->cin, g->cnoise, g->CP);
   CK(cudaGetLastError());
   mark();
-  if (g->use_halo) {
+  if (pl.use_halo) {
     auto kern = halo_conv_kernel<128, 3, 8, 1, HEPI_AFFINE>;
     constexpr int smem = HaloCfg<128, 3, 1>::SMEM;
     static bool attr0 = false;
     if (!attr0) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr0 = true; }
-    kern<<<g->h0grid, 224, smem, stream>>>(g->h0A, g->h0B, g->h0p);
+    kern<<<pl.h0grid, 224, smem, stream>>>(pl.h0A, pl.h0B, pl.h0p);
     CK(cudaGetLastError());
-  } else if (launch_conv(g->L0, stream)) return 1;
+  } else if (launch_conv(pl.L0, stream)) return 1;
   mark();
-  if (launch_conv(g->L2, stream)) return 1;
+  if (launch_conv(pl.L2, stream)) return 1;
   mark();
-  for (int t = 0; t < g->T; ++t)
-    if (launch_conv(g->LS[t], stream)) return 1;
+  for (int t = 0; t < pl.T; ++t)
+    if (launch_conv(pl.LS[t], stream)) return 1;
   mark();
-  if (launch_conv(g->L5, stream)) return 1;
+  if (launch_conv(pl.L5, stream)) return 1;
   mark();
-  if (launch_conv(g->L7, stream)) return 1;
+  if (launch_conv(pl.L7, stream)) return 1;
   mark();
   {
     const int CI = g->F / 4 + 128;
     const long long total = N * 4 * (S + 8) * (CI / 8);
-    edge_lines_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(g->catp, g->edgeE, total, (int)(S / 2), CI, CATP_PITCH);
+    edge_lines_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(pl.catp, pl.edgeE, total, (int)(S / 2), CI, CATP_PITCH);
     CK(cudaGetLastError());
-    if (launch_conv(g->LE, stream)) return 1;
+    if (launch_conv(pl.LE, stream)) return 1;
   }
   mark();
-  if (g->use_halo) {
+  if (pl.use_halo) {
     auto kern = halo_conv_kernel<64, 3, 16, 2, HEPI_UPCONV>;
     constexpr int smem = HaloCfg<64, 3, 2>::SMEM;
     static bool attr9 = false;
     if (!attr9) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr9 = true; }
-    kern<<<g->hgrid, 224, smem, stream>>>(g->hA, g->hB, g->hp);
+    kern<<<pl.hgrid, 224, smem, stream>>>(pl.hA, pl.hB, pl.hp);
     CK(cudaGetLastError());
-  } else if (launch_conv(g->L9, stream)) return 1;
+  } else if (launch_conv(pl.L9, stream)) return 1;
   mark();
-  final_conv3x3_kernel<16, 2><<<(unsigned)((npix + 127) / 128), 128, 0, stream>>>(g->g9, g->w11h, out_dev, npix, (int)S);
+  final_conv3x3_kernel<16, 2><<<(unsigned)((npix + 127) / 128), 128, 0, stream>>>(pl.g9, g->w11h, out_dev, npix, (int)S);
   CK(cudaGetLastError());
   mark();
   return 0;
+}
+
+
+extern "C" int wdg_generator_forward(wdg_generator* g, const float* image_dev, const float* noise_dev, float* out_dev,
+                                     void* stream_) {
+  if (!g || !image_dev || !noise_dev || !out_dev) return fail("null argument");
+  if (g->plans[0].B == 0) return fail("wdg_generator_bind must be called before forward");
+  return run_plan(g, g->plans[0], image_dev, noise_dev, out_dev, (cudaStream_t)stream_, true);
 }
 
 extern "C" int wdg_generator_profile(wdg_generator* g, int enable) {
@@ -813,26 +856,70 @@ extern "C" int wdg_generator_stage_ms(wdg_generator* g, float* ms, int n) {
   return 0;
 }
 
+// Host-buffer entry point.  For B >= 2*CHUNK_B the batch is cut into chunks of CHUNK_B sequences and pipelined over
+// three streams: H2D copy of chunk i+1 | forward of chunk i | D2H copy of chunk i-1 (double-buffered staging), so the
+// step costs ~max(PCIe, compute) instead of their sum.  Sequences are independent, so chunking does not change results.
 extern "C" int wdg_generator_predict_host(wdg_generator* g, const float* image_host, const float* noise_host,
                                           float* out_host, void* io_dev, void* stream_) {
   if (!g || !image_host || !noise_host || !out_host || !io_dev) return fail("null argument");
-  if (g->B == 0) return fail("wdg_generator_bind must be called before predict_host");
+  const Plan& full = g->plans[0];
+  if (full.B == 0) return fail("wdg_generator_bind must be called before predict_host");
   cudaStream_t stream = (cudaStream_t)stream_;
-  const size_t px = (size_t)g->B * g->T * g->S * g->S;
-  const size_t b_img = px * g->cin * 4, b_noise = px * g->cnoise * 4, b_out = px * g->cout * 4;
+  const size_t seq_px = (size_t)full.T * g->S * g->S;
+  const size_t s_img = seq_px * g->cin * 4, s_noise = seq_px * g->cnoise * 4, s_out = seq_px * g->cout * 4;
   uint8_t* io = (uint8_t*)io_dev;
-  float* d_img = (float*)io;
-  float* d_noise = (float*)(io + align_up(b_img, 256));
-  float* d_out = (float*)(io + align_up(b_img, 256) + align_up(b_noise, 256));
-  CK(cudaMemcpyAsync(d_img, image_host, b_img, cudaMemcpyHostToDevice, stream));
-  CK(cudaMemcpyAsync(d_noise, noise_host, b_noise, cudaMemcpyHostToDevice, stream));
-  if (wdg_generator_forward(g, d_img, d_noise, d_out, stream_)) return 1;
-  CK(cudaMemcpyAsync(out_host, d_out, b_out, cudaMemcpyDeviceToHost, stream));
+  if (!g->chunk_B) {
+    const size_t b_img = full.B * s_img, b_noise = full.B * s_noise, b_out = full.B * s_out;
+    float* d_img = (float*)io;
+    float* d_noise = (float*)(io + align_up(b_img, 256));
+    float* d_out = (float*)(io + align_up(b_img, 256) + align_up(b_noise, 256));
+    CK(cudaMemcpyAsync(d_img, image_host, b_img, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_noise, noise_host, b_noise, cudaMemcpyHostToDevice, stream));
+    if (run_plan(g, full, d_img, d_noise, d_out, stream, false)) return 1;
+    CK(cudaMemcpyAsync(out_host, d_out, b_out, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  if (!g->copy_in) {
+    CK(cudaStreamCreateWithFlags(&g->copy_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&g->ev_h2d[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&g->ev_fwd[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&g->ev_d2h[i], cudaEventDisableTiming));
+    }
+  }
+  const int cb = g->chunk_B;
+  const size_t slot = align_up(cb * s_img, 256) + align_up(cb * s_noise, 256) + align_up(cb * s_out, 256);
+  // order the side streams after whatever the caller queued on `stream`
+  CK(cudaEventRecord(g->ev_fwd[0], stream));
+  CK(cudaStreamWaitEvent(g->copy_in, g->ev_fwd[0], 0));
+  int i = 0;
+  for (int b0 = 0; b0 < full.B; b0 += cb, ++i) {
+    const int nb = full.B - b0 < cb ? full.B - b0 : cb;
+    const Plan& pl = nb == cb ? g->plans[1] : g->plans[2];
+    const int buf = i & 1;
+    float* d_img = (float*)(io + buf * slot);
+    float* d_noise = (float*)(io + buf * slot + align_up(cb * s_img, 256));
+    float* d_out = (float*)(io + buf * slot + align_up(cb * s_img, 256) + align_up(cb * s_noise, 256));
+    if (i >= 2) CK(cudaStreamWaitEvent(g->copy_in, g->ev_fwd[buf], 0));       // inputs of chunk i-2 consumed
+    CK(cudaMemcpyAsync(d_img, (const uint8_t*)image_host + b0 * s_img, nb * s_img, cudaMemcpyHostToDevice, g->copy_in));
+    CK(cudaMemcpyAsync(d_noise, (const uint8_t*)noise_host + b0 * s_noise, nb * s_noise, cudaMemcpyHostToDevice, g->copy_in));
+    CK(cudaEventRecord(g->ev_h2d[buf], g->copy_in));
+    CK(cudaStreamWaitEvent(stream, g->ev_h2d[buf], 0));
+    if (i >= 2) CK(cudaStreamWaitEvent(stream, g->ev_d2h[buf], 0));          // output of chunk i-2 copied out
+    if (run_plan(g, pl, d_img, d_noise, d_out, stream, false)) return 1;
+    CK(cudaEventRecord(g->ev_fwd[buf], stream));
+    CK(cudaStreamWaitEvent(g->copy_out, g->ev_fwd[buf], 0));
+    CK(cudaMemcpyAsync((uint8_t*)out_host + b0 * s_out, d_out, nb * s_out, cudaMemcpyDeviceToHost, g->copy_out));
+    CK(cudaEventRecord(g->ev_d2h[buf], g->copy_out));
+  }
+  CK(cudaStreamSynchronize(g->copy_out));
   CK(cudaStreamSynchronize(stream));
   return 0;
 }
 
-extern "C" int wdg_generator_launches_per_forward(const wdg_generator* g) { return g ? g->launches : 0; }
+extern "C" int wdg_generator_launches_per_forward(const wdg_generator* g) { return g ? g->plans[0].launches : 0; }
 
 // --------------------------------------------------------------- debug
 __global__ void bf16_to_f32_strided(const __nv_bfloat16* src, float* dst, long long n_img, int H, int W, int C,
@@ -849,18 +936,19 @@ __global__ void bf16_to_f32_strided(const __nv_bfloat16* src, float* dst, long l
 }
 
 extern "C" int wdg_generator_debug_read(const wdg_generator* g, int which, float* host_out, int64_t count) {
-  if (!g || g->B == 0 || !host_out) return fail("bad argument");
-  const long long N = (long long)g->B * g->T, S = g->S, S2 = S / 2, S4 = S / 4, F = g->F;
+  if (!g || g->plans[0].B == 0 || !host_out) return fail("bad argument");
+  const Plan& pl = g->plans[0];
+  const long long N = (long long)pl.B * pl.T, S = g->S, S2 = S / 2, S4 = S / 4, F = g->F;
   const __nv_bfloat16* src;
   int H, W, C;
   long long sn, sy, sx;
   switch (which) {
-    case 0: H = W = (int)S2; C = 128; sx = CATP_PITCH; sy = (S2 + 4) * sx; sn = (S2 + 4) * sy; src = g->catp + 2 * sy + 2 * sx + F / 4; break;
-    case 1: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = g->res4; break;
-    case 2: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = g->hseq; break;
-    case 3: H = W = (int)S4; C = (int)(F / 2); sx = C; sy = S4 * sx; sn = S4 * sy; src = g->g5; break;
-    case 4: H = W = (int)S2; C = (int)(F / 4); sx = CATP_PITCH; sy = (S2 + 4) * sx; sn = (S2 + 4) * sy; src = g->catp + 2 * sy + 2 * sx; break;
-    case 5: H = W = (int)S; C = (int)(F / 8); sx = C; sy = S * sx; sn = S * sy; src = g->g9; break;
+    case 0: H = W = (int)S2; C = 128; sx = CATP_PITCH; sy = (S2 + 4) * sx; sn = (S2 + 4) * sy; src = pl.catp + 2 * sy + 2 * sx + F / 4; break;
+    case 1: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = pl.res4; break;
+    case 2: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = pl.hseq; break;
+    case 3: H = W = (int)S4; C = (int)(F / 2); sx = C; sy = S4 * sx; sn = S4 * sy; src = pl.g5; break;
+    case 4: H = W = (int)S2; C = (int)(F / 4); sx = CATP_PITCH; sy = (S2 + 4) * sx; sn = (S2 + 4) * sy; src = pl.catp + 2 * sy + 2 * sx; break;
+    case 5: H = W = (int)S; C = (int)(F / 8); sx = C; sy = S * sx; sn = S * sy; src = pl.g9; break;
     default: return fail("unknown intermediate");
   }
   const long long total = N * H * W * C;
