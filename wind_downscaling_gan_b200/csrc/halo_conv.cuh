@@ -5,10 +5,11 @@
 // tap_shift[t] (= dy * pitch + dx).  So the A operand of every tap is the same block of shared memory:
 //
 //   pass  = 256 consecutive flat positions (2 GEMM tiles)
-//   A     = NCHUNK channel chunks x 416 rows x 128 B (SWIZZLE_128B), loaded ONCE per pass by two TMA boxes per
-//           chunk; the operand of (tile, tap) is the plain UMMA descriptor that starts `tile*128 + shift` rows into
-//           the chunk buffer -- SWIZZLE_128B is applied on absolute smem address bits, so any 128-byte row of the
-//           1024-byte aligned buffer is a valid start (verified on B200)
+//   A     = per channel chunk 416 rows x 128 B (SWIZZLE_128B), loaded ONCE per pass by two TMA boxes into a
+//           2-deep ring (K order is chunk-major, so chunk c+1 streams in while chunk c is consumed); the operand
+//           of (tile, tap) is the plain UMMA descriptor that starts `tile*128 + shift` rows into the chunk buffer
+//           -- SWIZZLE_128B is applied on absolute smem address bits, so any 128-byte row of the 1024-byte
+//           aligned buffer is a valid start (verified on B200)
 //   B     = packed weights [BN][NCHUNK*NTAP*64] (K-block = chunk*NTAP + tap), streamed through a ring of
 //           TPS-tap stages; each stage feeds both tiles (2*4*TPS MMAs per barrier round trip)
 //   D     = 2 tiles x BN fp32 columns in TMEM, double buffered
@@ -47,11 +48,12 @@ constexpr int H_TILES = 2;
 constexpr int H_ROWS = 416;                      // 256 + max tap shift (<= 160), two TMA boxes of 208 rows
 constexpr int H_BOX_ROWS = 208;
 constexpr int H_A_BYTES = H_ROWS * 128;          // one channel chunk
+constexpr int H_ABUFS = 2;                       // A ring depth (chunks in flight)
 
 template <int BN, int NCHUNK, int TPS>
 struct HaloCfg {
   static constexpr int B_STAGE_BYTES = TPS * BN * 128;
-  static constexpr int A_BYTES = NCHUNK * H_A_BYTES;
+  static constexpr int A_BYTES = H_ABUFS * H_A_BYTES;
   static constexpr int BSTAGES = (226 * 1024 - 1024 - 512 - A_BYTES) / B_STAGE_BYTES > 8
                                      ? 8 : (226 * 1024 - 1024 - 512 - A_BYTES) / B_STAGE_BYTES;
   static constexpr int SMEM = A_BYTES + BSTAGES * B_STAGE_BYTES + 1024 + 512;
@@ -72,9 +74,9 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smA = smem;
   uint8_t* smB = smem + Cfg::A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smB + BSTAGES * Cfg::B_STAGE_BYTES);
-  uint64_t* a_full = bars;                      // [NCHUNK]
-  uint64_t* a_empty = a_full + NCHUNK;          // [NCHUNK]
-  uint64_t* b_full = a_empty + NCHUNK;          // [BSTAGES]
+  uint64_t* a_full = bars;                      // [H_ABUFS]
+  uint64_t* a_empty = a_full + H_ABUFS;         // [H_ABUFS]
+  uint64_t* b_full = a_empty + H_ABUFS;         // [BSTAGES]
   uint64_t* b_empty = b_full + BSTAGES;         // [BSTAGES]
   uint64_t* tfull = b_empty + BSTAGES;          // [2]
   uint64_t* tempty = tfull + 2;                 // [2]
@@ -86,7 +88,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    for (int i = 0; i < NCHUNK; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < H_ABUFS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < BSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     fence_mbar_init();
@@ -99,20 +101,21 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   // Producer / MMA loops run warp-uniformly; one elected lane issues the TMA / tcgen05 instructions.
   if (warp == 0) {
-    // ================================================= A producer: NCHUNK buffers, one fill per pass
+    // ================================================= A producer: ring over (pass, chunk)
+    int ab = 0;
     uint32_t phase = 0;
     for (int pass = blockIdx.x; pass < p.num_passes; pass += gridDim.x) {
       const int f0 = pass * (H_TILES * TILE_M);
       for (int c = 0; c < NCHUNK; ++c) {
-        mbar_wait(&a_empty[c], phase ^ 1);
+        mbar_wait(&a_empty[ab], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&a_full[c], H_A_BYTES);
-          tma_load_2d(smA + c * H_A_BYTES, &tmA, &a_full[c], c * 64, f0);
-          tma_load_2d(smA + c * H_A_BYTES + H_BOX_ROWS * 128, &tmA, &a_full[c], c * 64, f0 + H_BOX_ROWS);
+          mbar_arrive_expect_tx(&a_full[ab], H_A_BYTES);
+          tma_load_2d(smA + ab * H_A_BYTES, &tmA, &a_full[ab], c * 64, f0);
+          tma_load_2d(smA + ab * H_A_BYTES + H_BOX_ROWS * 128, &tmA, &a_full[ab], c * 64, f0 + H_BOX_ROWS);
         }
         __syncwarp();
+        if (++ab == H_ABUFS) { ab = 0; phase ^= 1; }
       }
-      phase ^= 1;
     }
   } else if (warp == 6) {
     // ================================================= B producer: ring over (pass, stage of TPS K-blocks)
@@ -134,7 +137,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ================================================= MMA issuer
     constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
-    int stage = 0;
+    int stage = 0, ab = 0;
     uint32_t bphase = 0, aphase = 0, tphase = 0;
     int as = 0;
     for (int pass = blockIdx.x; pass < p.num_passes; pass += gridDim.x) {
@@ -142,9 +145,9 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * (H_TILES * BN);
       for (int c = 0; c < NCHUNK; ++c) {
-        mbar_wait(&a_full[c], aphase);
+        mbar_wait(&a_full[ab], aphase);
         tc_fence_after();
-        const uint64_t a_desc0 = umma_desc_kmajor(smem_u32(smA + c * H_A_BYTES), 128u);
+        const uint64_t a_desc0 = umma_desc_kmajor(smem_u32(smA + ab * H_A_BYTES), 128u);
         for (int g = 0; g < NTAP / TPS; ++g) {
           mbar_wait(&b_full[stage], bphase);
           tc_fence_after();
@@ -165,15 +168,15 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             umma_commit(&b_empty[stage]);
             if (g == NTAP / TPS - 1) {
-              umma_commit(&a_empty[c]);
+              umma_commit(&a_empty[ab]);
               if (c == NCHUNK - 1) umma_commit(&tfull[as]);
             }
           }
           __syncwarp();
           if (++stage == BSTAGES) { stage = 0; bphase ^= 1; }
         }
+        if (++ab == H_ABUFS) { ab = 0; aphase ^= 1; }
       }
-      aphase ^= 1;
       if (++as == 2) { as = 0; tphase ^= 1; }
     }
   } else {

@@ -791,8 +791,8 @@ static int run_plan(wdg_generator* g, const Plan& pl, const float* image_dev, co
   CK(cudaGetLastError());
   mark();
   if (pl.use_halo) {
-    auto kern = halo_conv_kernel<128, 3, 8, 1, HEPI_AFFINE>;
-    constexpr int smem = HaloCfg<128, 3, 1>::SMEM;
+    auto kern = halo_conv_kernel<128, 3, 8, 2, HEPI_AFFINE>;
+    constexpr int smem = HaloCfg<128, 3, 2>::SMEM;
     static bool attr0 = false;
     if (!attr0) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr0 = true; }
     kern<<<pl.h0grid, 224, smem, stream>>>(pl.h0A, pl.h0B, pl.h0p);
@@ -817,8 +817,8 @@ static int run_plan(wdg_generator* g, const Plan& pl, const float* image_dev, co
   }
   mark();
   if (pl.use_halo) {
-    auto kern = halo_conv_kernel<64, 3, 16, 2, HEPI_UPCONV>;
-    constexpr int smem = HaloCfg<64, 3, 2>::SMEM;
+    auto kern = halo_conv_kernel<64, 3, 16, 4, HEPI_UPCONV>;
+    constexpr int smem = HaloCfg<64, 3, 4>::SMEM;
     static bool attr9 = false;
     if (!attr9) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr9 = true; }
     kern<<<pl.hgrid, 224, smem, stream>>>(pl.hA, pl.hB, pl.hp);
