@@ -112,6 +112,52 @@ int wdg_stitch(const float* pred_dev, const int* starts_x_dev, int nx, const int
                int seq, int img, int crop, int channels, const int* rows_dev, int nrows, const int* cols_dev, int ncols,
                float* out_dev, void* stream);
 
+/* ---- fp32 building blocks of the WGAN training step (ganbase.py:21-94): critic forward/backward, training-mode
+ * generator, optimiser.  Channels-last fp32 device tensors; `*_cs` / `*_co` = channel stride / offset of a tensor
+ * inside a wider (concatenated) buffer.  geo[16] = {N, H, W, Ci, kh, kw, Co, stride, pad_top, pad_left, Ho, Wo,
+ * x_cs, x_co, y_cs, y_co}; weights are HWIO (a Conv2DTranspose kernel (kh,kw,out,in) is the HWIO kernel of the
+ * convolution it transposes, so its forward is wdg_conv2d_bwd_data). */
+int wdg_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, const int* geo, int accumulate, void* stream);
+int wdg_conv2d_bwd_data(const float* dy, const float* w, float* dx, const int* geo, int accumulate, void* stream);
+int wdg_conv2d_bwd_weight_scratch(const int* geo, size_t* bytes, int* splits);
+int wdg_conv2d_bwd_weight(const float* x, const float* dy, float* dw, const int* geo, void* scratch, int accumulate, void* stream);
+/* out[C] (+)= column sums over R rows; mode 0: a, 1: a*b, 2: a*a; scratch >= 64*C floats */
+int wdg_colsum(int mode, const float* a, int a_cs, int a_co, const float* b, int b_cs, int b_co, long long R, int C, float* out,
+               void* scratch, int accumulate, void* stream);
+int wdg_leaky_relu_fwd(float* x, long long n, float alpha, void* stream);
+int wdg_leaky_relu_bwd(float* dy, const float* y, long long n, float alpha, void* stream);
+int wdg_axpby(float* out, int o_cs, int o_co, const float* x, int x_cs, int x_co, float a, const float* y, int y_cs, int y_co,
+              float b, long long rows, int C, int accumulate, void* stream);
+int wdg_lerp_batch(float* out, const float* real, const float* fake, const float* eps, long long per_sample, long long n, void* stream);
+/* BatchNormalization (axis -1, eps, momentum): training mode uses batch statistics and updates the moving ones */
+int wdg_bn_train_fwd(const float* x, float* y, const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                     float* save_mean, float* save_invstd, long long rows, int C, float eps, float momentum, void* scratch, void* stream);
+int wdg_bn_infer(const float* x, float* y, const float* gamma, const float* beta, const float* mean, const float* var,
+                 long long rows, int C, float eps, void* scratch, void* stream);
+int wdg_bn_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
+                     float* dx, float* dgamma, float* dbeta, long long rows, int C, void* scratch, void* stream);
+/* LayerNormalization over the channel axis */
+int wdg_ln_fwd(const float* x, float* y, int y_cs, int y_co, const float* gamma, const float* beta, float* save_mean,
+               float* save_invstd, long long rows, int C, float eps, void* stream);
+int wdg_ln_bwd(const float* dy, int dy_cs, int dy_co, const float* x, const float* gamma, const float* save_mean,
+               const float* save_invstd, float* dx, float* dgamma, float* dbeta, long long rows, int C, void* scratch, void* stream);
+/* ConvLSTM2D gate math (gates i, f, c~, o; hard_sigmoid / tanh), one timestep */
+int wdg_lstm_gates_fwd(float* z, const float* c_prev, float* c_out, float* h_out, long long rows, int F, void* stream);
+int wdg_lstm_gates_bwd(float* gates, const float* c_prev, const float* c_cur, const float* dh, float* dc, long long rows, int F, void* stream);
+/* UpSampling2D(2, bilinear) and its adjoint */
+int wdg_upsample2x_fwd(const float* x, float* y, long long n_img, int h, int w, int C, void* stream);
+int wdg_upsample2x_bwd(const float* dy, float* dx, long long n_img, int h, int w, int C, void* stream);
+/* TimeDistributed(Dense(1)) + GlobalAveragePooling1D and their backward */
+int wdg_dense_mean_fwd(const float* flat, const float* w, const float* bias, float* score, int B, int T, int D, void* stream);
+int wdg_dense_mean_bwd(const float* dscore, const float* flat, const float* w, float* dflat, float* dw, float* dbias, int B, int T, int D, void* stream);
+/* out[0] = scale * sum(a | a*b | a*a); scratch >= 1024 doubles */
+int wdg_reduce(int mode, const float* a, const float* b, long long n, double scale, float* out, void* scratch, void* stream);
+/* gradient-penalty norms (ganbase.py:36): out[b*C+c] = sqrt(sum over (T,H,W) of g^2) */
+int wdg_gp_norm(const float* g, float* out, int B, long long per_sample_px, int C, void* stream);
+/* Keras Adam step (epsilon outside the square root) and one TFA SpectralNormalization power iteration (in place) */
+int wdg_adam(float* w, float* m, float* v, const float* g, long long n, float lr_t, float b1, float b2, float eps, void* stream);
+int wdg_sn_update(float* w, float* u, int R, int C, void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

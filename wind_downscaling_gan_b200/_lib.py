@@ -43,6 +43,34 @@ def _declare(lib):
         "wdg_gather_normalise": [vp, vp, vp, i, i, i, vp, i, vp, i, i, i, vp, vp, vp, vp, vp],
         "wdg_stitch": [vp, vp, i, vp, i, i, i, i, i, i, vp, i, vp, i, vp, vp],
     }
+    ll, f, d = C.c_longlong, C.c_float, C.c_double
+    ip = C.POINTER(i)
+    sigs.update({
+        "wdg_conv2d_fwd": [vp, vp, vp, vp, ip, i, vp],
+        "wdg_conv2d_bwd_data": [vp, vp, vp, ip, i, vp],
+        "wdg_conv2d_bwd_weight_scratch": [ip, C.POINTER(sz), ip],
+        "wdg_conv2d_bwd_weight": [vp, vp, vp, ip, vp, i, vp],
+        "wdg_colsum": [i, vp, i, i, vp, i, i, ll, i, vp, vp, i, vp],
+        "wdg_leaky_relu_fwd": [vp, ll, f, vp],
+        "wdg_leaky_relu_bwd": [vp, vp, ll, f, vp],
+        "wdg_axpby": [vp, i, i, vp, i, i, f, vp, i, i, f, ll, i, i, vp],
+        "wdg_lerp_batch": [vp, vp, vp, vp, ll, ll, vp],
+        "wdg_bn_train_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, ll, i, f, f, vp, vp],
+        "wdg_bn_infer": [vp, vp, vp, vp, vp, vp, ll, i, f, vp, vp],
+        "wdg_bn_train_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, ll, i, vp, vp],
+        "wdg_ln_fwd": [vp, vp, i, i, vp, vp, vp, vp, ll, i, f, vp],
+        "wdg_ln_bwd": [vp, i, i, vp, vp, vp, vp, vp, vp, vp, ll, i, vp, vp],
+        "wdg_lstm_gates_fwd": [vp, vp, vp, vp, ll, i, vp],
+        "wdg_lstm_gates_bwd": [vp, vp, vp, vp, vp, ll, i, vp],
+        "wdg_upsample2x_fwd": [vp, vp, ll, i, i, i, vp],
+        "wdg_upsample2x_bwd": [vp, vp, ll, i, i, i, vp],
+        "wdg_dense_mean_fwd": [vp, vp, vp, vp, i, i, i, vp],
+        "wdg_dense_mean_bwd": [vp, vp, vp, vp, vp, vp, i, i, i, vp],
+        "wdg_reduce": [i, vp, vp, ll, d, vp, vp, vp],
+        "wdg_gp_norm": [vp, vp, i, ll, i, vp],
+        "wdg_adam": [vp, vp, vp, vp, ll, f, f, f, f, vp],
+        "wdg_sn_update": [vp, vp, i, i, vp, vp],
+    })
     for name, args in sigs.items():
         if not hasattr(lib, name):
             continue

@@ -1,0 +1,771 @@
+// fp32 building blocks of the WGAN training step (critic forward/backward, training-mode generator, optimiser):
+// convolution forward / backward-data / backward-weight as implicit GEMMs on CUDA cores, normalisation layers,
+// ConvLSTM gate math, bilinear resize and its adjoint, reductions, Adam, spectral normalisation.
+//
+// These are the first, correctness-oriented kernels of SURVEY.md §8 rows A14-A16 (the inference path uses the
+// tcgen05 kernels in conv_umma.cuh / halo_conv.cuh).  All tensors are fp32 channels-last; `cs`/`co` arguments are
+// the channel stride / offset of a tensor inside a wider (concatenated) buffer.
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "../../include/wdg.h"
+
+extern int wdg_set_error(const std::string& m);
+
+#define CKT(call)                                                                                    \
+  do {                                                                                               \
+    cudaError_t _e = (call);                                                                         \
+    if (_e != cudaSuccess) return wdg_set_error(std::string(#call) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+namespace {
+
+struct ConvGeo {
+  int N, H, W, Ci, kh, kw, Co, stride, pad_t, pad_l, Ho, Wo;
+  int x_cs, x_co;   // channel stride / offset of x (input side, Ci channels)
+  int y_cs, y_co;   // channel stride / offset of y (output side, Co channels)
+};
+
+// ------------------------------------------------------------------ implicit GEMM on CUDA cores
+// C[M][N] (+)= sum_k A(m,k) * B(k,n); 64x64 block tile, 16-deep K tiles, 256 threads x (4x4) outputs.
+constexpr int TM = 64, TN = 64, TK = 16;
+
+struct FwdProblem {       // y = conv(x, w) + bias
+  ConvGeo g; const float* x; const float* w; const float* bias; float* y; int accumulate;
+  __device__ int M() const { return g.N * g.Ho * g.Wo; }
+  __device__ int Nn() const { return g.Co; }
+  __device__ int K() const { return g.kh * g.kw * g.Ci; }
+  __device__ float A(int m, int k) const {
+    const int ci = k % g.Ci, tap = k / g.Ci, kx = tap % g.kw, ky = tap / g.kw;
+    const int ox = m % g.Wo, oy = (m / g.Wo) % g.Ho, n = m / (g.Wo * g.Ho);
+    const int iy = oy * g.stride - g.pad_t + ky, ix = ox * g.stride - g.pad_l + kx;
+    if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) return 0.f;
+    return x[(((long long)n * g.H + iy) * g.W + ix) * g.x_cs + g.x_co + ci];
+  }
+  __device__ float B(int k, int n) const { return w[(long long)k * g.Co + n]; }
+  __device__ void store(int m, int n, float v) const {
+    float* p = y + (long long)m * g.y_cs + g.y_co + n;
+    if (bias) v += bias[n];
+    *p = accumulate ? *p + v : v;
+  }
+};
+
+struct BwdDataProblem {   // dx = conv_bwd_data(dy, w)
+  ConvGeo g; const float* dy; const float* w; float* dx; int accumulate;
+  __device__ int M() const { return g.N * g.H * g.W; }
+  __device__ int Nn() const { return g.Ci; }
+  __device__ int K() const { return g.kh * g.kw * g.Co; }
+  __device__ float A(int m, int k) const {
+    const int co = k % g.Co, tap = k / g.Co, kx = tap % g.kw, ky = tap / g.kw;
+    const int ix = m % g.W, iy = (m / g.W) % g.H, n = m / (g.W * g.H);
+    const int ty = iy + g.pad_t - ky, tx = ix + g.pad_l - kx;
+    if (ty < 0 || tx < 0 || ty % g.stride || tx % g.stride) return 0.f;
+    const int oy = ty / g.stride, ox = tx / g.stride;
+    if (oy >= g.Ho || ox >= g.Wo) return 0.f;
+    return dy[(((long long)n * g.Ho + oy) * g.Wo + ox) * g.y_cs + g.y_co + co];
+  }
+  __device__ float B(int k, int n) const {   // w[ky][kx][ci = n][co]
+    const int co = k % g.Co, tap = k / g.Co;
+    return w[((long long)tap * g.Ci + n) * g.Co + co];
+  }
+  __device__ void store(int m, int n, float v) const {
+    float* p = dx + (long long)m * g.x_cs + g.x_co + n;
+    *p = accumulate ? *p + v : v;
+  }
+};
+
+struct BwdWeightProblem {  // dw[tap][ci][co] = sum over pixels x * dy; split over K (pixels) into partial buffers
+  ConvGeo g; const float* x; const float* dy; float* part; int k_per_split;
+  __device__ int M() const { return g.kh * g.kw * g.Ci; }
+  __device__ int Nn() const { return g.Co; }
+  __device__ int K() const { return g.N * g.Ho * g.Wo; }
+  __device__ float A(int m, int k) const {
+    const int ci = m % g.Ci, tap = m / g.Ci, kx = tap % g.kw, ky = tap / g.kw;
+    const int ox = k % g.Wo, oy = (k / g.Wo) % g.Ho, n = k / (g.Wo * g.Ho);
+    const int iy = oy * g.stride - g.pad_t + ky, ix = ox * g.stride - g.pad_l + kx;
+    if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) return 0.f;
+    return x[(((long long)n * g.H + iy) * g.W + ix) * g.x_cs + g.x_co + ci];
+  }
+  __device__ float B(int k, int n) const { return dy[(long long)k * g.y_cs + g.y_co + n]; }
+};
+
+template <class P>
+__device__ __forceinline__ void gemm_tile(const P& p, int m0, int n0, int k_begin, int k_end, float (&acc)[4][4]) {
+  __shared__ float sA[TK][TM + 4];
+  __shared__ float sB[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int tm = (tid / 16) * 4, tn = (tid % 16) * 4;
+  const int M = p.M(), N = p.Nn();
+  for (int k0 = k_begin; k0 < k_end; k0 += TK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {            // A tile: 64 x 16, consecutive threads along m (or k) for coalescing
+      const int e = tid + i * 256;
+      const int mm = e % TM, kk = e / TM;
+      const int m = m0 + mm, k = k0 + kk;
+      sA[kk][mm] = (m < M && k < k_end) ? p.A(m, k) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {            // B tile: 16 x 64
+      const int e = tid + i * 256;
+      const int nn = e % TN, kk = e / TN;
+      const int n = n0 + nn, k = k0 + kk;
+      sB[kk][nn] = (n < N && k < k_end) ? p.B(k, n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sA[kk][tm + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sB[kk][tn + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+}
+
+template <class P>
+__global__ void __launch_bounds__(256) gemm_kernel(P p) {
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+  float acc[4][4] = {};
+  gemm_tile(p, m0, n0, 0, p.K(), acc);
+  const int tm = (threadIdx.x / 16) * 4, tn = (threadIdx.x % 16) * 4;
+  const int M = p.M(), N = p.Nn();
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (m0 + tm + i < M && n0 + tn + j < N) p.store(m0 + tm + i, n0 + tn + j, acc[i][j]);
+}
+
+__global__ void __launch_bounds__(256) gemm_wgrad_kernel(BwdWeightProblem p) {
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN, split = blockIdx.z;
+  const int K = p.K();
+  const int kb = split * p.k_per_split, ke = min(K, kb + p.k_per_split);
+  float acc[4][4] = {};
+  gemm_tile(p, m0, n0, kb, ke, acc);
+  const int tm = (threadIdx.x / 16) * 4, tn = (threadIdx.x % 16) * 4;
+  const int M = p.M(), N = p.Nn();
+  float* out = p.part + (long long)split * M * N;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (m0 + tm + i < M && n0 + tn + j < N) out[(long long)(m0 + tm + i) * N + n0 + tn + j] = acc[i][j];
+}
+
+// dst[i] (+)= sum_s part[s][i]   (fixed order: deterministic)
+__global__ void reduce_splits_kernel(const float* __restrict__ part, float* __restrict__ dst, long long n, int splits,
+                                     int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += part[(long long)k * n + i];
+  dst[i] = accumulate ? dst[i] + s : s;
+}
+
+// ------------------------------------------------------------------ column reductions over rows of [R][cs] (+co)
+// out[c] (+)= sum_r f(row r, channel c).  One block per 32 channels x row-slab; two-stage via partials.
+template <int MODE>   // 0: sum a   1: sum a*b   2: sum a*a
+__global__ void colsum_partial_kernel(const float* __restrict__ a, int a_cs, int a_co, const float* __restrict__ b, int b_cs,
+                                      int b_co, long long R, int C, float* __restrict__ part) {
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long long rows_per = (R + gridDim.y - 1) / gridDim.y;
+  const long long r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  float s = 0.f;
+  if (c < C)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float av = a[r * a_cs + a_co + c];
+      if (MODE == 0) s += av;
+      else if (MODE == 1) s += av * b[r * b_cs + b_co + c];
+      else s += av * av;
+    }
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    part[(long long)blockIdx.y * C + c] = t;
+  }
+}
+
+// ------------------------------------------------------------------ elementwise helpers
+__global__ void leaky_fwd_kernel(float* __restrict__ x, long long n, float alpha) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float v = x[i]; x[i] = v >= 0.f ? v : alpha * v; }
+}
+// dx = dy * (y >= 0 ? 1 : alpha), in place on dy; y is the activation OUTPUT (same sign as its input)
+__global__ void leaky_bwd_kernel(float* __restrict__ dy, const float* __restrict__ y, long long n, float alpha) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && y[i] < 0.f) dy[i] *= alpha;
+}
+// out = a*x + b*y (y may be null), with channel stride/offset on every operand: generic strided copy / axpby
+__global__ void axpby_kernel(float* __restrict__ out, int o_cs, int o_co, const float* __restrict__ x, int x_cs, int x_co,
+                             float a, const float* __restrict__ y, int y_cs, int y_co, float b, long long rows, int C,
+                             int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const long long r = i / C;
+  const int c = (int)(i % C);
+  float v = a * x[r * x_cs + x_co + c];
+  if (y) v += b * y[r * y_cs + y_co + c];
+  float* o = out + r * o_cs + o_co + c;
+  *o = accumulate ? *o + v : v;
+}
+// combined[b,...] = eps[b]*real + (1-eps[b])*fake   (ganbase.py:31)
+__global__ void lerp_batch_kernel(float* __restrict__ out, const float* __restrict__ real, const float* __restrict__ fake,
+                                  const float* __restrict__ eps, long long per_sample, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float e = eps[i / per_sample];
+  out[i] = e * real[i] + (1.f - e) * fake[i];
+}
+
+// ------------------------------------------------------------------ BatchNorm (training) / LayerNorm
+// y = (x - mean[c]) * invstd[c] * gamma[c] + beta[c]   (mean/invstd supplied: batch or moving statistics)
+__global__ void bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ mean,
+                                const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, long long rows, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const int c = (int)(i % C);
+  y[i] = (x[i] - mean[c]) * invstd[c] * gamma[c] + beta[c];
+}
+// stats from sums: mean = s1/R, var = s2/R - mean^2 (biased); moving stats update (momentum, Bessel-corrected var)
+__global__ void bn_finalize_kernel(const float* __restrict__ s1, const float* __restrict__ s2, long long R, int C, float eps,
+                                   float momentum, float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = (double)s1[c] / (double)R;
+  double v = (double)s2[c] / (double)R - m * m;
+  if (v < 0) v = 0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(v + (double)eps));
+  if (moving_mean) {
+    moving_mean[c] = moving_mean[c] * momentum + (float)m * (1.f - momentum);
+    moving_var[c] = moving_var[c] * momentum + (float)(v * ((double)R / (double)(R - 1))) * (1.f - momentum);
+  }
+}
+// dx = gamma*invstd*(dy - mean(dy) - xhat*mean(dy*xhat)), with sums dbeta = sum dy, dgamma = sum dy*xhat supplied
+__global__ void bn_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                              const float* __restrict__ invstd, const float* __restrict__ gamma,
+                              const float* __restrict__ dbeta, const float* __restrict__ dgamma, float* __restrict__ dx,
+                              long long rows, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const int c = (int)(i % C);
+  const float xhat = (x[i] - mean[c]) * invstd[c];
+  const float inv_r = 1.f / (float)rows;
+  dx[i] = gamma[c] * invstd[c] * (dy[i] - dbeta[c] * inv_r - xhat * dgamma[c] * inv_r);
+}
+// xhat-weighted sum needs xhat: dgamma[c] = sum dy * (x - mean) * invstd -> computed as colsum(dy * xhat) via this map
+__global__ void bn_xhat_mul_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                                   const float* __restrict__ invstd, float* __restrict__ out, long long rows, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const int c = (int)(i % C);
+  out[i] = dy[i] * (x[i] - mean[c]) * invstd[c];
+}
+
+// LayerNorm over the channel axis (C <= 1024), one warp per pixel; saves mean and invstd per pixel.
+__global__ void ln_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float* __restrict__ mean, float* __restrict__ invstd,
+                              long long rows, int C, float eps, int y_cs, int y_co) {
+  const long long r = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* xr = x + r * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
+  const float m = s / C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) { const float d = xr[c] - m; v += d * d; }
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffff, v, o);
+  const float is = rsqrtf(v / C + eps);
+  if (lane == 0 && mean) { mean[r] = m; invstd[r] = is; }
+  for (int c = lane; c < C; c += 32) y[r * y_cs + y_co + c] = (xr[c] - m) * is * gamma[c] + beta[c];
+}
+// dx = invstd * (g - mean_c(g) - xhat * mean_c(g * xhat)), g = dy * gamma; also emits dy*xhat for dgamma
+__global__ void ln_bwd_kernel(const float* __restrict__ dy, int dy_cs, int dy_co, const float* __restrict__ x,
+                              const float* __restrict__ gamma, const float* __restrict__ mean,
+                              const float* __restrict__ invstd, float* __restrict__ dx, float* __restrict__ dy_xhat,
+                              long long rows, int C) {
+  const long long r = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float m = mean[r], is = invstd[r];
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float g = dy[r * dy_cs + dy_co + c] * gamma[c];
+    const float xh = (x[r * C + c] - m) * is;
+    s1 += g; s2 += g * xh;
+  }
+  for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffff, s1, o); s2 += __shfl_xor_sync(0xffffffff, s2, o); }
+  s1 /= C; s2 /= C;
+  for (int c = lane; c < C; c += 32) {
+    const float d = dy[r * dy_cs + dy_co + c];
+    const float xh = (x[r * C + c] - m) * is;
+    dx[r * C + c] = is * (d * gamma[c] - s1 - xh * s2);
+    dy_xhat[r * C + c] = d * xh;
+  }
+}
+
+// ------------------------------------------------------------------ ConvLSTM gate math (gates i, f, c~, o on the last axis)
+// z: [rows][4F] pre-activations (x-conv + bias + h-conv).  Saves the activated gates in place of z for the backward.
+__global__ void lstm_gates_fwd_kernel(float* __restrict__ z, const float* __restrict__ c_prev, float* __restrict__ c_out,
+                                      float* __restrict__ h_out, long long rows, int F) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * F) return;
+  const long long r = i / F;
+  const int c = (int)(i % F);
+  float* zr = z + r * 4 * F;
+  const float gi = fminf(fmaxf(0.2f * zr[c] + 0.5f, 0.f), 1.f);
+  const float gf = fminf(fmaxf(0.2f * zr[F + c] + 0.5f, 0.f), 1.f);
+  const float gc = tanhf(zr[2 * F + c]);
+  const float go = fminf(fmaxf(0.2f * zr[3 * F + c] + 0.5f, 0.f), 1.f);
+  const float cp = c_prev ? c_prev[i] : 0.f;
+  const float cn = gf * cp + gi * gc;
+  zr[c] = gi; zr[F + c] = gf; zr[2 * F + c] = gc; zr[3 * F + c] = go;
+  c_out[i] = cn;
+  h_out[i] = go * tanhf(cn);
+}
+// Backward of one step.  gates: saved activated gates; dh: dL/dh_t (from the output and from step t+1);
+// dc: in = dL/dc_t carried from step t+1, out = dL/dc_{t-1}.  Writes dz (pre-activation gradient) over `gates`.
+__global__ void lstm_gates_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_cur,
+                                      const float* __restrict__ dh, float* __restrict__ dc, long long rows, int F) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * F) return;
+  const long long r = i / F;
+  const int c = (int)(i % F);
+  float* g = gates + r * 4 * F;
+  const float gi = g[c], gf = g[F + c], gc = g[2 * F + c], go = g[3 * F + c];
+  const float tc = tanhf(c_cur[i]);
+  const float dhv = dh[i];
+  const float dct = dc[i] + dhv * go * (1.f - tc * tc);
+  const float cp = c_prev ? c_prev[i] : 0.f;
+  // hard_sigmoid'(z) = 0.2 strictly inside (0, 1)
+  const float di = dct * gc * ((gi > 0.f && gi < 1.f) ? 0.2f : 0.f);
+  const float df = dct * cp * ((gf > 0.f && gf < 1.f) ? 0.2f : 0.f);
+  const float dg = dct * gi * (1.f - gc * gc);
+  const float dov = dhv * tc * ((go > 0.f && go < 1.f) ? 0.2f : 0.f);
+  g[c] = di; g[F + c] = df; g[2 * F + c] = dg; g[3 * F + c] = dov;
+  dc[i] = dct * gf;
+}
+
+// ------------------------------------------------------------------ bilinear x2 (half-pixel centres, edge clamp) and adjoint
+__device__ __forceinline__ void up_taps(int j, int n, int& a, int& b, float& wa) {
+  const int k = j >> 1;
+  if (j & 1) { a = k; b = min(k + 1, n - 1); wa = 0.75f; }
+  else { a = max(k - 1, 0); b = k; wa = 0.25f; }
+}
+__global__ void upsample2x_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n_img, int h, int w, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = n_img * 4 * h * w * C;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long long pix = i / C;
+  const int X = (int)(pix % (2 * w)), Y = (int)((pix / (2 * w)) % (2 * h));
+  const long long n = pix / ((long long)4 * w * h);
+  int ya, yb, xa, xb; float wy, wx;
+  up_taps(Y, h, ya, yb, wy); up_taps(X, w, xa, xb, wx);
+  const float* p = x + n * h * w * C + c;
+  y[i] = wy * (wx * p[((long long)ya * w + xa) * C] + (1.f - wx) * p[((long long)ya * w + xb) * C]) +
+         (1.f - wy) * (wx * p[((long long)yb * w + xa) * C] + (1.f - wx) * p[((long long)yb * w + xb) * C]);
+}
+// adjoint: dx[k] gathers from the (at most 3x3) hi-res positions that read it
+__global__ void upsample2x_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, long long n_img, int h, int w, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = n_img * h * w * C;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long long pix = i / C;
+  const int kx = (int)(pix % w), ky = (int)((pix / w) % h);
+  const long long n = pix / ((long long)w * h);
+  const float* p = dy + n * 4 * h * w * C + c;
+  float acc = 0.f;
+  for (int Y = max(2 * ky - 2, 0); Y <= min(2 * ky + 3, 2 * h - 1); ++Y) {
+    int ya, yb; float wy;
+    up_taps(Y, h, ya, yb, wy);
+    const float cy = (ya == ky ? wy : 0.f) + (yb == ky ? 1.f - wy : 0.f);
+    if (cy == 0.f) continue;
+    for (int X = max(2 * kx - 2, 0); X <= min(2 * kx + 3, 2 * w - 1); ++X) {
+      int xa, xb; float wx;
+      up_taps(X, w, xa, xb, wx);
+      const float cx = (xa == kx ? wx : 0.f) + (xb == kx ? 1.f - wx : 0.f);
+      if (cx != 0.f) acc += cy * cx * p[((long long)Y * 2 * w + X) * C];
+    }
+  }
+  dx[i] = acc;
+}
+
+// ------------------------------------------------------------------ Dense(1) + temporal mean, and their backward
+// score[b] = mean_t (flat[b,t,:] . w + bias)
+__global__ void dense_mean_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ w, const float* __restrict__ bias,
+                                      float* __restrict__ score, int T, int D) {
+  __shared__ float sm[256];
+  const int b = blockIdx.x;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < (long long)T * D; i += blockDim.x) s += flat[(long long)b * T * D + i] * w[i % D];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) score[b] = sm[0] / T + bias[0];
+}
+// dflat[b,t,d] = dscore[b] * w[d] / T ;  (dw, dbias by separate reductions on the host side of the ABI)
+__global__ void dense_mean_bwd_kernel(const float* __restrict__ dscore, const float* __restrict__ w, float* __restrict__ dflat,
+                                      long long B, int T, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * T * D) return;
+  dflat[i] = dscore[i / ((long long)T * D)] * w[i % D] / T;
+}
+// dw[d] = sum_{b,t} dscore[b]/T * flat[b,t,d]
+__global__ void dense_mean_wgrad_kernel(const float* __restrict__ dscore, const float* __restrict__ flat, float* __restrict__ dw,
+                                        float* __restrict__ dbias, int B, int T, int D) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < D) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b)
+      for (int t = 0; t < T; ++t) s += dscore[b] / T * flat[((long long)b * T + t) * D + d];
+    dw[d] = s;
+  }
+  if (d == 0) { float s = 0.f; for (int b = 0; b < B; ++b) s += dscore[b]; dbias[0] = s; }
+}
+
+// ------------------------------------------------------------------ generic full reduction: out[0] = sum f(a[,b])
+template <int MODE>   // 0 sum a, 1 sum a*b, 2 sum a*a
+__global__ void reduce_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, double* __restrict__ part) {
+  __shared__ double sm[256];
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double av = a[i];
+    s += MODE == 0 ? av : (MODE == 1 ? av * (double)b[i] : av * av);
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) part[blockIdx.x] = sm[0];
+}
+__global__ void reduce_final_kernel(const double* __restrict__ part, int n, float* __restrict__ out, double scale) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { double s = 0; for (int i = 0; i < n; ++i) s += part[i]; out[0] = (float)(s * scale); }
+}
+// gradient-penalty norms (ganbase.py:36): out[b*C + c] = sqrt(sum_{t,h,w} g[b,t,h,w,c]^2)
+__global__ void gp_norm_kernel(const float* __restrict__ g, float* __restrict__ out, long long per_sample_px, int C) {
+  __shared__ double sm[256];
+  const int b = blockIdx.x, c = blockIdx.y;
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < per_sample_px; i += blockDim.x) {
+    const double v = g[((long long)b * per_sample_px + i) * C + c];
+    s += v * v;
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) out[b * C + c] = (float)sqrt(sm[0]);
+}
+
+// ------------------------------------------------------------------ Keras Adam, spectral normalisation
+// m += (g-m)(1-b1); v += (g^2-v)(1-b2); w -= lr_t * m / (sqrt(v) + eps)       (train.py:35,58; eps outside the sqrt)
+__global__ void adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
+                            long long n, float lr_t, float b1, float b2, float eps) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+  const float vi = v[i] + (gi * gi - v[i]) * (1.f - b2);
+  m[i] = mi; v[i] = vi;
+  w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+// One power iteration of TFA SpectralNormalization on W = reshape(w, (R, C)):  v = l2n(u W^T); u' = l2n(v W);
+// sigma = v W u'^T; w /= sigma; u = u'.  Single block (R*C <= a few million; training-time only).
+__global__ void sn_update_kernel(float* __restrict__ w, float* __restrict__ u, float* __restrict__ vbuf, int R, int C) {
+  __shared__ float red[256];
+  __shared__ float scal;
+  const int tid = threadIdx.x;
+  // v_raw[r] = sum_c u[c] W[r][c]
+  float nv = 0.f;
+  for (int r = tid; r < R; r += blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += u[c] * w[(long long)r * C + c];
+    vbuf[r] = s;
+    nv += s * s;
+  }
+  red[tid] = nv; __syncthreads();
+  for (int o = 128; o; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  if (tid == 0) scal = rsqrtf(fmaxf(red[0], 1e-12f));
+  __syncthreads();
+  const float inv_nv = scal;
+  __syncthreads();
+  // u2_raw[c] = sum_r v[r] W[r][c]
+  float nu = 0.f;
+  for (int c = tid; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s += vbuf[r] * inv_nv * w[(long long)r * C + c];
+    u[c] = s;          // raw; normalised below
+    nu += s * s;
+  }
+  red[tid] = nu; __syncthreads();
+  for (int o = 128; o; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  if (tid == 0) scal = rsqrtf(fmaxf(red[0], 1e-12f));
+  __syncthreads();
+  const float inv_nu = scal;
+  // sigma = v W u'^T = sum_c u2_raw[c] * u'[c] = sum_c u2_raw[c]^2 * inv_nu = |u2_raw| (when not clamped)
+  const float sigma = red[0] * inv_nu;
+  __syncthreads();
+  for (int c = tid; c < C; c += blockDim.x) u[c] *= inv_nu;
+  const float inv_sigma = 1.f / sigma;
+  for (long long i = tid; i < (long long)R * C; i += blockDim.x) w[i] *= inv_sigma;
+}
+
+__global__ void rsqrt_eps_kernel(const float* __restrict__ v, float* __restrict__ o, int C, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) o[c] = 1.f / sqrtf(v[c] + eps);
+}
+
+inline unsigned blocks_for(long long n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+// ====================================================================== C ABI
+static ConvGeo make_geo(const int* g) {
+  ConvGeo c;
+  c.N = g[0]; c.H = g[1]; c.W = g[2]; c.Ci = g[3]; c.kh = g[4]; c.kw = g[5]; c.Co = g[6]; c.stride = g[7];
+  c.pad_t = g[8]; c.pad_l = g[9]; c.Ho = g[10]; c.Wo = g[11]; c.x_cs = g[12]; c.x_co = g[13]; c.y_cs = g[14]; c.y_co = g[15];
+  return c;
+}
+
+extern "C" int wdg_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, const int* geo, int accumulate,
+                              void* stream) {
+  FwdProblem p{make_geo(geo), x, w, bias, y, accumulate};
+  const long long M = (long long)p.g.N * p.g.Ho * p.g.Wo;
+  dim3 grid((unsigned)((M + TM - 1) / TM), (p.g.Co + TN - 1) / TN);
+  gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int wdg_conv2d_bwd_data(const float* dy, const float* w, float* dx, const int* geo, int accumulate, void* stream) {
+  BwdDataProblem p{make_geo(geo), dy, w, dx, accumulate};
+  const long long M = (long long)p.g.N * p.g.H * p.g.W;
+  dim3 grid((unsigned)((M + TM - 1) / TM), (p.g.Ci + TN - 1) / TN);
+  gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int wdg_conv2d_bwd_weight_scratch(const int* geo, size_t* bytes, int* splits_out) {
+  const ConvGeo g = make_geo(geo);
+  const long long M = (long long)g.kh * g.kw * g.Ci, K = (long long)g.N * g.Ho * g.Wo;
+  const long long tiles = ((M + TM - 1) / TM) * ((g.Co + TN - 1) / TN);
+  long long splits = (4 * 148 + tiles - 1) / tiles;
+  const long long max_splits = (K + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits_out) *splits_out = (int)splits;
+  if (bytes) *bytes = (size_t)(splits * M * g.Co * sizeof(float));
+  return 0;
+}
+
+extern "C" int wdg_conv2d_bwd_weight(const float* x, const float* dy, float* dw, const int* geo, void* scratch,
+                                     int accumulate, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int splits = 1;
+  wdg_conv2d_bwd_weight_scratch(geo, nullptr, &splits);
+  BwdWeightProblem p{make_geo(geo), x, dy, (float*)scratch, 0};
+  const long long M = (long long)p.g.kh * p.g.kw * p.g.Ci, K = (long long)p.g.N * p.g.Ho * p.g.Wo;
+  p.k_per_split = (int)((K + splits - 1) / splits);
+  dim3 grid((unsigned)((M + TM - 1) / TM), (p.g.Co + TN - 1) / TN, splits);
+  gemm_wgrad_kernel<<<grid, 256, 0, stream>>>(p);
+  CKT(cudaGetLastError());
+  const long long n = M * p.g.Co;
+  reduce_splits_kernel<<<blocks_for(n), 256, 0, stream>>>((const float*)scratch, dw, n, splits, accumulate);
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+// column sums: mode 0 sum a, 1 sum a*b, 2 sum a*a over R rows; out[C]; scratch >= 64*C floats
+extern "C" int wdg_colsum(int mode, const float* a, int a_cs, int a_co, const float* b, int b_cs, int b_co, long long R, int C,
+                          float* out, void* scratch, int accumulate, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int slabs = (int)((R + 2047) / 2048);
+  if (slabs > 64) slabs = 64;
+  if (slabs < 1) slabs = 1;
+  dim3 grid((C + 31) / 32, slabs), block(32, 8);
+  float* part = (float*)scratch;
+  if (mode == 0) colsum_partial_kernel<0><<<grid, block, 0, stream>>>(a, a_cs, a_co, b, b_cs, b_co, R, C, part);
+  else if (mode == 1) colsum_partial_kernel<1><<<grid, block, 0, stream>>>(a, a_cs, a_co, b, b_cs, b_co, R, C, part);
+  else colsum_partial_kernel<2><<<grid, block, 0, stream>>>(a, a_cs, a_co, b, b_cs, b_co, R, C, part);
+  CKT(cudaGetLastError());
+  reduce_splits_kernel<<<blocks_for(C), 256, 0, stream>>>(part, out, C, slabs, accumulate);
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int wdg_leaky_relu_fwd(float* x, long long n, float alpha, void* stream) {
+  leaky_fwd_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(x, n, alpha);
+  CKT(cudaGetLastError());
+  return 0;
+}
+extern "C" int wdg_leaky_relu_bwd(float* dy, const float* y, long long n, float alpha, void* stream) {
+  leaky_bwd_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(dy, y, n, alpha);
+  CKT(cudaGetLastError());
+  return 0;
+}
+extern "C" int wdg_axpby(float* out, int o_cs, int o_co, const float* x, int x_cs, int x_co, float a, const float* y, int y_cs,
+                         int y_co, float b, long long rows, int C, int accumulate, void* stream) {
+  axpby_kernel<<<blocks_for(rows * C), 256, 0, (cudaStream_t)stream>>>(out, o_cs, o_co, x, x_cs, x_co, a, y, y_cs, y_co, b, rows,
+                                                                      C, accumulate);
+  CKT(cudaGetLastError());
+  return 0;
+}
+extern "C" int wdg_lerp_batch(float* out, const float* real, const float* fake, const float* eps, long long per_sample,
+                              long long n, void* stream) {
+  lerp_batch_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(out, real, fake, eps, per_sample, n);
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+// BatchNorm, training mode: batch statistics (biased variance), moving statistics updated in place.
+// scratch >= (64*C + 2*C) floats.  Saves mean / invstd ([C] each) for the backward.
+extern "C" int wdg_bn_train_fwd(const float* x, float* y, const float* gamma, const float* beta, float* moving_mean,
+                                float* moving_var, float* save_mean, float* save_invstd, long long rows, int C, float eps,
+                                float momentum, void* scratch, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float* s1 = (float*)scratch + 64 * (size_t)C;
+  float* s2 = s1 + C;
+  if (wdg_colsum(0, x, C, 0, nullptr, 0, 0, rows, C, s1, scratch, 0, stream_)) return 1;
+  if (wdg_colsum(2, x, C, 0, nullptr, 0, 0, rows, C, s2, scratch, 0, stream_)) return 1;
+  bn_finalize_kernel<<<blocks_for(C), 256, 0, stream>>>(s1, s2, rows, C, eps, momentum, save_mean, save_invstd, moving_mean, moving_var);
+  CKT(cudaGetLastError());
+  bn_apply_kernel<<<blocks_for(rows * C), 256, 0, stream>>>(x, y, save_mean, save_invstd, gamma, beta, rows, C);
+  CKT(cudaGetLastError());
+  return 0;
+}
+// Inference-mode BN with explicit statistics (moving mean / variance): invstd computed on the fly into scratch[C].
+extern "C" int wdg_bn_infer(const float* x, float* y, const float* gamma, const float* beta, const float* mean,
+                            const float* var, long long rows, int C, float eps, void* scratch, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float* invstd = (float*)scratch;
+  rsqrt_eps_kernel<<<blocks_for(C), 256, 0, stream>>>(var, invstd, C, eps);
+  CKT(cudaGetLastError());
+  bn_apply_kernel<<<blocks_for(rows * C), 256, 0, stream>>>(x, y, mean, invstd, gamma, beta, rows, C);
+  CKT(cudaGetLastError());
+  return 0;
+}
+// dgamma, dbeta ([C]) and dx.  scratch >= rows*C + 64*C floats.
+extern "C" int wdg_bn_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean,
+                                const float* save_invstd, float* dx, float* dgamma, float* dbeta, long long rows, int C,
+                                void* scratch, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float* tmp = (float*)scratch;
+  float* part = tmp + rows * C;
+  bn_xhat_mul_kernel<<<blocks_for(rows * C), 256, 0, stream>>>(dy, x, save_mean, save_invstd, tmp, rows, C);
+  CKT(cudaGetLastError());
+  if (wdg_colsum(0, tmp, C, 0, nullptr, 0, 0, rows, C, dgamma, part, 0, stream_)) return 1;
+  if (wdg_colsum(0, dy, C, 0, nullptr, 0, 0, rows, C, dbeta, part, 0, stream_)) return 1;
+  bn_bwd_kernel<<<blocks_for(rows * C), 256, 0, stream>>>(dy, x, save_mean, save_invstd, gamma, dbeta, dgamma, dx, rows, C);
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int wdg_ln_fwd(const float* x, float* y, int y_cs, int y_co, const float* gamma, const float* beta, float* save_mean,
+                          float* save_invstd, long long rows, int C, float eps, void* stream) {
+  ln_fwd_kernel<<<blocks_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, y, gamma, beta, save_mean, save_invstd, rows, C, eps, y_cs, y_co);
+  CKT(cudaGetLastError());
+  return 0;
+}
+// dx, dgamma, dbeta.  scratch >= rows*C + 64*C floats.
+extern "C" int wdg_ln_bwd(const float* dy, int dy_cs, int dy_co, const float* x, const float* gamma, const float* save_mean,
+                          const float* save_invstd, float* dx, float* dgamma, float* dbeta, long long rows, int C,
+                          void* scratch, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float* tmp = (float*)scratch;
+  float* part = tmp + rows * C;
+  ln_bwd_kernel<<<blocks_for(rows, 8), 256, 0, stream>>>(dy, dy_cs, dy_co, x, gamma, save_mean, save_invstd, dx, tmp, rows, C);
+  CKT(cudaGetLastError());
+  if (wdg_colsum(0, tmp, C, 0, nullptr, 0, 0, rows, C, dgamma, part, 0, stream_)) return 1;
+  if (wdg_colsum(0, dy, dy_cs, dy_co, nullptr, 0, 0, rows, C, dbeta, part, 0, stream_)) return 1;
+  return 0;
+}
+
+extern "C" int wdg_lstm_gates_fwd(float* z, const float* c_prev, float* c_out, float* h_out, long long rows, int F, void* stream) {
+  lstm_gates_fwd_kernel<<<blocks_for(rows * F), 256, 0, (cudaStream_t)stream>>>(z, c_prev, c_out, h_out, rows, F);
+  CKT(cudaGetLastError());
+  return 0;
+}
+extern "C" int wdg_lstm_gates_bwd(float* gates, const float* c_prev, const float* c_cur, const float* dh, float* dc,
+                                  long long rows, int F, void* stream) {
+  lstm_gates_bwd_kernel<<<blocks_for(rows * F), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_cur, dh, dc, rows, F);
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int wdg_upsample2x_fwd(const float* x, float* y, long long n_img, int h, int w, int C, void* stream) {
+  upsample2x_fwd_kernel<<<blocks_for(n_img * 4 * h * w * C), 256, 0, (cudaStream_t)stream>>>(x, y, n_img, h, w, C);
+  CKT(cudaGetLastError());
+  return 0;
+}
+extern "C" int wdg_upsample2x_bwd(const float* dy, float* dx, long long n_img, int h, int w, int C, void* stream) {
+  upsample2x_bwd_kernel<<<blocks_for(n_img * h * w * C), 256, 0, (cudaStream_t)stream>>>(dy, dx, n_img, h, w, C);
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int wdg_dense_mean_fwd(const float* flat, const float* w, const float* bias, float* score, int B, int T, int D,
+                                  void* stream) {
+  dense_mean_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(flat, w, bias, score, T, D);
+  CKT(cudaGetLastError());
+  return 0;
+}
+extern "C" int wdg_dense_mean_bwd(const float* dscore, const float* flat, const float* w, float* dflat, float* dw, float* dbias,
+                                  int B, int T, int D, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  dense_mean_bwd_kernel<<<blocks_for((long long)B * T * D), 256, 0, stream>>>(dscore, w, dflat, B, T, D);
+  CKT(cudaGetLastError());
+  if (dw) {
+    dense_mean_wgrad_kernel<<<blocks_for(D), 256, 0, stream>>>(dscore, flat, dw, dbias, B, T, D);
+    CKT(cudaGetLastError());
+  }
+  return 0;
+}
+
+// out[0] = scale * sum f;  mode 0 sum a, 1 sum a*b, 2 sum a*a.  scratch >= 1024 doubles.
+extern "C" int wdg_reduce(int mode, const float* a, const float* b, long long n, double scale, float* out, void* scratch,
+                          void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
+  if (blocks > 1024) blocks = 1024;
+  if (blocks < 1) blocks = 1;
+  double* part = (double*)scratch;
+  if (mode == 0) reduce_partial_kernel<0><<<blocks, 256, 0, stream>>>(a, b, n, part);
+  else if (mode == 1) reduce_partial_kernel<1><<<blocks, 256, 0, stream>>>(a, b, n, part);
+  else reduce_partial_kernel<2><<<blocks, 256, 0, stream>>>(a, b, n, part);
+  CKT(cudaGetLastError());
+  reduce_final_kernel<<<1, 32, 0, stream>>>(part, blocks, out, scale);
+  CKT(cudaGetLastError());
+  return 0;
+}
+extern "C" int wdg_gp_norm(const float* g, float* out, int B, long long per_sample_px, int C, void* stream) {
+  gp_norm_kernel<<<dim3(B, C), 256, 0, (cudaStream_t)stream>>>(g, out, per_sample_px, C);
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int wdg_adam(float* w, float* m, float* v, const float* g, long long n, float lr_t, float b1, float b2, float eps,
+                        void* stream) {
+  adam_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(w, m, v, g, n, lr_t, b1, b2, eps);
+  CKT(cudaGetLastError());
+  return 0;
+}
+extern "C" int wdg_sn_update(float* w, float* u, int R, int C, void* scratch /* >= R floats */, void* stream) {
+  sn_update_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(w, u, (float*)scratch, R, C);
+  CKT(cudaGetLastError());
+  return 0;
+}

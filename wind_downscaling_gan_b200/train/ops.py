@@ -1,0 +1,194 @@
+"""Python wrappers of the training kernels (include/wdg.h, "fp32 building blocks").  Tensors are contiguous fp32
+CUDA torch tensors used as raw device buffers; `View` addresses a channel slice of a wider channels-last buffer."""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+
+F32 = torch.float32
+
+
+def _s():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def empty(*shape):
+    return torch.empty(shape, dtype=F32, device="cuda")
+
+
+def zeros(*shape):
+    return torch.zeros(shape, dtype=F32, device="cuda")
+
+
+class View:
+    """Channels [co, co+C) of a channels-last buffer whose pixel pitch is cs."""
+
+    def __init__(self, t, C_, cs=None, co=0):
+        self.t, self.C, self.cs, self.co = t, C_, (cs if cs is not None else t.shape[-1]), co
+
+    @property
+    def rows(self):
+        return self.t.numel() // self.t.shape[-1]
+
+
+def full(t):
+    return View(t, t.shape[-1])
+
+
+_scratch = {}
+
+
+def scratch(nbytes, tag="default"):
+    buf = _scratch.get(tag)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device="cuda")
+        _scratch[tag] = buf
+    return buf
+
+
+def _geo(N, H, W, Ci, kh, kw, Co, stride, pad_t, pad_l, Ho, Wo, xv, yv):
+    return (C.c_int * 16)(N, H, W, Ci, kh, kw, Co, stride, pad_t, pad_l, Ho, Wo, xv.cs, xv.co, yv.cs, yv.co)
+
+
+def conv_out(n, k, s, pad_lo, pad_hi):
+    return (n + pad_lo + pad_hi - k) // s + 1
+
+
+def conv2d_fwd(xv, w, bias, yv, N, H, W, stride, pad, Ho, Wo, accumulate=False):
+    kh, kw, Ci, Co = w.shape
+    g = _geo(N, H, W, Ci, kh, kw, Co, stride, pad, pad, Ho, Wo, xv, yv)
+    _lib.check(_lib.lib().wdg_conv2d_fwd(_p(xv.t), _p(w), _p(bias), _p(yv.t), g, int(accumulate), _s()))
+
+
+def conv2d_bwd_data(dyv, w, dxv, N, H, W, stride, pad, Ho, Wo, accumulate=False):
+    kh, kw, Ci, Co = w.shape
+    g = _geo(N, H, W, Ci, kh, kw, Co, stride, pad, pad, Ho, Wo, dxv, dyv)
+    _lib.check(_lib.lib().wdg_conv2d_bwd_data(_p(dyv.t), _p(w), _p(dxv.t), g, int(accumulate), _s()))
+
+
+def conv2d_bwd_weight(xv, dyv, dw, N, H, W, stride, pad, Ho, Wo, accumulate=False):
+    kh, kw, Ci, Co = dw.shape
+    g = _geo(N, H, W, Ci, kh, kw, Co, stride, pad, pad, Ho, Wo, xv, dyv)
+    nb = C.c_size_t()
+    _lib.check(_lib.lib().wdg_conv2d_bwd_weight_scratch(g, C.byref(nb), None))
+    sc = scratch(nb.value, "wgrad")
+    _lib.check(_lib.lib().wdg_conv2d_bwd_weight(_p(xv.t), _p(dyv.t), _p(dw), g, _p(sc), int(accumulate), _s()))
+
+
+def colsum(av, out, mode=0, bv=None, accumulate=False):
+    sc = scratch(64 * av.C * 4, "colsum")
+    b = bv if bv is not None else av
+    _lib.check(_lib.lib().wdg_colsum(mode, _p(av.t), av.cs, av.co, _p(b.t), b.cs, b.co, av.rows, av.C, _p(out), _p(sc),
+                                     int(accumulate), _s()))
+
+
+def leaky_fwd(x, alpha=0.2):
+    _lib.check(_lib.lib().wdg_leaky_relu_fwd(_p(x), x.numel(), alpha, _s()))
+
+
+def leaky_bwd(dy, y, alpha=0.2):
+    _lib.check(_lib.lib().wdg_leaky_relu_bwd(_p(dy), _p(y), dy.numel(), alpha, _s()))
+
+
+def axpby(outv, xv, a=1.0, yv=None, b=0.0, accumulate=False):
+    y = yv if yv is not None else xv
+    _lib.check(_lib.lib().wdg_axpby(_p(outv.t), outv.cs, outv.co, _p(xv.t), xv.cs, xv.co, a, _p(yv.t) if yv is not None else None,
+                                    y.cs, y.co, b, xv.rows, xv.C, int(accumulate), _s()))
+
+
+def lerp_batch(out, real, fake, eps):
+    n = real.numel()
+    _lib.check(_lib.lib().wdg_lerp_batch(_p(out), _p(real), _p(fake), _p(eps), n // real.shape[0], n, _s()))
+
+
+def bn_train_fwd(x, y, gamma, beta, mm, mv, save_mean, save_invstd, eps=1e-3, momentum=0.99):
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    sc = scratch((66 * Cc) * 4, "bn")
+    _lib.check(_lib.lib().wdg_bn_train_fwd(_p(x), _p(y), _p(gamma), _p(beta), _p(mm), _p(mv), _p(save_mean), _p(save_invstd), rows,
+                                           Cc, eps, momentum, _p(sc), _s()))
+
+
+def bn_infer(x, y, gamma, beta, mean, var, eps=1e-3):
+    Cc = x.shape[-1]
+    sc = scratch(Cc * 4, "bn")
+    _lib.check(_lib.lib().wdg_bn_infer(_p(x), _p(y), _p(gamma), _p(beta), _p(mean), _p(var), x.numel() // Cc, Cc, eps, _p(sc), _s()))
+
+
+def bn_train_bwd(dy, x, gamma, save_mean, save_invstd, dx, dgamma, dbeta):
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    sc = scratch((rows * Cc + 64 * Cc) * 4, "norm_bwd")
+    _lib.check(_lib.lib().wdg_bn_train_bwd(_p(dy), _p(x), _p(gamma), _p(save_mean), _p(save_invstd), _p(dx), _p(dgamma), _p(dbeta),
+                                           rows, Cc, _p(sc), _s()))
+
+
+def ln_fwd(x, yv, gamma, beta, save_mean, save_invstd, eps=1e-3):
+    Cc = x.shape[-1]
+    _lib.check(_lib.lib().wdg_ln_fwd(_p(x), _p(yv.t), yv.cs, yv.co, _p(gamma), _p(beta), _p(save_mean), _p(save_invstd),
+                                     x.numel() // Cc, Cc, eps, _s()))
+
+
+def ln_bwd(dyv, x, gamma, save_mean, save_invstd, dx, dgamma, dbeta):
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    sc = scratch((rows * Cc + 64 * Cc) * 4, "norm_bwd")
+    _lib.check(_lib.lib().wdg_ln_bwd(_p(dyv.t), dyv.cs, dyv.co, _p(x), _p(gamma), _p(save_mean), _p(save_invstd), _p(dx), _p(dgamma),
+                                     _p(dbeta), rows, Cc, _p(sc), _s()))
+
+
+def lstm_gates_fwd(z, c_prev, c_out, h_out):
+    Fc = c_out.shape[-1]
+    _lib.check(_lib.lib().wdg_lstm_gates_fwd(_p(z), _p(c_prev), _p(c_out), _p(h_out), c_out.numel() // Fc, Fc, _s()))
+
+
+def lstm_gates_bwd(gates, c_prev, c_cur, dh, dc):
+    Fc = c_cur.shape[-1]
+    _lib.check(_lib.lib().wdg_lstm_gates_bwd(_p(gates), _p(c_prev), _p(c_cur), _p(dh), _p(dc), c_cur.numel() // Fc, Fc, _s()))
+
+
+def upsample2x_fwd(x, y):
+    n, h, w, Cc = x.shape
+    _lib.check(_lib.lib().wdg_upsample2x_fwd(_p(x), _p(y), n, h, w, Cc, _s()))
+
+
+def upsample2x_bwd(dy, dx):
+    n, h, w, Cc = dx.shape
+    _lib.check(_lib.lib().wdg_upsample2x_bwd(_p(dy), _p(dx), n, h, w, Cc, _s()))
+
+
+def dense_mean_fwd(flat, w, bias, score, B, T, D):
+    _lib.check(_lib.lib().wdg_dense_mean_fwd(_p(flat), _p(w), _p(bias), _p(score), B, T, D, _s()))
+
+
+def dense_mean_bwd(dscore, flat, w, dflat, dw, dbias, B, T, D):
+    _lib.check(_lib.lib().wdg_dense_mean_bwd(_p(dscore), _p(flat), _p(w), _p(dflat), _p(dw), _p(dbias), B, T, D, _s()))
+
+
+def reduce(a, mode=0, b=None, scale=1.0):
+    """Returns a 1-element CUDA tensor: scale * sum(a | a*b | a*a)."""
+    out = empty(1)
+    sc = scratch(1024 * 8, "reduce")
+    _lib.check(_lib.lib().wdg_reduce(mode, _p(a), _p(b), a.numel(), scale, _p(out), _p(sc), _s()))
+    return out
+
+
+def gp_norm(g, out):
+    B, Cc = g.shape[0], g.shape[-1]
+    _lib.check(_lib.lib().wdg_gp_norm(_p(g), _p(out), B, g.numel() // (B * Cc), Cc, _s()))
+
+
+def adam(w, m, v, g, lr_t, b1, b2, eps):
+    _lib.check(_lib.lib().wdg_adam(_p(w), _p(m), _p(v), _p(g), w.numel(), lr_t, b1, b2, eps, _s()))
+
+
+def sn_update(w, u):
+    Cl = w.shape[-1]
+    R = w.numel() // Cl
+    sc = scratch(R * 4, "sn")
+    _lib.check(_lib.lib().wdg_sn_update(_p(w), _p(u), R, Cl, _p(sc), _s()))
