@@ -128,6 +128,9 @@ int wdg_leaky_relu_fwd(float* x, long long n, float alpha, void* stream);
 int wdg_leaky_relu_bwd(float* dy, const float* y, long long n, float alpha, void* stream);
 int wdg_axpby(float* out, int o_cs, int o_co, const float* x, int x_cs, int x_co, float a, const float* y, int y_cs, int y_co,
               float b, long long rows, int C, int accumulate, void* stream);
+/* x = leaky(x + bias, alpha) in place (alpha = 1: linear); out[b][a][:] = in[a][b][:] */
+int wdg_bias_act(float* x, int cs, int co, const float* bias, long long rows, int C, float alpha, void* stream);
+int wdg_transpose01(const float* in, float* out, int A, int B, long long inner, void* stream);
 int wdg_lerp_batch(float* out, const float* real, const float* fake, const float* eps, long long per_sample, long long n, void* stream);
 /* BatchNormalization (axis -1, eps, momentum): training mode uses batch statistics and updates the moving ones */
 int wdg_bn_train_fwd(const float* x, float* y, const float* gamma, const float* beta, float* moving_mean, float* moving_var,

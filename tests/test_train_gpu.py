@@ -1,0 +1,130 @@
+"""GPU parity tests of the training path (critic forward/backward, training-mode generator, WGAN train_step) against
+the float64 oracles (oracle/critic.py numpy, oracle/torch_train.py torch autograd).  The CUDA path is fp32:
+tolerances are relative L2 <= 1e-4 for activations / gradients and 1e-3 for quantities after several updates."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = np.asarray(a.detach().cpu().numpy() if hasattr(a, "detach") else a, np.float64)
+    b = np.asarray(b.detach().cpu().numpy() if hasattr(b, "detach") else b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def data(B, T, S, seed):
+    rng = np.random.default_rng(seed)
+    lr = rng.standard_normal((B, T, S, S, 3)).astype(np.float32)
+    hr = rng.standard_normal((B, T, S, S, 2)).astype(np.float32)
+    return rng, lr, hr
+
+
+@pytest.mark.parametrize("B,T,S", [(1, 2, 96), (2, 3, 32)])
+def test_critic_forward_matches_oracle(B, T, S):
+    from oracle.critic import critic_forward, synthetic_critic_weights
+    from wind_downscaling_gan_b200.gan.models import make_discriminator
+    _, lr, hr = data(B, T, S, 0)
+    w = synthetic_critic_weights(1, size=S)
+    d = make_discriminator(S, S, 3, 2, T)
+    assert set(d.weight_names()) == set(w)
+    d.set_weights(w)
+    out = d([lr, hr], training=False)
+    assert tuple(out.shape) == (B, 1)
+    assert rel(out, critic_forward(w, lr, hr)) < 1e-4
+    with pytest.raises(NotImplementedError):
+        make_discriminator(96, 48, 3, 2, T)          # models.py:89-91
+
+
+def test_generator_training_forward_backward():
+    import torch
+    from oracle import torch_train as tt
+    from oracle.generator import synthetic_generator_weights
+    from wind_downscaling_gan_b200.train.nets import GenNet, to_device
+    B, T, S = 2, 2, 32
+    rng, lr, _ = data(B, T, S, 2)
+    noise = (0.1 * rng.standard_normal((B, T, S, S, 20))).astype(np.float32)
+    gw = synthetic_generator_weights(3)
+    ref_w = {k: tt.T(v).clone() for k, v in gw.items()}
+    out_ref, reads = tt.generator(ref_w, tt.T(lr), tt.T(noise), training=True)
+    dout = rng.standard_normal(out_ref.shape)
+    names = tt.trainable(ref_w)
+    grads_ref = torch.autograd.grad((out_ref * tt.T(dout)).sum(), [reads[n] for n in names])
+    w = to_device(gw)
+    net = GenNet(w)
+    out = net.forward(torch.from_numpy(lr).cuda(), torch.from_numpy(noise).cuda(), training=True)
+    assert rel(out, out_ref) < 1e-4
+    # spectral norm (in place) and BatchNorm moving statistics were updated like the reference's
+    for k in ("layer_with_weights-0/layer/w", "layer_with_weights-7/layer/sn_u", "layer_with_weights-1/moving_mean",
+              "layer_with_weights-10/moving_variance"):
+        assert rel(w[k], ref_w[k]) < 1e-4, k
+    grads = net.backward(torch.from_numpy(dout.astype(np.float32)).cuda())
+    assert set(grads) == set(names)
+    for n, gr in zip(names, grads_ref):
+        assert rel(grads[n], gr) < 2e-4, n
+
+
+def test_critic_backward_weights_and_input():
+    import torch
+    from oracle import torch_train as tt
+    from oracle.critic import synthetic_critic_weights
+    from wind_downscaling_gan_b200.train.nets import CriticNet, to_device
+    B, T, S = 2, 2, 32
+    _, lr, hr = data(B, T, S, 4)
+    dw = synthetic_critic_weights(5, size=S)
+    ref_w = {k: tt.T(v).clone() for k, v in dw.items()}
+    hr_t = tt.T(hr).requires_grad_(True)
+    s_ref, reads = tt.critic(ref_w, tt.T(lr), hr_t, training=True)
+    ds = np.array([[0.7], [-1.3]])
+    names = tt.trainable(ref_w)
+    gr = torch.autograd.grad((s_ref * tt.T(ds)).sum(), [reads[n] for n in names] + [hr_t])
+    w = to_device(dw)
+    net = CriticNet(w, S)
+    s = net.forward(torch.from_numpy(lr).cuda(), torch.from_numpy(hr).cuda(), training=True)
+    assert rel(s, s_ref) < 1e-4
+    g, dhr = net.backward(torch.from_numpy(ds.astype(np.float32)).cuda(), need_weight_grads=True, need_input_grad=True)
+    assert set(g) == set(names)
+    for n, r in zip(names, gr[:-1]):
+        assert rel(g[n], r) < 2e-4, n
+    assert rel(dhr, gr[-1]) < 2e-4
+
+
+def test_train_step_matches_oracle():
+    """One full WGAN step (3 critic updates + 1 generator update + metric recompute) with shared random draws."""
+    from oracle import torch_train as tt
+    from oracle.critic import synthetic_critic_weights
+    from oracle.generator import synthetic_generator_weights
+    from wind_downscaling_gan_b200.data.data_generator import FlexibleNoiseGenerator
+    from wind_downscaling_gan_b200.gan import train
+    from wind_downscaling_gan_b200.gan.ganbase import GAN
+    from wind_downscaling_gan_b200.gan.models import make_discriminator, make_generator
+    B, T, S = 2, 2, 32
+    rng, lr, hr = data(B, T, S, 6)
+    gw, dw = synthetic_generator_weights(7), synthetic_critic_weights(8, size=S)
+    draws = []
+    for _ in range(3):
+        draws += [0.1 * rng.standard_normal((B, T, S, S, 20)), rng.uniform(0, 1, (B,)),
+                  0.1 * rng.standard_normal((B, T, S, S, 2)), 0.1 * rng.standard_normal((B, T, S, S, 2))]
+    draws += [0.1 * rng.standard_normal((B, T, S, S, 20)), 0.1 * rng.standard_normal((B, T, S, S, 20))]
+    draws = [np.asarray(d, np.float32) for d in draws]
+    st = tt.State(gw, dw)
+    m_ref = tt.train_step(st, lr, hr, draws)
+    gen, disc = make_generator(S, 3, 20, 2, T), make_discriminator(S, S, 3, 2, T)
+    gen.set_weights(gw)
+    disc.set_weights(dw)
+    gan = GAN(gen, disc, FlexibleNoiseGenerator((B, T, S, S, 20), std=0.1))
+    gan.compile(generator_optimizer=train.generator_optimizer(), discriminator_optimizer=train.discriminator_optimizer(),
+                discriminator_loss=train.discriminator_loss)
+    m = gan.train_step((lr, hr), draws=draws)
+    for k in ("g_loss", "g_disc_loss", "d_loss", "d_gradient_pen", "g_gradient_param", "d_gradient_param"):
+        assert abs(m[k] - m_ref[k]) <= 2e-3 * max(1.0, abs(m_ref[k])), (k, m[k], m_ref[k])
+    gan.sync_weights()
+    new_g, new_d = gen.get_weights(), disc.get_weights()
+    for k, v in st.g.items():
+        assert rel(new_g[k], v) < 1e-3, k
+    for k, v in st.d.items():
+        assert rel(new_d[k], v) < 1e-3, k
+    # the weights really moved (Adam + spectral normalisation)
+    assert rel(new_g["layer_with_weights-4/cell/kernel"], gw["layer_with_weights-4/cell/kernel"]) > 1e-5
+    t = gan.test_step((lr, hr), draws=[draws[-1]])
+    assert set(t) >= {"loss"} and np.isfinite(t["loss"])

@@ -55,6 +55,8 @@ def _declare(lib):
         "wdg_leaky_relu_bwd": [vp, vp, ll, f, vp],
         "wdg_axpby": [vp, i, i, vp, i, i, f, vp, i, i, f, ll, i, i, vp],
         "wdg_lerp_batch": [vp, vp, vp, vp, ll, ll, vp],
+        "wdg_bias_act": [vp, i, i, vp, ll, i, f, vp],
+        "wdg_transpose01": [vp, vp, i, i, ll, vp],
         "wdg_bn_train_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, ll, i, f, f, vp, vp],
         "wdg_bn_infer": [vp, vp, vp, vp, vp, vp, ll, i, f, vp, vp],
         "wdg_bn_train_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, ll, i, vp, vp],

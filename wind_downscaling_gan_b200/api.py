@@ -100,11 +100,8 @@ def get_network(weights_path=None):
     print('Loading network...')
     generator = make_generator(image_size=IMG_SIZE, in_channels=NB_INPUTS, noise_channels=NOISE_CHANNELS,
                                out_channels=NB_OUTPUTS, n_timesteps=SEQUENCE_LENGTH)
-    try:
-        discriminator = make_discriminator(low_res_size=IMG_SIZE, high_res_size=IMG_SIZE, low_res_channels=NB_INPUTS,
-                                           high_res_channels=NB_OUTPUTS, n_timesteps=SEQUENCE_LENGTH)
-    except ImportError:
-        discriminator = None   # critic kernels not built yet (inference does not need them)
+    discriminator = make_discriminator(low_res_size=IMG_SIZE, high_res_size=IMG_SIZE, low_res_channels=NB_INPUTS,
+                                       high_res_channels=NB_OUTPUTS, n_timesteps=SEQUENCE_LENGTH)
     noise_shape = (BATCH_SIZE, SEQUENCE_LENGTH, IMG_SIZE, IMG_SIZE, NOISE_CHANNELS)
     gan = GAN(generator, discriminator, noise_generator=FlexibleNoiseGenerator(noise_shape, std=NOISE_STD))
     gan.compile(generator_optimizer=train.generator_optimizer(), generator_metrics=[],
@@ -112,7 +109,7 @@ def get_network(weights_path=None):
                 metrics=[])
     path = Path(weights_path) if weights_path is not None else WEIGHTS_PATH
     try:
-        gan.generator.load_weights(path / 'generator')
+        gan.load_weights(path)
     except FileNotFoundError:
         print(f'  no tensor data under {path}: using randomly initialised weights')
     return gan

@@ -218,6 +218,25 @@ __global__ void axpby_kernel(float* __restrict__ out, int o_cs, int o_co, const 
   float* o = out + r * o_cs + o_co + c;
   *o = accumulate ? *o + v : v;
 }
+// x = act(x + bias[c]) in place on channels [co, co+C) of a buffer with pixel pitch cs; alpha = 1 -> linear
+__global__ void bias_act_kernel(float* __restrict__ x, int cs, int co, const float* __restrict__ bias, long long rows, int C,
+                                float alpha) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const int c = (int)(i % C);
+  float* p = x + (i / C) * cs + co + c;
+  const float v = *p + (bias ? bias[c] : 0.f);
+  *p = v >= 0.f ? v : alpha * v;
+}
+// out[b][a][inner] = in[a][b][inner]
+__global__ void transpose01_kernel(const float* __restrict__ in, float* __restrict__ out, int A, int B, long long inner) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)A * B * inner) return;
+  const long long k = i % inner;
+  const long long ab = i / inner;
+  const int b = (int)(ab % B), a = (int)(ab / B);
+  out[((long long)b * A + a) * inner + k] = in[i];
+}
 // combined[b,...] = eps[b]*real + (1-eps[b])*fake   (ganbase.py:31)
 __global__ void lerp_batch_kernel(float* __restrict__ out, const float* __restrict__ real, const float* __restrict__ fake,
                                   const float* __restrict__ eps, long long per_sample, long long n) {
@@ -622,6 +641,16 @@ extern "C" int wdg_axpby(float* out, int o_cs, int o_co, const float* x, int x_c
                          int y_co, float b, long long rows, int C, int accumulate, void* stream) {
   axpby_kernel<<<blocks_for(rows * C), 256, 0, (cudaStream_t)stream>>>(out, o_cs, o_co, x, x_cs, x_co, a, y, y_cs, y_co, b, rows,
                                                                       C, accumulate);
+  CKT(cudaGetLastError());
+  return 0;
+}
+extern "C" int wdg_bias_act(float* x, int cs, int co, const float* bias, long long rows, int C, float alpha, void* stream) {
+  bias_act_kernel<<<blocks_for(rows * C), 256, 0, (cudaStream_t)stream>>>(x, cs, co, bias, rows, C, alpha);
+  CKT(cudaGetLastError());
+  return 0;
+}
+extern "C" int wdg_transpose01(const float* in, float* out, int A, int B, long long inner, void* stream) {
+  transpose01_kernel<<<blocks_for((long long)A * B * inner), 256, 0, (cudaStream_t)stream>>>(in, out, A, B, inner);
   CKT(cudaGetLastError());
   return 0;
 }

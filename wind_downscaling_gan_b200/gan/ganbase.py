@@ -1,12 +1,11 @@
-"""`GAN` with the reference's constructor / compile / call / weight-I/O surface (`gan/ganbase.py`).
-
-The inference path (`.generator`, `.noise_generator`, `call`, `save_weights`, `load_weights`) is what
-`api.predict` uses.  `train_step` / `test_step` need the critic and the backward kernels, which are
-the next rows of SURVEY.md §8 (A14-A16) and raise NotImplementedError until they are built: there is
-deliberately no PyTorch-autograd fallback.
+"""`GAN` with the reference's constructor / compile / call / train_step / test_step / weight-I/O surface
+(`gan/ganbase.py`).  Inference (`call`, `.generator.predict`) runs the bf16 tcgen05 path; `train_step` /
+`test_step` run the fp32 training kernels (train/nets.py).  There is no autograd / PyTorch math fallback.
 """
 import os
 from pathlib import Path
+
+import numpy as np
 
 
 class GAN:
@@ -18,6 +17,7 @@ class GAN:
         self._n_critic = n_critic
         self.compiled_metrics = None
         self.metrics = []
+        self._train = None   # lazily built device-side training state
 
     def compile(self, generator_optimizer, discriminator_optimizer, generator_loss=None, generator_metrics=None,
                 discriminator_loss=None, **kwargs):
@@ -34,13 +34,34 @@ class GAN:
 
     __call__ = call
 
-    def train_step(self, data):
-        raise NotImplementedError("WGAN train_step (ganbase.py:21-94) needs the critic + backward kernels (SURVEY §8 A14-A16)")
+    # ------------------------------------------------------------------ training
+    def _state(self):
+        if self._train is None:
+            from ..train.step import TrainState
+            if self.reconstruction_loss is not None:
+                raise NotImplementedError("reconstruction_loss (autoencoder features) is outside the built path")
+            self._train = TrainState(self.generator, self.discriminator, self.generator.optimizer, self.discriminator.optimizer)
+        return self._train
 
-    def test_step(self, data):
-        raise NotImplementedError("test_step (ganbase.py:96-113) needs the critic forward (SURVEY §8 A14)")
+    def train_step(self, data, draws=None):
+        """ganbase.py:21-94.  data = (low_res, high_res[, sample_weight]); `draws` optionally replaces the random
+        tensors (parity tests): per critic iteration [G noise, eps (B,), noise on real, noise on fake], then
+        G noise for the generator update and for the metric recompute."""
+        from ..train.step import train_step
+        return train_step(self._state(), data[0], data[1], self.noise_generator, self._n_critic, draws)
+
+    def test_step(self, data, draws=None):
+        """ganbase.py:96-113."""
+        from ..train.step import test_step
+        return test_step(self._state(), data[0], data[1], self.noise_generator, draws)
+
+    def sync_weights(self):
+        """Copies the trained fp32 device weights back into the model handles (inference path, save_weights)."""
+        if self._train is not None:
+            self._train.push_weights()
 
     def save_weights(self, filepath, *args, **kwargs):
+        self.sync_weights()
         self.generator.save_weights(os.path.join(filepath, 'generator'), *args, **kwargs)
         if self.discriminator is not None:
             self.discriminator.save_weights(os.path.join(filepath, 'discriminator'), *args, **kwargs)
@@ -49,3 +70,4 @@ class GAN:
         self.generator.load_weights(Path(filepath) / 'generator', *args, **kwargs)
         if self.discriminator is not None:
             self.discriminator.load_weights(Path(filepath) / 'discriminator', *args, **kwargs)
+        self._train = None

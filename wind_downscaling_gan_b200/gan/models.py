@@ -237,10 +237,17 @@ class Generator(_NativeModel):
     def __call__(self, inputs, training=False, mask=None):
         """`generator([low_res, noise], training=False)` (ganbase.py:65).  Training-mode forward
         (batch statistics + spectral-norm power iteration) is not part of the inference path."""
-        if training:
-            raise NotImplementedError("training-mode generator forward is not built yet (SURVEY §8 A15/A16)")
         import torch
         image, noise = inputs
+        if training:
+            # training-mode call: spectral-norm power iteration (mutates w / sn_u), BatchNorm batch statistics and
+            # moving-average update -- on the fp32 training kernels (train/nets.py)
+            from ..train.nets import GenNet, to_device
+            from ..train.step import _dev
+            w = to_device(self.get_weights())
+            out = GenNet(w).forward(_dev(image), _dev(noise), training=True)
+            self.set_weights({k: v.cpu().numpy() for k, v in w.items()})
+            return out
         if isinstance(image, torch.Tensor) and image.is_cuda:
             return self.forward_device(image, noise)
         return self.predict_host(image, noise)

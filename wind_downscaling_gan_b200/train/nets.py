@@ -1,0 +1,403 @@
+"""Training-path generator and critic: explicit forward / backward over the fp32 kernels of train/ops.py.
+
+Graphs follow the reference's `make_generator` / `make_discriminator` (`gan/models.py:9-142`) in TRAINING mode:
+SpectralNormalization performs one in-place power iteration per call (TFA 0.14), BatchNormalization uses batch
+statistics and updates its moving averages, LayerNormalization / ConvLSTM2D as in inference.  Weights are fp32 CUDA
+tensors keyed by the checkpoint variable names.  Activations are channels-last [N = B*T, H, W, C].
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import View, full
+
+LW = "layer_with_weights-%d/"
+ALPHA = float(np.float32(0.2))
+
+
+def to_device(weights):
+    return {k: torch.as_tensor(np.asarray(v, np.float32)).cuda().contiguous() for k, v in weights.items()}
+
+
+def trainable_names(weights):
+    return [n for n in weights if not n.endswith(("sn_u", "moving_mean", "moving_variance"))]
+
+
+class Conv:
+    """Conv2D (HWIO kernel) or Conv2DTranspose (kernel (kh,kw,out,in) = HWIO of the conv it transposes)."""
+
+    def __init__(self, w, b, stride, pad, transposed=False, leaky=True):
+        self.w, self.b, self.stride, self.pad, self.T, self.leaky = w, b, stride, pad, transposed, leaky
+
+    def out_hw(self, H, W):
+        k, s, p = self.w.shape[0], self.stride, self.pad
+        if self.T:
+            return (H - 1) * s + k - 2 * p, (W - 1) * s + k - 2 * p
+        return ops.conv_out(H, k, s, p, p), ops.conv_out(W, k, s, p, p)
+
+    def forward(self, xv, N, H, W, out=None):
+        """xv: View of the input ([N,H,W,*]); returns the activation tensor [N,Ho,Wo,Cout] (or writes into `out` view)."""
+        Ho, Wo = self.out_hw(H, W)
+        cout = self.w.shape[2] if self.T else self.w.shape[3]
+        y = out if out is not None else full(ops.empty(N, Ho, Wo, cout))
+        if self.T:   # forward of the transposed conv = backward-data of the conv (conv input dims = our output dims)
+            ops.conv2d_bwd_data(xv, self.w, y, N, Ho, Wo, self.stride, self.pad, H, W)
+        else:
+            ops.conv2d_fwd(xv, self.w, None, y, N, H, W, self.stride, self.pad, Ho, Wo)
+        ops.bias_act(y, self.b, ALPHA if self.leaky else 1.0)
+        self.ctx = (xv, N, H, W, Ho, Wo, y)
+        return y
+
+    def backward(self, dy, need_dx=True, dx_out=None, accumulate_dx=False, need_dw=True):
+        """dy: dense tensor [N,Ho,Wo,Cout] (modified in place by the activation backward).  Returns (dx view, dw, db)."""
+        xv, N, H, W, Ho, Wo, y = self.ctx
+        dyv = full(dy)
+        if self.leaky:
+            if y.cs != y.C:
+                raise NotImplementedError("leaky backward needs a dense activation")
+            ops.leaky_bwd(dy, y.t, ALPHA)
+        db = dw = None
+        if need_dw:
+            db = ops.empty(self.b.shape[0])
+            ops.colsum(dyv, db)
+            dw = ops.empty(*self.w.shape)
+        dx = None
+        if self.T:
+            if need_dw:
+                ops.conv2d_bwd_weight(dyv, xv, dw, N, Ho, Wo, self.stride, self.pad, H, W)
+            if need_dx:
+                dx = dx_out if dx_out is not None else full(ops.empty(N, H, W, xv.C))
+                ops.conv2d_fwd(dyv, self.w, None, dx, N, Ho, Wo, self.stride, self.pad, H, W, accumulate=accumulate_dx)
+        else:
+            if need_dw:
+                ops.conv2d_bwd_weight(xv, dyv, dw, N, H, W, self.stride, self.pad, Ho, Wo)
+            if need_dx:
+                dx = dx_out if dx_out is not None else full(ops.empty(N, H, W, xv.C))
+                ops.conv2d_bwd_data(dyv, self.w, dx, N, H, W, self.stride, self.pad, Ho, Wo, accumulate=accumulate_dx)
+        return dx, dw, db
+
+
+class BatchNorm:
+    def __init__(self, w, i):
+        p = LW % i
+        self.names = (p + "gamma", p + "beta", p + "moving_mean", p + "moving_variance")
+        self.w = w
+
+    def forward(self, x, training):
+        g, b, mm, mv = (self.w[n] for n in self.names)
+        y = torch.empty_like(x)
+        if training:
+            C = x.shape[-1]
+            self.sm, self.si = ops.empty(C), ops.empty(C)
+            ops.bn_train_fwd(x, y, g, b, mm, mv, self.sm, self.si)
+            self.x = x
+        else:
+            ops.bn_infer(x, y, g, b, mm, mv)
+        return y
+
+    def backward(self, dy):
+        C = self.x.shape[-1]
+        dx, dg, db = torch.empty_like(self.x), ops.empty(C), ops.empty(C)
+        ops.bn_train_bwd(dy, self.x, self.w[self.names[0]], self.sm, self.si, dx, dg, db)
+        return dx, {self.names[0]: dg, self.names[1]: db}
+
+
+class LayerNorm:
+    def __init__(self, w, i):
+        p = LW % i
+        self.names = (p + "gamma", p + "beta")
+        self.w = w
+
+    def forward(self, x, out=None):
+        rows = x.numel() // x.shape[-1]
+        self.sm, self.si, self.x = ops.empty(rows), ops.empty(rows), x
+        y = out if out is not None else full(torch.empty_like(x))
+        ops.ln_fwd(x, y, self.w[self.names[0]], self.w[self.names[1]], self.sm, self.si)
+        return y
+
+    def backward(self, dyv):
+        C = self.x.shape[-1]
+        dx, dg, db = torch.empty_like(self.x), ops.empty(C), ops.empty(C)
+        ops.ln_bwd(dyv, self.x, self.w[self.names[0]], self.sm, self.si, dx, dg, db)
+        return dx, {self.names[0]: dg, self.names[1]: db}
+
+
+class ConvLSTM:
+    """ConvLSTM2D(F, 3x3, same, return_sequences): x-conv with bias + recurrent conv, gates i,f,c,o."""
+
+    def __init__(self, K, R, b):
+        self.K, self.R, self.b = K, R, b
+
+    def forward(self, x, B, T):
+        """x: [B*T, H, W, Cin] batch-major -> h sequence [B*T, H, W, F] batch-major."""
+        _, H, W, Cin = x.shape
+        F = self.R.shape[2]
+        xt = ops.transpose01(x.view(B, T, H, W, Cin))            # [T, B, H, W, Cin]
+        hs = ops.empty(T, B, H, W, F)
+        cs = ops.empty(T, B, H, W, F)
+        gates = ops.empty(T, B, H, W, 4 * F)
+        for t in range(T):
+            z = full(gates[t])
+            ops.conv2d_fwd(full(xt[t]), self.K, None, z, B, H, W, 1, 1, H, W)
+            if t > 0:
+                ops.conv2d_fwd(full(hs[t - 1]), self.R, None, z, B, H, W, 1, 1, H, W, accumulate=True)
+            ops.bias_act(z, self.b, 1.0)
+            ops.lstm_gates_fwd(gates[t], cs[t - 1] if t > 0 else None, cs[t], hs[t])
+        self.ctx = (xt, hs, cs, gates, B, T, H, W, Cin, F)
+        return ops.transpose01(hs).view(B * T, H, W, F)
+
+    def backward(self, dh_seq, need_dx=True, need_dw=True):
+        """dh_seq: [B*T, H, W, F] batch-major.  Returns (dx batch-major or None, dK, dR, db)."""
+        xt, hs, cs, gates, B, T, H, W, Cin, F = self.ctx
+        dhs = ops.transpose01(dh_seq.view(B, T, H, W, F))        # [T, B, ...]
+        dK, dR, db = torch.zeros_like(self.K), torch.zeros_like(self.R), torch.zeros_like(self.b)
+        dc = ops.zeros(B, H, W, F)
+        dh_rec = ops.zeros(B, H, W, F)
+        dxt = ops.empty(T, B, H, W, Cin) if need_dx else None
+        for t in range(T - 1, -1, -1):
+            dh = dhs[t]
+            if t < T - 1:
+                ops.axpby(full(dh), full(dh), 1.0, full(dh_rec), 1.0)
+            ops.lstm_gates_bwd(gates[t], cs[t - 1] if t > 0 else None, cs[t], dh, dc)   # gates[t] now holds dz
+            dz = full(gates[t])
+            if need_dw:
+                ops.conv2d_bwd_weight(full(xt[t]), dz, dK, B, H, W, 1, 1, H, W, accumulate=True)
+                ops.colsum(dz, db, accumulate=True)
+            if need_dx:
+                ops.conv2d_bwd_data(dz, self.K, full(dxt[t]), B, H, W, 1, 1, H, W)
+            if t > 0:
+                if need_dw:
+                    ops.conv2d_bwd_weight(full(hs[t - 1]), dz, dR, B, H, W, 1, 1, H, W, accumulate=True)
+                ops.conv2d_bwd_data(dz, self.R, full(dh_rec), B, H, W, 1, 1, H, W)
+        dx = ops.transpose01(dxt).view(B * T, H, W, Cin) if need_dx else None
+        return dx, dK, dR, db
+
+
+def sn_step(w, idx):
+    """One training-mode call of SpectralNormalization on layer `idx`: w <- w / sigma, u <- u' (in place)."""
+    ops.sn_update(w[(LW % idx) + "layer/w"], w[(LW % idx) + "layer/sn_u"])
+
+
+# =============================================================================================== generator
+class GenNet:
+    SN_LAYERS = (0, 2, 5, 7)
+
+    def __init__(self, weights):
+        self.w = weights   # dict name -> CUDA tensor (shared with the caller; updated in place)
+
+    def forward(self, image, noise, training):
+        """image [B,T,S,S,Cin], noise [B,T,S,S,Cn] -> [B,T,S,S,Cout].  Keeps the context for backward()."""
+        w = self.w
+        B, T, S = image.shape[:3]
+        N = B * T
+        if training:
+            for i in self.SN_LAYERS:
+                sn_step(w, i)
+        cin, cn = image.shape[-1], noise.shape[-1]
+        x0 = ops.empty(N, S, S, cin + cn)                                                      # models.py:28
+        ops.axpby(View(x0, cin, cin + cn, 0), full(image.reshape(N, S, S, cin)))
+        ops.axpby(View(x0, cn, cin + cn, cin), full(noise.reshape(N, S, S, cn)))
+        L = {}
+        L["c0"] = Conv(w[(LW % 0) + "layer/w"], w[(LW % 0) + "layer/layer/bias"], 2, 3)        # :32-33
+        a0 = L["c0"].forward(full(x0), N, S, S)
+        L["bn1"] = BatchNorm(w, 1)
+        r2 = L["bn1"].forward(a0.t, training)                                                  # :34
+        S2 = S // 2
+        L["c2"] = Conv(w[(LW % 2) + "layer/w"], w[(LW % 2) + "layer/layer/bias"], 2, 1)        # :38-39
+        a2 = L["c2"].forward(full(r2), N, S2, S2)
+        L["bn3"] = BatchNorm(w, 3)
+        r4 = L["bn3"].forward(a2.t, training)                                                  # :40
+        S4 = S // 4
+        L["lstm"] = ConvLSTM(w[(LW % 4) + "cell/kernel"], w[(LW % 4) + "cell/recurrent_kernel"], w[(LW % 4) + "cell/bias"])
+        hseq = L["lstm"].forward(r4, B, T)                                                     # :45
+        L["c5"] = Conv(w[(LW % 5) + "layer/w"], w[(LW % 5) + "layer/layer/bias"], 1, 1)        # :49
+        a5 = L["c5"].forward(full(hseq), N, S4, S4)
+        L["bn6"] = BatchNorm(w, 6)
+        r5 = L["bn6"].forward(a5.t, training)                                                  # :50
+        F = r4.shape[-1]
+        cat7 = ops.empty(N, S4, S4, F // 2 + F)                                                # :54
+        ops.axpby(View(cat7, F // 2, F // 2 + F, 0), full(r5))
+        ops.axpby(View(cat7, F, F // 2 + F, F // 2), full(r4))
+        L["c7"] = Conv(w[(LW % 7) + "layer/w"], w[(LW % 7) + "layer/layer/bias"], 2, 0, transposed=True)   # :55
+        a7 = L["c7"].forward(full(cat7), N, S4, S4)
+        L["bn8"] = BatchNorm(w, 8)
+        r7 = L["bn8"].forward(a7.t, training)                                                  # :56
+        C9 = F // 4 + r2.shape[-1]
+        cat9 = ops.empty(N, S2, S2, C9)                                                        # :60
+        ops.axpby(View(cat9, F // 4, C9, 0), full(r7))
+        ops.axpby(View(cat9, r2.shape[-1], C9, F // 4), full(r2))
+        up = ops.empty(N, S, S, C9)
+        ops.upsample2x_fwd(cat9, up)                                                           # :62
+        L["c9"] = Conv(w[(LW % 9) + "layer/kernel"], w[(LW % 9) + "layer/bias"], 1, 2, transposed=True)     # :63-64
+        a9 = L["c9"].forward(full(up), N, S, S)
+        L["bn10"] = BatchNorm(w, 10)
+        r9 = L["bn10"].forward(a9.t, training)                                                 # :69
+        L["c11"] = Conv(w[(LW % 11) + "layer/kernel"], w[(LW % 11) + "layer/bias"], 1, 1, leaky=False)      # :70
+        out = L["c11"].forward(full(r9), N, S, S)
+        self.L, self.dims = L, (B, T, S, N, F, r2.shape[-1])
+        return out.t.view(B, T, S, S, -1)
+
+    def backward(self, dout):
+        """dout [B,T,S,S,Cout] -> dict of weight gradients (checkpoint names)."""
+        L = self.L
+        B, T, S, N, F, C2 = self.dims
+        S2, S4 = S // 2, S // 4
+        g = {}
+
+        def put(i, leafw, leafb, dw, db):
+            g[(LW % i) + leafw], g[(LW % i) + leafb] = dw, db
+
+        d = dout.reshape(N, S, S, -1).contiguous().clone()
+        dr9, dw, db = L["c11"].backward(d)
+        put(11, "layer/kernel", "layer/bias", dw, db)
+        da9, gb = L["bn10"].backward(dr9.t)
+        g.update(gb)
+        dup, dw, db = L["c9"].backward(da9)
+        put(9, "layer/kernel", "layer/bias", dw, db)
+        dcat9 = ops.empty(N, S2, S2, F // 4 + C2)
+        ops.upsample2x_bwd(dup.t, dcat9)
+        dr7 = ops.empty(N, S2, S2, F // 4)
+        ops.axpby(full(dr7), View(dcat9, F // 4, F // 4 + C2, 0))
+        dr2 = ops.empty(N, S2, S2, C2)
+        ops.axpby(full(dr2), View(dcat9, C2, F // 4 + C2, F // 4))
+        da7, gb = L["bn8"].backward(dr7)
+        g.update(gb)
+        dcat7, dw, db = L["c7"].backward(da7)
+        put(7, "layer/w", "layer/layer/bias", dw, db)
+        dr5 = ops.empty(N, S4, S4, F // 2)
+        ops.axpby(full(dr5), View(dcat7.t, F // 2, F // 2 + F, 0))
+        dr4 = ops.empty(N, S4, S4, F)
+        ops.axpby(full(dr4), View(dcat7.t, F, F // 2 + F, F // 2))
+        da5, gb = L["bn6"].backward(dr5)
+        g.update(gb)
+        dh, dw, db = L["c5"].backward(da5)
+        put(5, "layer/w", "layer/layer/bias", dw, db)
+        dx, dK, dR, dbl = L["lstm"].backward(dh.t)
+        g[(LW % 4) + "cell/kernel"], g[(LW % 4) + "cell/recurrent_kernel"], g[(LW % 4) + "cell/bias"] = dK, dR, dbl
+        ops.axpby(full(dr4), full(dr4), 1.0, full(dx), 1.0)
+        da2, gb = L["bn3"].backward(dr4)
+        g.update(gb)
+        dr2b, dw, db = L["c2"].backward(da2)
+        put(2, "layer/w", "layer/layer/bias", dw, db)
+        ops.axpby(full(dr2), full(dr2), 1.0, dr2b, 1.0)
+        da0, gb = L["bn1"].backward(dr2)
+        g.update(gb)
+        _, dw, db = L["c0"].backward(da0, need_dx=False)
+        put(0, "layer/w", "layer/layer/bias", dw, db)
+        return g
+
+
+# =============================================================================================== critic
+def critic_plan(size, F):
+    """Shapes of the pyramid built by models.py:111-136 (current code: the `i > 1` shortcut never triggers)."""
+    convs, idx, s, c = [], 6, size, 2 * F
+    while s >= 16:
+        so = (s + 2 - 7) // 3 + 1
+        convs.append(dict(idx=idx, ln=idx + 1, k=7, stride=3, pad=1, cin=c, cout=2 * c, size_in=s, size_out=so))
+        s, c, idx = so, 2 * c, idx + 2
+    i = 0
+    while s >= 4:
+        so = (s + 2 - 7) // 3 + 1
+        if so < 1:
+            raise ValueError("invalid image size for the critic")
+        convs.append(dict(idx=idx, ln=idx + 1, k=7, stride=3, pad=1, cin=c, cout=2 * c, size_in=s, size_out=so))
+        s, c, idx = so, 2 * c, idx + 2
+        i += 1
+    if i > 1:
+        raise NotImplementedError("shortcut branch (models.py:127-130) is unreachable for valid sizes")
+    while s > 2:
+        so = (s - 3) // 2 + 1
+        convs.append(dict(idx=idx, ln=idx + 1, k=3, stride=2, pad=0, cin=c, cout=2 * c, size_in=s, size_out=so))
+        s, c, idx = so, 2 * c, idx + 2
+    return convs, idx, s * s * c
+
+
+class CriticNet:
+    def __init__(self, weights, size):
+        self.w = weights
+        self.F = weights[(LW % 2) + "layer/w"].shape[-1]
+        self.convs, self.dense_idx, self.flat = critic_plan(size, self.F)
+        self.sn_layers = [2, 3] + [e["idx"] for e in self.convs]
+
+    def forward(self, low_res, high_res, training):
+        """[B,T,S,S,3], [B,T,S,S,2] -> score [B,1]."""
+        w, F = self.w, self.F
+        B, T, S = low_res.shape[:3]
+        N = B * T
+        if training:
+            for i in self.sn_layers:
+                sn_step(w, i)
+            # every training-mode call reads the variables at their current value (later in-place SN updates of the
+            # shared tensors must not leak into this call's backward): snapshot them
+            w = {k: (v.clone() if k.endswith(("/w", "kernel", "bias", "gamma", "beta")) else v) for k, v in w.items()}
+        cl, ch = low_res.shape[-1], high_res.shape[-1]
+        hr_in = high_res.reshape(N, S, S, ch).contiguous()
+        mix_in = ops.empty(N, S, S, cl + ch)                                                   # models.py:100
+        ops.axpby(View(mix_in, cl, cl + ch, 0), full(low_res.reshape(N, S, S, cl)))
+        ops.axpby(View(mix_in, ch, cl + ch, cl), full(hr_in))
+        L = {}
+        L["lstm_hr"] = ConvLSTM(w[(LW % 0) + "cell/kernel"], w[(LW % 0) + "cell/recurrent_kernel"], w[(LW % 0) + "cell/bias"])
+        h1 = L["lstm_hr"].forward(hr_in, B, T)                                                 # :93
+        L["c_hr"] = Conv(w[(LW % 2) + "layer/w"], w[(LW % 2) + "layer/layer/bias"], 1, 1)      # :94-96
+        a_hr = L["c_hr"].forward(full(h1), N, S, S)
+        x = ops.empty(N, S, S, 2 * F)                                                          # :108
+        L["ln_hr"] = LayerNorm(w, 4)
+        L["ln_hr"].forward(a_hr.t, View(x, F, 2 * F, 0))                                       # :97
+        L["lstm_mix"] = ConvLSTM(w[(LW % 1) + "cell/kernel"], w[(LW % 1) + "cell/recurrent_kernel"], w[(LW % 1) + "cell/bias"])
+        h2 = L["lstm_mix"].forward(mix_in, B, T)                                               # :101
+        L["c_mix"] = Conv(w[(LW % 3) + "layer/w"], w[(LW % 3) + "layer/layer/bias"], 1, 1)     # :102-104
+        a_mix = L["c_mix"].forward(full(h2), N, S, S)
+        L["ln_mix"] = LayerNorm(w, 5)
+        L["ln_mix"].forward(a_mix.t, View(x, F, 2 * F, F))                                     # :105
+        cur, size = x, S
+        for n, e in enumerate(self.convs):                                                     # :111-136
+            c = Conv(w[(LW % e["idx"]) + "layer/w"], w[(LW % e["idx"]) + "layer/layer/bias"], e["stride"], e["pad"])
+            a = c.forward(full(cur), N, size, size)
+            ln = LayerNorm(w, e["ln"])
+            cur = ln.forward(a.t).t
+            L["pc%d" % n], L["pln%d" % n] = c, ln
+            size = e["size_out"]
+        D = self.flat
+        score = ops.empty(B, 1)
+        dk, db_ = w[(LW % self.dense_idx) + "layer/kernel"], w[(LW % self.dense_idx) + "layer/bias"]
+        ops.dense_mean_fwd(cur, dk, db_, score, B, T, D)                                       # :137-140
+        self.L, self.dims, self.flat_act, self.w_used = L, (B, T, S, N, cl, ch), cur, w
+        return score
+
+    def backward(self, dscore, need_weight_grads=True, need_input_grad=False):
+        """dscore [B,1].  Returns (weight grads dict or {}, d high_res [B,T,S,S,ch] or None)."""
+        w, F, L = self.w_used, self.F, self.L
+        B, T, S, N, cl, ch = self.dims
+        g = {}
+        nw = need_weight_grads
+        D = self.flat
+        dk = w[(LW % self.dense_idx) + "layer/kernel"]
+        dflat = torch.empty_like(self.flat_act)
+        ddk, ddb = ops.empty(*dk.shape), ops.empty(1)
+        ops.dense_mean_bwd(dscore, self.flat_act, dk, dflat, ddk, ddb, B, T, D)
+        g[(LW % self.dense_idx) + "layer/kernel"], g[(LW % self.dense_idx) + "layer/bias"] = ddk, ddb
+        d = dflat
+        for n in range(len(self.convs) - 1, -1, -1):
+            e = self.convs[n]
+            da, gb = L["pln%d" % n].backward(full(d))
+            g.update(gb)
+            dxv, dw, db = L["pc%d" % n].backward(da, need_dw=nw)
+            g[(LW % e["idx"]) + "layer/w"], g[(LW % e["idx"]) + "layer/layer/bias"] = dw, db
+            d = dxv.t
+        # d: [N,S,S,2F] gradient of the concat(hr, mix)
+        d_hr_in = ops.zeros(N, S, S, ch) if need_input_grad else None
+        for tag, ln_i, conv_i, lstm_i, off in (("hr", 4, 2, 0, 0), ("mix", 5, 3, 1, F)):
+            da, gb = L["ln_" + tag].backward(View(d, F, 2 * F, off))
+            g.update(gb)
+            dh, dw, db = L["c_" + tag].backward(da, need_dw=nw)
+            g[(LW % conv_i) + "layer/w"], g[(LW % conv_i) + "layer/layer/bias"] = dw, db
+            dx, dK, dR, dbl = L["lstm_" + tag].backward(dh.t, need_dx=need_input_grad, need_dw=nw)
+            g[(LW % lstm_i) + "cell/kernel"], g[(LW % lstm_i) + "cell/recurrent_kernel"], g[(LW % lstm_i) + "cell/bias"] = dK, dR, dbl
+            if need_input_grad:
+                if tag == "hr":
+                    ops.axpby(full(d_hr_in), full(d_hr_in), 1.0, full(dx), 1.0)
+                else:
+                    ops.axpby(full(d_hr_in), full(d_hr_in), 1.0, View(dx, ch, cl + ch, cl), 1.0)
+        return (g if need_weight_grads else {}), (d_hr_in.view(B, T, S, S, ch) if need_input_grad else None)

@@ -192,3 +192,16 @@ def sn_update(w, u):
     R = w.numel() // Cl
     sc = scratch(R * 4, "sn")
     _lib.check(_lib.lib().wdg_sn_update(_p(w), _p(u), R, Cl, _p(sc), _s()))
+
+
+def bias_act(xv, bias, alpha=1.0):
+    """x = leaky(x + bias, alpha) in place on a channel view (alpha = 1: linear)."""
+    _lib.check(_lib.lib().wdg_bias_act(_p(xv.t), xv.cs, xv.co, _p(bias), xv.rows, xv.C, alpha, _s()))
+
+
+def transpose01(x):
+    """[A][B][...] -> [B][A][...] (new tensor)."""
+    A, B = x.shape[0], x.shape[1]
+    out = torch.empty((B, A) + tuple(x.shape[2:]), dtype=F32, device="cuda")
+    _lib.check(_lib.lib().wdg_transpose01(_p(x), _p(out), A, B, x.numel() // (A * B), _s()))
+    return out
