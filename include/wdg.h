@@ -135,6 +135,14 @@ int wdg_lerp_batch(float* out, const float* real, const float* fake, const float
 /* BatchNormalization (axis -1, eps, momentum): training mode uses batch statistics and updates the moving ones */
 int wdg_bn_train_fwd(const float* x, float* y, const float* gamma, const float* beta, float* moving_mean, float* moving_var,
                      float* save_mean, float* save_invstd, long long rows, int C, float eps, float momentum, void* scratch, void* stream);
+/* Split forms for data-parallel (synchronised) BatchNorm: per-channel sums are all-reduced by the caller */
+int wdg_bn_finalize_apply(const float* x, float* y, const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                          const float* s1, const float* s2, float* save_mean, float* save_invstd, long long rows_local,
+                          long long rows_global, int C, float eps, float momentum, void* stream);
+int wdg_bn_bwd_sums(const float* dy, const float* x, const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
+                    long long rows, int C, void* scratch, void* stream);
+int wdg_bn_bwd_dx(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
+                  const float* dgamma, const float* dbeta, float* dx, long long rows_local, long long rows_global, int C, void* stream);
 int wdg_bn_infer(const float* x, float* y, const float* gamma, const float* beta, const float* mean, const float* var,
                  long long rows, int C, float eps, void* scratch, void* stream);
 int wdg_bn_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,

@@ -276,12 +276,12 @@ __global__ void bn_finalize_kernel(const float* __restrict__ s1, const float* __
 __global__ void bn_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                               const float* __restrict__ invstd, const float* __restrict__ gamma,
                               const float* __restrict__ dbeta, const float* __restrict__ dgamma, float* __restrict__ dx,
-                              long long rows, int C) {
+                              long long rows, int C, long long rows_global) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * C) return;
   const int c = (int)(i % C);
   const float xhat = (x[i] - mean[c]) * invstd[c];
-  const float inv_r = 1.f / (float)rows;
+  const float inv_r = 1.f / (float)rows_global;
   dx[i] = gamma[c] * invstd[c] * (dy[i] - dbeta[c] * inv_r - xhat * dgamma[c] * inv_r);
 }
 // xhat-weighted sum needs xhat: dgamma[c] = sum dy * (x - mean) * invstd -> computed as colsum(dy * xhat) via this map
@@ -677,6 +677,40 @@ extern "C" int wdg_bn_train_fwd(const float* x, float* y, const float* gamma, co
   CKT(cudaGetLastError());
   return 0;
 }
+// Pieces of the above for data-parallel (synchronised) BatchNorm: the caller all-reduces the per-channel sums
+// between the two calls.  s1 = sum x, s2 = sum x^2 over `rows_global` rows.
+extern "C" int wdg_bn_finalize_apply(const float* x, float* y, const float* gamma, const float* beta, float* moving_mean,
+                                     float* moving_var, const float* s1, const float* s2, float* save_mean, float* save_invstd,
+                                     long long rows_local, long long rows_global, int C, float eps, float momentum,
+                                     void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  bn_finalize_kernel<<<blocks_for(C), 256, 0, stream>>>(s1, s2, rows_global, C, eps, momentum, save_mean, save_invstd, moving_mean, moving_var);
+  CKT(cudaGetLastError());
+  bn_apply_kernel<<<blocks_for(rows_local * C), 256, 0, stream>>>(x, y, save_mean, save_invstd, gamma, beta, rows_local, C);
+  CKT(cudaGetLastError());
+  return 0;
+}
+// dgamma_part = sum dy*xhat, dbeta_part = sum dy over the local rows (to be all-reduced), then dx with global sums.
+extern "C" int wdg_bn_bwd_sums(const float* dy, const float* x, const float* save_mean, const float* save_invstd, float* dgamma,
+                               float* dbeta, long long rows, int C, void* scratch, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float* tmp = (float*)scratch;
+  float* part = tmp + rows * C;
+  bn_xhat_mul_kernel<<<blocks_for(rows * C), 256, 0, stream>>>(dy, x, save_mean, save_invstd, tmp, rows, C);
+  CKT(cudaGetLastError());
+  if (wdg_colsum(0, tmp, C, 0, nullptr, 0, 0, rows, C, dgamma, part, 0, stream_)) return 1;
+  if (wdg_colsum(0, dy, C, 0, nullptr, 0, 0, rows, C, dbeta, part, 0, stream_)) return 1;
+  return 0;
+}
+extern "C" int wdg_bn_bwd_dx(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
+                             const float* dgamma, const float* dbeta, float* dx, long long rows_local, long long rows_global,
+                             int C, void* stream_) {
+  bn_bwd_kernel<<<blocks_for(rows_local * C), 256, 0, (cudaStream_t)stream_>>>(dy, x, save_mean, save_invstd, gamma, dbeta, dgamma, dx,
+                                                                              rows_local, C, rows_global);
+  CKT(cudaGetLastError());
+  return 0;
+}
+
 // Inference-mode BN with explicit statistics (moving mean / variance): invstd computed on the fly into scratch[C].
 extern "C" int wdg_bn_infer(const float* x, float* y, const float* gamma, const float* beta, const float* mean,
                             const float* var, long long rows, int C, float eps, void* scratch, void* stream_) {
@@ -699,7 +733,7 @@ extern "C" int wdg_bn_train_bwd(const float* dy, const float* x, const float* ga
   CKT(cudaGetLastError());
   if (wdg_colsum(0, tmp, C, 0, nullptr, 0, 0, rows, C, dgamma, part, 0, stream_)) return 1;
   if (wdg_colsum(0, dy, C, 0, nullptr, 0, 0, rows, C, dbeta, part, 0, stream_)) return 1;
-  bn_bwd_kernel<<<blocks_for(rows * C), 256, 0, stream>>>(dy, x, save_mean, save_invstd, gamma, dbeta, dgamma, dx, rows, C);
+  bn_bwd_kernel<<<blocks_for(rows * C), 256, 0, stream>>>(dy, x, save_mean, save_invstd, gamma, dbeta, dgamma, dx, rows, C, rows);
   CKT(cudaGetLastError());
   return 0;
 }

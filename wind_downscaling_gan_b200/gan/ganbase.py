@@ -43,12 +43,13 @@ class GAN:
             self._train = TrainState(self.generator, self.discriminator, self.generator.optimizer, self.discriminator.optimizer)
         return self._train
 
-    def train_step(self, data, draws=None):
+    def train_step(self, data, draws=None, comm=None):
         """ganbase.py:21-94.  data = (low_res, high_res[, sample_weight]); `draws` optionally replaces the random
         tensors (parity tests): per critic iteration [G noise, eps (B,), noise on real, noise on fake], then
-        G noise for the generator update and for the metric recompute."""
+        G noise for the generator update and for the metric recompute.  `comm` (train/dist.py Comm): data-parallel
+        training, `data` being this rank's shard of the global batch."""
         from ..train.step import train_step
-        return train_step(self._state(), data[0], data[1], self.noise_generator, self._n_critic, draws)
+        return train_step(self._state(), data[0], data[1], self.noise_generator, self._n_critic, draws, comm=comm)
 
     def test_step(self, data, draws=None):
         """ganbase.py:96-113."""

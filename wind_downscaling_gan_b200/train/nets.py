@@ -80,18 +80,32 @@ class Conv:
 
 
 class BatchNorm:
-    def __init__(self, w, i):
+    """BatchNormalization (axis -1).  With a communicator the batch statistics (and the two backward sums) are
+    all-reduced over the data-parallel ranks, which makes N ranks x local batch equivalent to the reference's single
+    process at the global batch; dgamma / dbeta returned by backward() are then already global sums."""
+
+    def __init__(self, w, i, comm=None):
         p = LW % i
         self.names = (p + "gamma", p + "beta", p + "moving_mean", p + "moving_variance")
-        self.w = w
+        self.w, self.comm = w, comm
 
     def forward(self, x, training):
         g, b, mm, mv = (self.w[n] for n in self.names)
         y = torch.empty_like(x)
         if training:
             C = x.shape[-1]
+            rows = x.numel() // C
             self.sm, self.si = ops.empty(C), ops.empty(C)
-            ops.bn_train_fwd(x, y, g, b, mm, mv, self.sm, self.si)
+            if self.comm is None or self.comm.world == 1:
+                ops.bn_train_fwd(x, y, g, b, mm, mv, self.sm, self.si)
+                self.rows_global = rows
+            else:
+                sums = ops.empty(2, C)
+                ops.colsum(full(x), sums[0], mode=0)
+                ops.colsum(full(x), sums[1], mode=2)
+                self.comm.allreduce_sum(sums)
+                self.rows_global = rows * self.comm.world
+                ops.bn_finalize_apply(x, y, g, b, mm, mv, sums[0], sums[1], self.sm, self.si, self.rows_global)
             self.x = x
         else:
             ops.bn_infer(x, y, g, b, mm, mv)
@@ -99,8 +113,16 @@ class BatchNorm:
 
     def backward(self, dy):
         C = self.x.shape[-1]
-        dx, dg, db = torch.empty_like(self.x), ops.empty(C), ops.empty(C)
-        ops.bn_train_bwd(dy, self.x, self.w[self.names[0]], self.sm, self.si, dx, dg, db)
+        dx = torch.empty_like(self.x)
+        if self.comm is None or self.comm.world == 1:
+            dg, db = ops.empty(C), ops.empty(C)
+            ops.bn_train_bwd(dy, self.x, self.w[self.names[0]], self.sm, self.si, dx, dg, db)
+        else:
+            sums = ops.empty(2, C)
+            ops.bn_bwd_sums(dy, self.x, self.sm, self.si, sums[0], sums[1])
+            self.comm.allreduce_sum(sums)
+            ops.bn_bwd_dx(dy, self.x, self.w[self.names[0]], self.sm, self.si, sums[0], sums[1], dx, self.rows_global)
+            dg, db = sums[0], sums[1]
         return dx, {self.names[0]: dg, self.names[1]: db}
 
 
@@ -184,8 +206,9 @@ def sn_step(w, idx):
 class GenNet:
     SN_LAYERS = (0, 2, 5, 7)
 
-    def __init__(self, weights):
+    def __init__(self, weights, comm=None):
         self.w = weights   # dict name -> CUDA tensor (shared with the caller; updated in place)
+        self.comm = comm   # data-parallel communicator: synchronised BatchNorm statistics
 
     def forward(self, image, noise, training):
         """image [B,T,S,S,Cin], noise [B,T,S,S,Cn] -> [B,T,S,S,Cout].  Keeps the context for backward()."""
@@ -202,19 +225,19 @@ class GenNet:
         L = {}
         L["c0"] = Conv(w[(LW % 0) + "layer/w"], w[(LW % 0) + "layer/layer/bias"], 2, 3)        # :32-33
         a0 = L["c0"].forward(full(x0), N, S, S)
-        L["bn1"] = BatchNorm(w, 1)
+        L["bn1"] = BatchNorm(w, 1, self.comm)
         r2 = L["bn1"].forward(a0.t, training)                                                  # :34
         S2 = S // 2
         L["c2"] = Conv(w[(LW % 2) + "layer/w"], w[(LW % 2) + "layer/layer/bias"], 2, 1)        # :38-39
         a2 = L["c2"].forward(full(r2), N, S2, S2)
-        L["bn3"] = BatchNorm(w, 3)
+        L["bn3"] = BatchNorm(w, 3, self.comm)
         r4 = L["bn3"].forward(a2.t, training)                                                  # :40
         S4 = S // 4
         L["lstm"] = ConvLSTM(w[(LW % 4) + "cell/kernel"], w[(LW % 4) + "cell/recurrent_kernel"], w[(LW % 4) + "cell/bias"])
         hseq = L["lstm"].forward(r4, B, T)                                                     # :45
         L["c5"] = Conv(w[(LW % 5) + "layer/w"], w[(LW % 5) + "layer/layer/bias"], 1, 1)        # :49
         a5 = L["c5"].forward(full(hseq), N, S4, S4)
-        L["bn6"] = BatchNorm(w, 6)
+        L["bn6"] = BatchNorm(w, 6, self.comm)
         r5 = L["bn6"].forward(a5.t, training)                                                  # :50
         F = r4.shape[-1]
         cat7 = ops.empty(N, S4, S4, F // 2 + F)                                                # :54
@@ -222,7 +245,7 @@ class GenNet:
         ops.axpby(View(cat7, F, F // 2 + F, F // 2), full(r4))
         L["c7"] = Conv(w[(LW % 7) + "layer/w"], w[(LW % 7) + "layer/layer/bias"], 2, 0, transposed=True)   # :55
         a7 = L["c7"].forward(full(cat7), N, S4, S4)
-        L["bn8"] = BatchNorm(w, 8)
+        L["bn8"] = BatchNorm(w, 8, self.comm)
         r7 = L["bn8"].forward(a7.t, training)                                                  # :56
         C9 = F // 4 + r2.shape[-1]
         cat9 = ops.empty(N, S2, S2, C9)                                                        # :60
@@ -232,7 +255,7 @@ class GenNet:
         ops.upsample2x_fwd(cat9, up)                                                           # :62
         L["c9"] = Conv(w[(LW % 9) + "layer/kernel"], w[(LW % 9) + "layer/bias"], 1, 2, transposed=True)     # :63-64
         a9 = L["c9"].forward(full(up), N, S, S)
-        L["bn10"] = BatchNorm(w, 10)
+        L["bn10"] = BatchNorm(w, 10, self.comm)
         r9 = L["bn10"].forward(a9.t, training)                                                 # :69
         L["c11"] = Conv(w[(LW % 11) + "layer/kernel"], w[(LW % 11) + "layer/bias"], 1, 1, leaky=False)      # :70
         out = L["c11"].forward(full(r9), N, S, S)

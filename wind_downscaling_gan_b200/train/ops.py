@@ -205,3 +205,22 @@ def transpose01(x):
     out = torch.empty((B, A) + tuple(x.shape[2:]), dtype=F32, device="cuda")
     _lib.check(_lib.lib().wdg_transpose01(_p(x), _p(out), A, B, x.numel() // (A * B), _s()))
     return out
+
+
+def bn_finalize_apply(x, y, gamma, beta, mm, mv, s1, s2, save_mean, save_invstd, rows_global, eps=1e-3, momentum=0.99):
+    Cc = x.shape[-1]
+    _lib.check(_lib.lib().wdg_bn_finalize_apply(_p(x), _p(y), _p(gamma), _p(beta), _p(mm), _p(mv), _p(s1), _p(s2), _p(save_mean),
+                                                _p(save_invstd), x.numel() // Cc, rows_global, Cc, eps, momentum, _s()))
+
+
+def bn_bwd_sums(dy, x, save_mean, save_invstd, dgamma, dbeta):
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    sc = scratch((rows * Cc + 64 * Cc) * 4, "norm_bwd")
+    _lib.check(_lib.lib().wdg_bn_bwd_sums(_p(dy), _p(x), _p(save_mean), _p(save_invstd), _p(dgamma), _p(dbeta), rows, Cc, _p(sc), _s()))
+
+
+def bn_bwd_dx(dy, x, gamma, save_mean, save_invstd, dgamma, dbeta, dx, rows_global):
+    Cc = x.shape[-1]
+    _lib.check(_lib.lib().wdg_bn_bwd_dx(_p(dy), _p(x), _p(gamma), _p(save_mean), _p(save_invstd), _p(dgamma), _p(dbeta), _p(dx),
+                                        x.numel() // Cc, rows_global, Cc, _s()))

@@ -43,9 +43,14 @@ def _mean_sq(grads):
     return float(np.mean([float(ops.reduce(g, 2, scale=1.0 / g.numel()).item()) for g in grads.values()]))
 
 
-def train_step(st, low_res, high_res, noise_generator, n_critic=3, draws=None, gamma=100.0):
+def train_step(st, low_res, high_res, noise_generator, n_critic=3, draws=None, gamma=100.0, comm=None):
+    """One WGAN step on this rank's share of the batch.  With a communicator (train/dist.py) the gradients are
+    all-reduced after every backward pass and BatchNorm statistics are synchronised, so `world` ranks x local batch
+    reproduce the reference's single process at the global batch."""
     low_res, high_res = _dev(low_res), _dev(high_res)
     B = low_res.shape[0]
+    world = comm.world if comm is not None else 1
+    Bg = B * world                                    # global batch: the loss means run over it
     it = iter(draws) if draws is not None else None
 
     def noise(channels=None):
@@ -58,7 +63,7 @@ def train_step(st, low_res, high_res, noise_generator, n_critic=3, draws=None, g
             return _dev(next(it)).reshape(B)
         return torch.rand(B, device="cuda", dtype=torch.float32)
 
-    gen = GenNet(st.g)
+    gen = GenNet(st.g, comm)
     out_ch = high_res.shape[-1]
     def const(v):
         return torch.full((B, 1), float(v), device="cuda", dtype=torch.float32)
@@ -88,19 +93,23 @@ def train_step(st, low_res, high_res, noise_generator, n_critic=3, draws=None, g
         d_fake = CriticNet(st.d, st.size)
         s_fake = d_fake.forward(low_res, fhr, training=True)                          # :43
         # d_loss = -(mean(real) - mean(fake)) + gradient_reg                          # :44-45, train.py:11-12
-        g1, _ = d_real.backward(const(-1.0 / B))
-        g2, _ = d_fake.backward(const(1.0 / B))
+        g1, _ = d_real.backward(const(-1.0 / Bg))
+        g2, _ = d_fake.backward(const(1.0 / Bg))
         d_grads = {}
         for n in g1:
             ops.axpby(ops.full(g1[n]), ops.full(g1[n]), 1.0, ops.full(g2[n]), 1.0)
             d_grads[n] = g1[n]
+        if comm is not None:
+            comm.allreduce_grads(d_grads)
         adam_apply(st.d, st.d_slots, d_grads, st.d_opt)                               # :46-47
     fake = gen.forward(low_res, noise(), training=True)                               # :51-52
     d_g = CriticNet(st.d, st.size)
     score = d_g.forward(low_res, fake, training=True)                                 # :53
     gen_disc_loss = -mean(score)                                       # :54
-    _, dfake = d_g.backward(const(-1.0 / B), need_weight_grads=False, need_input_grad=True)
+    _, dfake = d_g.backward(const(-1.0 / Bg), need_weight_grads=False, need_input_grad=True)
     g_grads = gen.backward(dfake)                                                     # :60
+    if comm is not None:   # BatchNorm gamma/beta gradients are already global sums (synchronised BN)
+        comm.allreduce_grads(g_grads, skip=[n for n in g_grads if n.endswith(("gamma", "beta"))])
     adam_apply(st.g, st.g_slots, g_grads, st.g_opt)                                   # :61
     # metric recompute, inference mode                                               # :64-68
     d_eval = CriticNet(st.d, st.size)
