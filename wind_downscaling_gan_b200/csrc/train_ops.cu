@@ -29,25 +29,61 @@ struct ConvGeo {
 
 // ------------------------------------------------------------------ implicit GEMM on CUDA cores
 // C[M][N] (+)= sum_k A(m,k) * B(k,n); 64x64 block tile, 16-deep K tiles, 256 threads x (4x4) outputs.
+// Each problem supplies tile loaders that (a) walk global memory along its contiguous axis and (b) decompose the
+// GEMM indices into (image, y, x) / (tap, channel) ONCE per thread instead of once per element.
 constexpr int TM = 64, TN = 64, TK = 16;
+using TileA = float[TK][TM + 4];
+using TileB = float[TK][TN + 4];
 
 struct FwdProblem {       // y = conv(x, w) + bias
   ConvGeo g; const float* x; const float* w; const float* bias; float* y; int accumulate;
   __device__ int M() const { return g.N * g.Ho * g.Wo; }
   __device__ int Nn() const { return g.Co; }
   __device__ int K() const { return g.kh * g.kw * g.Ci; }
-  __device__ float A(int m, int k) const {
-    const int ci = k % g.Ci, tap = k / g.Ci, kx = tap % g.kw, ky = tap / g.kw;
-    const int ox = m % g.Wo, oy = (m / g.Wo) % g.Ho, n = m / (g.Wo * g.Ho);
-    const int iy = oy * g.stride - g.pad_t + ky, ix = ox * g.stride - g.pad_l + kx;
-    if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) return 0.f;
-    return x[(((long long)n * g.H + iy) * g.W + ix) * g.x_cs + g.x_co + ci];
-  }
-  __device__ float B(int k, int n) const { return w[(long long)k * g.Co + n]; }
+  struct ALoader {        // K-fastest: thread owns column kk = tid & 15 and rows (tid >> 4) + 16 i
+    const FwdProblem& p; int kk; int iy0[4], ix0[4]; const float* base[4];
+    __device__ ALoader(const FwdProblem& p_, int m0, int tid) : p(p_), kk(tid & 15) {
+      const ConvGeo& g = p.g;
+      const int M = p.M();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + (tid >> 4) + 16 * i;
+        if (m < M) {
+          const int ox = m % g.Wo, oy = (m / g.Wo) % g.Ho, n = m / (g.Wo * g.Ho);
+          iy0[i] = oy * g.stride - g.pad_t; ix0[i] = ox * g.stride - g.pad_l;
+          base[i] = p.x + (long long)n * g.H * g.W * g.x_cs + g.x_co;
+        } else { iy0[i] = -(1 << 28); ix0[i] = 0; base[i] = p.x; }
+      }
+    }
+    __device__ void load(TileA& sA, int tid, int k0, int k_end) const {
+      const ConvGeo& g = p.g;
+      const int k = k0 + kk;
+      const bool kv = k < k_end;
+      const int ci = k % g.Ci, tap = k / g.Ci, kx = tap % g.kw, ky = tap / g.kw;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int iy = iy0[i] + ky, ix = ix0[i] + kx;
+        float v = 0.f;
+        if (kv && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) v = base[i][((long long)iy * g.W + ix) * g.x_cs + ci];
+        sA[kk][(tid >> 4) + 16 * i] = v;
+      }
+    }
+  };
+  struct BLoader {        // N-fastest: w[k][n]
+    const FwdProblem& p; int n; bool nv;
+    __device__ BLoader(const FwdProblem& p_, int n0, int tid) : p(p_), n(n0 + (tid & 63)), nv(n0 + (tid & 63) < p_.g.Co) {}
+    __device__ void load(TileB& sB, int tid, int k0, int k_end) const {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = (tid >> 6) + 4 * i, k = k0 + kk;
+        sB[kk][tid & 63] = (nv && k < k_end) ? p.w[(long long)k * p.g.Co + n] : 0.f;
+      }
+    }
+  };
   __device__ void store(int m, int n, float v) const {
-    float* p = y + (long long)m * g.y_cs + g.y_co + n;
+    float* q = y + (long long)m * g.y_cs + g.y_co + n;
     if (bias) v += bias[n];
-    *p = accumulate ? *p + v : v;
+    *q = accumulate ? *q + v : v;
   }
 };
 
@@ -56,22 +92,58 @@ struct BwdDataProblem {   // dx = conv_bwd_data(dy, w)
   __device__ int M() const { return g.N * g.H * g.W; }
   __device__ int Nn() const { return g.Ci; }
   __device__ int K() const { return g.kh * g.kw * g.Co; }
-  __device__ float A(int m, int k) const {
-    const int co = k % g.Co, tap = k / g.Co, kx = tap % g.kw, ky = tap / g.kw;
-    const int ix = m % g.W, iy = (m / g.W) % g.H, n = m / (g.W * g.H);
-    const int ty = iy + g.pad_t - ky, tx = ix + g.pad_l - kx;
-    if (ty < 0 || tx < 0 || ty % g.stride || tx % g.stride) return 0.f;
-    const int oy = ty / g.stride, ox = tx / g.stride;
-    if (oy >= g.Ho || ox >= g.Wo) return 0.f;
-    return dy[(((long long)n * g.Ho + oy) * g.Wo + ox) * g.y_cs + g.y_co + co];
-  }
-  __device__ float B(int k, int n) const {   // w[ky][kx][ci = n][co]
-    const int co = k % g.Co, tap = k / g.Co;
-    return w[((long long)tap * g.Ci + n) * g.Co + co];
-  }
+  struct ALoader {        // K-fastest (co is the inner K index and contiguous in dy)
+    const BwdDataProblem& p; int kk; int ty0[4], tx0[4]; const float* base[4];
+    __device__ ALoader(const BwdDataProblem& p_, int m0, int tid) : p(p_), kk(tid & 15) {
+      const ConvGeo& g = p.g;
+      const int M = p.M();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + (tid >> 4) + 16 * i;
+        if (m < M) {
+          const int ix = m % g.W, iy = (m / g.W) % g.H, n = m / (g.W * g.H);
+          ty0[i] = iy + g.pad_t; tx0[i] = ix + g.pad_l;
+          base[i] = p.dy + (long long)n * g.Ho * g.Wo * g.y_cs + g.y_co;
+        } else { ty0[i] = -(1 << 28); tx0[i] = 0; base[i] = p.dy; }
+      }
+    }
+    __device__ void load(TileA& sA, int tid, int k0, int k_end) const {
+      const ConvGeo& g = p.g;
+      const int k = k0 + kk;
+      const bool kv = k < k_end;
+      const int co = k % g.Co, tap = k / g.Co, kx = tap % g.kw, ky = tap / g.kw;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ty = ty0[i] - ky, tx = tx0[i] - kx;
+        float v = 0.f;
+        if (kv && ty >= 0 && tx >= 0) {
+          int oy = ty, ox = tx;
+          bool ok = true;
+          if (g.stride > 1) { oy = ty / g.stride; ox = tx / g.stride; ok = (oy * g.stride == ty) && (ox * g.stride == tx); }
+          if (ok && oy < g.Ho && ox < g.Wo) v = base[i][((long long)oy * g.Wo + ox) * g.y_cs + co];
+        }
+        sA[kk][(tid >> 4) + 16 * i] = v;
+      }
+    }
+  };
+  struct BLoader {        // K-fastest: w[tap][ci = n][co], co contiguous
+    const BwdDataProblem& p; int kk; int n0;
+    __device__ BLoader(const BwdDataProblem& p_, int n0_, int tid) : p(p_), kk(tid & 15), n0(n0_) {}
+    __device__ void load(TileB& sB, int tid, int k0, int k_end) const {
+      const ConvGeo& g = p.g;
+      const int k = k0 + kk;
+      const bool kv = k < k_end;
+      const int co = k % g.Co, tap = k / g.Co;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int nn = (tid >> 4) + 16 * i, n = n0 + nn;
+        sB[kk][nn] = (kv && n < g.Ci) ? p.w[((long long)tap * g.Ci + n) * g.Co + co] : 0.f;
+      }
+    }
+  };
   __device__ void store(int m, int n, float v) const {
-    float* p = dx + (long long)m * g.x_cs + g.x_co + n;
-    *p = accumulate ? *p + v : v;
+    float* q = dx + (long long)m * g.x_cs + g.x_co + n;
+    *q = accumulate ? *q + v : v;
   }
 };
 
@@ -80,46 +152,62 @@ struct BwdWeightProblem {  // dw[tap][ci][co] = sum over pixels x * dy; split ov
   __device__ int M() const { return g.kh * g.kw * g.Ci; }
   __device__ int Nn() const { return g.Co; }
   __device__ int K() const { return g.N * g.Ho * g.Wo; }
-  __device__ float A(int m, int k) const {
-    const int ci = m % g.Ci, tap = m / g.Ci, kx = tap % g.kw, ky = tap / g.kw;
-    const int ox = k % g.Wo, oy = (k / g.Wo) % g.Ho, n = k / (g.Wo * g.Ho);
-    const int iy = oy * g.stride - g.pad_t + ky, ix = ox * g.stride - g.pad_l + kx;
-    if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) return 0.f;
-    return x[(((long long)n * g.H + iy) * g.W + ix) * g.x_cs + g.x_co + ci];
-  }
-  __device__ float B(int k, int n) const { return dy[(long long)k * g.y_cs + g.y_co + n]; }
+  struct ALoader {        // M-fastest: m = (tap, ci), ci contiguous in x
+    const BwdWeightProblem& p; int ky, kx, ci; bool mv;
+    __device__ ALoader(const BwdWeightProblem& p_, int m0, int tid) : p(p_) {
+      const ConvGeo& g = p.g;
+      const int m = m0 + (tid & 63);
+      mv = m < p.M();
+      ci = m % g.Ci;
+      const int tap = m / g.Ci;
+      kx = tap % g.kw; ky = tap / g.kw;
+    }
+    __device__ void load(TileA& sA, int tid, int k0, int k_end) const {
+      const ConvGeo& g = p.g;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = (tid >> 6) + 4 * i, k = k0 + kk;
+        float v = 0.f;
+        if (mv && k < k_end) {
+          const int ox = k % g.Wo, oy = (k / g.Wo) % g.Ho, n = k / (g.Wo * g.Ho);
+          const int iy = oy * g.stride - g.pad_t + ky, ix = ox * g.stride - g.pad_l + kx;
+          if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) v = p.x[(((long long)n * g.H + iy) * g.W + ix) * g.x_cs + g.x_co + ci];
+        }
+        sA[kk][tid & 63] = v;
+      }
+    }
+  };
+  struct BLoader {        // N-fastest: dy[k][co]
+    const BwdWeightProblem& p; int n; bool nv;
+    __device__ BLoader(const BwdWeightProblem& p_, int n0, int tid) : p(p_), n(n0 + (tid & 63)), nv(n0 + (tid & 63) < p_.g.Co) {}
+    __device__ void load(TileB& sB, int tid, int k0, int k_end) const {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = (tid >> 6) + 4 * i, k = k0 + kk;
+        sB[kk][tid & 63] = (nv && k < k_end) ? p.dy[(long long)k * p.g.y_cs + p.g.y_co + n] : 0.f;
+      }
+    }
+  };
 };
 
 template <class P>
 __device__ __forceinline__ void gemm_tile(const P& p, int m0, int n0, int k_begin, int k_end, float (&acc)[4][4]) {
-  __shared__ float sA[TK][TM + 4];
-  __shared__ float sB[TK][TN + 4];
+  __shared__ __align__(16) TileA sA;
+  __shared__ __align__(16) TileB sB;
   const int tid = threadIdx.x;
   const int tm = (tid / 16) * 4, tn = (tid % 16) * 4;
-  const int M = p.M(), N = p.Nn();
+  const typename P::ALoader la(p, m0, tid);
+  const typename P::BLoader lb(p, n0, tid);
   for (int k0 = k_begin; k0 < k_end; k0 += TK) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {            // A tile: 64 x 16, consecutive threads along m (or k) for coalescing
-      const int e = tid + i * 256;
-      const int mm = e % TM, kk = e / TM;
-      const int m = m0 + mm, k = k0 + kk;
-      sA[kk][mm] = (m < M && k < k_end) ? p.A(m, k) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {            // B tile: 16 x 64
-      const int e = tid + i * 256;
-      const int nn = e % TN, kk = e / TN;
-      const int n = n0 + nn, k = k0 + kk;
-      sB[kk][nn] = (n < N && k < k_end) ? p.B(k, n) : 0.f;
-    }
+    la.load(sA, tid, k0, k_end);
+    lb.load(sB, tid, k0, k_end);
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sA[kk][tm + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = sB[kk][tn + j];
+      const float4 a4 = *reinterpret_cast<const float4*>(&sA[kk][tm]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&sB[kk][tn]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
