@@ -76,6 +76,12 @@ int wdg_generator_io_bytes(const wdg_generator* g, int B, int T, size_t* bytes);
 int wdg_generator_predict_host(wdg_generator* g, const float* image_host, const float* noise_host,
                                float* out_host, void* io_dev, void* stream);
 
+/* As predict_host, but the noise (B,T,S,S,Cnoise) ~ N(0, noise_std^2) is generated on the device (wdg_noise_normal with
+ * key noise_seed, starting at counter block noise_offset), as the reference's FlexibleNoiseGenerator does with the
+ * TensorFlow generator (api.py:136): only the image crosses PCIe. */
+int wdg_generator_predict_host_gen_noise(wdg_generator* g, const float* image_host, float noise_std, uint64_t noise_seed,
+                                         uint64_t noise_offset, float* out_host, void* io_dev, void* stream);
+
 /* Number of kernels one forward() launches for the bound plan (bench.py's gpu_launches). */
 int wdg_generator_launches_per_forward(const wdg_generator* g);
 
@@ -111,6 +117,12 @@ int wdg_gather_normalise(const float* u10_dev, const float* v10_dev, const float
 int wdg_stitch(const float* pred_dev, const int* starts_x_dev, int nx, const int* starts_y_dev, int ny, int ntimeseq,
                int seq, int img, int crop, int channels, const int* rows_dev, int nrows, const int* cols_dev, int ncols,
                float* out_dev, void* stream);
+
+/* ---- On-device noise for FlexibleNoiseGenerator (data/data_generator.py:319-335): out[i] ~ N(0, stddev^2) from
+ * Philox4x32-10 + Box-Muller; element 4j..4j+3 come from counter block `offset + j` under key `seed`, so a generator
+ * advances `offset` by ceil(n/4) per call.  wdg_philox4x32_10 is the host-callable block function (known-answer tests). */
+void wdg_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+int wdg_noise_normal(float* out_dev, long long n, float stddev, uint64_t seed, uint64_t offset, void* stream);
 
 /* ---- fp32 building blocks of the WGAN training step (ganbase.py:21-94): critic forward/backward, training-mode
  * generator, optimiser.  Channels-last fp32 device tensors; `*_cs` / `*_co` = channel stride / offset of a tensor

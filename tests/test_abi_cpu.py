@@ -69,3 +69,15 @@ def test_tf_checkpoint_bundle_roundtrip(tmp_path):
     assert set(r) == set(t) and all(np.array_equal(r[k], t[k]) for k in t)
     idx = read_index(str(tmp_path / "generator") + ".index")
     assert idx["layer_with_weights-1/gamma/.ATTRIBUTES/VARIABLE_VALUE"]["shape"] == [5]
+
+
+def test_philox_known_answers(lib):
+    """Philox4x32-10 block function against the Random123 known-answer vectors (Salmon et al., SC'11)."""
+    import ctypes as C
+    def ph(ctr, key):
+        c, k, o = (C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), (C.c_uint32 * 4)()
+        lib.wdg_philox4x32_10(c, k, o)
+        return [int(v) for v in o]
+    assert ph([0] * 4, [0] * 2) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert ph([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert ph([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]

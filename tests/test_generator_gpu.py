@@ -164,5 +164,11 @@ def test_error_behaviour(mk):
         gen.set_weights({"nope": np.zeros(3)})
     with pytest.raises(ValueError):
         gen.set_weights({"layer_with_weights-1/gamma": np.zeros(3)})
-    with pytest.raises(NotImplementedError):
-        gen([image, noise], training=True)
+    # training-mode call (batch statistics + spectral-norm power iteration) runs on the fp32 training kernels and,
+    # like the Keras wrapper, mutates the stored kernel / sn_u / BatchNorm moving statistics
+    before = gen.get_weights()
+    out = gen([image, noise], training=True)
+    assert tuple(out.shape) == (1, 2, 96, 96, 2)
+    after = gen.get_weights()
+    assert not np.array_equal(before["layer_with_weights-0/layer/sn_u"], after["layer_with_weights-0/layer/sn_u"])
+    assert not np.array_equal(before["layer_with_weights-1/moving_mean"], after["layer_with_weights-1/moving_mean"])

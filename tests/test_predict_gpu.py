@@ -127,3 +127,24 @@ def test_noise_generator_shapes_and_std():
     assert tuple(g(channels=2).shape) == (8, 24, 96, 96, 2)
     b = FlexibleNoiseGenerator((8, 24, 96, 96, 20), std=0.1, random_seed=3)(bs=2, channels=20)
     assert bool((a == b).all())
+    c = g(bs=2, channels=20)                       # the stream advances between calls
+    assert not bool((a == c).all())
+    z = (a / 0.1).double()
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.05 and abs(float((z ** 3).mean())) < 0.02   # Gaussian moments
+
+
+def test_predict_host_with_device_noise_matches_explicit_noise():
+    """The generated-noise host entry point equals predict_host fed with the same Philox stream (both chunked paths)."""
+    import torch
+    from oracle.generator import synthetic_generator_weights
+    from wind_downscaling_gan_b200.data.data_generator import FlexibleNoiseGenerator
+    from wind_downscaling_gan_b200.gan.models import make_generator
+    for B in (3, 35):
+        T, S = 2, 32
+        gen = make_generator(S, 3, 20, 2, T)
+        gen.set_weights(synthetic_generator_weights(9))
+        image = torch.randn((B, T, S, S, 3)).pin_memory()
+        noise = FlexibleNoiseGenerator((B, T, S, S, 20), std=0.1, random_seed=5)()
+        ref = gen.predict_host(image, noise.cpu())
+        got = gen.predict_host_gen_noise(image, FlexibleNoiseGenerator((B, T, S, S, 20), std=0.1, random_seed=5))
+        assert torch.equal(ref, got)

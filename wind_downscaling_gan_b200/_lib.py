@@ -35,6 +35,7 @@ def _declare(lib):
         "wdg_generator_forward": [vp, vp, vp, vp, vp],
         "wdg_generator_io_bytes": [vp, i, i, C.POINTER(sz)],
         "wdg_generator_predict_host": [vp, vp, vp, vp, vp, vp],
+        "wdg_generator_predict_host_gen_noise": [vp, vp, C.c_float, C.c_uint64, C.c_uint64, vp, vp, vp],
         "wdg_generator_launches_per_forward": [vp],
         "wdg_generator_debug_read": [vp, i, vp, C.c_int64],
         "wdg_generator_profile": [vp, i],
@@ -75,6 +76,7 @@ def _declare(lib):
         "wdg_gp_norm": [vp, vp, i, ll, i, vp],
         "wdg_adam": [vp, vp, vp, vp, ll, f, f, f, f, vp],
         "wdg_sn_update": [vp, vp, i, i, vp, vp],
+        "wdg_noise_normal": [vp, ll, f, C.c_uint64, C.c_uint64, vp],
     })
     for name, args in sigs.items():
         if not hasattr(lib, name):
@@ -82,6 +84,8 @@ def _declare(lib):
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = i
+    lib.wdg_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.wdg_philox4x32_10.restype = None
     lib.wdg_generator_destroy.argtypes = [vp]
     lib.wdg_generator_destroy.restype = None
     del fp

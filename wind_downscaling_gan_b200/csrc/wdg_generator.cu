@@ -859,9 +859,9 @@ extern "C" int wdg_generator_stage_ms(wdg_generator* g, float* ms, int n) {
 // Host-buffer entry point.  For B >= 2*CHUNK_B the batch is cut into chunks of CHUNK_B sequences and pipelined over
 // three streams: H2D copy of chunk i+1 | forward of chunk i | D2H copy of chunk i-1 (double-buffered staging), so the
 // step costs ~max(PCIe, compute) instead of their sum.  Sequences are independent, so chunking does not change results.
-extern "C" int wdg_generator_predict_host(wdg_generator* g, const float* image_host, const float* noise_host,
-                                          float* out_host, void* io_dev, void* stream_) {
-  if (!g || !image_host || !noise_host || !out_host || !io_dev) return fail("null argument");
+static int predict_host_impl(wdg_generator* g, const float* image_host, const float* noise_host, float noise_std,
+                             uint64_t noise_seed, uint64_t noise_offset, float* out_host, void* io_dev, void* stream_) {
+  if (!g || !image_host || !out_host || !io_dev) return fail("null argument");
   const Plan& full = g->plans[0];
   if (full.B == 0) return fail("wdg_generator_bind must be called before predict_host");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -874,7 +874,8 @@ extern "C" int wdg_generator_predict_host(wdg_generator* g, const float* image_h
     float* d_noise = (float*)(io + align_up(b_img, 256));
     float* d_out = (float*)(io + align_up(b_img, 256) + align_up(b_noise, 256));
     CK(cudaMemcpyAsync(d_img, image_host, b_img, cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(d_noise, noise_host, b_noise, cudaMemcpyHostToDevice, stream));
+    if (noise_host) CK(cudaMemcpyAsync(d_noise, noise_host, b_noise, cudaMemcpyHostToDevice, stream));
+    else if (wdg_noise_normal(d_noise, (long long)(b_noise / 4), noise_std, noise_seed, noise_offset, stream)) return 1;
     if (run_plan(g, full, d_img, d_noise, d_out, stream, false)) return 1;
     CK(cudaMemcpyAsync(out_host, d_out, b_out, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
@@ -904,10 +905,14 @@ extern "C" int wdg_generator_predict_host(wdg_generator* g, const float* image_h
     float* d_out = (float*)(io + buf * slot + align_up(cb * s_img, 256) + align_up(cb * s_noise, 256));
     if (i >= 2) CK(cudaStreamWaitEvent(g->copy_in, g->ev_fwd[buf], 0));       // inputs of chunk i-2 consumed
     CK(cudaMemcpyAsync(d_img, (const uint8_t*)image_host + b0 * s_img, nb * s_img, cudaMemcpyHostToDevice, g->copy_in));
-    CK(cudaMemcpyAsync(d_noise, (const uint8_t*)noise_host + b0 * s_noise, nb * s_noise, cudaMemcpyHostToDevice, g->copy_in));
+    if (noise_host)
+      CK(cudaMemcpyAsync(d_noise, (const uint8_t*)noise_host + b0 * s_noise, nb * s_noise, cudaMemcpyHostToDevice, g->copy_in));
     CK(cudaEventRecord(g->ev_h2d[buf], g->copy_in));
     CK(cudaStreamWaitEvent(stream, g->ev_h2d[buf], 0));
     if (i >= 2) CK(cudaStreamWaitEvent(stream, g->ev_d2h[buf], 0));          // output of chunk i-2 copied out
+    if (!noise_host &&   // element index of this chunk in the whole noise tensor is a multiple of 4: counter blocks line up
+        wdg_noise_normal(d_noise, (long long)(nb * s_noise / 4), noise_std, noise_seed, noise_offset + b0 * (s_noise / 16), stream))
+      return 1;
     if (run_plan(g, pl, d_img, d_noise, d_out, stream, false)) return 1;
     CK(cudaEventRecord(g->ev_fwd[buf], stream));
     CK(cudaStreamWaitEvent(g->copy_out, g->ev_fwd[buf], 0));
@@ -917,6 +922,18 @@ extern "C" int wdg_generator_predict_host(wdg_generator* g, const float* image_h
   CK(cudaStreamSynchronize(g->copy_out));
   CK(cudaStreamSynchronize(stream));
   return 0;
+}
+
+extern "C" int wdg_generator_predict_host(wdg_generator* g, const float* image_host, const float* noise_host,
+                                          float* out_host, void* io_dev, void* stream) {
+  if (!noise_host) return fail("null argument");
+  return predict_host_impl(g, image_host, noise_host, 0.f, 0, 0, out_host, io_dev, stream);
+}
+
+extern "C" int wdg_generator_predict_host_gen_noise(wdg_generator* g, const float* image_host, float noise_std,
+                                                    uint64_t noise_seed, uint64_t noise_offset, float* out_host,
+                                                    void* io_dev, void* stream) {
+  return predict_host_impl(g, image_host, nullptr, noise_std, noise_seed, noise_offset, out_host, io_dev, stream);
 }
 
 extern "C" int wdg_generator_launches_per_forward(const wdg_generator* g) { return g ? g->plans[0].launches : 0; }

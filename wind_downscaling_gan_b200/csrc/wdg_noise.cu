@@ -1,0 +1,81 @@
+// On-device Gaussian noise for FlexibleNoiseGenerator (reference data/data_generator.py:319-335, which draws from
+// TensorFlow's Philox generator on the compute device): counter-based Philox4x32-10 + Box-Muller, so the
+// (B,T,S,S,20) noise tensor -- 87 % of the generator's input bytes -- never crosses PCIe.
+// The bit stream is NOT TensorFlow's (its counter/key bookkeeping cannot be verified here); parity runs pass
+// explicit noise tensors instead.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/wdg.h"
+
+extern int wdg_set_error(const std::string& m);
+
+namespace {
+
+struct U4 { uint32_t x, y, z, w; };
+
+__host__ __device__ inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+
+// Philox4x32 with 10 rounds (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11)
+__host__ __device__ inline U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = mulhi32(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = mulhi32(M1, c.z), lo1 = M1 * c.z;
+    c = U4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
+    k0 += W0; k1 += W1;
+  }
+  return c;
+}
+
+__device__ inline float u32_to_unit(uint32_t x) {   // 23 mantissa bits -> [0, 1)
+  return __uint_as_float((x & 0x7fffffu) | 0x3f800000u) - 1.0f;
+}
+
+// Each thread produces 4 consecutive normals from one Philox block (counter = offset + block index).
+__global__ void noise_normal_kernel(float* __restrict__ out, long long n, float stddev, uint32_t k0, uint32_t k1,
+                                    unsigned long long offset) {
+  const long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i0 = blk * 4;
+  if (i0 >= n) return;
+  const unsigned long long ctr = offset + (unsigned long long)blk;
+  const U4 r = philox4x32_10(U4{(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u}, k0, k1);
+  float v[4];
+  {
+    float u1 = fmaxf(u32_to_unit(r.x), 1.0e-7f);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincosf(6.283185307179586f * u32_to_unit(r.y), &s, &c);
+    v[0] = s * rad; v[1] = c * rad;
+    u1 = fmaxf(u32_to_unit(r.z), 1.0e-7f);
+    const float rad2 = sqrtf(-2.0f * logf(u1));
+    sincosf(6.283185307179586f * u32_to_unit(r.w), &s, &c);
+    v[2] = s * rad2; v[3] = c * rad2;
+  }
+  if (i0 + 3 < n && (reinterpret_cast<uintptr_t>(out + i0) & 15) == 0) {
+    *reinterpret_cast<float4*>(out + i0) = make_float4(v[0] * stddev, v[1] * stddev, v[2] * stddev, v[3] * stddev);
+  } else {
+    for (int j = 0; j < 4 && i0 + j < n; ++j) out[i0 + j] = v[j] * stddev;
+  }
+}
+
+}  // namespace
+
+extern "C" void wdg_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  const U4 r = philox4x32_10(U4{ctr[0], ctr[1], ctr[2], ctr[3]}, key[0], key[1]);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+extern "C" int wdg_noise_normal(float* out_dev, long long n, float stddev, uint64_t seed, uint64_t offset, void* stream) {
+  if (!out_dev || n < 0) return wdg_set_error("bad argument");
+  if (n == 0) return 0;
+  const long long blocks4 = (n + 3) / 4;
+  noise_normal_kernel<<<(unsigned)((blocks4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out_dev, n, stddev, (uint32_t)seed,
+                                                                                         (uint32_t)(seed >> 32), offset);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return wdg_set_error(std::string("noise_normal_kernel: ") + cudaGetErrorString(e));
+  return 0;
+}

@@ -226,6 +226,24 @@ class Generator(_NativeModel):
                                                          C.c_void_p(s)))
         return out
 
+    def predict_host_gen_noise(self, image, noise_generator, out=None):
+        """Host image in, host result out, noise drawn ON THE DEVICE from `noise_generator`'s Philox stream (what
+        `gen.predict([tensor, network.noise_generator(...)])` does in the reference, api.py:136-137)."""
+        import torch
+        img = image if isinstance(image, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(image, np.float32))
+        img = img.contiguous()
+        B, T, S = img.shape[:3]
+        self._ensure_plan(B, T)
+        if out is None:
+            out = torch.empty((B, T, S, S, self.out_channels), dtype=torch.float32)
+        n = B * T * S * S * self.noise_channels
+        s = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().wdg_generator_predict_host_gen_noise(
+            self._h, C.c_void_p(img.data_ptr()), float(noise_generator.std), C.c_uint64(noise_generator._seed & (2 ** 64 - 1)),
+            C.c_uint64(noise_generator._offset), C.c_void_p(out.data_ptr()), C.c_void_p(self._io.data_ptr()), C.c_void_p(s)))
+        noise_generator._offset += (n + 3) // 4
+        return out
+
     def predict(self, inputs, batch_size=None, verbose=0, **kwargs):
         """Keras `Model.predict([image, noise])` (api.py:137): returns a numpy array."""
         image, noise = inputs
