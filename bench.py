@@ -276,9 +276,14 @@ def main():
             stages[name] = ent
         dom = max(stage_ms, key=stage_ms.get)
         d = stages[dom]
+        traffic = None
+        try:   # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[dom]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"],
                     "peak": peaks["bf16_tflops_sustained"] if d["bound"] == "tensor" else peaks["hbm_gbs"],
-                    "unit": d["unit"], "frac": d["frac"], "traffic": None,
+                    "unit": d["unit"], "frac": d["frac"], "traffic": traffic,
                     "avg_launch_ms": d["ms_per_step"] / d["launches_per_step"], "peak_source": peaks["source"] +
                     (" (sustained bf16: kernel timed inside a long step)" if d["bound"] == "tensor" else ""),
                     "whole_forward": {"achieved": FLOP_PER_FIELD * value / world / 1e12, "unit": "TFLOP/s",
