@@ -31,22 +31,35 @@ struct ConvGeo {
 // C[M][N] (+)= sum_k A(m,k) * B(k,n); 64x64 block tile, 16-deep K tiles, 256 threads x (4x4) outputs.
 // Each problem supplies tile loaders that (a) walk global memory along its contiguous axis and (b) decompose the
 // GEMM indices into (image, y, x) / (tap, channel) ONCE per thread instead of once per element.
-constexpr int TM = 64, TN = 64, TK = 16;
-using TileA = float[TK][TM + 4];
-using TileB = float[TK][TN + 4];
+// Two tile shapes: 64x64 (4x4 outputs per thread) and, for GEMMs whose N axis is <= 16 wide (tiny channel counts of
+// the critic's ConvLSTMs, the 16-channel transposed conv, 2-channel output conv), 128x16 (2x4 per thread).
+constexpr int TK = 16;
+template <int TM, int TN>
+struct Tiles {
+  using A = float[TK][TM + 4];
+  using B = float[TK][TN + 4];
+  static constexpr int RA = TM / 16;            // A elements per thread (K-fastest: rows (tid>>4) + 16 i)
+  static constexpr int RBK = TN / 16;           // B elements per thread, K-fastest loaders
+  static constexpr int RBN = TN * TK / 256;     // B elements per thread, N-fastest loaders
+  static constexpr int KSTEP_N = 256 / TN;      // k rows covered per pass by N-fastest loaders
+  static constexpr int RAM = TM * TK / 256;     // A elements per thread, M-fastest loader
+  static constexpr int KSTEP_M = 256 / TM;
+};
 
 struct FwdProblem {       // y = conv(x, w) + bias
   ConvGeo g; const float* x; const float* w; const float* bias; float* y; int accumulate;
   __device__ int M() const { return g.N * g.Ho * g.Wo; }
   __device__ int Nn() const { return g.Co; }
   __device__ int K() const { return g.kh * g.kw * g.Ci; }
+  template <int TM, int TN>
   struct ALoader {        // K-fastest: thread owns column kk = tid & 15 and rows (tid >> 4) + 16 i
-    const FwdProblem& p; int kk; int iy0[4], ix0[4]; const float* base[4];
+    static constexpr int R = Tiles<TM, TN>::RA;
+    const FwdProblem& p; int kk; int iy0[R], ix0[R]; const float* base[R];
     __device__ ALoader(const FwdProblem& p_, int m0, int tid) : p(p_), kk(tid & 15) {
       const ConvGeo& g = p.g;
       const int M = p.M();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < R; ++i) {
         const int m = m0 + (tid >> 4) + 16 * i;
         if (m < M) {
           const int ox = m % g.Wo, oy = (m / g.Wo) % g.Ho, n = m / (g.Wo * g.Ho);
@@ -55,13 +68,13 @@ struct FwdProblem {       // y = conv(x, w) + bias
         } else { iy0[i] = -(1 << 28); ix0[i] = 0; base[i] = p.x; }
       }
     }
-    __device__ void load(TileA& sA, int tid, int k0, int k_end) const {
+    __device__ void load(typename Tiles<TM, TN>::A& sA, int tid, int k0, int k_end) const {
       const ConvGeo& g = p.g;
       const int k = k0 + kk;
       const bool kv = k < k_end;
       const int ci = k % g.Ci, tap = k / g.Ci, kx = tap % g.kw, ky = tap / g.kw;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < R; ++i) {
         const int iy = iy0[i] + ky, ix = ix0[i] + kx;
         float v = 0.f;
         if (kv && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) v = base[i][((long long)iy * g.W + ix) * g.x_cs + ci];
@@ -69,14 +82,15 @@ struct FwdProblem {       // y = conv(x, w) + bias
       }
     }
   };
+  template <int TM, int TN>
   struct BLoader {        // N-fastest: w[k][n]
     const FwdProblem& p; int n; bool nv;
-    __device__ BLoader(const FwdProblem& p_, int n0, int tid) : p(p_), n(n0 + (tid & 63)), nv(n0 + (tid & 63) < p_.g.Co) {}
-    __device__ void load(TileB& sB, int tid, int k0, int k_end) const {
+    __device__ BLoader(const FwdProblem& p_, int n0, int tid) : p(p_), n(n0 + tid % TN), nv(n0 + tid % TN < p_.g.Co) {}
+    __device__ void load(typename Tiles<TM, TN>::B& sB, int tid, int k0, int k_end) const {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int kk = (tid >> 6) + 4 * i, k = k0 + kk;
-        sB[kk][tid & 63] = (nv && k < k_end) ? p.w[(long long)k * p.g.Co + n] : 0.f;
+      for (int i = 0; i < Tiles<TM, TN>::RBN; ++i) {
+        const int kk = tid / TN + Tiles<TM, TN>::KSTEP_N * i, k = k0 + kk;
+        sB[kk][tid % TN] = (nv && k < k_end) ? p.w[(long long)k * p.g.Co + n] : 0.f;
       }
     }
   };
@@ -92,13 +106,15 @@ struct BwdDataProblem {   // dx = conv_bwd_data(dy, w)
   __device__ int M() const { return g.N * g.H * g.W; }
   __device__ int Nn() const { return g.Ci; }
   __device__ int K() const { return g.kh * g.kw * g.Co; }
+  template <int TM, int TN>
   struct ALoader {        // K-fastest (co is the inner K index and contiguous in dy)
-    const BwdDataProblem& p; int kk; int ty0[4], tx0[4]; const float* base[4];
+    static constexpr int R = Tiles<TM, TN>::RA;
+    const BwdDataProblem& p; int kk; int ty0[R], tx0[R]; const float* base[R];
     __device__ ALoader(const BwdDataProblem& p_, int m0, int tid) : p(p_), kk(tid & 15) {
       const ConvGeo& g = p.g;
       const int M = p.M();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < R; ++i) {
         const int m = m0 + (tid >> 4) + 16 * i;
         if (m < M) {
           const int ix = m % g.W, iy = (m / g.W) % g.H, n = m / (g.W * g.H);
@@ -107,13 +123,13 @@ struct BwdDataProblem {   // dx = conv_bwd_data(dy, w)
         } else { ty0[i] = -(1 << 28); tx0[i] = 0; base[i] = p.dy; }
       }
     }
-    __device__ void load(TileA& sA, int tid, int k0, int k_end) const {
+    __device__ void load(typename Tiles<TM, TN>::A& sA, int tid, int k0, int k_end) const {
       const ConvGeo& g = p.g;
       const int k = k0 + kk;
       const bool kv = k < k_end;
       const int co = k % g.Co, tap = k / g.Co, kx = tap % g.kw, ky = tap / g.kw;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < R; ++i) {
         const int ty = ty0[i] - ky, tx = tx0[i] - kx;
         float v = 0.f;
         if (kv && ty >= 0 && tx >= 0) {
@@ -126,16 +142,17 @@ struct BwdDataProblem {   // dx = conv_bwd_data(dy, w)
       }
     }
   };
+  template <int TM, int TN>
   struct BLoader {        // K-fastest: w[tap][ci = n][co], co contiguous
     const BwdDataProblem& p; int kk; int n0;
     __device__ BLoader(const BwdDataProblem& p_, int n0_, int tid) : p(p_), kk(tid & 15), n0(n0_) {}
-    __device__ void load(TileB& sB, int tid, int k0, int k_end) const {
+    __device__ void load(typename Tiles<TM, TN>::B& sB, int tid, int k0, int k_end) const {
       const ConvGeo& g = p.g;
       const int k = k0 + kk;
       const bool kv = k < k_end;
       const int co = k % g.Co, tap = k / g.Co;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < Tiles<TM, TN>::RBK; ++i) {
         const int nn = (tid >> 4) + 16 * i, n = n0 + nn;
         sB[kk][nn] = (kv && n < g.Ci) ? p.w[((long long)tap * g.Ci + n) * g.Co + co] : 0.f;
       }
@@ -147,69 +164,144 @@ struct BwdDataProblem {   // dx = conv_bwd_data(dy, w)
   }
 };
 
+// Backward-data of a stride-s convolution, one residue class (ry, rx) of (iy+pad_t, ix+pad_l) mod s at a time: inside
+// a class every input pixel sees the same taps ky = ry + s*j, so the GEMM has no structural zeros (a dense
+// formulation multiplies zeros for (s*s-1)/(s*s) of its K axis: 8/9 for the critic's 7x7 stride-3 convolutions).
+struct BwdDataClassProblem {
+  ConvGeo g; const float* dy; const float* w; float* dx; int accumulate;
+  int ry, rx, fy, fx, Hc, Wc, Jy, Jx;   // class residues, first pixel of the class, class grid, taps per axis
+  __device__ int M() const { return g.N * Hc * Wc; }
+  __device__ int Nn() const { return g.Ci; }
+  __device__ int K() const { return Jy * Jx * g.Co; }
+  template <int TM, int TN>
+  struct ALoader {
+    static constexpr int R = Tiles<TM, TN>::RA;
+    const BwdDataClassProblem& p; int kk; int ay[R], ax[R]; const float* base[R];
+    __device__ ALoader(const BwdDataClassProblem& p_, int m0, int tid) : p(p_), kk(tid & 15) {
+      const ConvGeo& g = p.g;
+      const int M = p.M();
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int m = m0 + (tid >> 4) + 16 * i;
+        if (m < M) {
+          const int b = m % p.Wc, a = (m / p.Wc) % p.Hc, n = m / (p.Wc * p.Hc);
+          ay[i] = (p.fy + g.stride * a + g.pad_t - p.ry) / g.stride;   // = oy + j
+          ax[i] = (p.fx + g.stride * b + g.pad_l - p.rx) / g.stride;
+          base[i] = p.dy + (long long)n * g.Ho * g.Wo * g.y_cs + g.y_co;
+        } else { ay[i] = -(1 << 28); ax[i] = 0; base[i] = p.dy; }
+      }
+    }
+    __device__ void load(typename Tiles<TM, TN>::A& sA, int tid, int k0, int k_end) const {
+      const ConvGeo& g = p.g;
+      const int k = k0 + kk;
+      const bool kv = k < k_end;
+      const int co = k % g.Co, tap = k / g.Co, jx = tap % p.Jx, jy = tap / p.Jx;
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int oy = ay[i] - jy, ox = ax[i] - jx;
+        float v = 0.f;
+        if (kv && oy >= 0 && oy < g.Ho && ox >= 0 && ox < g.Wo) v = base[i][((long long)oy * g.Wo + ox) * g.y_cs + co];
+        sA[kk][(tid >> 4) + 16 * i] = v;
+      }
+    }
+  };
+  template <int TM, int TN>
+  struct BLoader {
+    const BwdDataClassProblem& p; int kk; int n0;
+    __device__ BLoader(const BwdDataClassProblem& p_, int n0_, int tid) : p(p_), kk(tid & 15), n0(n0_) {}
+    __device__ void load(typename Tiles<TM, TN>::B& sB, int tid, int k0, int k_end) const {
+      const ConvGeo& g = p.g;
+      const int k = k0 + kk;
+      const bool kv = k < k_end;
+      const int co = k % g.Co, tap = k / g.Co, jx = tap % p.Jx, jy = tap / p.Jx;
+      const int ky = p.ry + g.stride * jy, kx = p.rx + g.stride * jx;
+#pragma unroll
+      for (int i = 0; i < Tiles<TM, TN>::RBK; ++i) {
+        const int nn = (tid >> 4) + 16 * i, n = n0 + nn;
+        sB[kk][nn] = (kv && n < g.Ci) ? p.w[(((long long)ky * g.kw + kx) * g.Ci + n) * g.Co + co] : 0.f;
+      }
+    }
+  };
+  __device__ void store(int m, int n, float v) const {
+    const int b = m % Wc, a = (m / Wc) % Hc, img = m / (Wc * Hc);
+    const int iy = fy + g.stride * a, ix = fx + g.stride * b;
+    float* q = dx + (((long long)img * g.H + iy) * g.W + ix) * g.x_cs + g.x_co + n;
+    *q = accumulate ? *q + v : v;
+  }
+};
+
 struct BwdWeightProblem {  // dw[tap][ci][co] = sum over pixels x * dy; split over K (pixels) into partial buffers
   ConvGeo g; const float* x; const float* dy; float* part; int k_per_split;
   __device__ int M() const { return g.kh * g.kw * g.Ci; }
   __device__ int Nn() const { return g.Co; }
   __device__ int K() const { return g.N * g.Ho * g.Wo; }
+  template <int TM, int TN>
   struct ALoader {        // M-fastest: m = (tap, ci), ci contiguous in x
     const BwdWeightProblem& p; int ky, kx, ci; bool mv;
     __device__ ALoader(const BwdWeightProblem& p_, int m0, int tid) : p(p_) {
       const ConvGeo& g = p.g;
-      const int m = m0 + (tid & 63);
+      const int m = m0 + tid % TM;
       mv = m < p.M();
       ci = m % g.Ci;
       const int tap = m / g.Ci;
       kx = tap % g.kw; ky = tap / g.kw;
     }
-    __device__ void load(TileA& sA, int tid, int k0, int k_end) const {
+    __device__ void load(typename Tiles<TM, TN>::A& sA, int tid, int k0, int k_end) const {
       const ConvGeo& g = p.g;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int kk = (tid >> 6) + 4 * i, k = k0 + kk;
+      for (int i = 0; i < Tiles<TM, TN>::RAM; ++i) {
+        const int kk = tid / TM + Tiles<TM, TN>::KSTEP_M * i, k = k0 + kk;
         float v = 0.f;
         if (mv && k < k_end) {
           const int ox = k % g.Wo, oy = (k / g.Wo) % g.Ho, n = k / (g.Wo * g.Ho);
           const int iy = oy * g.stride - g.pad_t + ky, ix = ox * g.stride - g.pad_l + kx;
           if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) v = p.x[(((long long)n * g.H + iy) * g.W + ix) * g.x_cs + g.x_co + ci];
         }
-        sA[kk][tid & 63] = v;
+        sA[kk][tid % TM] = v;
       }
     }
   };
+  template <int TM, int TN>
   struct BLoader {        // N-fastest: dy[k][co]
     const BwdWeightProblem& p; int n; bool nv;
-    __device__ BLoader(const BwdWeightProblem& p_, int n0, int tid) : p(p_), n(n0 + (tid & 63)), nv(n0 + (tid & 63) < p_.g.Co) {}
-    __device__ void load(TileB& sB, int tid, int k0, int k_end) const {
+    __device__ BLoader(const BwdWeightProblem& p_, int n0, int tid) : p(p_), n(n0 + tid % TN), nv(n0 + tid % TN < p_.g.Co) {}
+    __device__ void load(typename Tiles<TM, TN>::B& sB, int tid, int k0, int k_end) const {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int kk = (tid >> 6) + 4 * i, k = k0 + kk;
-        sB[kk][tid & 63] = (nv && k < k_end) ? p.dy[(long long)k * p.g.y_cs + p.g.y_co + n] : 0.f;
+      for (int i = 0; i < Tiles<TM, TN>::RBN; ++i) {
+        const int kk = tid / TN + Tiles<TM, TN>::KSTEP_N * i, k = k0 + kk;
+        sB[kk][tid % TN] = (nv && k < k_end) ? p.dy[(long long)k * p.g.y_cs + p.g.y_co + n] : 0.f;
       }
     }
   };
 };
 
-template <class P>
-__device__ __forceinline__ void gemm_tile(const P& p, int m0, int n0, int k_begin, int k_end, float (&acc)[4][4]) {
-  __shared__ __align__(16) TileA sA;
-  __shared__ __align__(16) TileB sB;
+template <class P, int TM, int TN>
+__device__ __forceinline__ void gemm_tile(const P& p, int m0, int n0, int k_begin, int k_end, float (&acc)[TM * TN / 1024][4]) {
+  constexpr int RM = TM * TN / 1024;            // rows per thread (columns per thread = 4)
+  __shared__ __align__(16) typename Tiles<TM, TN>::A sA;
+  __shared__ __align__(16) typename Tiles<TM, TN>::B sB;
   const int tid = threadIdx.x;
-  const int tm = (tid / 16) * 4, tn = (tid % 16) * 4;
-  const typename P::ALoader la(p, m0, tid);
-  const typename P::BLoader lb(p, n0, tid);
+  const int tm = (tid / (TN / 4)) * RM, tn = (tid % (TN / 4)) * 4;
+  const typename P::template ALoader<TM, TN> la(p, m0, tid);
+  const typename P::template BLoader<TM, TN> lb(p, n0, tid);
   for (int k0 = k_begin; k0 < k_end; k0 += TK) {
     la.load(sA, tid, k0, k_end);
     lb.load(sB, tid, k0, k_end);
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&sA[kk][tm]);
+      float a[RM];
+      if constexpr (RM == 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&sA[kk][tm]);
+        a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
+      } else {
+        const float2 a2 = *reinterpret_cast<const float2*>(&sA[kk][tm]);
+        a[0] = a2.x; a[1] = a2.y;
+      }
       const float4 b4 = *reinterpret_cast<const float4*>(&sB[kk][tn]);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
       const float b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
@@ -217,34 +309,50 @@ __device__ __forceinline__ void gemm_tile(const P& p, int m0, int n0, int k_begi
   }
 }
 
-template <class P>
+template <class P, int TM, int TN>
 __global__ void __launch_bounds__(256) gemm_kernel(P p) {
+  constexpr int RM = TM * TN / 1024;
   const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
-  float acc[4][4] = {};
-  gemm_tile(p, m0, n0, 0, p.K(), acc);
-  const int tm = (threadIdx.x / 16) * 4, tn = (threadIdx.x % 16) * 4;
+  float acc[RM][4] = {};
+  gemm_tile<P, TM, TN>(p, m0, n0, 0, p.K(), acc);
+  const int tm = (threadIdx.x / (TN / 4)) * RM, tn = (threadIdx.x % (TN / 4)) * 4;
   const int M = p.M(), N = p.Nn();
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (m0 + tm + i < M && n0 + tn + j < N) p.store(m0 + tm + i, n0 + tn + j, acc[i][j]);
 }
 
+template <int TM, int TN>
 __global__ void __launch_bounds__(256) gemm_wgrad_kernel(BwdWeightProblem p) {
+  constexpr int RM = TM * TN / 1024;
   const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN, split = blockIdx.z;
   const int K = p.K();
   const int kb = split * p.k_per_split, ke = min(K, kb + p.k_per_split);
-  float acc[4][4] = {};
-  gemm_tile(p, m0, n0, kb, ke, acc);
-  const int tm = (threadIdx.x / 16) * 4, tn = (threadIdx.x % 16) * 4;
+  float acc[RM][4] = {};
+  gemm_tile<BwdWeightProblem, TM, TN>(p, m0, n0, kb, ke, acc);
+  const int tm = (threadIdx.x / (TN / 4)) * RM, tn = (threadIdx.x % (TN / 4)) * 4;
   const int M = p.M(), N = p.Nn();
   float* out = p.part + (long long)split * M * N;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (m0 + tm + i < M && n0 + tn + j < N) out[(long long)(m0 + tm + i) * N + n0 + tn + j] = acc[i][j];
+}
+
+// N <= 16 wide problems use the 128x16 tile
+template <class P>
+static cudaError_t launch_gemm(const P& p, long long M, int N, cudaStream_t stream) {
+  if (N <= 16) {
+    dim3 grid((unsigned)((M + 127) / 128), (N + 15) / 16);
+    gemm_kernel<P, 128, 16><<<grid, 256, 0, stream>>>(p);
+  } else {
+    dim3 grid((unsigned)((M + 63) / 64), (N + 63) / 64);
+    gemm_kernel<P, 64, 64><<<grid, 256, 0, stream>>>(p);
+  }
+  return cudaGetLastError();
 }
 
 // dst[i] (+)= sum_s part[s][i]   (fixed order: deterministic)
@@ -652,25 +760,37 @@ extern "C" int wdg_conv2d_fwd(const float* x, const float* w, const float* bias,
                               void* stream) {
   FwdProblem p{make_geo(geo), x, w, bias, y, accumulate};
   const long long M = (long long)p.g.N * p.g.Ho * p.g.Wo;
-  dim3 grid((unsigned)((M + TM - 1) / TM), (p.g.Co + TN - 1) / TN);
-  gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-  CKT(cudaGetLastError());
+  CKT(launch_gemm(p, M, p.g.Co, (cudaStream_t)stream));
   return 0;
 }
 
 extern "C" int wdg_conv2d_bwd_data(const float* dy, const float* w, float* dx, const int* geo, int accumulate, void* stream) {
-  BwdDataProblem p{make_geo(geo), dy, w, dx, accumulate};
+  const ConvGeo gg = make_geo(geo);
+  if (gg.stride > 1 && gg.kh >= gg.stride && gg.kw >= gg.stride) {
+    const int s = gg.stride;
+    for (int ry = 0; ry < s; ++ry)
+      for (int rx = 0; rx < s; ++rx) {
+        BwdDataClassProblem p{gg, dy, w, dx, accumulate};
+        p.ry = ry; p.rx = rx;
+        p.fy = ((ry - gg.pad_t) % s + s) % s; p.fx = ((rx - gg.pad_l) % s + s) % s;
+        p.Hc = gg.H > p.fy ? (gg.H - p.fy + s - 1) / s : 0; p.Wc = gg.W > p.fx ? (gg.W - p.fx + s - 1) / s : 0;
+        p.Jy = (gg.kh - ry + s - 1) / s; p.Jx = (gg.kw - rx + s - 1) / s;
+        const long long M = (long long)gg.N * p.Hc * p.Wc;
+        if (M == 0) continue;
+        CKT(launch_gemm(p, M, gg.Ci, (cudaStream_t)stream));
+      }
+    return 0;
+  }
+  BwdDataProblem p{gg, dy, w, dx, accumulate};
   const long long M = (long long)p.g.N * p.g.H * p.g.W;
-  dim3 grid((unsigned)((M + TM - 1) / TM), (p.g.Ci + TN - 1) / TN);
-  gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-  CKT(cudaGetLastError());
+  CKT(launch_gemm(p, M, p.g.Ci, (cudaStream_t)stream));
   return 0;
 }
 
 extern "C" int wdg_conv2d_bwd_weight_scratch(const int* geo, size_t* bytes, int* splits_out) {
   const ConvGeo g = make_geo(geo);
   const long long M = (long long)g.kh * g.kw * g.Ci, K = (long long)g.N * g.Ho * g.Wo;
-  const long long tiles = ((M + TM - 1) / TM) * ((g.Co + TN - 1) / TN);
+  const long long tiles = g.Co <= 16 ? ((M + 127) / 128) * ((g.Co + 15) / 16) : ((M + 63) / 64) * ((g.Co + 63) / 64);
   long long splits = (4 * 148 + tiles - 1) / tiles;
   const long long max_splits = (K + 255) / 256;
   if (splits > max_splits) splits = max_splits;
@@ -688,8 +808,13 @@ extern "C" int wdg_conv2d_bwd_weight(const float* x, const float* dy, float* dw,
   BwdWeightProblem p{make_geo(geo), x, dy, (float*)scratch, 0};
   const long long M = (long long)p.g.kh * p.g.kw * p.g.Ci, K = (long long)p.g.N * p.g.Ho * p.g.Wo;
   p.k_per_split = (int)((K + splits - 1) / splits);
-  dim3 grid((unsigned)((M + TM - 1) / TM), (p.g.Co + TN - 1) / TN, splits);
-  gemm_wgrad_kernel<<<grid, 256, 0, stream>>>(p);
+  if (p.g.Co <= 16) {
+    dim3 grid((unsigned)((M + 127) / 128), (p.g.Co + 15) / 16, splits);
+    gemm_wgrad_kernel<128, 16><<<grid, 256, 0, stream>>>(p);
+  } else {
+    dim3 grid((unsigned)((M + 63) / 64), (p.g.Co + 63) / 64, splits);
+    gemm_wgrad_kernel<64, 64><<<grid, 256, 0, stream>>>(p);
+  }
   CKT(cudaGetLastError());
   const long long n = M * p.g.Co;
   reduce_splits_kernel<<<blocks_for(n), 256, 0, stream>>>((const float*)scratch, dw, n, splits, accumulate);
