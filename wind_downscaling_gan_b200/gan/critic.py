@@ -125,6 +125,8 @@ class Critic:
         import torch
         from ..train.nets import CriticNet, to_device
         from ..train.step import _dev
+        from ..train import ops as _ops
+        _ops.use_current_stream()
         if self._dev is None:
             self._dev = to_device(self._w)
         low_res, high_res = _dev(inputs[0]), _dev(inputs[1])

@@ -47,6 +47,7 @@ def train_step(st, low_res, high_res, noise_generator, n_critic=3, draws=None, g
     """One WGAN step on this rank's share of the batch.  With a communicator (train/dist.py) the gradients are
     all-reduced after every backward pass and BatchNorm statistics are synchronised, so `world` ranks x local batch
     reproduce the reference's single process at the global batch."""
+    ops.use_current_stream()
     low_res, high_res = _dev(low_res), _dev(high_res)
     B = low_res.shape[0]
     world = comm.world if comm is not None else 1
@@ -123,6 +124,7 @@ def train_step(st, low_res, high_res, noise_generator, n_critic=3, draws=None, g
 
 
 def test_step(st, x, y, noise_generator, draws=None):
+    ops.use_current_stream()
     x, y = _dev(x), _dev(y)
     B = x.shape[0]
     nz = _dev(draws[0]) if draws is not None else noise_generator(B)
