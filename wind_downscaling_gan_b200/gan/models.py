@@ -262,8 +262,8 @@ class Generator(_NativeModel):
             # moving-average update -- on the fp32 training kernels (train/nets.py)
             from ..train.nets import GenNet, to_device
             from ..train.step import _dev
-        from ..train import ops as _ops
-        _ops.use_current_stream()
+            from ..train import ops as _ops
+            _ops.use_current_stream()
             w = to_device(self.get_weights())
             out = GenNet(w).forward(_dev(image), _dev(noise), training=True)
             self.set_weights({k: v.cpu().numpy() for k, v in w.items()})
