@@ -68,14 +68,25 @@ def main():
         label = f"W-Europe 962x972 px, overlap 0.05, {units} (window, member) pairs x 24 h (BASELINE configs[4])"
     a, b = shard_batch(units, rank, world)
     net = api.get_network()
-    era, topo, tpl = synthetic_domain(H, W, 24, 100 + rank)
     devnull = open(os.devnull, "w")
+    if args.config == "switzerland":     # custom (COSMO) template: predict() on fields already on the hi-res grid
+        era, topo, tpl = synthetic_domain(H, W, 24, 100 + rank)
+        call = lambda: api.predict(era, topo, tpl, overlap_factor=ov, network=net, group_size=per_window)
+        path = "api.predict: host hi-res fields -> device gather/normalise -> generator (device noise) -> device stitch -> host"
+    else:                                # the CLI path: coarse ERA5 (54 x 37 points) + DEM raster through downscale()
+        from tests.synth import synthetic_dem, synthetic_era5
+        era5 = synthetic_era5(lon0=-4.96, lon1=8.3, lat0=42.2, lat1=51.3, hours=24, seed=100 + rank)
+        dem = synthetic_dem(lon0=-5.5, lon1=9.0, lat0=41.5, lat1=52.0, seed=200 + rank, n=2000)
+        assert (len(era5.coords["longitude"]), len(era5.coords["latitude"])) == (54, 37)
+        call = lambda: api.downscale(era5, dem, overlap_factor=ov, network=net, group_size=per_window)
+        path = ("api.downscale: host coarse ERA5 + DEM raster -> device regrid+gather/normalise -> generator (device noise) -> "
+                "device stitch -> host")
 
     def one():
         so = sys.stdout
         sys.stdout = devnull        # predict() prints progress like the reference
         try:
-            return api.predict(era, topo, tpl, overlap_factor=ov, network=net, group_size=per_window)
+            return call()
         finally:
             sys.stdout = so
 
@@ -98,8 +109,7 @@ def main():
                           "domain_timesteps_per_sec": units * 24 / dt, "seconds": dt, "scaling": "strong", "dtype": "bf16",
                           "data": "synthetic", "config": {"workload": label, "patches_per_window": per_window,
                                                           "output_shape": list(out["u10"].shape)},
-                          "path": "api.predict: host coarse fields -> device gather/normalise -> generator (device noise) -> "
-                                  "device stitch -> host", "timing": "wall clock around the public API calls, max over ranks"}),
+                          "path": path, "timing": "wall clock around the public API calls, max over ranks"}),
               flush=True)
     if world > 1:
         dist.destroy_process_group()

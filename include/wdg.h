@@ -111,6 +111,15 @@ int wdg_gather_normalise(const float* u10_dev, const float* v10_dev, const float
                          int W, const int* starts_x_dev, int nx, const int* starts_y_dev, int ny, int seq, int img,
                          double* mean_dev, double* std_dev, float* out_dev, void* scratch_dev, void* stream);
 
+/* Same, with the nearest-neighbour regridding of api.py:31-43 folded into the gather: u10/v10 stay on their coarse
+ * (uh, uw) grid and the DEM on its raster (eh, ew); *_row_map[H] / *_col_map[W] give, for every hi-res template row / col,
+ * the source row / col (`.sel(method='nearest')`), and the DEM is divided by dem_divisor (1e3, api.py:96). */
+int wdg_gather_normalise_regrid(const float* u10_coarse_dev, const float* v10_coarse_dev, int T_total, int uh, int uw,
+                                const int* uv_row_map_dev, const int* uv_col_map_dev, const float* dem_dev, int eh, int ew,
+                                const int* dem_row_map_dev, const int* dem_col_map_dev, float dem_divisor, int H, int W,
+                                const int* starts_x_dev, int nx, const int* starts_y_dev, int ny, int seq, int img,
+                                double* mean_dev, double* std_dev, float* out_dev, void* scratch_dev, void* stream);
+
 /* Replaces api.py:140-151: crops `crop` pixels off every patch side and averages overlapping predictions.
  * pred_dev (N,seq,img,img,channels) fp32; rows_dev/cols_dev: sorted covered domain rows/cols;
  * out_dev (channels, ntimeseq*seq, nrows, ncols) fp32.  Contributions are summed in fp64 in patch order. */

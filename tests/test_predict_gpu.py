@@ -102,6 +102,22 @@ def test_predict_cfg1_matches_oracle_pipeline():
         assert rel < 1e-2, (v, rel)
 
 
+def test_fused_regrid_downscale_equals_predict_on_regridded_inputs():
+    """downscale() folds the nearest-neighbour regrid (api.py:31-43) into the device gather; the result must equal
+    process_era5 / process_topo on the host followed by predict(), bit for bit."""
+    from oracle.generator import synthetic_generator_weights
+    from wind_downscaling_gan_b200 import api
+    era, dem = _cfg1()
+    net = api.get_network()
+    net.generator.set_weights(synthetic_generator_weights(7))
+    noise = (0.1 * np.random.default_rng(5).standard_normal((12, 24, 96, 96, 20))).astype(np.float32)
+    tpl = api.build_high_res_template_from_era5(era, range_lon=(-1.0, 3.0), range_lat=(48.0, 50.0))
+    a = api.predict(api.process_era5(era, tpl), api.process_topo(dem, tpl), tpl, overlap_factor=0.01, network=net, noise=noise)
+    b = api.downscale(era, dem, range_lon=(-1.0, 3.0), range_lat=(48.0, 50.0), overlap_factor=0.01, network=net, noise=noise)
+    assert np.array_equal(a["u10"], b["u10"]) and np.array_equal(a["v10"], b["v10"])
+    assert np.array_equal(a.coords["lat_1"], b.coords["lat_1"]) and np.array_equal(a.coords["lon_1"], b.coords["lon_1"])
+
+
 def test_downscale_and_cli(tmp_path):
     from wind_downscaling_gan_b200 import cli, downscale
     from wind_downscaling_gan_b200.grid import GridDataset

@@ -120,21 +120,24 @@ def _dev_i32(a):
     return torch.as_tensor(np.asarray(a, np.int32), device="cuda")
 
 
-def predict(inputs_era5, inputs_topo, high_res_template, overlap_factor=0.05, network=None, noise=None,
-            group_size=None):
-    """api.py:89-152.  Extra keyword arguments (not in the reference): `network` re-uses a GAN instead of
-    calling get_network(); `noise` (N,24,96,96,20) replaces the generator's own draws (parity runs);
-    `group_size` overrides the reference's 16 patches per generator call."""
+_pinned = {}
+
+
+def _pinned_out(shape):
+    """Page-locked host buffer for the stitched result (re-used across calls of the same shape)."""
     import torch
-    inputs_era5, inputs_topo, high_res_template = (from_xarray(x) for x in (inputs_era5, inputs_topo, high_res_template))
-    lat_coord_hr = [c for c in high_res_template.coords if c.startswith('lat') or c.startswith('y')][0]
-    lon_coord_hr = [c for c in high_res_template.coords if c.startswith('lon') or c.startswith('x')][0]
-    network = network if network is not None else get_network()
-    order = ('time', lat_coord_hr, lon_coord_hr)
-    u10 = np.ascontiguousarray(inputs_era5.transposed('u10', order), np.float32)
-    v10 = np.ascontiguousarray(inputs_era5.transposed('v10', order), np.float32)
-    elev_km = np.ascontiguousarray(inputs_topo.transposed('elevation', order[1:]) / 1e3, np.float32)   # api.py:96
-    time_window, pixels_lat, pixels_lon = u10.shape
+    buf = _pinned.get(shape)
+    if buf is None:
+        _pinned.clear()
+        buf = _pinned[shape] = torch.empty(shape, dtype=torch.float32).pin_memory()
+    return buf
+
+
+def _run_tiles(gather, time_window, pixels_lat, pixels_lon, lat_vals, lon_vals, times, lat_coord_hr, lon_coord_hr,
+               overlap_factor, network, noise, group_size):
+    """api.py:98-151 on the device.  `gather(d_sx, nx, d_sy, ny, mean, std, tensors, scratch, stream)` launches the
+    patch gather + normalisation (from hi-res fields, or straight from the coarse grids with the regrid folded in)."""
+    import torch
     ntimeseq = time_window // SEQUENCE_LENGTH
     starts_x, starts_y = tiling.patch_grid(pixels_lat, pixels_lon, overlap_factor, IMG_SIZE)          # api.py:101-116
     nx, ny = len(starts_x), len(starts_y)
@@ -142,7 +145,6 @@ def predict(inputs_era5, inputs_topo, high_res_template, overlap_factor=0.05, ne
     print(f'Applying model to {n_patches} patches')
     L = _lib.lib()
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    d_u, d_v, d_e = (torch.from_numpy(a).cuda() for a in (u10, v10, elev_km))
     d_sx, d_sy = _dev_i32(starts_x), _dev_i32(starts_y)
     nbytes = C.c_size_t()
     _lib.check(L.wdg_patch_scratch_bytes(nx, ny, max(ntimeseq, 1), IMG_SIZE, C.byref(nbytes)))
@@ -150,9 +152,7 @@ def predict(inputs_era5, inputs_topo, high_res_template, overlap_factor=0.05, ne
     mean = torch.empty((IMG_SIZE, 3), dtype=torch.float64, device="cuda")
     std = torch.empty((IMG_SIZE, 3), dtype=torch.float64, device="cuda")
     tensors = torch.empty((n_patches, SEQUENCE_LENGTH, IMG_SIZE, IMG_SIZE, NB_INPUTS), dtype=torch.float32, device="cuda")
-    _lib.check(L.wdg_gather_normalise(d_u.data_ptr(), d_v.data_ptr(), d_e.data_ptr(), time_window, pixels_lat, pixels_lon,
-                                      d_sx.data_ptr(), nx, d_sy.data_ptr(), ny, SEQUENCE_LENGTH, IMG_SIZE,
-                                      mean.data_ptr(), std.data_ptr(), tensors.data_ptr(), scratch.data_ptr(), stream))
+    gather(d_sx, nx, d_sy, ny, mean, std, tensors, scratch, stream)
     gen = network.generator
     preds = torch.empty((n_patches, SEQUENCE_LENGTH, IMG_SIZE, IMG_SIZE, NB_OUTPUTS), dtype=torch.float32, device="cuda")
     group_size = group_size or BATCH_SIZE * 2                                                        # api.py:132
@@ -173,22 +173,84 @@ def predict(inputs_era5, inputs_topo, high_res_template, overlap_factor=0.05, ne
     _lib.check(L.wdg_stitch(preds.data_ptr(), d_sx.data_ptr(), nx, d_sy.data_ptr(), ny, ntimeseq, SEQUENCE_LENGTH,
                             IMG_SIZE, CROP, NB_OUTPUTS, d_rows.data_ptr(), len(rows), d_cols.data_ptr(),
                             len(cols), out.data_ptr(), stream))
-    out = out.cpu().numpy()
+    host = _pinned_out(tuple(out.shape))
+    host.copy_(out, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    out = host.numpy()
     # groupby(...).mean() returns the labels sorted ascending (api.py:150)
-    lat_vals = np.asarray(high_res_template.coords[lat_coord_hr])[rows]
-    lon_vals = np.asarray(high_res_template.coords[lon_coord_hr])[cols]
+    lat_vals, lon_vals = np.asarray(lat_vals)[rows], np.asarray(lon_vals)[cols]
     oy, ox = np.argsort(lat_vals, kind="stable"), np.argsort(lon_vals, kind="stable")
-    out = out[:, :, oy][:, :, :, ox]
-    times = np.asarray(inputs_era5.coords['time'])[:ntimeseq * SEQUENCE_LENGTH]
+    if not (np.array_equal(oy, np.arange(len(oy))) and np.array_equal(ox, np.arange(len(ox)))):
+        out = out[:, :, oy][:, :, :, ox]
+        lat_vals, lon_vals = lat_vals[oy], lon_vals[ox]
+    else:
+        out = out.copy()   # detach from the re-used pinned staging buffer
+    times = np.asarray(times)[:ntimeseq * SEQUENCE_LENGTH]
     dims = ('time', lat_coord_hr, lon_coord_hr)
     return GridDataset({'u10': (dims, out[0]), 'v10': (dims, out[1])},
-                       {'time': times, lat_coord_hr: lat_vals[oy], lon_coord_hr: lon_vals[ox]})
+                       {'time': times, lat_coord_hr: lat_vals, lon_coord_hr: lon_vals})
 
 
-def downscale(era5, raster_topo, range_lon=None, range_lat=None, overlap_factor=0.05, **kwargs):
-    """api.py:155-160."""
-    high_res_template = build_high_res_template_from_era5(era5, range_lon=range_lon, range_lat=range_lat)
-    inputs_era5 = process_era5(era5, high_res_template)
-    inputs_topo = process_topo(raster_topo, high_res_template)
-    prediction = predict(inputs_era5, inputs_topo, high_res_template, overlap_factor=overlap_factor, **kwargs)
-    return prediction
+def predict(inputs_era5, inputs_topo, high_res_template, overlap_factor=0.05, network=None, noise=None,
+            group_size=None):
+    """api.py:89-152.  Extra keyword arguments (not in the reference): `network` re-uses a GAN instead of
+    calling get_network(); `noise` (N,24,96,96,20) replaces the generator's own draws (parity runs);
+    `group_size` overrides the reference's 16 patches per generator call."""
+    import torch
+    inputs_era5, inputs_topo, high_res_template = (from_xarray(x) for x in (inputs_era5, inputs_topo, high_res_template))
+    lat_coord_hr = [c for c in high_res_template.coords if c.startswith('lat') or c.startswith('y')][0]
+    lon_coord_hr = [c for c in high_res_template.coords if c.startswith('lon') or c.startswith('x')][0]
+    network = network if network is not None else get_network()
+    order = ('time', lat_coord_hr, lon_coord_hr)
+    u10 = np.ascontiguousarray(inputs_era5.transposed('u10', order), np.float32)
+    v10 = np.ascontiguousarray(inputs_era5.transposed('v10', order), np.float32)
+    elev_km = np.ascontiguousarray(inputs_topo.transposed('elevation', order[1:]) / 1e3, np.float32)   # api.py:96
+    time_window, pixels_lat, pixels_lon = u10.shape
+    d_u, d_v, d_e = (torch.from_numpy(a).cuda() for a in (u10, v10, elev_km))
+
+    def gather(d_sx, nx, d_sy, ny, mean, std, tensors, scratch, stream):
+        _lib.check(_lib.lib().wdg_gather_normalise(d_u.data_ptr(), d_v.data_ptr(), d_e.data_ptr(), time_window, pixels_lat,
+                                                   pixels_lon, d_sx.data_ptr(), nx, d_sy.data_ptr(), ny, SEQUENCE_LENGTH, IMG_SIZE,
+                                                   mean.data_ptr(), std.data_ptr(), tensors.data_ptr(), scratch.data_ptr(), stream))
+
+    return _run_tiles(gather, time_window, pixels_lat, pixels_lon, high_res_template.coords[lat_coord_hr],
+                      high_res_template.coords[lon_coord_hr], inputs_era5.coords['time'], lat_coord_hr, lon_coord_hr,
+                      overlap_factor, network, noise, group_size)
+
+
+def downscale(era5, raster_topo, range_lon=None, range_lat=None, overlap_factor=0.05, network=None, noise=None,
+              group_size=None):
+    """api.py:155-160.  Same result as process_era5 / process_topo / predict in sequence, but the nearest-neighbour
+    regridding (api.py:31-43) is folded into the device-side patch gather: only the coarse ERA5 fields and the DEM
+    raster cross PCIe instead of their 18x26-fold replicated hi-res copies."""
+    import torch
+    era5, raster_topo = from_xarray(era5), from_xarray(raster_topo)
+    tpl = build_high_res_template_from_era5(era5, range_lon=range_lon, range_lat=range_lat)
+    lon_coord, lat_coord = _coord_names(tpl)
+    lat_t, lon_t = tpl.coords[lat_coord], tpl.coords[lon_coord]
+    network = network if network is not None else get_network()
+    u10c = np.ascontiguousarray(era5.transposed('u10', ('time', 'latitude', 'longitude')), np.float32)
+    v10c = np.ascontiguousarray(era5.transposed('v10', ('time', 'latitude', 'longitude')), np.float32)
+    uv_r, uv_c = nearest_index(era5.coords['latitude'], lat_t), nearest_index(era5.coords['longitude'], lon_t)
+    name = next(iter(raster_topo.data_vars))
+    dims, dem = raster_topo.var_dims(name), raster_topo[name]
+    if 'band' in dims:
+        dem = np.take(dem, 0, axis=dims.index('band'))
+        dims = tuple(d for d in dims if d != 'band')
+    if dims != ('y', 'x'):
+        dem = np.transpose(dem, [dims.index('y'), dims.index('x')])
+    dem = np.ascontiguousarray(dem, np.float32)
+    e_r, e_c = nearest_index(raster_topo.coords['y'], lat_t), nearest_index(raster_topo.coords['x'], lon_t)
+    d_u, d_v, d_dem = (torch.from_numpy(a).cuda() for a in (u10c, v10c, dem))
+    d_maps = [_dev_i32(m) for m in (uv_r, uv_c, e_r, e_c)]
+    time_window, pixels_lat, pixels_lon = u10c.shape[0], len(lat_t), len(lon_t)
+
+    def gather(d_sx, nx, d_sy, ny, mean, std, tensors, scratch, stream):
+        _lib.check(_lib.lib().wdg_gather_normalise_regrid(
+            d_u.data_ptr(), d_v.data_ptr(), time_window, u10c.shape[1], u10c.shape[2], d_maps[0].data_ptr(), d_maps[1].data_ptr(),
+            d_dem.data_ptr(), dem.shape[0], dem.shape[1], d_maps[2].data_ptr(), d_maps[3].data_ptr(), C.c_float(1e3),
+            pixels_lat, pixels_lon, d_sx.data_ptr(), nx, d_sy.data_ptr(), ny, SEQUENCE_LENGTH, IMG_SIZE, mean.data_ptr(),
+            std.data_ptr(), tensors.data_ptr(), scratch.data_ptr(), stream))
+
+    return _run_tiles(gather, time_window, pixels_lat, pixels_lon, lat_t, lon_t, era5.coords['time'], lat_coord, lon_coord,
+                      overlap_factor, network, noise, group_size)

@@ -18,21 +18,30 @@ extern int wdg_set_error(const std::string& m);  // wdg_generator.cu
 namespace {
 
 struct Geo {
-  const float* u10;   // (T_total, H, W)
+  const float* u10;   // (T_total, uh, uw): hi-res (uh = H, uw = W, maps null) or coarse + nearest-neighbour maps
   const float* v10;
-  const float* elev;  // (H, W), already in km
+  const float* elev;  // (eh, ew)
   const int* sx;      // device, nx patch column starts
   const int* sy;      // device, ny patch row starts
   int T_total, H, W, nx, ny, seq, img, ntimeseq;
+  // optional nearest-neighbour regrid folded into the gather (api.py:31-43): hi-res (row, col) -> source (row, col)
+  const int* uv_rmap; const int* uv_cmap; int uh, uw;
+  const int* e_rmap; const int* e_cmap; int eh, ew;
+  float elev_div;     // elevation is divided by this (1 when already in km; 1e3 on the fused path, api.py:96)
 };
 
 // api.py:119: patch row p -> domain row; rows sy+img-1 .. sy, or img .. 1 when sy == 0 (F10)
 __device__ __forceinline__ int domain_row(int sy, int p, int img) { return (sy != 0 ? sy + img - 1 : img) - p; }
 
 __device__ __forceinline__ float load_var(const Geo& g, int var, int t, int row, int col) {
-  if (var == 2) return g.elev[(long long)row * g.W + col];
+  if (var == 2) {
+    const int r = g.e_rmap ? g.e_rmap[row] : row, c = g.e_cmap ? g.e_cmap[col] : col;
+    const float e = g.elev[(long long)r * g.ew + c];
+    return g.elev_div == 1.f ? e : e / g.elev_div;   // fp32 division, as numpy does for a float32 DEM (api.py:96)
+  }
   const float* src = var == 0 ? g.u10 : g.v10;
-  return src[((long long)t * g.H + row) * g.W + col];
+  const int r = g.uv_rmap ? g.uv_rmap[row] : row, c = g.uv_cmap ? g.uv_cmap[col] : col;
+  return src[((long long)t * g.uh + r) * g.uw + c];
 }
 
 // One block per (var, ix, iy, k); thread j owns patch column j (coalesced along the domain's lon axis).
@@ -136,6 +145,8 @@ extern "C" int wdg_patch_scratch_bytes(int nx, int ny, int ntimeseq, int img, si
   return 0;
 }
 
+static int gather_normalise_impl(Geo g, double* mean_dev, double* std_dev, float* out_dev, void* scratch_dev, void* stream_);
+
 extern "C" int wdg_gather_normalise(const float* u10_dev, const float* v10_dev, const float* elev_km_dev, int T_total,
                                     int H, int W, const int* starts_x_dev, int nx, const int* starts_y_dev, int ny,
                                     int seq, int img, double* mean_dev, double* std_dev, float* out_dev,
@@ -143,9 +154,29 @@ extern "C" int wdg_gather_normalise(const float* u10_dev, const float* v10_dev, 
   if (!u10_dev || !v10_dev || !elev_km_dev || !starts_x_dev || !starts_y_dev || !mean_dev || !std_dev || !out_dev ||
       !scratch_dev)
     return wdg_set_error("null argument");
+  Geo g{u10_dev, v10_dev, elev_km_dev, starts_x_dev, starts_y_dev, T_total, H, W, nx, ny, seq, img, seq > 0 ? T_total / seq : 0,
+        nullptr, nullptr, H, W, nullptr, nullptr, H, W, 1.f};
+  return gather_normalise_impl(g, mean_dev, std_dev, out_dev, scratch_dev, stream_);
+}
+
+extern "C" int wdg_gather_normalise_regrid(const float* u10_coarse_dev, const float* v10_coarse_dev, int T_total, int uh, int uw,
+                                           const int* uv_row_map_dev, const int* uv_col_map_dev, const float* dem_dev, int eh,
+                                           int ew, const int* dem_row_map_dev, const int* dem_col_map_dev, float dem_divisor,
+                                           int H, int W, const int* starts_x_dev, int nx, const int* starts_y_dev, int ny,
+                                           int seq, int img, double* mean_dev, double* std_dev, float* out_dev,
+                                           void* scratch_dev, void* stream_) {
+  if (!u10_coarse_dev || !v10_coarse_dev || !uv_row_map_dev || !uv_col_map_dev || !dem_dev || !dem_row_map_dev ||
+      !dem_col_map_dev || !starts_x_dev || !starts_y_dev || !mean_dev || !std_dev || !out_dev || !scratch_dev)
+    return wdg_set_error("null argument");
+  Geo g{u10_coarse_dev, v10_coarse_dev, dem_dev, starts_x_dev, starts_y_dev, T_total, H, W, nx, ny, seq, img,
+        seq > 0 ? T_total / seq : 0, uv_row_map_dev, uv_col_map_dev, uh, uw, dem_row_map_dev, dem_col_map_dev, eh, ew, dem_divisor};
+  return gather_normalise_impl(g, mean_dev, std_dev, out_dev, scratch_dev, stream_);
+}
+
+static int gather_normalise_impl(Geo g, double* mean_dev, double* std_dev, float* out_dev, void* scratch_dev, void* stream_) {
+  const int nx = g.nx, ny = g.ny, img = g.img, seq = g.seq;
   if (img > 1024) return wdg_set_error("img too large");
   cudaStream_t stream = (cudaStream_t)stream_;
-  Geo g{u10_dev, v10_dev, elev_km_dev, starts_x_dev, starts_y_dev, T_total, H, W, nx, ny, seq, img, T_total / seq};
   if (g.ntimeseq <= 0) return wdg_set_error("time window shorter than one sequence");
   const int bpv = nx * ny * g.ntimeseq;
   double* psum = (double*)scratch_dev;
