@@ -138,6 +138,11 @@ int wdg_noise_normal(float* out_dev, long long n, float stddev, uint64_t seed, u
  * inside a wider (concatenated) buffer.  geo[16] = {N, H, W, Ci, kh, kw, Co, stride, pad_top, pad_left, Ho, Wo,
  * x_cs, x_co, y_cs, y_co}; weights are HWIO (a Conv2DTranspose kernel (kh,kw,out,in) is the HWIO kernel of the
  * convolution it transposes, so its forward is wdg_conv2d_bwd_data). */
+/* Arithmetic of the three convolution GEMMs below: 0 = fp32 on CUDA cores (default), 1 = tf32 operands, 2 = bf16
+ * operands on the tcgen05 tensor cores (operands rounded to nearest in the loaders, fp32 accumulation in TMEM,
+ * fp32 tensors in memory either way).  Process-wide setting. */
+int wdg_train_set_precision(int mode);
+int wdg_train_get_precision(void);
 int wdg_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, const int* geo, int accumulate, void* stream);
 int wdg_conv2d_bwd_data(const float* dy, const float* w, float* dx, const int* geo, int accumulate, void* stream);
 int wdg_conv2d_bwd_weight_scratch(const int* geo, size_t* bytes, int* splits);

@@ -48,6 +48,8 @@ def _declare(lib):
     ll, f, d = C.c_longlong, C.c_float, C.c_double
     ip = C.POINTER(i)
     sigs.update({
+        "wdg_train_set_precision": [i],
+        "wdg_train_get_precision": [],
         "wdg_conv2d_fwd": [vp, vp, vp, vp, ip, i, vp],
         "wdg_conv2d_bwd_data": [vp, vp, vp, ip, i, vp],
         "wdg_conv2d_bwd_weight_scratch": [ip, C.POINTER(sz), ip],

@@ -1,0 +1,609 @@
+// Training convolutions on the 5th-generation tensor cores (critic and training-mode
+// generator forward / backward-data / backward-weight).
+//
+// One kernel template, `tc_gemm_kernel<P, BN, OP>`: C[128 x BN] tiles of an implicit GEMM whose operands are
+// GATHERED by 8 loader warps straight from the fp32 channels-last activations / weights (no im2col buffer, no
+// packed copies), rounded to bf16 or tf32 in registers and written into shared memory in the canonical K-major
+// SWIZZLE_128B UMMA layout (one 16-byte chunk = 8 bf16 / 4 tf32 per st.shared.v4); a ninth warp issues
+// `tcgen05.mma` (kind::f16 or kind::tf32) with the fp32 accumulator in TMEM; after the K loop the loader warps
+// read the accumulator back (`tcgen05.ld`) and run the problem's epilogue (bias / accumulate / strided channel
+// views / split-K partials).  Two CTAs are co-resident per SM so one tile's epilogue overlaps the other's gathers.
+//
+// The three problems are the same ones train_ops.cu defines for the CUDA-core path:
+//   forward        C[m = (n,oy,ox)][co]      = sum_{k=(ky,kx,ci)} x[n, oy*s-p+ky, ox*s-p+kx, ci] * w[k][co]
+//   backward-data  C[m = (n,a,b) in class][ci] = sum_{k=(jy,jx,co)} dy[n, ay-jy, ax-jx, co] * w[ry+s*jy][rx+s*jx][ci][co]
+//                  (one residue class of the stride at a time: no structural zeros; stride 1 is the single class)
+//   backward-weight C[m = (ky,kx,ci)][co]    = sum_{k=(n,oy,ox)} x[n, oy*s-p+ky, ox*s-p+kx, ci] * dy[k][co]   (split-K)
+#include <cuda_runtime.h>
+
+#include "../../include/wdg.h"
+#include "ptx.cuh"
+#include "train_geo.cuh"
+
+namespace {
+using namespace wdg;
+
+constexpr int OP_TF32 = 1, OP_BF16 = 2;
+template <int OP> struct OpT { static constexpr int G = (OP == OP_BF16) ? 8 : 4; };   // elements per 16-byte chunk
+constexpr int LOADER_THREADS = 256;
+constexpr int TC_THREADS = LOADER_THREADS + 32;
+constexpr int TILE_M = 128;
+constexpr uint32_t A_STAGE_BYTES = TILE_M * 128;
+
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+
+// 16 bytes of one K-major SWIZZLE_128B row: tile rows are 128 bytes, chunk c of row r lives at chunk c ^ (r & 7).
+template <int OP>
+__device__ __forceinline__ void store_chunk(uint32_t tile, int row, int chunk, const float (&v)[OpT<OP>::G]) {
+  const uint32_t addr = tile + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+  uint32_t w0, w1, w2, w3;
+  if constexpr (OP == OP_BF16) {
+    w0 = pack_bf16x2(v[0], v[1]); w1 = pack_bf16x2(v[2], v[3]); w2 = pack_bf16x2(v[4], v[5]); w3 = pack_bf16x2(v[6], v[7]);
+  } else {
+    w0 = to_tf32(v[0]); w1 = to_tf32(v[1]); w2 = to_tf32(v[2]); w3 = to_tf32(v[3]);
+  }
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {   // A/B = tf32 K-major, D = fp32, K = 8
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ K walkers
+// k = (ty * ntx + tx) * C + c, advanced incrementally (no division in the K loop).
+struct TapK {
+  int c, tx, ty;
+  __device__ void init(long long k, int C, int ntx) {
+    c = (int)(k % C);
+    const int t = (int)(k / C);
+    tx = t % ntx; ty = t / ntx;
+  }
+  __device__ __forceinline__ void advance(int d, int C, int ntx) {
+    c += d;
+    while (c >= C) { c -= C; if (++tx == ntx) { tx = 0; ++ty; } }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ A: tap gather
+// K-fastest gather of 4 rows x one 16-byte chunk per thread (rows (tid >> 3) + 32 i, chunk tid & 7): the
+// forward A operand (sgn = +1) and the backward-data A operand (sgn = -1).
+struct GatherSrc {
+  int cs, C, ntx, nty, sgn, Hs, Ws, vec;
+};
+template <int OP>
+struct TapGatherA {
+  static constexpr int G = OpT<OP>::G;
+  GatherSrc s;
+  const float* base[4];   // pixel (y0, x0) of the row's image, channel offset applied (may point outside; never read then)
+  int y0[4], x0[4];
+  __device__ __forceinline__ void set_row(int i, bool valid, const float* img, int y, int x) {
+    y0[i] = valid ? y : -(1 << 28);
+    x0[i] = x;
+    base[i] = valid ? img + ((long long)y * s.Ws + x) * s.cs : img;
+  }
+  __device__ __forceinline__ void load(uint32_t tile, int tid, const TapK& k) const {
+    const int j = tid & 7, r0 = tid >> 3;
+    float v[4][G];
+    if (s.vec && k.c + G <= s.C) {
+      const int dy = s.sgn * k.ty, dx = s.sgn * k.tx;
+      const long long off = ((long long)dy * s.Ws + dx) * s.cs + k.c;
+      const bool kin = k.ty < s.nty;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int y = y0[i] + dy, x = x0[i] + dx;
+        if (kin && (unsigned)y < (unsigned)s.Hs && (unsigned)x < (unsigned)s.Ws) {
+          const float4* q = reinterpret_cast<const float4*>(base[i] + off);
+#pragma unroll
+          for (int h = 0; h < G / 4; ++h) {
+            const float4 t = __ldg(q + h);
+            v[i][4 * h] = t.x; v[i][4 * h + 1] = t.y; v[i][4 * h + 2] = t.z; v[i][4 * h + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < G; ++e) v[i][e] = 0.f;
+        }
+      }
+    } else {
+      TapK w = k;
+#pragma unroll
+      for (int e = 0; e < G; ++e) {
+        const int dy = s.sgn * w.ty, dx = s.sgn * w.tx;
+        const long long off = ((long long)dy * s.Ws + dx) * s.cs + w.c;
+        const bool kin = w.ty < s.nty;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int y = y0[i] + dy, x = x0[i] + dx;
+          v[i][e] = (kin && (unsigned)y < (unsigned)s.Hs && (unsigned)x < (unsigned)s.Ws) ? __ldg(base[i] + off) : 0.f;
+        }
+        w.advance(1, s.C, s.ntx);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) store_chunk<OP>(tile, r0 + 32 * i, j, v[i]);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ B: linear rows
+// Row-fastest loader of B(k, n) = base[k * ld + n] (forward: the HWIO weights; backward-weight: dy): thread owns
+// row tid % BN and CPT consecutive chunks; lanes walk n, so every load instruction is coalesced.
+template <int OP, int BN>
+struct LinearRowFastB {
+  static constexpr int G = OpT<OP>::G;
+  static constexpr int CPT = BN >= 32 ? BN / 32 : 1;
+  const float* q;          // element (k of this thread's first chunk, n)
+  long long ld;
+  long long k, k_end;      // k of this thread's first chunk in the current K block
+  bool active, nv;
+  int row, chunk0;
+  __device__ void init(const float* base, long long ld_, int n0, int n_valid, long long k_begin, long long k_end_, int tid) {
+    row = tid % BN;
+    const int group = tid / BN;
+    chunk0 = group * CPT;
+    active = chunk0 < 8;
+    nv = n0 + row < n_valid;
+    ld = ld_; k_end = k_end_;
+    k = k_begin + chunk0 * G;
+    q = base + k * ld + n0 + row;
+  }
+  __device__ __forceinline__ void load(uint32_t tile) {
+    if (active) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < CPT; c0 += 4) {
+        constexpr int NB = CPT < 4 ? CPT : 4;
+        float v[NB][G];
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+#pragma unroll
+          for (int e = 0; e < G; ++e) {
+            const int kk = (c0 + c) * G + e;
+            v[c][e] = (nv && k + kk < k_end) ? __ldg(q + kk * ld) : 0.f;
+          }
+#pragma unroll
+        for (int c = 0; c < NB; ++c) store_chunk<OP>(tile, row, chunk0 + c0 + c, v[c]);
+      }
+    }
+    k += 8 * G;
+    q += 8 * G * ld;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ problems
+struct TcFwd {
+  ConvGeo g; const float* x; const float* w; const float* bias; float* y; int accumulate, vec_in, vec_out;
+  __device__ long long M() const { return (long long)g.N * g.Ho * g.Wo; }
+  __device__ int Nn() const { return g.Co; }
+  __device__ long long K() const { return (long long)g.kh * g.kw * g.Ci; }
+
+  template <int OP, int BN>
+  struct Loaders {
+    TapGatherA<OP> a; LinearRowFastB<OP, BN> b; TapK k;
+    __device__ Loaders(const TcFwd& p, long long m0, int n0, long long k_begin, long long k_end, int tid) {
+      const ConvGeo& g = p.g;
+      a.s = GatherSrc{g.x_cs, g.Ci, g.kw, g.kh, +1, g.H, g.W, p.vec_in};
+      const long long M = p.M();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + (tid >> 3) + 32 * i;
+        const bool valid = m < M;
+        const long long mm = valid ? m : 0;
+        const int ox = (int)(mm % g.Wo), oy = (int)((mm / g.Wo) % g.Ho), n = (int)(mm / ((long long)g.Wo * g.Ho));
+        a.set_row(i, valid, p.x + g.x_co + (long long)n * g.H * g.W * g.x_cs, oy * g.stride - g.pad_t, ox * g.stride - g.pad_l);
+      }
+      k.init(k_begin + (tid & 7) * OpT<OP>::G, g.Ci, g.kw);
+      b.init(p.w, g.Co, n0, g.Co, k_begin, k_end, tid);
+    }
+    __device__ __forceinline__ void load(uint32_t a_tile, uint32_t b_tile, int tid) {
+      a.load(a_tile, tid, k);
+      b.load(b_tile);
+      k.advance(8 * OpT<OP>::G, a.s.C, a.s.ntx);
+    }
+  };
+  __device__ __forceinline__ void store16(long long m, int n, const uint32_t (&r)[16], int) const {
+    float* q = y + m * g.y_cs + g.y_co + n;
+    if (vec_out && n + 16 <= g.Co) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                               __uint_as_float(r[4 * i + 3]));
+        if (bias) { v.x += __ldg(bias + n + 4 * i); v.y += __ldg(bias + n + 4 * i + 1); v.z += __ldg(bias + n + 4 * i + 2); v.w += __ldg(bias + n + 4 * i + 3); }
+        float4* d = reinterpret_cast<float4*>(q) + i;
+        if (accumulate) { const float4 o = *d; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        *d = v;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (n + e < g.Co) {
+          float v = __uint_as_float(r[e]);
+          if (bias) v += __ldg(bias + n + e);
+          q[e] = accumulate ? q[e] + v : v;
+        }
+    }
+  }
+};
+
+struct TcBwdData {
+  ConvGeo g; BwdClass c; const float* dy; const float* w; float* dx; int accumulate, vec_in, vec_w, vec_out;
+  __device__ long long M() const { return (long long)g.N * c.Hc * c.Wc; }
+  __device__ int Nn() const { return g.Ci; }
+  __device__ long long K() const { return (long long)c.Jy * c.Jx * g.Co; }
+
+  template <int OP, int BN>
+  struct Loaders {
+    static constexpr int G = OpT<OP>::G;
+    static constexpr int RB = BN >= 32 ? BN / 32 : 1;   // B rows per thread: n = (tid >> 3) + 32 i
+    TapGatherA<OP> a; TapK k;
+    const float* w; int Ci, Co, kw, s, ry, rx, Jy, n0, vec_w;
+    __device__ Loaders(const TcBwdData& p, long long m0, int n0_, long long k_begin, long long, int tid) {
+      const ConvGeo& g = p.g;
+      a.s = GatherSrc{g.y_cs, g.Co, p.c.Jx, p.c.Jy, -1, g.Ho, g.Wo, p.vec_in};
+      const long long M = p.M();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + (tid >> 3) + 32 * i;
+        const bool valid = m < M;
+        const long long mm = valid ? m : 0;
+        const int b = (int)(mm % p.c.Wc), aa = (int)((mm / p.c.Wc) % p.c.Hc), n = (int)(mm / ((long long)p.c.Wc * p.c.Hc));
+        const int ay = (p.c.fy + g.stride * aa + g.pad_t - p.c.ry) / g.stride;   // = oy + jy
+        const int ax = (p.c.fx + g.stride * b + g.pad_l - p.c.rx) / g.stride;
+        a.set_row(i, valid, p.dy + g.y_co + (long long)n * g.Ho * g.Wo * g.y_cs, ay, ax);
+      }
+      k.init(k_begin + (tid & 7) * G, g.Co, p.c.Jx);
+      w = p.w; Ci = g.Ci; Co = g.Co; kw = g.kw; s = g.stride; ry = p.c.ry; rx = p.c.rx; Jy = p.c.Jy; n0 = n0_; vec_w = p.vec_w;
+    }
+    // B(k = (jy, jx, co), n = ci) = w[((ry + s jy) * kw + rx + s jx) * Ci + ci][co]: co contiguous -> K-fastest
+    __device__ __forceinline__ void load_b(uint32_t tile, int tid) const {
+      const int j = tid & 7, r0 = tid >> 3;
+      if (BN < 32 && r0 >= BN) return;
+#pragma unroll 1
+      for (int i0 = 0; i0 < RB; i0 += 4) {
+        constexpr int NB = RB < 4 ? RB : 4;
+        float v[NB][G];
+        if (vec_w && k.c + G <= Co) {
+          const bool kin = k.ty < Jy;
+          const long long off = ((long long)((ry + s * k.ty) * kw + rx + s * k.tx) * Ci) * Co + k.c;
+#pragma unroll
+          for (int i = 0; i < NB; ++i) {
+            const int n = n0 + r0 + 32 * (i0 + i);
+            if (kin && n < Ci) {
+              const float4* q = reinterpret_cast<const float4*>(w + off + (long long)n * Co);
+#pragma unroll
+              for (int h = 0; h < G / 4; ++h) {
+                const float4 t = __ldg(q + h);
+                v[i][4 * h] = t.x; v[i][4 * h + 1] = t.y; v[i][4 * h + 2] = t.z; v[i][4 * h + 3] = t.w;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < G; ++e) v[i][e] = 0.f;
+            }
+          }
+        } else {
+          TapK t = k;
+#pragma unroll
+          for (int e = 0; e < G; ++e) {
+            const bool kin = t.ty < Jy;
+            const long long off = ((long long)((ry + s * t.ty) * kw + rx + s * t.tx) * Ci) * Co + t.c;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+              const int n = n0 + r0 + 32 * (i0 + i);
+              v[i][e] = (kin && n < Ci) ? __ldg(w + off + (long long)n * Co) : 0.f;
+            }
+            t.advance(1, Co, a.s.ntx);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) store_chunk<OP>(tile, r0 + 32 * (i0 + i), j, v[i]);
+      }
+    }
+    __device__ __forceinline__ void load(uint32_t a_tile, uint32_t b_tile, int tid) {
+      a.load(a_tile, tid, k);
+      load_b(b_tile, tid);
+      k.advance(8 * G, a.s.C, a.s.ntx);
+    }
+  };
+  __device__ __forceinline__ void store16(long long m, int n, const uint32_t (&r)[16], int) const {
+    const int b = (int)(m % c.Wc), a = (int)((m / c.Wc) % c.Hc), img = (int)(m / ((long long)c.Wc * c.Hc));
+    const int iy = c.fy + g.stride * a, ix = c.fx + g.stride * b;
+    float* q = dx + (((long long)img * g.H + iy) * g.W + ix) * g.x_cs + g.x_co + n;
+    if (vec_out && n + 16 <= g.Ci) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                               __uint_as_float(r[4 * i + 3]));
+        float4* d = reinterpret_cast<float4*>(q) + i;
+        if (accumulate) { const float4 o = *d; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        *d = v;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (n + e < g.Ci) q[e] = accumulate ? q[e] + __uint_as_float(r[e]) : __uint_as_float(r[e]);
+    }
+  }
+};
+
+struct TcWgrad {
+  ConvGeo g; const float* x; const float* dy; float* part; long long k_per_split;
+  __device__ long long M() const { return (long long)g.kh * g.kw * g.Ci; }
+  __device__ int Nn() const { return g.Co; }
+  __device__ long long K() const { return (long long)g.N * g.Ho * g.Wo; }
+
+  template <int OP, int BN>
+  struct Loaders {
+    static constexpr int G = OpT<OP>::G;
+    static constexpr int RUN = 4 * G;      // consecutive k per thread and K block (4 chunks); the two thread halves interleave
+    LinearRowFastB<OP, BN> b;
+    // A(m = (ky, kx, ci), k = (n, oy, ox)) = x[n, oy s - p + ky, ox s - p + kx, ci]: ci contiguous -> row-fastest
+    const float* col;   // x + x_co + ci
+    int ky, kx, row, half;
+    bool mv;
+    int ox, oy, n;
+    long long k, k_end;
+    int H, W, Ho, Wo, s, pad_t, pad_l, cs;
+    __device__ Loaders(const TcWgrad& p, long long m0, int n0, long long k_begin, long long k_end_, int tid) {
+      const ConvGeo& g = p.g;
+      row = tid & 127; half = tid >> 7;
+      const long long m = m0 + row;
+      mv = m < p.M();
+      const int mm = mv ? (int)m : 0;
+      const int ci = mm % g.Ci, tap = mm / g.Ci;
+      kx = tap % g.kw; ky = tap / g.kw;
+      col = p.x + g.x_co + ci;
+      H = g.H; W = g.W; Ho = g.Ho; Wo = g.Wo; s = g.stride; pad_t = g.pad_t; pad_l = g.pad_l; cs = g.x_cs;
+      k = k_begin + half * RUN; k_end = k_end_;
+      ox = (int)(k % Wo); oy = (int)((k / Wo) % Ho); n = (int)(k / ((long long)Wo * Ho));
+      b.init(p.dy + g.y_co, g.y_cs, n0, g.Co, k_begin, k_end_, tid);
+    }
+    __device__ __forceinline__ void advance(int d) {
+      k += d; ox += d;
+      while (ox >= Wo) { ox -= Wo; if (++oy == Ho) { oy = 0; ++n; } }
+    }
+    __device__ __forceinline__ void load(uint32_t a_tile, uint32_t b_tile, int) {
+      float v[4][G];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int e = 0; e < G; ++e) {
+          const int iy = oy * s - pad_t + ky, ix = ox * s - pad_l + kx;
+          const bool ok = mv && k < k_end && (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+          v[c][e] = ok ? __ldg(col + (((long long)n * H + iy) * W + ix) * cs) : 0.f;
+          ++k;
+          if (++ox == Wo) { ox = 0; if (++oy == Ho) { oy = 0; ++n; } }
+        }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) store_chunk<OP>(a_tile, row, half * 4 + c, v[c]);
+      advance(RUN);
+      b.load(b_tile);
+    }
+  };
+  __device__ __forceinline__ void store16(long long m, int n, const uint32_t (&r)[16], int split) const {
+    float* q = part + ((long long)split * M() + m) * g.Co + n;
+    if ((g.Co & 3) == 0 && n + 16 <= g.Co) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<float4*>(q)[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                      __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (n + e < g.Co) q[e] = __uint_as_float(r[e]);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int BN> struct TcCfg {
+  static constexpr int STAGES = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
+  static constexpr uint32_t B_STAGE_BYTES = BN * 128;
+  static constexpr uint32_t SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <class P, int BN, int OP>
+__global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const P p, int n_tiles_n, long long k_per_split) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int KB = 8 * OpT<OP>::G;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = sm;
+  uint8_t* smB = sm + STAGES * A_STAGE_BYTES;
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], LOADER_THREADS); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc<Cfg::TMEM_COLS>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  const int n_tile = blockIdx.x % n_tiles_n;
+  const long long m0 = (long long)(blockIdx.x / n_tiles_n) * TILE_M;
+  const int n0 = n_tile * BN;
+  const int split = blockIdx.y;
+  const long long K = p.K();
+  const long long k_begin = (long long)split * k_per_split;
+  const long long k_end = (k_begin + k_per_split < K) ? k_begin + k_per_split : K;
+  const int num_kb = k_end > k_begin ? (int)((k_end - k_begin + KB - 1) / KB) : 0;
+
+  if (warp < 8) {
+    // ===================================================== gather warps, then epilogue
+    {
+      typename P::template Loaders<OP, BN> ld(p, m0, n0, k_begin, k_end, tid);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        ld.load(smem_u32(smA + stage * A_STAGE_BYTES), smem_u32(smB + stage * Cfg::B_STAGE_BYTES), tid);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+        mbar_arrive(&full_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    if (num_kb > 0) {
+      mbar_wait(&acc_bar, 0);
+      tc_fence_after();
+    }
+    const int quad = warp & 3, half = warp >> 2;
+    const long long m = m0 + quad * 32 + lane;
+    const bool mvalid = m < p.M();
+    const int N = p.Nn();
+    constexpr int COLS_PER_HALF = BN >= 32 ? BN / 2 : BN;
+    if (BN >= 32 || half == 0) {
+#pragma unroll 1
+      for (int c0 = half * COLS_PER_HALF; c0 < (half + 1) * COLS_PER_HALF; c0 += 16) {
+        uint32_t r[16];
+        if (num_kb > 0) {
+          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + c0, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r[e] = 0u;
+        }
+        if (mvalid && n0 + c0 < N) p.store16(m, n0 + c0, r, split);
+      }
+    }
+  } else {
+    // ===================================================== MMA issuer
+    constexpr uint32_t idesc = (OP == OP_BF16) ? umma_idesc_bf16(TILE_M, BN) : umma_idesc_tf32(TILE_M, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = umma_desc_kmajor(smem_u32(smA + stage * A_STAGE_BYTES), 128u);
+        const uint64_t db = umma_desc_kmajor(smem_u32(smB + stage * Cfg::B_STAGE_BYTES), 128u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {   // 4 x 32 bytes of K per 128-byte row
+          if constexpr (OP == OP_BF16) umma_bf16(tmem_base, da + 2 * q, db + 2 * q, idesc, (kb | q) ? 1u : 0u);
+          else umma_tf32(tmem_base, da + 2 * q, db + 2 * q, idesc, (kb | q) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (kb == num_kb - 1) umma_commit(&acc_bar);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <class P, int BN, int OP>
+cudaError_t launch_one(const P& p, long long M, int N, int splits, long long k_per_split, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<P, BN, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)TcCfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int ntn = (N + BN - 1) / BN;
+  const long long ntm = (M + TILE_M - 1) / TILE_M;
+  dim3 grid((unsigned)(ntm * ntn), (unsigned)splits);
+  tc_gemm_kernel<P, BN, OP><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, stream>>>(p, ntn, k_per_split);
+  return cudaGetLastError();
+}
+
+int pick_bn(int N) {
+  if (N <= 16) return 16;
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  return (N % 256 == 0 || N > 384) ? 256 : 128;
+}
+
+template <class P, int OP>
+cudaError_t launch_bn(const P& p, long long M, int N, int splits, long long kps, cudaStream_t stream) {
+  switch (pick_bn(N)) {
+    case 16: return launch_one<P, 16, OP>(p, M, N, splits, kps, stream);
+    case 32: return launch_one<P, 32, OP>(p, M, N, splits, kps, stream);
+    case 64: return launch_one<P, 64, OP>(p, M, N, splits, kps, stream);
+    case 128: return launch_one<P, 128, OP>(p, M, N, splits, kps, stream);
+    default: return launch_one<P, 256, OP>(p, M, N, splits, kps, stream);
+  }
+}
+template <class P>
+cudaError_t launch_tc(const P& p, long long M, int N, int splits, long long kps, int op, cudaStream_t stream) {
+  return op == OP_BF16 ? launch_bn<P, OP_BF16>(p, M, N, splits, kps, stream) : launch_bn<P, OP_TF32>(p, M, N, splits, kps, stream);
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+int wdg_tc_conv2d_fwd(const ConvGeo& g, const float* x, const float* w, const float* bias, float* y, int accumulate, int op,
+                      cudaStream_t stream) {
+  TcFwd p{g, x, w, bias, y, accumulate, 0, 0};
+  p.vec_in = (g.x_cs % 4 == 0) && (g.x_co % 4 == 0) && (g.Ci % 4 == 0) && al16(x);
+  p.vec_out = (g.y_cs % 4 == 0) && (g.y_co % 4 == 0) && al16(y);
+  const long long M = (long long)g.N * g.Ho * g.Wo, K = (long long)g.kh * g.kw * g.Ci;
+  if (M == 0) return 0;
+  CKT(launch_tc(p, M, g.Co, 1, K, op, stream));
+  return 0;
+}
+
+int wdg_tc_conv2d_bwd_data(const ConvGeo& g, const float* dy, const float* w, float* dx, int accumulate, int op,
+                           cudaStream_t stream) {
+  const int s = g.stride;
+  for (int ry = 0; ry < s; ++ry)
+    for (int rx = 0; rx < s; ++rx) {
+      TcBwdData p{g, make_bwd_class(g, ry, rx), dy, w, dx, accumulate, 0, 0, 0};
+      p.vec_in = (g.y_cs % 4 == 0) && (g.y_co % 4 == 0) && (g.Co % 4 == 0) && al16(dy);
+      p.vec_w = (g.Co % 4 == 0) && al16(w);
+      p.vec_out = (g.x_cs % 4 == 0) && (g.x_co % 4 == 0) && al16(dx);
+      const long long M = (long long)g.N * p.c.Hc * p.c.Wc, K = (long long)p.c.Jy * p.c.Jx * g.Co;
+      if (M == 0) continue;
+      CKT(launch_tc(p, M, g.Ci, 1, K > 0 ? K : 1, op, stream));
+    }
+  return 0;
+}
+
+// Split-K plan of the backward-weight GEMM: about two waves of CTAs (2 CTAs per SM), at least 4 K blocks per split.
+void wdg_tc_wgrad_plan(const ConvGeo& g, int op, int* splits_out, long long* kps_out) {
+  const long long M = (long long)g.kh * g.kw * g.Ci, K = (long long)g.N * g.Ho * g.Wo;
+  const int BN = pick_bn(g.Co), KB = op == OP_BF16 ? 64 : 32;
+  const long long tiles = ((M + TILE_M - 1) / TILE_M) * ((g.Co + BN - 1) / BN);
+  long long splits = (4 * 148 + tiles - 1) / tiles;
+  const long long max_splits = (K + 4 * KB - 1) / (4 * KB);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  long long kps = (K + splits - 1) / splits;
+  kps = (kps + KB - 1) / KB * KB;
+  splits = (K + kps - 1) / kps;
+  if (splits < 1) splits = 1;
+  *splits_out = (int)splits;
+  *kps_out = kps;
+}
+
+int wdg_tc_conv2d_bwd_weight(const ConvGeo& g, const float* x, const float* dy, float* part, int splits, long long kps, int op,
+                             cudaStream_t stream) {
+  TcWgrad p{g, x, dy, part, kps};
+  const long long M = (long long)g.kh * g.kw * g.Ci;
+  CKT(launch_tc(p, M, g.Co, splits, kps, op, stream));
+  return 0;
+}

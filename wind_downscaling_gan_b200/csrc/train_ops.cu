@@ -10,22 +10,9 @@
 #include <string>
 
 #include "../../include/wdg.h"
-
-extern int wdg_set_error(const std::string& m);
-
-#define CKT(call)                                                                                    \
-  do {                                                                                               \
-    cudaError_t _e = (call);                                                                         \
-    if (_e != cudaSuccess) return wdg_set_error(std::string(#call) + ": " + cudaGetErrorString(_e)); \
-  } while (0)
+#include "train_geo.cuh"
 
 namespace {
-
-struct ConvGeo {
-  int N, H, W, Ci, kh, kw, Co, stride, pad_t, pad_l, Ho, Wo;
-  int x_cs, x_co;   // channel stride / offset of x (input side, Ci channels)
-  int y_cs, y_co;   // channel stride / offset of y (output side, Co channels)
-};
 
 // ------------------------------------------------------------------ implicit GEMM on CUDA cores
 // C[M][N] (+)= sum_k A(m,k) * B(k,n); 64x64 block tile, 16-deep K tiles, 256 threads x (4x4) outputs.
@@ -749,15 +736,19 @@ inline unsigned blocks_for(long long n, int t = 256) { return (unsigned)((n + t 
 }  // namespace
 
 // ====================================================================== C ABI
-static ConvGeo make_geo(const int* g) {
-  ConvGeo c;
-  c.N = g[0]; c.H = g[1]; c.W = g[2]; c.Ci = g[3]; c.kh = g[4]; c.kw = g[5]; c.Co = g[6]; c.stride = g[7];
-  c.pad_t = g[8]; c.pad_l = g[9]; c.Ho = g[10]; c.Wo = g[11]; c.x_cs = g[12]; c.x_co = g[13]; c.y_cs = g[14]; c.y_co = g[15];
-  return c;
+// Arithmetic of the convolution GEMMs: 0 = fp32 on CUDA cores (this file), 1 = tf32 / 2 = bf16 operands on tcgen05
+// with fp32 accumulation (train_gemm_tc.cu).  Process-wide, like the error string; set between steps.
+static int g_train_precision = 0;
+extern "C" int wdg_train_set_precision(int mode) {
+  if (mode < 0 || mode > 2) return wdg_set_error("wdg_train_set_precision: mode must be 0 (fp32), 1 (tf32) or 2 (bf16)");
+  g_train_precision = mode;
+  return 0;
 }
+extern "C" int wdg_train_get_precision(void) { return g_train_precision; }
 
 extern "C" int wdg_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, const int* geo, int accumulate,
                               void* stream) {
+  if (g_train_precision) return wdg_tc_conv2d_fwd(make_geo(geo), x, w, bias, y, accumulate, g_train_precision, (cudaStream_t)stream);
   FwdProblem p{make_geo(geo), x, w, bias, y, accumulate};
   const long long M = (long long)p.g.N * p.g.Ho * p.g.Wo;
   CKT(launch_gemm(p, M, p.g.Co, (cudaStream_t)stream));
@@ -766,6 +757,7 @@ extern "C" int wdg_conv2d_fwd(const float* x, const float* w, const float* bias,
 
 extern "C" int wdg_conv2d_bwd_data(const float* dy, const float* w, float* dx, const int* geo, int accumulate, void* stream) {
   const ConvGeo gg = make_geo(geo);
+  if (g_train_precision) return wdg_tc_conv2d_bwd_data(gg, dy, w, dx, accumulate, g_train_precision, (cudaStream_t)stream);
   if (gg.stride > 1 && gg.kh >= gg.stride && gg.kw >= gg.stride) {
     const int s = gg.stride;
     for (int ry = 0; ry < s; ++ry)
@@ -790,6 +782,13 @@ extern "C" int wdg_conv2d_bwd_data(const float* dy, const float* w, float* dx, c
 extern "C" int wdg_conv2d_bwd_weight_scratch(const int* geo, size_t* bytes, int* splits_out) {
   const ConvGeo g = make_geo(geo);
   const long long M = (long long)g.kh * g.kw * g.Ci, K = (long long)g.N * g.Ho * g.Wo;
+  if (g_train_precision) {
+    int sp; long long kps;
+    wdg_tc_wgrad_plan(g, g_train_precision, &sp, &kps);
+    if (splits_out) *splits_out = sp;
+    if (bytes) *bytes = (size_t)((long long)sp * M * g.Co * sizeof(float));
+    return 0;
+  }
   const long long tiles = g.Co <= 16 ? ((M + 127) / 128) * ((g.Co + 15) / 16) : ((M + 63) / 64) * ((g.Co + 63) / 64);
   long long splits = (4 * 148 + tiles - 1) / tiles;
   const long long max_splits = (K + 255) / 256;
@@ -808,7 +807,11 @@ extern "C" int wdg_conv2d_bwd_weight(const float* x, const float* dy, float* dw,
   BwdWeightProblem p{make_geo(geo), x, dy, (float*)scratch, 0};
   const long long M = (long long)p.g.kh * p.g.kw * p.g.Ci, K = (long long)p.g.N * p.g.Ho * p.g.Wo;
   p.k_per_split = (int)((K + splits - 1) / splits);
-  if (p.g.Co <= 16) {
+  if (g_train_precision) {
+    long long kps;
+    wdg_tc_wgrad_plan(p.g, g_train_precision, &splits, &kps);
+    if (int rc = wdg_tc_conv2d_bwd_weight(p.g, x, dy, (float*)scratch, splits, kps, g_train_precision, stream)) return rc;
+  } else if (p.g.Co <= 16) {
     dim3 grid((unsigned)((M + 127) / 128), (p.g.Co + 15) / 16, splits);
     gemm_wgrad_kernel<128, 16><<<grid, 256, 0, stream>>>(p);
   } else {

@@ -18,6 +18,19 @@ def use_current_stream():
     _stream[0] = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2}
+
+
+def set_precision(name):
+    """Arithmetic of the convolution GEMMs: "fp32" (CUDA cores), "tf32" or "bf16" (tcgen05, fp32 accumulate)."""
+    _lib.check(_lib.lib().wdg_train_set_precision(PRECISIONS[name]))
+
+
+def get_precision():
+    mode = _lib.lib().wdg_train_get_precision()
+    return {v: k for k, v in PRECISIONS.items()}[mode]
+
+
 def _s():
     if _stream[0] is None:
         use_current_stream()
