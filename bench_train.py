@@ -5,8 +5,9 @@ N GPUs with an NCCL gradient all-reduce and synchronised BatchNorm (weak scaling
 
     python bench_train.py [--steps K] [--warmup W]          (N > 1: launch with torch.distributed.run)
 
-Prints one JSON line (rank 0).  The fp32 training kernels run on CUDA cores (first, correctness-oriented version):
-the roofline entry is reported against the fp32 FMA peak of the SMs, not against the tensor-core peak.
+Prints one JSON line (rank 0).  --precision selects the arithmetic of the convolution GEMMs: fp32 (CUDA cores),
+tf32 (default) or bf16 (tcgen05 tensor cores, fp32 accumulation); the roofline entry is reported against the
+matching peak.
 The CPU baseline is the torch-CPU float32 restatement of the same step (oracle/torch_train.py) on a bounded sample.
 """
 import argparse
@@ -52,6 +53,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"],
+                    help="arithmetic of the convolution GEMMs: fp32 = CUDA cores, tf32 / bf16 = tcgen05 (fp32 accumulate)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -60,6 +63,8 @@ def main():
     from wind_downscaling_gan_b200.gan.ganbase import GAN
     from wind_downscaling_gan_b200.gan.models import make_discriminator, make_generator
     from wind_downscaling_gan_b200.train.dist import Comm
+    from wind_downscaling_gan_b200.train import ops as train_ops
+    train_ops.set_precision(args.precision)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
@@ -102,19 +107,28 @@ def main():
         ms_step = ms / args.steps
         samples = world * B / (ms_step * 1e-3)
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12     # FMA lanes x 2 flop x max SM clock
+        try:
+            bf16_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
+        except Exception:
+            bf16_peak = 1377.3
+        peak = {"fp32": fp32_peak, "tf32": bf16_peak / 2, "bf16": bf16_peak}[args.precision]
+        bound = {"fp32": "fp32-cuda-core", "tf32": "tensor", "bf16": "tensor"}[args.precision]
+        note = {"fp32": "implicit-GEMM convs on CUDA cores (fp32 FMA peak of the SMs)",
+                "tf32": "tcgen05 kind::tf32 gather-fed implicit GEMMs; peak = half the measured sustained bf16 rate",
+                "bf16": "tcgen05 kind::f16 (bf16) gather-fed implicit GEMMs; peak = measured sustained bf16 rate"}[args.precision]
         cpu = None
         if not args.no_cpu_baseline:
             v, cores, sample = cpu_baseline()
             cpu = {"value": v, "unit": "sequence-timesteps/s", "cores": cores, "kind": "port", "sample": sample + "; torch-CPU fp32 autograd restatement of ganbase.py:21-94"}
         line = {"metric": "wgan_train_samples_per_sec", "value": samples, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
+                "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
                 "config": {"workload": f"WGAN train_step, batch {B} per GPU x {T} timesteps x {S}x{S} (BASELINE configs[3])",
                            "parallelism": f"data parallel x{world}: NCCL flat-bucket gradient all-reduce + synchronised BatchNorm"},
                 "sequence_timesteps_per_sec": samples * T,
-                "roofline": {"bound": "fp32-cuda-core", "achieved": FLOP_PER_SAMPLE * samples / world / 1e12, "peak": fp32_peak,
-                             "unit": "TFLOP/s", "frac": FLOP_PER_SAMPLE * samples / world / 1e12 / fp32_peak, "traffic": None,
-                             "note": "implicit-GEMM convs on CUDA cores (fp32); tensor-core version is future work"},
+                "roofline": {"bound": bound, "achieved": FLOP_PER_SAMPLE * samples / world / 1e12, "peak": peak,
+                             "unit": "TFLOP/s", "frac": FLOP_PER_SAMPLE * samples / world / 1e12 / peak, "traffic": None,
+                             "note": note},
                 "cpu_baseline": cpu, "last_metrics": {k: v for k, v in m.items() if v is not None}}
         print(json.dumps(line), flush=True)
     if world > 1:

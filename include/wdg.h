@@ -147,7 +147,7 @@ int wdg_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, 
 int wdg_conv2d_bwd_data(const float* dy, const float* w, float* dx, const int* geo, int accumulate, void* stream);
 int wdg_conv2d_bwd_weight_scratch(const int* geo, size_t* bytes, int* splits);
 int wdg_conv2d_bwd_weight(const float* x, const float* dy, float* dw, const int* geo, void* scratch, int accumulate, void* stream);
-/* out[C] (+)= column sums over R rows; mode 0: a, 1: a*b, 2: a*a; scratch >= 64*C floats */
+/* out[C] (+)= column sums over R rows; mode 0: a, 1: a*b, 2: a*a; scratch >= 512*C floats */
 int wdg_colsum(int mode, const float* a, int a_cs, int a_co, const float* b, int b_cs, int b_co, long long R, int C, float* out,
                void* scratch, int accumulate, void* stream);
 int wdg_leaky_relu_fwd(float* x, long long n, float alpha, void* stream);
@@ -158,7 +158,8 @@ int wdg_axpby(float* out, int o_cs, int o_co, const float* x, int x_cs, int x_co
 int wdg_bias_act(float* x, int cs, int co, const float* bias, long long rows, int C, float alpha, void* stream);
 int wdg_transpose01(const float* in, float* out, int A, int B, long long inner, void* stream);
 int wdg_lerp_batch(float* out, const float* real, const float* fake, const float* eps, long long per_sample, long long n, void* stream);
-/* BatchNormalization (axis -1, eps, momentum): training mode uses batch statistics and updates the moving ones */
+/* BatchNormalization (axis -1, eps, momentum): training mode uses batch statistics and updates the moving ones.
+ * scratch: wdg_bn_train_fwd >= 514*C floats, wdg_bn_bwd_sums / wdg_bn_train_bwd >= 512*C floats, wdg_bn_infer >= C floats */
 int wdg_bn_train_fwd(const float* x, float* y, const float* gamma, const float* beta, float* moving_mean, float* moving_var,
                      float* save_mean, float* save_invstd, long long rows, int C, float eps, float momentum, void* scratch, void* stream);
 /* Split forms for data-parallel (synchronised) BatchNorm: per-channel sums are all-reduced by the caller */
@@ -173,7 +174,7 @@ int wdg_bn_infer(const float* x, float* y, const float* gamma, const float* beta
                  long long rows, int C, float eps, void* scratch, void* stream);
 int wdg_bn_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
                      float* dx, float* dgamma, float* dbeta, long long rows, int C, void* scratch, void* stream);
-/* LayerNormalization over the channel axis */
+/* LayerNormalization over the channel axis (wdg_ln_bwd scratch >= rows*C + 512*C floats) */
 int wdg_ln_fwd(const float* x, float* y, int y_cs, int y_co, const float* gamma, const float* beta, float* save_mean,
                float* save_invstd, long long rows, int C, float eps, void* stream);
 int wdg_ln_bwd(const float* dy, int dy_cs, int dy_co, const float* x, const float* gamma, const float* save_mean,
@@ -191,7 +192,8 @@ int wdg_dense_mean_bwd(const float* dscore, const float* flat, const float* w, f
 int wdg_reduce(int mode, const float* a, const float* b, long long n, double scale, float* out, void* scratch, void* stream);
 /* gradient-penalty norms (ganbase.py:36): out[b*C+c] = sqrt(sum over (T,H,W) of g^2) */
 int wdg_gp_norm(const float* g, float* out, int B, long long per_sample_px, int C, void* stream);
-/* Keras Adam step (epsilon outside the square root) and one TFA SpectralNormalization power iteration (in place) */
+/* Keras Adam step (epsilon outside the square root) and one TFA SpectralNormalization power iteration (in place;
+ * scratch >= (R + 64*C + 4) floats) */
 int wdg_adam(float* w, float* m, float* v, const float* g, long long n, float lr_t, float b1, float b2, float eps, void* stream);
 int wdg_sn_update(float* w, float* u, int R, int C, void* scratch, void* stream);
 

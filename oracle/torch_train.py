@@ -16,6 +16,60 @@ from .critic import critic_weight_shapes
 
 LW = "layer_with_weights-%d/"
 DT = torch.float64
+# Operand rounding of the convolution GEMMs, to check the tensor-core training kernels decision-for-decision:
+# None (exact), "tf32" (fp32 -> 10-bit mantissa, round to nearest, ties away: PTX cvt.rna.tf32.f32) or "bf16"
+# (fp32 -> bf16, round to nearest even).  Every GEMM of the product path rounds BOTH operands: the forward
+# (x, w), the backward-data (dy, w) and the backward-weight (x, dy) one; accumulation stays exact here.
+OPERAND = None
+
+
+def rnd(x):
+    if OPERAND is None:
+        return x
+    x32 = x.detach().to(torch.float32)
+    if OPERAND == "bf16":
+        return x32.to(torch.bfloat16).to(DT)
+    bits = x32.contiguous().view(torch.int32)
+    bits = (bits + 0x1000) & ~0x1FFF          # sign-magnitude: rounds the magnitude, ties away from zero
+    return bits.view(torch.float32).to(DT)
+
+
+class _RoundedConv(torch.autograd.Function):
+    """conv2d / conv_transpose2d whose three GEMMs see rounded operands (bias and accumulation exact)."""
+
+    @staticmethod
+    def forward(ctx, x, w, transposed, stride, padding):
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (transposed, stride, padding)
+        if transposed:
+            return Fn.conv_transpose2d(rnd(x), rnd(w), None, stride=stride, padding=padding)
+        return Fn.conv2d(rnd(x), rnd(w), None, stride=stride, padding=padding)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        transposed, stride, padding = ctx.cfg
+        if transposed:   # y = conv_bwd_data(x, w): dx = conv_fwd(dy, w), dw = conv_bwd_weight(input = dy, grad = x)
+            dx = Fn.conv2d(rnd(dy), rnd(w), None, stride=stride, padding=padding)
+            dw = torch.nn.grad.conv2d_weight(rnd(dy), w.shape, rnd(x), stride=stride, padding=padding)
+        else:
+            dx = torch.nn.grad.conv2d_input(x.shape, rnd(w), rnd(dy), stride=stride, padding=padding)
+            dw = torch.nn.grad.conv2d_weight(rnd(x), w.shape, rnd(dy), stride=stride, padding=padding)
+        return dx, dw, None, None, None
+
+
+def conv2d(x, w, b=None, stride=1, padding=0):
+    if OPERAND is None:
+        return Fn.conv2d(x, w, b, stride=stride, padding=padding)
+    y = _RoundedConv.apply(x, w, False, stride, padding)
+    return y if b is None else y + b.view(1, -1, 1, 1)
+
+
+def conv_transpose2d(x, w, b=None, stride=1, padding=0):
+    if OPERAND is None:
+        return Fn.conv_transpose2d(x, w, b, stride=stride, padding=padding)
+    y = _RoundedConv.apply(x, w, True, stride, padding)
+    return y if b is None else y + b.view(1, -1, 1, 1)
 
 
 def T(a):
@@ -97,7 +151,7 @@ def conv_lstm(x, K, R, b):
     c = torch.zeros_like(h)
     outs = []
     for t in range(Tn):
-        z = Fn.conv2d(x[:, t], hwio(K), b, padding=1) + Fn.conv2d(h, hwio(R), None, padding=1)
+        z = conv2d(x[:, t], hwio(K), b, padding=1) + conv2d(h, hwio(R), None, padding=1)
         zi, zf, zc, zo = z.split(Fc, 1)
         i = torch.clamp(0.2 * zi + 0.5, 0, 1)
         f = torch.clamp(0.2 * zf + 0.5, 0, 1)
@@ -125,20 +179,20 @@ def generator(w, image, noise, training):
     r = leafify(w, trainable(w)) if training else w
     B, Tn, S = image.shape[:3]
     x = torch.cat([image, noise], -1).reshape(B * Tn, S, S, -1).permute(0, 3, 1, 2)
-    x = bn(lrelu(Fn.conv2d(x, hwio(r[(LW % 0) + "layer/w"]), r[(LW % 0) + "layer/layer/bias"], stride=2, padding=3)), r, 1, training)
+    x = bn(lrelu(conv2d(x, hwio(r[(LW % 0) + "layer/w"]), r[(LW % 0) + "layer/layer/bias"], stride=2, padding=3)), r, 1, training)
     res2 = x
-    x = bn(lrelu(Fn.conv2d(x, hwio(r[(LW % 2) + "layer/w"]), r[(LW % 2) + "layer/layer/bias"], stride=2, padding=1)), r, 3, training)
+    x = bn(lrelu(conv2d(x, hwio(r[(LW % 2) + "layer/w"]), r[(LW % 2) + "layer/layer/bias"], stride=2, padding=1)), r, 3, training)
     res4 = x
     s4 = x.shape[-1]
     x = conv_lstm(x.reshape(B, Tn, -1, s4, s4), r[(LW % 4) + "cell/kernel"], r[(LW % 4) + "cell/recurrent_kernel"], r[(LW % 4) + "cell/bias"])
     x = x.reshape(B * Tn, -1, s4, s4)
-    x = bn(lrelu(Fn.conv2d(x, hwio(r[(LW % 5) + "layer/w"]), r[(LW % 5) + "layer/layer/bias"], padding=1)), r, 6, training)
+    x = bn(lrelu(conv2d(x, hwio(r[(LW % 5) + "layer/w"]), r[(LW % 5) + "layer/layer/bias"], padding=1)), r, 6, training)
     x = torch.cat([x, res4], 1)
-    x = bn(lrelu(Fn.conv_transpose2d(x, convt_w(r[(LW % 7) + "layer/w"]), r[(LW % 7) + "layer/layer/bias"], stride=2)), r, 8, training)
+    x = bn(lrelu(conv_transpose2d(x, convt_w(r[(LW % 7) + "layer/w"]), r[(LW % 7) + "layer/layer/bias"], stride=2)), r, 8, training)
     x = torch.cat([x, res2], 1)
     x = Fn.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
-    x = bn(lrelu(Fn.conv_transpose2d(x, convt_w(r[(LW % 9) + "layer/kernel"]), r[(LW % 9) + "layer/bias"], padding=2)), r, 10, training)
-    x = Fn.conv2d(x, hwio(r[(LW % 11) + "layer/kernel"]), r[(LW % 11) + "layer/bias"], padding=1)
+    x = bn(lrelu(conv_transpose2d(x, convt_w(r[(LW % 9) + "layer/kernel"]), r[(LW % 9) + "layer/bias"], padding=2)), r, 10, training)
+    x = conv2d(x, hwio(r[(LW % 11) + "layer/kernel"]), r[(LW % 11) + "layer/bias"], padding=1)
     if training:   # BN moving statistics were written into r (a copy): propagate
         for k in w:
             if k.endswith(("moving_mean", "moving_variance")):
@@ -159,7 +213,7 @@ def critic(w, low_res, high_res, training, P=None):
     r = leafify(w, trainable(w)) if training else w
 
     def snconv(x, i, stride=1, pad=0):
-        return lrelu(Fn.conv2d(x, hwio(r[(LW % i) + "layer/w"]), r[(LW % i) + "layer/layer/bias"], stride=stride, padding=pad))
+        return lrelu(conv2d(x, hwio(r[(LW % i) + "layer/w"]), r[(LW % i) + "layer/layer/bias"], stride=stride, padding=pad))
 
     def cf(x):   # (B,T,S,S,C) -> (B,T,C,S,S)
         return x.permute(0, 1, 4, 2, 3)

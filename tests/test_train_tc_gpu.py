@@ -87,6 +87,29 @@ def test_conv_fwd_bwd_tc(ops, prec, N, H, W, Ci, k, Co, s, p):
     yv = wide_y[..., 2:2 + Co].double().permute(0, 3, 1, 2)
     ref2 = torch.autograd.grad(F.conv2d(xr, wr.detach(), None, stride=s, padding=p), xr, yv)[0].permute(0, 2, 3, 1)
     assert rel(dx2[..., 4:] - 2.0, ref2) < tol
+    # Operands that are exactly representable in the operand type make the loaders' rounding the identity: what is left
+    # is the fp32 accumulation in TMEM, so all three GEMMs must match float64 like the fp32 kernels do (1e-5).
+    from oracle import torch_train as tt
+    tt.OPERAND = prec
+    try:
+        xq, wq, dyq = (tt.rnd(t.cpu()).float().cuda() for t in (x, w, dy))
+    finally:
+        tt.OPERAND = None
+    xr = xq.double().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wq.double().permute(3, 2, 0, 1).requires_grad_(True)
+    yr = F.conv2d(xr, wr, b.double(), stride=s, padding=p)
+    yr.backward(dyq.double().permute(0, 3, 1, 2))
+    ops.set_precision(prec)
+    try:
+        ops.conv2d_fwd(ops.full(xq), wq, b, ops.full(y), N, H, W, s, p, Ho, Wo)
+        ops.conv2d_bwd_data(ops.full(dyq), wq, ops.full(dx), N, H, W, s, p, Ho, Wo)
+        ops.conv2d_bwd_weight(ops.full(xq), ops.full(dyq), dw, N, H, W, s, p, Ho, Wo)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_precision("fp32")
+    e = {"y": rel(y, yr.permute(0, 2, 3, 1)), "dx": rel(dx, xr.grad.permute(0, 2, 3, 1)), "dw": rel(dw, wr.grad.permute(2, 3, 1, 0))}
+    print(prec, "pre-rounded operands", {k_: f"{v:.2e}" for k_, v in e.items()})
+    assert all(v < 1e-5 for v in e.values()), e
 
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
@@ -110,3 +133,131 @@ def test_conv_transpose_via_bwd_data_tc(ops, prec):
         assert rel(y, ref) < TOL[prec]
     finally:
         ops.set_precision("fp32")
+
+
+# ---------------------------------------------------------------------------------------- whole graphs
+# The graph wiring (layer order, saved tensors, SN / BN state updates, Adam) is the same Python for every operand type
+# and is checked to 2e-4 in fp32 by test_train_gpu.py; each tcgen05 GEMM is checked alone above.  Here the whole
+# graphs run on the tcgen05 GEMMs and are compared with the EXACT float64 oracle:
+#   * forward outputs (generator image, critic score): north_star's tolerance for the operand type;
+#   * gradients: direction (cosine over all weights) and a loose relative bound.  A perturbation of relative size eps
+#     flips the LeakyReLU / hard-sigmoid branch of a fraction ~eps of the units and each flip changes that unit's
+#     term by O(1), so gradients of these piecewise-linear networks move by O(sqrt(eps)) in relative L2 under ANY
+#     rounding of the operands (measured: 1-6e-2 for tf32, 2-10e-2 for bf16); they cannot be held to the forward tolerance.
+EXACT_FWD_TOL = {"tf32": 1e-3, "bf16": 1e-2}
+GRAD_REL_BOUND = {"tf32": 0.15, "bf16": 0.4}
+GRAD_COSINE = {"tf32": 0.999, "bf16": 0.995}
+
+
+def _np(a):
+    import numpy as np
+    return np.asarray(a.detach().cpu().numpy() if hasattr(a, "detach") else a, np.float64)
+
+
+def _np_rel(a, b):
+    import numpy as np
+    a, b = _np(a), _np(b)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def _cosine(ga, gb):
+    import numpy as np
+    a = np.concatenate([_np(ga[n]).ravel() for n in sorted(gb)])
+    b = np.concatenate([_np(gb[n]).ravel() for n in sorted(gb)])
+    return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_generator_and_critic_graphs_tc(ops, prec):
+    """Training-mode generator forward/backward and critic forward/backward on the tcgen05 GEMMs."""
+    import numpy as np
+    import torch
+    from oracle import torch_train as tt
+    from oracle.critic import synthetic_critic_weights
+    from oracle.generator import synthetic_generator_weights
+    from wind_downscaling_gan_b200.train.nets import CriticNet, GenNet, to_device
+    B, T, S = 2, 2, 32
+    rng = np.random.default_rng(2)
+    lr = rng.standard_normal((B, T, S, S, 3)).astype(np.float32)
+    hr = rng.standard_normal((B, T, S, S, 2)).astype(np.float32)
+    noise = (0.1 * rng.standard_normal((B, T, S, S, 20))).astype(np.float32)
+    gw, dw_ = synthetic_generator_weights(3), synthetic_critic_weights(5, size=S)
+    dout = rng.standard_normal((B, T, S, S, 2))
+    ds = np.array([[0.7], [-1.3]])
+    ref_w = {k: tt.T(v).clone() for k, v in gw.items()}
+    out_ref, reads = tt.generator(ref_w, tt.T(lr), tt.T(noise), training=True)
+    names = tt.trainable(ref_w)
+    gg_ref = dict(zip(names, torch.autograd.grad((out_ref * tt.T(dout)).sum(), [reads[n] for n in names])))
+    ref_d = {k: tt.T(v).clone() for k, v in dw_.items()}
+    hr_t = tt.T(hr).requires_grad_(True)
+    s_ref, dreads = tt.critic(ref_d, tt.T(lr), hr_t, training=True)
+    dnames = tt.trainable(ref_d)
+    dgr = torch.autograd.grad((s_ref * tt.T(ds)).sum(), [dreads[n] for n in dnames] + [hr_t])
+    dg_ref = dict(zip(dnames, dgr[:-1]))
+    ops.set_precision(prec)
+    try:
+        net = GenNet(to_device(gw))
+        out = net.forward(torch.from_numpy(lr).cuda(), torch.from_numpy(noise).cuda(), training=True)
+        grads = net.backward(torch.from_numpy(dout.astype(np.float32)).cuda())
+        cnet = CriticNet(to_device(dw_), S)
+        s = cnet.forward(torch.from_numpy(lr).cuda(), torch.from_numpy(hr).cuda(), training=True)
+        g, dhr = cnet.backward(torch.from_numpy(ds.astype(np.float32)).cuda(), need_weight_grads=True, need_input_grad=True)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_precision("fp32")
+    assert set(grads) == set(gg_ref) and set(g) == set(dg_ref)
+    fwd = {"G out": _np_rel(out, out_ref), "D score": _np_rel(s, s_ref)}
+    grd = {"D dhr": _np_rel(dhr, dgr[-1]), "G grads (max)": max(_np_rel(grads[n], r) for n, r in gg_ref.items()),
+           "D grads (max)": max(_np_rel(g[n], r) for n, r in dg_ref.items())}
+    cos = {"G": _cosine(grads, gg_ref), "D": _cosine(g, dg_ref)}
+    print(prec, "forward", {k: f"{v:.2e}" for k, v in fwd.items()}, "gradients", {k: f"{v:.2e}" for k, v in grd.items()},
+          "cosine", {k: f"{v:.6f}" for k, v in cos.items()})
+    assert all(v < EXACT_FWD_TOL[prec] for v in fwd.values()), fwd
+    assert all(v < GRAD_REL_BOUND[prec] for v in grd.values()), grd
+    assert all(v > GRAD_COSINE[prec] for v in cos.values()), cos
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_train_step_tc(ops, prec):
+    """One full WGAN step on the tcgen05 GEMMs vs the exact float64 oracle step: metrics and updated weights within
+    10x the forward tolerance of the operand type (three critic updates and one generator update deep)."""
+    import numpy as np
+    from oracle import torch_train as tt
+    from oracle.critic import synthetic_critic_weights
+    from oracle.generator import synthetic_generator_weights
+    from wind_downscaling_gan_b200.data.data_generator import FlexibleNoiseGenerator
+    from wind_downscaling_gan_b200.gan import train
+    from wind_downscaling_gan_b200.gan.ganbase import GAN
+    from wind_downscaling_gan_b200.gan.models import make_discriminator, make_generator
+    B, T, S = 2, 2, 32
+    rng = np.random.default_rng(6)
+    lr = rng.standard_normal((B, T, S, S, 3)).astype(np.float32)
+    hr = rng.standard_normal((B, T, S, S, 2)).astype(np.float32)
+    gw, dw = synthetic_generator_weights(7), synthetic_critic_weights(8, size=S)
+    draws = []
+    for _ in range(3):
+        draws += [0.1 * rng.standard_normal((B, T, S, S, 20)), rng.uniform(0, 1, (B,)),
+                  0.1 * rng.standard_normal((B, T, S, S, 2)), 0.1 * rng.standard_normal((B, T, S, S, 2))]
+    draws += [0.1 * rng.standard_normal((B, T, S, S, 20)), 0.1 * rng.standard_normal((B, T, S, S, 20))]
+    draws = [np.asarray(d, np.float32) for d in draws]
+    st = tt.State(gw, dw)
+    m_ref = tt.train_step(st, lr, hr, draws)
+    gen, disc = make_generator(S, 3, 20, 2, T), make_discriminator(S, S, 3, 2, T)
+    gen.set_weights(gw)
+    disc.set_weights(dw)
+    gan = GAN(gen, disc, FlexibleNoiseGenerator((B, T, S, S, 20), std=0.1))
+    gan.compile(generator_optimizer=train.generator_optimizer(), discriminator_optimizer=train.discriminator_optimizer(),
+                discriminator_loss=train.discriminator_loss)
+    ops.set_precision(prec)
+    try:
+        m = gan.train_step((lr, hr), draws=draws)
+        gan.sync_weights()
+    finally:
+        ops.set_precision("fp32")
+    new_g, new_d = gen.get_weights(), disc.get_weights()
+    tol = 10 * EXACT_FWD_TOL[prec]
+    worst = max(max(_np_rel(new_g[k], v) for k, v in st.g.items()), max(_np_rel(new_d[k], v) for k, v in st.d.items()))
+    dm = {k: abs(m[k] - m_ref[k]) / max(1.0, abs(m_ref[k])) for k in
+          ("g_loss", "g_disc_loss", "d_loss", "d_gradient_pen", "g_gradient_param", "d_gradient_param")}
+    print(prec, "updated weights worst rel-L2", f"{worst:.2e}", "metrics", {k: f"{v:.2e}" for k, v in dm.items()})
+    assert worst < tol and max(dm.values()) < 2 * tol, (worst, dm)

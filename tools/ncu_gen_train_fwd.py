@@ -4,6 +4,8 @@ import torch
 from wind_downscaling_gan_b200.train.nets import GenNet, CriticNet, to_device
 from oracle.generator import synthetic_generator_weights
 from oracle.critic import synthetic_critic_weights
+from wind_downscaling_gan_b200.train import ops
+ops.set_precision(sys.argv[1] if len(sys.argv) > 1 else "fp32")
 B, T, S = 8, 24, 96
 gw, dw = to_device(synthetic_generator_weights(0)), to_device(synthetic_critic_weights(1, size=S))
 g = torch.Generator(device="cuda").manual_seed(0)

@@ -7,6 +7,8 @@
 // the channel stride / offset of a tensor inside a wider (concatenated) buffer.
 #include <cuda_runtime.h>
 
+#include <stdint.h>
+
 #include <string>
 
 #include "../../include/wdg.h"
@@ -342,39 +344,59 @@ static cudaError_t launch_gemm(const P& p, long long M, int N, cudaStream_t stre
   return cudaGetLastError();
 }
 
-// dst[i] (+)= sum_s part[s][i]   (fixed order: deterministic)
+// dst[i] (+)= sum_s part[s * stride + i]   (fixed order: deterministic)
 __global__ void reduce_splits_kernel(const float* __restrict__ part, float* __restrict__ dst, long long n, int splits,
-                                     int accumulate) {
+                                     int accumulate, long long stride = 0) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (stride == 0) stride = n;
   float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += part[(long long)k * n + i];
+  for (int k = 0; k < splits; ++k) s += part[(long long)k * stride + i];
   dst[i] = accumulate ? dst[i] + s : s;
 }
 
 // ------------------------------------------------------------------ column reductions over rows of [R][cs] (+co)
-// out[c] (+)= sum_r f(row r, channel c).  One block per 32 channels x row-slab; two-stage via partials.
-template <int MODE>   // 0: sum a   1: sum a*b   2: sum a*a
+// One block per 32 channels x row-slab (8 row lanes, 4 rows in flight per lane); partials part[slab][2][C] are then
+// reduced in slab order (deterministic).  MODE 0: s1 = sum a   1: s1 = sum a*b   2: s1 = sum a*a
+// 3: s1 = sum a, s2 = sum a*a (BatchNorm statistics)   4: s1 = sum a*(b - mean)*invstd, s2 = sum a (BatchNorm backward)
+constexpr int CS_SLABS = 256;
+template <int MODE>
 __global__ void colsum_partial_kernel(const float* __restrict__ a, int a_cs, int a_co, const float* __restrict__ b, int b_cs,
-                                      int b_co, long long R, int C, float* __restrict__ part) {
-  __shared__ float sm[8][33];
+                                      int b_co, const float* __restrict__ mean, const float* __restrict__ invstd, long long R,
+                                      int C, float* __restrict__ part) {
+  __shared__ float sm[2][8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const long long rows_per = (R + gridDim.y - 1) / gridDim.y;
   const long long r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
-  float s = 0.f;
-  if (c < C)
-    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
-      const float av = a[r * a_cs + a_co + c];
-      if (MODE == 0) s += av;
-      else if (MODE == 1) s += av * b[r * b_cs + b_co + c];
-      else s += av * av;
+  float s1 = 0.f, s2 = 0.f;
+  if (c < C) {
+    float mu = 0.f, is = 0.f;
+    if (MODE == 4) { mu = mean[c]; is = invstd[c]; }
+    for (long long r = r0 + threadIdx.y; r < r1; r += 32) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long rr = r + 8 * j;
+        av[j] = rr < r1 ? a[rr * a_cs + a_co + c] : 0.f;
+        if (MODE == 1 || MODE == 4) bv[j] = rr < r1 ? b[rr * b_cs + b_co + c] : mu;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (MODE == 0) s1 += av[j];
+        else if (MODE == 1) s1 += av[j] * bv[j];
+        else if (MODE == 2) s1 += av[j] * av[j];
+        else if (MODE == 3) { s1 += av[j]; s2 += av[j] * av[j]; }
+        else { s1 += av[j] * (bv[j] - mu) * is; s2 += av[j]; }
+      }
     }
-  sm[threadIdx.y][threadIdx.x] = s;
+  }
+  sm[0][threadIdx.y][threadIdx.x] = s1;
+  sm[1][threadIdx.y][threadIdx.x] = s2;
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
+  if (threadIdx.y < 2 && c < C) {
     float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
-    part[(long long)blockIdx.y * C + c] = t;
+    for (int i = 0; i < 8; ++i) t += sm[threadIdx.y][i][threadIdx.x];
+    part[((long long)blockIdx.y * 2 + threadIdx.y) * C + c] = t;
   }
 }
 
@@ -466,14 +488,6 @@ __global__ void bn_bwd_kernel(const float* __restrict__ dy, const float* __restr
   const float xhat = (x[i] - mean[c]) * invstd[c];
   const float inv_r = 1.f / (float)rows_global;
   dx[i] = gamma[c] * invstd[c] * (dy[i] - dbeta[c] * inv_r - xhat * dgamma[c] * inv_r);
-}
-// xhat-weighted sum needs xhat: dgamma[c] = sum dy * (x - mean) * invstd -> computed as colsum(dy * xhat) via this map
-__global__ void bn_xhat_mul_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
-                                   const float* __restrict__ invstd, float* __restrict__ out, long long rows, int C) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * C) return;
-  const int c = (int)(i % C);
-  out[i] = dy[i] * (x[i] - mean[c]) * invstd[c];
 }
 
 // LayerNorm over the channel axis (C <= 1024), one warp per pixel; saves mean and invstd per pixel.
@@ -608,6 +622,62 @@ __global__ void upsample2x_bwd_kernel(const float* __restrict__ dy, float* __res
   dx[i] = acc;
 }
 
+// float4 versions (C % 4 == 0): one thread per (output pixel, 4 channels), 32-bit index math
+__global__ void upsample2x_fwd_v4_kernel(const float4* __restrict__ x, float4* __restrict__ y, int n_img, int h, int w, int C4) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = (unsigned)n_img * 4u * h * w * C4;
+  if (i >= total) return;
+  const int c = i % C4;
+  const unsigned pix = i / C4;
+  const int X = pix % (2 * w), Y = (pix / (2 * w)) % (2 * h);
+  const int n = pix / (4u * w * h);
+  int ya, yb, xa, xb; float wy, wx;
+  up_taps(Y, h, ya, yb, wy); up_taps(X, w, xa, xb, wx);
+  const float4* p = x + (long long)n * h * w * C4 + c;
+  const float4 aa = __ldg(p + (ya * w + xa) * C4), ab = __ldg(p + (ya * w + xb) * C4);
+  const float4 ba = __ldg(p + (yb * w + xa) * C4), bb = __ldg(p + (yb * w + xb) * C4);
+  float4 o;
+  o.x = wy * (wx * aa.x + (1.f - wx) * ab.x) + (1.f - wy) * (wx * ba.x + (1.f - wx) * bb.x);
+  o.y = wy * (wx * aa.y + (1.f - wx) * ab.y) + (1.f - wy) * (wx * ba.y + (1.f - wx) * bb.y);
+  o.z = wy * (wx * aa.z + (1.f - wx) * ab.z) + (1.f - wy) * (wx * ba.z + (1.f - wx) * bb.z);
+  o.w = wy * (wx * aa.w + (1.f - wx) * ab.w) + (1.f - wy) * (wx * ba.w + (1.f - wx) * bb.w);
+    y[i] = o;
+}
+// adjoint per axis: dx[k] = .25 dy[2k-1] (k >= 1) + (.75 + .25 [k == 0]) dy[2k] + (.75 + .25 [k == n-1]) dy[2k+1] + .25 dy[2k+2] (k <= n-2)
+__device__ __forceinline__ void up_adj_taps(int k, int n, float (&wt)[4]) {
+  wt[0] = k >= 1 ? 0.25f : 0.f;
+  wt[1] = k == 0 ? 1.f : 0.75f;
+  wt[2] = k == n - 1 ? 1.f : 0.75f;
+  wt[3] = k <= n - 2 ? 0.25f : 0.f;
+}
+__global__ void upsample2x_bwd_v4_kernel(const float4* __restrict__ dy, float4* __restrict__ dx, int n_img, int h, int w, int C4) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = (unsigned)n_img * h * w * C4;
+  if (i >= total) return;
+  const int c = i % C4;
+  const unsigned pix = i / C4;
+  const int kx = pix % w, ky = (pix / w) % h;
+  const int n = pix / ((unsigned)w * h);
+  const float4* p = dy + (long long)n * 4 * h * w * C4 + c;
+  float wy[4], wx[4];
+  up_adj_taps(ky, h, wy); up_adj_taps(kx, w, wx);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    if (wy[a] == 0.f) continue;
+    const int Y = 2 * ky - 1 + a;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (wx[b] == 0.f) continue;
+      const int X = 2 * kx - 1 + b;
+      const float4 v = __ldg(p + (Y * 2 * w + X) * C4);
+      const float cw = wy[a] * wx[b];
+      acc.x += cw * v.x; acc.y += cw * v.y; acc.z += cw * v.z; acc.w += cw * v.w;
+    }
+  }
+  dx[i] = acc;
+}
+
 // ------------------------------------------------------------------ Dense(1) + temporal mean, and their backward
 // score[b] = mean_t (flat[b,t,:] . w + bias)
 __global__ void dense_mean_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ w, const float* __restrict__ bias,
@@ -686,44 +756,69 @@ __global__ void adam_kernel(float* __restrict__ w, float* __restrict__ m, float*
   w[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
 // One power iteration of TFA SpectralNormalization on W = reshape(w, (R, C)):  v = l2n(u W^T); u' = l2n(v W);
-// sigma = v W u'^T; w /= sigma; u = u'.  Single block (R*C <= a few million; training-time only).
-__global__ void sn_update_kernel(float* __restrict__ w, float* __restrict__ u, float* __restrict__ vbuf, int R, int C) {
-  __shared__ float red[256];
-  __shared__ float scal;
-  const int tid = threadIdx.x;
-  // v_raw[r] = sum_c u[c] W[r][c]
-  float nv = 0.f;
-  for (int r = tid; r < R; r += blockDim.x) {
-    float s = 0.f;
-    for (int c = 0; c < C; ++c) s += u[c] * w[(long long)r * C + c];
-    vbuf[r] = s;
-    nv += s * s;
+// sigma = v W u'^T; w /= sigma; u = u'.  Four small grid-wide kernels, every reduction in a fixed order
+// (deterministic, so data-parallel replicas stay bit-identical).  scratch: R + SN_SLABS*C + 4 floats.
+constexpr int SN_SLABS = 64;
+// v_raw[r] = sum_c u[c] W[r][c]: one warp per row
+__global__ void sn_rowdot_kernel(const float* __restrict__ w, const float* __restrict__ u, float* __restrict__ vbuf, int R, int C) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += u[c] * w[(long long)r * C + c];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) vbuf[r] = s;
+}
+// part[slab][c] = sum_{r in slab} v_raw[r] W[r][c]   (32 channels x 8 row lanes per block)
+__global__ void sn_coldot_kernel(const float* __restrict__ w, const float* __restrict__ vbuf, float* __restrict__ part, int R, int C) {
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int rows_per = (R + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  float s = 0.f;
+  if (c < C)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) s += vbuf[r] * w[(long long)r * C + c];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    part[(long long)blockIdx.y * C + c] = t;
   }
+}
+// single block: |v_raw|, u2_raw = (sum of slabs) / |v_raw|, |u2_raw|, u = l2n(u2_raw), scal[0] = 1 / sigma
+__global__ void sn_finish_kernel(const float* __restrict__ vbuf, const float* __restrict__ part, float* __restrict__ u,
+                                 float* __restrict__ scal, int R, int C, int slabs) {
+  __shared__ float red[256];
+  __shared__ float bc;
+  const int tid = threadIdx.x;
+  float nv = 0.f;
+  for (int r = tid; r < R; r += 256) nv += vbuf[r] * vbuf[r];
   red[tid] = nv; __syncthreads();
   for (int o = 128; o; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
-  if (tid == 0) scal = rsqrtf(fmaxf(red[0], 1e-12f));
+  if (tid == 0) bc = rsqrtf(fmaxf(red[0], 1e-12f));
   __syncthreads();
-  const float inv_nv = scal;
+  const float inv_nv = bc;
   __syncthreads();
-  // u2_raw[c] = sum_r v[r] W[r][c]
   float nu = 0.f;
-  for (int c = tid; c < C; c += blockDim.x) {
+  for (int c = tid; c < C; c += 256) {
     float s = 0.f;
-    for (int r = 0; r < R; ++r) s += vbuf[r] * inv_nv * w[(long long)r * C + c];
-    u[c] = s;          // raw; normalised below
+    for (int k = 0; k < slabs; ++k) s += part[(long long)k * C + c];
+    s *= inv_nv;
+    u[c] = s;
     nu += s * s;
   }
   red[tid] = nu; __syncthreads();
   for (int o = 128; o; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
-  if (tid == 0) scal = rsqrtf(fmaxf(red[0], 1e-12f));
-  __syncthreads();
-  const float inv_nu = scal;
-  // sigma = v W u'^T = sum_c u2_raw[c] * u'[c] = sum_c u2_raw[c]^2 * inv_nu = |u2_raw| (when not clamped)
+  const float inv_nu = rsqrtf(fmaxf(red[0], 1e-12f));
+  // sigma = v W u'^T = sum_c u2_raw[c] u'[c] = |u2_raw|^2 * inv_nu
   const float sigma = red[0] * inv_nu;
-  __syncthreads();
-  for (int c = tid; c < C; c += blockDim.x) u[c] *= inv_nu;
-  const float inv_sigma = 1.f / sigma;
-  for (long long i = tid; i < (long long)R * C; i += blockDim.x) w[i] *= inv_sigma;
+  for (int c = tid; c < C; c += 256) u[c] *= inv_nu;
+  if (tid == 0) scal[0] = 1.f / sigma;
+}
+__global__ void sn_scale_kernel(float* __restrict__ w, const float* __restrict__ scal, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) w[i] *= scal[0];
 }
 
 __global__ void rsqrt_eps_kernel(const float* __restrict__ v, float* __restrict__ o, int C, float eps) {
@@ -825,22 +920,34 @@ extern "C" int wdg_conv2d_bwd_weight(const float* x, const float* dy, float* dw,
   return 0;
 }
 
-// column sums: mode 0 sum a, 1 sum a*b, 2 sum a*a over R rows; out[C]; scratch >= 64*C floats
-extern "C" int wdg_colsum(int mode, const float* a, int a_cs, int a_co, const float* b, int b_cs, int b_co, long long R, int C,
-                          float* out, void* scratch, int accumulate, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  int slabs = (int)((R + 2047) / 2048);
-  if (slabs > 64) slabs = 64;
+// Two column sums in one pass (modes 3 / 4 of colsum_partial_kernel); scratch >= 2*CS_SLABS*C floats.
+static int colsum_dual(int mode, const float* a, int a_cs, int a_co, const float* b, int b_cs, int b_co, const float* mean,
+                       const float* invstd, long long R, int C, float* out1, float* out2, void* scratch, int accumulate,
+                       cudaStream_t stream) {
+  long long slabs = (R + 255) / 256;
+  if (slabs > CS_SLABS) slabs = CS_SLABS;
   if (slabs < 1) slabs = 1;
-  dim3 grid((C + 31) / 32, slabs), block(32, 8);
+  dim3 grid((C + 31) / 32, (unsigned)slabs), block(32, 8);
   float* part = (float*)scratch;
-  if (mode == 0) colsum_partial_kernel<0><<<grid, block, 0, stream>>>(a, a_cs, a_co, b, b_cs, b_co, R, C, part);
-  else if (mode == 1) colsum_partial_kernel<1><<<grid, block, 0, stream>>>(a, a_cs, a_co, b, b_cs, b_co, R, C, part);
-  else colsum_partial_kernel<2><<<grid, block, 0, stream>>>(a, a_cs, a_co, b, b_cs, b_co, R, C, part);
+  switch (mode) {
+    case 0: colsum_partial_kernel<0><<<grid, block, 0, stream>>>(a, a_cs, a_co, b, b_cs, b_co, mean, invstd, R, C, part); break;
+    case 1: colsum_partial_kernel<1><<<grid, block, 0, stream>>>(a, a_cs, a_co, b, b_cs, b_co, mean, invstd, R, C, part); break;
+    case 2: colsum_partial_kernel<2><<<grid, block, 0, stream>>>(a, a_cs, a_co, b, b_cs, b_co, mean, invstd, R, C, part); break;
+    case 3: colsum_partial_kernel<3><<<grid, block, 0, stream>>>(a, a_cs, a_co, b, b_cs, b_co, mean, invstd, R, C, part); break;
+    default: colsum_partial_kernel<4><<<grid, block, 0, stream>>>(a, a_cs, a_co, b, b_cs, b_co, mean, invstd, R, C, part); break;
+  }
   CKT(cudaGetLastError());
-  reduce_splits_kernel<<<blocks_for(C), 256, 0, stream>>>(part, out, C, slabs, accumulate);
+  reduce_splits_kernel<<<blocks_for(C), 256, 0, stream>>>(part, out1, C, (int)slabs, accumulate, 2ll * C);
+  if (out2) reduce_splits_kernel<<<blocks_for(C), 256, 0, stream>>>(part + C, out2, C, (int)slabs, accumulate, 2ll * C);
   CKT(cudaGetLastError());
   return 0;
+}
+// column sums: mode 0 sum a, 1 sum a*b, 2 sum a*a over R rows; out[C]; scratch >= 512*C floats
+extern "C" int wdg_colsum(int mode, const float* a, int a_cs, int a_co, const float* b, int b_cs, int b_co, long long R, int C,
+                          float* out, void* scratch, int accumulate, void* stream_) {
+  if (mode < 0 || mode > 2) return wdg_set_error("wdg_colsum: mode must be 0, 1 or 2");
+  return colsum_dual(mode, a, a_cs, a_co, b, b_cs, b_co, nullptr, nullptr, R, C, out, nullptr, scratch, accumulate,
+                     (cudaStream_t)stream_);
 }
 
 extern "C" int wdg_leaky_relu_fwd(float* x, long long n, float alpha, void* stream) {
@@ -878,15 +985,14 @@ extern "C" int wdg_lerp_batch(float* out, const float* real, const float* fake, 
 }
 
 // BatchNorm, training mode: batch statistics (biased variance), moving statistics updated in place.
-// scratch >= (64*C + 2*C) floats.  Saves mean / invstd ([C] each) for the backward.
+// scratch >= (512*C + 2*C) floats.  Saves mean / invstd ([C] each) for the backward.
 extern "C" int wdg_bn_train_fwd(const float* x, float* y, const float* gamma, const float* beta, float* moving_mean,
                                 float* moving_var, float* save_mean, float* save_invstd, long long rows, int C, float eps,
                                 float momentum, void* scratch, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  float* s1 = (float*)scratch + 64 * (size_t)C;
+  float* s1 = (float*)scratch + 2 * CS_SLABS * (size_t)C;
   float* s2 = s1 + C;
-  if (wdg_colsum(0, x, C, 0, nullptr, 0, 0, rows, C, s1, scratch, 0, stream_)) return 1;
-  if (wdg_colsum(2, x, C, 0, nullptr, 0, 0, rows, C, s2, scratch, 0, stream_)) return 1;
+  if (colsum_dual(3, x, C, 0, nullptr, 0, 0, nullptr, nullptr, rows, C, s1, s2, scratch, 0, stream)) return 1;
   bn_finalize_kernel<<<blocks_for(C), 256, 0, stream>>>(s1, s2, rows, C, eps, momentum, save_mean, save_invstd, moving_mean, moving_var);
   CKT(cudaGetLastError());
   bn_apply_kernel<<<blocks_for(rows * C), 256, 0, stream>>>(x, y, save_mean, save_invstd, gamma, beta, rows, C);
@@ -910,12 +1016,7 @@ extern "C" int wdg_bn_finalize_apply(const float* x, float* y, const float* gamm
 extern "C" int wdg_bn_bwd_sums(const float* dy, const float* x, const float* save_mean, const float* save_invstd, float* dgamma,
                                float* dbeta, long long rows, int C, void* scratch, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  float* tmp = (float*)scratch;
-  float* part = tmp + rows * C;
-  bn_xhat_mul_kernel<<<blocks_for(rows * C), 256, 0, stream>>>(dy, x, save_mean, save_invstd, tmp, rows, C);
-  CKT(cudaGetLastError());
-  if (wdg_colsum(0, tmp, C, 0, nullptr, 0, 0, rows, C, dgamma, part, 0, stream_)) return 1;
-  if (wdg_colsum(0, dy, C, 0, nullptr, 0, 0, rows, C, dbeta, part, 0, stream_)) return 1;
+  if (colsum_dual(4, dy, C, 0, x, C, 0, save_mean, save_invstd, rows, C, dgamma, dbeta, scratch, 0, stream)) return 1;
   return 0;
 }
 extern "C" int wdg_bn_bwd_dx(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
@@ -938,17 +1039,12 @@ extern "C" int wdg_bn_infer(const float* x, float* y, const float* gamma, const 
   CKT(cudaGetLastError());
   return 0;
 }
-// dgamma, dbeta ([C]) and dx.  scratch >= rows*C + 64*C floats.
+// dgamma, dbeta ([C]) and dx.  scratch >= 512*C floats.
 extern "C" int wdg_bn_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean,
                                 const float* save_invstd, float* dx, float* dgamma, float* dbeta, long long rows, int C,
                                 void* scratch, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  float* tmp = (float*)scratch;
-  float* part = tmp + rows * C;
-  bn_xhat_mul_kernel<<<blocks_for(rows * C), 256, 0, stream>>>(dy, x, save_mean, save_invstd, tmp, rows, C);
-  CKT(cudaGetLastError());
-  if (wdg_colsum(0, tmp, C, 0, nullptr, 0, 0, rows, C, dgamma, part, 0, stream_)) return 1;
-  if (wdg_colsum(0, dy, C, 0, nullptr, 0, 0, rows, C, dbeta, part, 0, stream_)) return 1;
+  if (colsum_dual(4, dy, C, 0, x, C, 0, save_mean, save_invstd, rows, C, dgamma, dbeta, scratch, 0, stream)) return 1;
   bn_bwd_kernel<<<blocks_for(rows * C), 256, 0, stream>>>(dy, x, save_mean, save_invstd, gamma, dbeta, dgamma, dx, rows, C, rows);
   CKT(cudaGetLastError());
   return 0;
@@ -960,7 +1056,7 @@ extern "C" int wdg_ln_fwd(const float* x, float* y, int y_cs, int y_co, const fl
   CKT(cudaGetLastError());
   return 0;
 }
-// dx, dgamma, dbeta.  scratch >= rows*C + 64*C floats.
+// dx, dgamma, dbeta.  scratch >= rows*C + 512*C floats.
 extern "C" int wdg_ln_bwd(const float* dy, int dy_cs, int dy_co, const float* x, const float* gamma, const float* save_mean,
                           const float* save_invstd, float* dx, float* dgamma, float* dbeta, long long rows, int C,
                           void* scratch, void* stream_) {
@@ -987,12 +1083,20 @@ extern "C" int wdg_lstm_gates_bwd(float* gates, const float* c_prev, const float
 }
 
 extern "C" int wdg_upsample2x_fwd(const float* x, float* y, long long n_img, int h, int w, int C, void* stream) {
-  upsample2x_fwd_kernel<<<blocks_for(n_img * 4 * h * w * C), 256, 0, (cudaStream_t)stream>>>(x, y, n_img, h, w, C);
+  if (C % 4 == 0 && n_img * 4 * h * w * (C / 4) < (1ll << 31) && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0)
+    upsample2x_fwd_v4_kernel<<<blocks_for(n_img * 4 * h * w * (C / 4)), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)x, (float4*)y, (int)n_img, h, w, C / 4);
+  else
+    upsample2x_fwd_kernel<<<blocks_for(n_img * 4 * h * w * C), 256, 0, (cudaStream_t)stream>>>(x, y, n_img, h, w, C);
   CKT(cudaGetLastError());
   return 0;
 }
 extern "C" int wdg_upsample2x_bwd(const float* dy, float* dx, long long n_img, int h, int w, int C, void* stream) {
-  upsample2x_bwd_kernel<<<blocks_for(n_img * h * w * C), 256, 0, (cudaStream_t)stream>>>(dy, dx, n_img, h, w, C);
+  if (C % 4 == 0 && n_img * 4 * h * w * (C / 4) < (1ll << 31) && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)dy & 15) == 0)
+    upsample2x_bwd_v4_kernel<<<blocks_for(n_img * h * w * (C / 4)), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)dy, (float4*)dx, (int)n_img, h, w, C / 4);
+  else
+    upsample2x_bwd_kernel<<<blocks_for(n_img * h * w * C), 256, 0, (cudaStream_t)stream>>>(dy, dx, n_img, h, w, C);
   CKT(cudaGetLastError());
   return 0;
 }
@@ -1043,8 +1147,17 @@ extern "C" int wdg_adam(float* w, float* m, float* v, const float* g, long long 
   CKT(cudaGetLastError());
   return 0;
 }
-extern "C" int wdg_sn_update(float* w, float* u, int R, int C, void* scratch /* >= R floats */, void* stream) {
-  sn_update_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(w, u, (float*)scratch, R, C);
+extern "C" int wdg_sn_update(float* w, float* u, int R, int C, void* scratch /* >= R + 64*C + 4 floats */, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float* vbuf = (float*)scratch;
+  float* part = vbuf + R;
+  float* scal = part + (long long)SN_SLABS * C;
+  int slabs = (R + 31) / 32;
+  if (slabs > SN_SLABS) slabs = SN_SLABS;
+  sn_rowdot_kernel<<<(R + 7) / 8, 256, 0, stream>>>(w, u, vbuf, R, C);
+  sn_coldot_kernel<<<dim3((C + 31) / 32, slabs), dim3(32, 8), 0, stream>>>(w, vbuf, part, R, C);
+  sn_finish_kernel<<<1, 256, 0, stream>>>(vbuf, part, u, scal, R, C, slabs);
+  sn_scale_kernel<<<blocks_for((long long)R * C), 256, 0, stream>>>(w, scal, (long long)R * C);
   CKT(cudaGetLastError());
   return 0;
 }

@@ -160,12 +160,11 @@ class ConvLSTM:
         hs = ops.empty(T, B, H, W, F)
         cs = ops.empty(T, B, H, W, F)
         gates = ops.empty(T, B, H, W, 4 * F)
+        # the input convolution (+ bias) of every timestep is one GEMM; only the recurrent convolution is serial
+        ops.conv2d_fwd(full(xt.view(T * B, H, W, Cin)), self.K, self.b, full(gates.view(T * B, H, W, 4 * F)), T * B, H, W, 1, 1, H, W)
         for t in range(T):
-            z = full(gates[t])
-            ops.conv2d_fwd(full(xt[t]), self.K, None, z, B, H, W, 1, 1, H, W)
             if t > 0:
-                ops.conv2d_fwd(full(hs[t - 1]), self.R, None, z, B, H, W, 1, 1, H, W, accumulate=True)
-            ops.bias_act(z, self.b, 1.0)
+                ops.conv2d_fwd(full(hs[t - 1]), self.R, None, full(gates[t]), B, H, W, 1, 1, H, W, accumulate=True)
             ops.lstm_gates_fwd(gates[t], cs[t - 1] if t > 0 else None, cs[t], hs[t])
         self.ctx = (xt, hs, cs, gates, B, T, H, W, Cin, F)
         return ops.transpose01(hs).view(B * T, H, W, F)
@@ -174,25 +173,31 @@ class ConvLSTM:
         """dh_seq: [B*T, H, W, F] batch-major.  Returns (dx batch-major or None, dK, dR, db)."""
         xt, hs, cs, gates, B, T, H, W, Cin, F = self.ctx
         dhs = ops.transpose01(dh_seq.view(B, T, H, W, F))        # [T, B, ...]
-        dK, dR, db = torch.zeros_like(self.K), torch.zeros_like(self.R), torch.zeros_like(self.b)
+        dK = dR = db = None
         dc = ops.zeros(B, H, W, F)
         dh_rec = ops.zeros(B, H, W, F)
-        dxt = ops.empty(T, B, H, W, Cin) if need_dx else None
-        for t in range(T - 1, -1, -1):
+        for t in range(T - 1, -1, -1):            # serial part: gate backward and the recurrent backward-data
             dh = dhs[t]
             if t < T - 1:
                 ops.axpby(full(dh), full(dh), 1.0, full(dh_rec), 1.0)
-            ops.lstm_gates_bwd(gates[t], cs[t - 1] if t > 0 else None, cs[t], dh, dc)   # gates[t] now holds dz
-            dz = full(gates[t])
-            if need_dw:
-                ops.conv2d_bwd_weight(full(xt[t]), dz, dK, B, H, W, 1, 1, H, W, accumulate=True)
-                ops.colsum(dz, db, accumulate=True)
-            if need_dx:
-                ops.conv2d_bwd_data(dz, self.K, full(dxt[t]), B, H, W, 1, 1, H, W)
+            ops.lstm_gates_bwd(gates[t], cs[t - 1] if t > 0 else None, cs[t], dh, dc)   # gates[t] now holds dz_t
             if t > 0:
-                if need_dw:
-                    ops.conv2d_bwd_weight(full(hs[t - 1]), dz, dR, B, H, W, 1, 1, H, W, accumulate=True)
-                ops.conv2d_bwd_data(dz, self.R, full(dh_rec), B, H, W, 1, 1, H, W)
+                ops.conv2d_bwd_data(full(gates[t]), self.R, full(dh_rec), B, H, W, 1, 1, H, W)
+        # everything that only needs all dz_t: one GEMM each over the T*B images
+        dz_all = full(gates.view(T * B, H, W, 4 * F))
+        if need_dw:
+            dK, dR, db = torch.empty_like(self.K), torch.empty_like(self.R), torch.empty_like(self.b)
+            ops.conv2d_bwd_weight(full(xt.view(T * B, H, W, Cin)), dz_all, dK, T * B, H, W, 1, 1, H, W)
+            if T > 1:
+                ops.conv2d_bwd_weight(full(hs[:T - 1].view((T - 1) * B, H, W, F)), full(gates[1:].view((T - 1) * B, H, W, 4 * F)),
+                                      dR, (T - 1) * B, H, W, 1, 1, H, W)
+            else:
+                dR.zero_()
+            ops.colsum(dz_all, db)
+        dxt = None
+        if need_dx:
+            dxt = ops.empty(T, B, H, W, Cin)
+            ops.conv2d_bwd_data(dz_all, self.K, full(dxt.view(T * B, H, W, Cin)), T * B, H, W, 1, 1, H, W)
         dx = ops.transpose01(dxt).view(B * T, H, W, Cin) if need_dx else None
         return dx, dK, dR, db
 
