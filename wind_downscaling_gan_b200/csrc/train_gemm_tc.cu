@@ -1,20 +1,27 @@
 // Training convolutions on the 5th-generation tensor cores (critic and training-mode
 // generator forward / backward-data / backward-weight).
 //
-// One kernel template, `tc_gemm_kernel<P, BN, OP>`: C[128 x BN] tiles of an implicit GEMM whose operands are
-// GATHERED by 8 loader warps straight from the fp32 channels-last activations / weights (no im2col buffer, no
-// packed copies), rounded to bf16 or tf32 in registers and written into shared memory in the canonical K-major
-// SWIZZLE_128B UMMA layout (one 16-byte chunk = 8 bf16 / 4 tf32 per st.shared.v4); a ninth warp issues
-// `tcgen05.mma` (kind::f16 or kind::tf32) with the fp32 accumulator in TMEM; after the K loop the loader warps
-// read the accumulator back (`tcgen05.ld`) and run the problem's epilogue (bias / accumulate / strided channel
-// views / split-K partials).  Two CTAs are co-resident per SM so one tile's epilogue overlaps the other's gathers.
+// One kernel template, `tc_gemm_kernel<P, BN, OP>`: C[128 x BN] tiles of an implicit GEMM.  The A operand (and, for
+// backward-weight, B) is GATHERED by 8 loader warps straight from the fp32 channels-last activations (no im2col
+// buffer), rounded to bf16 or tf32 in registers and written into shared memory in the canonical K-major
+// SWIZZLE_128B UMMA layout (one 16-byte chunk = 8 bf16 / 4 tf32 per st.shared.v4).  For forward / backward-data the B
+// operand is the weight matrix: a small pre-pass rounds and packs it K-major ([N][K]) into a library arena and a
+// producer warp streams its tiles with TMA (cp.async.bulk.tensor, SWIZZLE_128B), so the loader warps make ONE global
+// round trip per K block.  A ninth warp issues `tcgen05.mma` (kind::f16 or kind::tf32) with the fp32 accumulator in
+// TMEM; after the K loop the loader warps read the accumulator back (`tcgen05.ld`) and run the problem's epilogue
+// (bias / accumulate / strided channel views / split-K partials).  Two CTAs are co-resident per SM so one tile's
+// epilogue overlaps the other's gathers.
 //
 // The three problems are the same ones train_ops.cu defines for the CUDA-core path:
 //   forward        C[m = (n,oy,ox)][co]      = sum_{k=(ky,kx,ci)} x[n, oy*s-p+ky, ox*s-p+kx, ci] * w[k][co]
 //   backward-data  C[m = (n,a,b) in class][ci] = sum_{k=(jy,jx,co)} dy[n, ay-jy, ax-jx, co] * w[ry+s*jy][rx+s*jx][ci][co]
 //                  (one residue class of the stride at a time: no structural zeros; stride 1 is the single class)
 //   backward-weight C[m = (ky,kx,ci)][co]    = sum_{k=(n,oy,ox)} x[n, oy*s-p+ky, ox*s-p+kx, ci] * dy[k][co]   (split-K)
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <string.h>
+
+#include <type_traits>
 
 #include "../../include/wdg.h"
 #include "ptx.cuh"
@@ -26,7 +33,7 @@ using namespace wdg;
 constexpr int OP_TF32 = 1, OP_BF16 = 2;
 template <int OP> struct OpT { static constexpr int G = (OP == OP_BF16) ? 8 : 4; };   // elements per 16-byte chunk
 constexpr int LOADER_THREADS = 256;
-constexpr int TC_THREADS = LOADER_THREADS + 32;
+constexpr int TC_THREADS = LOADER_THREADS + 64;   // + MMA warp + TMA producer warp
 constexpr int TILE_M = 128;
 constexpr uint32_t A_STAGE_BYTES = TILE_M * 128;
 
@@ -177,6 +184,10 @@ struct LinearRowFastB {
     k += 8 * G;
     q += 8 * G * ld;
   }
+  __device__ __forceinline__ void load_skip() {
+    k += 8 * G;
+    q += 8 * G * ld;
+  }
 };
 
 // ------------------------------------------------------------------------------------------------ problems
@@ -186,9 +197,11 @@ struct TcFwd {
   __device__ int Nn() const { return g.Co; }
   __device__ long long K() const { return (long long)g.kh * g.kw * g.Ci; }
 
+  static constexpr bool TMA_B = true;
+  __device__ float B(long long k, int n) const { return w[k * g.Co + n]; }
   template <int OP, int BN>
   struct Loaders {
-    TapGatherA<OP> a; LinearRowFastB<OP, BN> b; TapK k;
+    TapGatherA<OP> a; TapK k;
     __device__ Loaders(const TcFwd& p, long long m0, int n0, long long k_begin, long long k_end, int tid) {
       const ConvGeo& g = p.g;
       a.s = GatherSrc{g.x_cs, g.Ci, g.kw, g.kh, +1, g.H, g.W, p.vec_in};
@@ -202,11 +215,9 @@ struct TcFwd {
         a.set_row(i, valid, p.x + g.x_co + (long long)n * g.H * g.W * g.x_cs, oy * g.stride - g.pad_t, ox * g.stride - g.pad_l);
       }
       k.init(k_begin + (tid & 7) * OpT<OP>::G, g.Ci, g.kw);
-      b.init(p.w, g.Co, n0, g.Co, k_begin, k_end, tid);
     }
-    __device__ __forceinline__ void load(uint32_t a_tile, uint32_t b_tile, int tid) {
+    __device__ __forceinline__ void load(uint32_t a_tile, uint32_t, int tid) {
       a.load(a_tile, tid, k);
-      b.load(b_tile);
       k.advance(8 * OpT<OP>::G, a.s.C, a.s.ntx);
     }
   };
@@ -240,13 +251,17 @@ struct TcBwdData {
   __device__ int Nn() const { return g.Ci; }
   __device__ long long K() const { return (long long)c.Jy * c.Jx * g.Co; }
 
+  static constexpr bool TMA_B = true;
+  // B(k = (jy, jx, co), n = ci) = w[((ry + s jy) * kw + rx + s jx) * Ci + ci][co]
+  __device__ float B(long long k, int n) const {
+    const int co = (int)(k % g.Co), t = (int)(k / g.Co), jx = t % c.Jx, jy = t / c.Jx;
+    return w[(((long long)(c.ry + g.stride * jy) * g.kw + c.rx + g.stride * jx) * g.Ci + n) * g.Co + co];
+  }
   template <int OP, int BN>
   struct Loaders {
     static constexpr int G = OpT<OP>::G;
-    static constexpr int RB = BN >= 32 ? BN / 32 : 1;   // B rows per thread: n = (tid >> 3) + 32 i
     TapGatherA<OP> a; TapK k;
-    const float* w; int Ci, Co, kw, s, ry, rx, Jy, n0, vec_w;
-    __device__ Loaders(const TcBwdData& p, long long m0, int n0_, long long k_begin, long long, int tid) {
+    __device__ Loaders(const TcBwdData& p, long long m0, int, long long k_begin, long long, int tid) {
       const ConvGeo& g = p.g;
       a.s = GatherSrc{g.y_cs, g.Co, p.c.Jx, p.c.Jy, -1, g.Ho, g.Wo, p.vec_in};
       const long long M = p.M();
@@ -261,55 +276,9 @@ struct TcBwdData {
         a.set_row(i, valid, p.dy + g.y_co + (long long)n * g.Ho * g.Wo * g.y_cs, ay, ax);
       }
       k.init(k_begin + (tid & 7) * G, g.Co, p.c.Jx);
-      w = p.w; Ci = g.Ci; Co = g.Co; kw = g.kw; s = g.stride; ry = p.c.ry; rx = p.c.rx; Jy = p.c.Jy; n0 = n0_; vec_w = p.vec_w;
     }
-    // B(k = (jy, jx, co), n = ci) = w[((ry + s jy) * kw + rx + s jx) * Ci + ci][co]: co contiguous -> K-fastest
-    __device__ __forceinline__ void load_b(uint32_t tile, int tid) const {
-      const int j = tid & 7, r0 = tid >> 3;
-      if (BN < 32 && r0 >= BN) return;
-#pragma unroll 1
-      for (int i0 = 0; i0 < RB; i0 += 4) {
-        constexpr int NB = RB < 4 ? RB : 4;
-        float v[NB][G];
-        if (vec_w && k.c + G <= Co) {
-          const bool kin = k.ty < Jy;
-          const long long off = ((long long)((ry + s * k.ty) * kw + rx + s * k.tx) * Ci) * Co + k.c;
-#pragma unroll
-          for (int i = 0; i < NB; ++i) {
-            const int n = n0 + r0 + 32 * (i0 + i);
-            if (kin && n < Ci) {
-              const float4* q = reinterpret_cast<const float4*>(w + off + (long long)n * Co);
-#pragma unroll
-              for (int h = 0; h < G / 4; ++h) {
-                const float4 t = __ldg(q + h);
-                v[i][4 * h] = t.x; v[i][4 * h + 1] = t.y; v[i][4 * h + 2] = t.z; v[i][4 * h + 3] = t.w;
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < G; ++e) v[i][e] = 0.f;
-            }
-          }
-        } else {
-          TapK t = k;
-#pragma unroll
-          for (int e = 0; e < G; ++e) {
-            const bool kin = t.ty < Jy;
-            const long long off = ((long long)((ry + s * t.ty) * kw + rx + s * t.tx) * Ci) * Co + t.c;
-#pragma unroll
-            for (int i = 0; i < NB; ++i) {
-              const int n = n0 + r0 + 32 * (i0 + i);
-              v[i][e] = (kin && n < Ci) ? __ldg(w + off + (long long)n * Co) : 0.f;
-            }
-            t.advance(1, Co, a.s.ntx);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < NB; ++i) store_chunk<OP>(tile, r0 + 32 * (i0 + i), j, v[i]);
-      }
-    }
-    __device__ __forceinline__ void load(uint32_t a_tile, uint32_t b_tile, int tid) {
+    __device__ __forceinline__ void load(uint32_t a_tile, uint32_t, int tid) {
       a.load(a_tile, tid, k);
-      load_b(b_tile, tid);
       k.advance(8 * G, a.s.C, a.s.ntx);
     }
   };
@@ -335,26 +304,35 @@ struct TcBwdData {
 };
 
 struct TcWgrad {
-  ConvGeo g; const float* x; const float* dy; float* part; long long k_per_split;
+  ConvGeo g; const float* x; const float* dy; float* part; long long k_per_split; int vec_a, vec_b;
   __device__ long long M() const { return (long long)g.kh * g.kw * g.Ci; }
   __device__ int Nn() const { return g.Co; }
   __device__ long long K() const { return (long long)g.N * g.Ho * g.Wo; }
+  static constexpr bool TMA_B = false;
 
+  // Both operands are contiguous along their ROW index in memory (A: ci, B: co) while a 16-byte smem chunk holds G
+  // consecutive k (pixels) of ONE row, so the loaders transpose in registers.  Vector form (channel counts and views
+  // multiples of 4): a thread loads float4 = 4 consecutive rows for each of the G pixels of its chunk and writes 4
+  // chunks (G LDG.128 per 4 chunks); scalar form: 4 G LDG.32 per 4 chunks, lanes walking the rows.
   template <int OP, int BN>
   struct Loaders {
     static constexpr int G = OpT<OP>::G;
-    static constexpr int RUN = 4 * G;      // consecutive k per thread and K block (4 chunks); the two thread halves interleave
+    static constexpr int KB = 8 * G;
+    static constexpr int RUN = 4 * G;      // scalar form: consecutive k per thread and K block (4 chunks); two thread halves interleave
     LinearRowFastB<OP, BN> b;
-    // A(m = (ky, kx, ci), k = (n, oy, ox)) = x[n, oy s - p + ky, ox s - p + kx, ci]: ci contiguous -> row-fastest
-    const float* col;   // x + x_co + ci
-    int ky, kx, row, half;
-    bool mv;
+    // A(m = (ky, kx, ci), k = (n, oy, ox)) = x[n, oy s - p + ky, ox s - p + kx, ci]
+    const float* col;   // x + x_co + ci of this thread's (first) row
+    const float* dyb;   // dy + y_co + n0
+    int ky, kx, row, chunk0;
+    bool mv, vecA, vecB;
     int ox, oy, n;
-    long long k, k_end;
-    int H, W, Ho, Wo, s, pad_t, pad_l, cs;
+    long long k, k_end, kb0;
+    int H, W, Ho, Wo, s, pad_t, pad_l, cs, y_cs, n_left;
     __device__ Loaders(const TcWgrad& p, long long m0, int n0, long long k_begin, long long k_end_, int tid) {
       const ConvGeo& g = p.g;
-      row = tid & 127; half = tid >> 7;
+      vecA = p.vec_a; vecB = p.vec_b;
+      if (vecA) { row = 4 * (tid >> 3); chunk0 = tid & 7; }
+      else { row = tid & 127; chunk0 = (tid >> 7) * 4; }
       const long long m = m0 + row;
       mv = m < p.M();
       const int mm = mv ? (int)m : 0;
@@ -362,30 +340,75 @@ struct TcWgrad {
       kx = tap % g.kw; ky = tap / g.kw;
       col = p.x + g.x_co + ci;
       H = g.H; W = g.W; Ho = g.Ho; Wo = g.Wo; s = g.stride; pad_t = g.pad_t; pad_l = g.pad_l; cs = g.x_cs;
-      k = k_begin + half * RUN; k_end = k_end_;
+      k = k_begin + chunk0 * G; k_end = k_end_; kb0 = k_begin;
       ox = (int)(k % Wo); oy = (int)((k / Wo) % Ho); n = (int)(k / ((long long)Wo * Ho));
       b.init(p.dy + g.y_co, g.y_cs, n0, g.Co, k_begin, k_end_, tid);
+      dyb = p.dy + g.y_co + n0; y_cs = g.y_cs; n_left = g.Co - n0;
     }
     __device__ __forceinline__ void advance(int d) {
       k += d; ox += d;
       while (ox >= Wo) { ox -= Wo; if (++oy == Ho) { oy = 0; ++n; } }
     }
-    __device__ __forceinline__ void load(uint32_t a_tile, uint32_t b_tile, int) {
-      float v[4][G];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
+    __device__ __forceinline__ void step() {
+      ++k;
+      if (++ox == Wo) { ox = 0; if (++oy == Ho) { oy = 0; ++n; } }
+    }
+    __device__ __forceinline__ void load(uint32_t a_tile, uint32_t b_tile, int tid) {
+      if (vecA) {
+        float4 t[G];
 #pragma unroll
         for (int e = 0; e < G; ++e) {
           const int iy = oy * s - pad_t + ky, ix = ox * s - pad_l + kx;
           const bool ok = mv && k < k_end && (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
-          v[c][e] = ok ? __ldg(col + (((long long)n * H + iy) * W + ix) * cs) : 0.f;
-          ++k;
-          if (++ox == Wo) { ox = 0; if (++oy == Ho) { oy = 0; ++n; } }
+          t[e] = ok ? __ldg(reinterpret_cast<const float4*>(col + (((long long)n * H + iy) * W + ix) * cs)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          step();
         }
+        float v[4][G];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) store_chunk<OP>(a_tile, row, half * 4 + c, v[c]);
-      advance(RUN);
-      b.load(b_tile);
+        for (int e = 0; e < G; ++e) { v[0][e] = t[e].x; v[1][e] = t[e].y; v[2][e] = t[e].z; v[3][e] = t[e].w; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) store_chunk<OP>(a_tile, row + i, chunk0, v[i]);
+        advance(KB - G);
+      } else {
+        float v[4][G];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < G; ++e) {
+            const int iy = oy * s - pad_t + ky, ix = ox * s - pad_l + kx;
+            const bool ok = mv && k < k_end && (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+            v[c][e] = ok ? __ldg(col + (((long long)n * H + iy) * W + ix) * cs) : 0.f;
+            step();
+          }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) store_chunk<OP>(a_tile, row, chunk0 + c, v[c]);
+        advance(RUN);
+      }
+      if (vecB) {
+        // B(k, n) = dy[k][n]: row groups of 4 consecutive n, chunk = tid & 7
+        const int j = tid & 7;
+        const long long kk = kb0 + j * G;
+#pragma unroll
+        for (int i = 0; i < (BN + 127) / 128; ++i) {
+          const int r4 = 4 * ((tid >> 3) + 32 * i);
+          if (r4 < BN) {
+            const bool nv = r4 < n_left;
+            float4 t[G];
+#pragma unroll
+            for (int e = 0; e < G; ++e)
+              t[e] = (nv && kk + e < k_end) ? __ldg(reinterpret_cast<const float4*>(dyb + (kk + e) * y_cs + r4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float v[4][G];
+#pragma unroll
+            for (int e = 0; e < G; ++e) { v[0][e] = t[e].x; v[1][e] = t[e].y; v[2][e] = t[e].z; v[3][e] = t[e].w; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) store_chunk<OP>(b_tile, r4 + q, j, v[q]);
+          }
+        }
+        b.load_skip();
+      } else {
+        b.load(b_tile);
+      }
+      kb0 += KB;
     }
   };
   __device__ __forceinline__ void store16(long long m, int n, const uint32_t (&r)[16], int split) const {
@@ -411,8 +434,34 @@ template <int BN> struct TcCfg {
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
+// Rounds B(k, n) to the operand type and packs it K-major: out[n][K_pad] (K_pad = K rounded up to whole K blocks, zero
+// filled).  N_FAST: consecutive threads walk n (forward weights: n contiguous in memory), else k.
+template <class P, int OP, bool N_FAST>
+__global__ void pack_b_kernel(const P p, void* __restrict__ out, int N, long long K, long long K_pad) {
+  constexpr int G = OpT<OP>::G;
+  const long long chunks = K_pad / G;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= chunks * N) return;
+  const int n = N_FAST ? (int)(i % N) : (int)(i / chunks);
+  const long long kc = N_FAST ? i / N : i % chunks;
+  float v[G];
+#pragma unroll
+  for (int e = 0; e < G; ++e) {
+    const long long k = kc * G + e;
+    v[e] = k < K ? p.B(k, n) : 0.f;
+  }
+  uint4 o;
+  if constexpr (OP == OP_BF16) {
+    o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  } else {
+    o = make_uint4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+  }
+  reinterpret_cast<uint4*>(out)[(long long)n * chunks + kc] = o;
+}
+
 template <class P, int BN, int OP>
-__global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const P p, int n_tiles_n, long long k_per_split) {
+__global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const P p, int n_tiles_n, long long k_per_split,
+                                                                const __grid_constant__ CUtensorMap tmB) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int KB = 8 * OpT<OP>::G;
@@ -425,9 +474,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const P p, int n
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], LOADER_THREADS); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], LOADER_THREADS + (P::TMA_B ? 1 : 0)); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_bar, 1);
     fence_mbar_init();
+    if (P::TMA_B) prefetch_tmap(&tmB);
   }
   if (warp == 8) tmem_alloc<Cfg::TMEM_COLS>(&tmem_slot);
   tc_fence_before();
@@ -481,6 +531,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const P p, int n
         if (mvalid && n0 + c0 < N) p.store16(m, n0 + c0, r, split);
       }
     }
+  } else if (warp == 9) {
+    // ===================================================== TMA producer of the packed B tiles
+    if (P::TMA_B) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::B_STAGE_BYTES);
+          tma_load_2d(smB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], (int)(k_begin + (long long)kb * KB), n0);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
   } else {
     // ===================================================== MMA issuer
     constexpr uint32_t idesc = (OP == OP_BF16) ? umma_idesc_bf16(TILE_M, BN) : umma_idesc_tf32(TILE_M, BN);
@@ -513,8 +578,38 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const P p, int n
   }
 }
 
+// ---- library arena for the packed B operands (weights): a 64 MB ring, allocated on first use.  Calls are ordered
+// by the single stream the training ops run on; a packed copy is only read by the GEMM launched right after it.
+constexpr size_t ARENA_BYTES = 64ull << 20;
+char* g_arena = nullptr;
+size_t g_arena_off = 0;
+void* arena_get(size_t bytes) {
+  if (!g_arena && cudaMalloc(&g_arena, ARENA_BYTES) != cudaSuccess) return nullptr;
+  bytes = (bytes + 1023) & ~(size_t)1023;
+  if (bytes > ARENA_BYTES) return nullptr;
+  if (g_arena_off + bytes > ARENA_BYTES) g_arena_off = 0;
+  void* p = g_arena + g_arena_off;
+  g_arena_off += bytes;
+  return p;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
 template <class P, int BN, int OP>
-cudaError_t launch_one(const P& p, long long M, int N, int splits, long long k_per_split, cudaStream_t stream) {
+cudaError_t launch_one(const P& p, long long M, int N, long long K, int splits, long long k_per_split, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<P, BN, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -522,10 +617,28 @@ cudaError_t launch_one(const P& p, long long M, int N, int splits, long long k_p
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof tm);
+  if constexpr (P::TMA_B) if (K > 0) {
+    constexpr int G = OpT<OP>::G, KB = 8 * G;
+    constexpr size_t ES = OP == OP_BF16 ? 2 : 4;
+    const long long K_pad = (K + KB - 1) / KB * KB;
+    void* packed = arena_get((size_t)N * K_pad * ES);
+    EncodeTiledFn enc = get_encode_fn();
+    if (!packed || !enc) return cudaErrorMemoryAllocation;
+    const long long items = (long long)N * (K_pad / G);
+    pack_b_kernel<P, OP, std::is_same<P, TcFwd>::value><<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(p, packed, N, K, K_pad);
+    cuuint64_t gdim[2] = {(cuuint64_t)K_pad, (cuuint64_t)N}, gstr[1] = {(cuuint64_t)K_pad * ES};
+    cuuint32_t gbox[2] = {(cuuint32_t)KB, (cuuint32_t)BN}, estr[2] = {1, 1};
+    if (enc(&tm, OP == OP_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, packed, gdim, gstr, gbox,
+            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
   const int ntn = (N + BN - 1) / BN;
   const long long ntm = (M + TILE_M - 1) / TILE_M;
   dim3 grid((unsigned)(ntm * ntn), (unsigned)splits);
-  tc_gemm_kernel<P, BN, OP><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, stream>>>(p, ntn, k_per_split);
+  tc_gemm_kernel<P, BN, OP><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, stream>>>(p, ntn, k_per_split, tm);
   return cudaGetLastError();
 }
 
@@ -538,18 +651,18 @@ int pick_bn(int N) {
 }
 
 template <class P, int OP>
-cudaError_t launch_bn(const P& p, long long M, int N, int splits, long long kps, cudaStream_t stream) {
+cudaError_t launch_bn(const P& p, long long M, int N, long long K, int splits, long long kps, cudaStream_t stream) {
   switch (pick_bn(N)) {
-    case 16: return launch_one<P, 16, OP>(p, M, N, splits, kps, stream);
-    case 32: return launch_one<P, 32, OP>(p, M, N, splits, kps, stream);
-    case 64: return launch_one<P, 64, OP>(p, M, N, splits, kps, stream);
-    case 128: return launch_one<P, 128, OP>(p, M, N, splits, kps, stream);
-    default: return launch_one<P, 256, OP>(p, M, N, splits, kps, stream);
+    case 16: return launch_one<P, 16, OP>(p, M, N, K, splits, kps, stream);
+    case 32: return launch_one<P, 32, OP>(p, M, N, K, splits, kps, stream);
+    case 64: return launch_one<P, 64, OP>(p, M, N, K, splits, kps, stream);
+    case 128: return launch_one<P, 128, OP>(p, M, N, K, splits, kps, stream);
+    default: return launch_one<P, 256, OP>(p, M, N, K, splits, kps, stream);
   }
 }
 template <class P>
-cudaError_t launch_tc(const P& p, long long M, int N, int splits, long long kps, int op, cudaStream_t stream) {
-  return op == OP_BF16 ? launch_bn<P, OP_BF16>(p, M, N, splits, kps, stream) : launch_bn<P, OP_TF32>(p, M, N, splits, kps, stream);
+cudaError_t launch_tc(const P& p, long long M, int N, long long K, int splits, long long kps, int op, cudaStream_t stream) {
+  return op == OP_BF16 ? launch_bn<P, OP_BF16>(p, M, N, K, splits, kps, stream) : launch_bn<P, OP_TF32>(p, M, N, K, splits, kps, stream);
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -563,7 +676,7 @@ int wdg_tc_conv2d_fwd(const ConvGeo& g, const float* x, const float* w, const fl
   p.vec_out = (g.y_cs % 4 == 0) && (g.y_co % 4 == 0) && al16(y);
   const long long M = (long long)g.N * g.Ho * g.Wo, K = (long long)g.kh * g.kw * g.Ci;
   if (M == 0) return 0;
-  CKT(launch_tc(p, M, g.Co, 1, K, op, stream));
+  CKT(launch_tc(p, M, g.Co, K, 1, K, op, stream));
   return 0;
 }
 
@@ -578,7 +691,7 @@ int wdg_tc_conv2d_bwd_data(const ConvGeo& g, const float* dy, const float* w, fl
       p.vec_out = (g.x_cs % 4 == 0) && (g.x_co % 4 == 0) && al16(dx);
       const long long M = (long long)g.N * p.c.Hc * p.c.Wc, K = (long long)p.c.Jy * p.c.Jx * g.Co;
       if (M == 0) continue;
-      CKT(launch_tc(p, M, g.Ci, 1, K > 0 ? K : 1, op, stream));
+      CKT(launch_tc(p, M, g.Ci, K, 1, K > 0 ? K : 1, op, stream));
     }
   return 0;
 }
@@ -602,8 +715,12 @@ void wdg_tc_wgrad_plan(const ConvGeo& g, int op, int* splits_out, long long* kps
 
 int wdg_tc_conv2d_bwd_weight(const ConvGeo& g, const float* x, const float* dy, float* part, int splits, long long kps, int op,
                              cudaStream_t stream) {
-  TcWgrad p{g, x, dy, part, kps};
-  const long long M = (long long)g.kh * g.kw * g.Ci;
-  CKT(launch_tc(p, M, g.Co, splits, kps, op, stream));
+  TcWgrad p{g, x, dy, part, kps, 0, 0};
+  // measured on B200: the float4 form wins with 8-element chunks (bf16, -10..25 %) and loses as often as it wins with
+  // 4-element chunks (tf32), so tf32 keeps the lane-per-row scalar form
+  p.vec_a = op == OP_BF16 && (g.Ci % 4 == 0) && (g.x_cs % 4 == 0) && (g.x_co % 4 == 0) && al16(x);
+  p.vec_b = op == OP_BF16 && (g.Co % 4 == 0) && (g.y_cs % 4 == 0) && (g.y_co % 4 == 0) && al16(dy);
+  const long long M = (long long)g.kh * g.kw * g.Ci, K = (long long)g.N * g.Ho * g.Wo;
+  CKT(launch_tc(p, M, g.Co, K, splits, kps, op, stream));
   return 0;
 }
