@@ -197,6 +197,19 @@ int wdg_gp_norm(const float* g, float* out, int B, long long per_sample_px, int 
 int wdg_adam(float* w, float* m, float* v, const float* g, long long n, float lr_t, float b1, float b2, float eps, void* stream);
 int wdg_sn_update(float* w, float* u, int R, int C, void* scratch, void* stream);
 
+/* ---- on-device evaluation metrics (reference gan/metrics.py).  real / fake: fp32 [B,T,H,W,C].
+ * wdg_metrics_pointwise: out[5][B] = wind_speed_weighted_rmse (metrics.py:32-45), wind_speed_rmse (:81-91),
+ * angular_cosine_distance (:97-105), opposite_cosine_similarity (:108-111), extreme_weighted_rmse (:66-73), all in
+ * one pass; pixels_per_sample = T*H*W; scratch from wdg_metrics_pointwise_scratch.
+ * wdg_metric_lsd: log_spectral_distance (:121-137) -- like tf.signal.rfft2d on the [B,T,H,W,C] tensor the transform
+ * runs over the two innermost axes (W, C); out[B]; scratch >= B*T*H doubles.
+ * wdg_metric_spatial_ks: spatially_convolved_ks_stat (:155-187), patch x patch windows, stride 1; out[(H-patch+1)*(W-patch+1)]. */
+int wdg_metrics_pointwise_scratch(int B, size_t* bytes);
+int wdg_metrics_pointwise(const float* real, const float* fake, int B, long long pixels_per_sample, int C, float* out,
+                          void* scratch, void* stream);
+int wdg_metric_lsd(const float* real, const float* fake, int B, int T, int H, int W, int C, float* out, void* scratch, void* stream);
+int wdg_metric_spatial_ks(const float* real, const float* fake, int B, int T, int H, int W, int C, int patch, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,10 @@ def _declare(lib):
         "wdg_adam": [vp, vp, vp, vp, ll, f, f, f, f, vp],
         "wdg_sn_update": [vp, vp, i, i, vp, vp],
         "wdg_noise_normal": [vp, ll, f, C.c_uint64, C.c_uint64, vp],
+        "wdg_metrics_pointwise_scratch": [i, C.POINTER(sz)],
+        "wdg_metrics_pointwise": [vp, vp, i, ll, i, vp, vp, vp],
+        "wdg_metric_lsd": [vp, vp, i, i, i, i, i, vp, vp, vp],
+        "wdg_metric_spatial_ks": [vp, vp, i, i, i, i, i, i, vp, vp],
     })
     for name, args in sigs.items():
         if not hasattr(lib, name):
