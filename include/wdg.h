@@ -147,7 +147,7 @@ int wdg_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, 
 int wdg_conv2d_bwd_data(const float* dy, const float* w, float* dx, const int* geo, int accumulate, void* stream);
 int wdg_conv2d_bwd_weight_scratch(const int* geo, size_t* bytes, int* splits);
 int wdg_conv2d_bwd_weight(const float* x, const float* dy, float* dw, const int* geo, void* scratch, int accumulate, void* stream);
-/* out[C] (+)= column sums over R rows; mode 0: a, 1: a*b, 2: a*a; scratch >= 512*C floats */
+/* out[C] (+)= column sums over R rows; mode 0: a, 1: a*b, 2: a*a; scratch >= 512*max(C,32) floats */
 int wdg_colsum(int mode, const float* a, int a_cs, int a_co, const float* b, int b_cs, int b_co, long long R, int C, float* out,
                void* scratch, int accumulate, void* stream);
 int wdg_leaky_relu_fwd(float* x, long long n, float alpha, void* stream);
@@ -159,7 +159,8 @@ int wdg_bias_act(float* x, int cs, int co, const float* bias, long long rows, in
 int wdg_transpose01(const float* in, float* out, int A, int B, long long inner, void* stream);
 int wdg_lerp_batch(float* out, const float* real, const float* fake, const float* eps, long long per_sample, long long n, void* stream);
 /* BatchNormalization (axis -1, eps, momentum): training mode uses batch statistics and updates the moving ones.
- * scratch: wdg_bn_train_fwd >= 514*C floats, wdg_bn_bwd_sums / wdg_bn_train_bwd >= 512*C floats, wdg_bn_infer >= C floats */
+ * scratch: wdg_bn_train_fwd >= 512*max(C,32) + 2*C floats, wdg_bn_bwd_sums / wdg_bn_train_bwd >= 512*max(C,32) floats,
+ * wdg_bn_infer >= C floats */
 int wdg_bn_train_fwd(const float* x, float* y, const float* gamma, const float* beta, float* moving_mean, float* moving_var,
                      float* save_mean, float* save_invstd, long long rows, int C, float eps, float momentum, void* scratch, void* stream);
 /* Split forms for data-parallel (synchronised) BatchNorm: per-channel sums are all-reduced by the caller */
@@ -174,7 +175,7 @@ int wdg_bn_infer(const float* x, float* y, const float* gamma, const float* beta
                  long long rows, int C, float eps, void* scratch, void* stream);
 int wdg_bn_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
                      float* dx, float* dgamma, float* dbeta, long long rows, int C, void* scratch, void* stream);
-/* LayerNormalization over the channel axis (wdg_ln_bwd scratch >= rows*C + 512*C floats) */
+/* LayerNormalization over the channel axis (wdg_ln_bwd scratch >= rows*C + 512*max(C,32) floats) */
 int wdg_ln_fwd(const float* x, float* y, int y_cs, int y_co, const float* gamma, const float* beta, float* save_mean,
                float* save_invstd, long long rows, int C, float eps, void* stream);
 int wdg_ln_bwd(const float* dy, int dy_cs, int dy_co, const float* x, const float* gamma, const float* save_mean,

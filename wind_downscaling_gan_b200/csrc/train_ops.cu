@@ -490,49 +490,59 @@ __global__ void bn_bwd_kernel(const float* __restrict__ dy, const float* __restr
   dx[i] = gamma[c] * invstd[c] * (dy[i] - dbeta[c] * inv_r - xhat * dgamma[c] * inv_r);
 }
 
-// LayerNorm over the channel axis (C <= 1024), one warp per pixel; saves mean and invstd per pixel.
+// LayerNorm over the channel axis: LPR lanes per pixel (LPR = 4 for the critic's 16-channel full-resolution layers, so a
+// warp handles 8 pixels and no lane idles); saves mean and invstd per pixel.
+template <int LPR>
 __global__ void ln_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
                               const float* __restrict__ beta, float* __restrict__ mean, float* __restrict__ invstd,
                               long long rows, int C, float eps, int y_cs, int y_co) {
-  const long long r = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
-  const int lane = threadIdx.x & 31;
-  if (r >= rows) return;
-  const float* xr = x + r * C;
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int lane = threadIdx.x % LPR;
+  const bool ok = r < rows;
+  const float* xr = x + (ok ? r : 0) * C;
   float s = 0.f;
-  for (int c = lane; c < C; c += 32) s += xr[c];
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
+  for (int c = lane; c < C; c += LPR) s += xr[c];
+#pragma unroll
+  for (int o = LPR / 2; o; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
   const float m = s / C;
   float v = 0.f;
-  for (int c = lane; c < C; c += 32) { const float d = xr[c] - m; v += d * d; }
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffff, v, o);
+  for (int c = lane; c < C; c += LPR) { const float d = xr[c] - m; v += d * d; }
+#pragma unroll
+  for (int o = LPR / 2; o; o >>= 1) v += __shfl_xor_sync(0xffffffff, v, o);
   const float is = rsqrtf(v / C + eps);
+  if (!ok) return;
   if (lane == 0 && mean) { mean[r] = m; invstd[r] = is; }
-  for (int c = lane; c < C; c += 32) y[r * y_cs + y_co + c] = (xr[c] - m) * is * gamma[c] + beta[c];
+  for (int c = lane; c < C; c += LPR) y[r * y_cs + y_co + c] = (xr[c] - m) * is * gamma[c] + beta[c];
 }
 // dx = invstd * (g - mean_c(g) - xhat * mean_c(g * xhat)), g = dy * gamma; also emits dy*xhat for dgamma
+template <int LPR>
 __global__ void ln_bwd_kernel(const float* __restrict__ dy, int dy_cs, int dy_co, const float* __restrict__ x,
                               const float* __restrict__ gamma, const float* __restrict__ mean,
                               const float* __restrict__ invstd, float* __restrict__ dx, float* __restrict__ dy_xhat,
                               long long rows, int C) {
-  const long long r = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
-  const int lane = threadIdx.x & 31;
-  if (r >= rows) return;
+  const long long r0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int lane = threadIdx.x % LPR;
+  const bool ok = r0 < rows;
+  const long long r = ok ? r0 : 0;
   const float m = mean[r], is = invstd[r];
   float s1 = 0.f, s2 = 0.f;
-  for (int c = lane; c < C; c += 32) {
+  for (int c = lane; c < C; c += LPR) {
     const float g = dy[r * dy_cs + dy_co + c] * gamma[c];
     const float xh = (x[r * C + c] - m) * is;
     s1 += g; s2 += g * xh;
   }
-  for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffff, s1, o); s2 += __shfl_xor_sync(0xffffffff, s2, o); }
+#pragma unroll
+  for (int o = LPR / 2; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffff, s1, o); s2 += __shfl_xor_sync(0xffffffff, s2, o); }
+  if (!ok) return;
   s1 /= C; s2 /= C;
-  for (int c = lane; c < C; c += 32) {
+  for (int c = lane; c < C; c += LPR) {
     const float d = dy[r * dy_cs + dy_co + c];
     const float xh = (x[r * C + c] - m) * is;
     dx[r * C + c] = is * (d * gamma[c] - s1 - xh * s2);
     dy_xhat[r * C + c] = d * xh;
   }
 }
+static inline int ln_lanes(int C) { return C <= 16 ? 4 : (C <= 32 ? 8 : (C <= 64 ? 16 : 32)); }
 
 // ------------------------------------------------------------------ ConvLSTM gate math (gates i, f, c~, o on the last axis)
 // z: [rows][4F] pre-activations (x-conv + bias + h-conv).  Saves the activated gates in place of z for the backward.
@@ -920,10 +930,27 @@ extern "C" int wdg_conv2d_bwd_weight(const float* x, const float* dy, float* dw,
   return 0;
 }
 
-// Two column sums in one pass (modes 3 / 4 of colsum_partial_kernel); scratch >= 2*CS_SLABS*C floats.
+// dst[c] (+)= sum_s sum_j part[s * stride + j * C + c]: final step of a column sum computed on the [R/k][k*C] view of a
+// dense narrow matrix (k = 32 / C pixels per 32-lane row, so no lane idles for the critic's 2..16-channel tensors)
+__global__ void reduce_fold_kernel(const float* __restrict__ part, float* __restrict__ dst, int C, int k, int splits,
+                                   long long stride, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int sp = 0; sp < splits; ++sp)
+    for (int j = 0; j < k; ++j) s += part[(long long)sp * stride + j * C + c];
+  dst[c] = accumulate ? dst[c] + s : s;
+}
+// Two column sums in one pass (modes 3 / 4 of colsum_partial_kernel); scratch >= 2*CS_SLABS*max(C, 32) floats.
 static int colsum_dual(int mode, const float* a, int a_cs, int a_co, const float* b, int b_cs, int b_co, const float* mean,
                        const float* invstd, long long R, int C, float* out1, float* out2, void* scratch, int accumulate,
                        cudaStream_t stream) {
+  int fold = 1;
+  const int C_out = C;
+  if (mode != 4 && C < 32 && 32 % C == 0 && a_cs == C && a_co == 0 && (mode != 1 || (b_cs == C && b_co == 0)) &&
+      R % (32 / C) == 0) {
+    fold = 32 / C; R /= fold; C = 32; a_cs = 32; b_cs = 32;
+  }
   long long slabs = (R + 255) / 256;
   if (slabs > CS_SLABS) slabs = CS_SLABS;
   if (slabs < 1) slabs = 1;
@@ -937,8 +964,13 @@ static int colsum_dual(int mode, const float* a, int a_cs, int a_co, const float
     default: colsum_partial_kernel<4><<<grid, block, 0, stream>>>(a, a_cs, a_co, b, b_cs, b_co, mean, invstd, R, C, part); break;
   }
   CKT(cudaGetLastError());
-  reduce_splits_kernel<<<blocks_for(C), 256, 0, stream>>>(part, out1, C, (int)slabs, accumulate, 2ll * C);
-  if (out2) reduce_splits_kernel<<<blocks_for(C), 256, 0, stream>>>(part + C, out2, C, (int)slabs, accumulate, 2ll * C);
+  if (fold > 1) {
+    reduce_fold_kernel<<<1, 32, 0, stream>>>(part, out1, C_out, fold, (int)slabs, 2ll * C, accumulate);
+    if (out2) reduce_fold_kernel<<<1, 32, 0, stream>>>(part + C, out2, C_out, fold, (int)slabs, 2ll * C, accumulate);
+  } else {
+    reduce_splits_kernel<<<blocks_for(C), 256, 0, stream>>>(part, out1, C, (int)slabs, accumulate, 2ll * C);
+    if (out2) reduce_splits_kernel<<<blocks_for(C), 256, 0, stream>>>(part + C, out2, C, (int)slabs, accumulate, 2ll * C);
+  }
   CKT(cudaGetLastError());
   return 0;
 }
@@ -985,12 +1017,12 @@ extern "C" int wdg_lerp_batch(float* out, const float* real, const float* fake, 
 }
 
 // BatchNorm, training mode: batch statistics (biased variance), moving statistics updated in place.
-// scratch >= (512*C + 2*C) floats.  Saves mean / invstd ([C] each) for the backward.
+// scratch >= (512*max(C,32) + 2*C) floats.  Saves mean / invstd ([C] each) for the backward.
 extern "C" int wdg_bn_train_fwd(const float* x, float* y, const float* gamma, const float* beta, float* moving_mean,
                                 float* moving_var, float* save_mean, float* save_invstd, long long rows, int C, float eps,
                                 float momentum, void* scratch, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  float* s1 = (float*)scratch + 2 * CS_SLABS * (size_t)C;
+  float* s1 = (float*)scratch + 2 * CS_SLABS * (size_t)(C < 32 ? 32 : C);
   float* s2 = s1 + C;
   if (colsum_dual(3, x, C, 0, nullptr, 0, 0, nullptr, nullptr, rows, C, s1, s2, scratch, 0, stream)) return 1;
   bn_finalize_kernel<<<blocks_for(C), 256, 0, stream>>>(s1, s2, rows, C, eps, momentum, save_mean, save_invstd, moving_mean, moving_var);
@@ -1052,7 +1084,13 @@ extern "C" int wdg_bn_train_bwd(const float* dy, const float* x, const float* ga
 
 extern "C" int wdg_ln_fwd(const float* x, float* y, int y_cs, int y_co, const float* gamma, const float* beta, float* save_mean,
                           float* save_invstd, long long rows, int C, float eps, void* stream) {
-  ln_fwd_kernel<<<blocks_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, y, gamma, beta, save_mean, save_invstd, rows, C, eps, y_cs, y_co);
+  const int lpr = ln_lanes(C);
+  const unsigned nb = blocks_for(rows * lpr);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (lpr == 4) ln_fwd_kernel<4><<<nb, 256, 0, st>>>(x, y, gamma, beta, save_mean, save_invstd, rows, C, eps, y_cs, y_co);
+  else if (lpr == 8) ln_fwd_kernel<8><<<nb, 256, 0, st>>>(x, y, gamma, beta, save_mean, save_invstd, rows, C, eps, y_cs, y_co);
+  else if (lpr == 16) ln_fwd_kernel<16><<<nb, 256, 0, st>>>(x, y, gamma, beta, save_mean, save_invstd, rows, C, eps, y_cs, y_co);
+  else ln_fwd_kernel<32><<<nb, 256, 0, st>>>(x, y, gamma, beta, save_mean, save_invstd, rows, C, eps, y_cs, y_co);
   CKT(cudaGetLastError());
   return 0;
 }
@@ -1063,7 +1101,12 @@ extern "C" int wdg_ln_bwd(const float* dy, int dy_cs, int dy_co, const float* x,
   cudaStream_t stream = (cudaStream_t)stream_;
   float* tmp = (float*)scratch;
   float* part = tmp + rows * C;
-  ln_bwd_kernel<<<blocks_for(rows, 8), 256, 0, stream>>>(dy, dy_cs, dy_co, x, gamma, save_mean, save_invstd, dx, tmp, rows, C);
+  const int lpr = ln_lanes(C);
+  const unsigned nb = blocks_for(rows * lpr);
+  if (lpr == 4) ln_bwd_kernel<4><<<nb, 256, 0, stream>>>(dy, dy_cs, dy_co, x, gamma, save_mean, save_invstd, dx, tmp, rows, C);
+  else if (lpr == 8) ln_bwd_kernel<8><<<nb, 256, 0, stream>>>(dy, dy_cs, dy_co, x, gamma, save_mean, save_invstd, dx, tmp, rows, C);
+  else if (lpr == 16) ln_bwd_kernel<16><<<nb, 256, 0, stream>>>(dy, dy_cs, dy_co, x, gamma, save_mean, save_invstd, dx, tmp, rows, C);
+  else ln_bwd_kernel<32><<<nb, 256, 0, stream>>>(dy, dy_cs, dy_co, x, gamma, save_mean, save_invstd, dx, tmp, rows, C);
   CKT(cudaGetLastError());
   if (wdg_colsum(0, tmp, C, 0, nullptr, 0, 0, rows, C, dgamma, part, 0, stream_)) return 1;
   if (wdg_colsum(0, dy, dy_cs, dy_co, nullptr, 0, 0, rows, C, dbeta, part, 0, stream_)) return 1;

@@ -105,7 +105,7 @@ def conv2d_bwd_weight(xv, dyv, dw, N, H, W, stride, pad, Ho, Wo, accumulate=Fals
 
 
 def colsum(av, out, mode=0, bv=None, accumulate=False):
-    sc = scratch(512 * av.C * 4, "colsum")
+    sc = scratch(512 * max(av.C, 32) * 4, "colsum")
     b = bv if bv is not None else av
     _lib.check(_lib.lib().wdg_colsum(mode, _p(av.t), av.cs, av.co, _p(b.t), b.cs, b.co, av.rows, av.C, _p(out), _p(sc),
                                      int(accumulate), _s()))
@@ -133,7 +133,7 @@ def lerp_batch(out, real, fake, eps):
 def bn_train_fwd(x, y, gamma, beta, mm, mv, save_mean, save_invstd, eps=1e-3, momentum=0.99):
     Cc = x.shape[-1]
     rows = x.numel() // Cc
-    sc = scratch((514 * Cc) * 4, "bn")
+    sc = scratch((512 * max(Cc, 32) + 2 * Cc) * 4, "bn")
     _lib.check(_lib.lib().wdg_bn_train_fwd(_p(x), _p(y), _p(gamma), _p(beta), _p(mm), _p(mv), _p(save_mean), _p(save_invstd), rows,
                                            Cc, eps, momentum, _p(sc), _s()))
 
@@ -147,7 +147,7 @@ def bn_infer(x, y, gamma, beta, mean, var, eps=1e-3):
 def bn_train_bwd(dy, x, gamma, save_mean, save_invstd, dx, dgamma, dbeta):
     Cc = x.shape[-1]
     rows = x.numel() // Cc
-    sc = scratch((rows * Cc + 512 * Cc) * 4, "norm_bwd")
+    sc = scratch((rows * Cc + 512 * max(Cc, 32)) * 4, "norm_bwd")
     _lib.check(_lib.lib().wdg_bn_train_bwd(_p(dy), _p(x), _p(gamma), _p(save_mean), _p(save_invstd), _p(dx), _p(dgamma), _p(dbeta),
                                            rows, Cc, _p(sc), _s()))
 
@@ -161,7 +161,7 @@ def ln_fwd(x, yv, gamma, beta, save_mean, save_invstd, eps=1e-3):
 def ln_bwd(dyv, x, gamma, save_mean, save_invstd, dx, dgamma, dbeta):
     Cc = x.shape[-1]
     rows = x.numel() // Cc
-    sc = scratch((rows * Cc + 512 * Cc) * 4, "norm_bwd")
+    sc = scratch((rows * Cc + 512 * max(Cc, 32)) * 4, "norm_bwd")
     _lib.check(_lib.lib().wdg_ln_bwd(_p(dyv.t), dyv.cs, dyv.co, _p(x), _p(gamma), _p(save_mean), _p(save_invstd), _p(dx), _p(dgamma),
                                      _p(dbeta), rows, Cc, _p(sc), _s()))
 
@@ -240,7 +240,7 @@ def bn_finalize_apply(x, y, gamma, beta, mm, mv, s1, s2, save_mean, save_invstd,
 def bn_bwd_sums(dy, x, save_mean, save_invstd, dgamma, dbeta):
     Cc = x.shape[-1]
     rows = x.numel() // Cc
-    sc = scratch((rows * Cc + 512 * Cc) * 4, "norm_bwd")
+    sc = scratch((rows * Cc + 512 * max(Cc, 32)) * 4, "norm_bwd")
     _lib.check(_lib.lib().wdg_bn_bwd_sums(_p(dy), _p(x), _p(save_mean), _p(save_invstd), _p(dgamma), _p(dbeta), rows, Cc, _p(sc), _s()))
 
 
