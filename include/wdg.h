@@ -182,7 +182,15 @@ int wdg_ln_bwd(const float* dy, int dy_cs, int dy_co, const float* x, const floa
                const float* save_invstd, float* dx, float* dgamma, float* dbeta, long long rows, int C, void* scratch, void* stream);
 /* ConvLSTM2D gate math (gates i, f, c~, o; hard_sigmoid / tanh), one timestep */
 int wdg_lstm_gates_fwd(float* z, const float* c_prev, float* c_out, float* h_out, long long rows, int F, void* stream);
-int wdg_lstm_gates_bwd(float* gates, const float* c_prev, const float* c_cur, const float* dh, float* dc, long long rows, int F, void* stream);
+/* dh_rec (may be NULL): recurrent part of dL/dh_t carried from step t+1, added to dh inside the kernel */
+int wdg_lstm_gates_bwd(float* gates, const float* c_prev, const float* c_cur, const float* dh, const float* dh_rec, float* dc,
+                       long long rows, int F, void* stream);
+/* Cells with F in {1, 2, 4} filters (critic high-resolution branch): recurrent 3x3 convolution fused with the gate math
+ * (z: x-conv + bias in, activated gates out; h_prev / c_prev NULL at t = 0; R = recurrent kernel [3][3][F][4F]) and
+ * the recurrent backward-data stencil dh_rec = conv_bwd_data(dz, R). */
+int wdg_lstm_small_fwd(float* z, const float* h_prev, const float* R, const float* c_prev, float* c_out, float* h_out,
+                       int N, int H, int W, int F, void* stream);
+int wdg_lstm_small_bwd_data(const float* dz, const float* R, float* dh_rec, int N, int H, int W, int F, void* stream);
 /* UpSampling2D(2, bilinear) and its adjoint */
 int wdg_upsample2x_fwd(const float* x, float* y, long long n_img, int h, int w, int C, void* stream);
 int wdg_upsample2x_bwd(const float* dy, float* dx, long long n_img, int h, int w, int C, void* stream);

@@ -137,8 +137,44 @@ def test_lstm_gates(ops):
     (hn * dh.double()).sum().backward(retain_graph=True)
     (cn * dc_next.double()).sum().backward()
     dc = dc_next.clone()
+    # the recurrent part of dL/dh may be passed separately and is added inside the kernel
+    dh_a = torch.randn((rows, Fc), device="cuda", generator=g)
+    zz2, dc2 = zz.clone(), dc_next.clone()
+    ops.lstm_gates_bwd(zz2, cp, c_out, dh - dh_a, dc2, dh_a)
     ops.lstm_gates_bwd(zz, cp, c_out, dh, dc)
     assert rel(zz, zr.grad) < 1e-4 and rel(dc, cr.grad) < 1e-4
+    assert rel(zz2, zr.grad) < 1e-4 and rel(dc2, cr.grad) < 1e-4
+
+
+@pytest.mark.parametrize("Fc", [1, 2, 4])
+def test_lstm_small_filters(ops, Fc):
+    """Fused recurrent-conv + gate kernel for cells with 1/2/4 filters and its backward-data stencil against the
+    generic path (conv2d_fwd accumulate + lstm_gates_fwd, conv2d_bwd_data)."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(6)
+    N, H, W = 3, 13, 17
+    xz = torch.randn((N, H, W, 4 * Fc), device="cuda", generator=g)
+    hp = torch.randn((N, H, W, Fc), device="cuda", generator=g)
+    cp = torch.randn((N, H, W, Fc), device="cuda", generator=g)
+    R = torch.randn((3, 3, Fc, 4 * Fc), device="cuda", generator=g) * 0.5
+    ref_z = xz.clone()
+    ops.conv2d_fwd(ops.full(hp), R, None, ops.full(ref_z), N, H, W, 1, 1, H, W, accumulate=True)
+    ref_c, ref_h = ops.empty(N, H, W, Fc), ops.empty(N, H, W, Fc)
+    ops.lstm_gates_fwd(ref_z, cp, ref_c, ref_h)
+    z, c, h = xz.clone(), ops.empty(N, H, W, Fc), ops.empty(N, H, W, Fc)
+    ops.lstm_small_fwd(z, hp, R, cp, c, h)
+    assert rel(z, ref_z) < 1e-5 and rel(c, ref_c) < 1e-5 and rel(h, ref_h) < 1e-5
+    # first timestep: no previous state
+    z0, c0, h0 = xz.clone(), ops.empty(N, H, W, Fc), ops.empty(N, H, W, Fc)
+    ops.lstm_small_fwd(z0, None, R, None, c0, h0)
+    r0, rc0, rh0 = xz.clone(), ops.empty(N, H, W, Fc), ops.empty(N, H, W, Fc)
+    ops.lstm_gates_fwd(r0, None, rc0, rh0)
+    assert rel(z0, r0) < 1e-6 and rel(h0, rh0) < 1e-6
+    dz = torch.randn((N, H, W, 4 * Fc), device="cuda", generator=g)
+    ref_dh, dh = ops.empty(N, H, W, Fc), ops.empty(N, H, W, Fc)
+    ops.conv2d_bwd_data(ops.full(dz), R, ops.full(ref_dh), N, H, W, 1, 1, H, W)
+    ops.lstm_small_bwd_data(dz, R, dh)
+    assert rel(dh, ref_dh) < 1e-5
 
 
 def test_upsample_and_adjoint(ops):

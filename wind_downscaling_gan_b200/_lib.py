@@ -70,7 +70,9 @@ def _declare(lib):
         "wdg_ln_fwd": [vp, vp, i, i, vp, vp, vp, vp, ll, i, f, vp],
         "wdg_ln_bwd": [vp, i, i, vp, vp, vp, vp, vp, vp, vp, ll, i, vp, vp],
         "wdg_lstm_gates_fwd": [vp, vp, vp, vp, ll, i, vp],
-        "wdg_lstm_gates_bwd": [vp, vp, vp, vp, vp, ll, i, vp],
+        "wdg_lstm_gates_bwd": [vp, vp, vp, vp, vp, vp, ll, i, vp],
+        "wdg_lstm_small_fwd": [vp, vp, vp, vp, vp, vp, i, i, i, i, vp],
+        "wdg_lstm_small_bwd_data": [vp, vp, vp, i, i, i, i, vp],
         "wdg_upsample2x_fwd": [vp, vp, ll, i, i, i, vp],
         "wdg_upsample2x_bwd": [vp, vp, ll, i, i, i, vp],
         "wdg_dense_mean_fwd": [vp, vp, vp, vp, i, i, i, vp],

@@ -565,8 +565,10 @@ __global__ void lstm_gates_fwd_kernel(float* __restrict__ z, const float* __rest
 }
 // Backward of one step.  gates: saved activated gates; dh: dL/dh_t (from the output and from step t+1);
 // dc: in = dL/dc_t carried from step t+1, out = dL/dc_{t-1}.  Writes dz (pre-activation gradient) over `gates`.
+// dh_rec (optional): the recurrent contribution dL/dh_t carried from step t+1, added here instead of by a separate pass.
 __global__ void lstm_gates_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_cur,
-                                      const float* __restrict__ dh, float* __restrict__ dc, long long rows, int F) {
+                                      const float* __restrict__ dh, const float* __restrict__ dh_rec, float* __restrict__ dc,
+                                      long long rows, int F) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * F) return;
   const long long r = i / F;
@@ -574,7 +576,7 @@ __global__ void lstm_gates_bwd_kernel(float* __restrict__ gates, const float* __
   float* g = gates + r * 4 * F;
   const float gi = g[c], gf = g[F + c], gc = g[2 * F + c], go = g[3 * F + c];
   const float tc = tanhf(c_cur[i]);
-  const float dhv = dh[i];
+  const float dhv = dh_rec ? dh[i] + dh_rec[i] : dh[i];
   const float dct = dc[i] + dhv * go * (1.f - tc * tc);
   const float cp = c_prev ? c_prev[i] : 0.f;
   // hard_sigmoid'(z) = 0.2 strictly inside (0, 1)
@@ -584,6 +586,91 @@ __global__ void lstm_gates_bwd_kernel(float* __restrict__ gates, const float* __
   const float dov = dhv * tc * ((go > 0.f && go < 1.f) ? 0.2f : 0.f);
   g[c] = di; g[F + c] = df; g[2 * F + c] = dg; g[3 * F + c] = dov;
   dc[i] = dct * gf;
+}
+
+// ConvLSTM cells with very few filters (the critic's high-resolution branch: ConvLSTM2D(2) on 96x96 images): the
+// recurrent 3x3 convolution has K = 9 F <= 36 and N = 4 F <= 16, a bandwidth-bound stencil rather than a GEMM, so one
+// thread per pixel does the recurrent convolution AND the gate math in one pass (fp32, whatever the GEMM precision).
+// z in: x-conv + bias of this step; out: activated gates (as lstm_gates_fwd_kernel leaves them).  R: [3][3][F][4F].
+template <int F>
+__global__ void lstm_small_fwd_kernel(float* __restrict__ z, const float* __restrict__ h_prev, const float* __restrict__ R,
+                                      const float* __restrict__ c_prev, float* __restrict__ c_out, float* __restrict__ h_out,
+                                      int N, int H, int W) {
+  __shared__ float sR[9 * F * 4 * F];
+  for (int i = threadIdx.x; i < 9 * F * 4 * F; i += blockDim.x) sR[i] = R[i];
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * H * W) return;
+  const int x = (int)(idx % W), y = (int)((idx / W) % H);
+  const long long img = idx / ((long long)W * H);
+  float acc[4 * F];
+#pragma unroll
+  for (int g = 0; g < 4 * F; ++g) acc[g] = z[idx * 4 * F + g];
+  if (h_prev) {
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const float* hp = h_prev + ((img * H + yy) * W + xx) * F;
+#pragma unroll
+        for (int ci = 0; ci < F; ++ci) {
+          const float hv = hp[ci];
+#pragma unroll
+          for (int g = 0; g < 4 * F; ++g) acc[g] = fmaf(hv, sR[((ky * 3 + kx) * F + ci) * 4 * F + g], acc[g]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < F; ++c) {
+    const float gi = fminf(fmaxf(0.2f * acc[c] + 0.5f, 0.f), 1.f);
+    const float gf = fminf(fmaxf(0.2f * acc[F + c] + 0.5f, 0.f), 1.f);
+    const float gc = tanhf(acc[2 * F + c]);
+    const float go = fminf(fmaxf(0.2f * acc[3 * F + c] + 0.5f, 0.f), 1.f);
+    const float cp = c_prev ? c_prev[idx * F + c] : 0.f;
+    const float cn = gf * cp + gi * gc;
+    z[idx * 4 * F + c] = gi; z[idx * 4 * F + F + c] = gf; z[idx * 4 * F + 2 * F + c] = gc; z[idx * 4 * F + 3 * F + c] = go;
+    c_out[idx * F + c] = cn;
+    h_out[idx * F + c] = go * tanhf(cn);
+  }
+}
+// dh_rec[n, iy, ix, ci] = sum_{ky, kx, g} dz[n, iy + 1 - ky, ix + 1 - kx, g] * R[ky][kx][ci][g]
+template <int F>
+__global__ void lstm_small_bwd_data_kernel(const float* __restrict__ dz, const float* __restrict__ R, float* __restrict__ dh_rec,
+                                           int N, int H, int W) {
+  __shared__ float sR[9 * F * 4 * F];
+  for (int i = threadIdx.x; i < 9 * F * 4 * F; i += blockDim.x) sR[i] = R[i];
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * H * W) return;
+  const int x = (int)(idx % W), y = (int)((idx / W) % H);
+  const long long img = idx / ((long long)W * H);
+  float acc[F];
+#pragma unroll
+  for (int c = 0; c < F; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int oy = y + 1 - ky;
+    if (oy < 0 || oy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ox = x + 1 - kx;
+      if (ox < 0 || ox >= W) continue;
+      const float* d = dz + ((img * H + oy) * W + ox) * 4 * F;
+#pragma unroll
+      for (int g = 0; g < 4 * F; ++g) {
+        const float dv = d[g];
+#pragma unroll
+        for (int ci = 0; ci < F; ++ci) acc[ci] = fmaf(dv, sR[((ky * 3 + kx) * F + ci) * 4 * F + g], acc[ci]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < F; ++c) dh_rec[idx * F + c] = acc[c];
 }
 
 // ------------------------------------------------------------------ bilinear x2 (half-pixel centres, edge clamp) and adjoint
@@ -1118,9 +1205,31 @@ extern "C" int wdg_lstm_gates_fwd(float* z, const float* c_prev, float* c_out, f
   CKT(cudaGetLastError());
   return 0;
 }
-extern "C" int wdg_lstm_gates_bwd(float* gates, const float* c_prev, const float* c_cur, const float* dh, float* dc,
-                                  long long rows, int F, void* stream) {
-  lstm_gates_bwd_kernel<<<blocks_for(rows * F), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_cur, dh, dc, rows, F);
+extern "C" int wdg_lstm_gates_bwd(float* gates, const float* c_prev, const float* c_cur, const float* dh, const float* dh_rec,
+                                  float* dc, long long rows, int F, void* stream) {
+  lstm_gates_bwd_kernel<<<blocks_for(rows * F), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_cur, dh, dh_rec, dc, rows, F);
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int wdg_lstm_small_fwd(float* z, const float* h_prev, const float* R, const float* c_prev, float* c_out, float* h_out,
+                                  int N, int H, int W, int F, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const unsigned nb = blocks_for((long long)N * H * W);
+  if (F == 1) lstm_small_fwd_kernel<1><<<nb, 256, 0, stream>>>(z, h_prev, R, c_prev, c_out, h_out, N, H, W);
+  else if (F == 2) lstm_small_fwd_kernel<2><<<nb, 256, 0, stream>>>(z, h_prev, R, c_prev, c_out, h_out, N, H, W);
+  else if (F == 4) lstm_small_fwd_kernel<4><<<nb, 256, 0, stream>>>(z, h_prev, R, c_prev, c_out, h_out, N, H, W);
+  else return wdg_set_error("wdg_lstm_small_fwd: F must be 1, 2 or 4");
+  CKT(cudaGetLastError());
+  return 0;
+}
+extern "C" int wdg_lstm_small_bwd_data(const float* dz, const float* R, float* dh_rec, int N, int H, int W, int F, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const unsigned nb = blocks_for((long long)N * H * W);
+  if (F == 1) lstm_small_bwd_data_kernel<1><<<nb, 256, 0, stream>>>(dz, R, dh_rec, N, H, W);
+  else if (F == 2) lstm_small_bwd_data_kernel<2><<<nb, 256, 0, stream>>>(dz, R, dh_rec, N, H, W);
+  else if (F == 4) lstm_small_bwd_data_kernel<4><<<nb, 256, 0, stream>>>(dz, R, dh_rec, N, H, W);
+  else return wdg_set_error("wdg_lstm_small_bwd_data: F must be 1, 2 or 4");
   CKT(cudaGetLastError());
   return 0;
 }

@@ -162,7 +162,11 @@ class ConvLSTM:
         gates = ops.empty(T, B, H, W, 4 * F)
         # the input convolution (+ bias) of every timestep is one GEMM; only the recurrent convolution is serial
         ops.conv2d_fwd(full(xt.view(T * B, H, W, Cin)), self.K, self.b, full(gates.view(T * B, H, W, 4 * F)), T * B, H, W, 1, 1, H, W)
+        small = F in ops.SMALL_LSTM_FILTERS and tuple(self.R.shape[:2]) == (3, 3)
         for t in range(T):
+            if small:      # recurrent conv + gates in one bandwidth-bound pass (critic high-resolution branch)
+                ops.lstm_small_fwd(gates[t], hs[t - 1] if t > 0 else None, self.R, cs[t - 1] if t > 0 else None, cs[t], hs[t])
+                continue
             if t > 0:
                 ops.conv2d_fwd(full(hs[t - 1]), self.R, None, full(gates[t]), B, H, W, 1, 1, H, W, accumulate=True)
             ops.lstm_gates_fwd(gates[t], cs[t - 1] if t > 0 else None, cs[t], hs[t])
@@ -175,14 +179,16 @@ class ConvLSTM:
         dhs = ops.transpose01(dh_seq.view(B, T, H, W, F))        # [T, B, ...]
         dK = dR = db = None
         dc = ops.zeros(B, H, W, F)
-        dh_rec = ops.zeros(B, H, W, F)
+        dh_rec = ops.empty(B, H, W, F)
+        small = F in ops.SMALL_LSTM_FILTERS and tuple(self.R.shape[:2]) == (3, 3)
         for t in range(T - 1, -1, -1):            # serial part: gate backward and the recurrent backward-data
-            dh = dhs[t]
-            if t < T - 1:
-                ops.axpby(full(dh), full(dh), 1.0, full(dh_rec), 1.0)
-            ops.lstm_gates_bwd(gates[t], cs[t - 1] if t > 0 else None, cs[t], dh, dc)   # gates[t] now holds dz_t
+            ops.lstm_gates_bwd(gates[t], cs[t - 1] if t > 0 else None, cs[t], dhs[t], dc,
+                               dh_rec if t < T - 1 else None)                            # gates[t] now holds dz_t
             if t > 0:
-                ops.conv2d_bwd_data(full(gates[t]), self.R, full(dh_rec), B, H, W, 1, 1, H, W)
+                if small:
+                    ops.lstm_small_bwd_data(gates[t], self.R, dh_rec)
+                else:
+                    ops.conv2d_bwd_data(full(gates[t]), self.R, full(dh_rec), B, H, W, 1, 1, H, W)
         # everything that only needs all dz_t: one GEMM each over the T*B images
         dz_all = full(gates.view(T * B, H, W, 4 * F))
         if need_dw:

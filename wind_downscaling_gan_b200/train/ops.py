@@ -171,9 +171,24 @@ def lstm_gates_fwd(z, c_prev, c_out, h_out):
     _lib.check(_lib.lib().wdg_lstm_gates_fwd(_p(z), _p(c_prev), _p(c_out), _p(h_out), c_out.numel() // Fc, Fc, _s()))
 
 
-def lstm_gates_bwd(gates, c_prev, c_cur, dh, dc):
+def lstm_gates_bwd(gates, c_prev, c_cur, dh, dc, dh_rec=None):
     Fc = c_cur.shape[-1]
-    _lib.check(_lib.lib().wdg_lstm_gates_bwd(_p(gates), _p(c_prev), _p(c_cur), _p(dh), _p(dc), c_cur.numel() // Fc, Fc, _s()))
+    _lib.check(_lib.lib().wdg_lstm_gates_bwd(_p(gates), _p(c_prev), _p(c_cur), _p(dh), _p(dh_rec), _p(dc),
+                                              c_cur.numel() // Fc, Fc, _s()))
+
+
+SMALL_LSTM_FILTERS = (1, 2, 4)
+
+
+def lstm_small_fwd(z, h_prev, R, c_prev, c_out, h_out):
+    """Fused recurrent 3x3 conv + gates for cells with 1/2/4 filters; z [N,H,W,4F] holds x-conv + bias, becomes the gates."""
+    N, H, W, Fc = c_out.shape
+    _lib.check(_lib.lib().wdg_lstm_small_fwd(_p(z), _p(h_prev), _p(R), _p(c_prev), _p(c_out), _p(h_out), N, H, W, Fc, _s()))
+
+
+def lstm_small_bwd_data(dz, R, dh_rec):
+    N, H, W, Fc = dh_rec.shape
+    _lib.check(_lib.lib().wdg_lstm_small_bwd_data(_p(dz), _p(R), _p(dh_rec), N, H, W, Fc, _s()))
 
 
 def upsample2x_fwd(x, y):
