@@ -188,6 +188,39 @@ struct LinearRowFastB {
     k += 8 * G;
     q += 8 * G * ld;
   }
+  // Split form: fetch the first (up to 4-chunk) batch into registers so that the caller can issue it together with
+  // its own global loads (ONE round trip per K block), store it later; the remaining batches (BN = 256) follow.
+  static constexpr int NB0 = CPT < 4 ? CPT : 4;
+  __device__ __forceinline__ void fetch0(float (&v)[NB0][G]) const {
+#pragma unroll
+    for (int c = 0; c < NB0; ++c)
+#pragma unroll
+      for (int e = 0; e < G; ++e) {
+        const int kk = c * G + e;
+        v[c][e] = (active && nv && k + kk < k_end) ? __ldg(q + kk * ld) : 0.f;
+      }
+  }
+  __device__ __forceinline__ void store0_and_rest(uint32_t tile, const float (&v0)[NB0][G]) {
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < NB0; ++c) store_chunk<OP>(tile, row, chunk0 + c, v0[c]);
+#pragma unroll 1
+      for (int c0 = 4; c0 < CPT; c0 += 4) {
+        float v[NB0][G];
+#pragma unroll
+        for (int c = 0; c < NB0; ++c)
+#pragma unroll
+          for (int e = 0; e < G; ++e) {
+            const int kk = (c0 + c) * G + e;
+            v[c][e] = (nv && k + kk < k_end) ? __ldg(q + kk * ld) : 0.f;
+          }
+#pragma unroll
+        for (int c = 0; c < NB0; ++c) store_chunk<OP>(tile, row, chunk0 + c0 + c, v[c]);
+      }
+    }
+    k += 8 * G;
+    q += 8 * G * ld;
+  }
 };
 
 // ------------------------------------------------------------------------------------------------ problems
@@ -380,6 +413,16 @@ struct TcWgrad {
             v[c][e] = ok ? __ldg(col + (((long long)n * H + iy) * W + ix) * cs) : 0.f;
             step();
           }
+        if (!vecB) {       // issue the B gathers before the first shared-memory store: one global round trip per K block
+          float vb[LinearRowFastB<OP, BN>::NB0][G];
+          b.fetch0(vb);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) store_chunk<OP>(a_tile, row, chunk0 + c, v[c]);
+          advance(RUN);
+          b.store0_and_rest(b_tile, vb);
+          kb0 += KB;
+          return;
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) store_chunk<OP>(a_tile, row, chunk0 + c, v[c]);
         advance(RUN);

@@ -1017,16 +1017,52 @@ extern "C" int wdg_conv2d_bwd_weight(const float* x, const float* dy, float* dw,
   return 0;
 }
 
+// Column sums of a DENSE [R][32] fp32 matrix (the folded view of a narrow tensor): float4 loads, 8 lanes per row, 32
+// rows per block pass, 4 passes in flight per thread.  Same partial layout as colsum_partial_kernel (part[slab][2][32]).
+template <int MODE>   // 0: sum a   1: sum a*b   2: sum a*a   3: sum a and sum a*a
+__global__ void __launch_bounds__(256) colsum32_dense_kernel(const float4* __restrict__ a, const float4* __restrict__ b, long long R,
+                                                             float* __restrict__ part) {
+  __shared__ float4 sm[2][32][9];
+  const int q = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const long long rows_per = (R + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * rows_per, r1 = min(R, r0 + rows_per);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  for (long long r = r0 + rl; r < r1; r += 128) {
+    float4 av[4], bv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long rr = r + 32 * j;
+      av[j] = rr < r1 ? __ldg(a + rr * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE == 1) bv[j] = rr < r1 ? __ldg(b + rr * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (MODE == 0 || MODE == 3) { s1.x += av[j].x; s1.y += av[j].y; s1.z += av[j].z; s1.w += av[j].w; }
+      if (MODE == 1) { s1.x += av[j].x * bv[j].x; s1.y += av[j].y * bv[j].y; s1.z += av[j].z * bv[j].z; s1.w += av[j].w * bv[j].w; }
+      if (MODE == 2) { s1.x += av[j].x * av[j].x; s1.y += av[j].y * av[j].y; s1.z += av[j].z * av[j].z; s1.w += av[j].w * av[j].w; }
+      if (MODE == 3) { s2.x += av[j].x * av[j].x; s2.y += av[j].y * av[j].y; s2.z += av[j].z * av[j].z; s2.w += av[j].w * av[j].w; }
+    }
+  }
+  sm[0][rl][q] = s1; sm[1][rl][q] = s2;
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    const int which = threadIdx.x >> 3, qq = threadIdx.x & 7;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 32; ++i) { const float4 v = sm[which][i][qq]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    reinterpret_cast<float4*>(part + ((long long)blockIdx.x * 2 + which) * 32)[qq] = t;
+  }
+}
+
 // dst[c] (+)= sum_s sum_j part[s * stride + j * C + c]: final step of a column sum computed on the [R/k][k*C] view of a
 // dense narrow matrix (k = 32 / C pixels per 32-lane row, so no lane idles for the critic's 2..16-channel tensors)
 __global__ void reduce_fold_kernel(const float* __restrict__ part, float* __restrict__ dst, int C, int k, int splits,
                                    long long stride, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  const int c = blockIdx.x, lane = threadIdx.x;          // one warp per output channel, fixed reduction tree
   float s = 0.f;
-  for (int sp = 0; sp < splits; ++sp)
-    for (int j = 0; j < k; ++j) s += part[(long long)sp * stride + j * C + c];
-  dst[c] = accumulate ? dst[c] + s : s;
+  for (int i = lane; i < splits * k; i += 32) s += part[(long long)(i / k) * stride + (i % k) * C + c];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) dst[c] = accumulate ? dst[c] + s : s;
 }
 // Two column sums in one pass (modes 3 / 4 of colsum_partial_kernel); scratch >= 2*CS_SLABS*max(C, 32) floats.
 static int colsum_dual(int mode, const float* a, int a_cs, int a_co, const float* b, int b_cs, int b_co, const float* mean,
@@ -1043,7 +1079,15 @@ static int colsum_dual(int mode, const float* a, int a_cs, int a_co, const float
   if (slabs < 1) slabs = 1;
   dim3 grid((C + 31) / 32, (unsigned)slabs), block(32, 8);
   float* part = (float*)scratch;
-  switch (mode) {
+  const bool dense32 = fold > 1 && ((uintptr_t)a & 15) == 0 && (mode != 1 || ((uintptr_t)b & 15) == 0);
+  if (dense32) {
+    const float4* a4 = (const float4*)a;
+    const float4* b4 = (const float4*)b;
+    if (mode == 0) colsum32_dense_kernel<0><<<(unsigned)slabs, 256, 0, stream>>>(a4, b4, R, part);
+    else if (mode == 1) colsum32_dense_kernel<1><<<(unsigned)slabs, 256, 0, stream>>>(a4, b4, R, part);
+    else if (mode == 2) colsum32_dense_kernel<2><<<(unsigned)slabs, 256, 0, stream>>>(a4, b4, R, part);
+    else colsum32_dense_kernel<3><<<(unsigned)slabs, 256, 0, stream>>>(a4, b4, R, part);
+  } else switch (mode) {
     case 0: colsum_partial_kernel<0><<<grid, block, 0, stream>>>(a, a_cs, a_co, b, b_cs, b_co, mean, invstd, R, C, part); break;
     case 1: colsum_partial_kernel<1><<<grid, block, 0, stream>>>(a, a_cs, a_co, b, b_cs, b_co, mean, invstd, R, C, part); break;
     case 2: colsum_partial_kernel<2><<<grid, block, 0, stream>>>(a, a_cs, a_co, b, b_cs, b_co, mean, invstd, R, C, part); break;
@@ -1052,8 +1096,8 @@ static int colsum_dual(int mode, const float* a, int a_cs, int a_co, const float
   }
   CKT(cudaGetLastError());
   if (fold > 1) {
-    reduce_fold_kernel<<<1, 32, 0, stream>>>(part, out1, C_out, fold, (int)slabs, 2ll * C, accumulate);
-    if (out2) reduce_fold_kernel<<<1, 32, 0, stream>>>(part + C, out2, C_out, fold, (int)slabs, 2ll * C, accumulate);
+    reduce_fold_kernel<<<C_out, 32, 0, stream>>>(part, out1, C_out, fold, (int)slabs, 2ll * C, accumulate);
+    if (out2) reduce_fold_kernel<<<C_out, 32, 0, stream>>>(part + C, out2, C_out, fold, (int)slabs, 2ll * C, accumulate);
   } else {
     reduce_splits_kernel<<<blocks_for(C), 256, 0, stream>>>(part, out1, C, (int)slabs, accumulate, 2ll * C);
     if (out2) reduce_splits_kernel<<<blocks_for(C), 256, 0, stream>>>(part + C, out2, C, (int)slabs, accumulate, 2ll * C);

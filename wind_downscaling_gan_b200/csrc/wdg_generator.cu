@@ -2,6 +2,7 @@
 // C ABI declared in include/wdg.h for the generator forward (reference models.py:9-73).
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 
 #include <cmath>
@@ -447,7 +448,12 @@ static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
 // The pipelined host entry point splits B into chunks of CHUNK_B sequences (plus a tail); each plan gets its own region.
 static const int CHUNK_B = 16;
 static void chunking(int B, int* chunk_B, int* tail_B) {
-  if (B >= 2 * CHUNK_B) { *chunk_B = CHUNK_B; *tail_B = B % CHUNK_B; }
+  int cb = CHUNK_B;
+  if (const char* e = getenv("WDG_CHUNK_B")) {   // tuning knob of the host pipeline (sequences per chunk)
+    const int v = atoi(e);
+    if (v > 0) cb = v;
+  }
+  if (B >= 2 * cb) { *chunk_B = cb; *tail_B = B % cb; }
   else { *chunk_B = 0; *tail_B = 0; }
 }
 
