@@ -387,14 +387,28 @@ struct TcWgrad {
       if (++ox == Wo) { ox = 0; if (++oy == Ho) { oy = 0; ++n; } }
     }
     __device__ __forceinline__ void load(uint32_t a_tile, uint32_t b_tile, int tid) {
+      // incremental addressing along an image row: pointer += s * cs per pixel, full recomputation only at a row wrap
+      int iy = oy * s - pad_t + ky, ix = ox * s - pad_l + kx;
+      bool rowok = mv && (unsigned)iy < (unsigned)H;
+      const float* p = col + (((long long)n * H + iy) * W + ix) * cs;
+      const int dp = s * cs;
+      auto next_px = [&]() {
+        ++k; ix += s; p += dp;
+        if (++ox == Wo) {
+          ox = 0;
+          if (++oy == Ho) { oy = 0; ++n; }
+          iy = oy * s - pad_t + ky; ix = kx - pad_l;
+          rowok = mv && (unsigned)iy < (unsigned)H;
+          p = col + (((long long)n * H + iy) * W + ix) * cs;
+        }
+      };
       if (vecA) {
         float4 t[G];
 #pragma unroll
         for (int e = 0; e < G; ++e) {
-          const int iy = oy * s - pad_t + ky, ix = ox * s - pad_l + kx;
-          const bool ok = mv && k < k_end && (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
-          t[e] = ok ? __ldg(reinterpret_cast<const float4*>(col + (((long long)n * H + iy) * W + ix) * cs)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          step();
+          const bool ok = rowok && k < k_end && (unsigned)ix < (unsigned)W;
+          t[e] = ok ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          next_px();
         }
         float v[4][G];
 #pragma unroll
@@ -408,10 +422,9 @@ struct TcWgrad {
         for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int e = 0; e < G; ++e) {
-            const int iy = oy * s - pad_t + ky, ix = ox * s - pad_l + kx;
-            const bool ok = mv && k < k_end && (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
-            v[c][e] = ok ? __ldg(col + (((long long)n * H + iy) * W + ix) * cs) : 0.f;
-            step();
+            const bool ok = rowok && k < k_end && (unsigned)ix < (unsigned)W;
+            v[c][e] = ok ? __ldg(p) : 0.f;
+            next_px();
           }
         if (!vecB) {       // issue the B gathers before the first shared-memory store: one global round trip per K block
           float vb[LinearRowFastB<OP, BN>::NB0][G];
