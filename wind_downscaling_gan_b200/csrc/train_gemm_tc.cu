@@ -19,6 +19,7 @@
 //   backward-weight C[m = (ky,kx,ci)][co]    = sum_{k=(n,oy,ox)} x[n, oy*s-p+ky, ox*s-p+kx, ci] * dy[k][co]   (split-K)
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <type_traits>
@@ -772,10 +773,14 @@ void wdg_tc_wgrad_plan(const ConvGeo& g, int op, int* splits_out, long long* kps
 int wdg_tc_conv2d_bwd_weight(const ConvGeo& g, const float* x, const float* dy, float* part, int splits, long long kps, int op,
                              cudaStream_t stream) {
   TcWgrad p{g, x, dy, part, kps, 0, 0};
-  // measured on B200: the float4 form wins with 8-element chunks (bf16, -10..25 %) and loses as often as it wins with
-  // 4-element chunks (tf32), so tf32 keeps the lane-per-row scalar form
-  p.vec_a = op == OP_BF16 && (g.Ci % 4 == 0) && (g.x_cs % 4 == 0) && (g.x_co % 4 == 0) && al16(x);
-  p.vec_b = op == OP_BF16 && (g.Co % 4 == 0) && (g.y_cs % 4 == 0) && (g.y_co % 4 == 0) && al16(dy);
+  // Measured on B200 (profiles/r1_train_conv_table.md): with incremental row addressing and both gathers issued in one
+  // round trip the lane-per-row scalar form beats the float4 register-transposing form for every layer wider than 16
+  // output channels (-10..35 %); the float4 form keeps a 3-15 % edge for the narrow ones.  WDG_WGRAD_VEC=0/1 forces it.
+  static int force = -2;
+  if (force == -2) { const char* e = getenv("WDG_WGRAD_VEC"); force = e ? atoi(e) : -1; }
+  const bool want = force < 0 ? g.Co <= 16 : force != 0;
+  p.vec_a = want && (g.Ci % 4 == 0) && (g.x_cs % 4 == 0) && (g.x_co % 4 == 0) && al16(x);
+  p.vec_b = want && (g.Co % 4 == 0) && (g.y_cs % 4 == 0) && (g.y_co % 4 == 0) && al16(dy);
   const long long M = (long long)g.kh * g.kw * g.Ci, K = (long long)g.N * g.Ho * g.Wo;
   CKT(launch_tc(p, M, g.Co, K, splits, kps, op, stream));
   return 0;
