@@ -157,6 +157,9 @@ int wdg_axpby(float* out, int o_cs, int o_co, const float* x, int x_cs, int x_co
 /* x = leaky(x + bias, alpha) in place (alpha = 1: linear); out[b][a][:] = in[a][b][:] */
 int wdg_bias_act(float* x, int cs, int co, const float* bias, long long rows, int C, float alpha, void* stream);
 int wdg_transpose01(const float* in, float* out, int A, int B, long long inner, void* stream);
+/* Overlap-add for a stride-1 transposed convolution computed as a 1x1 GEMM into per-pixel tap columns
+ * cols[N,H,W,(kh,kw,Co)]: out[n,iy,ix,o] = sum_{ky,kx} cols[n, iy+pad-ky, ix+pad-kx, (ky,kx,o)] */
+int wdg_col2im(const float* cols, float* out, int N, int H, int W, int kh, int kw, int Co, int pad, int o_cs, int o_co, void* stream);
 int wdg_lerp_batch(float* out, const float* real, const float* fake, const float* eps, long long per_sample, long long n, void* stream);
 /* BatchNormalization (axis -1, eps, momentum): training mode uses batch statistics and updates the moving ones.
  * scratch: wdg_bn_train_fwd >= 512*max(C,32) + 2*C floats, wdg_bn_bwd_sums / wdg_bn_train_bwd >= 512*max(C,32) floats,

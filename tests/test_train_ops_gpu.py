@@ -75,6 +75,28 @@ def test_conv_transpose_via_bwd_data(ops):
     assert rel(y, ref) < 1e-5
 
 
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-5), ("tf32", 1e-3), ("bf16", 1e-2)])
+def test_conv_transpose_s1_gemm_col2im(ops, prec, tol):
+    """Stride-1 Conv2DTranspose forward as a 1x1 GEMM into tap columns + overlap-add (wdg_col2im)."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for (N, H, W, cin, cout, k, p) in [(2, 10, 13, 160, 16, 5, 2), (1, 7, 9, 64, 6, 3, 1)]:
+        x = torch.randn((N, H, W, cin), device="cuda", generator=g)
+        w = torch.randn((k, k, cout, cin), device="cuda", generator=g) * 0.1
+        ref = F.conv_transpose2d(x.double().permute(0, 3, 1, 2), w.double().permute(3, 2, 0, 1), padding=p).permute(0, 2, 3, 1)
+        wide = torch.full((N, H, W, cout + 3), 5.0, device="cuda")
+        ops.set_precision(prec)
+        try:
+            y = ops.empty(N, H, W, cout)
+            ops.conv_transpose_s1_fwd(ops.full(x), w, ops.full(y), N, H, W, p)
+            ops.conv_transpose_s1_fwd(ops.full(x), w, ops.View(wide, cout, cout + 3, 2), N, H, W, p)
+        finally:
+            ops.set_precision("fp32")
+        assert rel(y, ref) < tol
+        assert rel(wide[..., 2:2 + cout], ref) < tol and float((wide[..., :2] - 5).abs().max()) == 0
+
+
 def test_batchnorm_train(ops):
     import torch
     g = torch.Generator(device="cuda").manual_seed(3)

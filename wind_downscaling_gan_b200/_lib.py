@@ -61,6 +61,7 @@ def _declare(lib):
         "wdg_lerp_batch": [vp, vp, vp, vp, ll, ll, vp],
         "wdg_bias_act": [vp, i, i, vp, ll, i, f, vp],
         "wdg_transpose01": [vp, vp, i, i, ll, vp],
+        "wdg_col2im": [vp, vp, i, i, i, i, i, i, i, i, i, vp],
         "wdg_bn_train_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, ll, i, f, f, vp, vp],
         "wdg_bn_infer": [vp, vp, vp, vp, vp, vp, ll, i, f, vp, vp],
         "wdg_bn_finalize_apply": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, ll, i, f, f, vp],

@@ -42,7 +42,10 @@ class Conv:
         Ho, Wo = self.out_hw(H, W)
         cout = self.w.shape[2] if self.T else self.w.shape[3]
         y = out if out is not None else full(ops.empty(N, Ho, Wo, cout))
-        if self.T:   # forward of the transposed conv = backward-data of the conv (conv input dims = our output dims)
+        if self.T and self.stride == 1 and self.w.shape[0] > 1 and xv.C >= 64:
+            # wide input, many taps (generator: 5x5 over 160 channels): 1x1 GEMM + overlap-add instead of a tap gather
+            ops.conv_transpose_s1_fwd(xv, self.w, y, N, H, W, self.pad)
+        elif self.T:   # forward of the transposed conv = backward-data of the conv (conv input dims = our output dims)
             ops.conv2d_bwd_data(xv, self.w, y, N, Ho, Wo, self.stride, self.pad, H, W)
         else:
             ops.conv2d_fwd(xv, self.w, None, y, N, H, W, self.stride, self.pad, Ho, Wo)

@@ -238,6 +238,18 @@ def bias_act(xv, bias, alpha=1.0):
     _lib.check(_lib.lib().wdg_bias_act(_p(xv.t), xv.cs, xv.co, _p(bias), xv.rows, xv.C, alpha, _s()))
 
 
+def conv_transpose_s1_fwd(xv, w, yv, N, H, W, pad):
+    """Stride-1 Conv2DTranspose forward as one 1x1 GEMM into per-pixel tap columns + overlap-add (wdg_col2im): the wide
+    input is read once instead of once per tap.  w: (kh, kw, out, in); xv: view with `in` channels; yv: `out` channels."""
+    kh, kw, cout, cin = w.shape
+    wmat = empty(cin, kh * kw * cout)                       # [in][(ky, kx, out)]
+    _lib.check(_lib.lib().wdg_transpose01(_p(w), _p(wmat), kh * kw * cout, cin, 1, _s()))
+    nb = N * H * W * kh * kw * cout * 4
+    cols = scratch(nb, "col2im")[:nb].view(F32).view(N, H, W, kh * kw * cout)
+    conv2d_fwd(xv, wmat.view(1, 1, cin, kh * kw * cout), None, full(cols), N, H, W, 1, 0, H, W)
+    _lib.check(_lib.lib().wdg_col2im(_p(cols), _p(yv.t), N, H, W, kh, kw, cout, pad, yv.cs, yv.co, _s()))
+
+
 def transpose01(x):
     """[A][B][...] -> [B][A][...] (new tensor)."""
     A, B = x.shape[0], x.shape[1]
