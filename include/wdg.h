@@ -133,7 +133,7 @@ int wdg_stitch(const float* pred_dev, const int* starts_x_dev, int nx, const int
 void wdg_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 int wdg_noise_normal(float* out_dev, long long n, float stddev, uint64_t seed, uint64_t offset, void* stream);
 
-/* ---- fp32 building blocks of the WGAN training step (ganbase.py:21-94): critic forward/backward, training-mode
+/* ---- building blocks of the WGAN training step (ganbase.py:21-94): critic forward/backward, training-mode
  * generator, optimiser.  Channels-last fp32 device tensors; `*_cs` / `*_co` = channel stride / offset of a tensor
  * inside a wider (concatenated) buffer.  geo[16] = {N, H, W, Ci, kh, kw, Co, stride, pad_top, pad_left, Ho, Wo,
  * x_cs, x_co, y_cs, y_co}; weights are HWIO (a Conv2DTranspose kernel (kh,kw,out,in) is the HWIO kernel of the

@@ -347,7 +347,8 @@ struct TcWgrad {
   // Both operands are contiguous along their ROW index in memory (A: ci, B: co) while a 16-byte smem chunk holds G
   // consecutive k (pixels) of ONE row, so the loaders transpose in registers.  Vector form (channel counts and views
   // multiples of 4): a thread loads float4 = 4 consecutive rows for each of the G pixels of its chunk and writes 4
-  // chunks (G LDG.128 per 4 chunks); scalar form: 4 G LDG.32 per 4 chunks, lanes walking the rows.
+  // chunks (G LDG.128 per 4 chunks); scalar form: 4 G LDG.32 per 4 chunks, lanes walking the rows.  Which one runs
+  // is decided per layer from measurements (wdg_tc_conv2d_bwd_weight below).
   template <int OP, int BN>
   struct Loaders {
     static constexpr int G = OpT<OP>::G;

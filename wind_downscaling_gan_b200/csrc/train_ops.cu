@@ -1,10 +1,9 @@
-// fp32 building blocks of the WGAN training step (critic forward/backward, training-mode generator, optimiser):
-// convolution forward / backward-data / backward-weight as implicit GEMMs on CUDA cores, normalisation layers,
-// ConvLSTM gate math, bilinear resize and its adjoint, reductions, Adam, spectral normalisation.
-//
-// These are the first, correctness-oriented kernels of SURVEY.md §8 rows A14-A16 (the inference path uses the
-// tcgen05 kernels in conv_umma.cuh / halo_conv.cuh).  All tensors are fp32 channels-last; `cs`/`co` arguments are
-// the channel stride / offset of a tensor inside a wider (concatenated) buffer.
+// Building blocks of the WGAN training step (critic forward/backward, training-mode
+// generator, optimiser): the C ABI of the training path, the exact fp32 convolution GEMMs on CUDA cores (forward /
+// backward-data / backward-weight; the tcgen05 tf32 / bf16 versions live in train_gemm_tc.cu and are selected by
+// wdg_train_set_precision), normalisation layers, ConvLSTM gate math and the fused small-filter cell, bilinear resize
+// and its adjoint, overlap-add, column sums, Adam, spectral normalisation.  All tensors are fp32 channels-last;
+// `cs`/`co` arguments are the channel stride / offset of a tensor inside a wider (concatenated) buffer.
 #include <cuda_runtime.h>
 
 #include <stdint.h>

@@ -1,6 +1,8 @@
 """`GAN` with the reference's constructor / compile / call / train_step / test_step / weight-I/O surface
 (`gan/ganbase.py`).  Inference (`call`, `.generator.predict`) runs the bf16 tcgen05 path; `train_step` /
-`test_step` run the fp32 training kernels (train/nets.py).  There is no autograd / PyTorch math fallback.
+`test_step` run the training kernels (train/nets.py: fp32 tensors; convolution GEMMs in fp32 on CUDA cores by default,
+tf32 / bf16 on tcgen05 with `compile(..., train_precision="tf32")` or `train.ops.set_precision`).  There is no
+autograd / PyTorch math fallback.
 """
 import os
 from pathlib import Path
@@ -22,6 +24,9 @@ class GAN:
     def compile(self, generator_optimizer, discriminator_optimizer, generator_loss=None, generator_metrics=None,
                 discriminator_loss=None, **kwargs):
         self.metrics = list(kwargs.get("metrics") or [])
+        if kwargs.get("train_precision"):          # extension: arithmetic of the training convolution GEMMs
+            from ..train import ops as _train_ops
+            _train_ops.set_precision(kwargs["train_precision"])
         self.generator.compile(generator_optimizer, generator_loss, metrics=generator_metrics)
         if self.discriminator is not None:
             self.discriminator.compile(discriminator_optimizer, discriminator_loss)

@@ -1,4 +1,5 @@
-"""Training-path generator and critic: explicit forward / backward over the fp32 kernels of train/ops.py.
+"""Training-path generator and critic: explicit forward / backward over the kernels of train/ops.py (fp32 tensors;
+convolution GEMMs in the precision selected by `ops.set_precision`).
 
 Graphs follow the reference's `make_generator` / `make_discriminator` (`gan/models.py:9-142`) in TRAINING mode:
 SpectralNormalization performs one in-place power iteration per call (TFA 0.14), BatchNormalization uses batch

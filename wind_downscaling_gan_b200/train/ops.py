@@ -1,4 +1,4 @@
-"""Python wrappers of the training kernels (include/wdg.h, "fp32 building blocks").  Tensors are contiguous fp32
+"""Python wrappers of the training kernels (include/wdg.h, "building blocks of the WGAN training step").  Tensors are contiguous fp32
 CUDA torch tensors used as raw device buffers; `View` addresses a channel slice of a wider channels-last buffer."""
 import ctypes as C
 
