@@ -305,7 +305,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint32_t pk[8] = {pack_bf16x2(v[0], v[1]),   pack_bf16x2(v[2], v[3]),   pack_bf16x2(v[4], v[5]),
                                     pack_bf16x2(v[6], v[7]),   pack_bf16x2(v[8], v[9]),   pack_bf16x2(v[10], v[11]),
                                     pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])};
-            st_global_v8(reinterpret_cast<__nv_bfloat16*>(e.out) + (((long long)img * S + Y) * S + X) * 16, pk);
+            st_global_v8(reinterpret_cast<__nv_bfloat16*>(e.out) + (long long)img * e.out_sn + (long long)Y * e.out_sy + X * 16, pk);
           }
         }
       } else {

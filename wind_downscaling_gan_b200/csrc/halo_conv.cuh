@@ -21,20 +21,26 @@
 
 namespace wdg {
 
-enum { HEPI_UPCONV = 0, HEPI_AFFINE = 1 };
+enum { HEPI_UPCONV = 0, HEPI_AFFINE = 1, HEPI_FINAL = 2 };
 
 struct HaloParams {
   int num_passes;        // ceil(total flat positions / 256)
   int n_img;             // images
   int pw, ph;            // flat positions per image = pw * ph (row pitch pw)
   int tap_shift[16];     // row shift of each tap
+  int box_rows;          // rows per A TMA box (two boxes per chunk; <= H_BOX_ROWS): 2 * box_rows >= 256 + max tap shift
+  unsigned char kmask[16];   // per tap: bit k set = the k-th 16-element K slice of the tap has non-zero weights (issue its MMA)
   const float* bias;     // [BN] (HEPI_UPCONV: [16])
   const float* scale;
   const float* shift;
   // ---- HEPI_UPCONV: anchors of the fused bilinear x2 + 5x5 transposed conv
   int S;                 // high-res size
   const float* delta;    // fp32 border corrections [n][S][192]
-  __nv_bfloat16* out;    // [n][S][S][16]
+  __nv_bfloat16* out;    // pixel (n, Y, X) channel c at out + n*up_sn + Y*up_sy + X*16 + c
+  long long up_sn, up_sy;
+  // ---- HEPI_FINAL: 3x3 conv 16 -> 2 over "super-pixels" (4 pixels x 16 channels = one 128-byte row); GEMM columns
+  //      0..7 = (pixel in super-pixel, output channel); fp32 out[n][S][S][2], bias[2]
+  float* outf;
   // ---- HEPI_AFFINE: valid outputs are (y < vh, x < vw); v = leaky(acc + bias) * scale + shift -> bf16, two destinations
   int vw, vh;
   __nv_bfloat16* out1;
@@ -109,9 +115,9 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int c = 0; c < NCHUNK; ++c) {
         mbar_wait(&a_empty[ab], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&a_full[ab], H_A_BYTES);
+          mbar_arrive_expect_tx(&a_full[ab], 2 * p.box_rows * 128);
           tma_load_2d(smA + ab * H_A_BYTES, &tmA, &a_full[ab], c * 64, f0);
-          tma_load_2d(smA + ab * H_A_BYTES + H_BOX_ROWS * 128, &tmA, &a_full[ab], c * 64, f0 + H_BOX_ROWS);
+          tma_load_2d(smA + ab * H_A_BYTES + p.box_rows * 128, &tmA, &a_full[ab], c * 64, f0 + p.box_rows);
         }
         __syncwarp();
         if (++ab == H_ABUFS) { ab = 0; phase ^= 1; }
@@ -157,13 +163,15 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < TPS; ++j) {
               const int tap = g * TPS + j;
               const uint32_t shift_rows = (uint32_t)p.tap_shift[tap];
+              const uint32_t kmask = p.kmask[tap];
+              const int first_k = __ffs((int)kmask) - 1;     // the first MMA of a tile overwrites the accumulator
               const uint64_t db = b_desc0 + (uint64_t)(j * BN * 8);                          // BN rows * 128 B >> 4
 #pragma unroll
               for (int t = 0; t < H_TILES; ++t) {
                 const uint64_t da = a_desc0 + (uint64_t)((t * TILE_M + shift_rows) * 8);     // rows * 128 B >> 4
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16(d_tmem + t * BN, da + 2 * k, db + 2 * k, idesc, (c | tap | k) ? 1u : 0u);
+                  if (kmask & (1u << k)) umma_bf16(d_tmem + t * BN, da + 2 * k, db + 2 * k, idesc, (c | tap) ? 1u : (k != first_k ? 1u : 0u));
               }
             }
             umma_commit(&b_empty[stage]);
@@ -236,8 +244,21 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint32_t pk[8] = {pack_bf16x2(v[0], v[1]),   pack_bf16x2(v[2], v[3]),   pack_bf16x2(v[4], v[5]),
                                       pack_bf16x2(v[6], v[7]),   pack_bf16x2(v[8], v[9]),   pack_bf16x2(v[10], v[11]),
                                       pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])};
-              st_global_v8(p.out + (((long long)img * S + Y) * S + X) * 16, pk);
+              st_global_v8(p.out + (long long)img * p.up_sn + (long long)Y * p.up_sy + X * 16, pk);
             }
+          }
+        } else if constexpr (EPI == HEPI_FINAL) {
+          static_assert(EPI != HEPI_FINAL || BN == 16, "FINAL expects 4 pixels x 2 channels (+ 8 padding columns)");
+          uint32_t r[16];
+          tmem_ld16(taddr, r);
+          tmem_ld_wait();
+          if (arow && pr < p.S && ps < (p.S >> 2)) {
+            const float b0 = __ldg(p.bias), b1 = __ldg(p.bias + 1);
+            float4* o = reinterpret_cast<float4*>(p.outf + (((long long)img * p.S + pr) * p.S + 4 * ps) * 2);
+            o[0] = make_float4(__uint_as_float(r[0]) + b0, __uint_as_float(r[1]) + b1, __uint_as_float(r[2]) + b0,
+                               __uint_as_float(r[3]) + b1);
+            o[1] = make_float4(__uint_as_float(r[4]) + b0, __uint_as_float(r[5]) + b1, __uint_as_float(r[6]) + b0,
+                               __uint_as_float(r[7]) + b1);
           }
         } else {
           const bool valid = arow && pr < p.vh && ps < p.vw;

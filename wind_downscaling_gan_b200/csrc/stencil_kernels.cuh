@@ -111,8 +111,8 @@ struct FinalConvW {
 
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(128)
-final_conv3x3_kernel(const __nv_bfloat16* __restrict__ in, const __grid_constant__ FinalConvW<CIN, COUT> W,
-                     float* __restrict__ out, long long npix, int S) {
+final_conv3x3_kernel(const __nv_bfloat16* __restrict__ in, long long in_sn, long long in_sy,
+                     const __grid_constant__ FinalConvW<CIN, COUT> W, float* __restrict__ out, long long npix, int S) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
   const int x = (int)(i % S);
@@ -129,7 +129,7 @@ final_conv3x3_kernel(const __nv_bfloat16* __restrict__ in, const __grid_constant
     for (int dx = 0; dx < 3; ++dx) {
       const int xx = x + dx - 1;
       if (xx < 0 || xx >= S) continue;
-      const uint4* p = reinterpret_cast<const uint4*>(in + ((n * S + yy) * S + xx) * CIN);
+      const uint4* p = reinterpret_cast<const uint4*>(in + n * in_sn + yy * in_sy + (long long)xx * CIN);
 #pragma unroll
       for (int c8 = 0; c8 < CIN; c8 += 8) {
         const uint4 v = __ldg(p + c8 / 8);

@@ -116,9 +116,10 @@ struct Plan {
   ConvLaunch L0, L2, L5, L7, LE, L9;
   std::vector<ConvLaunch> LS;  // one per timestep
   bool use_halo = false;       // halo-reuse kernels (halo_conv.cuh) for the 8x8 s2 conv and the fused upsample conv
-  CUtensorMap hA, hB, h0A, h0B;
-  HaloParams hp, h0p;
-  int hgrid = 0, h0grid = 0;
+  CUtensorMap hA, hB, h0A, h0B, h11A, h11B;
+  HaloParams hp, h0p, h11p;
+  int hgrid = 0, h0grid = 0, h11grid = 0;
+  bool use_halo11 = false;     // final 3x3 conv on the tensor cores (super-pixel form)
   int launches = 0;
 };
 
@@ -132,7 +133,7 @@ struct wdg_generator {
   std::map<std::string, bool> set_;
   bool finalized = false;
   // packed device weights
-  __nv_bfloat16 *B0 = nullptr, *B2 = nullptr, *BL = nullptr, *B5 = nullptr, *B7 = nullptr, *B9 = nullptr, *B9h = nullptr, *BE = nullptr;
+  __nv_bfloat16 *B0 = nullptr, *B2 = nullptr, *BL = nullptr, *B5 = nullptr, *B7 = nullptr, *B9 = nullptr, *B9h = nullptr, *BE = nullptr, *B11 = nullptr;
   float* fparams = nullptr;  // all fp32 per-column vectors, see offsets
   float *bias0, *sc0, *sh0, *bias2, *sc2, *sh2, *biasL, *bias5, *sc5, *sh5, *bias7, *sc7, *sh7, *bias9, *sc9, *sh9,
       *w11, *b11;
@@ -206,7 +207,7 @@ extern "C" void wdg_generator_destroy(wdg_generator* g) {
   }
   if (g->copy_in) cudaStreamDestroy(g->copy_in);
   if (g->copy_out) cudaStreamDestroy(g->copy_out);
-  cudaFree(g->B0); cudaFree(g->B2); cudaFree(g->BL); cudaFree(g->B5); cudaFree(g->B7); cudaFree(g->B9); cudaFree(g->B9h); cudaFree(g->BE);
+  cudaFree(g->B0); cudaFree(g->B2); cudaFree(g->BL); cudaFree(g->B5); cudaFree(g->B7); cudaFree(g->B9); cudaFree(g->B9h); cudaFree(g->BE); cudaFree(g->B11);
   cudaFree(g->fparams);
   delete g;
 }
@@ -360,6 +361,21 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
           }
           return (float)(0.25 * v);
         })) return 1;
+    // Final 3x3 conv (16 -> 2) in super-pixel form: one GEMM row = 4 horizontally adjacent pixels x 16 channels (one
+    // 128-byte row of the padded g9 image), K-block = super-tap (dy, dsx) with dsx in {-1, 0, +1} super-pixels, GEMM
+    // column n = (output pixel po, output channel o) for n < 8; weight of input pixel pi / channel c:
+    // w[dy][kx][c][o] with kx = 4 (dsx - 1) + pi - po + 1 when that lies in 0..2, else 0.
+    {
+      const auto& w11 = W(11, "layer/kernel");   // [3][3][16][2]
+      if (F / 8 != 16 || g->cout != 2) return fail("final conv kernel expects 16 -> 2 channels");
+      if (upload_B(&g->B11, 16, 9, [&](int n, int kb, int j) {
+            if (n >= 8) return 0.f;
+            const int po = n / 2, o = n % 2, dy = kb / 3, dsx = kb % 3, pi = j / 16, c = j % 16;
+            const int kx = 4 * (dsx - 1) + pi - po + 1;
+            if (kx < 0 || kx > 2) return 0.f;
+            return w11[((size_t)(dy * 3 + kx) * 16 + c) * 2 + o];
+          })) return 1;
+    }
   }
   // ---- fp32 per-column vectors
   std::vector<float> fp;
@@ -440,7 +456,7 @@ static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
   L.catp = take(N * (S2 + 4) * (S2 + 4) * CATP_PITCH * 2 + 4096);
   L.edgeE = take(N * 4 * (S + 8) * (F / 4 + 128) * 2);
   L.deltaD = take(N * S * 192 * 4);
-  L.g9 = take(N * S * S * (F / 8) * 2);
+  L.g9 = take(N * (S + 2) * (S + 8) * (F / 8) * 2);   // zero ring: 1 row above/below, one 4-pixel super-pixel left/right
   L.total = o;
   return L;
 }
@@ -545,8 +561,8 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       HaloParams& h = pl.h0p;
       std::memset(&h, 0, sizeof h);
       h.num_passes = (int)((flat + H_TILES * TILE_M - 1) / (H_TILES * TILE_M));
-      h.n_img = (int)N; h.pw = (int)Q; h.ph = (int)Q;
-      for (int tap = 0; tap < 8; ++tap) h.tap_shift[tap] = (tap / 2) * (int)Q + 2 * (tap % 2);
+      h.n_img = (int)N; h.pw = (int)Q; h.ph = (int)Q; h.box_rows = H_BOX_ROWS;
+      for (int tap = 0; tap < 8; ++tap) { h.tap_shift[tap] = (tap / 2) * (int)Q + 2 * (tap % 2); h.kmask[tap] = 0xF; }
       h.bias = g->bias0; h.scale = g->sc0; h.shift = g->sh0;
       h.vw = (int)S2; h.vh = (int)S2;
       h.out1 = pl.catp + (2 * PW + 2) * CI + F / 4; h.o1_sn = PW * PW * CI; h.o1_sy = PW * CI; h.o1_sx = CI;
@@ -719,7 +735,9 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       }
     EpiParams& e = c.p.ep;
     std::memset(&e, 0, sizeof e);
-    e.bias = g->bias9; e.scale = g->sc9; e.shift = g->sh9; e.out = pl.g9;
+    const long long G9C = F / 8, G9X = S + 8, G9Y = S + 2;      // padded g9 image [G9Y][G9X][G9C], interior at (1, 4)
+    e.bias = g->bias9; e.scale = g->sc9; e.shift = g->sh9; e.out = pl.g9 + (G9X + 4) * G9C;
+    e.out_sn = G9Y * G9X * G9C; e.out_sy = G9X * G9C;
     e.up_pw = (int)PW; e.up_ph = (int)PW; e.up_S = (int)S; e.up_delta = pl.deltaD;
     c.bn = 64; c.epi = EPI_UPCONV; c.grid = grid_for(c.p);
     // halo-reuse variant (halo_conv.cuh): needs 256 + 3*PW + 3 <= 416 rows of shared memory
@@ -733,10 +751,39 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       HaloParams& h = pl.hp;
       std::memset(&h, 0, sizeof h);
       h.num_passes = (int)((flat + H_TILES * TILE_M - 1) / (H_TILES * TILE_M));
-      h.n_img = (int)N; h.pw = (int)PW; h.ph = (int)PW; h.S = (int)S; h.delta = pl.deltaD;
-      for (int tap = 0; tap < 16; ++tap) h.tap_shift[tap] = (tap / 4) * (int)PW + tap % 4;
-      h.bias = g->bias9; h.scale = g->sc9; h.shift = g->sh9; h.out = pl.g9;
+      h.n_img = (int)N; h.pw = (int)PW; h.ph = (int)PW; h.S = (int)S; h.delta = pl.deltaD; h.box_rows = H_BOX_ROWS;
+      for (int tap = 0; tap < 16; ++tap) { h.tap_shift[tap] = (tap / 4) * (int)PW + tap % 4; h.kmask[tap] = 0xF; }
+      h.bias = g->bias9; h.scale = g->sc9; h.shift = g->sh9; h.out = pl.g9 + (G9X + 4) * G9C;
+      h.up_sn = G9Y * G9X * G9C; h.up_sy = G9X * G9C;
       pl.hgrid = h.num_passes < sms ? h.num_passes : sms;
+    }
+    // ---------------- L11: final 3x3 conv on the tensor cores, super-pixel form (halo_conv.cuh, HEPI_FINAL)
+    const long long SPW = G9X / 4;                              // super-pixels per padded row
+    pl.use_halo11 = G9C == 16 && (2 * SPW + 2 + H_TILES * TILE_M) <= (long long)H_ROWS && !getenv("WDG_NO_HALO11");
+    if (pl.use_halo11) {
+      const uint64_t rows = N * G9Y * SPW;
+      uint64_t ad[2] = {64, rows};
+      uint64_t as_[1] = {64};
+      // only 256 + 2 SPW + 2 rows are needed per pass: two boxes of half that (rounded up to 8 rows) instead of 2 x 208
+      const uint32_t box11 = (uint32_t)(((H_TILES * TILE_M + 2 * SPW + 2 + 1) / 2 + 7) / 8 * 8);
+      uint32_t ab[2] = {64, box11};
+      if (make_tmap(&pl.h11A, pl.g9, 2, ad, as_, ab, 128)) return 1;
+      uint64_t b11d[2] = {9 * 64, 16};
+      uint64_t b11s[1] = {9 * 64};
+      uint32_t b11b[2] = {64, 16};
+      if (make_tmap(&pl.h11B, g->B11, 2, b11d, b11s, b11b, 128)) return 1;
+      HaloParams& h = pl.h11p;
+      std::memset(&h, 0, sizeof h);
+      h.num_passes = (int)((rows + H_TILES * TILE_M - 1) / (H_TILES * TILE_M));
+      h.n_img = (int)N; h.pw = (int)SPW; h.ph = (int)G9Y; h.S = (int)S; h.box_rows = (int)box11;
+      // K slice k of a super-tap = input pixel k of the super-pixel: the left neighbour only contributes its last pixel,
+      // the right neighbour its first one (all other weights are structural zeros: their MMAs are skipped)
+      for (int tap = 0; tap < 9; ++tap) {
+        h.tap_shift[tap] = (tap / 3) * (int)SPW + tap % 3;
+        h.kmask[tap] = tap % 3 == 0 ? 0x8 : (tap % 3 == 1 ? 0xF : 0x1);
+      }
+      h.bias = g->b11;
+      pl.h11grid = h.num_passes < sms ? h.num_passes : sms;
     }
   }
   pl.B = B; pl.T = T;
@@ -845,7 +892,19 @@ static int run_plan(wdg_generator* g, const Plan& pl, const float* image_dev, co
     CK(cudaGetLastError());
   } else if (launch_conv(pl.L9, stream)) return 1;
   mark();
-  final_conv3x3_kernel<16, 2><<<(unsigned)((npix + 127) / 128), 128, 0, stream>>>(pl.g9, g->w11h, out_dev, npix, (int)S);
+  if (pl.use_halo11) {
+    auto kern = halo_conv_kernel<16, 1, 9, 3, HEPI_FINAL>;
+    constexpr int smem = HaloCfg<16, 1, 3>::SMEM;
+    static bool attr11 = false;
+    if (!attr11) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr11 = true; }
+    HaloParams hp = pl.h11p;
+    hp.outf = out_dev;
+    kern<<<pl.h11grid, 224, smem, stream>>>(pl.h11A, pl.h11B, hp);
+  } else {
+    const long long G9C = g->F / 8, G9X = S + 8, G9Y = S + 2;
+    final_conv3x3_kernel<16, 2><<<(unsigned)((npix + 127) / 128), 128, 0, stream>>>(pl.g9 + (G9X + 4) * G9C, G9Y * G9X * G9C,
+                                                                                  G9X * G9C, g->w11h, out_dev, npix, (int)S);
+  }
   CK(cudaGetLastError());
   mark();
   return 0;
@@ -989,7 +1048,7 @@ extern "C" int wdg_generator_debug_read(const wdg_generator* g, int which, float
     case 2: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = pl.hseq; break;
     case 3: H = W = (int)S4; C = (int)(F / 2); sx = C; sy = S4 * sx; sn = S4 * sy; src = pl.g5; break;
     case 4: H = W = (int)S2; C = (int)(F / 4); sx = CATP_PITCH; sy = (S2 + 4) * sx; sn = (S2 + 4) * sy; src = pl.catp + 2 * sy + 2 * sx; break;
-    case 5: H = W = (int)S; C = (int)(F / 8); sx = C; sy = S * sx; sn = S * sy; src = pl.g9; break;
+    case 5: H = W = (int)S; C = (int)(F / 8); sx = C; sy = (S + 8) * sx; sn = (S + 2) * sy; src = pl.g9 + sy + 4 * sx; break;
     default: return fail("unknown intermediate");
   }
   const long long total = N * H * W * C;
