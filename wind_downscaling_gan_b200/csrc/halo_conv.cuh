@@ -39,7 +39,8 @@ struct HaloParams {
   __nv_bfloat16* out;    // pixel (n, Y, X) channel c at out + n*up_sn + Y*up_sy + X*16 + c
   long long up_sn, up_sy;
   // ---- HEPI_FINAL: 3x3 conv 16 -> 2 over "super-pixels" (4 pixels x 16 channels = one 128-byte row); GEMM columns
-  //      0..7 = (pixel in super-pixel, output channel); fp32 out[n][S][S][2], bias[2]
+  //      0..7 = (pixel in super-pixel, output channel), 8..15 = the same with the bf16 residual of the weights;
+  //      fp32 out[n][S][S][2], bias[2]
   float* outf;
   // ---- HEPI_AFFINE: valid outputs are (y < vh, x < vw); v = leaky(acc + bias) * scale + shift -> bf16, two destinations
   int vw, vh;
@@ -255,10 +256,11 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (arow && pr < p.S && ps < (p.S >> 2)) {
             const float b0 = __ldg(p.bias), b1 = __ldg(p.bias + 1);
             float4* o = reinterpret_cast<float4*>(p.outf + (((long long)img * p.S + pr) * p.S + 4 * ps) * 2);
-            o[0] = make_float4(__uint_as_float(r[0]) + b0, __uint_as_float(r[1]) + b1, __uint_as_float(r[2]) + b0,
-                               __uint_as_float(r[3]) + b1);
-            o[1] = make_float4(__uint_as_float(r[4]) + b0, __uint_as_float(r[5]) + b1, __uint_as_float(r[6]) + b0,
-                               __uint_as_float(r[7]) + b1);
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(r[j + 8]);   // bf16 weights + their residual
+            o[0] = make_float4(v[0] + b0, v[1] + b1, v[2] + b0, v[3] + b1);
+            o[1] = make_float4(v[4] + b0, v[5] + b1, v[6] + b0, v[7] + b1);
           }
         } else {
           const bool valid = arow && pr < p.vh && ps < p.vw;

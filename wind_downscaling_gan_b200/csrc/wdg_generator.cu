@@ -368,12 +368,14 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
     {
       const auto& w11 = W(11, "layer/kernel");   // [3][3][16][2]
       if (F / 8 != 16 || g->cout != 2) return fail("final conv kernel expects 16 -> 2 channels");
+      // columns 8..15 carry the bf16 residual of the same weights (w - bf16(w)); the epilogue adds the two halves, so the
+      // output layer sees its weights to ~16 bits at no extra MMA (N = 16 is the minimum tile width anyway)
       if (upload_B(&g->B11, 16, 9, [&](int n, int kb, int j) {
-            if (n >= 8) return 0.f;
-            const int po = n / 2, o = n % 2, dy = kb / 3, dsx = kb % 3, pi = j / 16, c = j % 16;
+            const int po = (n % 8) / 2, o = n % 2, dy = kb / 3, dsx = kb % 3, pi = j / 16, c = j % 16;
             const int kx = 4 * (dsx - 1) + pi - po + 1;
             if (kx < 0 || kx > 2) return 0.f;
-            return w11[((size_t)(dy * 3 + kx) * 16 + c) * 2 + o];
+            const float w = w11[((size_t)(dy * 3 + kx) * 16 + c) * 2 + o];
+            return n < 8 ? w : w - __bfloat162float(tobf(w));
           })) return 1;
     }
   }
