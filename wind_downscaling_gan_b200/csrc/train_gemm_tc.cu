@@ -101,9 +101,7 @@ struct TapGatherA {
     x0[i] = x;
     base[i] = valid ? img + ((long long)y * s.Ws + x) * s.cs : img;
   }
-  __device__ __forceinline__ void load(uint32_t tile, int tid, const TapK& k) const {
-    const int j = tid & 7, r0 = tid >> 3;
-    float v[4][G];
+  __device__ __forceinline__ void fetch(const TapK& k, float (&v)[4][G]) const {
     if (s.vec && k.c + G <= s.C) {
       const int dy = s.sgn * k.ty, dx = s.sgn * k.tx;
       const long long off = ((long long)dy * s.Ws + dx) * s.cs + k.c;
@@ -138,8 +136,16 @@ struct TapGatherA {
         w.advance(1, s.C, s.ntx);
       }
     }
+  }
+  __device__ __forceinline__ void store(uint32_t tile, int tid, const float (&v)[4][G]) const {
+    const int j = tid & 7, r0 = tid >> 3;
 #pragma unroll
     for (int i = 0; i < 4; ++i) store_chunk<OP>(tile, r0 + 32 * i, j, v[i]);
+  }
+  __device__ __forceinline__ void load(uint32_t tile, int tid, const TapK& k) const {
+    float v[4][G];
+    fetch(k, v);
+    store(tile, tid, v);
   }
 };
 
@@ -232,6 +238,7 @@ struct TcFwd {
   __device__ long long K() const { return (long long)g.kh * g.kw * g.Ci; }
 
   static constexpr bool TMA_B = true;
+  static constexpr bool PAIR = true;    // loaders offer fetch / store (two K blocks in flight)
   __device__ float B(long long k, int n) const { return w[k * g.Co + n]; }
   template <int OP, int BN>
   struct Loaders {
@@ -254,6 +261,12 @@ struct TcFwd {
       a.load(a_tile, tid, k);
       k.advance(8 * OpT<OP>::G, a.s.C, a.s.ntx);
     }
+    // split form: the kernel keeps the gathers of TWO K blocks in flight before the first shared-memory store
+    __device__ __forceinline__ void fetch(float (&v)[4][OpT<OP>::G]) {
+      a.fetch(k, v);
+      k.advance(8 * OpT<OP>::G, a.s.C, a.s.ntx);
+    }
+    __device__ __forceinline__ void store(uint32_t a_tile, int tid, const float (&v)[4][OpT<OP>::G]) const { a.store(a_tile, tid, v); }
   };
   __device__ __forceinline__ void store16(long long m, int n, const uint32_t (&r)[16], int) const {
     float* q = y + m * g.y_cs + g.y_co + n;
@@ -286,6 +299,7 @@ struct TcBwdData {
   __device__ long long K() const { return (long long)c.Jy * c.Jx * g.Co; }
 
   static constexpr bool TMA_B = true;
+  static constexpr bool PAIR = true;    // loaders offer fetch / store (two K blocks in flight)
   // B(k = (jy, jx, co), n = ci) = w[((ry + s jy) * kw + rx + s jx) * Ci + ci][co]
   __device__ float B(long long k, int n) const {
     const int co = (int)(k % g.Co), t = (int)(k / g.Co), jx = t % c.Jx, jy = t / c.Jx;
@@ -315,6 +329,11 @@ struct TcBwdData {
       a.load(a_tile, tid, k);
       k.advance(8 * G, a.s.C, a.s.ntx);
     }
+    __device__ __forceinline__ void fetch(float (&v)[4][G]) {
+      a.fetch(k, v);
+      k.advance(8 * G, a.s.C, a.s.ntx);
+    }
+    __device__ __forceinline__ void store(uint32_t a_tile, int tid, const float (&v)[4][G]) const { a.store(a_tile, tid, v); }
   };
   __device__ __forceinline__ void store16(long long m, int n, const uint32_t (&r)[16], int) const {
     const int b = (int)(m % c.Wc), a = (int)((m / c.Wc) % c.Hc), img = (int)(m / ((long long)c.Wc * c.Hc));
@@ -343,6 +362,7 @@ struct TcWgrad {
   __device__ int Nn() const { return g.Co; }
   __device__ long long K() const { return (long long)g.N * g.Ho * g.Wo; }
   static constexpr bool TMA_B = false;
+  static constexpr bool PAIR = false;
 
   // Both operands are contiguous along their ROW index in memory (A: ci, B: co) while a 16-byte smem chunk holds G
   // consecutive k (pixels) of ONE row, so the loaders transpose in registers.  Vector form (channel counts and views
@@ -558,12 +578,38 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const P p, int n
       typename P::template Loaders<OP, BN> ld(p, m0, n0, k_begin, k_end, tid);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        ld.load(smem_u32(smA + stage * A_STAGE_BYTES), smem_u32(smB + stage * Cfg::B_STAGE_BYTES), tid);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-        mbar_arrive(&full_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      if constexpr (P::PAIR && OP == OP_TF32 && STAGES >= 3) {
+        // tf32 chunks are 16 source bytes: one K block keeps only 4 x 16 B per thread in flight and the loop is bound by
+        // the L2 round trip, so two K blocks are gathered back to back (8 x 16 B in flight) before the first store
+        for (int kb = 0; kb < num_kb; kb += 2) {
+          const bool two = kb + 1 < num_kb;
+          int stage2 = stage + 1;
+          uint32_t phase2 = phase;
+          if (stage2 == STAGES) { stage2 = 0; phase2 ^= 1; }
+          float v0[4][OpT<OP>::G], v1[4][OpT<OP>::G];
+          ld.fetch(v0);
+          if (two) ld.fetch(v1);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          ld.store(smem_u32(smA + stage * A_STAGE_BYTES), tid, v0);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(&full_bar[stage]);
+          if (two) {
+            mbar_wait(&empty_bar[stage2], phase2 ^ 1);
+            ld.store(smem_u32(smA + stage2 * A_STAGE_BYTES), tid, v1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&full_bar[stage2]);
+            stage = stage2; phase = phase2;
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      } else {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          ld.load(smem_u32(smA + stage * A_STAGE_BYTES), smem_u32(smB + stage * Cfg::B_STAGE_BYTES), tid);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+          mbar_arrive(&full_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
     if (num_kb > 0) {
