@@ -58,10 +58,14 @@ __global__ void edge_lines_kernel(const __nv_bfloat16* __restrict__ catp, __nv_b
   if (i >= total) return;
   const int groups = C / 8;
   const int P = 2 * h + 8;
-  const int g = (int)(i % groups);
-  const int p = (int)((i / groups) % P);
-  const int edge = (int)((i / ((long long)groups * P)) % 4);
-  const long long n = i / ((long long)groups * P * 4);
+  // one 64-bit division for the image index, 32-bit arithmetic below it (the kernel is index-math bound)
+  const unsigned per_img = (unsigned)groups * P * 4;
+  const long long n = i / per_img;
+  const unsigned r = (unsigned)(i - n * per_img);
+  const int g = (int)(r % groups);
+  const unsigned pe = r / groups;
+  const int p = (int)(pe % P);
+  const int edge = (int)(pe / P);
   const int j = p - 4;
   const int PW = h + 4;
   const __nv_bfloat16* img = catp + n * (long long)PW * PW * pitch + g * 8;
