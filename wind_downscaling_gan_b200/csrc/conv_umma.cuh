@@ -52,8 +52,9 @@ struct EpiParams {
   const float* up_delta;             // fp32 border corrections [n][S][4 edges * 48]
   // ---- EPI_LSTM (BN = 256 = 4 gates x 64 channels per N tile)
   float* c_state;                    // fp32 [n][H][W][F], updated in place
-  __nv_bfloat16* h_out;              // bf16, pixel (n,y,x) channel c at n*h_sn + h_off + (y*W+x)*F + c
+  __nv_bfloat16* h_out;              // bf16, pixel (n,y,x) channel c at n*h_sn + h_off + (y*h_pitch+x)*F + c
   long long h_sn, h_off;
+  int h_pitch;                       // pixels per row of the (zero-ring padded) h image
   int first_step;                    // c_{t-1} = 0: skip the state read
   int F;
 };
@@ -352,7 +353,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint32_t pk[8] = {pack_bf16x2(hn[0], hn[1]),   pack_bf16x2(hn[2], hn[3]),   pack_bf16x2(hn[4], hn[5]),
                                     pack_bf16x2(hn[6], hn[7]),   pack_bf16x2(hn[8], hn[9]),   pack_bf16x2(hn[10], hn[11]),
                                     pack_bf16x2(hn[12], hn[13]), pack_bf16x2(hn[14], hn[15])};
-            st_global_v8(e.h_out + (long long)n * e.h_sn + e.h_off + ((long long)y * p.W + x) * e.F + ch0, pk);
+            st_global_v8(e.h_out + (long long)n * e.h_sn + e.h_off + ((long long)y * e.h_pitch + x) * e.F + ch0, pk);
           }
         }
       }

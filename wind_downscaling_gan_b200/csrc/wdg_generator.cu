@@ -116,10 +116,11 @@ struct Plan {
   ConvLaunch L0, L2, L5, L7, LE, L9;
   std::vector<ConvLaunch> LS;  // one per timestep
   bool use_halo = false;       // halo-reuse kernels (halo_conv.cuh) for the 8x8 s2 conv and the fused upsample conv
-  CUtensorMap hA, hB, h0A, h0B, h11A, h11B;
-  HaloParams hp, h0p, h11p;
-  int hgrid = 0, h0grid = 0, h11grid = 0;
+  CUtensorMap hA, hB, h0A, h0B, h11A, h11B, h5A, h5B;
+  HaloParams hp, h0p, h11p, h5p;
+  int hgrid = 0, h0grid = 0, h11grid = 0, h5grid = 0;
   bool use_halo11 = false;     // final 3x3 conv on the tensor cores (super-pixel form)
+  bool use_halo5 = false;      // 3x3 conv on the (zero-ring padded) hidden-state sequence with halo reuse
   int launches = 0;
 };
 
@@ -133,7 +134,7 @@ struct wdg_generator {
   std::map<std::string, bool> set_;
   bool finalized = false;
   // packed device weights
-  __nv_bfloat16 *B0 = nullptr, *B2 = nullptr, *BL = nullptr, *B5 = nullptr, *B7 = nullptr, *B9 = nullptr, *B9h = nullptr, *BE = nullptr, *B11 = nullptr;
+  __nv_bfloat16 *B0 = nullptr, *B2 = nullptr, *BL = nullptr, *B5 = nullptr, *B7 = nullptr, *B9 = nullptr, *B9h = nullptr, *BE = nullptr, *B11 = nullptr, *B5h = nullptr;
   float* fparams = nullptr;  // all fp32 per-column vectors, see offsets
   float *bias0, *sc0, *sh0, *bias2, *sc2, *sh2, *biasL, *bias5, *sc5, *sh5, *bias7, *sc7, *sh7, *bias9, *sc9, *sh9,
       *w11, *b11;
@@ -207,7 +208,7 @@ extern "C" void wdg_generator_destroy(wdg_generator* g) {
   }
   if (g->copy_in) cudaStreamDestroy(g->copy_in);
   if (g->copy_out) cudaStreamDestroy(g->copy_out);
-  cudaFree(g->B0); cudaFree(g->B2); cudaFree(g->BL); cudaFree(g->B5); cudaFree(g->B7); cudaFree(g->B9); cudaFree(g->B9h); cudaFree(g->BE); cudaFree(g->B11);
+  cudaFree(g->B0); cudaFree(g->B2); cudaFree(g->BL); cudaFree(g->B5); cudaFree(g->B7); cudaFree(g->B9); cudaFree(g->B9h); cudaFree(g->BE); cudaFree(g->B11); cudaFree(g->B5h);
   cudaFree(g->fparams);
   delete g;
 }
@@ -306,6 +307,11 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
     const auto& w = W(5, "layer/w");  // [3][3][128][64]
     if (upload_B(&g->B5, F / 2, 18, [&](int n, int kb, int j) {
           const int tap = kb / 2, c = (kb % 2) * 64 + j;
+          return w[((size_t)tap * F + c) * (F / 2) + n];
+        })) return 1;
+    // halo kernel: K-block = chunk * 9 + tap
+    if (upload_B(&g->B5h, F / 2, 18, [&](int n, int kb, int j) {
+          const int tap = kb % 9, c = (kb / 9) * 64 + j;
           return w[((size_t)tap * F + c) * (F / 2) + n];
         })) return 1;
   }
@@ -452,7 +458,7 @@ static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return r; };
   L.xpad = take(N * (S + 6) * (S + 6) * g->CP * 2 + 1024);   // s2d image [N][(S+6)/2][(S+6)/2][4*CP] (+ window slack)
   L.res4 = take(N * S4 * S4 * F * 2);
-  L.hseq = take(N * S4 * S4 * F * 2);
+  L.hseq = take(N * (S4 + 2) * (S4 + 2) * F * 2);   // zero ring 1 (halo form of the 3x3 conv)
   L.cstate = take((size_t)B * S4 * S4 * F * 4);
   L.g5 = take(N * S4 * S4 * (F / 2) * 2);
   L.catp = take(N * (S2 + 4) * (S2 + 4) * CATP_PITCH * 2 + 4096);
@@ -605,7 +611,10 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
     uint64_t str[4] = {F, S4 * F, S4 * S4 * F, (uint64_t)T * S4 * S4 * F};
     uint32_t box[5] = {64, 8, 8, 1, 2};
     if (make_tmap(&tmX, pl.res4, 5, dims, str, box, 128)) return 1;
-    if (make_tmap(&tmH, pl.hseq, 5, dims, str, box, 128)) return 1;
+    // hseq images carry a zero ring of 1 pixel: same logical dims, padded strides, base at the interior origin
+    const uint64_t SP = S4 + 2;
+    uint64_t strh[4] = {F, SP * F, SP * SP * F, (uint64_t)T * SP * SP * F};
+    if (make_tmap(&tmH, pl.hseq + (SP + 1) * F, 5, dims, strh, box, 128)) return 1;
     uint64_t bd[2] = {36 * 64, 4 * F};
     uint64_t bs[1] = {36 * 64};
     uint32_t bb[2] = {64, 256};
@@ -626,8 +635,8 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       }
       EpiParams& e = c.p.ep;
       std::memset(&e, 0, sizeof e);
-      e.bias = g->biasL; e.c_state = pl.cstate; e.h_out = pl.hseq;
-      e.h_sn = (long long)T * S4 * S4 * F; e.h_off = (long long)t * S4 * S4 * F;
+      e.bias = g->biasL; e.c_state = pl.cstate; e.h_out = pl.hseq + (SP + 1) * F;
+      e.h_sn = (long long)T * SP * SP * F; e.h_off = (long long)t * SP * SP * F; e.h_pitch = (int)SP;
       e.first_step = t == 0; e.F = (int)F;
       c.bn = 256; c.epi = EPI_LSTM; c.grid = grid_for(c.p);
     }
@@ -636,10 +645,11 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
   {
     ConvLaunch& c = pl.L5;
     std::memset(&c.p, 0, sizeof c.p);
+    const uint64_t SP = S4 + 2;
     uint64_t dims[5] = {F, S4, S4, N, 1};
-    uint64_t str[4] = {F, S4 * F, S4 * S4 * F, N * S4 * S4 * F};
+    uint64_t str[4] = {F, SP * F, SP * SP * F, N * SP * SP * F};
     uint32_t box[5] = {64, 8, 8, 2, 1};
-    if (make_tmap(&c.tmA[0], pl.hseq, 5, dims, str, box, 128)) return 1;
+    if (make_tmap(&c.tmA[0], pl.hseq + (SP + 1) * F, 5, dims, str, box, 128)) return 1;
     c.tmA[1] = c.tmA[0]; c.tmA[2] = c.tmA[0];
     uint64_t bd[2] = {18 * 64, F / 2};
     uint64_t bs[1] = {18 * 64};
@@ -654,6 +664,27 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
     }
     affine_epi(c.p.ep, g->bias5, g->sc5, g->sh5, pl.g5, (long long)S4 * S4 * (F / 2), (long long)S4 * (F / 2), F / 2, 0, 1);
     c.bn = 64; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
+    // halo-reuse variant: flat positions of the padded hseq images (pitch SP), tap (dy, dx) = rows + dy*SP + dx
+    pl.use_halo5 = F == 128 && (2 * SP + 2 + H_TILES * TILE_M) <= (uint64_t)H_ROWS && !getenv("WDG_NO_HALO5");
+    if (pl.use_halo5) {
+      const uint64_t rows = N * SP * SP;
+      const uint32_t box5 = (uint32_t)(((H_TILES * TILE_M + 2 * SP + 2 + 1) / 2 + 7) / 8 * 8);
+      uint64_t ad[2] = {F, rows};
+      uint64_t as_[1] = {F};
+      uint32_t ab[2] = {64, box5};
+      if (make_tmap(&pl.h5A, pl.hseq, 2, ad, as_, ab, 128)) return 1;
+      if (make_tmap(&pl.h5B, g->B5h, 2, bd, bs, bb, 128)) return 1;
+      HaloParams& h = pl.h5p;
+      std::memset(&h, 0, sizeof h);
+      h.num_passes = (int)((rows + H_TILES * TILE_M - 1) / (H_TILES * TILE_M));
+      h.n_img = (int)N; h.pw = (int)SP; h.ph = (int)SP; h.box_rows = (int)box5;
+      for (int tap = 0; tap < 9; ++tap) { h.tap_shift[tap] = (tap / 3) * (int)SP + tap % 3; h.kmask[tap] = 0xF; }
+      h.bias = g->bias5; h.scale = g->sc5; h.shift = g->sh5;
+      h.vw = (int)S4; h.vh = (int)S4;
+      h.out1 = pl.g5; h.o1_sn = (long long)S4 * S4 * (F / 2); h.o1_sy = (long long)S4 * (F / 2); h.o1_sx = F / 2;
+      h.out2 = nullptr;
+      pl.h5grid = h.num_passes < sms ? h.num_passes : sms;
+    }
   }
   // ---------------- L7: ConvT 2x2 s2 on concat(g5, res4) -> g7 [N][S2][S2][32] (pixel shuffle)
   {
@@ -873,7 +904,14 @@ static int run_plan(wdg_generator* g, const Plan& pl, const float* image_dev, co
   for (int t = 0; t < pl.T; ++t)
     if (launch_conv(pl.LS[t], stream)) return 1;
   mark();
-  if (launch_conv(pl.L5, stream)) return 1;
+  if (pl.use_halo5) {
+    auto kern = halo_conv_kernel<64, 2, 9, 3, HEPI_AFFINE>;
+    constexpr int smem = HaloCfg<64, 2, 3>::SMEM;
+    static bool attr5 = false;
+    if (!attr5) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr5 = true; }
+    kern<<<pl.h5grid, 224, smem, stream>>>(pl.h5A, pl.h5B, pl.h5p);
+    CK(cudaGetLastError());
+  } else if (launch_conv(pl.L5, stream)) return 1;
   mark();
   if (launch_conv(pl.L7, stream)) return 1;
   mark();
@@ -1047,7 +1085,7 @@ extern "C" int wdg_generator_debug_read(const wdg_generator* g, int which, float
   switch (which) {
     case 0: H = W = (int)S2; C = 128; sx = CATP_PITCH; sy = (S2 + 4) * sx; sn = (S2 + 4) * sy; src = pl.catp + 2 * sy + 2 * sx + F / 4; break;
     case 1: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = pl.res4; break;
-    case 2: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = pl.hseq; break;
+    case 2: H = W = (int)S4; C = (int)F; sx = F; sy = (S4 + 2) * F; sn = (S4 + 2) * sy; src = pl.hseq + sy + sx; break;
     case 3: H = W = (int)S4; C = (int)(F / 2); sx = C; sy = S4 * sx; sn = S4 * sy; src = pl.g5; break;
     case 4: H = W = (int)S2; C = (int)(F / 4); sx = CATP_PITCH; sy = (S2 + 4) * sx; sn = (S2 + 4) * sy; src = pl.catp + 2 * sy + 2 * sx; break;
     case 5: H = W = (int)S; C = (int)(F / 8); sx = C; sy = (S + 8) * sx; sn = (S + 2) * sy; src = pl.g9 + sy + 4 * sx; break;
