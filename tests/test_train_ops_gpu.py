@@ -20,7 +20,10 @@ def ops():
 
 
 @pytest.mark.parametrize("N,H,W,Ci,k,Co,s,p", [(3, 13, 11, 5, 3, 7, 1, 1), (2, 38, 38, 23, 8, 40, 2, 3), (2, 34, 34, 32, 7, 64, 3, 1),
-                                               (2, 12, 12, 16, 4, 24, 2, 1), (1, 9, 9, 70, 6, 66, 11, 4), (2, 16, 16, 130, 1, 33, 1, 0)])
+                                               (2, 12, 12, 16, 4, 24, 2, 1), (1, 9, 9, 70, 6, 66, 11, 4), (2, 16, 16, 130, 1, 33, 1, 0),
+                                               # narrow 3x3 / stride-1 / same layers: direct stencil kernels (train_direct.cuh)
+                                               (1, 20, 17, 2, 3, 8, 1, 1), (2, 11, 13, 2, 3, 16, 1, 1), (1, 37, 12, 16, 3, 2, 1, 1),
+                                               (3, 33, 35, 2, 3, 8, 1, 1), (1, 16, 16, 5, 3, 64, 1, 1)])
 def test_conv_fwd_bwd(ops, N, H, W, Ci, k, Co, s, p):
     import torch
     import torch.nn.functional as F

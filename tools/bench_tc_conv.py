@@ -18,6 +18,8 @@ LAYERS = [
     ("G5 conv3x3 128->64", 192, 24, 24, 128, 3, 64, 1, 1),
     ("G8 convT5x5 160->16 (as conv 16->160)", 192, 96, 96, 16, 5, 160, 1, 2),
     ("G9 conv3x3 16->2", 192, 96, 96, 16, 3, 2, 1, 1),
+    ("D lstm2 x-conv 2->8", 192, 96, 96, 2, 3, 8, 1, 1),
+    ("D conv 2->16", 192, 96, 96, 2, 3, 16, 1, 1),
     ("D lstm16 x-conv 5->64", 192, 96, 96, 5, 3, 64, 1, 1),
     ("D lstm16 h-conv 16->64 (1 step)", 8, 96, 96, 16, 3, 64, 1, 1),
     ("D conv 16->16", 192, 96, 96, 16, 3, 16, 1, 1),

@@ -7,10 +7,12 @@
 #include <cuda_runtime.h>
 
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <string>
 
 #include "../../include/wdg.h"
+#include "train_direct.cuh"
 #include "train_geo.cuh"
 
 namespace {
@@ -971,8 +973,68 @@ extern "C" int wdg_train_set_precision(int mode) {
 }
 extern "C" int wdg_train_get_precision(void) { return g_train_precision; }
 
+// ---- direct kernels for narrow 3x3 / stride-1 / same convolutions (train_direct.cuh); WDG_NO_DIRECT=1 disables them
+// Which (Ci, Co) pairs use them was decided per GEMM kind from measurements at 192 x 96 x 96 (tools/bench_tc_conv.py,
+// ms direct vs tcgen05 tf32): forward 2->8 0.046 / 0.270, 2->16 0.128 / 0.264 (16->2 0.484 / 0.363: not used);
+// backward-data 2->8 0.136 / 0.328, 16->2 0.123 / 0.298 (2->16 0.483 / 0.396: not used); backward-weight 2->8
+// 0.239 / 0.469, 2->16 0.354 / 0.558 (16->2 0.991 / 0.613: not used).  5->64 and 16->16 lose everywhere (FMA-bound).
+#define WDG_DIRECT_PAIRS(X) X(2, 8) X(2, 16) X(16, 2)
+enum { DIRECT_FWD = 0, DIRECT_BWD_DATA = 1, DIRECT_BWD_WEIGHT = 2 };
+static bool direct_ok(const ConvGeo& g, int kind) {
+  static int off = -1;
+  if (off < 0) off = getenv("WDG_NO_DIRECT") ? 1 : 0;
+  if (off || g.kh != 3 || g.kw != 3 || g.stride != 1 || g.pad_t != 1 || g.pad_l != 1 || g.Ho != g.H || g.Wo != g.W) return false;
+  if (g.Ci == 2 && g.Co == 8) return true;
+  if (g.Ci == 2 && g.Co == 16) return kind != DIRECT_BWD_DATA;
+  if (g.Ci == 16 && g.Co == 2) return kind == DIRECT_BWD_DATA;
+  return false;
+}
+static int direct_fwd(const ConvGeo& g, const float* x, const float* w, const float* bias, float* y, int accumulate, cudaStream_t st) {
+  const long long npix = (long long)g.N * g.H * g.W;
+#define X(ci, co)                                                                                                            \
+  if (g.Ci == ci && g.Co == co)                                                                                              \
+    wdg_direct::conv3x3_fwd_kernel<ci, co><<<blocks_for(npix), 256, 0, st>>>(x, g.x_cs, g.x_co, w, bias, y, g.y_cs, g.y_co, npix, \
+                                                                            g.H, g.W, accumulate);
+  WDG_DIRECT_PAIRS(X)
+#undef X
+  CKT(cudaGetLastError());
+  return 0;
+}
+static int direct_bwd_data(const ConvGeo& g, const float* dy, const float* w, float* dx, int accumulate, cudaStream_t st) {
+  const long long npix = (long long)g.N * g.H * g.W;
+#define X(ci, co)                                                                                                              \
+  if (g.Ci == ci && g.Co == co)                                                                                                \
+    wdg_direct::conv3x3_bwd_data_kernel<ci, co><<<blocks_for(npix), 256, 0, st>>>(dy, g.y_cs, g.y_co, w, dx, g.x_cs, g.x_co, npix, \
+                                                                                 g.H, g.W, accumulate);
+  WDG_DIRECT_PAIRS(X)
+#undef X
+  CKT(cudaGetLastError());
+  return 0;
+}
+static long long direct_slabs(const ConvGeo& g) {
+  const long long npix = (long long)g.N * g.H * g.W;
+  long long slabs = (npix + 1023) / 1024;
+  if (slabs > 592) slabs = 592;
+  return slabs < 1 ? 1 : slabs;
+}
+static int direct_bwd_weight(const ConvGeo& g, const float* x, const float* dy, float* dw, float* part, int accumulate, cudaStream_t st) {
+  const long long npix = (long long)g.N * g.H * g.W, slabs = direct_slabs(g), per = (npix + slabs - 1) / slabs;
+#define X(ci, co)                                                                                                            \
+  if (g.Ci == ci && g.Co == co)                                                                                              \
+    wdg_direct::conv3x3_bwd_weight_kernel<ci, co><<<(unsigned)slabs, 256, 0, st>>>(x, g.x_cs, g.x_co, dy, g.y_cs, g.y_co, part, \
+                                                                                  npix, g.H, g.W, per);
+  WDG_DIRECT_PAIRS(X)
+#undef X
+  CKT(cudaGetLastError());
+  const long long n = 9ll * g.Ci * g.Co;
+  reduce_splits_kernel<<<blocks_for(n), 256, 0, st>>>(part, dw, n, (int)slabs, accumulate);
+  CKT(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int wdg_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, const int* geo, int accumulate,
                               void* stream) {
+  if (direct_ok(make_geo(geo), DIRECT_FWD)) return direct_fwd(make_geo(geo), x, w, bias, y, accumulate, (cudaStream_t)stream);
   if (g_train_precision) return wdg_tc_conv2d_fwd(make_geo(geo), x, w, bias, y, accumulate, g_train_precision, (cudaStream_t)stream);
   FwdProblem p{make_geo(geo), x, w, bias, y, accumulate};
   const long long M = (long long)p.g.N * p.g.Ho * p.g.Wo;
@@ -982,6 +1044,7 @@ extern "C" int wdg_conv2d_fwd(const float* x, const float* w, const float* bias,
 
 extern "C" int wdg_conv2d_bwd_data(const float* dy, const float* w, float* dx, const int* geo, int accumulate, void* stream) {
   const ConvGeo gg = make_geo(geo);
+  if (direct_ok(gg, DIRECT_BWD_DATA)) return direct_bwd_data(gg, dy, w, dx, accumulate, (cudaStream_t)stream);
   if (g_train_precision) return wdg_tc_conv2d_bwd_data(gg, dy, w, dx, accumulate, g_train_precision, (cudaStream_t)stream);
   if (gg.stride > 1 && gg.kh >= gg.stride && gg.kw >= gg.stride) {
     const int s = gg.stride;
@@ -1007,6 +1070,12 @@ extern "C" int wdg_conv2d_bwd_data(const float* dy, const float* w, float* dx, c
 extern "C" int wdg_conv2d_bwd_weight_scratch(const int* geo, size_t* bytes, int* splits_out) {
   const ConvGeo g = make_geo(geo);
   const long long M = (long long)g.kh * g.kw * g.Ci, K = (long long)g.N * g.Ho * g.Wo;
+  if (direct_ok(g, DIRECT_BWD_WEIGHT)) {
+    const long long sl = direct_slabs(g);
+    if (splits_out) *splits_out = (int)sl;
+    if (bytes) *bytes = (size_t)(sl * M * g.Co * sizeof(float));
+    return 0;
+  }
   if (g_train_precision) {
     int sp; long long kps;
     wdg_tc_wgrad_plan(g, g_train_precision, &sp, &kps);
@@ -1029,6 +1098,7 @@ extern "C" int wdg_conv2d_bwd_weight(const float* x, const float* dy, float* dw,
   cudaStream_t stream = (cudaStream_t)stream_;
   int splits = 1;
   wdg_conv2d_bwd_weight_scratch(geo, nullptr, &splits);
+  if (direct_ok(make_geo(geo), DIRECT_BWD_WEIGHT)) return direct_bwd_weight(make_geo(geo), x, dy, dw, (float*)scratch, accumulate, stream);
   BwdWeightProblem p{make_geo(geo), x, dy, (float*)scratch, 0};
   const long long M = (long long)p.g.kh * p.g.kw * p.g.Ci, K = (long long)p.g.N * p.g.Ho * p.g.Wo;
   p.k_per_split = (int)((K + splits - 1) / splits);
