@@ -78,3 +78,27 @@ def test_grid_dataset_npz_roundtrip(tmp_path):
     back = GridDataset.from_npz(tmp_path / "a.npz")
     assert np.array_equal(back["u10"], era["u10"]) and back.var_dims("v10") == ("time", "latitude", "longitude")
     assert np.array_equal(back.coords["time"], era.coords["time"])
+
+
+def test_gan_compile_selects_training_precision():
+    """GAN.compile(..., train_precision=...) is an extension over ganbase.py:115-124: it selects the arithmetic of the
+    training convolution GEMMs (process-wide setting of the C ABI, wdg_train_set_precision)."""
+    import pytest
+    from wind_downscaling_gan_b200.gan.ganbase import GAN
+    from wind_downscaling_gan_b200.train import ops
+
+    class Stub:
+        def compile(self, *a, **k):
+            self.args = (a, k)
+
+    gan = GAN(Stub(), Stub(), noise_generator=None)
+    try:
+        gan.compile(generator_optimizer="g", discriminator_optimizer="d", train_precision="tf32")
+        assert ops.get_precision() == "tf32"
+        gan.compile(generator_optimizer="g", discriminator_optimizer="d", train_precision="bf16")
+        assert ops.get_precision() == "bf16"
+        with pytest.raises(KeyError):
+            gan.compile(generator_optimizer="g", discriminator_optimizer="d", train_precision="fp8")
+    finally:
+        ops.set_precision("fp32")
+    assert ops.get_precision() == "fp32"

@@ -25,7 +25,7 @@ def conv_table():
     by = {}
     for r in rows:
         by.setdefault(r["layer"], {})[r["prec"]] = r
-    out = ["# r1 — training convolution GEMMs per layer shape (B200, `python tools/bench_tc_conv.py`, CUDA events, 5 reps)\n",
+    out = ["# r1 — training convolution GEMMs per layer shape (B200, `python tools/bench_tc_conv.py`, CUDA events, 10 reps)\n",
            "Layer shapes of one WGAN step at B=8, T=24 (192 images; '1 step' rows: the 8 images of one ConvLSTM timestep).",
            "fp32 = CUDA-core implicit GEMM (`train_ops.cu`); tf32 / bf16 = tcgen05 implicit GEMM (`train_gemm_tc.cu`), fp32 accumulate.",
            "Numbers are TFLOP/s of the dense convolution FLOPs (2·N·Ho·Wo·k²·Ci·Co); tf32 ms in the last column.\n",
