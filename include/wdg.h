@@ -144,6 +144,9 @@ int wdg_noise_normal(float* out_dev, long long n, float stddev, uint64_t seed, u
 int wdg_train_set_precision(int mode);
 int wdg_train_get_precision(void);
 int wdg_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, const int* geo, int accumulate, void* stream);
+/* same with the LeakyReLU(alpha) of the reference's `activation=` argument fused into the epilogue (alpha = 1: linear) */
+int wdg_conv2d_fwd_act(const float* x, const float* w, const float* bias, float* y, const int* geo, int accumulate, float alpha,
+                       void* stream);
 int wdg_conv2d_bwd_data(const float* dy, const float* w, float* dx, const int* geo, int accumulate, void* stream);
 int wdg_conv2d_bwd_weight_scratch(const int* geo, size_t* bytes, int* splits);
 int wdg_conv2d_bwd_weight(const float* x, const float* dy, float* dw, const int* geo, void* scratch, int accumulate, void* stream);

@@ -51,6 +51,7 @@ def _declare(lib):
         "wdg_train_set_precision": [i],
         "wdg_train_get_precision": [],
         "wdg_conv2d_fwd": [vp, vp, vp, vp, ip, i, vp],
+        "wdg_conv2d_fwd_act": [vp, vp, vp, vp, ip, i, f, vp],
         "wdg_conv2d_bwd_data": [vp, vp, vp, ip, i, vp],
         "wdg_conv2d_bwd_weight_scratch": [ip, C.POINTER(sz), ip],
         "wdg_conv2d_bwd_weight": [vp, vp, vp, ip, vp, i, vp],

@@ -9,11 +9,11 @@
 
 namespace wdg_direct {
 
-// y[n,y,x,co] (+)= bias[co] + sum_{ky,kx,ci} x[n,y+ky-1,x+kx-1,ci] * w[ky][kx][ci][co]
+// y[n,y,x,co] = leaky_alpha((y +) bias[co] + sum_{ky,kx,ci} x[n,y+ky-1,x+kx-1,ci] * w[ky][kx][ci][co])
 template <int CI, int CO>
 __global__ void __launch_bounds__(256) conv3x3_fwd_kernel(const float* __restrict__ x, int x_cs, int x_co, const float* __restrict__ w,
                                                           const float* __restrict__ bias, float* __restrict__ y, int y_cs, int y_co,
-                                                          long long npix, int H, int W, int accumulate) {
+                                                          long long npix, int H, int W, int accumulate, float alpha) {
   __shared__ __align__(16) float sw[9 * CI * CO];
   for (int i = threadIdx.x; i < 9 * CI * CO; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -54,7 +54,10 @@ __global__ void __launch_bounds__(256) conv3x3_fwd_kernel(const float* __restric
   }
   float* yp = y + p * y_cs + y_co;
 #pragma unroll
-  for (int o = 0; o < CO; ++o) yp[o] = accumulate ? yp[o] + acc[o] : acc[o];
+  for (int o = 0; o < CO; ++o) {
+    const float v = accumulate ? yp[o] + acc[o] : acc[o];
+    yp[o] = v >= 0.f ? v : alpha * v;
+  }
 }
 
 // dx[n,iy,ix,ci] (+)= sum_{ky,kx,co} dy[n,iy+1-ky,ix+1-kx,co] * w[ky][kx][ci][co]

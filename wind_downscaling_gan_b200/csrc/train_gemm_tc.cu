@@ -232,7 +232,7 @@ struct LinearRowFastB {
 
 // ------------------------------------------------------------------------------------------------ problems
 struct TcFwd {
-  ConvGeo g; const float* x; const float* w; const float* bias; float* y; int accumulate, vec_in, vec_out;
+  ConvGeo g; const float* x; const float* w; const float* bias; float* y; int accumulate, vec_in, vec_out; float alpha;
   __device__ long long M() const { return (long long)g.N * g.Ho * g.Wo; }
   __device__ int Nn() const { return g.Co; }
   __device__ long long K() const { return (long long)g.kh * g.kw * g.Ci; }
@@ -278,6 +278,8 @@ struct TcFwd {
         if (bias) { v.x += __ldg(bias + n + 4 * i); v.y += __ldg(bias + n + 4 * i + 1); v.z += __ldg(bias + n + 4 * i + 2); v.w += __ldg(bias + n + 4 * i + 3); }
         float4* d = reinterpret_cast<float4*>(q) + i;
         if (accumulate) { const float4 o = *d; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        v.x = v.x >= 0.f ? v.x : alpha * v.x; v.y = v.y >= 0.f ? v.y : alpha * v.y;
+        v.z = v.z >= 0.f ? v.z : alpha * v.z; v.w = v.w >= 0.f ? v.w : alpha * v.w;
         *d = v;
       }
     } else {
@@ -286,7 +288,8 @@ struct TcFwd {
         if (n + e < g.Co) {
           float v = __uint_as_float(r[e]);
           if (bias) v += __ldg(bias + n + e);
-          q[e] = accumulate ? q[e] + v : v;
+          if (accumulate) v += q[e];
+          q[e] = v >= 0.f ? v : alpha * v;
         }
     }
   }
@@ -773,9 +776,9 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 
 }  // namespace
 
-int wdg_tc_conv2d_fwd(const ConvGeo& g, const float* x, const float* w, const float* bias, float* y, int accumulate, int op,
-                      cudaStream_t stream) {
-  TcFwd p{g, x, w, bias, y, accumulate, 0, 0};
+int wdg_tc_conv2d_fwd(const ConvGeo& g, const float* x, const float* w, const float* bias, float* y, int accumulate, float alpha,
+                      int op, cudaStream_t stream) {
+  TcFwd p{g, x, w, bias, y, accumulate, 0, 0, alpha};
   p.vec_in = (g.x_cs % 4 == 0) && (g.x_co % 4 == 0) && (g.Ci % 4 == 0) && al16(x);
   p.vec_out = (g.y_cs % 4 == 0) && (g.y_co % 4 == 0) && al16(y);
   const long long M = (long long)g.N * g.Ho * g.Wo, K = (long long)g.kh * g.kw * g.Ci;

@@ -42,8 +42,9 @@ static inline BwdClass make_bwd_class(const ConvGeo& g, int ry, int rx) {
 }
 
 // tcgen05 paths (train_gemm_tc.cu).  op: 1 = tf32 operands, 2 = bf16 operands; fp32 accumulation in TMEM.
-int wdg_tc_conv2d_fwd(const ConvGeo& g, const float* x, const float* w, const float* bias, float* y, int accumulate, int op,
-                      cudaStream_t stream);
+// alpha: slope of the LeakyReLU applied to the final value (1 = linear)
+int wdg_tc_conv2d_fwd(const ConvGeo& g, const float* x, const float* w, const float* bias, float* y, int accumulate, float alpha,
+                      int op, cudaStream_t stream);
 int wdg_tc_conv2d_bwd_data(const ConvGeo& g, const float* dy, const float* w, float* dx, int accumulate, int op,
                            cudaStream_t stream);
 void wdg_tc_wgrad_plan(const ConvGeo& g, int op, int* splits, long long* k_per_split);

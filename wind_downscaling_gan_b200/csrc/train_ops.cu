@@ -37,7 +37,7 @@ struct Tiles {
 };
 
 struct FwdProblem {       // y = conv(x, w) + bias
-  ConvGeo g; const float* x; const float* w; const float* bias; float* y; int accumulate;
+  ConvGeo g; const float* x; const float* w; const float* bias; float* y; int accumulate; float alpha;
   __device__ int M() const { return g.N * g.Ho * g.Wo; }
   __device__ int Nn() const { return g.Co; }
   __device__ int K() const { return g.kh * g.kw * g.Ci; }
@@ -87,7 +87,8 @@ struct FwdProblem {       // y = conv(x, w) + bias
   __device__ void store(int m, int n, float v) const {
     float* q = y + (long long)m * g.y_cs + g.y_co + n;
     if (bias) v += bias[n];
-    *q = accumulate ? *q + v : v;
+    if (accumulate) v += *q;
+    *q = v >= 0.f ? v : alpha * v;
   }
 };
 
@@ -989,12 +990,13 @@ static bool direct_ok(const ConvGeo& g, int kind) {
   if (g.Ci == 16 && g.Co == 2) return kind == DIRECT_BWD_DATA;
   return false;
 }
-static int direct_fwd(const ConvGeo& g, const float* x, const float* w, const float* bias, float* y, int accumulate, cudaStream_t st) {
+static int direct_fwd(const ConvGeo& g, const float* x, const float* w, const float* bias, float* y, int accumulate, float alpha,
+                      cudaStream_t st) {
   const long long npix = (long long)g.N * g.H * g.W;
 #define X(ci, co)                                                                                                            \
   if (g.Ci == ci && g.Co == co)                                                                                              \
     wdg_direct::conv3x3_fwd_kernel<ci, co><<<blocks_for(npix), 256, 0, st>>>(x, g.x_cs, g.x_co, w, bias, y, g.y_cs, g.y_co, npix, \
-                                                                            g.H, g.W, accumulate);
+                                                                            g.H, g.W, accumulate, alpha);
   WDG_DIRECT_PAIRS(X)
 #undef X
   CKT(cudaGetLastError());
@@ -1032,14 +1034,19 @@ static int direct_bwd_weight(const ConvGeo& g, const float* x, const float* dy, 
   return 0;
 }
 
-extern "C" int wdg_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, const int* geo, int accumulate,
-                              void* stream) {
-  if (direct_ok(make_geo(geo), DIRECT_FWD)) return direct_fwd(make_geo(geo), x, w, bias, y, accumulate, (cudaStream_t)stream);
-  if (g_train_precision) return wdg_tc_conv2d_fwd(make_geo(geo), x, w, bias, y, accumulate, g_train_precision, (cudaStream_t)stream);
-  FwdProblem p{make_geo(geo), x, w, bias, y, accumulate};
+extern "C" int wdg_conv2d_fwd_act(const float* x, const float* w, const float* bias, float* y, const int* geo, int accumulate,
+                                  float alpha, void* stream) {
+  if (direct_ok(make_geo(geo), DIRECT_FWD)) return direct_fwd(make_geo(geo), x, w, bias, y, accumulate, alpha, (cudaStream_t)stream);
+  if (g_train_precision)
+    return wdg_tc_conv2d_fwd(make_geo(geo), x, w, bias, y, accumulate, alpha, g_train_precision, (cudaStream_t)stream);
+  FwdProblem p{make_geo(geo), x, w, bias, y, accumulate, alpha};
   const long long M = (long long)p.g.N * p.g.Ho * p.g.Wo;
   CKT(launch_gemm(p, M, p.g.Co, (cudaStream_t)stream));
   return 0;
+}
+extern "C" int wdg_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, const int* geo, int accumulate,
+                              void* stream) {
+  return wdg_conv2d_fwd_act(x, w, bias, y, geo, accumulate, 1.f, stream);
 }
 
 extern "C" int wdg_conv2d_bwd_data(const float* dy, const float* w, float* dx, const int* geo, int accumulate, void* stream) {

@@ -48,9 +48,10 @@ class Conv:
             ops.conv_transpose_s1_fwd(xv, self.w, y, N, H, W, self.pad)
         elif self.T:   # forward of the transposed conv = backward-data of the conv (conv input dims = our output dims)
             ops.conv2d_bwd_data(xv, self.w, y, N, Ho, Wo, self.stride, self.pad, H, W)
-        else:
-            ops.conv2d_fwd(xv, self.w, None, y, N, H, W, self.stride, self.pad, Ho, Wo)
-        ops.bias_act(y, self.b, ALPHA if self.leaky else 1.0)
+        else:             # bias + LeakyReLU fused into the GEMM epilogue
+            ops.conv2d_fwd(xv, self.w, self.b, y, N, H, W, self.stride, self.pad, Ho, Wo, alpha=ALPHA if self.leaky else 1.0)
+        if self.T:
+            ops.bias_act(y, self.b, ALPHA if self.leaky else 1.0)
         self.ctx = (xv, N, H, W, Ho, Wo, y)
         return y
 

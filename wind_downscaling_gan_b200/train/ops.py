@@ -83,10 +83,11 @@ def conv_out(n, k, s, pad_lo, pad_hi):
     return (n + pad_lo + pad_hi - k) // s + 1
 
 
-def conv2d_fwd(xv, w, bias, yv, N, H, W, stride, pad, Ho, Wo, accumulate=False):
+def conv2d_fwd(xv, w, bias, yv, N, H, W, stride, pad, Ho, Wo, accumulate=False, alpha=1.0):
+    """y = leaky_alpha((y +) conv(x, w) + bias); alpha = 1: linear."""
     kh, kw, Ci, Co = w.shape
     g = _geo(N, H, W, Ci, kh, kw, Co, stride, pad, pad, Ho, Wo, xv, yv)
-    _lib.check(_lib.lib().wdg_conv2d_fwd(_p(xv.t), _p(w), _p(bias), _p(yv.t), g, int(accumulate), _s()))
+    _lib.check(_lib.lib().wdg_conv2d_fwd_act(_p(xv.t), _p(w), _p(bias), _p(yv.t), g, int(accumulate), alpha, _s()))
 
 
 def conv2d_bwd_data(dyv, w, dxv, N, H, W, stride, pad, Ho, Wo, accumulate=False):
