@@ -166,7 +166,9 @@ int wdg_col2im(const float* cols, float* out, int N, int H, int W, int kh, int k
 int wdg_lerp_batch(float* out, const float* real, const float* fake, const float* eps, long long per_sample, long long n, void* stream);
 /* BatchNormalization (axis -1, eps, momentum): training mode uses batch statistics and updates the moving ones.
  * scratch: wdg_bn_train_fwd >= 512*max(C,32) + 2*C floats, wdg_bn_bwd_sums / wdg_bn_train_bwd >= 512*max(C,32) floats,
- * wdg_bn_infer >= C floats */
+ * wdg_bn_infer >= C floats.  act_alpha of the backward entry points (BatchNorm and LayerNorm): when x is the output of a
+ * LeakyReLU(act_alpha) -- the reference's conv -> LeakyReLU -> norm blocks -- that activation's backward is folded into
+ * the dx they write (1 = x is not an activation output) */
 int wdg_bn_train_fwd(const float* x, float* y, const float* gamma, const float* beta, float* moving_mean, float* moving_var,
                      float* save_mean, float* save_invstd, long long rows, int C, float eps, float momentum, void* scratch, void* stream);
 /* Split forms for data-parallel (synchronised) BatchNorm: per-channel sums are all-reduced by the caller */
@@ -176,16 +178,18 @@ int wdg_bn_finalize_apply(const float* x, float* y, const float* gamma, const fl
 int wdg_bn_bwd_sums(const float* dy, const float* x, const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
                     long long rows, int C, void* scratch, void* stream);
 int wdg_bn_bwd_dx(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
-                  const float* dgamma, const float* dbeta, float* dx, long long rows_local, long long rows_global, int C, void* stream);
+                  const float* dgamma, const float* dbeta, float* dx, long long rows_local, long long rows_global, int C,
+                  float act_alpha, void* stream);
 int wdg_bn_infer(const float* x, float* y, const float* gamma, const float* beta, const float* mean, const float* var,
                  long long rows, int C, float eps, void* scratch, void* stream);
 int wdg_bn_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
-                     float* dx, float* dgamma, float* dbeta, long long rows, int C, void* scratch, void* stream);
+                     float* dx, float* dgamma, float* dbeta, long long rows, int C, float act_alpha, void* scratch, void* stream);
 /* LayerNormalization over the channel axis (wdg_ln_bwd scratch >= rows*C + 512*max(C,32) floats) */
 int wdg_ln_fwd(const float* x, float* y, int y_cs, int y_co, const float* gamma, const float* beta, float* save_mean,
                float* save_invstd, long long rows, int C, float eps, void* stream);
 int wdg_ln_bwd(const float* dy, int dy_cs, int dy_co, const float* x, const float* gamma, const float* save_mean,
-               const float* save_invstd, float* dx, float* dgamma, float* dbeta, long long rows, int C, void* scratch, void* stream);
+               const float* save_invstd, float* dx, float* dgamma, float* dbeta, long long rows, int C, float act_alpha,
+               void* scratch, void* stream);
 /* ConvLSTM2D gate math (gates i, f, c~, o; hard_sigmoid / tanh), one timestep */
 int wdg_lstm_gates_fwd(float* z, const float* c_prev, float* c_out, float* h_out, long long rows, int F, void* stream);
 /* dh_rec (may be NULL): recurrent part of dL/dh_t carried from step t+1, added to dh inside the kernel */

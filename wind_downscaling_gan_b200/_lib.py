@@ -67,10 +67,10 @@ def _declare(lib):
         "wdg_bn_infer": [vp, vp, vp, vp, vp, vp, ll, i, f, vp, vp],
         "wdg_bn_finalize_apply": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, ll, i, f, f, vp],
         "wdg_bn_bwd_sums": [vp, vp, vp, vp, vp, vp, ll, i, vp, vp],
-        "wdg_bn_bwd_dx": [vp, vp, vp, vp, vp, vp, vp, vp, ll, ll, i, vp],
-        "wdg_bn_train_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, ll, i, vp, vp],
+        "wdg_bn_bwd_dx": [vp, vp, vp, vp, vp, vp, vp, vp, ll, ll, i, f, vp],
+        "wdg_bn_train_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, ll, i, f, vp, vp],
         "wdg_ln_fwd": [vp, vp, i, i, vp, vp, vp, vp, ll, i, f, vp],
-        "wdg_ln_bwd": [vp, i, i, vp, vp, vp, vp, vp, vp, vp, ll, i, vp, vp],
+        "wdg_ln_bwd": [vp, i, i, vp, vp, vp, vp, vp, vp, vp, ll, i, f, vp, vp],
         "wdg_lstm_gates_fwd": [vp, vp, vp, vp, ll, i, vp],
         "wdg_lstm_gates_bwd": [vp, vp, vp, vp, vp, vp, ll, i, vp],
         "wdg_lstm_small_fwd": [vp, vp, vp, vp, vp, vp, i, i, i, i, vp],

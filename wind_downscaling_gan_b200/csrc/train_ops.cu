@@ -517,13 +517,16 @@ __global__ void bn_finalize_kernel(const float* __restrict__ s1, const float* __
 __global__ void bn_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                               const float* __restrict__ invstd, const float* __restrict__ gamma,
                               const float* __restrict__ dbeta, const float* __restrict__ dgamma, float* __restrict__ dx,
-                              long long rows, int C, long long rows_global) {
+                              long long rows, int C, long long rows_global, float act_alpha) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * C) return;
   const int c = (int)(i % C);
-  const float xhat = (x[i] - mean[c]) * invstd[c];
+  const float xv = x[i];
+  const float xhat = (xv - mean[c]) * invstd[c];
   const float inv_r = 1.f / (float)rows_global;
-  dx[i] = gamma[c] * invstd[c] * (dy[i] - dbeta[c] * inv_r - xhat * dgamma[c] * inv_r);
+  const float d = gamma[c] * invstd[c] * (dy[i] - dbeta[c] * inv_r - xhat * dgamma[c] * inv_r);
+  // act_alpha != 1: x is the output of a LeakyReLU(act_alpha); its backward is folded in here
+  dx[i] = xv >= 0.f ? d : act_alpha * d;
 }
 
 // LayerNorm over the channel axis: LPR lanes per pixel (LPR = 4 for the critic's 16-channel full-resolution layers, so a
@@ -555,7 +558,7 @@ template <int LPR>
 __global__ void ln_bwd_kernel(const float* __restrict__ dy, int dy_cs, int dy_co, const float* __restrict__ x,
                               const float* __restrict__ gamma, const float* __restrict__ mean,
                               const float* __restrict__ invstd, float* __restrict__ dx, float* __restrict__ dy_xhat,
-                              long long rows, int C) {
+                              long long rows, int C, float act_alpha) {
   const long long r0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int lane = threadIdx.x % LPR;
   const bool ok = r0 < rows;
@@ -573,8 +576,10 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, int dy_cs, int dy_co
   s1 /= C; s2 /= C;
   for (int c = lane; c < C; c += LPR) {
     const float d = dy[r * dy_cs + dy_co + c];
-    const float xh = (x[r * C + c] - m) * is;
-    dx[r * C + c] = is * (d * gamma[c] - s1 - xh * s2);
+    const float xv = x[r * C + c];
+    const float xh = (xv - m) * is;
+    const float dd = is * (d * gamma[c] - s1 - xh * s2);
+    dx[r * C + c] = xv >= 0.f ? dd : act_alpha * dd;       // LeakyReLU backward of the layer that produced x, folded in
     dy_xhat[r * C + c] = d * xh;
   }
 }
@@ -1303,9 +1308,9 @@ extern "C" int wdg_bn_bwd_sums(const float* dy, const float* x, const float* sav
 }
 extern "C" int wdg_bn_bwd_dx(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
                              const float* dgamma, const float* dbeta, float* dx, long long rows_local, long long rows_global,
-                             int C, void* stream_) {
+                             int C, float act_alpha, void* stream_) {
   bn_bwd_kernel<<<blocks_for(rows_local * C), 256, 0, (cudaStream_t)stream_>>>(dy, x, save_mean, save_invstd, gamma, dbeta, dgamma, dx,
-                                                                              rows_local, C, rows_global);
+                                                                              rows_local, C, rows_global, act_alpha);
   CKT(cudaGetLastError());
   return 0;
 }
@@ -1324,10 +1329,10 @@ extern "C" int wdg_bn_infer(const float* x, float* y, const float* gamma, const 
 // dgamma, dbeta ([C]) and dx.  scratch >= 512*C floats.
 extern "C" int wdg_bn_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean,
                                 const float* save_invstd, float* dx, float* dgamma, float* dbeta, long long rows, int C,
-                                void* scratch, void* stream_) {
+                                float act_alpha, void* scratch, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (colsum_dual(4, dy, C, 0, x, C, 0, save_mean, save_invstd, rows, C, dgamma, dbeta, scratch, 0, stream)) return 1;
-  bn_bwd_kernel<<<blocks_for(rows * C), 256, 0, stream>>>(dy, x, save_mean, save_invstd, gamma, dbeta, dgamma, dx, rows, C, rows);
+  bn_bwd_kernel<<<blocks_for(rows * C), 256, 0, stream>>>(dy, x, save_mean, save_invstd, gamma, dbeta, dgamma, dx, rows, C, rows, act_alpha);
   CKT(cudaGetLastError());
   return 0;
 }
@@ -1347,16 +1352,16 @@ extern "C" int wdg_ln_fwd(const float* x, float* y, int y_cs, int y_co, const fl
 // dx, dgamma, dbeta.  scratch >= rows*C + 512*C floats.
 extern "C" int wdg_ln_bwd(const float* dy, int dy_cs, int dy_co, const float* x, const float* gamma, const float* save_mean,
                           const float* save_invstd, float* dx, float* dgamma, float* dbeta, long long rows, int C,
-                          void* scratch, void* stream_) {
+                          float act_alpha, void* scratch, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   float* tmp = (float*)scratch;
   float* part = tmp + rows * C;
   const int lpr = ln_lanes(C);
   const unsigned nb = blocks_for(rows * lpr);
-  if (lpr == 4) ln_bwd_kernel<4><<<nb, 256, 0, stream>>>(dy, dy_cs, dy_co, x, gamma, save_mean, save_invstd, dx, tmp, rows, C);
-  else if (lpr == 8) ln_bwd_kernel<8><<<nb, 256, 0, stream>>>(dy, dy_cs, dy_co, x, gamma, save_mean, save_invstd, dx, tmp, rows, C);
-  else if (lpr == 16) ln_bwd_kernel<16><<<nb, 256, 0, stream>>>(dy, dy_cs, dy_co, x, gamma, save_mean, save_invstd, dx, tmp, rows, C);
-  else ln_bwd_kernel<32><<<nb, 256, 0, stream>>>(dy, dy_cs, dy_co, x, gamma, save_mean, save_invstd, dx, tmp, rows, C);
+  if (lpr == 4) ln_bwd_kernel<4><<<nb, 256, 0, stream>>>(dy, dy_cs, dy_co, x, gamma, save_mean, save_invstd, dx, tmp, rows, C, act_alpha);
+  else if (lpr == 8) ln_bwd_kernel<8><<<nb, 256, 0, stream>>>(dy, dy_cs, dy_co, x, gamma, save_mean, save_invstd, dx, tmp, rows, C, act_alpha);
+  else if (lpr == 16) ln_bwd_kernel<16><<<nb, 256, 0, stream>>>(dy, dy_cs, dy_co, x, gamma, save_mean, save_invstd, dx, tmp, rows, C, act_alpha);
+  else ln_bwd_kernel<32><<<nb, 256, 0, stream>>>(dy, dy_cs, dy_co, x, gamma, save_mean, save_invstd, dx, tmp, rows, C, act_alpha);
   CKT(cudaGetLastError());
   if (wdg_colsum(0, tmp, C, 0, nullptr, 0, 0, rows, C, dgamma, part, 0, stream_)) return 1;
   if (wdg_colsum(0, dy, dy_cs, dy_co, nullptr, 0, 0, rows, C, dbeta, part, 0, stream_)) return 1;

@@ -55,11 +55,12 @@ class Conv:
         self.ctx = (xv, N, H, W, Ho, Wo, y)
         return y
 
-    def backward(self, dy, need_dx=True, dx_out=None, accumulate_dx=False, need_dw=True):
-        """dy: dense tensor [N,Ho,Wo,Cout] (modified in place by the activation backward).  Returns (dx view, dw, db)."""
+    def backward(self, dy, need_dx=True, dx_out=None, accumulate_dx=False, need_dw=True, act_done=False):
+        """dy: dense tensor [N,Ho,Wo,Cout] (modified in place by the activation backward).  Returns (dx view, dw, db).
+        act_done: the LeakyReLU backward was already folded into dy by the normalisation layer's backward."""
         xv, N, H, W, Ho, Wo, y = self.ctx
         dyv = full(dy)
-        if self.leaky:
+        if self.leaky and not act_done:
             if y.cs != y.C:
                 raise NotImplementedError("leaky backward needs a dense activation")
             ops.leaky_bwd(dy, y.t, ALPHA)
@@ -116,17 +117,18 @@ class BatchNorm:
             ops.bn_infer(x, y, g, b, mm, mv)
         return y
 
-    def backward(self, dy):
+    def backward(self, dy, act_alpha=1.0):
+        """act_alpha != 1: the input of this layer is the output of LeakyReLU(act_alpha); its backward is folded into dx."""
         C = self.x.shape[-1]
         dx = torch.empty_like(self.x)
         if self.comm is None or self.comm.world == 1:
             dg, db = ops.empty(C), ops.empty(C)
-            ops.bn_train_bwd(dy, self.x, self.w[self.names[0]], self.sm, self.si, dx, dg, db)
+            ops.bn_train_bwd(dy, self.x, self.w[self.names[0]], self.sm, self.si, dx, dg, db, act_alpha)
         else:
             sums = ops.empty(2, C)
             ops.bn_bwd_sums(dy, self.x, self.sm, self.si, sums[0], sums[1])
             self.comm.allreduce_sum(sums)
-            ops.bn_bwd_dx(dy, self.x, self.w[self.names[0]], self.sm, self.si, sums[0], sums[1], dx, self.rows_global)
+            ops.bn_bwd_dx(dy, self.x, self.w[self.names[0]], self.sm, self.si, sums[0], sums[1], dx, self.rows_global, act_alpha)
             dg, db = sums[0], sums[1]
         return dx, {self.names[0]: dg, self.names[1]: db}
 
@@ -144,10 +146,10 @@ class LayerNorm:
         ops.ln_fwd(x, y, self.w[self.names[0]], self.w[self.names[1]], self.sm, self.si)
         return y
 
-    def backward(self, dyv):
+    def backward(self, dyv, act_alpha=1.0):
         C = self.x.shape[-1]
         dx, dg, db = torch.empty_like(self.x), ops.empty(C), ops.empty(C)
-        ops.ln_bwd(dyv, self.x, self.w[self.names[0]], self.sm, self.si, dx, dg, db)
+        ops.ln_bwd(dyv, self.x, self.w[self.names[0]], self.sm, self.si, dx, dg, db, act_alpha)
         return dx, {self.names[0]: dg, self.names[1]: db}
 
 
@@ -291,9 +293,9 @@ class GenNet:
         d = dout.reshape(N, S, S, -1).contiguous().clone()
         dr9, dw, db = L["c11"].backward(d)
         put(11, "layer/kernel", "layer/bias", dw, db)
-        da9, gb = L["bn10"].backward(dr9.t)
+        da9, gb = L["bn10"].backward(dr9.t, ALPHA)
         g.update(gb)
-        dup, dw, db = L["c9"].backward(da9)
+        dup, dw, db = L["c9"].backward(da9, act_done=True)
         put(9, "layer/kernel", "layer/bias", dw, db)
         dcat9 = ops.empty(N, S2, S2, F // 4 + C2)
         ops.upsample2x_bwd(dup.t, dcat9)
@@ -301,29 +303,29 @@ class GenNet:
         ops.axpby(full(dr7), View(dcat9, F // 4, F // 4 + C2, 0))
         dr2 = ops.empty(N, S2, S2, C2)
         ops.axpby(full(dr2), View(dcat9, C2, F // 4 + C2, F // 4))
-        da7, gb = L["bn8"].backward(dr7)
+        da7, gb = L["bn8"].backward(dr7, ALPHA)
         g.update(gb)
-        dcat7, dw, db = L["c7"].backward(da7)
+        dcat7, dw, db = L["c7"].backward(da7, act_done=True)
         put(7, "layer/w", "layer/layer/bias", dw, db)
         dr5 = ops.empty(N, S4, S4, F // 2)
         ops.axpby(full(dr5), View(dcat7.t, F // 2, F // 2 + F, 0))
         dr4 = ops.empty(N, S4, S4, F)
         ops.axpby(full(dr4), View(dcat7.t, F, F // 2 + F, F // 2))
-        da5, gb = L["bn6"].backward(dr5)
+        da5, gb = L["bn6"].backward(dr5, ALPHA)
         g.update(gb)
-        dh, dw, db = L["c5"].backward(da5)
+        dh, dw, db = L["c5"].backward(da5, act_done=True)
         put(5, "layer/w", "layer/layer/bias", dw, db)
         dx, dK, dR, dbl = L["lstm"].backward(dh.t)
         g[(LW % 4) + "cell/kernel"], g[(LW % 4) + "cell/recurrent_kernel"], g[(LW % 4) + "cell/bias"] = dK, dR, dbl
         ops.axpby(full(dr4), full(dr4), 1.0, full(dx), 1.0)
-        da2, gb = L["bn3"].backward(dr4)
+        da2, gb = L["bn3"].backward(dr4, ALPHA)
         g.update(gb)
-        dr2b, dw, db = L["c2"].backward(da2)
+        dr2b, dw, db = L["c2"].backward(da2, act_done=True)
         put(2, "layer/w", "layer/layer/bias", dw, db)
         ops.axpby(full(dr2), full(dr2), 1.0, dr2b, 1.0)
-        da0, gb = L["bn1"].backward(dr2)
+        da0, gb = L["bn1"].backward(dr2, ALPHA)
         g.update(gb)
-        _, dw, db = L["c0"].backward(da0, need_dx=False)
+        _, dw, db = L["c0"].backward(da0, need_dx=False, act_done=True)
         put(0, "layer/w", "layer/layer/bias", dw, db)
         return g
 
@@ -420,17 +422,17 @@ class CriticNet:
         d = dflat
         for n in range(len(self.convs) - 1, -1, -1):
             e = self.convs[n]
-            da, gb = L["pln%d" % n].backward(full(d))
+            da, gb = L["pln%d" % n].backward(full(d), ALPHA)
             g.update(gb)
-            dxv, dw, db = L["pc%d" % n].backward(da, need_dw=nw)
+            dxv, dw, db = L["pc%d" % n].backward(da, need_dw=nw, act_done=True)
             g[(LW % e["idx"]) + "layer/w"], g[(LW % e["idx"]) + "layer/layer/bias"] = dw, db
             d = dxv.t
         # d: [N,S,S,2F] gradient of the concat(hr, mix)
         d_hr_in = ops.zeros(N, S, S, ch) if need_input_grad else None
         for tag, ln_i, conv_i, lstm_i, off in (("hr", 4, 2, 0, 0), ("mix", 5, 3, 1, F)):
-            da, gb = L["ln_" + tag].backward(View(d, F, 2 * F, off))
+            da, gb = L["ln_" + tag].backward(View(d, F, 2 * F, off), ALPHA)
             g.update(gb)
-            dh, dw, db = L["c_" + tag].backward(da, need_dw=nw)
+            dh, dw, db = L["c_" + tag].backward(da, need_dw=nw, act_done=True)
             g[(LW % conv_i) + "layer/w"], g[(LW % conv_i) + "layer/layer/bias"] = dw, db
             dx, dK, dR, dbl = L["lstm_" + tag].backward(dh.t, need_dx=need_input_grad, need_dw=nw)
             g[(LW % lstm_i) + "cell/kernel"], g[(LW % lstm_i) + "cell/recurrent_kernel"], g[(LW % lstm_i) + "cell/bias"] = dK, dR, dbl

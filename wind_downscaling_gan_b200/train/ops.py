@@ -145,12 +145,13 @@ def bn_infer(x, y, gamma, beta, mean, var, eps=1e-3):
     _lib.check(_lib.lib().wdg_bn_infer(_p(x), _p(y), _p(gamma), _p(beta), _p(mean), _p(var), x.numel() // Cc, Cc, eps, _p(sc), _s()))
 
 
-def bn_train_bwd(dy, x, gamma, save_mean, save_invstd, dx, dgamma, dbeta):
+def bn_train_bwd(dy, x, gamma, save_mean, save_invstd, dx, dgamma, dbeta, act_alpha=1.0):
+    """act_alpha != 1: x is the output of LeakyReLU(act_alpha); its backward is folded into dx."""
     Cc = x.shape[-1]
     rows = x.numel() // Cc
     sc = scratch((rows * Cc + 512 * max(Cc, 32)) * 4, "norm_bwd")
     _lib.check(_lib.lib().wdg_bn_train_bwd(_p(dy), _p(x), _p(gamma), _p(save_mean), _p(save_invstd), _p(dx), _p(dgamma), _p(dbeta),
-                                           rows, Cc, _p(sc), _s()))
+                                           rows, Cc, act_alpha, _p(sc), _s()))
 
 
 def ln_fwd(x, yv, gamma, beta, save_mean, save_invstd, eps=1e-3):
@@ -159,12 +160,12 @@ def ln_fwd(x, yv, gamma, beta, save_mean, save_invstd, eps=1e-3):
                                      x.numel() // Cc, Cc, eps, _s()))
 
 
-def ln_bwd(dyv, x, gamma, save_mean, save_invstd, dx, dgamma, dbeta):
+def ln_bwd(dyv, x, gamma, save_mean, save_invstd, dx, dgamma, dbeta, act_alpha=1.0):
     Cc = x.shape[-1]
     rows = x.numel() // Cc
     sc = scratch((rows * Cc + 512 * max(Cc, 32)) * 4, "norm_bwd")
     _lib.check(_lib.lib().wdg_ln_bwd(_p(dyv.t), dyv.cs, dyv.co, _p(x), _p(gamma), _p(save_mean), _p(save_invstd), _p(dx), _p(dgamma),
-                                     _p(dbeta), rows, Cc, _p(sc), _s()))
+                                     _p(dbeta), rows, Cc, act_alpha, _p(sc), _s()))
 
 
 def lstm_gates_fwd(z, c_prev, c_out, h_out):
@@ -272,7 +273,7 @@ def bn_bwd_sums(dy, x, save_mean, save_invstd, dgamma, dbeta):
     _lib.check(_lib.lib().wdg_bn_bwd_sums(_p(dy), _p(x), _p(save_mean), _p(save_invstd), _p(dgamma), _p(dbeta), rows, Cc, _p(sc), _s()))
 
 
-def bn_bwd_dx(dy, x, gamma, save_mean, save_invstd, dgamma, dbeta, dx, rows_global):
+def bn_bwd_dx(dy, x, gamma, save_mean, save_invstd, dgamma, dbeta, dx, rows_global, act_alpha=1.0):
     Cc = x.shape[-1]
     _lib.check(_lib.lib().wdg_bn_bwd_dx(_p(dy), _p(x), _p(gamma), _p(save_mean), _p(save_invstd), _p(dgamma), _p(dbeta), _p(dx),
-                                        x.numel() // Cc, rows_global, Cc, _s()))
+                                        x.numel() // Cc, rows_global, Cc, act_alpha, _s()))
