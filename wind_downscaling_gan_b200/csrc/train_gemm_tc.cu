@@ -756,10 +756,19 @@ int pick_bn(int N) {
   if (N <= 128) return 128;
   return (N % 256 == 0 || N > 384) ? 256 : 128;
 }
+// Without split-K (forward, backward-data) a short M axis leaves SMs idle: the generator's recurrent convolution is 36 M
+// tiles x 2 N tiles of 256 = 72 CTAs for 148 SMs, each walking 36-144 K blocks.  Narrower N tiles re-gather the (small) A
+// operand but fill the machine.
+int pick_bn_grid(int N, long long M, int splits) {
+  int bn = pick_bn(N);
+  const long long mt = (M + TILE_M - 1) / TILE_M;
+  while (bn > 32 && mt * ((N + bn - 1) / bn) * splits < 148) bn /= 2;
+  return bn;
+}
 
 template <class P, int OP>
 cudaError_t launch_bn(const P& p, long long M, int N, long long K, int splits, long long kps, cudaStream_t stream) {
-  switch (pick_bn(N)) {
+  switch (P::TMA_B ? pick_bn_grid(N, M, splits) : pick_bn(N)) {
     case 16: return launch_one<P, 16, OP>(p, M, N, K, splits, kps, stream);
     case 32: return launch_one<P, 32, OP>(p, M, N, K, splits, kps, stream);
     case 64: return launch_one<P, 64, OP>(p, M, N, K, splits, kps, stream);
