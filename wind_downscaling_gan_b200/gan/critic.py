@@ -122,7 +122,6 @@ class Critic:
 
     def __call__(self, inputs, training=False, mask=None):
         """`discriminator([low_res, high_res], training=False)` -> score (B, 1) CUDA tensor."""
-        import torch
         from ..train.nets import CriticNet, to_device
         from ..train.step import _dev
         from ..train import ops as _ops

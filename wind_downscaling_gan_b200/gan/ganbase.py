@@ -7,7 +7,6 @@ autograd / PyTorch math fallback.
 import os
 from pathlib import Path
 
-import numpy as np
 
 
 class GAN:

@@ -6,7 +6,6 @@ SpectralNormalization performs one in-place power iteration per call (TFA 0.14),
 statistics and updates its moving averages, LayerNormalization / ConvLSTM2D as in inference.  Weights are fp32 CUDA
 tensors keyed by the checkpoint variable names.  Activations are channels-last [N = B*T, H, W, C].
 """
-import math
 
 import numpy as np
 import torch
