@@ -57,6 +57,17 @@ int wdg_generator_get_weight(const wdg_generator* g, const char* name, float* ho
  * BatchNorm folded to scale/shift).  Must be called after the last set_weight and before forward. */
 int wdg_generator_finalize(wdg_generator* g);
 
+/* Operand precision of the GEMM stages (default WDG_PREC_BF16).  The reference generator is fp32
+ * (models.py:24-73); north_star's tolerances are rel-L2 <= 1e-3 for fp32/TF32 and <= 1e-2 for bf16:
+ *   WDG_PREC_BF16: bf16 activations/weights in HBM, tcgen05.mma kind::f16, fp32 accumulation and epilogue math;
+ *   WDG_PREC_TF32: fp32 activations/weights rounded to nearest tf32 by their producer, tcgen05.mma kind::tf32,
+ *                  fp32 accumulation, fp32 cell state, output 3x3 convolution in full fp32.
+ * Changing it invalidates finalize() and the bound plan (workspace_bytes depends on it). */
+#define WDG_PREC_BF16 0
+#define WDG_PREC_TF32 1
+int wdg_generator_set_precision(wdg_generator* g, int mode);
+int wdg_generator_get_precision(const wdg_generator* g);
+
 /* Workspace (activation buffers) needed for a forward of B sequences x T timesteps. */
 int wdg_generator_workspace_bytes(const wdg_generator* g, int B, int T, size_t* bytes);
 /* Binds a caller-owned device workspace of at least that size and builds the TMA descriptors /

@@ -30,6 +30,8 @@ def _declare(lib):
         "wdg_generator_set_weight": [vp, C.c_char_p, vp, i64p, i],
         "wdg_generator_get_weight": [vp, C.c_char_p, vp, C.c_int64],
         "wdg_generator_finalize": [vp],
+        "wdg_generator_set_precision": [vp, i],
+        "wdg_generator_get_precision": [vp],
         "wdg_generator_workspace_bytes": [vp, i, i, C.POINTER(sz)],
         "wdg_generator_bind": [vp, i, i, vp, sz, vp],
         "wdg_generator_forward": [vp, vp, vp, vp, vp],

@@ -35,14 +35,14 @@ struct EpiParams {
   const float* bias;
   const float* scale;
   const float* shift;
-  void* out;                         // bf16, or fp32 when out_f32
+  void* out;                         // act_t (bf16 / tf32-in-fp32), or plain fp32 when out_f32
   long long out_sn, out_sy, out_sx;  // destination element strides for (image, row, col)
   int out_c0;                        // first destination channel
   int out_mul;                       // 1; 2 = 2x2 stride-2 transposed conv (pixel shuffle by column group)
   int group_cols;                    // columns per (ky,kx) group when out_mul == 2
   int lrelu;
   int out_f32;
-  void* out2;                        // optional second bf16 destination (same values), own strides
+  void* out2;                        // optional second act_t destination (same values), own strides
   long long out2_sn, out2_sy, out2_sx;
   int out2_c0;
   // ---- EPI_UPCONV (BN = 64 = 2x2 output phases x 16 channels; GEMM rows are window anchors on the
@@ -52,7 +52,7 @@ struct EpiParams {
   const float* up_delta;             // fp32 border corrections [n][S][4 edges * 48]
   // ---- EPI_LSTM (BN = 256 = 4 gates x 64 channels per N tile)
   float* c_state;                    // fp32 [n][H][W][F], updated in place
-  __nv_bfloat16* h_out;              // bf16, pixel (n,y,x) channel c at n*h_sn + h_off + (y*h_pitch+x)*F + c
+  void* h_out;                       // act_t, pixel (n,y,x) channel c at n*h_sn + h_off + (y*h_pitch+x)*F + c
   long long h_sn, h_off;
   int h_pitch;                       // pixels per row of the (zero-ring padded) h image
   int first_step;                    // c_{t-1} = 0: skip the state read
@@ -83,12 +83,14 @@ struct ConvCfg {
 __device__ __forceinline__ float leaky02(float v) { return v >= 0.f ? v : 0.2f * v; }
 __device__ __forceinline__ float hard_sigmoid(float v) { return fminf(fmaxf(0.2f * v + 0.5f, 0.f), 1.f); }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int PREC>
 __global__ void __launch_bounds__(192, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN>;
+  using P = Prec<PREC>;
+  using act_t = typename P::act_t;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -154,7 +156,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           mbar_arrive_expect_tx(&full_bar[stage], a_bytes + Cfg::B_STAGE_BYTES);
           const CUtensorMap* tm = (k.src == 0) ? &tmA0 : ((k.src == 1) ? &tmA1 : &tmA2);
           tma_load_5d(smA + stage * A_STAGE_BYTES, tm, &full_bar[stage], b0 + k.o0, b1 + k.o1, b2 + k.o2, b3 + k.o3, b4);
-          tma_load_2d(smB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * 64, n_tile * BN);
+          tma_load_2d(smB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * P::KB_ELEMS, n_tile * BN);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -162,7 +164,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+    constexpr uint32_t idesc = P::idesc(TILE_M, BN);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -178,12 +180,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (elect_one()) {
           const uint64_t da = umma_desc_kmajor(smem_u32(smA + stage * A_STAGE_BYTES), half ? 64u : 128u);
           const uint64_t db = umma_desc_kmajor(smem_u32(smB + stage * Cfg::B_STAGE_BYTES), 128u);
-          // advancing K by 16 elements = +32 bytes = +2 in the descriptor's (address >> 4) field
-          umma_bf16(d_tmem, da, db, idesc, kb ? 1u : 0u);
-          umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+          // advancing K by one MMA (16 bf16 / 8 tf32 elements) = +32 bytes = +2 in the descriptor's (address >> 4) field
+          P::mma(d_tmem, da, db, idesc, kb ? 1u : 0u);
+          P::mma(d_tmem, da + 2, db + 2, idesc, 1u);
           if (!half) {
-            umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
-            umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+            P::mma(d_tmem, da + 4, db + 4, idesc, 1u);
+            P::mma(d_tmem, da + 6, db + 6, idesc, 1u);
           }
           umma_commit(&empty_bar[stage]);                        // frees the smem slot once these MMAs have read it
           if (kb == p.num_kb - 1) umma_commit(&tfull_bar[as]);   // accumulator complete -> epilogue
@@ -247,12 +249,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 dst[i] = make_float4(a0 * ss.x + tt.x, a1 * ss.y + tt.y, a2 * ss.z + tt.z, a3 * ss.w + tt.w);
               }
             } else {
-              uint32_t pk[8];
-              affine16_pack(r, e.bias + col, e.scale + col, e.shift + col, e.lrelu != 0, pk);
-              st_global_v8(reinterpret_cast<__nv_bfloat16*>(e.out) + off, pk);
+              float v[16];
+              affine16(r, e.bias + col, e.scale + col, e.shift + col, e.lrelu != 0, v);
+              P::store16(reinterpret_cast<act_t*>(e.out) + off, v);
               if (e.out2)
-                st_global_v8(reinterpret_cast<__nv_bfloat16*>(e.out2) + (long long)n * e.out2_sn + (long long)oy * e.out2_sy +
-                                 (long long)ox * e.out2_sx + e.out2_c0 + oc, pk);
+                P::store16(reinterpret_cast<act_t*>(e.out2) + (long long)n * e.out2_sn + (long long)oy * e.out2_sy +
+                               (long long)ox * e.out2_sx + e.out2_c0 + oc, v);
             }
           }
         }
@@ -303,10 +305,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               const float a = leaky02(v[i] + __ldg(e.bias + i));
               v[i] = a * __ldg(e.scale + i) + __ldg(e.shift + i);
             }
-            const uint32_t pk[8] = {pack_bf16x2(v[0], v[1]),   pack_bf16x2(v[2], v[3]),   pack_bf16x2(v[4], v[5]),
-                                    pack_bf16x2(v[6], v[7]),   pack_bf16x2(v[8], v[9]),   pack_bf16x2(v[10], v[11]),
-                                    pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])};
-            st_global_v8(reinterpret_cast<__nv_bfloat16*>(e.out) + (long long)img * e.out_sn + (long long)Y * e.out_sy + X * 16, pk);
+            P::store16_exact(reinterpret_cast<act_t*>(e.out) + (long long)img * e.out_sn + (long long)Y * e.out_sy + X * 16, v);
           }
         }
       } else {
@@ -350,10 +349,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               reinterpret_cast<float4*>(cptr)[i] = make_float4(cn[4 * i], cn[4 * i + 1], cn[4 * i + 2], cn[4 * i + 3]);
-            const uint32_t pk[8] = {pack_bf16x2(hn[0], hn[1]),   pack_bf16x2(hn[2], hn[3]),   pack_bf16x2(hn[4], hn[5]),
-                                    pack_bf16x2(hn[6], hn[7]),   pack_bf16x2(hn[8], hn[9]),   pack_bf16x2(hn[10], hn[11]),
-                                    pack_bf16x2(hn[12], hn[13]), pack_bf16x2(hn[14], hn[15])};
-            st_global_v8(e.h_out + (long long)n * e.h_sn + e.h_off + ((long long)y * e.h_pitch + x) * e.F + ch0, pk);
+            P::store16(reinterpret_cast<act_t*>(e.h_out) + (long long)n * e.h_sn + e.h_off + ((long long)y * e.h_pitch + x) * e.F + ch0, hn);
           }
         }
       }

@@ -36,7 +36,7 @@ struct HaloParams {
   // ---- HEPI_UPCONV: anchors of the fused bilinear x2 + 5x5 transposed conv
   int S;                 // high-res size
   const float* delta;    // fp32 border corrections [n][S][192]
-  __nv_bfloat16* out;    // pixel (n, Y, X) channel c at out + n*up_sn + Y*up_sy + X*16 + c
+  void* out;             // act_t; pixel (n, Y, X) channel c at out + n*up_sn + Y*up_sy + X*16 + c
   long long up_sn, up_sy;
   // ---- HEPI_FINAL: 3x3 conv 16 -> 2 over "super-pixels" (4 pixels x 16 channels = one 128-byte row); GEMM columns
   //      0..7 = (pixel in super-pixel, output channel), 8..15 = the same with the bf16 residual of the weights;
@@ -44,9 +44,9 @@ struct HaloParams {
   float* outf;
   // ---- HEPI_AFFINE: valid outputs are (y < vh, x < vw); v = leaky(acc + bias) * scale + shift -> bf16, two destinations
   int vw, vh;
-  __nv_bfloat16* out1;
+  void* out1;            // act_t
   long long o1_sn, o1_sy, o1_sx;
-  __nv_bfloat16* out2;
+  void* out2;
   long long o2_sn, o2_sy, o2_sx;
   int o2_c0;
 };
@@ -69,11 +69,13 @@ struct HaloCfg {
   static_assert(2 * H_TILES * BN <= 512, "accumulators exceed TMEM");
 };
 
-template <int BN, int NCHUNK, int NTAP, int TPS, int EPI>
+template <int BN, int NCHUNK, int NTAP, int TPS, int EPI, int PREC>
 __global__ void __launch_bounds__(224, 1)
 halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ HaloParams p) {
   using Cfg = HaloCfg<BN, NCHUNK, TPS>;
+  using P = Prec<PREC>;
+  using act_t = typename P::act_t;
   constexpr int BSTAGES = Cfg::BSTAGES;
   static_assert(NTAP % TPS == 0, "taps per stage must divide the tap count");
   extern __shared__ uint8_t smem_raw[];
@@ -117,8 +119,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&a_empty[ab], phase ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&a_full[ab], 2 * p.box_rows * 128);
-          tma_load_2d(smA + ab * H_A_BYTES, &tmA, &a_full[ab], c * 64, f0);
-          tma_load_2d(smA + ab * H_A_BYTES + p.box_rows * 128, &tmA, &a_full[ab], c * 64, f0 + p.box_rows);
+          tma_load_2d(smA + ab * H_A_BYTES, &tmA, &a_full[ab], c * P::KB_ELEMS, f0);
+          tma_load_2d(smA + ab * H_A_BYTES + p.box_rows * 128, &tmA, &a_full[ab], c * P::KB_ELEMS, f0 + p.box_rows);
         }
         __syncwarp();
         if (++ab == H_ABUFS) { ab = 0; phase ^= 1; }
@@ -135,7 +137,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_arrive_expect_tx(&b_full[stage], Cfg::B_STAGE_BYTES);
 #pragma unroll
           for (int j = 0; j < TPS; ++j)
-            tma_load_2d(smB + stage * Cfg::B_STAGE_BYTES + j * BN * 128, &tmB, &b_full[stage], (g * TPS + j) * 64, 0);
+            tma_load_2d(smB + stage * Cfg::B_STAGE_BYTES + j * BN * 128, &tmB, &b_full[stage], (g * TPS + j) * P::KB_ELEMS, 0);
         }
         __syncwarp();
         if (++stage == BSTAGES) { stage = 0; phase ^= 1; }
@@ -143,7 +145,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ================================================= MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+    constexpr uint32_t idesc = P::idesc(TILE_M, BN);
     int stage = 0, ab = 0;
     uint32_t bphase = 0, aphase = 0, tphase = 0;
     int as = 0;
@@ -172,7 +174,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint64_t da = a_desc0 + (uint64_t)((t * TILE_M + shift_rows) * 8);     // rows * 128 B >> 4
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  if (kmask & (1u << k)) umma_bf16(d_tmem + t * BN, da + 2 * k, db + 2 * k, idesc, (c | tap) ? 1u : (k != first_k ? 1u : 0u));
+                  if (kmask & (1u << k)) P::mma(d_tmem + t * BN, da + 2 * k, db + 2 * k, idesc, (c | tap) ? 1u : (k != first_k ? 1u : 0u));
               }
             }
             umma_commit(&b_empty[stage]);
@@ -242,14 +244,11 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const float a = leaky02(v[i] + __ldg(p.bias + i));
                 v[i] = a * __ldg(p.scale + i) + __ldg(p.shift + i);
               }
-              const uint32_t pk[8] = {pack_bf16x2(v[0], v[1]),   pack_bf16x2(v[2], v[3]),   pack_bf16x2(v[4], v[5]),
-                                      pack_bf16x2(v[6], v[7]),   pack_bf16x2(v[8], v[9]),   pack_bf16x2(v[10], v[11]),
-                                      pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])};
-              st_global_v8(p.out + (long long)img * p.up_sn + (long long)Y * p.up_sy + X * 16, pk);
+              P::store16_exact(reinterpret_cast<act_t*>(p.out) + (long long)img * p.up_sn + (long long)Y * p.up_sy + X * 16, v);
             }
           }
         } else if constexpr (EPI == HEPI_FINAL) {
-          static_assert(EPI != HEPI_FINAL || BN == 16, "FINAL expects 4 pixels x 2 channels (+ 8 padding columns)");
+          static_assert(EPI != HEPI_FINAL || (BN == 16 && PREC == PREC_BF16), "FINAL expects 4 bf16 pixels x 2 channels (+ 8 padding columns)");
           uint32_t r[16];
           tmem_ld16(taddr, r);
           tmem_ld_wait();
@@ -264,8 +263,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         } else {
           const bool valid = arow && pr < p.vh && ps < p.vw;
-          __nv_bfloat16* d1 = p.out1 + (long long)img * p.o1_sn + (long long)pr * p.o1_sy + (long long)ps * p.o1_sx;
-          __nv_bfloat16* d2 = p.out2 + (long long)img * p.o2_sn + (long long)pr * p.o2_sy + (long long)ps * p.o2_sx + p.o2_c0;
+          act_t* d1 = reinterpret_cast<act_t*>(p.out1) + (long long)img * p.o1_sn + (long long)pr * p.o1_sy + (long long)ps * p.o1_sx;
+          act_t* d2 = reinterpret_cast<act_t*>(p.out2) + (long long)img * p.o2_sn + (long long)pr * p.o2_sy + (long long)ps * p.o2_sx + p.o2_c0;
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r0[16], r1[16];
@@ -273,14 +272,14 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tmem_ld16(taddr + c0 + 16, r1);
             tmem_ld_wait();
             if (valid) {
-              uint32_t pk0[8], pk1[8];
-              affine16_pack(r0, p.bias + c0, p.scale + c0, p.shift + c0, true, pk0);
-              affine16_pack(r1, p.bias + c0 + 16, p.scale + c0 + 16, p.shift + c0 + 16, true, pk1);
-              st_global_v8(d1 + c0, pk0);
-              st_global_v8(d1 + c0 + 16, pk1);
+              float v0[16], v1[16];
+              affine16(r0, p.bias + c0, p.scale + c0, p.shift + c0, true, v0);
+              affine16(r1, p.bias + c0 + 16, p.scale + c0 + 16, p.shift + c0 + 16, true, v1);
+              P::store16(d1 + c0, v0);
+              P::store16(d1 + c0 + 16, v1);
               if (p.out2) {
-                st_global_v8(d2 + c0, pk0);
-                st_global_v8(d2 + c0 + 16, pk1);
+                P::store16(d2 + c0, v0);
+                P::store16(d2 + c0 + 16, v1);
               }
             }
           }

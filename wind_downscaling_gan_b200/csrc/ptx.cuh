@@ -105,6 +105,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem], tf32 x tf32 -> fp32 (K = 8 per instruction; the tensor core ignores the low 13
+// mantissa bits, so producers round to nearest with cvt.rna.tf32.f32 before the operand reaches shared memory).
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once every previously issued tcgen05.mma has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -142,10 +153,20 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Instruction descriptor for kind::tf32, A/B = tf32 K-major, D = fp32, shape M x N (K = 8).
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ------------------------------------------------------------- misc helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t to_tf32(float v) {   // round to nearest (ties away) onto the 10-bit tf32 mantissa
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
 }
 // 256-bit global store (sm_100+): one full 32-byte sector per lane and instruction.
 __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) {
@@ -153,11 +174,71 @@ __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) 
                "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
-// bias -> LeakyReLU(0.2) -> folded BatchNorm for 16 consecutive GEMM columns, packed to 8 x bf16x2.
-// The per-column vectors are read as warp-uniform float4 loads.
-__device__ __forceinline__ void affine16_pack(const uint32_t (&acc)[16], const float* __restrict__ bias,
-                                              const float* __restrict__ scale, const float* __restrict__ shift,
-                                              bool lrelu, uint32_t (&out)[8]) {
+// ------------------------------------------------------------- operand precision of the inference kernels
+// PREC_BF16: activations / weights are bf16 in HBM, kind::f16 MMAs (K = 16), 64 channels per 128-byte K-block row.
+// PREC_TF32: activations / weights are fp32 containers holding tf32-rounded values, kind::tf32 MMAs (K = 8), 32
+// channels per 128-byte K-block row.  Shared-memory stage bytes, swizzle, descriptors and the number of MMAs per
+// K-block (4, each advancing 32 bytes) are identical, so the two precisions share every kernel.
+enum { PREC_BF16 = 0, PREC_TF32 = 1 };
+template <int PREC> struct Prec;
+template <> struct Prec<PREC_BF16> {
+  using act_t = __nv_bfloat16;
+  static constexpr int KB_ELEMS = 64;
+  static __host__ __device__ constexpr uint32_t idesc(int M, int N) { return umma_idesc_bf16(M, N); }
+  static __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) { umma_bf16(d, a, b, id, acc); }
+  static __device__ __forceinline__ float load(const act_t* p) { return __bfloat162float(*p); }
+  // 16 consecutive channels -> 32 bytes
+  static __device__ __forceinline__ void store16(act_t* dst, const float (&v)[16]) {
+    const uint32_t pk[8] = {pack_bf16x2(v[0], v[1]),   pack_bf16x2(v[2], v[3]),   pack_bf16x2(v[4], v[5]),
+                            pack_bf16x2(v[6], v[7]),   pack_bf16x2(v[8], v[9]),   pack_bf16x2(v[10], v[11]),
+                            pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])};
+    st_global_v8(dst, pk);
+  }
+  // same, for a tensor that no GEMM reads (input of the CUDA-core output convolution): no operand rounding needed
+  static __device__ __forceinline__ void store16_exact(act_t* dst, const float (&v)[16]) { store16(dst, v); }
+  // 8 consecutive channels
+  static __device__ __forceinline__ void load8(const act_t* p, float (&v)[8]) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(hv[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+  }
+  static __device__ __forceinline__ void store8(act_t* dst, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                                pack_bf16x2(v[6], v[7]));
+  }
+};
+template <> struct Prec<PREC_TF32> {
+  using act_t = float;
+  static constexpr int KB_ELEMS = 32;
+  static __host__ __device__ constexpr uint32_t idesc(int M, int N) { return umma_idesc_tf32(M, N); }
+  static __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) { umma_tf32(d, a, b, id, acc); }
+  static __device__ __forceinline__ float load(const act_t* p) { return *p; }
+  static __device__ __forceinline__ void store16(act_t* dst, const float (&v)[16]) {
+    const uint32_t a[8] = {to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]), to_tf32(v[4]), to_tf32(v[5]), to_tf32(v[6]), to_tf32(v[7])};
+    const uint32_t b[8] = {to_tf32(v[8]), to_tf32(v[9]), to_tf32(v[10]), to_tf32(v[11]), to_tf32(v[12]), to_tf32(v[13]), to_tf32(v[14]), to_tf32(v[15])};
+    st_global_v8(dst, a);
+    st_global_v8(dst + 8, b);
+  }
+  static __device__ __forceinline__ void store16_exact(act_t* dst, const float (&v)[16]) {
+    float4* d = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+  static __device__ __forceinline__ void load8(const act_t* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store8(act_t* dst, const float (&v)[8]) {
+    const uint32_t a[8] = {to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]), to_tf32(v[4]), to_tf32(v[5]), to_tf32(v[6]), to_tf32(v[7])};
+    st_global_v8(dst, a);
+  }
+};
+
+// bias -> LeakyReLU(0.2) -> folded BatchNorm for 16 consecutive GEMM columns (fp32 math)
+__device__ __forceinline__ void affine16(const uint32_t (&acc)[16], const float* __restrict__ bias,
+                                         const float* __restrict__ scale, const float* __restrict__ shift, bool lrelu,
+                                         float (&out)[16]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q);
@@ -169,10 +250,9 @@ __device__ __forceinline__ void affine16_pack(const uint32_t (&acc)[16], const f
       a0 = a0 >= 0.f ? a0 : 0.2f * a0; a1 = a1 >= 0.f ? a1 : 0.2f * a1;
       a2 = a2 >= 0.f ? a2 : 0.2f * a2; a3 = a3 >= 0.f ? a3 : 0.2f * a3;
     }
-    out[2 * q] = pack_bf16x2(a0 * s.x + t.x, a1 * s.y + t.y);
-    out[2 * q + 1] = pack_bf16x2(a2 * s.z + t.z, a3 * s.w + t.w);
+    out[4 * q] = a0 * s.x + t.x; out[4 * q + 1] = a1 * s.y + t.y;
+    out[4 * q + 2] = a2 * s.z + t.z; out[4 * q + 3] = a3 * s.w + t.w;
   }
 }
-
 
 }  // namespace wdg

@@ -9,9 +9,11 @@ namespace wdg {
 // bf16 image X2[n][Q][Q][(p, q, c)], Q = (S+6)/2: padded pixel (y+3, x+3) = (2Y+p, 2X+q), CP channels per pixel
 // (pad channels and the zero ring are never written).  One block per image row: the row's fp32 image and noise
 // are staged in shared memory with coalesced float4 loads, then each thread emits one 2*CP-byte pixel.
+template <int PREC>
 __global__ void __launch_bounds__(128)
-pack_input_s2d_kernel(const float* __restrict__ image, const float* __restrict__ noise, __nv_bfloat16* __restrict__ x2,
-                      int S, int cin, int cnoise, int CP) {
+pack_input_s2d_kernel(const float* __restrict__ image, const float* __restrict__ noise,
+                      typename Prec<PREC>::act_t* __restrict__ x2, int S, int cin, int cnoise, int CP) {
+  using P = Prec<PREC>;
   extern __shared__ float row[];          // [S*cin image | S*cnoise noise]
   const long long r = blockIdx.x;         // n * S + y
   const int y = (int)(r % S);
@@ -27,7 +29,7 @@ pack_input_s2d_kernel(const float* __restrict__ image, const float* __restrict__
   const int py = y + 3, Y = py >> 1, p = py & 1;
   for (int x = threadIdx.x; x < S; x += blockDim.x) {
     const int px = x + 3, X = px >> 1, q = px & 1;
-    __nv_bfloat16* dst = x2 + ((((n * Q + Y) * Q + X) * 2 + p) * 2 + q) * CP;
+    typename P::act_t* dst = x2 + ((((n * Q + Y) * Q + X) * 2 + p) * 2 + q) * CP;
     const float* ip = row + x * cin;
     const float* np = row + S * cin + x * cnoise;
     for (int c = 0; c < CP; c += 8) {
@@ -37,8 +39,7 @@ pack_input_s2d_kernel(const float* __restrict__ image, const float* __restrict__
         const int cc = c + k;
         v[k] = cc < cin ? ip[cc] : (cc < cin + cnoise ? np[cc - cin] : 0.f);
       }
-      *reinterpret_cast<uint4*>(dst + c) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                      pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      P::store8(dst + c, v);
     }
   }
 }
@@ -52,23 +53,25 @@ pack_input_s2d_kernel(const float* __restrict__ image, const float* __restrict__
 //   edge 0/1 (top/bottom): clamped x-upsample of low-res row 0 / h-1,       j in [0, 2w)
 //   edge 2/3 (left/right): zero-extended y-upsample of low-res col 0 / w-1, j in [-1, 2h]
 // One thread per (n, edge, p, 8-channel group).
-__global__ void edge_lines_kernel(const __nv_bfloat16* __restrict__ catp, __nv_bfloat16* __restrict__ E,
+template <int PREC>
+__global__ void edge_lines_kernel(const typename Prec<PREC>::act_t* __restrict__ catp, typename Prec<PREC>::act_t* __restrict__ E,
                                   long long total, int h, int C, int pitch) {
+  using P = Prec<PREC>;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int groups = C / 8;
-  const int P = 2 * h + 8;
+  const int PP = 2 * h + 8;
   // one 64-bit division for the image index, 32-bit arithmetic below it (the kernel is index-math bound)
-  const unsigned per_img = (unsigned)groups * P * 4;
+  const unsigned per_img = (unsigned)groups * PP * 4;
   const long long n = i / per_img;
   const unsigned r = (unsigned)(i - n * per_img);
   const int g = (int)(r % groups);
   const unsigned pe = r / groups;
-  const int p = (int)(pe % P);
-  const int edge = (int)(pe / P);
+  const int p = (int)(pe % PP);
+  const int edge = (int)(pe / PP);
   const int j = p - 4;
   const int PW = h + 4;
-  const __nv_bfloat16* img = catp + n * (long long)PW * PW * pitch + g * 8;
+  const typename P::act_t* img = catp + n * (long long)PW * PW * pitch + g * 8;
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
@@ -88,19 +91,13 @@ __global__ void edge_lines_kernel(const __nv_bfloat16* __restrict__ catp, __nv_b
       // padded coordinates (+2): positions outside [0, h) read the physical zero ring
       const int y = (edge < 2) ? fixed : ks[t];
       const int x = (edge < 2) ? ks[t] : fixed;
-      const uint4 v = *reinterpret_cast<const uint4*>(img + ((long long)(y + 2) * PW + (x + 2)) * pitch);
-      const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&v);
+      float f[8];
+      P::load8(img + ((long long)(y + 2) * PW + (x + 2)) * pitch, f);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = __bfloat1622float2(hv[k]);
-        acc[2 * k] += ws[t] * f.x;
-        acc[2 * k + 1] += ws[t] * f.y;
-      }
+      for (int k = 0; k < 8; ++k) acc[k] += ws[t] * f[k];
     }
   }
-  *reinterpret_cast<uint4*>(E + ((n * 4 + edge) * P + p) * C + g * 8) =
-      make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                 pack_bf16x2(acc[6], acc[7]));
+  P::store8(E + ((n * 4 + edge) * PP + p) * C + g * 8, acc);
 }
 
 // K9: Conv2D(out_channels, 3x3, 'same', linear) on the post-BatchNorm 16-channel tensor (models.py:70-71).
@@ -113,9 +110,9 @@ struct FinalConvW {
   float b[COUT];
 };
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int PREC>
 __global__ void __launch_bounds__(128)
-final_conv3x3_kernel(const __nv_bfloat16* __restrict__ in, long long in_sn, long long in_sy,
+final_conv3x3_kernel(const typename Prec<PREC>::act_t* __restrict__ in, long long in_sn, long long in_sy,
                      const __grid_constant__ FinalConvW<CIN, COUT> W, float* __restrict__ out, long long npix, int S) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
@@ -133,19 +130,15 @@ final_conv3x3_kernel(const __nv_bfloat16* __restrict__ in, long long in_sn, long
     for (int dx = 0; dx < 3; ++dx) {
       const int xx = x + dx - 1;
       if (xx < 0 || xx >= S) continue;
-      const uint4* p = reinterpret_cast<const uint4*>(in + n * in_sn + yy * in_sy + (long long)xx * CIN);
+      const typename Prec<PREC>::act_t* p = in + n * in_sn + yy * in_sy + (long long)xx * CIN;
 #pragma unroll
       for (int c8 = 0; c8 < CIN; c8 += 8) {
-        const uint4 v = __ldg(p + c8 / 8);
-        const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&v);
+        float f[8];
+        Prec<PREC>::load8(p + c8, f);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = __bfloat1622float2(hv[k]);
+        for (int k = 0; k < 8; ++k) {
 #pragma unroll
-          for (int o = 0; o < COUT; ++o) {
-            acc[o] = fmaf(f.x, W.w[((dy * 3 + dx) * CIN + c8 + 2 * k) * COUT + o], acc[o]);
-            acc[o] = fmaf(f.y, W.w[((dy * 3 + dx) * CIN + c8 + 2 * k + 1) * COUT + o], acc[o]);
-          }
+          for (int o = 0; o < COUT; ++o) acc[o] = fmaf(f[k], W.w[((dy * 3 + dx) * CIN + c8 + k) * COUT + o], acc[o]);
         }
       }
     }

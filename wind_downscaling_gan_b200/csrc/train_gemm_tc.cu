@@ -38,12 +38,6 @@ constexpr int TC_THREADS = LOADER_THREADS + 64;   // + MMA warp + TMA producer w
 constexpr int TILE_M = 128;
 constexpr uint32_t A_STAGE_BYTES = TILE_M * 128;
 
-__device__ __forceinline__ uint32_t to_tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return r;
-}
-
 // 16 bytes of one K-major SWIZZLE_128B row: tile rows are 128 bytes, chunk c of row r lives at chunk c ^ (r & 7).
 template <int OP>
 __device__ __forceinline__ void store_chunk(uint32_t tile, int row, int chunk, const float (&v)[OpT<OP>::G]) {
@@ -55,18 +49,6 @@ __device__ __forceinline__ void store_chunk(uint32_t tile, int row, int chunk, c
     w0 = to_tf32(v[0]); w1 = to_tf32(v[1]); w2 = to_tf32(v[2]); w3 = to_tf32(v[3]);
   }
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {   // A/B = tf32 K-major, D = fp32, K = 8
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------ K walkers

@@ -60,9 +60,10 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// bf16 tensor map of rank 2..5.  dims/box in elements (dim 0 innermost), strides in ELEMENTS for dims 1..rank-1.
+// Tensor map of rank 2..5 over bf16 (esz 2) or fp32 (esz 4: tf32 operands) elements.  dims/box in elements (dim 0
+// innermost), strides in ELEMENTS for dims 1..rank-1.
 static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
-                     const uint32_t* box, int inner_bytes) {
+                     const uint32_t* box, int inner_bytes, int esz) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint64_t gdim[5], gstr[4];
@@ -71,12 +72,12 @@ static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t
     gdim[i] = dims[i];
     gbox[i] = box[i];
     estr[i] = 1;
-    if (i > 0) gstr[i - 1] = strides_el[i - 1] * 2;
+    if (i > 0) gstr[i - 1] = strides_el[i - 1] * (uint64_t)esz;
   }
   CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                               : CU_TENSOR_MAP_SWIZZLE_32B;
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, gbox, estr,
+  CUresult r = enc(tm, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), gdim, gstr, gbox, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -111,7 +112,7 @@ struct WeightDesc {
 
 struct Plan {
   int B = 0, T = 0;
-  __nv_bfloat16 *xpad, *res4, *hseq, *g5, *catp, *edgeE, *g9;
+  uint8_t *xpad, *res4, *hseq, *g5, *catp, *edgeE, *g9;   // act_t buffers (bf16 or tf32-in-fp32), addressed in bytes
   float *cstate, *deltaD;
   ConvLaunch L0, L2, L5, L7, LE, L9;
   std::vector<ConvLaunch> LS;  // one per timestep
@@ -127,6 +128,10 @@ struct Plan {
 struct wdg_generator {
   int S, cin, cnoise, cout, T_default, F;
   int CP;                 // padded input channels of the packed image
+  int prec = PREC_BF16;   // operand precision of the GEMM stages (wdg_generator_set_precision)
+  int esz() const { return prec == PREC_TF32 ? 4 : 2; }     // bytes per activation / packed-weight element
+  int kbe() const { return prec == PREC_TF32 ? 32 : 64; }   // elements per 128-byte K-block row
+  int catp_pitch() const { return prec == PREC_TF32 ? 160 : 192; }   // channels per pixel of the concat image
   int device = 0;
   int sm_count = 148;
   std::vector<WeightDesc> descs;
@@ -134,7 +139,7 @@ struct wdg_generator {
   std::map<std::string, bool> set_;
   bool finalized = false;
   // packed device weights
-  __nv_bfloat16 *B0 = nullptr, *B2 = nullptr, *BL = nullptr, *B5 = nullptr, *B7 = nullptr, *B9 = nullptr, *B9h = nullptr, *BE = nullptr, *B11 = nullptr, *B5h = nullptr;
+  void *B0 = nullptr, *B2 = nullptr, *BL = nullptr, *B5 = nullptr, *B7 = nullptr, *B9 = nullptr, *B9h = nullptr, *BE = nullptr, *B11 = nullptr, *B5h = nullptr;
   float* fparams = nullptr;  // all fp32 per-column vectors, see offsets
   float *bias0, *sc0, *sh0, *bias2, *sc2, *sh2, *biasL, *bias5, *sc5, *sh5, *bias7, *sc7, *sh7, *bias9, *sc9, *sh9,
       *w11, *b11;
@@ -250,34 +255,64 @@ extern "C" int wdg_generator_get_weight(const wdg_generator* g, const char* name
 
 // -------------------------------------------------------- weight packing
 static inline __nv_bfloat16 tobf(float v) { return __float2bfloat16_rn(v); }
+// cvt.rna.tf32.f32 on the host: round to nearest, ties away, onto 10 mantissa bits
+static inline float totf32(float v) {
+  uint32_t u;
+  std::memcpy(&u, &v, 4);
+  if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0x1000u) & ~0x1FFFu;
+  std::memcpy(&v, &u, 4);
+  return v;
+}
 
+// Packed K-major weight matrix [n_rows][num_kb * kbe]: bf16 (kbe 64) or tf32-rounded fp32 (kbe 32).
 template <class Fn>
-static int upload_B(__nv_bfloat16** dev, int n_rows, int num_kb, Fn value /* (row, kb, j) -> float */) {
-  std::vector<__nv_bfloat16> h((size_t)n_rows * num_kb * 64);
+static int upload_B(const wdg_generator* g, void** dev, int n_rows, int num_kb, Fn value /* (row, kb, j) -> float */) {
+  const int kbe = g->kbe();
+  const size_t count = (size_t)n_rows * num_kb * kbe;
+  std::vector<uint8_t> h(count * g->esz());
   for (int r = 0; r < n_rows; ++r)
     for (int kb = 0; kb < num_kb; ++kb)
-      for (int j = 0; j < 64; ++j) h[((size_t)r * num_kb + kb) * 64 + j] = tobf(value(r, kb, j));
+      for (int j = 0; j < kbe; ++j) {
+        const size_t idx = ((size_t)r * num_kb + kb) * kbe + j;
+        const float v = value(r, kb, j);
+        if (g->prec == PREC_TF32) reinterpret_cast<float*>(h.data())[idx] = totf32(v);
+        else reinterpret_cast<__nv_bfloat16*>(h.data())[idx] = tobf(v);
+      }
   if (*dev) cudaFree(*dev);
   *dev = nullptr;
-  CK(cudaMalloc(dev, h.size() * sizeof(__nv_bfloat16)));
-  CK(cudaMemcpy(*dev, h.data(), h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(dev, h.size()));
+  CK(cudaMemcpy(*dev, h.data(), h.size(), cudaMemcpyHostToDevice));
   return 0;
 }
+
+extern "C" int wdg_generator_set_precision(wdg_generator* g, int mode) {
+  if (!g) return fail("null handle");
+  if (mode != WDG_PREC_BF16 && mode != WDG_PREC_TF32) return fail("precision must be WDG_PREC_BF16 (0) or WDG_PREC_TF32 (1)");
+  if (mode != g->prec) {
+    g->prec = mode;
+    g->finalized = false;
+    for (auto& pl : g->plans) pl.B = 0;
+  }
+  return 0;
+}
+extern "C" int wdg_generator_get_precision(const wdg_generator* g) { return g ? g->prec : -1; }
 
 extern "C" int wdg_generator_finalize(wdg_generator* g) {
   if (!g) return fail("null handle");
   const int F = g->F, C = g->cin + g->cnoise, CP = g->CP;
+  const int kbe = g->kbe();          // elements per K-block (one 128-byte row)
+  const int cpk = F / kbe;           // K-blocks per 128 channels
   auto W = [&](int i, const char* leaf) -> const std::vector<float>& { return g->w[wname(i, leaf)]; };
   // ---- L0: 8x8 s2 conv on the space-to-depth image X2[n][Y][X][(p,q,c)] (padded pixel (2Y+p, 2X+q), CP channels).
   //      It becomes a 4x4 stride-1 conv over 4*CP channels; two horizontally adjacent s2d pixels are contiguous
-  //      (8*CP = 192 elements = 3 chunks of 64), so tap (a, w) = rows +a, window starting at pixel +2w, and
+  //      (8*CP = 192 elements = 3 (bf16) / 6 (tf32) chunks), so tap (a, w) = rows +a, window starting at pixel +2w, and
   //      K-block = chunk*8 + (a*2 + w).  Window element e: pixel w' = e / (4*CP), parity (p,q), channel c.
   {
     const auto& w = W(0, "layer/w");  // [8][8][C][128]
     if (8 * CP != 192) return fail("8x8 s2 conv kernel expects 8*CP == 192 (CP == 24)");
-    if (upload_B(&g->B0, 128, 24, [&](int n, int kb, int j) {
+    if (upload_B(g, &g->B0, 128, 192 / kbe * 8, [&](int n, int kb, int j) {
           const int chunk = kb / 8, tap = kb % 8, a = tap / 2, ww = tap % 2;
-          const int e = chunk * 64 + j, wp = e / (4 * CP), rem = e % (4 * CP), pq = rem / CP, c = rem % CP;
+          const int e = chunk * kbe + j, wp = e / (4 * CP), rem = e % (4 * CP), pq = rem / CP, c = rem % CP;
           const int ky = 2 * a + pq / 2, kx = 2 * (2 * ww + wp) + pq % 2;
           return c < C ? w[(((size_t)ky * 8 + kx) * C + c) * 128 + n] : 0.f;
         })) return 1;
@@ -285,8 +320,9 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
   // ---- L2: 4x4 s2 conv on the padded res_2.  K within tap row = kx*128 + c.
   {
     const auto& w = W(2, "layer/w");  // [4][4][128][128]
-    if (upload_B(&g->B2, 128, 4 * 8, [&](int n, int kb, int j) {
-          const int ky = kb / 8, e = (kb % 8) * 64 + j, kx = e / 128, c = e % 128;
+    const int per = 4 * 128 / kbe;    // K-blocks per filter row
+    if (upload_B(g, &g->B2, 128, 4 * per, [&](int n, int kb, int j) {
+          const int ky = kb / per, e = (kb % per) * kbe + j, kx = e / 128, c = e % 128;
           return w[(((size_t)ky * 4 + kx) * 128 + c) * 128 + n];
         })) return 1;
   }
@@ -294,24 +330,25 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
   {
     const auto& k = W(4, "cell/kernel");
     const auto& r = W(4, "cell/recurrent_kernel");
-    if (upload_B(&g->BL, 4 * F, 36, [&](int n, int kb, int j) {
+    const int nk = 9 * cpk;           // K-blocks of one operand (x-conv or h-conv)
+    if (upload_B(g, &g->BL, 4 * F, 2 * nk, [&](int n, int kb, int j) {
           const int ntile = n / 256, gate = (n % 256) / 64, cc = n % 64;
           const int orig = gate * F + ntile * 64 + cc;
-          const int kk = kb % 18, tap = kk / 2, c = (kk % 2) * 64 + j;
-          const auto& src = kb < 18 ? k : r;
+          const int kk = kb % nk, tap = kk / cpk, c = (kk % cpk) * kbe + j;
+          const auto& src = kb < nk ? k : r;
           return src[((size_t)tap * F + c) * (4 * F) + orig];
         })) return 1;
   }
   // ---- L5: 3x3 same conv 128 -> 64
   {
     const auto& w = W(5, "layer/w");  // [3][3][128][64]
-    if (upload_B(&g->B5, F / 2, 18, [&](int n, int kb, int j) {
-          const int tap = kb / 2, c = (kb % 2) * 64 + j;
+    if (upload_B(g, &g->B5, F / 2, 9 * cpk, [&](int n, int kb, int j) {
+          const int tap = kb / cpk, c = (kb % cpk) * kbe + j;
           return w[((size_t)tap * F + c) * (F / 2) + n];
         })) return 1;
     // halo kernel: K-block = chunk * 9 + tap
-    if (upload_B(&g->B5h, F / 2, 18, [&](int n, int kb, int j) {
-          const int tap = kb % 9, c = (kb / 9) * 64 + j;
+    if (upload_B(g, &g->B5h, F / 2, 9 * cpk, [&](int n, int kb, int j) {
+          const int tap = kb % 9, c = (kb / 9) * kbe + j;
           return w[((size_t)tap * F + c) * (F / 2) + n];
         })) return 1;
   }
@@ -319,8 +356,8 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
   {
     const auto& w = W(7, "layer/w");  // [2][2][32][192]
     const int O = F / 4, I = F / 2 + F;
-    if (upload_B(&g->B7, 4 * O, I / 64, [&](int n, int kb, int j) {
-          const int grp = n / O, o = n % O, i = kb * 64 + j;
+    if (upload_B(g, &g->B7, 4 * O, I / kbe, [&](int n, int kb, int j) {
+          const int grp = n / O, o = n % O, i = kb * kbe + j;
           return w[((size_t)grp * O + o) * I + i];
         })) return 1;
   }
@@ -332,14 +369,15 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
     const auto& w = W(9, "layer/kernel");  // [5][5][16][160]
     const int O = F / 8, I = F / 4 + 128;
     if (O != 16 || I != 160) return fail("fused upsample conv expects 160 -> 16 channels");
+    const int nch = (I + kbe - 1) / kbe;   // channel chunks: 3 (bf16; the last one half full) / 5 (tf32)
     static const double U[6][4] = {{.75, .25, 0, 0}, {.25, .75, 0, 0}, {0, .75, .25, 0},
                                    {0, .25, .75, 0}, {0, 0, .75, .25}, {0, 0, .25, .75}};
     auto Wf = [&](int ty, int tx, int c, int o) { return (double)w[(((size_t)(4 - ty) * 5 + (4 - tx)) * O + o) * I + c]; };
     auto comp = [&](int n, int tap, int chunk, int j) {
       const int py = n / (2 * O), px = (n / O) % 2, o = n % O;
       const int dy = tap / 4, dx = tap % 4;
-      if (chunk == 2 && j >= 32) return 0.f;
-      const int c = chunk * 64 + j;
+      const int c = chunk * kbe + j;
+      if (c >= I) return 0.f;
       double acc = 0;
       for (int ty = 0; ty < 5; ++ty) {
         const double uy = U[py + ty][dy];
@@ -348,16 +386,16 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
       }
       return (float)acc;
     };
-    // generic kernel: K-block = tap*3 + chunk;  halo kernel: K-block = chunk*16 + tap
-    if (upload_B(&g->B9, 4 * O, 16 * 3, [&](int n, int kb, int j) { return comp(n, kb / 3, kb % 3, j); })) return 1;
-    if (upload_B(&g->B9h, 4 * O, 16 * 3, [&](int n, int kb, int j) { return comp(n, kb % 16, kb / 16, j); })) return 1;
+    // generic kernel: K-block = tap*nch + chunk;  halo kernel: K-block = chunk*16 + tap
+    if (upload_B(g, &g->B9, 4 * O, 16 * nch, [&](int n, int kb, int j) { return comp(n, kb / nch, kb % nch, j); })) return 1;
+    if (upload_B(g, &g->B9h, 4 * O, 16 * nch, [&](int n, int kb, int j) { return comp(n, kb % 16, kb / 16, j); })) return 1;
     // Border "dipole" corrections (see stencil_kernels.cuh: edge_lines_kernel): 1-D 5-tap convolutions of the four
     // upsampled edge lines; row = edge*48 + e*16 + o, where e is the distance of the output row/col from that edge.
-    if (upload_B(&g->BE, 4 * 48, 5 * 3, [&](int n, int kb, int j) {
+    if (upload_B(g, &g->BE, 4 * 48, 5 * nch, [&](int n, int kb, int j) {
           const int edge = n / 48, e = (n % 48) / 16, o = n % 16;
-          const int t = kb / 3, chunk = kb % 3;
-          if (chunk == 2 && j >= 32) return 0.f;
-          const int c = chunk * 64 + j;
+          const int t = kb / nch, chunk = kb % nch;
+          const int c = chunk * kbe + j;
+          if (c >= I) return 0.f;
           double v = 0;
           switch (edge) {
             case 0: v = Wf(2 - e, t, c, o) - (e <= 1 ? Wf(1 - e, t, c, o) : 0.0); break;
@@ -367,16 +405,17 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
           }
           return (float)(0.25 * v);
         })) return 1;
-    // Final 3x3 conv (16 -> 2) in super-pixel form: one GEMM row = 4 horizontally adjacent pixels x 16 channels (one
+    // Final 3x3 conv (16 -> 2) in super-pixel form (bf16 only; the tf32 path keeps this 0.14 % of the MACs in full fp32 on
+    // the CUDA cores): one GEMM row = 4 horizontally adjacent pixels x 16 channels (one
     // 128-byte row of the padded g9 image), K-block = super-tap (dy, dsx) with dsx in {-1, 0, +1} super-pixels, GEMM
     // column n = (output pixel po, output channel o) for n < 8; weight of input pixel pi / channel c:
     // w[dy][kx][c][o] with kx = 4 (dsx - 1) + pi - po + 1 when that lies in 0..2, else 0.
-    {
+    if (g->prec == PREC_BF16) {
       const auto& w11 = W(11, "layer/kernel");   // [3][3][16][2]
       if (F / 8 != 16 || g->cout != 2) return fail("final conv kernel expects 16 -> 2 channels");
       // columns 8..15 carry the bf16 residual of the same weights (w - bf16(w)); the epilogue adds the two halves, so the
       // output layer sees its weights to ~16 bits at no extra MMA (N = 16 is the minimum tile width anyway)
-      if (upload_B(&g->B11, 16, 9, [&](int n, int kb, int j) {
+      if (upload_B(g, &g->B11, 16, 9, [&](int n, int kb, int j) {
             const int po = (n % 8) / 2, o = n % 2, dy = kb / 3, dsx = kb % 3, pi = j / 16, c = j % 16;
             const int kx = 4 * (dsx - 1) + pi - po + 1;
             if (kx < 0 || kx > 2) return 0.f;
@@ -449,22 +488,21 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
 struct WsLayout {
   size_t xpad, res4, hseq, cstate, g5, catp, edgeE, deltaD, g9, total;
 };
-static const int CATP_PITCH = 192;  // 160 concat channels padded to 3 x 64 (pad channels stay zero)
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
-  const size_t N = (size_t)B * T, S = g->S, S2 = S / 2, S4 = S / 4, F = g->F;
+  const size_t N = (size_t)B * T, S = g->S, S2 = S / 2, S4 = S / 4, F = g->F, E = g->esz();
   WsLayout L;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return r; };
-  L.xpad = take(N * (S + 6) * (S + 6) * g->CP * 2 + 1024);   // s2d image [N][(S+6)/2][(S+6)/2][4*CP] (+ window slack)
-  L.res4 = take(N * S4 * S4 * F * 2);
-  L.hseq = take(N * (S4 + 2) * (S4 + 2) * F * 2);   // zero ring 1 (halo form of the 3x3 conv)
+  L.xpad = take(N * (S + 6) * (S + 6) * g->CP * E + 1024);   // s2d image [N][(S+6)/2][(S+6)/2][4*CP] (+ window slack)
+  L.res4 = take(N * S4 * S4 * F * E);
+  L.hseq = take(N * (S4 + 2) * (S4 + 2) * F * E);   // zero ring 1 (halo form of the 3x3 conv)
   L.cstate = take((size_t)B * S4 * S4 * F * 4);
-  L.g5 = take(N * S4 * S4 * (F / 2) * 2);
-  L.catp = take(N * (S2 + 4) * (S2 + 4) * CATP_PITCH * 2 + 4096);
-  L.edgeE = take(N * 4 * (S + 8) * (F / 4 + 128) * 2);
+  L.g5 = take(N * S4 * S4 * (F / 2) * E);
+  L.catp = take(N * (S2 + 4) * (S2 + 4) * g->catp_pitch() * E + 8192);
+  L.edgeE = take(N * 4 * (S + 8) * (F / 4 + 128) * E);
   L.deltaD = take(N * S * 192 * 4);
-  L.g9 = take(N * (S + 2) * (S + 8) * (F / 8) * 2);   // zero ring: 1 row above/below, one 4-pixel super-pixel left/right
+  L.g9 = take(N * (S + 2) * (S + 8) * (F / 8) * E);   // zero ring: 1 row above/below, one 4-pixel super-pixel left/right
   L.total = o;
   return L;
 }
@@ -520,42 +558,49 @@ static void affine_epi(EpiParams& e, const float* bias, const float* sc, const f
 
 static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
   const WsLayout L = ws_layout(g, B, T);
-  pl.xpad = (__nv_bfloat16*)(ws + L.xpad);
-  pl.res4 = (__nv_bfloat16*)(ws + L.res4); pl.hseq = (__nv_bfloat16*)(ws + L.hseq);
-  pl.cstate = (float*)(ws + L.cstate); pl.g5 = (__nv_bfloat16*)(ws + L.g5); pl.catp = (__nv_bfloat16*)(ws + L.catp);
-  pl.edgeE = (__nv_bfloat16*)(ws + L.edgeE); pl.deltaD = (float*)(ws + L.deltaD); pl.g9 = (__nv_bfloat16*)(ws + L.g9);
+  pl.xpad = ws + L.xpad;
+  pl.res4 = ws + L.res4; pl.hseq = ws + L.hseq;
+  pl.cstate = (float*)(ws + L.cstate); pl.g5 = ws + L.g5; pl.catp = ws + L.catp;
+  pl.edgeE = ws + L.edgeE; pl.deltaD = (float*)(ws + L.deltaD); pl.g9 = ws + L.g9;
   const uint64_t N = (uint64_t)B * T, S = g->S, S2 = S / 2, S4 = S / 4, F = g->F, CP = g->CP;
+  const int esz = g->esz();
+  const uint32_t kbe = (uint32_t)g->kbe();       // elements per K-block
+  const int cpk = (int)(F / kbe);                // K-blocks per 128 channels
+  const uint64_t CI = g->catp_pitch();           // channel pitch of the concat image
   const int sms = g->sm_count;
+  auto at = [&](uint8_t* base, long long elems) { return base + elems * esz; };   // element offset into an act_t buffer
+  auto tmap = [&](CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* str, const uint32_t* box,
+                  int inner_bytes = 128) { return make_tmap(tm, base, rank, dims, str, box, inner_bytes, esz); };
   auto grid_for = [&](const ConvParams& p) {
     const int total = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_N;
     return total < sms ? total : sms;
   };
-  // dummy map for unused A slots: reuse slot 0
   // ---------------- L0: 8x8 s2 as 4x4 s1 on the s2d image X2 [N][Q][Q][4*CP], Q = (S+6)/2; dims (window 8*CP, X, Y, n)
   {
     ConvLaunch& c = pl.L0;
     std::memset(&c.p, 0, sizeof c.p);
     const uint64_t Q = (S + 6) / 2, PC = 4 * CP;
+    const int nch = (int)(2 * PC / kbe);          // chunks of the 2-pixel window: 3 (bf16) / 6 (tf32)
     uint64_t dims[5] = {2 * PC, Q, Q, N, 1};
     uint64_t str[4] = {PC, Q * PC, Q * Q * PC, N * Q * Q * PC};
-    uint32_t box[5] = {64, 16, 8, 1, 1};
-    if (make_tmap(&c.tmA[0], pl.xpad, 5, dims, str, box, 128)) return 1;
+    uint32_t box[5] = {kbe, 16, 8, 1, 1};
+    if (tmap(&c.tmA[0], pl.xpad, 5, dims, str, box)) return 1;
     c.tmA[1] = c.tmA[0]; c.tmA[2] = c.tmA[0];
-    uint64_t bd[2] = {24 * 64, 128};
-    uint64_t bs[1] = {24 * 64};
-    uint32_t bb[2] = {64, 128};
-    if (make_tmap(&c.tmB, g->B0, 2, bd, bs, bb, 128)) return 1;
+    uint64_t bd[2] = {(uint64_t)nch * 8 * kbe, 128};
+    uint64_t bs[1] = {(uint64_t)nch * 8 * kbe};
+    uint32_t bb[2] = {kbe, 128};
+    if (tmap(&c.tmB, g->B0, 2, bd, bs, bb)) return 1;
     set_tiles(c.p, (int)S2, (int)S2, (int)N, 16, 8, 1, 1, 3);
-    c.p.num_kb = 24;
-    for (int ch = 0; ch < 3; ++ch)
+    c.p.num_kb = nch * 8;
+    for (int ch = 0; ch < nch; ++ch)
       for (int tap = 0; tap < 8; ++tap) {
         KBlock& k = c.p.kb[ch * 8 + tap];
-        k.src = 0; k.half = 0; k.o0 = (int16_t)(ch * 64); k.o1 = (int16_t)(2 * (tap % 2)); k.o2 = (int16_t)(tap / 2); k.o3 = 0;
+        k.src = 0; k.half = 0; k.o0 = (int16_t)(ch * kbe); k.o1 = (int16_t)(2 * (tap % 2)); k.o2 = (int16_t)(tap / 2); k.o3 = 0;
       }
     // res_2 is written once, as channels 32..159 of the zero-padded concat image `catp` (ring 2): it is read there
     // by the 4x4 s2 conv (through an overlapping-stride window map) and by the fused upsample conv.
-    const long long CI = CATP_PITCH, PW = S2 + 4;
-    affine_epi(c.p.ep, g->bias0, g->sc0, g->sh0, pl.catp + (2 * PW + 2) * CI, PW * PW * CI, PW * CI, CI, (int)(F / 4), 1);
+    const long long PW = S2 + 4, ci = (long long)CI;
+    affine_epi(c.p.ep, g->bias0, g->sc0, g->sh0, at(pl.catp, (2 * PW + 2) * ci), PW * PW * ci, PW * ci, ci, (int)(F / 4), 1);
     c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
     // halo-reuse variant: flat positions of X2 (pitch Q), taps shift by a*Q + 2w rows
     const bool fits = (3 * Q + 2 + H_TILES * TILE_M) <= (uint64_t)H_ROWS;
@@ -563,8 +608,8 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       const uint64_t flat = N * Q * Q;
       uint64_t hd[2] = {2 * PC, flat};
       uint64_t hs[1] = {PC};
-      uint32_t hb[2] = {64, H_BOX_ROWS};
-      if (make_tmap(&pl.h0A, pl.xpad, 2, hd, hs, hb, 128)) return 1;
+      uint32_t hb[2] = {kbe, H_BOX_ROWS};
+      if (tmap(&pl.h0A, pl.xpad, 2, hd, hs, hb)) return 1;
       pl.h0B = c.tmB;
       HaloParams& h = pl.h0p;
       std::memset(&h, 0, sizeof h);
@@ -573,33 +618,35 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       for (int tap = 0; tap < 8; ++tap) { h.tap_shift[tap] = (tap / 2) * (int)Q + 2 * (tap % 2); h.kmask[tap] = 0xF; }
       h.bias = g->bias0; h.scale = g->sc0; h.shift = g->sh0;
       h.vw = (int)S2; h.vh = (int)S2;
-      h.out1 = pl.catp + (2 * PW + 2) * CI + F / 4; h.o1_sn = PW * PW * CI; h.o1_sy = PW * CI; h.o1_sx = CI;
+      h.out1 = at(pl.catp, (2 * PW + 2) * ci + F / 4); h.o1_sn = PW * PW * ci; h.o1_sy = PW * ci; h.o1_sx = ci;
       h.out2 = nullptr;
       pl.h0grid = h.num_passes < sms ? h.num_passes : sms;
     }
     pl.use_halo = fits;
   }
-  // ---------------- L2: ZeroPadding2D(1) + 4x4 s2 on res_2 = channels 32..159 of catp [N][S2+4][S2+4][192] (ring 2,
+  // ---------------- L2: ZeroPadding2D(1) + 4x4 s2 on res_2 = channels 32..159 of catp [N][S2+4][S2+4][CI] (ring 2,
   //                  so the pad-1 image starts at (1,1)); dims (window of 4 pixels, ox, oy, row parity, n)
   {
     ConvLaunch& c = pl.L2;
     std::memset(&c.p, 0, sizeof c.p);
-    const uint64_t PW = S2 + 4, CI = CATP_PITCH;
+    const uint64_t PW = S2 + 4;
+    const int per = (int)(4 * 128 / kbe);         // K-blocks per filter row
     uint64_t dims[5] = {3 * CI + 128, S4, PW / 2 - 1, 2, N};
     uint64_t str[4] = {2 * CI, 2 * PW * CI, PW * CI, PW * PW * CI};
-    uint32_t box[5] = {64, 8, 8, 1, 2};
-    if (make_tmap(&c.tmA[0], pl.catp + (PW + 1) * CI + F / 4, 5, dims, str, box, 128)) return 1;
+    uint32_t box[5] = {kbe, 8, 8, 1, 2};
+    if (tmap(&c.tmA[0], at(pl.catp, (PW + 1) * CI + F / 4), 5, dims, str, box)) return 1;
     c.tmA[1] = c.tmA[0]; c.tmA[2] = c.tmA[0];
-    uint64_t bd[2] = {32 * 64, 128};
-    uint64_t bs[1] = {32 * 64};
-    uint32_t bb[2] = {64, 128};
-    if (make_tmap(&c.tmB, g->B2, 2, bd, bs, bb, 128)) return 1;
+    uint64_t bd[2] = {(uint64_t)4 * per * kbe, 128};
+    uint64_t bs[1] = {(uint64_t)4 * per * kbe};
+    uint32_t bb[2] = {kbe, 128};
+    if (tmap(&c.tmB, g->B2, 2, bd, bs, bb)) return 1;
     set_tiles(c.p, (int)S4, (int)S4, (int)N, 8, 8, 2, 1, 4);
-    c.p.num_kb = 32;
+    c.p.num_kb = 4 * per;
     for (int ky = 0; ky < 4; ++ky)
-      for (int ch = 0; ch < 8; ++ch) {   // ch = kx*2 + half
-        KBlock& k = c.p.kb[ky * 8 + ch];
-        k.src = 0; k.half = 0; k.o0 = (int16_t)((ch / 2) * CI + (ch % 2) * 64); k.o1 = 0; k.o2 = (int16_t)(ky / 2); k.o3 = (int16_t)(ky % 2);
+      for (int q = 0; q < per; ++q) {   // element q*kbe of the 4-pixel x 128-channel filter row: pixel kx, channel c0
+        KBlock& k = c.p.kb[ky * per + q];
+        const int e0 = q * (int)kbe, kx = e0 / 128, c0 = e0 % 128;
+        k.src = 0; k.half = 0; k.o0 = (int16_t)(kx * CI + c0); k.o1 = 0; k.o2 = (int16_t)(ky / 2); k.o3 = (int16_t)(ky % 2);
       }
     affine_epi(c.p.ep, g->bias2, g->sc2, g->sh2, pl.res4, (long long)S4 * S4 * F, (long long)S4 * F, F, 0, 1);
     c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
@@ -607,35 +654,37 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
   // ---------------- ConvLSTM steps: A maps over (c, x, y, t, b) of res4 (x_t) and hseq (h_{t-1})
   {
     CUtensorMap tmX, tmH, tmB;
+    const int nk = 9 * cpk;                       // K-blocks of one operand
     uint64_t dims[5] = {F, S4, S4, (uint64_t)T, (uint64_t)B};
     uint64_t str[4] = {F, S4 * F, S4 * S4 * F, (uint64_t)T * S4 * S4 * F};
-    uint32_t box[5] = {64, 8, 8, 1, 2};
-    if (make_tmap(&tmX, pl.res4, 5, dims, str, box, 128)) return 1;
+    uint32_t box[5] = {kbe, 8, 8, 1, 2};
+    if (tmap(&tmX, pl.res4, 5, dims, str, box)) return 1;
     // hseq images carry a zero ring of 1 pixel: same logical dims, padded strides, base at the interior origin
     const uint64_t SP = S4 + 2;
     uint64_t strh[4] = {F, SP * F, SP * SP * F, (uint64_t)T * SP * SP * F};
-    if (make_tmap(&tmH, pl.hseq + (SP + 1) * F, 5, dims, strh, box, 128)) return 1;
-    uint64_t bd[2] = {36 * 64, 4 * F};
-    uint64_t bs[1] = {36 * 64};
-    uint32_t bb[2] = {64, 256};
-    if (make_tmap(&tmB, g->BL, 2, bd, bs, bb, 128)) return 1;
+    if (tmap(&tmH, at(pl.hseq, (SP + 1) * F), 5, dims, strh, box)) return 1;
+    uint64_t bd[2] = {(uint64_t)2 * nk * kbe, 4 * F};
+    uint64_t bs[1] = {(uint64_t)2 * nk * kbe};
+    uint32_t bb[2] = {kbe, 256};
+    if (tmap(&tmB, g->BL, 2, bd, bs, bb)) return 1;
+    if (2 * nk > MAX_KB) return fail("ConvLSTM K-blocks exceed MAX_KB");
     pl.LS.assign(T, ConvLaunch());
     for (int t = 0; t < T; ++t) {
       ConvLaunch& c = pl.LS[t];
       std::memset(&c.p, 0, sizeof c.p);
       c.tmA[0] = tmX; c.tmA[1] = tmH; c.tmA[2] = tmX; c.tmB = tmB;
       set_tiles(c.p, (int)S4, (int)S4, B, 8, 8, 2, (int)(4 * F / 256), 4);
-      c.p.num_kb = t == 0 ? 18 : 36;
+      c.p.num_kb = t == 0 ? nk : 2 * nk;
       for (int kb = 0; kb < c.p.num_kb; ++kb) {
         KBlock& k = c.p.kb[kb];
-        const int kk = kb % 18, tap = kk / 2;
-        k.src = kb < 18 ? 0 : 1; k.half = 0;
-        k.o0 = (int16_t)((kk % 2) * 64); k.o1 = (int16_t)(tap % 3 - 1); k.o2 = (int16_t)(tap / 3 - 1);
-        k.o3 = (int16_t)(kb < 18 ? t : t - 1);
+        const int kk = kb % nk, tap = kk / cpk;
+        k.src = kb < nk ? 0 : 1; k.half = 0;
+        k.o0 = (int16_t)((kk % cpk) * kbe); k.o1 = (int16_t)(tap % 3 - 1); k.o2 = (int16_t)(tap / 3 - 1);
+        k.o3 = (int16_t)(kb < nk ? t : t - 1);
       }
       EpiParams& e = c.p.ep;
       std::memset(&e, 0, sizeof e);
-      e.bias = g->biasL; e.c_state = pl.cstate; e.h_out = pl.hseq + (SP + 1) * F;
+      e.bias = g->biasL; e.c_state = pl.cstate; e.h_out = at(pl.hseq, (SP + 1) * F);
       e.h_sn = (long long)T * SP * SP * F; e.h_off = (long long)t * SP * SP * F; e.h_pitch = (int)SP;
       e.first_step = t == 0; e.F = (int)F;
       c.bn = 256; c.epi = EPI_LSTM; c.grid = grid_for(c.p);
@@ -648,19 +697,19 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
     const uint64_t SP = S4 + 2;
     uint64_t dims[5] = {F, S4, S4, N, 1};
     uint64_t str[4] = {F, SP * F, SP * SP * F, N * SP * SP * F};
-    uint32_t box[5] = {64, 8, 8, 2, 1};
-    if (make_tmap(&c.tmA[0], pl.hseq + (SP + 1) * F, 5, dims, str, box, 128)) return 1;
+    uint32_t box[5] = {kbe, 8, 8, 2, 1};
+    if (tmap(&c.tmA[0], at(pl.hseq, (SP + 1) * F), 5, dims, str, box)) return 1;
     c.tmA[1] = c.tmA[0]; c.tmA[2] = c.tmA[0];
-    uint64_t bd[2] = {18 * 64, F / 2};
-    uint64_t bs[1] = {18 * 64};
-    uint32_t bb[2] = {64, 64};
-    if (make_tmap(&c.tmB, g->B5, 2, bd, bs, bb, 128)) return 1;
+    uint64_t bd[2] = {(uint64_t)9 * cpk * kbe, F / 2};
+    uint64_t bs[1] = {(uint64_t)9 * cpk * kbe};
+    uint32_t bb[2] = {kbe, 64};
+    if (tmap(&c.tmB, g->B5, 2, bd, bs, bb)) return 1;
     set_tiles(c.p, (int)S4, (int)S4, (int)N, 8, 8, 2, 1, 3);
-    c.p.num_kb = 18;
-    for (int kb = 0; kb < 18; ++kb) {
+    c.p.num_kb = 9 * cpk;
+    for (int kb = 0; kb < 9 * cpk; ++kb) {
       KBlock& k = c.p.kb[kb];
-      const int tap = kb / 2;
-      k.src = 0; k.half = 0; k.o0 = (int16_t)((kb % 2) * 64); k.o1 = (int16_t)(tap % 3 - 1); k.o2 = (int16_t)(tap / 3 - 1); k.o3 = 0;
+      const int tap = kb / cpk;
+      k.src = 0; k.half = 0; k.o0 = (int16_t)((kb % cpk) * kbe); k.o1 = (int16_t)(tap % 3 - 1); k.o2 = (int16_t)(tap / 3 - 1); k.o3 = 0;
     }
     affine_epi(c.p.ep, g->bias5, g->sc5, g->sh5, pl.g5, (long long)S4 * S4 * (F / 2), (long long)S4 * (F / 2), F / 2, 0, 1);
     c.bn = 64; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
@@ -671,9 +720,9 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       const uint32_t box5 = (uint32_t)(((H_TILES * TILE_M + 2 * SP + 2 + 1) / 2 + 7) / 8 * 8);
       uint64_t ad[2] = {F, rows};
       uint64_t as_[1] = {F};
-      uint32_t ab[2] = {64, box5};
-      if (make_tmap(&pl.h5A, pl.hseq, 2, ad, as_, ab, 128)) return 1;
-      if (make_tmap(&pl.h5B, g->B5h, 2, bd, bs, bb, 128)) return 1;
+      uint32_t ab[2] = {kbe, box5};
+      if (tmap(&pl.h5A, pl.hseq, 2, ad, as_, ab)) return 1;
+      if (tmap(&pl.h5B, g->B5h, 2, bd, bs, bb)) return 1;
       HaloParams& h = pl.h5p;
       std::memset(&h, 0, sizeof h);
       h.num_passes = (int)((rows + H_TILES * TILE_M - 1) / (H_TILES * TILE_M));
@@ -694,48 +743,53 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
     uint64_t s0[4] = {F / 2, S4 * (F / 2), S4 * S4 * (F / 2), N * S4 * S4 * (F / 2)};
     uint64_t d1[5] = {F, S4, S4, N, 1};
     uint64_t s1[4] = {F, S4 * F, S4 * S4 * F, N * S4 * S4 * F};
-    uint32_t box[5] = {64, 8, 8, 2, 1};
-    if (make_tmap(&c.tmA[0], pl.g5, 5, d0, s0, box, 128)) return 1;
-    if (make_tmap(&c.tmA[1], pl.res4, 5, d1, s1, box, 128)) return 1;
+    uint32_t box[5] = {kbe, 8, 8, 2, 1};
+    if (tmap(&c.tmA[0], pl.g5, 5, d0, s0, box)) return 1;
+    if (tmap(&c.tmA[1], pl.res4, 5, d1, s1, box)) return 1;
     c.tmA[2] = c.tmA[0];
-    uint64_t bd[2] = {3 * 64, 128};
-    uint64_t bs[1] = {3 * 64};
-    uint32_t bb[2] = {64, 128};
-    if (make_tmap(&c.tmB, g->B7, 2, bd, bs, bb, 128)) return 1;
+    const int n5 = (int)(F / 2 / kbe), n4 = (int)(F / kbe);   // K-blocks from g5 / res_4
+    uint64_t bd[2] = {(uint64_t)(n5 + n4) * kbe, 128};
+    uint64_t bs[1] = {(uint64_t)(n5 + n4) * kbe};
+    uint32_t bb[2] = {kbe, 128};
+    if (tmap(&c.tmB, g->B7, 2, bd, bs, bb)) return 1;
     set_tiles(c.p, (int)S4, (int)S4, (int)N, 8, 8, 2, 1, 3);
-    c.p.num_kb = 3;
-    for (int kb = 0; kb < 3; ++kb) {
+    c.p.num_kb = n5 + n4;
+    for (int kb = 0; kb < n5 + n4; ++kb) {
       KBlock& k = c.p.kb[kb];
-      k.src = kb == 0 ? 0 : 1; k.half = 0; k.o0 = (int16_t)(kb <= 1 ? 0 : 64); k.o1 = 0; k.o2 = 0; k.o3 = 0;
+      k.src = kb < n5 ? 0 : 1; k.half = 0; k.o0 = (int16_t)((kb < n5 ? kb : kb - n5) * kbe); k.o1 = 0; k.o2 = 0; k.o3 = 0;
     }
-    const long long O = F / 4, CI = CATP_PITCH, PW = S2 + 4;
-    affine_epi(c.p.ep, g->bias7, g->sc7, g->sh7, pl.catp + (2 * PW + 2) * CI, PW * PW * CI, PW * CI, CI, 0, 1);
+    const long long O = F / 4, ci = (long long)CI, PW = S2 + 4;
+    affine_epi(c.p.ep, g->bias7, g->sc7, g->sh7, at(pl.catp, (2 * PW + 2) * ci), PW * PW * ci, PW * ci, ci, 0, 1);
     c.p.ep.out_mul = 2; c.p.ep.group_cols = (int)O;
     c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
   }
+  const uint64_t I9 = F / 4 + 128;                          // channels of concat(g7, res_2)
+  const int nch9 = (int)((I9 + kbe - 1) / kbe);             // 3 (bf16, the last chunk half full) / 5 (tf32)
+  const bool half9 = I9 % kbe != 0;
   // ---------------- LE: border corrections, 1-D 5-tap conv over the 4 edge lines E[N][4][S+8][160] -> D[N][S][4*48] fp32
   {
     ConvLaunch& c = pl.LE;
     std::memset(&c.p, 0, sizeof c.p);
-    const uint64_t I = F / 4 + 128, P = S + 8;
+    const uint64_t I = I9, P = S + 8;
     uint64_t dims[5] = {I, P, 4, N, 1};
     uint64_t str[4] = {I, P * I, 4 * P * I, N * 4 * P * I};
-    uint32_t box[5] = {64, 16, 1, 8, 1};
-    uint32_t boxh[5] = {32, 16, 1, 8, 1};
-    if (make_tmap(&c.tmA[0], pl.edgeE, 5, dims, str, box, 128)) return 1;
-    if (make_tmap(&c.tmA[1], pl.edgeE, 5, dims, str, boxh, 64)) return 1;
+    uint32_t box[5] = {kbe, 16, 1, 8, 1};
+    uint32_t boxh[5] = {kbe / 2, 16, 1, 8, 1};
+    if (tmap(&c.tmA[0], pl.edgeE, 5, dims, str, box)) return 1;
+    if (tmap(&c.tmA[1], pl.edgeE, 5, dims, str, boxh, 64)) return 1;
     c.tmA[2] = c.tmA[0];
-    uint64_t bd[2] = {15 * 64, 192};
-    uint64_t bs[1] = {15 * 64};
-    uint32_t bb[2] = {64, 48};
-    if (make_tmap(&c.tmB, g->BE, 2, bd, bs, bb, 128)) return 1;
+    uint64_t bd[2] = {(uint64_t)5 * nch9 * kbe, 192};
+    uint64_t bs[1] = {(uint64_t)5 * nch9 * kbe};
+    uint32_t bb[2] = {kbe, 48};
+    if (tmap(&c.tmB, g->BE, 2, bd, bs, bb)) return 1;
     set_tiles(c.p, 1, (int)S, (int)N, 16, 1, 8, 4, 3);
     c.p.ntile_coord = 2;
-    c.p.num_kb = 15;
+    c.p.num_kb = 5 * nch9;
     for (int t = 0; t < 5; ++t)
-      for (int ch = 0; ch < 3; ++ch) {
-        KBlock& k = c.p.kb[t * 3 + ch];
-        k.src = ch == 2 ? 1 : 0; k.half = ch == 2; k.o0 = (int16_t)(ch * 64); k.o1 = (int16_t)(t + 2); k.o2 = 0; k.o3 = 0;
+      for (int ch = 0; ch < nch9; ++ch) {
+        KBlock& k = c.p.kb[t * nch9 + ch];
+        const bool hf = half9 && ch == nch9 - 1;
+        k.src = hf ? 1 : 0; k.half = hf; k.o0 = (int16_t)(ch * kbe); k.o1 = (int16_t)(t + 2); k.o2 = 0; k.o3 = 0;
       }
     affine_epi(c.p.ep, g->zero48, g->one48, g->zero48, pl.deltaD, (long long)S * 192, 0, 192, 0, 0);
     c.p.ep.out_f32 = 1;
@@ -745,31 +799,33 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
   {
     ConvLaunch& c = pl.L9;
     std::memset(&c.p, 0, sizeof c.p);
-    const uint64_t I = F / 4 + 128, PW = S2 + 4, flat = N * PW * PW, CI = CATP_PITCH;
+    const uint64_t I = I9, PW = S2 + 4, flat = N * PW * PW;
     uint64_t dims[5] = {I, flat, 1, 1, 1};
     uint64_t str[4] = {CI, flat * CI, flat * CI, flat * CI};
-    uint32_t box[5] = {64, 128, 1, 1, 1};
-    uint32_t boxh[5] = {32, 128, 1, 1, 1};
-    if (make_tmap(&c.tmA[0], pl.catp, 5, dims, str, box, 128)) return 1;
-    if (make_tmap(&c.tmA[1], pl.catp, 5, dims, str, boxh, 64)) return 1;
+    uint32_t box[5] = {kbe, 128, 1, 1, 1};
+    uint32_t boxh[5] = {kbe / 2, 128, 1, 1, 1};
+    if (tmap(&c.tmA[0], pl.catp, 5, dims, str, box)) return 1;
+    if (tmap(&c.tmA[1], pl.catp, 5, dims, str, boxh, 64)) return 1;
     c.tmA[2] = c.tmA[0];
-    uint64_t bd[2] = {48 * 64, 64};
-    uint64_t bs[1] = {48 * 64};
-    uint32_t bb[2] = {64, 64};
-    if (make_tmap(&c.tmB, g->B9, 2, bd, bs, bb, 128)) return 1;
+    uint64_t bd[2] = {(uint64_t)16 * nch9 * kbe, 64};
+    uint64_t bs[1] = {(uint64_t)16 * nch9 * kbe};
+    uint32_t bb[2] = {kbe, 64};
+    if (tmap(&c.tmB, g->B9, 2, bd, bs, bb)) return 1;
     set_tiles(c.p, 1, (int)flat, 1, 128, 1, 1, 1, 3);
     c.p.N = (int)N;  // images, for the epilogue's row decode
-    c.p.num_kb = 48;
+    c.p.num_kb = 16 * nch9;
+    if (c.p.num_kb > MAX_KB) return fail("upsample conv K-blocks exceed MAX_KB");
     for (int tap = 0; tap < 16; ++tap)
-      for (int ch = 0; ch < 3; ++ch) {
-        KBlock& k = c.p.kb[tap * 3 + ch];
-        k.src = ch == 2 ? 1 : 0; k.half = ch == 2; k.o0 = (int16_t)(ch * 64);
+      for (int ch = 0; ch < nch9; ++ch) {
+        KBlock& k = c.p.kb[tap * nch9 + ch];
+        const bool hf = half9 && ch == nch9 - 1;
+        k.src = hf ? 1 : 0; k.half = hf; k.o0 = (int16_t)(ch * kbe);
         k.o1 = (int16_t)((tap / 4) * PW + (tap % 4)); k.o2 = 0; k.o3 = 0;
       }
     EpiParams& e = c.p.ep;
     std::memset(&e, 0, sizeof e);
     const long long G9C = F / 8, G9X = S + 8, G9Y = S + 2;      // padded g9 image [G9Y][G9X][G9C], interior at (1, 4)
-    e.bias = g->bias9; e.scale = g->sc9; e.shift = g->sh9; e.out = pl.g9 + (G9X + 4) * G9C;
+    e.bias = g->bias9; e.scale = g->sc9; e.shift = g->sh9; e.out = at(pl.g9, (G9X + 4) * G9C);
     e.out_sn = G9Y * G9X * G9C; e.out_sy = G9X * G9C;
     e.up_pw = (int)PW; e.up_ph = (int)PW; e.up_S = (int)S; e.up_delta = pl.deltaD;
     c.bn = 64; c.epi = EPI_UPCONV; c.grid = grid_for(c.p);
@@ -778,21 +834,21 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
     if (pl.use_halo) {
       uint64_t hd[2] = {CI, flat};
       uint64_t hs[1] = {CI};
-      uint32_t hb[2] = {64, H_BOX_ROWS};
-      if (make_tmap(&pl.hA, pl.catp, 2, hd, hs, hb, 128)) return 1;
-      if (make_tmap(&pl.hB, g->B9h, 2, bd, bs, bb, 128)) return 1;
+      uint32_t hb[2] = {kbe, H_BOX_ROWS};
+      if (tmap(&pl.hA, pl.catp, 2, hd, hs, hb)) return 1;
+      if (tmap(&pl.hB, g->B9h, 2, bd, bs, bb)) return 1;
       HaloParams& h = pl.hp;
       std::memset(&h, 0, sizeof h);
       h.num_passes = (int)((flat + H_TILES * TILE_M - 1) / (H_TILES * TILE_M));
       h.n_img = (int)N; h.pw = (int)PW; h.ph = (int)PW; h.S = (int)S; h.delta = pl.deltaD; h.box_rows = H_BOX_ROWS;
       for (int tap = 0; tap < 16; ++tap) { h.tap_shift[tap] = (tap / 4) * (int)PW + tap % 4; h.kmask[tap] = 0xF; }
-      h.bias = g->bias9; h.scale = g->sc9; h.shift = g->sh9; h.out = pl.g9 + (G9X + 4) * G9C;
+      h.bias = g->bias9; h.scale = g->sc9; h.shift = g->sh9; h.out = at(pl.g9, (G9X + 4) * G9C);
       h.up_sn = G9Y * G9X * G9C; h.up_sy = G9X * G9C;
       pl.hgrid = h.num_passes < sms ? h.num_passes : sms;
     }
-    // ---------------- L11: final 3x3 conv on the tensor cores, super-pixel form (halo_conv.cuh, HEPI_FINAL)
+    // ---------------- L11: final 3x3 conv on the tensor cores, super-pixel form (halo_conv.cuh, HEPI_FINAL; bf16 only)
     const long long SPW = G9X / 4;                              // super-pixels per padded row
-    pl.use_halo11 = G9C == 16 && (2 * SPW + 2 + H_TILES * TILE_M) <= (long long)H_ROWS && !getenv("WDG_NO_HALO11");
+    pl.use_halo11 = g->prec == PREC_BF16 && G9C == 16 && (2 * SPW + 2 + H_TILES * TILE_M) <= (long long)H_ROWS && !getenv("WDG_NO_HALO11");
     if (pl.use_halo11) {
       const uint64_t rows = N * G9Y * SPW;
       uint64_t ad[2] = {64, rows};
@@ -800,11 +856,11 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       // only 256 + 2 SPW + 2 rows are needed per pass: two boxes of half that (rounded up to 8 rows) instead of 2 x 208
       const uint32_t box11 = (uint32_t)(((H_TILES * TILE_M + 2 * SPW + 2 + 1) / 2 + 7) / 8 * 8);
       uint32_t ab[2] = {64, box11};
-      if (make_tmap(&pl.h11A, pl.g9, 2, ad, as_, ab, 128)) return 1;
+      if (tmap(&pl.h11A, pl.g9, 2, ad, as_, ab)) return 1;
       uint64_t b11d[2] = {9 * 64, 16};
       uint64_t b11s[1] = {9 * 64};
       uint32_t b11b[2] = {64, 16};
-      if (make_tmap(&pl.h11B, g->B11, 2, b11d, b11s, b11b, 128)) return 1;
+      if (tmap(&pl.h11B, g->B11, 2, b11d, b11s, b11b)) return 1;
       HaloParams& h = pl.h11p;
       std::memset(&h, 0, sizeof h);
       h.num_passes = (int)((rows + H_TILES * TILE_M - 1) / (H_TILES * TILE_M));
@@ -856,98 +912,116 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
 }
 
 // ---------------------------------------------------------------- launch
-template <int BN, int EPI>
-static int launch_conv_t(const ConvLaunch& c, cudaStream_t stream) {
-  auto kern = conv_umma_kernel<BN, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::SMEM_BYTES));
-    attr_set = true;
-  }
+// The opt-in shared-memory size is a per-device function attribute: set it once per (kernel, device).  `done` must be
+// a static of the CALLER's template instantiation (one per kernel), hence the macro.
+#define ENSURE_SMEM(kern, device, smem)                                                              \
+  do {                                                                                               \
+    static bool done_[64] = {};                                                                      \
+    const int d_ = (device);                                                                         \
+    if (d_ < 0 || d_ >= 64 || !done_[d_]) {                                                          \
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));             \
+      if (d_ >= 0 && d_ < 64) done_[d_] = true;                                                      \
+    }                                                                                                \
+  } while (0)
+
+template <int BN, int EPI, int PREC>
+static int launch_conv_t(const ConvLaunch& c, int device, cudaStream_t stream) {
+  auto kern = conv_umma_kernel<BN, EPI, PREC>;
+  ENSURE_SMEM(kern, device, ConvCfg<BN>::SMEM_BYTES);
   kern<<<c.grid, 192, ConvCfg<BN>::SMEM_BYTES, stream>>>(c.tmA[0], c.tmA[1], c.tmA[2], c.tmB, c.p);
   CK(cudaGetLastError());
   return 0;
 }
-static int launch_conv(const ConvLaunch& c, cudaStream_t stream) {
-  if (c.epi == EPI_LSTM) return launch_conv_t<256, EPI_LSTM>(c, stream);
-  if (c.epi == EPI_UPCONV) return launch_conv_t<64, EPI_UPCONV>(c, stream);
+template <int PREC>
+static int launch_conv(const ConvLaunch& c, int device, cudaStream_t stream) {
+  if (c.epi == EPI_LSTM) return launch_conv_t<256, EPI_LSTM, PREC>(c, device, stream);
+  if (c.epi == EPI_UPCONV) return launch_conv_t<64, EPI_UPCONV, PREC>(c, device, stream);
   switch (c.bn) {
-    case 128: return launch_conv_t<128, EPI_AFFINE>(c, stream);
-    case 64: return launch_conv_t<64, EPI_AFFINE>(c, stream);
-    case 48: return launch_conv_t<48, EPI_AFFINE>(c, stream);
+    case 128: return launch_conv_t<128, EPI_AFFINE, PREC>(c, device, stream);
+    case 64: return launch_conv_t<64, EPI_AFFINE, PREC>(c, device, stream);
+    case 48: return launch_conv_t<48, EPI_AFFINE, PREC>(c, device, stream);
   }
   return fail("no kernel instantiated for this BN");
 }
+template <int BN, int NCHUNK, int NTAP, int TPS, int EPI, int PREC>
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& hp, int grid, int device, cudaStream_t stream) {
+  auto kern = halo_conv_kernel<BN, NCHUNK, NTAP, TPS, EPI, PREC>;
+  constexpr int smem = HaloCfg<BN, NCHUNK, TPS>::SMEM;
+  ENSURE_SMEM(kern, device, smem);
+  kern<<<grid, 224, smem, stream>>>(tmA, tmB, hp);
+  CK(cudaGetLastError());
+  return 0;
+}
 
-static int run_plan(wdg_generator* g, const Plan& pl, const float* image_dev, const float* noise_dev, float* out_dev,
-                    cudaStream_t stream, bool profile) {
+template <int PREC>
+static int run_plan_t(wdg_generator* g, const Plan& pl, const float* image_dev, const float* noise_dev, float* out_dev,
+                      cudaStream_t stream, bool profile) {
+  using act_t = typename Prec<PREC>::act_t;
+  constexpr int NC128 = 128 / Prec<PREC>::KB_ELEMS;     // K chunks per 128 channels: 2 (bf16) / 4 (tf32)
+  constexpr int NC192 = 192 / Prec<PREC>::KB_ELEMS;     // chunks of the 8x8 conv's 192-element window
+  constexpr int NC160 = (160 + Prec<PREC>::KB_ELEMS - 1) / Prec<PREC>::KB_ELEMS;   // concat(g7, res_2): 3 / 5
   const long long N = (long long)pl.B * pl.T, S = g->S;
   const long long npix = N * S * S;
+  const int dev = g->device;
   int stage_i = 0;
   auto mark = [&]() { if (g->profiling && profile) cudaEventRecord(g->ev[stage_i++], stream); };
   mark();
-  pack_input_s2d_kernel<<<(unsigned)(N * S), 128, (size_t)S * (g->cin + g->cnoise) * sizeof(float), stream>>>(
-      image_dev, noise_dev, pl.xpad, (int)S, g->cin, g->cnoise, g->CP);
+  pack_input_s2d_kernel<PREC><<<(unsigned)(N * S), 128, (size_t)S * (g->cin + g->cnoise) * sizeof(float), stream>>>(
+      image_dev, noise_dev, (act_t*)pl.xpad, (int)S, g->cin, g->cnoise, g->CP);
   CK(cudaGetLastError());
   mark();
   if (pl.use_halo) {
-    auto kern = halo_conv_kernel<128, 3, 8, 2, HEPI_AFFINE>;
-    constexpr int smem = HaloCfg<128, 3, 2>::SMEM;
-    static bool attr0 = false;
-    if (!attr0) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr0 = true; }
-    kern<<<pl.h0grid, 224, smem, stream>>>(pl.h0A, pl.h0B, pl.h0p);
-    CK(cudaGetLastError());
-  } else if (launch_conv(pl.L0, stream)) return 1;
+    if (launch_halo<128, NC192, 8, 2, HEPI_AFFINE, PREC>(pl.h0A, pl.h0B, pl.h0p, pl.h0grid, dev, stream)) return 1;
+  } else if (launch_conv<PREC>(pl.L0, dev, stream)) return 1;
   mark();
-  if (launch_conv(pl.L2, stream)) return 1;
+  if (launch_conv<PREC>(pl.L2, dev, stream)) return 1;
   mark();
   for (int t = 0; t < pl.T; ++t)
-    if (launch_conv(pl.LS[t], stream)) return 1;
+    if (launch_conv<PREC>(pl.LS[t], dev, stream)) return 1;
   mark();
   if (pl.use_halo5) {
-    auto kern = halo_conv_kernel<64, 2, 9, 3, HEPI_AFFINE>;
-    constexpr int smem = HaloCfg<64, 2, 3>::SMEM;
-    static bool attr5 = false;
-    if (!attr5) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr5 = true; }
-    kern<<<pl.h5grid, 224, smem, stream>>>(pl.h5A, pl.h5B, pl.h5p);
-    CK(cudaGetLastError());
-  } else if (launch_conv(pl.L5, stream)) return 1;
+    if (launch_halo<64, NC128, 9, 3, HEPI_AFFINE, PREC>(pl.h5A, pl.h5B, pl.h5p, pl.h5grid, dev, stream)) return 1;
+  } else if (launch_conv<PREC>(pl.L5, dev, stream)) return 1;
   mark();
-  if (launch_conv(pl.L7, stream)) return 1;
+  if (launch_conv<PREC>(pl.L7, dev, stream)) return 1;
   mark();
   {
     const int CI = g->F / 4 + 128;
     const long long total = N * 4 * (S + 8) * (CI / 8);
-    edge_lines_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(pl.catp, pl.edgeE, total, (int)(S / 2), CI, CATP_PITCH);
+    edge_lines_kernel<PREC><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const act_t*)pl.catp, (act_t*)pl.edgeE, total,
+                                                                               (int)(S / 2), CI, g->catp_pitch());
     CK(cudaGetLastError());
-    if (launch_conv(pl.LE, stream)) return 1;
+    if (launch_conv<PREC>(pl.LE, dev, stream)) return 1;
   }
   mark();
   if (pl.use_halo) {
-    auto kern = halo_conv_kernel<64, 3, 16, 4, HEPI_UPCONV>;
-    constexpr int smem = HaloCfg<64, 3, 4>::SMEM;
-    static bool attr9 = false;
-    if (!attr9) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr9 = true; }
-    kern<<<pl.hgrid, 224, smem, stream>>>(pl.hA, pl.hB, pl.hp);
-    CK(cudaGetLastError());
-  } else if (launch_conv(pl.L9, stream)) return 1;
+    if (launch_halo<64, NC160, 16, 4, HEPI_UPCONV, PREC>(pl.hA, pl.hB, pl.hp, pl.hgrid, dev, stream)) return 1;
+  } else if (launch_conv<PREC>(pl.L9, dev, stream)) return 1;
   mark();
-  if (pl.use_halo11) {
-    auto kern = halo_conv_kernel<16, 1, 9, 3, HEPI_FINAL>;
-    constexpr int smem = HaloCfg<16, 1, 3>::SMEM;
-    static bool attr11 = false;
-    if (!attr11) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr11 = true; }
-    HaloParams hp = pl.h11p;
-    hp.outf = out_dev;
-    kern<<<pl.h11grid, 224, smem, stream>>>(pl.h11A, pl.h11B, hp);
-  } else {
-    const long long G9C = g->F / 8, G9X = S + 8, G9Y = S + 2;
-    final_conv3x3_kernel<16, 2><<<(unsigned)((npix + 127) / 128), 128, 0, stream>>>(pl.g9 + (G9X + 4) * G9C, G9Y * G9X * G9C,
-                                                                                  G9X * G9C, g->w11h, out_dev, npix, (int)S);
+  bool done11 = false;
+  if constexpr (PREC == PREC_BF16) {
+    if (pl.use_halo11) {
+      HaloParams hp = pl.h11p;
+      hp.outf = out_dev;
+      if (launch_halo<16, 1, 9, 3, HEPI_FINAL, PREC_BF16>(pl.h11A, pl.h11B, hp, pl.h11grid, dev, stream)) return 1;
+      done11 = true;
+    }
   }
-  CK(cudaGetLastError());
+  if (!done11) {
+    // tf32 path: the output layer (0.14 % of the MACs) runs in full fp32 on the CUDA cores, on the unrounded g9
+    const long long G9C = g->F / 8, G9X = S + 8, G9Y = S + 2;
+    final_conv3x3_kernel<16, 2, PREC><<<(unsigned)((npix + 127) / 128), 128, 0, stream>>>(
+        (const act_t*)pl.g9 + (G9X + 4) * G9C, G9Y * G9X * G9C, G9X * G9C, g->w11h, out_dev, npix, (int)S);
+    CK(cudaGetLastError());
+  }
   mark();
   return 0;
+}
+
+static int run_plan(wdg_generator* g, const Plan& pl, const float* image_dev, const float* noise_dev, float* out_dev,
+                    cudaStream_t stream, bool profile) {
+  return g->prec == PREC_TF32 ? run_plan_t<PREC_TF32>(g, pl, image_dev, noise_dev, out_dev, stream, profile)
+                              : run_plan_t<PREC_BF16>(g, pl, image_dev, noise_dev, out_dev, stream, profile);
 }
 
 
@@ -1062,8 +1136,9 @@ extern "C" int wdg_generator_predict_host_gen_noise(wdg_generator* g, const floa
 extern "C" int wdg_generator_launches_per_forward(const wdg_generator* g) { return g ? g->plans[0].launches : 0; }
 
 // --------------------------------------------------------------- debug
-__global__ void bf16_to_f32_strided(const __nv_bfloat16* src, float* dst, long long n_img, int H, int W, int C,
-                                    long long sn, long long sy, long long sx) {
+template <int PREC>
+__global__ void act_to_f32_strided(const typename Prec<PREC>::act_t* src, float* dst, long long n_img, int H, int W, int C,
+                                   long long sn, long long sy, long long sx) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = n_img * H * W * C;
   if (i >= total) return;
@@ -1072,30 +1147,35 @@ __global__ void bf16_to_f32_strided(const __nv_bfloat16* src, float* dst, long l
   const int x = (int)(pix % W);
   const int y = (int)((pix / W) % H);
   const long long n = pix / ((long long)W * H);
-  dst[i] = __bfloat162float(src[n * sn + y * sy + x * sx + c]);
+  dst[i] = Prec<PREC>::load(src + n * sn + y * sy + x * sx + c);
 }
 
 extern "C" int wdg_generator_debug_read(const wdg_generator* g, int which, float* host_out, int64_t count) {
   if (!g || g->plans[0].B == 0 || !host_out) return fail("bad argument");
   const Plan& pl = g->plans[0];
-  const long long N = (long long)pl.B * pl.T, S = g->S, S2 = S / 2, S4 = S / 4, F = g->F;
-  const __nv_bfloat16* src;
+  const long long N = (long long)pl.B * pl.T, S = g->S, S2 = S / 2, S4 = S / 4, F = g->F, CI = g->catp_pitch();
+  const uint8_t* base;
+  long long off;   // element offset
   int H, W, C;
   long long sn, sy, sx;
   switch (which) {
-    case 0: H = W = (int)S2; C = 128; sx = CATP_PITCH; sy = (S2 + 4) * sx; sn = (S2 + 4) * sy; src = pl.catp + 2 * sy + 2 * sx + F / 4; break;
-    case 1: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; src = pl.res4; break;
-    case 2: H = W = (int)S4; C = (int)F; sx = F; sy = (S4 + 2) * F; sn = (S4 + 2) * sy; src = pl.hseq + sy + sx; break;
-    case 3: H = W = (int)S4; C = (int)(F / 2); sx = C; sy = S4 * sx; sn = S4 * sy; src = pl.g5; break;
-    case 4: H = W = (int)S2; C = (int)(F / 4); sx = CATP_PITCH; sy = (S2 + 4) * sx; sn = (S2 + 4) * sy; src = pl.catp + 2 * sy + 2 * sx; break;
-    case 5: H = W = (int)S; C = (int)(F / 8); sx = C; sy = (S + 8) * sx; sn = (S + 2) * sy; src = pl.g9 + sy + 4 * sx; break;
+    case 0: H = W = (int)S2; C = 128; sx = CI; sy = (S2 + 4) * sx; sn = (S2 + 4) * sy; base = pl.catp; off = 2 * sy + 2 * sx + F / 4; break;
+    case 1: H = W = (int)S4; C = (int)F; sx = F; sy = S4 * F; sn = S4 * sy; base = pl.res4; off = 0; break;
+    case 2: H = W = (int)S4; C = (int)F; sx = F; sy = (S4 + 2) * F; sn = (S4 + 2) * sy; base = pl.hseq; off = sy + sx; break;
+    case 3: H = W = (int)S4; C = (int)(F / 2); sx = C; sy = S4 * sx; sn = S4 * sy; base = pl.g5; off = 0; break;
+    case 4: H = W = (int)S2; C = (int)(F / 4); sx = CI; sy = (S2 + 4) * sx; sn = (S2 + 4) * sy; base = pl.catp; off = 2 * sy + 2 * sx; break;
+    case 5: H = W = (int)S; C = (int)(F / 8); sx = C; sy = (S + 8) * sx; sn = (S + 2) * sy; base = pl.g9; off = sy + 4 * sx; break;
     default: return fail("unknown intermediate");
   }
   const long long total = N * H * W * C;
   if (count != total) return fail("count mismatch");
   float* d = nullptr;
   CK(cudaMalloc(&d, total * sizeof(float)));
-  bf16_to_f32_strided<<<(unsigned)((total + 255) / 256), 256>>>(src, d, N, H, W, C, sn, sy, sx);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (g->prec == PREC_TF32)
+    act_to_f32_strided<PREC_TF32><<<grid, 256>>>((const float*)base + off, d, N, H, W, C, sn, sy, sx);
+  else
+    act_to_f32_strided<PREC_BF16><<<grid, 256>>>((const __nv_bfloat16*)base + off, d, N, H, W, C, sn, sy, sx);
   cudaError_t e = cudaMemcpy(host_out, d, total * sizeof(float), cudaMemcpyDeviceToHost);
   cudaFree(d);
   if (e != cudaSuccess) return fail(std::string("debug_read: ") + cudaGetErrorString(e));

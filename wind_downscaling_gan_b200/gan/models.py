@@ -56,8 +56,10 @@ class Generator(_NativeModel):
 
     name = "generator"
 
+    PRECISIONS = {"bf16": 0, "tf32": 1}
+
     def __init__(self, image_size, in_channels, noise_channels, out_channels, n_timesteps, batch_size=None,
-                 feature_channels=128, seed=None):
+                 feature_channels=128, seed=None, precision=None):
         assert image_size % 4 == 0          # models.py:19
         assert feature_channels % 8 == 0    # models.py:20
         self.image_size, self.in_channels, self.noise_channels = image_size, in_channels, noise_channels
@@ -78,6 +80,8 @@ class Generator(_NativeModel):
         self._plan = None      # (B, T)
         self._ws = None
         self._io = None
+        self.precision = "bf16"
+        self.set_precision(precision or os.environ.get("WDG_PRECISION", "bf16"))
         self._init_weights(np.random.default_rng(seed))
 
     def __del__(self):
@@ -85,6 +89,19 @@ class Generator(_NativeModel):
         if h is not None and _lib._lib is not None:
             _lib._lib.wdg_generator_destroy(h)
             self._h = None
+
+    def set_precision(self, precision):
+        """Operand precision of the GEMM stages: "bf16" (kind::f16 MMAs, rel-L2 <= 1e-2 of the fp32 reference) or
+        "tf32" (kind::tf32 MMAs on fp32 activations, output convolution in fp32: rel-L2 <= 1e-3).  Default "bf16",
+        or the WDG_PRECISION environment variable."""
+        if precision not in self.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(self.PRECISIONS)}, got {precision!r}")
+        _lib.check(_lib.lib().wdg_generator_set_precision(self._h, self.PRECISIONS[precision]))
+        if precision != self.precision:
+            self._dirty = True
+            self._plan = None
+        self.precision = precision
+        return self
 
     # ------------------------------------------------------------ weights
     def _init_weights(self, rng):
