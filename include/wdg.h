@@ -138,6 +138,17 @@ int wdg_stitch(const float* pred_dev, const int* starts_x_dev, int nx, const int
                int seq, int img, int crop, int channels, const int* rows_dev, int nrows, const int* cols_dev, int ncols,
                float* out_dev, void* stream);
 
+/* Same with the accumulation type of the mean stated.  The reference's mean is pandas' `groupby(level=...).mean()`
+ * (api.py:150) = Cython group_mean: Kahan-compensated sum in order of appearance, divided by the count --
+ * WDG_STITCH_F64: in float64, result cast to float32 (pandas==1.3.3, the reference's pin, upcasts float32 columns; this is
+ * what wdg_stitch does); WDG_STITCH_F32: in float32 (pandas >= 1.5 keeps float32).  Both are bit-exact against real
+ * pandas output (tests/golden/stitch_pandas.npz). */
+#define WDG_STITCH_F64 0
+#define WDG_STITCH_F32 1
+int wdg_stitch_accum(const float* pred_dev, const int* starts_x_dev, int nx, const int* starts_y_dev, int ny, int ntimeseq,
+                     int seq, int img, int crop, int channels, const int* rows_dev, int nrows, const int* cols_dev, int ncols,
+                     float* out_dev, int accum, void* stream);
+
 /* ---- On-device noise for FlexibleNoiseGenerator (data/data_generator.py:319-335): out[i] ~ N(0, stddev^2) from
  * Philox4x32-10 + Box-Muller; element 4j..4j+3 come from counter block `offset + j` under key `seed`, so a generator
  * advances `offset` by ceil(n/4) per call.  wdg_philox4x32_10 is the host-callable block function (known-answer tests). */

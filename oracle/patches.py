@@ -84,20 +84,29 @@ def covered(starts, first_is_zero_shift, img=IMG, crop=CROP):
     return np.array(sorted(idx), dtype=np.int64)
 
 
-def stitch(pred, starts_x, starts_y, ntimeseq, seq=SEQ, img=IMG, crop=CROP):
+def stitch(pred, starts_x, starts_y, ntimeseq, seq=SEQ, img=IMG, crop=CROP, accum="float64"):
     """api.py:140-151.  pred: float32 (N, seq, img, img, C) in gather order.
 
-    Crop [2:-2] in both patch axes, key every value by (time, lat, lon), mean over
-    duplicates (accumulated in float64 in order of appearance = patch index, divided,
-    cast back to float32), sorted ascending by (time, row, col).
+    Crop [2:-2] in both patch axes, key every value by (time, lat, lon), mean over duplicates, sorted ascending by
+    (time, row, col).  The mean is pandas' `groupby(level=...).mean()` = Cython `group_mean`
+    (pandas/_libs/groupby.pyx): per key, Kahan-compensated running sum in order of appearance (= patch index),
+    divided by the count, in the template's floating type:
+      accum="float64": pandas==1.3.3, the reference's pin (requirements.txt:11) -- `_call_cython_op` upcasts float32
+                       columns with `ensure_float64`, runs group_mean[float64] and casts the result back to float32;
+      accum="float32": pandas >= 1.5 (3.0.2 is what this image has) -- group_mean[float32] directly.
+    PINNED: tests/golden/stitch_pandas.npz holds the output of REAL pandas 3.0.2 `concat(...).groupby(level=...).mean()`
+    on float32 frames (-> the float32 mode, bit for bit) and on the same frames cast to float64 (-> the float64
+    template of the same loop, bit for bit); tests/golden/make_stitch_golden.py is the generating script.
     Returns (rows, cols, out) with out float32 (ntimeseq*seq, len(rows), len(cols), C)."""
+    dt = {"float64": np.float64, "float32": np.float32}[accum]
     pred = np.asarray(pred, np.float32)
     C = pred.shape[-1]
     rows = covered(starts_y, True, img, crop)
     cols = covered(starts_x, False, img, crop)
     rpos = {int(r): i for i, r in enumerate(rows)}
     cpos = {int(c): i for i, c in enumerate(cols)}
-    acc = np.zeros((ntimeseq * seq, len(rows), len(cols), C), np.float64)
+    shape = (ntimeseq * seq, len(rows), len(cols), C)
+    sumx, comp = np.zeros(shape, dt), np.zeros(shape, dt)
     cnt = np.zeros((len(rows), len(cols)), np.int64)
     n = 0
     for sx in starts_x:
@@ -107,8 +116,13 @@ def stitch(pred, starts_x, starts_y, ntimeseq, seq=SEQ, img=IMG, crop=CROP):
             ri = np.array([rpos[int(r)] for r in prow])
             cnt[np.ix_(ri, ci)] += 1
             for k in range(ntimeseq):
-                acc[k * seq:(k + 1) * seq][:, ri[:, None], ci[None, :]] += pred[n, :, crop:img - crop, crop:img - crop].astype(np.float64)
+                sl = (slice(k * seq, (k + 1) * seq), ri[:, None], ci[None, :])
+                val = pred[n, :, crop:img - crop, crop:img - crop].astype(dt)
+                y = val - comp[sl]                 # group_mean: y = val - compensation
+                t = sumx[sl] + y                   #             t = sumx + y
+                comp[sl] = (t - sumx[sl]) - y      #             compensation = t - sumx - y
+                sumx[sl] = t
                 n += 1
     assert n == pred.shape[0]
-    out = (acc / cnt[None, :, :, None]).astype(np.float32)
+    out = (sumx / cnt[None, :, :, None].astype(dt)).astype(np.float32)
     return rows, cols, out

@@ -93,3 +93,38 @@ def test_stitch_overlap_mean_in_patch_order():
     for v in vals:
         acc += np.float64(v)
     assert out[5, list(rows).index(r), list(cols).index(c), 0] == np.float32(acc / len(vals))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The stitch mean pinned against REAL pandas (tests/golden/stitch_pandas.npz, made by make_stitch_golden.py with
+# `pd.concat(...).groupby(level=[time, lat, lon]).mean()` as api.py:149-150 calls them).
+def _stitch_cases():
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "stitch_pandas.npz"))
+    for key in z.files:
+        if key.endswith("_meta"):
+            yield key[:-5], z
+
+
+def test_stitch_oracle_is_bit_exact_against_real_pandas():
+    import hashlib
+    n = 0
+    for name, z in _stitch_cases():
+        H, W, ov100, img, seq, nts, seed, full = (int(v) for v in z[name + "_meta"])
+        sx, sy = P.patch_grid(H, W, ov100 / 100.0, img=img)
+        N = len(sx) * len(sy) * nts
+        pred = (np.random.default_rng(seed).standard_normal((N, seq, img, img, 2)) * 5).astype(np.float32)
+        for accum, tag in (("float32", "f32"), ("float64", "f64")):
+            rows, cols, out = P.stitch(pred, sx, sy, nts, seq=seq, img=img, accum=accum)
+            assert hashlib.sha256(out.tobytes()).hexdigest() == str(z[f"{name}_sha_{tag}"]), (name, accum)
+            if full:
+                assert np.array_equal(out, z[f"{name}_{tag}"])
+        n += 1
+    assert n >= 4
+
+
+def test_stitch_accumulation_modes_differ_only_in_the_last_bit():
+    name, z = next(c for c in _stitch_cases() if c[0] == "img32_ov30")
+    a, b = z[name + "_f32"], z[name + "_f64"]
+    assert not np.array_equal(a, b)
+    assert np.max(np.abs(a.astype(np.float64) - b)) < 2e-6       # inputs ~ N(0, 5^2): one float32 ulp of the partial sums

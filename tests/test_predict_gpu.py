@@ -67,6 +67,33 @@ def test_stitch_bit_exact(H, W, nts, ov):
     assert np.array_equal(got[0], ref[..., 0]) and np.array_equal(got[1], ref[..., 1])   # bit-exact
 
 
+@pytest.mark.parametrize("accum", ["float64", "float32"])
+def test_stitch_bit_exact_against_real_pandas(accum):
+    """tests/golden/stitch_pandas.npz = output of real pandas `concat(...).groupby(level=...).mean()` (api.py:149-150)
+    on float32 frames (pandas >= 1.5 semantics) and float64 frames (pandas 1.3.3, the reference's pin)."""
+    import hashlib
+    import os
+    import torch
+    from wind_downscaling_gan_b200 import _lib, tiling
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "stitch_pandas.npz"))
+    tag, mode = {"float64": ("f64", 0), "float32": ("f32", 1)}[accum]
+    for name in [k[:-5] for k in z.files if k.endswith("_meta")]:
+        H, W, ov100, img, seq, nts, seed, full = (int(v) for v in z[name + "_meta"])
+        sx, sy = tiling.patch_grid(H, W, ov100 / 100.0, img)
+        N = len(sx) * len(sy) * nts
+        pred = (np.random.default_rng(seed).standard_normal((N, seq, img, img, 2)) * 5).astype(np.float32)
+        rows, cols = tiling.covered_rows(sy, img, 2), tiling.covered_cols(sx, img, 2)
+        out = torch.empty((2, nts * seq, len(rows), len(cols)), dtype=torch.float32, device="cuda")
+        dp = torch.from_numpy(pred).cuda()
+        dsx, dsy, dr, dc = _dev_i32(sx), _dev_i32(sy), _dev_i32(rows), _dev_i32(cols)
+        _lib.check(_lib.lib().wdg_stitch_accum(dp.data_ptr(), dsx.data_ptr(), len(sx), dsy.data_ptr(), len(sy), nts, seq, img, 2, 2,
+                                               dr.data_ptr(), len(rows), dc.data_ptr(), len(cols), out.data_ptr(), mode, None))
+        got = np.ascontiguousarray(out.cpu().numpy().transpose(1, 2, 3, 0))     # (T, rows, cols, C) like the golden
+        assert hashlib.sha256(got.tobytes()).hexdigest() == str(z[f"{name}_sha_{tag}"]), (name, accum)
+        if full:
+            assert np.array_equal(got, z[f"{name}_{tag}"])
+
+
 def _cfg1():
     from tests.synth import synthetic_dem, synthetic_era5
     return synthetic_era5(), synthetic_dem()

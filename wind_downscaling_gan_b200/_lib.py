@@ -46,6 +46,7 @@ def _declare(lib):
         "wdg_gather_normalise": [vp, vp, vp, i, i, i, vp, i, vp, i, i, i, vp, vp, vp, vp, vp],
         "wdg_gather_normalise_regrid": [vp, vp, i, i, i, vp, vp, vp, i, i, vp, vp, C.c_float, i, i, vp, i, vp, i, i, i, vp, vp, vp, vp, vp],
         "wdg_stitch": [vp, vp, i, vp, i, i, i, i, i, i, vp, i, vp, i, vp, vp],
+        "wdg_stitch_accum": [vp, vp, i, vp, i, i, i, i, i, i, vp, i, vp, i, vp, i, vp],
     }
     ll, f, d = C.c_longlong, C.c_float, C.c_double
     ip = C.POINTER(i)

@@ -105,9 +105,14 @@ __global__ void gather_normalise_kernel(Geo g, const double* __restrict__ mean, 
   }
 }
 
-// Overlap mean of the cropped patches (api.py:148-150) as a gather: one thread per output value, contributions
-// accumulated in fp64 in patch order (sx-major, then sy), divided by their count, cast to fp32.
+// Overlap mean of the cropped patches (api.py:148-150) as a gather: one thread per output value.  The mean is
+// pandas' Cython `group_mean` (what `groupby(level=...).mean()` runs): a Kahan-compensated running sum of the
+// contributions in order of appearance (= patch order: sx-major, then sy), divided by their count, in the template's
+// floating type ACC -- double for pandas 1.3.3 (the reference's pin; float32 columns are upcast first and the result
+// is cast back), float for pandas >= 1.5.  The three Kahan statements must not be re-associated or contracted:
+// they contain no multiply, and this file is built without fast-math.
 // out (C, T_total', nrows, ncols) with T_total' = ntimeseq * seq.
+template <typename ACC>
 __global__ void stitch_kernel(const float* __restrict__ pred, const int* __restrict__ sx, const int* __restrict__ sy,
                               int nx, int ny, int ntimeseq, int seq, int img, int crop, int C,
                               const int* __restrict__ rows, int nrows, const int* __restrict__ cols, int ncols,
@@ -120,7 +125,7 @@ __global__ void stitch_kernel(const float* __restrict__ pred, const int* __restr
   const int ch = (int)(i / ((long long)ncols * nrows * ntimeseq * seq));
   const int r = rows[ri], c = cols[ci];
   const int k = tg / seq, t = tg % seq;
-  double acc = 0.0;
+  ACC sumx = 0, comp = 0;
   int cnt = 0;
   for (int ix = 0; ix < nx; ++ix) {
     const int pc = c - sx[ix];
@@ -130,11 +135,15 @@ __global__ void stitch_kernel(const float* __restrict__ pred, const int* __restr
       const int pr = (s != 0 ? s + img - 1 : img) - r;
       if (pr < crop || pr >= img - crop) continue;
       const long long n = ((long long)ix * ny + iy) * ntimeseq + k;
-      acc += (double)pred[(((n * seq + t) * img + pr) * img + pc) * C + ch];
+      const ACC val = (ACC)pred[(((n * seq + t) * img + pr) * img + pc) * C + ch];
+      const ACC y = val - comp;
+      const ACC tt = sumx + y;
+      comp = (tt - sumx) - y;
+      sumx = tt;
       ++cnt;
     }
   }
-  out[i] = (float)(acc / (double)cnt);
+  out[i] = (float)(sumx / (ACC)cnt);
 }
 
 }  // namespace
@@ -194,16 +203,28 @@ static int gather_normalise_impl(Geo g, double* mean_dev, double* std_dev, float
   return 0;
 }
 
+extern "C" int wdg_stitch_accum(const float* pred_dev, const int* starts_x_dev, int nx, const int* starts_y_dev, int ny,
+                                int ntimeseq, int seq, int img, int crop, int channels, const int* rows_dev, int nrows,
+                                const int* cols_dev, int ncols, float* out_dev, int accum, void* stream_) {
+  if (!pred_dev || !starts_x_dev || !starts_y_dev || !rows_dev || !cols_dev || !out_dev)
+    return wdg_set_error("null argument");
+  if (accum != WDG_STITCH_F64 && accum != WDG_STITCH_F32) return wdg_set_error("accum must be WDG_STITCH_F64 or WDG_STITCH_F32");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const long long total = (long long)channels * ntimeseq * seq * nrows * ncols;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (accum == WDG_STITCH_F64)
+    stitch_kernel<double><<<grid, 256, 0, stream>>>(pred_dev, starts_x_dev, starts_y_dev, nx, ny, ntimeseq, seq, img, crop,
+                                                    channels, rows_dev, nrows, cols_dev, ncols, out_dev, total);
+  else
+    stitch_kernel<float><<<grid, 256, 0, stream>>>(pred_dev, starts_x_dev, starts_y_dev, nx, ny, ntimeseq, seq, img, crop,
+                                                   channels, rows_dev, nrows, cols_dev, ncols, out_dev, total);
+  CKP(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int wdg_stitch(const float* pred_dev, const int* starts_x_dev, int nx, const int* starts_y_dev, int ny,
                           int ntimeseq, int seq, int img, int crop, int channels, const int* rows_dev, int nrows,
                           const int* cols_dev, int ncols, float* out_dev, void* stream_) {
-  if (!pred_dev || !starts_x_dev || !starts_y_dev || !rows_dev || !cols_dev || !out_dev)
-    return wdg_set_error("null argument");
-  cudaStream_t stream = (cudaStream_t)stream_;
-  const long long total = (long long)channels * ntimeseq * seq * nrows * ncols;
-  stitch_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(pred_dev, starts_x_dev, starts_y_dev, nx, ny, ntimeseq,
-                                                                    seq, img, crop, channels, rows_dev, nrows, cols_dev,
-                                                                    ncols, out_dev, total);
-  CKP(cudaGetLastError());
-  return 0;
+  return wdg_stitch_accum(pred_dev, starts_x_dev, nx, starts_y_dev, ny, ntimeseq, seq, img, crop, channels, rows_dev, nrows,
+                          cols_dev, ncols, out_dev, WDG_STITCH_F64, stream_);
 }
