@@ -148,6 +148,42 @@ def test_full_size_properties(mk):
     assert not torch.equal(changed[:, 5:], full[:, 5:])
 
 
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_full_size_batch_slices_match_oracle(mk, precision):
+    """BASELINE configs[1] at full size (64 sequences x 8 timesteps x 96 x 96, the bench workload): sequences 0, 31
+    and 63 of the batch against the float64 oracle run on those sequences (sequences are independent)."""
+    import torch
+    from oracle.generator import generator_forward, synthetic_generator_weights
+    B, T, S = 64, 8, 96
+    image, noise = inputs(B, T, S, 21)
+    w = synthetic_generator_weights(0)
+    gen = mk(S, 3, 20, 2, T).set_precision(precision)
+    gen.set_weights(w)
+    out = gen.forward_device(torch.from_numpy(image).cuda(), torch.from_numpy(noise).cuda()).cpu().numpy()
+    pick = [0, 31, 63]
+    ref = generator_forward(w, image[pick], noise[pick])
+    for i, b in enumerate(pick):
+        assert rl2(out[b], ref[i]) < TOLS[precision], (b, rl2(out[b], ref[i]))
+    # and through the pipelined host entry point (chunks of 16 sequences)
+    host = gen.predict_host(image, noise).numpy()
+    assert np.array_equal(host, out)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_24_timesteps_match_oracle(mk, precision):
+    """The reference's sequence length (api.py:22): error does not build up over 24 recurrent steps."""
+    from oracle.generator import generator_forward, synthetic_generator_weights
+    B, T, S = 2, 24, 96
+    image, noise = inputs(B, T, S, 22)
+    w = synthetic_generator_weights(6)
+    gen = mk(S, 3, 20, 2, T).set_precision(precision)
+    gen.set_weights(w)
+    out = gen.predict([image, noise])
+    ref = generator_forward(w, image, noise)
+    assert rl2(out, ref) < TOLS[precision]
+    assert rl2(out[:, -1], ref[:, -1]) < TOLS[precision]      # the last timestep alone
+
+
 def test_weights_roundtrip_and_reload(mk, tmp_path):
     from oracle.generator import synthetic_generator_weights
     w = synthetic_generator_weights(2)

@@ -146,3 +146,58 @@ def test_weight_shapes_match_reference_checkpoint_index():
         assert list(shp) == man[k]["shape"], k
         assert man[k]["dtype"] == 1
     assert sum(int(np.prod(s)) for s in ours.values()) - 128 - 128 - 64 - 192 == 1_795_154  # params excl. sn_u
+
+
+def test_train_golden_fixture_is_what_the_oracle_computes():
+    """tests/golden/train_step_s96_t24.npz (one WGAN step at 96 px x 24 timesteps) is reproducible from its script:
+    guards both the committed numbers and the oracle against drift.  ~20 s of CPU."""
+    import os
+    import torch
+    from oracle import torch_train as tt
+    from tests.golden.make_train_golden import case, projections
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_step_s96_t24.npz"))
+    B, T, S = (int(v) for v in z["meta"][:3])
+    torch.set_num_threads(os.cpu_count() or 1)
+    lr, hr, draws, gw, dw = case(B, T, S)
+    st = tt.State(gw, dw)
+    m = tt.train_step(st, lr, hr, draws)
+    for k, v in m.items():
+        assert abs(v - float(z["metric/" + k])) <= 1e-9 * max(1.0, abs(v)), k
+    for prefix, old, new in (("g", gw, st.g), ("d", dw, st.d)):
+        for k in (("layer_with_weights-0/layer/w", "layer_with_weights-4/cell/recurrent_kernel") if prefix == "g" else
+                  ("layer_with_weights-2/layer/w", "layer_with_weights-1/cell/recurrent_kernel")):
+            d = new[k].numpy() - np.asarray(old[k], np.float64)
+            assert np.allclose(projections(f"{prefix}/{k}", d), z[f"{prefix}/{k}/proj"], rtol=1e-7, atol=1e-12), (prefix, k)
+
+
+def test_operand_rounding_cascade():
+    """Why a tensor-core run cannot be compared decision for decision with an operand-rounding emulation: with the
+    operands of every convolution rounded to tf32 in BOTH runs, accumulating in float32 instead of float64 moves the
+    first layer by ~5e-7, but every later layer re-rounds its input, a tiny difference flips the rounding of a
+    fraction (difference / tf32 ulp) of the elements by a whole ulp, and after three layers the two runs carry
+    independent rounding noise: outputs ~3e-4 apart -- as far as either is from the exact result within a factor ~2."""
+    import torch
+    from oracle import torch_train as tt
+    from oracle.generator import synthetic_generator_weights
+    B, T, S = 2, 2, 32
+    rng = np.random.default_rng(2)
+    lr = rng.standard_normal((B, T, S, S, 3)).astype(np.float32)
+    noise = (0.1 * rng.standard_normal((B, T, S, S, 20))).astype(np.float32)
+    gw = synthetic_generator_weights(3)
+
+    def run(dt, operand):
+        tt.DT, tt.OPERAND = dt, operand
+        try:
+            out, _ = tt.generator({k: tt.T(v).clone() for k, v in gw.items()}, tt.T(lr), tt.T(noise), training=False)
+        finally:
+            tt.DT, tt.OPERAND = torch.float64, None
+        return out.double().numpy()
+
+    def rel(a, b):
+        return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+    exact, emul64, emul32, plain32 = run(torch.float64, None), run(torch.float64, "tf32"), run(torch.float32, "tf32"), run(torch.float32, None)
+    assert rel(plain32, exact) < 1e-5                     # fp32 accumulation alone: harmless
+    assert 1e-4 < rel(emul64, exact) < 2e-3               # operand rounding: the tf32 error level
+    assert 5e-5 < rel(emul32, emul64) < 2e-3              # same rounding rule, different accumulation: already decorrelated
+    assert rel(emul32, emul64) > 20 * rel(plain32, exact)

@@ -128,3 +128,45 @@ def test_train_step_matches_oracle():
     assert rel(new_g["layer_with_weights-4/cell/kernel"], gw["layer_with_weights-4/cell/kernel"]) > 1e-5
     t = gan.test_step((lr, hr), draws=[draws[-1]])
     assert set(t) >= {"loss"} and np.isfinite(t["loss"])
+
+
+def test_train_step_s96_t24_matches_golden():
+    """The reference's real training shape (96 px, 24 timesteps, api.py:22-23): one full WGAN step on the fp32 CUDA
+    path against tests/golden/train_step_s96_t24.npz (float64 torch-autograd oracle, make_train_golden.py): the 98 ->
+    31 -> 9 -> 2 critic pyramid backward and 24-step BPTT of both ConvLSTMs included.  Per tensor: norm of the updated
+    weights, norm of their change over the step and 8 seeded projections of that change.  Tolerance on the change:
+    3x the distance at which the oracle's own float32 run lands from its float64 run (`floor` in the fixture: ~2e-2
+    for the generator, ~2e-3 for the critic -- fp32 rounding amplified by the piecewise-linear units), at least 2e-3."""
+    import os
+    from tests.golden.make_train_golden import case, projections
+    from wind_downscaling_gan_b200.data.data_generator import FlexibleNoiseGenerator
+    from wind_downscaling_gan_b200.gan import train
+    from wind_downscaling_gan_b200.gan.ganbase import GAN
+    from wind_downscaling_gan_b200.gan.models import make_discriminator, make_generator
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_step_s96_t24.npz"))
+    B, T, S = (int(v) for v in z["meta"][:3])
+    assert (T, S) == (24, 96)
+    lr, hr, draws, gw, dw = case(B, T, S)
+    gen, disc = make_generator(S, 3, 20, 2, T), make_discriminator(S, S, 3, 2, T)
+    gen.set_weights(gw)
+    disc.set_weights(dw)
+    gan = GAN(gen, disc, FlexibleNoiseGenerator((B, T, S, S, 20), std=0.1))
+    gan.compile(generator_optimizer=train.generator_optimizer(), discriminator_optimizer=train.discriminator_optimizer(),
+                discriminator_loss=train.discriminator_loss)
+    m = gan.train_step((lr, hr), draws=draws)
+    for k in ("g_loss", "g_disc_loss", "d_loss", "d_gradient_pen", "g_gradient_param", "d_gradient_param", "d_real", "d_fake"):
+        ref = float(z["metric/" + k])
+        assert abs(m[k] - ref) <= 2e-3 * max(1.0, abs(ref)), (k, m[k], ref)
+    gan.sync_weights()
+    worst = 0.0
+    for prefix, old, new in (("g", gw, gen.get_weights()), ("d", dw, disc.get_weights())):
+        for k in sorted(new):
+            a, b = np.asarray(old[k], np.float64), np.asarray(new[k], np.float64)
+            norm, dnorm = float(z[f"{prefix}/{k}/norm"]), float(z[f"{prefix}/{k}/dnorm"])
+            assert abs(np.linalg.norm(b) - norm) <= 1e-4 * norm + 1e-7, (prefix, k)
+            # a difference e between the two changes moves each projection by ~|e| (max of 8 Gaussians: ~2|e|)
+            slack = max(3 * float(z[f"{prefix}/{k}/floor"]), 2e-3) * dnorm + 2e-7 * norm
+            err = np.abs(projections(f"{prefix}/{k}", b - a) - z[f"{prefix}/{k}/proj"]).max()
+            worst = max(worst, err / max(slack, 1e-30))
+            assert err <= 2 * slack, (prefix, k, err, slack)
+    print("worst projection error / slack:", worst)
