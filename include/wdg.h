@@ -80,6 +80,14 @@ int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspace_dev, size
 int wdg_generator_forward(wdg_generator* g, const float* image_dev, const float* noise_dev, float* out_dev,
                           void* stream);
 
+/* forward() with the noise drawn INSIDE the input-packing kernel (what the reference does per group with the TF
+ * generator, api.py:136 / data_generator.py:327-335): noise element i = stddev * N(0,1) from Philox counter block
+ * noise_offset + i/4 under key noise_seed -- bit-identical to wdg_noise_normal() of the whole (B,T,S,S,Cnoise) tensor
+ * followed by forward(), without that tensor's HBM round trip.  noise_scratch_dev: NULL for the reference's 3 + 20
+ * channels; other channel counts draw the tensor first and need B*T*S*S*Cnoise floats of scratch. */
+int wdg_generator_forward_gen_noise(wdg_generator* g, const float* image_dev, float noise_std, uint64_t noise_seed,
+                                    uint64_t noise_offset, float* out_dev, void* noise_scratch_dev, void* stream);
+
 /* Same call with HOST buffers: copies inputs host->device, runs forward, copies the result
  * back and synchronises.  io_dev is a caller-owned device staging buffer of at least
  * wdg_generator_io_bytes() bytes. */

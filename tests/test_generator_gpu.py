@@ -121,6 +121,30 @@ def test_pipelined_host_path_is_bitwise_equal(mk):
     assert np.array_equal(again, dev)
 
 
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_in_kernel_noise_equals_materialised_noise(mk, precision):
+    """Noise drawn inside the packing kernel (wdg_generator_forward_gen_noise) == the FlexibleNoiseGenerator tensor fed
+    through forward(), bit for bit, on the device entry point and on the pipelined host entry point (chunk offsets)."""
+    import torch
+    from oracle.generator import synthetic_generator_weights
+    from wind_downscaling_gan_b200.data.data_generator import FlexibleNoiseGenerator
+    B, T, S = 37, 2, 32
+    gen = mk(S, 3, 20, 2, T).set_precision(precision)
+    gen.set_weights(synthetic_generator_weights(4))
+    image, _ = inputs(B, T, S, 8)
+    img_d = torch.from_numpy(image).cuda()
+    a_gen, b_gen, c_gen = (FlexibleNoiseGenerator((B, T, S, S, 20), std=0.1, random_seed=11) for _ in range(3))
+    a_gen(3), b_gen(3), c_gen(3)                      # start from a non-zero stream offset
+    noise = a_gen(B)
+    ref = gen.forward_device(img_d, noise).clone()
+    fused = gen.forward_device_gen_noise(img_d, b_gen)
+    assert torch.equal(fused, ref)
+    assert b_gen._offset == a_gen._offset             # the generator advanced as if the tensor had been drawn
+    host = gen.predict_host_gen_noise(image, c_gen)
+    assert torch.equal(host.cuda(), ref)
+    assert float(noise.std()) == pytest.approx(0.1, rel=2e-2)
+
+
 def test_full_size_properties(mk):
     """BASELINE configs[1] size (64 x 8 x 96 x 96): size-independent properties instead of the oracle.
     (1) sequences are independent: a sequence computed inside the batch of 64 equals the same sequence

@@ -35,6 +35,7 @@ def _declare(lib):
         "wdg_generator_workspace_bytes": [vp, i, i, C.POINTER(sz)],
         "wdg_generator_bind": [vp, i, i, vp, sz, vp],
         "wdg_generator_forward": [vp, vp, vp, vp, vp],
+        "wdg_generator_forward_gen_noise": [vp, vp, C.c_float, C.c_uint64, C.c_uint64, vp, vp, vp],
         "wdg_generator_io_bytes": [vp, i, i, C.POINTER(sz)],
         "wdg_generator_predict_host": [vp, vp, vp, vp, vp, vp],
         "wdg_generator_predict_host_gen_noise": [vp, vp, C.c_float, C.c_uint64, C.c_uint64, vp, vp, vp],
@@ -118,6 +119,11 @@ def lib():
     return _lib
 
 
+calls = 0   # library entry points called so far (every one launches at least one kernel on the training path)
+
+
 def check(rc):
+    global calls
+    calls += 1
     if rc != 0:
         raise WdgError(lib().wdg_last_error().decode())

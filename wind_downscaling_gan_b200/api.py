@@ -160,11 +160,16 @@ def _run_tiles(gather, time_window, pixels_lat, pixels_lon, lat_vals, lon_vals, 
     for t in range(num_groups):
         sl = slice(t * group_size, min((t + 1) * group_size, n_patches))
         tensor = tensors[sl]
-        if noise is None:
-            nz = network.noise_generator(bs=tensor.shape[0], channels=NOISE_CHANNELS)
+        ng = network.noise_generator
+        if noise is None and hasattr(ng, "reserve") and ng.noise_shape[1:4] == tuple(tensor.shape[1:4]):
+            # api.py:136 draws this group's noise from the generator: drawn inside the packing kernel instead
+            gen.forward_device_gen_noise(tensor, ng, out=preds[sl])
         else:
-            nz = torch.as_tensor(noise[sl], dtype=torch.float32).cuda()
-        gen.forward_device(tensor, nz, out=preds[sl])
+            if noise is None:
+                nz = ng(bs=tensor.shape[0], channels=NOISE_CHANNELS)
+            else:
+                nz = torch.as_tensor(noise[sl], dtype=torch.float32).cuda()
+            gen.forward_device(tensor, nz, out=preds[sl])
         print(f'Predicted {(t + 1) / num_groups:.0%}')
     rows = tiling.covered_rows(starts_y, IMG_SIZE, CROP)
     cols = tiling.covered_cols(starts_x, IMG_SIZE, CROP)

@@ -1,14 +1,25 @@
 // Bandwidth-bound kernels of the generator forward: input packing (concat + pad + cast),
 // bilinear x2 upsample of the concatenated skip tensor, and the final 3x3 16->2 convolution.
 #pragma once
+#include "philox.cuh"
 #include "ptx.cuh"
 
 namespace wdg {
 
 // K1: Concatenate([image, noise]) + ZeroPadding2D(3) + cast (models.py:28,32), written as the space-to-depth
-// bf16 image X2[n][Q][Q][(p, q, c)], Q = (S+6)/2: padded pixel (y+3, x+3) = (2Y+p, 2X+q), CP channels per pixel
-// (pad channels and the zero ring are never written).  One block per image row: the row's fp32 image and noise
-// are staged in shared memory with coalesced float4 loads, then each thread emits one 2*CP-byte pixel.
+// act_t image X2[n][Q][Q][(p, q, c)], Q = (S+6)/2: padded pixel (y+3, x+3) = (2Y+p, 2X+q), CP channels per pixel
+// (pad channels and the zero ring are never written).  One block per image row: the row's fp32 image (and noise) is
+// staged in shared memory with coalesced float4 loads, then each thread emits one CP-channel pixel.
+// pack_input_gen_noise_kernel: the noise is not read but DRAWN here, in registers (api.py:136 draws it per group with the TF generator):
+// channel c of pixel i is element (i * cnoise + c) of the Philox stream of wdg_noise_normal(seed, offset) scaled by
+// noise_std -- bit-identical to generating the (B,T,S,S,cnoise) tensor first, without its 2 x 737 KB per field of HBM
+// traffic.  Requires cnoise % 4 == 0 (one counter block = 4 channels of one pixel).
+struct NoiseSpec {
+  float stddev;
+  uint32_t k0, k1;
+  unsigned long long offset;   // counter block of element 0
+};
+
 template <int PREC>
 __global__ void __launch_bounds__(128)
 pack_input_s2d_kernel(const float* __restrict__ image, const float* __restrict__ noise,
@@ -40,6 +51,47 @@ pack_input_s2d_kernel(const float* __restrict__ image, const float* __restrict__
         v[k] = cc < cin ? ip[cc] : (cc < cin + cnoise ? np[cc - cin] : 0.f);
       }
       P::store8(dst + c, v);
+    }
+  }
+}
+
+// Same with the channel counts fixed at compile time (the reference's 3 + 20 -> 24, api.py:25-27) and the noise drawn
+// in registers; one thread per pixel, everything unrolled (no local-memory arrays).
+template <int PREC, int CIN, int CNOISE, int CP>
+__global__ void __launch_bounds__(128)
+pack_input_gen_noise_kernel(const float* __restrict__ image, NoiseSpec ns, typename Prec<PREC>::act_t* __restrict__ x2, int S) {
+  using P = Prec<PREC>;
+  static_assert(CNOISE % 4 == 0 && CP % 8 == 0 && CIN + CNOISE <= CP, "channel layout");
+  extern __shared__ float row[];          // [S*CIN image]
+  const long long r = blockIdx.x;         // n * S + y
+  const int y = (int)(r % S);
+  const long long n = r / S;
+  const float4* img4 = reinterpret_cast<const float4*>(image + r * S * CIN);
+  float4* row4 = reinterpret_cast<float4*>(row);
+  for (int i = threadIdx.x; i < S * CIN / 4; i += blockDim.x) row4[i] = __ldg(img4 + i);
+  __syncthreads();
+  const int Q = (S + 6) / 2;
+  const int py = y + 3, Y = py >> 1, p = py & 1;
+  for (int x = threadIdx.x; x < S; x += blockDim.x) {
+    const int px = x + 3, X = px >> 1, q = px & 1;
+    typename P::act_t* dst = x2 + ((((n * Q + Y) * Q + X) * 2 + p) * 2 + q) * CP;
+    float v[CP];
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) v[c] = row[x * CIN + c];
+    const unsigned long long blk0 = ns.offset + (unsigned long long)((r * S + x) * (long long)(CNOISE / 4));
+#pragma unroll
+    for (int b = 0; b < CNOISE / 4; ++b) {
+      float nz[4];
+      philox_normal4(blk0 + b, ns.k0, ns.k1, nz);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[CIN + 4 * b + k] = nz[k] * ns.stddev;
+    }
+#pragma unroll
+    for (int c = CIN + CNOISE; c < CP; ++c) v[c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; c += 8) {
+      const float w[8] = {v[c], v[c + 1], v[c + 2], v[c + 3], v[c + 4], v[c + 5], v[c + 6], v[c + 7]};
+      P::store8(dst + c, w);
     }
   }
 }

@@ -912,6 +912,8 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
 }
 
 // ---------------------------------------------------------------- launch
+static bool fused_noise_ok(const wdg_generator* g) { return g->cin == 3 && g->cnoise == 20 && g->CP == 24; }
+
 // The opt-in shared-memory size is a per-device function attribute: set it once per (kernel, device).  `done` must be
 // a static of the CALLER's template instantiation (one per kernel), hence the macro.
 #define ENSURE_SMEM(kern, device, smem)                                                              \
@@ -953,9 +955,10 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Hal
   return 0;
 }
 
+// noise_dev == nullptr: the noise is drawn inside the packing kernel from `ns` (std, key, first counter block)
 template <int PREC>
-static int run_plan_t(wdg_generator* g, const Plan& pl, const float* image_dev, const float* noise_dev, float* out_dev,
-                      cudaStream_t stream, bool profile) {
+static int run_plan_t(wdg_generator* g, const Plan& pl, const float* image_dev, const float* noise_dev, const NoiseSpec& ns,
+                      float* out_dev, cudaStream_t stream, bool profile) {
   using act_t = typename Prec<PREC>::act_t;
   constexpr int NC128 = 128 / Prec<PREC>::KB_ELEMS;     // K chunks per 128 channels: 2 (bf16) / 4 (tf32)
   constexpr int NC192 = 192 / Prec<PREC>::KB_ELEMS;     // chunks of the 8x8 conv's 192-element window
@@ -966,8 +969,14 @@ static int run_plan_t(wdg_generator* g, const Plan& pl, const float* image_dev, 
   int stage_i = 0;
   auto mark = [&]() { if (g->profiling && profile) cudaEventRecord(g->ev[stage_i++], stream); };
   mark();
-  pack_input_s2d_kernel<PREC><<<(unsigned)(N * S), 128, (size_t)S * (g->cin + g->cnoise) * sizeof(float), stream>>>(
-      image_dev, noise_dev, (act_t*)pl.xpad, (int)S, g->cin, g->cnoise, g->CP);
+  if (noise_dev) {
+    pack_input_s2d_kernel<PREC><<<(unsigned)(N * S), 128, (size_t)S * (g->cin + g->cnoise) * sizeof(float), stream>>>(
+        image_dev, noise_dev, (act_t*)pl.xpad, (int)S, g->cin, g->cnoise, g->CP);
+  } else {
+    if (!fused_noise_ok(g)) return fail("in-kernel noise is built for 3 + 20 input channels");
+    pack_input_gen_noise_kernel<PREC, 3, 20, 24><<<(unsigned)(N * S), 96, (size_t)S * 3 * sizeof(float), stream>>>(
+        image_dev, ns, (act_t*)pl.xpad, (int)S);
+  }
   CK(cudaGetLastError());
   mark();
   if (pl.use_halo) {
@@ -1018,10 +1027,13 @@ static int run_plan_t(wdg_generator* g, const Plan& pl, const float* image_dev, 
   return 0;
 }
 
-static int run_plan(wdg_generator* g, const Plan& pl, const float* image_dev, const float* noise_dev, float* out_dev,
-                    cudaStream_t stream, bool profile) {
-  return g->prec == PREC_TF32 ? run_plan_t<PREC_TF32>(g, pl, image_dev, noise_dev, out_dev, stream, profile)
-                              : run_plan_t<PREC_BF16>(g, pl, image_dev, noise_dev, out_dev, stream, profile);
+static int run_plan(wdg_generator* g, const Plan& pl, const float* image_dev, const float* noise_dev, const NoiseSpec& ns,
+                    float* out_dev, cudaStream_t stream, bool profile) {
+  return g->prec == PREC_TF32 ? run_plan_t<PREC_TF32>(g, pl, image_dev, noise_dev, ns, out_dev, stream, profile)
+                              : run_plan_t<PREC_BF16>(g, pl, image_dev, noise_dev, ns, out_dev, stream, profile);
+}
+static NoiseSpec noise_spec(float stddev, uint64_t seed, uint64_t offset) {
+  return NoiseSpec{stddev, (uint32_t)seed, (uint32_t)(seed >> 32), (unsigned long long)offset};
 }
 
 
@@ -1029,7 +1041,22 @@ extern "C" int wdg_generator_forward(wdg_generator* g, const float* image_dev, c
                                      void* stream_) {
   if (!g || !image_dev || !noise_dev || !out_dev) return fail("null argument");
   if (g->plans[0].B == 0) return fail("wdg_generator_bind must be called before forward");
-  return run_plan(g, g->plans[0], image_dev, noise_dev, out_dev, (cudaStream_t)stream_, true);
+  return run_plan(g, g->plans[0], image_dev, noise_dev, NoiseSpec{}, out_dev, (cudaStream_t)stream_, true);
+}
+
+extern "C" int wdg_generator_forward_gen_noise(wdg_generator* g, const float* image_dev, float noise_std, uint64_t noise_seed,
+                                               uint64_t noise_offset, float* out_dev, void* noise_scratch_dev, void* stream_) {
+  if (!g || !image_dev || !out_dev) return fail("null argument");
+  const Plan& pl = g->plans[0];
+  if (pl.B == 0) return fail("wdg_generator_bind must be called before forward");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (fused_noise_ok(g))
+    return run_plan(g, pl, image_dev, nullptr, noise_spec(noise_std, noise_seed, noise_offset), out_dev, stream, true);
+  // other channel counts: draw the tensor first
+  if (!noise_scratch_dev) return fail("this channel configuration needs a (B,T,S,S,Cnoise) fp32 noise scratch buffer");
+  const long long n = (long long)pl.B * pl.T * g->S * g->S * g->cnoise;
+  if (wdg_noise_normal((float*)noise_scratch_dev, n, noise_std, noise_seed, noise_offset, stream)) return 1;
+  return run_plan(g, pl, image_dev, (const float*)noise_scratch_dev, NoiseSpec{}, out_dev, stream, true);
 }
 
 extern "C" int wdg_generator_profile(wdg_generator* g, int enable) {
@@ -1067,9 +1094,10 @@ static int predict_host_impl(wdg_generator* g, const float* image_host, const fl
     float* d_noise = (float*)(io + align_up(b_img, 256));
     float* d_out = (float*)(io + align_up(b_img, 256) + align_up(b_noise, 256));
     CK(cudaMemcpyAsync(d_img, image_host, b_img, cudaMemcpyHostToDevice, stream));
+    const bool fused = !noise_host && fused_noise_ok(g);
     if (noise_host) CK(cudaMemcpyAsync(d_noise, noise_host, b_noise, cudaMemcpyHostToDevice, stream));
-    else if (wdg_noise_normal(d_noise, (long long)(b_noise / 4), noise_std, noise_seed, noise_offset, stream)) return 1;
-    if (run_plan(g, full, d_img, d_noise, d_out, stream, false)) return 1;
+    else if (!fused && wdg_noise_normal(d_noise, (long long)(b_noise / 4), noise_std, noise_seed, noise_offset, stream)) return 1;
+    if (run_plan(g, full, d_img, fused ? nullptr : d_noise, noise_spec(noise_std, noise_seed, noise_offset), d_out, stream, false)) return 1;
     CK(cudaMemcpyAsync(out_host, d_out, b_out, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     return 0;
@@ -1107,10 +1135,12 @@ static int predict_host_impl(wdg_generator* g, const float* image_host, const fl
     CK(cudaEventRecord(g->ev_h2d[buf], g->copy_in));
     CK(cudaStreamWaitEvent(stream, g->ev_h2d[buf], 0));
     if (i >= 2) CK(cudaStreamWaitEvent(stream, g->ev_d2h[buf], 0));          // output of chunk i-2 copied out
-    if (!noise_host &&   // element index of this chunk in the whole noise tensor is a multiple of 4: counter blocks line up
-        wdg_noise_normal(d_noise, (long long)(nb * s_noise / 4), noise_std, noise_seed, noise_offset + b0 * (s_noise / 16), stream))
+    // element index of this chunk in the whole noise tensor is a multiple of 4: counter blocks line up
+    const uint64_t chunk_off = noise_offset + b0 * (s_noise / 16);
+    const bool fused = !noise_host && fused_noise_ok(g);
+    if (!noise_host && !fused && wdg_noise_normal(d_noise, (long long)(nb * s_noise / 4), noise_std, noise_seed, chunk_off, stream))
       return 1;
-    if (run_plan(g, pl, d_img, d_noise, d_out, stream, false)) return 1;
+    if (run_plan(g, pl, d_img, fused ? nullptr : d_noise, noise_spec(noise_std, noise_seed, chunk_off), d_out, stream, false)) return 1;
     CK(cudaEventRecord(g->ev_fwd[buf], stream));
     CK(cudaStreamWaitEvent(g->copy_out, g->ev_fwd[buf], 0));
     CK(cudaMemcpyAsync((uint8_t*)out_host + b0 * s_out, d_out, nb * s_out, cudaMemcpyDeviceToHost, g->copy_out));

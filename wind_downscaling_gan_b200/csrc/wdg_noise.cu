@@ -9,31 +9,12 @@
 #include <string>
 
 #include "../../include/wdg.h"
+#include "philox.cuh"
 
 extern int wdg_set_error(const std::string& m);
 
 namespace {
-
-struct U4 { uint32_t x, y, z, w; };
-
-__host__ __device__ inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
-
-// Philox4x32 with 10 rounds (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11)
-__host__ __device__ inline U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = mulhi32(M0, c.x), lo0 = M0 * c.x;
-    const uint32_t hi1 = mulhi32(M1, c.z), lo1 = M1 * c.z;
-    c = U4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
-    k0 += W0; k1 += W1;
-  }
-  return c;
-}
-
-__device__ inline float u32_to_unit(uint32_t x) {   // 23 mantissa bits -> [0, 1)
-  return __uint_as_float((x & 0x7fffffu) | 0x3f800000u) - 1.0f;
-}
+using namespace wdg;
 
 // Each thread produces 4 consecutive normals from one Philox block (counter = offset + block index).
 __global__ void noise_normal_kernel(float* __restrict__ out, long long n, float stddev, uint32_t k0, uint32_t k1,
@@ -42,19 +23,8 @@ __global__ void noise_normal_kernel(float* __restrict__ out, long long n, float 
   const long long i0 = blk * 4;
   if (i0 >= n) return;
   const unsigned long long ctr = offset + (unsigned long long)blk;
-  const U4 r = philox4x32_10(U4{(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u}, k0, k1);
   float v[4];
-  {
-    float u1 = fmaxf(u32_to_unit(r.x), 1.0e-7f);
-    const float rad = sqrtf(-2.0f * logf(u1));
-    float s, c;
-    sincosf(6.283185307179586f * u32_to_unit(r.y), &s, &c);
-    v[0] = s * rad; v[1] = c * rad;
-    u1 = fmaxf(u32_to_unit(r.z), 1.0e-7f);
-    const float rad2 = sqrtf(-2.0f * logf(u1));
-    sincosf(6.283185307179586f * u32_to_unit(r.w), &s, &c);
-    v[2] = s * rad2; v[3] = c * rad2;
-  }
+  philox_normal4(ctr, k0, k1, v);
   if (i0 + 3 < n && (reinterpret_cast<uintptr_t>(out + i0) & 15) == 0) {
     *reinterpret_cast<float4*>(out + i0) = make_float4(v[0] * stddev, v[1] * stddev, v[2] * stddev, v[3] * stddev);
   } else {

@@ -29,3 +29,11 @@ class FlexibleNoiseGenerator(object):
                                                C.c_uint64(self._offset), stream))
         self._offset += (n + 3) // 4
         return out
+
+    def reserve(self, n_elements):
+        """Hands out the next `n_elements` of the stream WITHOUT materialising them: returns (std, seed, offset) for a
+        kernel that draws the same values itself (the generator's input packing, wdg_generator_forward_gen_noise) and
+        advances the generator exactly as `__call__` would."""
+        spec = (float(self.std), self._seed & (2 ** 64 - 1), self._offset)
+        self._offset += (int(n_elements) + 3) // 4
+        return spec

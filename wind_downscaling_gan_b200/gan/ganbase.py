@@ -52,8 +52,16 @@ class GAN:
         tensors (parity tests): per critic iteration [G noise, eps (B,), noise on real, noise on fake], then
         G noise for the generator update and for the metric recompute.  `comm` (train/dist.py Comm): data-parallel
         training, `data` being this rank's shard of the global batch."""
+        from .. import _lib
         from ..train.step import train_step
-        return train_step(self._state(), data[0], data[1], self.noise_generator, self._n_critic, draws, comm=comm)
+        before = _lib.calls
+        out = train_step(self._state(), data[0], data[1], self.noise_generator, self._n_critic, draws, comm=comm)
+        self._last_step_calls = _lib.calls - before
+        return out
+
+    def launches_per_step(self):
+        """Library entry points the last train_step called (each launches at least one kernel): bench.py's gpu_launches."""
+        return getattr(self, "_last_step_calls", None)
 
     def test_step(self, data, draws=None):
         """ganbase.py:96-113."""

@@ -221,6 +221,30 @@ class Generator(_NativeModel):
                                                     C.c_void_p(out.data_ptr()), C.c_void_p(s)))
         return out
 
+    def forward_device_gen_noise(self, image, noise_generator, out=None):
+        """`generator([image, noise_generator(bs, channels=Cn)])` with the noise drawn inside the input-packing kernel:
+        same values as materialising the tensor from `noise_generator` first (it is advanced identically), but the
+        (B,T,S,S,Cn) fp32 tensor is never written to or read from HBM.  image: contiguous fp32 CUDA tensor."""
+        import torch
+        assert image.is_cuda and image.dtype == torch.float32
+        image = image.contiguous()
+        B, T, S = image.shape[:3]
+        if tuple(image.shape[2:]) != (S, S, self.in_channels) or S != self.image_size:
+            raise ValueError(f"input_image: expected (B,T,{self.image_size},{self.image_size},{self.in_channels}), got {tuple(image.shape)}")
+        self._ensure_plan(B, T)
+        if out is None:
+            out = torch.empty((B, T, S, S, self.out_channels), dtype=torch.float32, device=image.device)
+        n = B * T * S * S * self.noise_channels
+        std, seed, offset = noise_generator.reserve(n)
+        scratch = None
+        if (self.in_channels, self.noise_channels) != (3, 20):
+            scratch = torch.empty(n, dtype=torch.float32, device=image.device)
+        s = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().wdg_generator_forward_gen_noise(
+            self._h, C.c_void_p(image.data_ptr()), std, C.c_uint64(seed), C.c_uint64(offset), C.c_void_p(out.data_ptr()),
+            C.c_void_p(scratch.data_ptr()) if scratch is not None else None, C.c_void_p(s)))
+        return out
+
     def predict_host(self, image, noise, out=None):
         """Host numpy (or CPU torch, ideally pinned) in, host numpy out: H2D copy, forward, D2H copy, sync --
         the call `gen.predict([tensor, noise])` of api.py:137 makes."""
@@ -253,12 +277,11 @@ class Generator(_NativeModel):
         self._ensure_plan(B, T)
         if out is None:
             out = torch.empty((B, T, S, S, self.out_channels), dtype=torch.float32)
-        n = B * T * S * S * self.noise_channels
+        std, seed, offset = noise_generator.reserve(B * T * S * S * self.noise_channels)
         s = torch.cuda.current_stream().cuda_stream
         _lib.check(_lib.lib().wdg_generator_predict_host_gen_noise(
-            self._h, C.c_void_p(img.data_ptr()), float(noise_generator.std), C.c_uint64(noise_generator._seed & (2 ** 64 - 1)),
-            C.c_uint64(noise_generator._offset), C.c_void_p(out.data_ptr()), C.c_void_p(self._io.data_ptr()), C.c_void_p(s)))
-        noise_generator._offset += (n + 3) // 4
+            self._h, C.c_void_p(img.data_ptr()), std, C.c_uint64(seed), C.c_uint64(offset), C.c_void_p(out.data_ptr()),
+            C.c_void_p(self._io.data_ptr()), C.c_void_p(s)))
         return out
 
     def predict(self, inputs, batch_size=None, verbose=0, **kwargs):

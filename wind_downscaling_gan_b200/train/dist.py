@@ -13,11 +13,34 @@ class Comm:
         self.enabled = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(group) if self.enabled else 1
         self.rank = dist.get_rank(group) if self.enabled else 0
+        self._events = []      # (start, stop) CUDA events around every collective since reset_timers()
+        self.timing = False
+
+    def reset_timers(self):
+        """Start recording the device time of every collective (CUDA events on the launching stream)."""
+        self._events, self.timing = [], True
+
+    def collective_ms(self):
+        """Device milliseconds spent in collectives since reset_timers() (synchronises)."""
+        if not self._events:
+            return 0.0
+        torch.cuda.synchronize()
+        return float(sum(a.elapsed_time(b) for a, b in self._events))
+
+    def _all_reduce(self, t):
+        if self.timing and t.is_cuda:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            b.record()
+            self._events.append((a, b))
+        else:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
 
     def allreduce_sum(self, t):
         """In-place sum over ranks of one tensor."""
         if self.world > 1:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            self._all_reduce(t)
         return t
 
     def allreduce_grads(self, grads, skip=()):
@@ -28,7 +51,7 @@ class Comm:
         if not names:
             return grads
         flat = torch.cat([grads[n].reshape(-1) for n in names])
-        self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group)
+        self._all_reduce(flat)
         off = 0
         for n in names:
             k = grads[n].numel()
