@@ -71,24 +71,30 @@ struct ConvParams {
   KBlock kb[MAX_KB];
 };
 
-template <int BN>
+// NSTAGE = 0: as many shared-memory stages as one CTA per SM can hold (long-K layers, throughput-bound).
+// NSTAGE = 3: a shallow ring sized so that TWO CTAs are resident per SM (short-K layers -- the 2x2 transposed conv has 3
+// K-blocks per tile, the border GEMM 15 -- whose tiles are a TMA -> MMA -> epilogue latency chain: the second CTA
+// fills the bubbles).  TMEM: 2 x BN columns per CTA, so two CTAs fit for BN <= 128.
+template <int BN, int NSTAGE = 0>
 struct ConvCfg {
   static constexpr int B_STAGE_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8);
+  static constexpr int STAGES = NSTAGE ? NSTAGE : ((BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8));
+  static constexpr int CTAS_PER_SM = (NSTAGE && NSTAGE * STAGE_BYTES <= 100 * 1024 && BN <= 128) ? 2 : 1;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int VEC_COLS = 512;   // per-column epilogue vectors (bias | scale | shift) staged in shared memory
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 3 * VEC_COLS * 4;
 };
 
 __device__ __forceinline__ float leaky02(float v) { return v >= 0.f ? v : 0.2f * v; }
 __device__ __forceinline__ float hard_sigmoid(float v) { return fminf(fmaxf(0.2f * v + 0.5f, 0.f), 1.f); }
 
-template <int BN, int EPI, int PREC>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int EPI, int PREC, int NSTAGE = 0>
+__global__ void __launch_bounds__(192, ConvCfg<BN, NSTAGE>::CTAS_PER_SM)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, NSTAGE>;
   using P = Prec<PREC>;
   using act_t = typename P::act_t;
   constexpr int STAGES = Cfg::STAGES;
@@ -102,6 +108,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  // Per-column epilogue vectors live in shared memory: read per 16-column group as warp-uniform LDS.128 broadcasts
+  // (from global memory each group cost a full L2 round trip that nothing overlapped -- ncu: long-scoreboard stalls on
+  // the first FADD of every group; the 3-K-block transposed conv spent most of its time there).
+  float* sm_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+  float* sm_scale = sm_bias + Cfg::VEC_COLS;
+  float* sm_shift = sm_scale + Cfg::VEC_COLS;
+  {
+    const int ncols = (EPI == EPI_UPCONV) ? 16 : p.n_tiles_N * BN;
+    for (int i = threadIdx.x; i < ncols && i < Cfg::VEC_COLS; i += blockDim.x) {
+      sm_bias[i] = p.ep.bias[i];
+      if constexpr (EPI != EPI_LSTM) { sm_scale[i] = p.ep.scale[i]; sm_shift[i] = p.ep.shift[i]; }
+    }
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -220,41 +239,38 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
       if constexpr (EPI == EPI_AFFINE) {
         const EpiParams& e = p.ep;
+        constexpr int GROUPS = (BN % 32 == 0) ? 2 : 1;      // 16-column groups per TMEM round trip
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + c0, r);
+        for (int c0 = 0; c0 < BN; c0 += 16 * GROUPS) {
+          uint32_t r[GROUPS][16];
+#pragma unroll
+          for (int g = 0; g < GROUPS; ++g) tmem_ld16(taddr + c0 + 16 * g, r[g]);
           tmem_ld_wait();
           if (valid) {
-            const int col = n_tile * BN + c0;
-            int oy = y, ox = x, oc = col;
-            if (e.out_mul == 2) {
-              const int g = col / e.group_cols;
-              oc = col - g * e.group_cols;
-              oy = 2 * y + (g >> 1);
-              ox = 2 * x + (g & 1);
-            }
-            const long long off = (long long)n * e.out_sn + (long long)oy * e.out_sy + (long long)ox * e.out_sx +
-                                  e.out_c0 + oc;
-            if (e.out_f32) {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + col) + i);
-                const float4 ss = __ldg(reinterpret_cast<const float4*>(e.scale + col) + i);
-                const float4 tt = __ldg(reinterpret_cast<const float4*>(e.shift + col) + i);
-                float a0 = __uint_as_float(r[4 * i]) + bb.x, a1 = __uint_as_float(r[4 * i + 1]) + bb.y;
-                float a2 = __uint_as_float(r[4 * i + 2]) + bb.z, a3 = __uint_as_float(r[4 * i + 3]) + bb.w;
-                if (e.lrelu) { a0 = leaky02(a0); a1 = leaky02(a1); a2 = leaky02(a2); a3 = leaky02(a3); }
-                dst[i] = make_float4(a0 * ss.x + tt.x, a1 * ss.y + tt.y, a2 * ss.z + tt.z, a3 * ss.w + tt.w);
+            for (int g = 0; g < GROUPS; ++g) {
+              const int col = n_tile * BN + c0 + 16 * g;
+              int oy = y, ox = x, oc = col;
+              if (e.out_mul == 2) {
+                const int grp = col / e.group_cols;
+                oc = col - grp * e.group_cols;
+                oy = 2 * y + (grp >> 1);
+                ox = 2 * x + (grp & 1);
               }
-            } else {
+              const long long off = (long long)n * e.out_sn + (long long)oy * e.out_sy + (long long)ox * e.out_sx +
+                                    e.out_c0 + oc;
               float v[16];
-              affine16(r, e.bias + col, e.scale + col, e.shift + col, e.lrelu != 0, v);
-              P::store16(reinterpret_cast<act_t*>(e.out) + off, v);
-              if (e.out2)
-                P::store16(reinterpret_cast<act_t*>(e.out2) + (long long)n * e.out2_sn + (long long)oy * e.out2_sy +
-                               (long long)ox * e.out2_sx + e.out2_c0 + oc, v);
+              affine16(r[g], sm_bias + col, sm_scale + col, sm_shift + col, e.lrelu != 0, v);
+              if (e.out_f32) {
+                float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              } else {
+                P::store16(reinterpret_cast<act_t*>(e.out) + off, v);
+                if (e.out2)
+                  P::store16(reinterpret_cast<act_t*>(e.out2) + (long long)n * e.out2_sn + (long long)oy * e.out2_sy +
+                                 (long long)ox * e.out2_sx + e.out2_c0 + oc, v);
+              }
             }
           }
         }
@@ -302,8 +318,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float a = leaky02(v[i] + __ldg(e.bias + i));
-              v[i] = a * __ldg(e.scale + i) + __ldg(e.shift + i);
+              const float a = leaky02(v[i] + sm_bias[i]);
+              v[i] = a * sm_scale[i] + sm_shift[i];
             }
             P::store16_exact(reinterpret_cast<act_t*>(e.out) + (long long)img * e.out_sn + (long long)Y * e.out_sy + X * 16, v);
           }
@@ -323,7 +339,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           tmem_ld_wait();
           if (valid) {
             const int ch0 = n_tile * 64 + s * 16;
-            const float* bias = e.bias + n_tile * 256 + s * 16;
+            const float* bias = sm_bias + n_tile * 256 + s * 16;
             float* cptr = e.c_state + pix * e.F + ch0;
             float cprev[16];
             if (e.first_step) {
@@ -339,10 +355,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             float cn[16], hn[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float gi = hard_sigmoid(__uint_as_float(zi[i]) + __ldg(bias + i));
-              const float gf = hard_sigmoid(__uint_as_float(zf[i]) + __ldg(bias + 64 + i));
-              const float gc = tanhf(__uint_as_float(zc[i]) + __ldg(bias + 128 + i));
-              const float go = hard_sigmoid(__uint_as_float(zo[i]) + __ldg(bias + 192 + i));
+              const float gi = hard_sigmoid(__uint_as_float(zi[i]) + bias[i]);
+              const float gf = hard_sigmoid(__uint_as_float(zf[i]) + bias[64 + i]);
+              const float gc = tanhf(__uint_as_float(zc[i]) + bias[128 + i]);
+              const float go = hard_sigmoid(__uint_as_float(zo[i]) + bias[192 + i]);
               cn[i] = gf * cprev[i] + gi * gc;
               hn[i] = go * tanhf(cn[i]);
             }

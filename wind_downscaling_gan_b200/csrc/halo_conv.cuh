@@ -61,9 +61,10 @@ template <int BN, int NCHUNK, int TPS>
 struct HaloCfg {
   static constexpr int B_STAGE_BYTES = TPS * BN * 128;
   static constexpr int A_BYTES = H_ABUFS * H_A_BYTES;
-  static constexpr int BSTAGES = (226 * 1024 - 1024 - 512 - A_BYTES) / B_STAGE_BYTES > 8
-                                     ? 8 : (226 * 1024 - 1024 - 512 - A_BYTES) / B_STAGE_BYTES;
-  static constexpr int SMEM = A_BYTES + BSTAGES * B_STAGE_BYTES + 1024 + 512;
+  static constexpr int VEC_BYTES = 3 * 128 * 4;   // bias | scale | shift of up to 128 columns, staged in shared memory
+  static constexpr int BSTAGES = (226 * 1024 - 1024 - 512 - VEC_BYTES - A_BYTES) / B_STAGE_BYTES > 8
+                                     ? 8 : (226 * 1024 - 1024 - 512 - VEC_BYTES - A_BYTES) / B_STAGE_BYTES;
+  static constexpr int SMEM = A_BYTES + BSTAGES * B_STAGE_BYTES + 1024 + 512 + VEC_BYTES;
   static constexpr int TMEM_COLS = (2 * H_TILES * BN <= 256) ? 256 : 512;
   static_assert(BSTAGES >= 2, "not enough shared memory for the B ring");
   static_assert(2 * H_TILES * BN <= 512, "accumulators exceed TMEM");
@@ -90,6 +91,13 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull = b_empty + BSTAGES;          // [2]
   uint64_t* tempty = tfull + 2;                 // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sm_bias = reinterpret_cast<float*>(smB + BSTAGES * Cfg::B_STAGE_BYTES + 512);   // see conv_umma.cuh
+  float* sm_scale = sm_bias + 128;
+  float* sm_shift = sm_scale + 128;
+  if constexpr (EPI != HEPI_FINAL) {
+    const int ncols = (EPI == HEPI_UPCONV) ? 16 : BN;
+    for (int i = threadIdx.x; i < ncols; i += blockDim.x) { sm_bias[i] = p.bias[i]; sm_scale[i] = p.scale[i]; sm_shift[i] = p.shift[i]; }
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -241,8 +249,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const float a = leaky02(v[i] + __ldg(p.bias + i));
-                v[i] = a * __ldg(p.scale + i) + __ldg(p.shift + i);
+                const float a = leaky02(v[i] + sm_bias[i]);
+                v[i] = a * sm_scale[i] + sm_shift[i];
               }
               P::store16_exact(reinterpret_cast<act_t*>(p.out) + (long long)img * p.up_sn + (long long)Y * p.up_sy + X * 16, v);
             }
@@ -273,8 +281,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tmem_ld_wait();
             if (valid) {
               float v0[16], v1[16];
-              affine16(r0, p.bias + c0, p.scale + c0, p.shift + c0, true, v0);
-              affine16(r1, p.bias + c0 + 16, p.scale + c0 + 16, p.shift + c0 + 16, true, v1);
+              affine16(r0, sm_bias + c0, sm_scale + c0, sm_shift + c0, true, v0);
+              affine16(r1, sm_bias + c0 + 16, sm_scale + c0 + 16, sm_shift + c0 + 16, true, v1);
               P::store16(d1 + c0, v0);
               P::store16(d1 + c0 + 16, v1);
               if (p.out2) {

@@ -241,9 +241,9 @@ __device__ __forceinline__ void affine16(const uint32_t (&acc)[16], const float*
                                          float (&out)[16]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q);
-    const float4 s = __ldg(reinterpret_cast<const float4*>(scale) + q);
-    const float4 t = __ldg(reinterpret_cast<const float4*>(shift) + q);
+    const float4 b = reinterpret_cast<const float4*>(bias)[q];      // shared-memory (or global) vectors, 16-byte aligned
+    const float4 s = reinterpret_cast<const float4*>(scale)[q];
+    const float4 t = reinterpret_cast<const float4*>(shift)[q];
     float a0 = __uint_as_float(acc[4 * q]) + b.x, a1 = __uint_as_float(acc[4 * q + 1]) + b.y;
     float a2 = __uint_as_float(acc[4 * q + 2]) + b.z, a3 = __uint_as_float(acc[4 * q + 3]) + b.w;
     if (lrelu) {

@@ -98,6 +98,7 @@ struct ConvLaunch {
   int bn;
   int epi;
   int grid;
+  int shallow = 0;   // 1: 3-stage ring, two CTAs per SM (short-K layers)
 };
 
 struct WeightDesc {
@@ -571,10 +572,11 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
   auto at = [&](uint8_t* base, long long elems) { return base + elems * esz; };   // element offset into an act_t buffer
   auto tmap = [&](CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* str, const uint32_t* box,
                   int inner_bytes = 128) { return make_tmap(tm, base, rank, dims, str, box, inner_bytes, esz); };
-  auto grid_for = [&](const ConvParams& p) {
+  auto grid_for = [&](const ConvParams& p, int ctas_per_sm = 1) {
     const int total = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_N;
-    return total < sms ? total : sms;
+    return total < sms * ctas_per_sm ? total : sms * ctas_per_sm;
   };
+  static const int shallow_mask = getenv("WDG_SHALLOW") ? atoi(getenv("WDG_SHALLOW")) : 7;   // bit 0: convT 2x2, 1: border GEMM, 2: conv 4x4
   // ---------------- L0: 8x8 s2 as 4x4 s1 on the s2d image X2 [N][Q][Q][4*CP], Q = (S+6)/2; dims (window 8*CP, X, Y, n)
   {
     ConvLaunch& c = pl.L0;
@@ -649,7 +651,7 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
         k.src = 0; k.half = 0; k.o0 = (int16_t)(kx * CI + c0); k.o1 = 0; k.o2 = (int16_t)(ky / 2); k.o3 = (int16_t)(ky % 2);
       }
     affine_epi(c.p.ep, g->bias2, g->sc2, g->sh2, pl.res4, (long long)S4 * S4 * F, (long long)S4 * F, F, 0, 1);
-    c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
+    c.bn = 128; c.epi = EPI_AFFINE; c.shallow = (shallow_mask >> 2) & 1; c.grid = grid_for(c.p, c.shallow ? 2 : 1);
   }
   // ---------------- ConvLSTM steps: A maps over (c, x, y, t, b) of res4 (x_t) and hseq (h_{t-1})
   {
@@ -761,7 +763,7 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
     const long long O = F / 4, ci = (long long)CI, PW = S2 + 4;
     affine_epi(c.p.ep, g->bias7, g->sc7, g->sh7, at(pl.catp, (2 * PW + 2) * ci), PW * PW * ci, PW * ci, ci, 0, 1);
     c.p.ep.out_mul = 2; c.p.ep.group_cols = (int)O;
-    c.bn = 128; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
+    c.bn = 128; c.epi = EPI_AFFINE; c.shallow = shallow_mask & 1; c.grid = grid_for(c.p, c.shallow ? 2 : 1);
   }
   const uint64_t I9 = F / 4 + 128;                          // channels of concat(g7, res_2)
   const int nch9 = (int)((I9 + kbe - 1) / kbe);             // 3 (bf16, the last chunk half full) / 5 (tf32)
@@ -793,7 +795,7 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       }
     affine_epi(c.p.ep, g->zero48, g->one48, g->zero48, pl.deltaD, (long long)S * 192, 0, 192, 0, 0);
     c.p.ep.out_f32 = 1;
-    c.bn = 48; c.epi = EPI_AFFINE; c.grid = grid_for(c.p);
+    c.bn = 48; c.epi = EPI_AFFINE; c.shallow = (shallow_mask >> 1) & 1; c.grid = grid_for(c.p, c.shallow ? 2 : 1);
   }
   // ---------------- L9: fused bilinear x2 + ConvT 5x5 on the flattened zero-padded concat image catp
   {
@@ -926,11 +928,12 @@ static bool fused_noise_ok(const wdg_generator* g) { return g->cin == 3 && g->cn
     }                                                                                                \
   } while (0)
 
-template <int BN, int EPI, int PREC>
+template <int BN, int EPI, int PREC, int NSTAGE = 0>
 static int launch_conv_t(const ConvLaunch& c, int device, cudaStream_t stream) {
-  auto kern = conv_umma_kernel<BN, EPI, PREC>;
-  ENSURE_SMEM(kern, device, ConvCfg<BN>::SMEM_BYTES);
-  kern<<<c.grid, 192, ConvCfg<BN>::SMEM_BYTES, stream>>>(c.tmA[0], c.tmA[1], c.tmA[2], c.tmB, c.p);
+  auto kern = conv_umma_kernel<BN, EPI, PREC, NSTAGE>;
+  using Cfg = ConvCfg<BN, NSTAGE>;
+  ENSURE_SMEM(kern, device, Cfg::SMEM_BYTES);
+  kern<<<c.grid, 192, Cfg::SMEM_BYTES, stream>>>(c.tmA[0], c.tmA[1], c.tmA[2], c.tmB, c.p);
   CK(cudaGetLastError());
   return 0;
 }
@@ -939,9 +942,9 @@ static int launch_conv(const ConvLaunch& c, int device, cudaStream_t stream) {
   if (c.epi == EPI_LSTM) return launch_conv_t<256, EPI_LSTM, PREC>(c, device, stream);
   if (c.epi == EPI_UPCONV) return launch_conv_t<64, EPI_UPCONV, PREC>(c, device, stream);
   switch (c.bn) {
-    case 128: return launch_conv_t<128, EPI_AFFINE, PREC>(c, device, stream);
+    case 128: return c.shallow ? launch_conv_t<128, EPI_AFFINE, PREC, 3>(c, device, stream) : launch_conv_t<128, EPI_AFFINE, PREC>(c, device, stream);
     case 64: return launch_conv_t<64, EPI_AFFINE, PREC>(c, device, stream);
-    case 48: return launch_conv_t<48, EPI_AFFINE, PREC>(c, device, stream);
+    case 48: return c.shallow ? launch_conv_t<48, EPI_AFFINE, PREC, 3>(c, device, stream) : launch_conv_t<48, EPI_AFFINE, PREC>(c, device, stream);
   }
   return fail("no kernel instantiated for this BN");
 }
@@ -1017,10 +1020,21 @@ static int run_plan_t(wdg_generator* g, const Plan& pl, const float* image_dev, 
     }
   }
   if (!done11) {
-    // tf32 path: the output layer (0.14 % of the MACs) runs in full fp32 on the CUDA cores, on the unrounded g9
+    // tf32 path: the output layer (0.14 % of the MACs) runs in full fp32 on the CUDA cores, on the unrounded g9.
+    // Measured, 512 fields: tiled + register-blocked 0.25 ms (shared-memory port and uniform-register weight loads bound),
+    // per-pixel gather form 0.41 ms; the bf16 super-pixel tensor-core form takes 0.078 ms, which is why bf16 keeps it.
     const long long G9C = g->F / 8, G9X = S + 8, G9Y = S + 2;
-    final_conv3x3_kernel<16, 2, PREC><<<(unsigned)((npix + 127) / 128), 128, 0, stream>>>(
-        (const act_t*)pl.g9 + (G9X + 4) * G9C, G9Y * G9X * G9C, G9X * G9C, g->w11h, out_dev, npix, (int)S);
+    const int smem = (FT_ROWS + 2) * ((int)S + 2) * FT_PITCH * (int)sizeof(float);
+    if (G9C == 16 && smem <= 200 * 1024) {
+      auto kern = final_conv3x3_tiled_kernel<PREC>;
+      ENSURE_SMEM(kern, dev, smem);
+      const unsigned blocks = (unsigned)(N * ((S + FT_ROWS - 1) / FT_ROWS));
+      // view starting at padded (row 0, col 3): the left zero ring pixel of the interior
+      kern<<<blocks, 192, smem, stream>>>((const act_t*)pl.g9 + 3 * G9C, G9Y * G9X * G9C, G9X * G9C, g->w11h, out_dev, (int)S);
+    } else {
+      final_conv3x3_kernel<16, 2, PREC><<<(unsigned)((npix + 127) / 128), 128, 0, stream>>>(
+          (const act_t*)pl.g9 + (G9X + 4) * G9C, G9Y * G9X * G9C, G9X * G9C, g->w11h, out_dev, npix, (int)S);
+    }
     CK(cudaGetLastError());
   }
   mark();
