@@ -163,6 +163,13 @@ int wdg_stitch_accum(const float* pred_dev, const int* starts_x_dev, int nx, con
 void wdg_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 int wdg_noise_normal(float* out_dev, long long n, float stddev, uint64_t seed, uint64_t offset, void* stream);
 
+/* Graph-capturable form: state_dev[0] = key, state_dev[1] = next counter block, both in device memory; the draw is
+ * followed by a one-thread kernel that advances the counter by ceil(n/4), so a replayed CUDA graph draws fresh noise. */
+int wdg_noise_normal_state(float* out_dev, long long n, float stddev, uint64_t* state_dev, void* stream);
+int wdg_rng_advance(uint64_t* state_dev, uint64_t blocks, void* stream);
+/* out[i] ~ U[0, 1) from the same device-resident stream (the interpolation weights of ganbase.py:30) */
+int wdg_uniform_state(float* out_dev, long long n, uint64_t* state_dev, void* stream);
+
 /* ---- building blocks of the WGAN training step (ganbase.py:21-94): critic forward/backward, training-mode
  * generator, optimiser.  Channels-last fp32 device tensors; `*_cs` / `*_co` = channel stride / offset of a tensor
  * inside a wider (concatenated) buffer.  geo[16] = {N, H, W, Ci, kh, kw, Co, stride, pad_top, pad_left, Ho, Wo,
@@ -231,6 +238,22 @@ int wdg_lstm_gates_bwd(float* gates, const float* c_prev, const float* c_cur, co
 int wdg_lstm_small_fwd(float* z, const float* h_prev, const float* R, const float* c_prev, float* c_out, float* h_out,
                        int N, int H, int W, int F, void* stream);
 int wdg_lstm_small_bwd_data(const float* dz, const float* R, float* dh_rec, int N, int H, int W, int F, void* stream);
+/* Cells with F = 16 filters (critic mixed branch, models.py:100-101), tensor-core training modes: ONE launch per
+ * timestep -- a TMA-fed tcgen05 (kind::tf32) recurrent convolution with the gate math in the TMEM epilogue.
+ * wdg_lstm16_pack: R [3][3][16][64] -> `packed` (WDG_LSTM16_PACK_FLOATS floats: forward and backward-data operands,
+ * rounded to tf32); call again whenever R changes.  wdg_lstm16_fwd_step (t >= 1): gates [N,H,W,64] holds the input
+ * convolution + bias of step t and receives the activated gates; h_prev / c_prev of step t-1; writes c_out, h_out (h_out
+ * rounded to tf32 -- it is only ever a GEMM operand; round h_0 of the unfused first step with wdg_round_tf32).
+ * wdg_lstm16_bwd_step: dz_next = dz of step s+1 (as left in its gates buffer); gates_s = activated gates of step s, receives
+ * dz_s; c_prev = c_{s-1} (NULL at s = 0), c_cur = c_s, dh = dL/dh_s from above, dc carried in place. */
+#define WDG_LSTM16_PACK_FWD_FLOATS (64 * 9 * 32)
+#define WDG_LSTM16_PACK_FLOATS (64 * 9 * 32 + 16 * 18 * 32)
+int wdg_lstm16_pack(const float* R, float* packed, void* stream);
+int wdg_round_tf32(float* x, long long n, void* stream);
+int wdg_lstm16_fwd_step(float* gates, const float* h_prev, const float* packed, const float* c_prev, float* c_out, float* h_out,
+                        int N, int H, int W, void* stream);
+int wdg_lstm16_bwd_step(const float* dz_next, const float* packed, float* gates_s, const float* c_prev, const float* c_cur,
+                        const float* dh, float* dc, int N, int H, int W, void* stream);
 /* UpSampling2D(2, bilinear) and its adjoint */
 int wdg_upsample2x_fwd(const float* x, float* y, long long n_img, int h, int w, int C, void* stream);
 int wdg_upsample2x_bwd(const float* dy, float* dx, long long n_img, int h, int w, int C, void* stream);
@@ -244,6 +267,11 @@ int wdg_gp_norm(const float* g, float* out, int B, long long per_sample_px, int 
 /* Keras Adam step (epsilon outside the square root) and one TFA SpectralNormalization power iteration (in place;
  * scratch >= (R + 64*C + 4) floats) */
 int wdg_adam(float* w, float* m, float* v, const float* g, long long n, float lr_t, float b1, float b2, float eps, void* stream);
+/* Graph-capturable Adam: wdg_adam_lr increments the device step counter t and writes lr_t = lr sqrt(1-b2^t)/(1-b1^t);
+ * wdg_adam_dev reads lr_t from device memory. */
+int wdg_adam_lr(float* lr_t_dev, int* step_dev, float lr, float b1, float b2, void* stream);
+int wdg_adam_dev(float* w, float* m, float* v, const float* g, long long n, const float* lr_t_dev, float b1, float b2, float eps,
+                 void* stream);
 int wdg_sn_update(float* w, float* u, int R, int C, void* scratch, void* stream);
 
 /* ---- on-device evaluation metrics (reference gan/metrics.py).  real / fake: fp32 [B,T,H,W,C].

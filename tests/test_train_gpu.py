@@ -170,3 +170,53 @@ def test_train_step_s96_t24_matches_golden():
             worst = max(worst, err / max(slack, 1e-30))
             assert err <= 2 * slack, (prefix, k, err, slack)
     print("worst projection error / slack:", worst)
+
+
+def test_graphed_train_step_equals_eager_and_syncs_weights():
+    """GAN.train_step captures the step into one CUDA graph after two eager calls.  Two GANs with identical weights and
+    noise seeds -- one replaying the graph, one forced eager -- stay bit-identical over 5 steps (same kernels, same
+    device-resident random stream, same Adam clocks); the handles see the trained weights without an explicit sync, and
+    writing weights into a handle restarts the optimizer state."""
+    import torch
+    from oracle.critic import synthetic_critic_weights
+    from oracle.generator import synthetic_generator_weights
+    from wind_downscaling_gan_b200.data.data_generator import FlexibleNoiseGenerator
+    from wind_downscaling_gan_b200.gan import train
+    from wind_downscaling_gan_b200.gan.ganbase import GAN
+    from wind_downscaling_gan_b200.gan.models import make_discriminator, make_generator
+    B, T, S = 2, 2, 32
+    rng, lr, hr = data(B, T, S, 9)
+    gw, dw = synthetic_generator_weights(7), synthetic_critic_weights(8, size=S)
+
+    def build(graph):
+        gen, disc = make_generator(S, 3, 20, 2, T), make_discriminator(S, S, 3, 2, T)
+        gen.set_weights(gw)
+        disc.set_weights(dw)
+        gan = GAN(gen, disc, FlexibleNoiseGenerator((B, T, S, S, 20), std=0.1, random_seed=5))
+        gan.use_cuda_graph = graph
+        gan.compile(generator_optimizer=train.generator_optimizer(), discriminator_optimizer=train.discriminator_optimizer(),
+                    discriminator_loss=train.discriminator_loss)
+        return gan
+
+    a, b = build(True), build(False)
+    for step in range(5):
+        ma, mb = a.train_step((lr, hr)), b.train_step((lr, hr))
+        assert ma == mb, (step, ma, mb)
+    assert a._graphed.graph is not None and b._graphed is None
+    assert a.noise_generator._offset == b.noise_generator._offset
+    assert a.generator.optimizer.iterations == b.generator.optimizer.iterations == 5
+    assert a.discriminator.optimizer.iterations == 15
+    wa, wb = a.generator.get_weights(), b.generator.get_weights()          # no sync_weights() call: pulled in lazily
+    assert all(np.array_equal(wa[k], wb[k]) for k in wa)
+    assert not np.array_equal(wa["layer_with_weights-4/cell/kernel"], gw["layer_with_weights-4/cell/kernel"])
+    # inference through the handle runs the TRAINED weights
+    noise = (0.1 * rng.standard_normal((B, T, S, S, 20))).astype(np.float32)
+    out_a = a.generator.predict([lr, noise])
+    fresh = make_generator(S, 3, 20, 2, T)
+    fresh.set_weights(wa)
+    assert np.array_equal(out_a, fresh.predict([lr, noise]))
+    # writing weights into a handle invalidates the training state (fresh Adam slots, clocks back to 0)
+    a.generator.set_weights(gw)
+    assert a._train is None and a.generator.optimizer.iterations == 0
+    m = a.train_step((lr, hr))
+    assert np.isfinite(m["d_loss"]) and a.generator.optimizer.iterations == 1

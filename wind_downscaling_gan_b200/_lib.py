@@ -79,6 +79,10 @@ def _declare(lib):
         "wdg_lstm_gates_bwd": [vp, vp, vp, vp, vp, vp, ll, i, vp],
         "wdg_lstm_small_fwd": [vp, vp, vp, vp, vp, vp, i, i, i, i, vp],
         "wdg_lstm_small_bwd_data": [vp, vp, vp, i, i, i, i, vp],
+        "wdg_lstm16_pack": [vp, vp, vp],
+        "wdg_round_tf32": [vp, ll, vp],
+        "wdg_lstm16_fwd_step": [vp, vp, vp, vp, vp, vp, i, i, i, vp],
+        "wdg_lstm16_bwd_step": [vp, vp, vp, vp, vp, vp, vp, i, i, i, vp],
         "wdg_upsample2x_fwd": [vp, vp, ll, i, i, i, vp],
         "wdg_upsample2x_bwd": [vp, vp, ll, i, i, i, vp],
         "wdg_dense_mean_fwd": [vp, vp, vp, vp, i, i, i, vp],
@@ -87,6 +91,11 @@ def _declare(lib):
         "wdg_gp_norm": [vp, vp, i, ll, i, vp],
         "wdg_adam": [vp, vp, vp, vp, ll, f, f, f, f, vp],
         "wdg_sn_update": [vp, vp, i, i, vp, vp],
+        "wdg_adam_lr": [vp, vp, f, f, f, vp],
+        "wdg_adam_dev": [vp, vp, vp, vp, ll, vp, f, f, f, vp],
+        "wdg_noise_normal_state": [vp, ll, f, vp, vp],
+        "wdg_rng_advance": [vp, C.c_uint64, vp],
+        "wdg_uniform_state": [vp, ll, vp, vp],
         "wdg_noise_normal": [vp, ll, f, C.c_uint64, C.c_uint64, vp],
         "wdg_metrics_pointwise_scratch": [i, C.POINTER(sz)],
         "wdg_metrics_pointwise": [vp, vp, i, ll, i, vp, vp, vp],

@@ -22,7 +22,7 @@ constexpr int MAX_KB = 80;
 constexpr int TILE_M = 128;
 constexpr int A_STAGE_BYTES = TILE_M * 128;
 
-enum { EPI_AFFINE = 0, EPI_LSTM = 1, EPI_UPCONV = 2 };
+enum { EPI_AFFINE = 0, EPI_LSTM = 1, EPI_UPCONV = 2, EPI_LSTM16_FWD = 3, EPI_LSTM16_BWD = 4 };
 
 struct KBlock {        // one slice of the GEMM K axis
   int8_t src;          // which A tensor map (0..2)
@@ -57,6 +57,18 @@ struct EpiParams {
   int h_pitch;                       // pixels per row of the (zero-ring padded) h image
   int first_step;                    // c_{t-1} = 0: skip the state read
   int F;
+  // ---- EPI_LSTM16_FWD / EPI_LSTM16_BWD: one recurrent step of the critic's 16-filter ConvLSTM2D in the TRAINING
+  //      path (fp32 tensors, pixel-major [n][H][W][C]; train_lstm16.cu).  FWD (BN = 64 = [i|f|c~|o] x 16): acc =
+  //      recurrent conv of h_{t-1}; t_gates holds the input conv + bias of this step and receives the activated gates;
+  //      writes c_t and h_t (h_t rounded to tf32: it is only ever a GEMM operand).  BWD (BN = 16): acc = recurrent
+  //      part of dL/dh_s carried from step s + 1; applies the gate backward of step s in place over t_gates (dz,
+  //      rounded to tf32) and updates the carried dL/dc.
+  float* t_gates;                    // [pix][64]
+  const float* t_c_prev;             // [pix][16] c_{s-1} (NULL: zero)
+  float* t_c;                        // FWD: c_t out; BWD: c_s in
+  float* t_h;                        // FWD: h_t out
+  const float* t_dh;                 // BWD: dL/dh_s from the layers above
+  float* t_dc;                       // BWD: in dL/dc_s carried, out dL/dc_{s-1}
 };
 
 struct ConvParams {
@@ -115,10 +127,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   float* sm_scale = sm_bias + Cfg::VEC_COLS;
   float* sm_shift = sm_scale + Cfg::VEC_COLS;
   {
-    const int ncols = (EPI == EPI_UPCONV) ? 16 : p.n_tiles_N * BN;
+    const int ncols = (EPI == EPI_UPCONV) ? 16 : ((EPI == EPI_LSTM16_FWD || EPI == EPI_LSTM16_BWD) ? 0 : p.n_tiles_N * BN);
     for (int i = threadIdx.x; i < ncols && i < Cfg::VEC_COLS; i += blockDim.x) {
       sm_bias[i] = p.ep.bias[i];
-      if constexpr (EPI != EPI_LSTM) { sm_scale[i] = p.ep.scale[i]; sm_shift[i] = p.ep.shift[i]; }
+      if constexpr (EPI == EPI_AFFINE || EPI == EPI_UPCONV) { sm_scale[i] = p.ep.scale[i]; sm_shift[i] = p.ep.shift[i]; }
     }
   }
 
@@ -322,6 +334,83 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               v[i] = a * sm_scale[i] + sm_shift[i];
             }
             P::store16_exact(reinterpret_cast<act_t*>(e.out) + (long long)img * e.out_sn + (long long)Y * e.out_sy + X * 16, v);
+          }
+        }
+      } else if constexpr (EPI == EPI_LSTM16_FWD) {
+        static_assert(EPI != EPI_LSTM16_FWD || BN == 64, "LSTM16 forward expects 4 gates x 16 channels");
+        const EpiParams& e = p.ep;
+        uint32_t zi[16], zf[16], zc[16], zo[16];
+        tmem_ld16(taddr + 0, zi);
+        tmem_ld16(taddr + 16, zf);
+        tmem_ld16(taddr + 32, zc);
+        tmem_ld16(taddr + 48, zo);
+        tmem_ld_wait();
+        if (valid) {
+          const long long pix = ((long long)n * p.H + y) * p.W + x;
+          float4* g4 = reinterpret_cast<float4*>(e.t_gates + pix * 64);
+          const float4* cp4 = reinterpret_cast<const float4*>(e.t_c_prev + pix * 16);
+          float4* c4 = reinterpret_cast<float4*>(e.t_c + pix * 16);
+          float4* h4 = reinterpret_cast<float4*>(e.t_h + pix * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 xi = g4[q], xf = g4[4 + q], xc = g4[8 + q], xo = g4[12 + q], cp = cp4[q];
+            const float xi_[4] = {xi.x, xi.y, xi.z, xi.w}, xf_[4] = {xf.x, xf.y, xf.z, xf.w};
+            const float xc_[4] = {xc.x, xc.y, xc.z, xc.w}, xo_[4] = {xo.x, xo.y, xo.z, xo.w}, cp_[4] = {cp.x, cp.y, cp.z, cp.w};
+            float gi[4], gf[4], gc[4], go[4], cn[4], hn[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              gi[k] = hard_sigmoid(__uint_as_float(zi[4 * q + k]) + xi_[k]);
+              gf[k] = hard_sigmoid(__uint_as_float(zf[4 * q + k]) + xf_[k]);
+              gc[k] = tanhf(__uint_as_float(zc[4 * q + k]) + xc_[k]);
+              go[k] = hard_sigmoid(__uint_as_float(zo[4 * q + k]) + xo_[k]);
+              cn[k] = gf[k] * cp_[k] + gi[k] * gc[k];
+              hn[k] = __uint_as_float(to_tf32(go[k] * tanhf(cn[k])));
+            }
+            g4[q] = make_float4(gi[0], gi[1], gi[2], gi[3]);
+            g4[4 + q] = make_float4(gf[0], gf[1], gf[2], gf[3]);
+            g4[8 + q] = make_float4(gc[0], gc[1], gc[2], gc[3]);
+            g4[12 + q] = make_float4(go[0], go[1], go[2], go[3]);
+            c4[q] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            h4[q] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          }
+        }
+      } else if constexpr (EPI == EPI_LSTM16_BWD) {
+        static_assert(EPI != EPI_LSTM16_BWD || BN == 16, "LSTM16 backward expects 16 channels");
+        const EpiParams& e = p.ep;
+        uint32_t r[16];
+        tmem_ld16(taddr, r);
+        tmem_ld_wait();
+        if (valid) {
+          const long long pix = ((long long)n * p.H + y) * p.W + x;
+          float4* g4 = reinterpret_cast<float4*>(e.t_gates + pix * 64);
+          const float4* cc4 = reinterpret_cast<const float4*>(e.t_c + pix * 16);
+          const float4* dh4 = reinterpret_cast<const float4*>(e.t_dh + pix * 16);
+          float4* dc4 = reinterpret_cast<float4*>(e.t_dc + pix * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 vi = g4[q], vf = g4[4 + q], vc = g4[8 + q], vo = g4[12 + q], cc = cc4[q], dh = dh4[q], dcv = dc4[q];
+            float4 cp = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e.t_c_prev) cp = reinterpret_cast<const float4*>(e.t_c_prev + pix * 16)[q];
+            const float gi[4] = {vi.x, vi.y, vi.z, vi.w}, gf[4] = {vf.x, vf.y, vf.z, vf.w}, gc[4] = {vc.x, vc.y, vc.z, vc.w};
+            const float go[4] = {vo.x, vo.y, vo.z, vo.w}, cc_[4] = {cc.x, cc.y, cc.z, cc.w}, dh_[4] = {dh.x, dh.y, dh.z, dh.w};
+            const float dc_[4] = {dcv.x, dcv.y, dcv.z, dcv.w}, cp_[4] = {cp.x, cp.y, cp.z, cp.w};
+            float di[4], df[4], dg[4], dov[4], dcn[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float tc = tanhf(cc_[k]);
+              const float dhv = dh_[k] + __uint_as_float(r[4 * q + k]);
+              const float dct = dc_[k] + dhv * go[k] * (1.f - tc * tc);
+              di[k] = __uint_as_float(to_tf32(dct * gc[k] * ((gi[k] > 0.f && gi[k] < 1.f) ? 0.2f : 0.f)));
+              df[k] = __uint_as_float(to_tf32(dct * cp_[k] * ((gf[k] > 0.f && gf[k] < 1.f) ? 0.2f : 0.f)));
+              dg[k] = __uint_as_float(to_tf32(dct * gi[k] * (1.f - gc[k] * gc[k])));
+              dov[k] = __uint_as_float(to_tf32(dhv * tc * ((go[k] > 0.f && go[k] < 1.f) ? 0.2f : 0.f)));
+              dcn[k] = dct * gf[k];
+            }
+            g4[q] = make_float4(di[0], di[1], di[2], di[3]);
+            g4[4 + q] = make_float4(df[0], df[1], df[2], df[3]);
+            g4[8 + q] = make_float4(dg[0], dg[1], dg[2], dg[3]);
+            g4[12 + q] = make_float4(dov[0], dov[1], dov[2], dov[3]);
+            dc4[q] = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
           }
         }
       } else {

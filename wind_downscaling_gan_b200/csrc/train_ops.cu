@@ -893,6 +893,22 @@ __global__ void adam_kernel(float* __restrict__ w, float* __restrict__ m, float*
   m[i] = mi; v[i] = vi;
   w[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
+// Graph-capturable form: the step counter and the bias-corrected learning rate live in device memory.
+__global__ void adam_lr_kernel(float* lr_t, int* step, float lr, float b1, float b2) {
+  const int t = ++(*step);
+  *lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+}
+__global__ void adam_dev_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
+                                long long n, const float* __restrict__ lr_t_dev, float b1, float b2, float eps) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lr_t = *lr_t_dev;
+  const float gi = g[i];
+  const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+  const float vi = v[i] + (gi * gi - v[i]) * (1.f - b2);
+  m[i] = mi; v[i] = vi;
+  w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
 // One power iteration of TFA SpectralNormalization on W = reshape(w, (R, C)):  v = l2n(u W^T); u' = l2n(v W);
 // sigma = v W u'^T; w /= sigma; u = u'.  Four small grid-wide kernels, every reduction in a fixed order
 // (deterministic, so data-parallel replicas stay bit-identical).  scratch: R + SN_SLABS*C + 4 floats.
@@ -1464,6 +1480,18 @@ extern "C" int wdg_gp_norm(const float* g, float* out, int B, long long per_samp
 extern "C" int wdg_adam(float* w, float* m, float* v, const float* g, long long n, float lr_t, float b1, float b2, float eps,
                         void* stream) {
   adam_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(w, m, v, g, n, lr_t, b1, b2, eps);
+  CKT(cudaGetLastError());
+  return 0;
+}
+extern "C" int wdg_adam_lr(float* lr_t_dev, int* step_dev, float lr, float b1, float b2, void* stream) {
+  if (!lr_t_dev || !step_dev) return wdg_set_error("null argument");
+  adam_lr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(lr_t_dev, step_dev, lr, b1, b2);
+  CKT(cudaGetLastError());
+  return 0;
+}
+extern "C" int wdg_adam_dev(float* w, float* m, float* v, const float* g, long long n, const float* lr_t_dev, float b1, float b2,
+                            float eps, void* stream) {
+  adam_dev_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(w, m, v, g, n, lr_t_dev, b1, b2, eps);
   CKT(cudaGetLastError());
   return 0;
 }

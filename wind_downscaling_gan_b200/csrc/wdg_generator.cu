@@ -62,8 +62,8 @@ static EncodeTiledFn get_encode() {
 
 // Tensor map of rank 2..5 over bf16 (esz 2) or fp32 (esz 4: tf32 operands) elements.  dims/box in elements (dim 0
 // innermost), strides in ELEMENTS for dims 1..rank-1.
-static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
-                     const uint32_t* box, int inner_bytes, int esz) {
+int wdg_make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                  const uint32_t* box, int inner_bytes, int esz) {   // shared with train_lstm16.cu
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint64_t gdim[5], gstr[4];
@@ -571,7 +571,7 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
   const int sms = g->sm_count;
   auto at = [&](uint8_t* base, long long elems) { return base + elems * esz; };   // element offset into an act_t buffer
   auto tmap = [&](CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* str, const uint32_t* box,
-                  int inner_bytes = 128) { return make_tmap(tm, base, rank, dims, str, box, inner_bytes, esz); };
+                  int inner_bytes = 128) { return wdg_make_tmap(tm, base, rank, dims, str, box, inner_bytes, esz); };
   auto grid_for = [&](const ConvParams& p, int ctas_per_sm = 1) {
     const int total = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_N;
     return total < sms * ctas_per_sm ? total : sms * ctas_per_sm;

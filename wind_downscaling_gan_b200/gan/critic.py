@@ -56,6 +56,8 @@ class Critic:
         self.metrics = []
         self._shapes = critic_weight_shapes(high_res_size, low_res_channels, high_res_channels, feature_channels)
         self._dev = None
+        self._before_read = None     # hooks of an owning GAN, see gan/models.py
+        self._after_write = None
         rng = np.random.default_rng(seed)
         w = {}
         for name, shp in self._shapes.items():
@@ -85,7 +87,12 @@ class Critic:
     def trainable_weights(self):
         return [n for n in self._shapes if not n.endswith("sn_u")]
 
-    def set_weights(self, weights):
+    def set_weights(self, weights, _from_state=False):
+        if not _from_state:
+            if self._before_read is not None:
+                self._before_read()
+            if self._after_write is not None:
+                self._after_write()
         for name, arr in weights.items():
             if name not in self._shapes:
                 raise KeyError(name)
@@ -96,12 +103,14 @@ class Critic:
         self._dev = None
 
     def get_weights(self):
+        if self._before_read is not None:
+            self._before_read()
         return {k: v.copy() for k, v in self._w.items()}
 
     def save_weights(self, filepath, *args, **kwargs):
         filepath = str(filepath)
         os.makedirs(os.path.dirname(filepath) or ".", exist_ok=True)
-        np.savez(filepath + ".npz", **self._w)
+        np.savez(filepath + ".npz", **self.get_weights())
 
     def load_weights(self, filepath, *args, **kwargs):
         filepath = str(filepath)
@@ -110,9 +119,8 @@ class Critic:
                 self.set_weights({k: z[k] for k in z.files})
             return
         if os.path.exists(filepath + ".index"):
-            from ..tf_checkpoint import read_bundle
-            tensors = read_bundle(filepath)
-            self.set_weights({k: v for k, v in tensors.items() if k in self._shapes})
+            from ..tf_checkpoint import read_bundle, select_model_variables
+            self.set_weights(select_model_variables(read_bundle(filepath), self._shapes, "discriminator"))
             return
         raise FileNotFoundError(filepath)
 
@@ -126,6 +134,8 @@ class Critic:
         from ..train.step import _dev
         from ..train import ops as _ops
         _ops.use_current_stream()
+        if self._before_read is not None:
+            self._before_read()
         if self._dev is None:
             self._dev = to_device(self._w)
         low_res, high_res = _dev(inputs[0]), _dev(inputs[1])
@@ -134,6 +144,8 @@ class Critic:
         score = CriticNet(self._dev, self.image_size).forward(low_res, high_res, training=bool(training))
         if training:   # the spectral-norm power iteration mutated w / sn_u in place, as the Keras wrapper does
             self._w = {k: v.cpu().numpy() for k, v in self._dev.items()}
+            if self._after_write is not None:
+                self._after_write()
         return score
 
     call = __call__

@@ -19,6 +19,13 @@ class GAN:
         self.compiled_metrics = None
         self.metrics = []
         self._train = None   # lazily built device-side training state
+        self._graphed = None
+        self.use_cuda_graph = os.environ.get("WDG_TRAIN_GRAPH", "1") != "0"
+        # One set of variables, as in Keras: the trained weights live in the device-side TrainState; the model handles
+        # pull them in lazily before anything reads them, and writing weights into a handle drops the TrainState.
+        for m in (generator, discriminator):
+            if m is not None and hasattr(m, "_before_read"):
+                m._before_read, m._after_write = self.sync_weights, self._invalidate_state
 
     def compile(self, generator_optimizer, discriminator_optimizer, generator_loss=None, generator_metrics=None,
                 discriminator_loss=None, **kwargs):
@@ -45,7 +52,18 @@ class GAN:
             if self.reconstruction_loss is not None:
                 raise NotImplementedError("reconstruction_loss (autoencoder features) is outside the built path")
             self._train = TrainState(self.generator, self.discriminator, self.generator.optimizer, self.discriminator.optimizer)
+            self._graphed = None
         return self._train
+
+    def _invalidate_state(self):
+        """A handle's weights were written (set_weights / load_weights / training-mode call): the next train_step starts
+        from them, with fresh Adam slots and the optimizers' step counters reset -- a reload restarts the optimizer."""
+        if self._train is not None:
+            self._train = None
+            self._graphed = None
+            for m in (self.generator, self.discriminator):
+                if m is not None and getattr(m, "optimizer", None) is not None and hasattr(m.optimizer, "iterations"):
+                    m.optimizer.iterations = 0
 
     def train_step(self, data, draws=None, comm=None):
         """ganbase.py:21-94.  data = (low_res, high_res[, sample_weight]); `draws` optionally replaces the random
@@ -53,10 +71,20 @@ class GAN:
         G noise for the generator update and for the metric recompute.  `comm` (train/dist.py Comm): data-parallel
         training, `data` being this rank's shard of the global batch."""
         from .. import _lib
-        from ..train.step import train_step
+        from ..train.step import GraphedStep, train_step
+        st = self._state()
         before = _lib.calls
-        out = train_step(self._state(), data[0], data[1], self.noise_generator, self._n_critic, draws, comm=comm)
-        self._last_step_calls = _lib.calls - before
+        if draws is None and self.use_cuda_graph:
+            # steady state: the whole step is ONE captured CUDA graph (train/step.py: GraphedStep); the first calls run
+            # eagerly and size every buffer
+            if self._graphed is None or self._graphed.comm is not comm:
+                self._graphed = GraphedStep(st, self.noise_generator, self._n_critic, comm)
+            out = self._graphed(data[0], data[1])
+            if self._graphed.graph is None or self._graphed.calls == GraphedStep.WARMUP + 1:
+                self._last_step_calls = _lib.calls - before      # launches of one step, counted while it ran eagerly / was captured
+        else:
+            out = train_step(st, data[0], data[1], self.noise_generator, self._n_critic, draws, comm=comm)
+            self._last_step_calls = _lib.calls - before
         return out
 
     def launches_per_step(self):
@@ -69,8 +97,9 @@ class GAN:
         return test_step(self._state(), data[0], data[1], self.noise_generator, draws)
 
     def sync_weights(self):
-        """Copies the trained fp32 device weights back into the model handles (inference path, save_weights)."""
-        if self._train is not None:
+        """Copies the trained fp32 device weights back into the model handles.  Called automatically (lazily) before a
+        handle is read -- predict / call / get_weights / save_weights -- so trained weights are what inference runs."""
+        if self._train is not None and self._train.dirty:
             self._train.push_weights()
 
     def save_weights(self, filepath, *args, **kwargs):
@@ -83,4 +112,4 @@ class GAN:
         self.generator.load_weights(Path(filepath) / 'generator', *args, **kwargs)
         if self.discriminator is not None:
             self.discriminator.load_weights(Path(filepath) / 'discriminator', *args, **kwargs)
-        self._train = None
+        self._invalidate_state()

@@ -80,6 +80,10 @@ class Generator(_NativeModel):
         self._plan = None      # (B, T)
         self._ws = None
         self._io = None
+        # hooks of an owning GAN: trained weights live in its device-side TrainState and are pulled in lazily before
+        # anything reads this handle; writing weights here invalidates that state (one set of variables, as in Keras)
+        self._before_read = None
+        self._after_write = None
         self.precision = "bf16"
         self.set_precision(precision or os.environ.get("WDG_PRECISION", "bf16"))
         self._init_weights(np.random.default_rng(seed))
@@ -135,8 +139,13 @@ class Generator(_NativeModel):
     def trainable_weights(self):
         return [n for n in self._shapes if not n.endswith(("moving_mean", "moving_variance", "sn_u"))]
 
-    def set_weights(self, weights):
+    def set_weights(self, weights, _from_state=False):
         """weights: dict name -> array, names/layouts of weights-55.ckpt/generator.index."""
+        if not _from_state:
+            if self._before_read is not None:
+                self._before_read()          # a partial update must land on top of the trained weights
+            if self._after_write is not None:
+                self._after_write()
         L = _lib.lib()
         for name, arr in weights.items():
             if name not in self._shapes:
@@ -149,6 +158,8 @@ class Generator(_NativeModel):
         self._dirty = True
 
     def get_weights(self):
+        if self._before_read is not None:
+            self._before_read()
         L = _lib.lib()
         out = {}
         for name, shp in self._shapes.items():
@@ -173,9 +184,8 @@ class Generator(_NativeModel):
                 self.set_weights({k: z[k] for k in z.files})
             return
         if os.path.exists(filepath + ".index"):
-            from ..tf_checkpoint import read_bundle
-            tensors = read_bundle(filepath)
-            self.set_weights({k: v for k, v in tensors.items() if k in self._shapes})
+            from ..tf_checkpoint import read_bundle, select_model_variables
+            self.set_weights(select_model_variables(read_bundle(filepath), self._shapes, "generator"))
             return
         raise FileNotFoundError(filepath)
 
@@ -183,6 +193,8 @@ class Generator(_NativeModel):
     def _ensure_plan(self, B, T, stream=None):
         import torch
         L = _lib.lib()
+        if self._before_read is not None:
+            self._before_read()
         if self._dirty:
             _lib.check(L.wdg_generator_finalize(self._h))
             self._dirty = False

@@ -163,3 +163,25 @@ def write_bundle(prefix, tensors):
         f.write(out)
     with open(prefix + ".data-00000-of-00001", "wb") as f:
         f.write(data)
+
+
+def select_model_variables(tensors, shapes, model_name):
+    """Model variables of a checkpoint bundle, checked against the model's own table (`shapes`: name -> shape).
+
+    The bundle also holds optimizer slots and object-graph bookkeeping, which are skipped; but a model variable that
+    the checkpoint lacks, a `layer_with_weights-*` variable the model does not have, or a shape mismatch means the
+    checkpoint was written by a DIFFERENT topology (the reference's shipped critic checkpoint has the shortcut branch,
+    SURVEY F6) and a silent partial load would leave layers at their random initialisation: raise instead."""
+    def is_model_var(k):
+        return k.startswith("layer_with_weights-") and "/.OPTIMIZER_SLOT" not in k and not k.endswith("/.ATTRIBUTES/OBJECT_CONFIG_JSON")
+    missing = sorted(k for k in shapes if k not in tensors)
+    extra = sorted(k for k in tensors if is_model_var(k) and k not in shapes)
+    wrong = sorted(k for k in shapes if k in tensors and tuple(tensors[k].shape) != tuple(shapes[k]))
+    if missing or extra or wrong:
+        def head(v):
+            return ", ".join(v[:4]) + (f", ... ({len(v)} in all)" if len(v) > 4 else "")
+        raise ValueError(f"{model_name} checkpoint does not match this model's topology: "
+                         + "; ".join(t for t in (f"missing from the checkpoint: {head(missing)}" if missing else "",
+                                                 f"in the checkpoint but not in the model: {head(extra)}" if extra else "",
+                                                 f"shape mismatch: {head(wrong)}" if wrong else "") if t))
+    return {k: tensors[k] for k in shapes}

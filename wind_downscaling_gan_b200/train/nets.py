@@ -169,14 +169,24 @@ class ConvLSTM:
         # the input convolution (+ bias) of every timestep is one GEMM; only the recurrent convolution is serial
         ops.conv2d_fwd(full(xt.view(T * B, H, W, Cin)), self.K, self.b, full(gates.view(T * B, H, W, 4 * F)), T * B, H, W, 1, 1, H, W)
         small = F in ops.SMALL_LSTM_FILTERS and tuple(self.R.shape[:2]) == (3, 3)
+        fused16 = F == 16 and tuple(self.R.shape[:2]) == (3, 3) and ops.lstm16_fused()
+        packed = ops.lstm16_pack(self.R) if fused16 else None
         for t in range(T):
             if small:      # recurrent conv + gates in one bandwidth-bound pass (critic high-resolution branch)
                 ops.lstm_small_fwd(gates[t], hs[t - 1] if t > 0 else None, self.R, cs[t - 1] if t > 0 else None, cs[t], hs[t])
+                continue
+            if fused16:    # critic mixed branch: recurrent conv (tcgen05) + gates in ONE launch per step
+                if t == 0:
+                    ops.lstm_gates_fwd(gates[0], None, cs[0], hs[0])
+                    ops.round_tf32(hs[0])
+                else:
+                    ops.lstm16_fwd_step(gates[t], hs[t - 1], packed, cs[t - 1], cs[t], hs[t])
                 continue
             if t > 0:
                 ops.conv2d_fwd(full(hs[t - 1]), self.R, None, full(gates[t]), B, H, W, 1, 1, H, W, accumulate=True)
             ops.lstm_gates_fwd(gates[t], cs[t - 1] if t > 0 else None, cs[t], hs[t])
         self.ctx = (xt, hs, cs, gates, B, T, H, W, Cin, F)
+        self.packed = packed
         return ops.transpose01(hs).view(B * T, H, W, F)
 
     def backward(self, dh_seq, need_dx=True, need_dw=True):
@@ -187,7 +197,14 @@ class ConvLSTM:
         dc = ops.zeros(B, H, W, F)
         dh_rec = ops.empty(B, H, W, F)
         small = F in ops.SMALL_LSTM_FILTERS and tuple(self.R.shape[:2]) == (3, 3)
-        for t in range(T - 1, -1, -1):            # serial part: gate backward and the recurrent backward-data
+        fused16 = getattr(self, "packed", None) is not None
+        if fused16:      # step T-1 has no recurrent gradient; every earlier step is one fused launch:
+            # recurrent backward-data of dz_{t+1} (tcgen05) + gate backward of step t in the epilogue
+            ops.lstm_gates_bwd(gates[T - 1], cs[T - 2] if T > 1 else None, cs[T - 1], dhs[T - 1], dc, None)
+            ops.round_tf32(gates[T - 1])
+            for t in range(T - 2, -1, -1):
+                ops.lstm16_bwd_step(gates[t + 1], self.packed, gates[t], cs[t - 1] if t > 0 else None, cs[t], dhs[t], dc)
+        for t in range(T - 1, -1, -1) if not fused16 else ():            # serial part: gate backward and the recurrent backward-data
             ops.lstm_gates_bwd(gates[t], cs[t - 1] if t > 0 else None, cs[t], dhs[t], dc,
                                dh_rec if t < T - 1 else None)                            # gates[t] now holds dz_t
             if t > 0:
@@ -227,8 +244,10 @@ class GenNet:
         self.w = weights   # dict name -> CUDA tensor (shared with the caller; updated in place)
         self.comm = comm   # data-parallel communicator: synchronised BatchNorm statistics
 
-    def forward(self, image, noise, training):
-        """image [B,T,S,S,Cin], noise [B,T,S,S,Cn] -> [B,T,S,S,Cout].  Keeps the context for backward()."""
+    def forward(self, image, noise, training, keep_context=True):
+        """image [B,T,S,S,Cin], noise [B,T,S,S,Cn] -> [B,T,S,S,Cout].  Keeps the context for backward() unless
+        keep_context is False (the critic-loop and metric forwards of train_step are never differentiated: dropping their
+        saved activations returns ~3 GB per call to the allocator)."""
         w = self.w
         B, T, S = image.shape[:3]
         N = B * T
@@ -276,7 +295,7 @@ class GenNet:
         r9 = L["bn10"].forward(a9.t, training)                                                 # :69
         L["c11"] = Conv(w[(LW % 11) + "layer/kernel"], w[(LW % 11) + "layer/bias"], 1, 1, leaky=False)      # :70
         out = L["c11"].forward(full(r9), N, S, S)
-        self.L, self.dims = L, (B, T, S, N, F, r2.shape[-1])
+        self.L, self.dims = (L if keep_context else None), (B, T, S, N, F, r2.shape[-1])
         return out.t.view(B, T, S, S, -1)
 
     def backward(self, dout):

@@ -193,6 +193,33 @@ def lstm_small_bwd_data(dz, R, dh_rec):
     _lib.check(_lib.lib().wdg_lstm_small_bwd_data(_p(dz), _p(R), _p(dh_rec), N, H, W, Fc, _s()))
 
 
+def lstm16_fused():
+    """The 16-filter cell runs its recurrent steps as fused tcgen05 launches in the tensor-core training modes."""
+    import os
+    return get_precision() != "fp32" and not os.environ.get("WDG_NO_LSTM16")
+
+
+def lstm16_pack(R):
+    """R [3,3,16,64] -> packed forward / backward-data operands of the fused recurrent steps (tf32)."""
+    packed = torch.empty(64 * 9 * 32 + 16 * 18 * 32, dtype=F32, device="cuda")
+    _lib.check(_lib.lib().wdg_lstm16_pack(_p(R), _p(packed), _s()))
+    return packed
+
+
+def round_tf32(x):
+    _lib.check(_lib.lib().wdg_round_tf32(_p(x), x.numel(), _s()))
+
+
+def lstm16_fwd_step(gates, h_prev, packed, c_prev, c_out, h_out):
+    N, H, W, _ = c_out.shape
+    _lib.check(_lib.lib().wdg_lstm16_fwd_step(_p(gates), _p(h_prev), _p(packed), _p(c_prev), _p(c_out), _p(h_out), N, H, W, _s()))
+
+
+def lstm16_bwd_step(dz_next, packed, gates_s, c_prev, c_cur, dh, dc):
+    N, H, W, _ = c_cur.shape
+    _lib.check(_lib.lib().wdg_lstm16_bwd_step(_p(dz_next), _p(packed), _p(gates_s), _p(c_prev), _p(c_cur), _p(dh), _p(dc), N, H, W, _s()))
+
+
 def upsample2x_fwd(x, y):
     n, h, w, Cc = x.shape
     _lib.check(_lib.lib().wdg_upsample2x_fwd(_p(x), _p(y), n, h, w, Cc, _s()))
@@ -219,6 +246,12 @@ def reduce(a, mode=0, b=None, scale=1.0):
     return out
 
 
+def reduce_into(out, a, mode=0, b=None, scale=1.0):
+    """out[0] = scale * sum(a | a*b | a*a), `out` a 1-element view of a device buffer (no host round trip)."""
+    sc = scratch(1024 * 8, "reduce")
+    _lib.check(_lib.lib().wdg_reduce(mode, _p(a), _p(b), a.numel(), scale, _p(out), _p(sc), _s()))
+
+
 def gp_norm(g, out):
     B, Cc = g.shape[0], g.shape[-1]
     _lib.check(_lib.lib().wdg_gp_norm(_p(g), _p(out), B, g.numel() // (B * Cc), Cc, _s()))
@@ -226,6 +259,15 @@ def gp_norm(g, out):
 
 def adam(w, m, v, g, lr_t, b1, b2, eps):
     _lib.check(_lib.lib().wdg_adam(_p(w), _p(m), _p(v), _p(g), w.numel(), lr_t, b1, b2, eps, _s()))
+
+
+def adam_lr(lr_t, step, lr, b1, b2):
+    """step += 1; lr_t = lr * sqrt(1 - b2^step) / (1 - b1^step), both device scalars."""
+    _lib.check(_lib.lib().wdg_adam_lr(_p(lr_t), _p(step), lr, b1, b2, _s()))
+
+
+def adam_dev(w, m, v, g, lr_t, b1, b2, eps):
+    _lib.check(_lib.lib().wdg_adam_dev(_p(w), _p(m), _p(v), _p(g), w.numel(), _p(lr_t), b1, b2, eps, _s()))
 
 
 def sn_update(w, u):
