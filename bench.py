@@ -461,6 +461,17 @@ def run_training(args):
     launches = gan.launches_per_step() if hasattr(gan, "launches_per_step") else None
     step_e2e()
     ms_e2e = D.timed(step_e2e, args.steps)
+    # extension, reported beside the headline: the gradient-penalty passes whose result nothing uses are skipped
+    # (bit-identical weights and metrics, tests/test_train_gpu.py); the headline `value` runs every pass of ganbase.py:21-94
+    gen2, disc2 = make_generator(S, 3, 20, 2, TT), make_discriminator(S, S, 3, 2, TT)
+    gen2.set_weights(synthetic_generator_weights(0))
+    disc2.set_weights(synthetic_critic_weights(1, size=S))
+    gan2 = GAN(gen2, disc2, FlexibleNoiseGenerator((TB, TT, S, S, 20), std=0.1, random_seed=100 + D.rank), skip_dead_gradient_penalty=True)
+    gan2.compile(generator_optimizer=train.generator_optimizer(), discriminator_optimizer=train.discriminator_optimizer(),
+                 discriminator_loss=train.discriminator_loss, train_precision=args.precision)
+    for _ in range(args.warmup):
+        gan2.train_step((lr_d, hr_d), comm=comm)
+    ms_skip = D.timed(lambda: gan2.train_step((lr_d, hr_d), comm=comm), args.steps)
     if D.rank == 0:
         samples = D.world * TB / (ms_step * 1e-3)
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12     # FMA lanes x 2 flop x max SM clock
@@ -487,6 +498,9 @@ def run_training(args):
                 "gpu_launches": launches * args.steps if launches else None,
                 "collective": {"allreduce_ms_per_step": ar_ms, "share_of_step": ar_ms / ms_step if ms_step else None,
                                "note": "device time of the NCCL collectives (gradient buckets + BatchNorm statistics), CUDA events on the launch stream"},
+                "dead_gradient_penalty_skipped": {"value": D.world * TB / (ms_skip * 1e-3), "unit": "samples/s", "ms_per_step": ms_skip,
+                                                  "note": "GAN(..., skip_dead_gradient_penalty=True): same weights and metrics bit for bit; NOT the headline"},
+                "cuda_graph": bool(getattr(gan, "_graphed", None) is not None and gan._graphed.graph is not None),
                 "clocks": clocks,
                 "roofline": {"kernel": "whole train_step (many kernels)", "bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,

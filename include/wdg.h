@@ -254,6 +254,14 @@ int wdg_lstm16_fwd_step(float* gates, const float* h_prev, const float* packed, 
                         int N, int H, int W, void* stream);
 int wdg_lstm16_bwd_step(const float* dz_next, const float* packed, float* gates_s, const float* c_prev, const float* c_cur,
                         const float* dh, float* dc, int N, int H, int W, void* stream);
+/* Generator block Concatenate([a, b]) -> UpSampling2D(2, bilinear) -> Conv2DTranspose(16, 5x5, same) + bias -> LeakyReLU(0.2)
+ * (models.py:60-64) in ONE fused pass for the training forward (tensor-core modes): a [N,h,h,32], b [N,h,h,128] dense fp32
+ * -> out [N,2h,2h,16] dense fp32 (pre-BatchNorm).  w is the layer's kernel [5][5][16][160]; the 4x4 phase weights and the
+ * border-correction weights are composed from it on the device at every call (the optimizer changes it every step).
+ * tf32 operands, fp32 accumulation.  workspace: wdg_upconv5x5_workspace_bytes(N, h), 1024-byte aligned. */
+int wdg_upconv5x5_workspace_bytes(long long N, int h, size_t* bytes);
+int wdg_upconv5x5_fwd(const float* a, const float* b, const float* w, const float* bias, float* out, long long N, int h,
+                      void* workspace, size_t ws_bytes, void* stream);
 /* UpSampling2D(2, bilinear) and its adjoint */
 int wdg_upsample2x_fwd(const float* x, float* y, long long n_img, int h, int w, int C, void* stream);
 int wdg_upsample2x_bwd(const float* dy, float* dx, long long n_img, int h, int w, int C, void* stream);

@@ -220,3 +220,32 @@ def test_graphed_train_step_equals_eager_and_syncs_weights():
     assert a._train is None and a.generator.optimizer.iterations == 0
     m = a.train_step((lr, hr))
     assert np.isfinite(m["d_loss"]) and a.generator.optimizer.iterations == 1
+
+
+def test_skipping_the_dead_gradient_penalty_passes_changes_nothing():
+    """GAN(..., skip_dead_gradient_penalty=True) drops the interpolate -> critic -> input-gradient passes of all but the last
+    critic iteration (their result reaches neither the weights nor the log): metrics and weights bit-identical."""
+    from oracle.critic import synthetic_critic_weights
+    from oracle.generator import synthetic_generator_weights
+    from wind_downscaling_gan_b200.data.data_generator import FlexibleNoiseGenerator
+    from wind_downscaling_gan_b200.gan import train
+    from wind_downscaling_gan_b200.gan.ganbase import GAN
+    from wind_downscaling_gan_b200.gan.models import make_discriminator, make_generator
+    B, T, S = 2, 2, 32
+    _, lr, hr = data(B, T, S, 10)
+    gw, dw = synthetic_generator_weights(7), synthetic_critic_weights(8, size=S)
+    out = []
+    for skip in (False, True):
+        gen, disc = make_generator(S, 3, 20, 2, T), make_discriminator(S, S, 3, 2, T)
+        gen.set_weights(gw)
+        disc.set_weights(dw)
+        gan = GAN(gen, disc, FlexibleNoiseGenerator((B, T, S, S, 20), std=0.1, random_seed=3), skip_dead_gradient_penalty=skip)
+        gan.use_cuda_graph = False
+        gan.compile(generator_optimizer=train.generator_optimizer(), discriminator_optimizer=train.discriminator_optimizer(),
+                    discriminator_loss=train.discriminator_loss)
+        ms = [gan.train_step((lr, hr)) for _ in range(2)]
+        out.append((ms, gen.get_weights(), disc.get_weights(), gan.launches_per_step()))
+    (ma, ga, da, la), (mb, gb, db, lb) = out
+    assert ma == mb
+    assert all(np.array_equal(ga[k], gb[k]) for k in ga) and all(np.array_equal(da[k], db[k]) for k in da)
+    assert lb < la

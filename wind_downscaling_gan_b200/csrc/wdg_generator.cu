@@ -1225,3 +1225,186 @@ extern "C" int wdg_generator_debug_read(const wdg_generator* g, int which, float
   if (e != cudaSuccess) return fail(std::string("debug_read: ") + cudaGetErrorString(e));
   return 0;
 }
+
+// ====================================================================================================================
+// Training-path entry point for the generator's largest layer: Concatenate([x, res_2]) -> UpSampling2D(2, bilinear) ->
+// Conv2DTranspose(16, 5x5, same) + bias -> LeakyReLU (models.py:60-64), fp32 tensors in, fp32 out, tf32 operands.
+// The training graph used to materialise the 96x96x160 upsampled tensor (1.1 GB at batch 8 x 24), run a 1x1 GEMM into
+// 25 tap columns (2.8 GB written and read back) and overlap-add them: 3.1 ms per forward, five forwards per WGAN step.
+// This runs the inference engine's kernels instead (fused bilinear + conv over 4x4 low-res windows with host... here
+// DEVICE-composed phase weights, exact border correction): ~0.5 ms.  The weights change with every optimizer step, so
+// the composition (generator finalize does it on the host in double) is a kernel here.
+namespace {
+
+__device__ __forceinline__ double up_w(int m, int d) {     // bilinear taps U[m][d] of wdg_generator_finalize
+  const double U[6][4] = {{.75, .25, 0, 0}, {.25, .75, 0, 0}, {0, .75, .25, 0}, {0, .25, .75, 0}, {0, 0, .75, .25}, {0, 0, .25, .75}};
+  return U[m][d];
+}
+// w: [5][5][16][160] (kh, kw, out, in).  B9h: [64][5 chunks * 16 taps][32] (K-block = chunk*16 + tap);
+// BE: [192][5 taps * 5 chunks][32] (K-block = t*5 + chunk).  tf32-rounded.
+__global__ void compose_upconv_kernel(const float* __restrict__ w, float* __restrict__ B9h, float* __restrict__ BE) {
+  const int O = 16, I = 160;
+  auto Wf = [&](int ty, int tx, int c, int o) { return (double)w[(((4 - ty) * 5 + (4 - tx)) * O + o) * I + c]; };
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 64 * 80 * 32) {
+    const int n = i / (80 * 32), kb = (i / 32) % 80, j = i % 32;
+    const int tap = kb % 16, chunk = kb / 16, c = chunk * 32 + j;
+    const int py = n / (2 * O), px = (n / O) % 2, o = n % O, dy = tap / 4, dx = tap % 4;
+    double acc = 0;
+    for (int ty = 0; ty < 5; ++ty) {
+      const double uy = up_w(py + ty, dy);
+      if (uy == 0) continue;
+      for (int tx = 0; tx < 5; ++tx) acc += uy * up_w(px + tx, dx) * Wf(ty, tx, c, o);
+    }
+    B9h[i] = __uint_as_float(to_tf32((float)acc));
+  }
+  if (i < 192 * 25 * 32) {
+    const int n = i / (25 * 32), kb = (i / 32) % 25, j = i % 32;
+    const int edge = n / 48, e = (n % 48) / 16, o = n % 16, t = kb / 5, chunk = kb % 5, c = chunk * 32 + j;
+    double v;
+    switch (edge) {
+      case 0: v = Wf(2 - e, t, c, o) - (e <= 1 ? Wf(1 - e, t, c, o) : 0.0); break;
+      case 1: v = Wf(2 + e, t, c, o) - (e <= 1 ? Wf(3 + e, t, c, o) : 0.0); break;
+      case 2: v = Wf(t, 2 - e, c, o) - (e <= 1 ? Wf(t, 1 - e, c, o) : 0.0); break;
+      default: v = Wf(t, 2 + e, c, o) - (e <= 1 ? Wf(t, 3 + e, c, o) : 0.0); break;
+    }
+    BE[i] = __uint_as_float(to_tf32((float)(0.25 * v)));
+  }
+}
+
+// Concatenate([a (Ca channels), b (Cb channels)]) of dense [N][h][w][*] fp32 tensors into the zero-ring-2 padded image
+// [N][h+4][w+4][Ca+Cb], values rounded to tf32 (GEMM operand).  One thread per (padded pixel, 4 channels).
+__global__ void pad_concat_tf32_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ b, int Cb,
+                                       float* __restrict__ out, long long total, int h, int w) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int C = Ca + Cb, g4 = C / 4;
+  const int c = (int)(i % g4) * 4;
+  const long long pp = i / g4;
+  const int px = (int)(pp % (w + 4)), py = (int)((pp / (w + 4)) % (h + 4));
+  const long long n = pp / ((long long)(w + 4) * (h + 4));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int y = py - 2, x = px - 2;
+  if (y >= 0 && y < h && x >= 0 && x < w) {
+    const long long pix = (n * h + y) * w + x;
+    v = c < Ca ? *reinterpret_cast<const float4*>(a + pix * Ca + c) : *reinterpret_cast<const float4*>(b + pix * Cb + (c - Ca));
+    v.x = __uint_as_float(to_tf32(v.x)); v.y = __uint_as_float(to_tf32(v.y));
+    v.z = __uint_as_float(to_tf32(v.z)); v.w = __uint_as_float(to_tf32(v.w));
+  }
+  *reinterpret_cast<float4*>(out + pp * C + c) = v;
+}
+
+__global__ void fill_vec_kernel(float* p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+struct UpconvWs {
+  size_t catp, edgeE, deltaD, B9h, BE, vecs, total;
+};
+UpconvWs upconv_ws(long long N, int h) {
+  const size_t S = 2 * (size_t)h, PW = h + 4;
+  UpconvWs L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return r; };
+  L.catp = take((size_t)N * PW * PW * 160 * 4 + 8192);
+  L.edgeE = take((size_t)N * 4 * (S + 8) * 160 * 4);
+  L.deltaD = take((size_t)N * S * 192 * 4);
+  L.B9h = take((size_t)64 * 80 * 32 * 4);
+  L.BE = take((size_t)192 * 25 * 32 * 4);
+  L.vecs = take(3 * 192 * 4);      // zeros[192] | ones[192] | (unused)
+  L.total = o;
+  return L;
+}
+
+}  // namespace
+
+extern "C" int wdg_upconv5x5_workspace_bytes(long long N, int h, size_t* bytes) {
+  if (!bytes || N <= 0 || h <= 0) return fail("bad argument");
+  *bytes = upconv_ws(N, h).total;
+  return 0;
+}
+
+extern "C" int wdg_upconv5x5_fwd(const float* a, const float* b, const float* w, const float* bias, float* out, long long N,
+                                 int h, void* workspace, size_t ws_bytes, void* stream_) {
+  if (!a || !b || !w || !bias || !out || !workspace || N <= 0 || h <= 0) return fail("bad argument");
+  const int S = 2 * h, PW = h + 4, sms_cap = 148;
+  if ((3 * PW + 3 + H_TILES * TILE_M) > H_ROWS) return fail("wdg_upconv5x5_fwd: low-res size too large for the halo kernel (<= 48)");
+  if ((uintptr_t)workspace % 1024) return fail("workspace must be 1024-byte aligned");
+  const UpconvWs L = upconv_ws(N, h);
+  if (ws_bytes < L.total) return fail("workspace too small");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  uint8_t* ws = (uint8_t*)workspace;
+  float* catp = (float*)(ws + L.catp);
+  float* edgeE = (float*)(ws + L.edgeE);
+  float* deltaD = (float*)(ws + L.deltaD);
+  float* B9h = (float*)(ws + L.B9h);
+  float* BE = (float*)(ws + L.BE);
+  float* zeros = (float*)(ws + L.vecs);
+  float* ones = zeros + 192;
+  int dev = 0, sms = sms_cap;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // 1. operands: composed weights, constant vectors, padded concat
+  compose_upconv_kernel<<<(64 * 80 * 32 + 255) / 256, 256, 0, stream>>>(w, B9h, BE);
+  CK(cudaGetLastError());
+  fill_vec_kernel<<<1, 192, 0, stream>>>(zeros, 192, 0.f);
+  fill_vec_kernel<<<1, 192, 0, stream>>>(ones, 192, 1.f);
+  {
+    const long long total = N * PW * PW * 40;
+    pad_concat_tf32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a, 32, b, 128, catp, total, h, h);
+    CK(cudaGetLastError());
+  }
+  // 2. border corrections: upsampled edge lines -> 5-tap GEMM -> deltaD [N][S][192]
+  {
+    const long long total = N * 4 * (S + 8) * 20;
+    edge_lines_kernel<PREC_TF32><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(catp, edgeE, total, h, 160, 160);
+    CK(cudaGetLastError());
+    ConvLaunch c;
+    std::memset(&c.p, 0, sizeof c.p);
+    const uint64_t I = 160, P = S + 8;
+    uint64_t dims[5] = {I, P, 4, (uint64_t)N, 1};
+    uint64_t str[4] = {I, P * I, 4 * P * I, (uint64_t)N * 4 * P * I};
+    uint32_t box[5] = {32, 16, 1, 8, 1};
+    if (wdg_make_tmap(&c.tmA[0], edgeE, 5, dims, str, box, 128, 4)) return 1;
+    c.tmA[1] = c.tmA[0]; c.tmA[2] = c.tmA[0];
+    uint64_t bd[2] = {25 * 32, 192}, bs[1] = {25 * 32};
+    uint32_t bb[2] = {32, 48};
+    if (wdg_make_tmap(&c.tmB, BE, 2, bd, bs, bb, 128, 4)) return 1;
+    set_tiles(c.p, 1, S, (int)N, 16, 1, 8, 4, 3);
+    c.p.ntile_coord = 2;
+    c.p.num_kb = 25;
+    for (int t = 0; t < 5; ++t)
+      for (int ch = 0; ch < 5; ++ch) {
+        KBlock& k = c.p.kb[t * 5 + ch];
+        k.src = 0; k.half = 0; k.o0 = (int16_t)(ch * 32); k.o1 = (int16_t)(t + 2); k.o2 = 0; k.o3 = 0;
+      }
+    affine_epi(c.p.ep, zeros, ones, zeros, deltaD, (long long)S * 192, 0, 192, 0, 0);
+    c.p.ep.out_f32 = 1;
+    c.bn = 48; c.epi = EPI_AFFINE; c.shallow = 1;
+    const int total_tiles = c.p.tiles_x * c.p.tiles_y * c.p.tiles_n * c.p.n_tiles_N;
+    c.grid = total_tiles < 2 * sms ? total_tiles : 2 * sms;
+    if (launch_conv<PREC_TF32>(c, dev, stream)) return 1;
+  }
+  // 3. fused bilinear x2 + 5x5 transposed conv + bias + LeakyReLU, dense fp32 output (BatchNorm follows in training mode)
+  {
+    const uint64_t flat = (uint64_t)N * PW * PW;
+    CUtensorMap hA, hB;
+    uint64_t hd[2] = {160, flat}, hs[1] = {160};
+    uint32_t hb[2] = {32, H_BOX_ROWS};
+    if (wdg_make_tmap(&hA, catp, 2, hd, hs, hb, 128, 4)) return 1;
+    uint64_t bd[2] = {80 * 32, 64}, bs[1] = {80 * 32};
+    uint32_t bb[2] = {32, 64};
+    if (wdg_make_tmap(&hB, B9h, 2, bd, bs, bb, 128, 4)) return 1;
+    HaloParams hp;
+    std::memset(&hp, 0, sizeof hp);
+    hp.num_passes = (int)((flat + H_TILES * TILE_M - 1) / (H_TILES * TILE_M));
+    hp.n_img = (int)N; hp.pw = PW; hp.ph = PW; hp.S = S; hp.delta = deltaD; hp.box_rows = H_BOX_ROWS;
+    for (int tap = 0; tap < 16; ++tap) { hp.tap_shift[tap] = (tap / 4) * PW + tap % 4; hp.kmask[tap] = 0xF; }
+    hp.bias = bias; hp.scale = ones; hp.shift = zeros; hp.out = out;
+    hp.up_sn = (long long)S * S * 16; hp.up_sy = (long long)S * 16;
+    const int grid = hp.num_passes < sms ? hp.num_passes : sms;
+    if (launch_halo<64, 5, 16, 4, HEPI_UPCONV, PREC_TF32>(hA, hB, hp, grid, dev, stream)) return 1;
+  }
+  return 0;
+}

@@ -21,6 +21,8 @@ class GAN:
         self._train = None   # lazily built device-side training state
         self._graphed = None
         self.use_cuda_graph = os.environ.get("WDG_TRAIN_GRAPH", "1") != "0"
+        # extension, off by default: skip the gradient-penalty passes whose result nothing uses (train/step.py)
+        self.skip_dead_gradient_penalty = bool(kwargs.get("skip_dead_gradient_penalty", False))
         # One set of variables, as in Keras: the trained weights live in the device-side TrainState; the model handles
         # pull them in lazily before anything reads them, and writing weights into a handle drops the TrainState.
         for m in (generator, discriminator):
@@ -78,12 +80,13 @@ class GAN:
             # steady state: the whole step is ONE captured CUDA graph (train/step.py: GraphedStep); the first calls run
             # eagerly and size every buffer
             if self._graphed is None or self._graphed.comm is not comm:
-                self._graphed = GraphedStep(st, self.noise_generator, self._n_critic, comm)
+                self._graphed = GraphedStep(st, self.noise_generator, self._n_critic, comm, self.skip_dead_gradient_penalty)
             out = self._graphed(data[0], data[1])
             if self._graphed.graph is None or self._graphed.calls == GraphedStep.WARMUP + 1:
                 self._last_step_calls = _lib.calls - before      # launches of one step, counted while it ran eagerly / was captured
         else:
-            out = train_step(st, data[0], data[1], self.noise_generator, self._n_critic, draws, comm=comm)
+            out = train_step(st, data[0], data[1], self.noise_generator, self._n_critic, draws, comm=comm,
+                             skip_dead_gp=self.skip_dead_gradient_penalty)
             self._last_step_calls = _lib.calls - before
         return out
 

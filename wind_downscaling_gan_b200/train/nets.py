@@ -284,13 +284,21 @@ class GenNet:
         L["bn8"] = BatchNorm(w, 8, self.comm)
         r7 = L["bn8"].forward(a7.t, training)                                                  # :56
         C9 = F // 4 + r2.shape[-1]
-        cat9 = ops.empty(N, S2, S2, C9)                                                        # :60
-        ops.axpby(View(cat9, F // 4, C9, 0), full(r7))
-        ops.axpby(View(cat9, r2.shape[-1], C9, F // 4), full(r2))
-        up = ops.empty(N, S, S, C9)
-        ops.upsample2x_fwd(cat9, up)                                                           # :62
         L["c9"] = Conv(w[(LW % 9) + "layer/kernel"], w[(LW % 9) + "layer/bias"], 1, 2, transposed=True)     # :63-64
-        a9 = L["c9"].forward(full(up), N, S, S)
+        if ops.upconv_fused() and F // 4 == 32 and r2.shape[-1] == 128 and S2 <= 48:
+            # :60-64 in one fused tcgen05 pass: neither the concat, nor the 96x96x160 upsampled tensor, nor tap columns exist
+            a9 = full(ops.empty(N, S, S, F // 8))
+            ops.upconv5x5_fwd(r7, r2, L["c9"].w, L["c9"].b, a9.t)
+            L["c9"].ctx = None
+            self._up_inputs = (r7, r2, a9) if keep_context else None       # backward rebuilds the upsampled tensor from these
+        else:
+            cat9 = ops.empty(N, S2, S2, C9)                                                    # :60
+            ops.axpby(View(cat9, F // 4, C9, 0), full(r7))
+            ops.axpby(View(cat9, r2.shape[-1], C9, F // 4), full(r2))
+            up = ops.empty(N, S, S, C9)
+            ops.upsample2x_fwd(cat9, up)                                                       # :62
+            a9 = L["c9"].forward(full(up), N, S, S)
+            self._up_inputs = None
         L["bn10"] = BatchNorm(w, 10, self.comm)
         r9 = L["bn10"].forward(a9.t, training)                                                 # :69
         L["c11"] = Conv(w[(LW % 11) + "layer/kernel"], w[(LW % 11) + "layer/bias"], 1, 1, leaky=False)      # :70
@@ -313,6 +321,16 @@ class GenNet:
         put(11, "layer/kernel", "layer/bias", dw, db)
         da9, gb = L["bn10"].backward(dr9.t, ALPHA)
         g.update(gb)
+        if getattr(self, "_up_inputs", None) is not None:      # fused forward: materialise the upsampled tensor now, once
+            r7, r2, a9 = self._up_inputs
+            C9 = F // 4 + C2
+            cat9 = ops.empty(N, S2, S2, C9)
+            ops.axpby(View(cat9, F // 4, C9, 0), full(r7))
+            ops.axpby(View(cat9, C2, C9, F // 4), full(r2))
+            up = ops.empty(N, S, S, C9)
+            ops.upsample2x_fwd(cat9, up)
+            L["c9"].ctx = (full(up), N, S, S, S, S, a9)
+            del cat9
         dup, dw, db = L["c9"].backward(da9, act_done=True)
         put(9, "layer/kernel", "layer/bias", dw, db)
         dcat9 = ops.empty(N, S2, S2, F // 4 + C2)
@@ -379,6 +397,12 @@ class CriticNet:
         self.F = weights[(LW % 2) + "layer/w"].shape[-1]
         self.convs, self.dense_idx, self.flat = critic_plan(size, self.F)
         self.sn_layers = [2, 3] + [e["idx"] for e in self.convs]
+
+    def spectral_norm_step(self):
+        """What a training-mode call does to the critic's VARIABLES (one power iteration per wrapped layer), without the
+        forward pass."""
+        for i in self.sn_layers:
+            sn_step(self.w, i)
 
     def forward(self, low_res, high_res, training):
         """[B,T,S,S,3], [B,T,S,S,2] -> score [B,1]."""

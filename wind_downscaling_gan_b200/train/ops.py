@@ -220,6 +220,23 @@ def lstm16_bwd_step(dz_next, packed, gates_s, c_prev, c_cur, dh, dc):
     _lib.check(_lib.lib().wdg_lstm16_bwd_step(_p(dz_next), _p(packed), _p(gates_s), _p(c_prev), _p(c_cur), _p(dh), _p(dc), N, H, W, _s()))
 
 
+def upconv_fused():
+    """The generator's concat -> bilinear x2 -> 5x5 transposed conv block runs as the fused tcgen05 kernel in the tensor-core
+    training modes."""
+    import os
+    return get_precision() != "fp32" and not os.environ.get("WDG_NO_FUSED_UPCONV")
+
+
+def upconv5x5_fwd(a, b, w, bias, out):
+    """a [N,h,h,32], b [N,h,h,128] -> out [N,2h,2h,16] = leaky(convT5x5(upsample2x(concat(a, b))) + bias)."""
+    N, h = a.shape[0], a.shape[1]
+    nb = C.c_size_t()
+    _lib.check(_lib.lib().wdg_upconv5x5_workspace_bytes(N, h, C.byref(nb)))
+    ws = scratch(nb.value + 1024, "upconv")
+    base = (ws.data_ptr() + 1023) // 1024 * 1024
+    _lib.check(_lib.lib().wdg_upconv5x5_fwd(_p(a), _p(b), _p(w), _p(bias), _p(out), N, h, C.c_void_p(base), nb.value, _s()))
+
+
 def upsample2x_fwd(x, y):
     n, h, w, Cc = x.shape
     _lib.check(_lib.lib().wdg_upsample2x_fwd(_p(x), _p(y), n, h, w, Cc, _s()))

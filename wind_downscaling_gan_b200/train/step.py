@@ -60,11 +60,18 @@ def _mean_sq_into(grads, out):
     ops.reduce_into(out, per, 0, scale=1.0 / len(grads))
 
 
-def train_step_device(st, low_res, high_res, noise_generator, n_critic=3, draws=None, gamma=100.0, comm=None):
+def train_step_device(st, low_res, high_res, noise_generator, n_critic=3, draws=None, gamma=100.0, comm=None,
+                      skip_dead_gp=False):
     """One WGAN step on this rank's share of the batch; returns the metrics as a device tensor (order METRIC_KEYS).
     With a communicator (train/dist.py) the gradients are all-reduced after every backward pass and BatchNorm
     statistics are synchronised, so `world` ranks x local batch reproduce the reference's single process at the global
-    batch."""
+    batch.
+
+    skip_dead_gp (extension, OFF by default): the gradient penalty never reaches the weights (ganbase.py:32-37 computes it
+    outside `disc_tape`) and only the LAST critic iteration's norms are logged (:85-88), so the interpolate ->
+    critic forward -> backward-to-input passes of the earlier iterations influence nothing but the critic's spectral-norm
+    state.  With the flag those iterations run just that power iteration (and still draw eps, so the random stream is
+    unchanged): weights and metrics come out bit-identical, two critic forward + input-backward passes cheaper."""
     ops.use_current_stream()
     B = low_res.shape[0]
     world = comm.world if comm is not None else 1
@@ -93,16 +100,20 @@ def train_step_device(st, low_res, high_res, noise_generator, n_critic=3, draws=
 
     ones = const(1.0)
     norms = None
-    for _ in range(n_critic):                                                        # ganbase.py:26
+    for ci in range(n_critic):                                                       # ganbase.py:26
         fake = gen.forward(low_res, noise(), training=True, keep_context=False)       # :28-29 (no backward through it)
         eps = uniform()                                                               # :30
-        combined = torch.empty_like(high_res)
-        ops.lerp_batch(combined, high_res, fake, eps)                                 # :31
-        d_gp = CriticNet(st.d, st.size)
-        d_gp.forward(low_res, combined, training=True)                                # :32-34
-        _, g_img = d_gp.backward(ones, need_weight_grads=False, need_input_grad=True) # :35
-        norms = ops.empty(B, out_ch)
-        ops.gp_norm(g_img, norms)                                                     # :36 (reduced over T, H, W only)
+        if skip_dead_gp and ci < n_critic - 1:
+            CriticNet(st.d, st.size).spectral_norm_step()                             # the only live effect of :32-35 here
+        else:
+            combined = torch.empty_like(high_res)
+            ops.lerp_batch(combined, high_res, fake, eps)                             # :31
+            d_gp = CriticNet(st.d, st.size)
+            d_gp.forward(low_res, combined, training=True)                            # :32-34
+            _, g_img = d_gp.backward(ones, need_weight_grads=False, need_input_grad=True)   # :35
+            norms = ops.empty(B, out_ch)
+            ops.gp_norm(g_img, norms)                                                 # :36 (reduced over T, H, W only)
+            del d_gp, g_img, combined
         hr_n = torch.empty_like(high_res)
         ops.axpby(ops.full(hr_n), ops.full(high_res), 1.0, ops.full(noise(out_ch)), 1.0)   # :40
         d_real = CriticNet(st.d, st.size)
@@ -160,9 +171,9 @@ def metrics_dict(M):
     return out
 
 
-def train_step(st, low_res, high_res, noise_generator, n_critic=3, draws=None, gamma=100.0, comm=None):
+def train_step(st, low_res, high_res, noise_generator, n_critic=3, draws=None, gamma=100.0, comm=None, skip_dead_gp=False):
     """Eager form: runs the step and reads the metrics back (one device -> host copy)."""
-    M, _ = train_step_device(st, _dev(low_res), _dev(high_res), noise_generator, n_critic, draws, gamma, comm)
+    M, _ = train_step_device(st, _dev(low_res), _dev(high_res), noise_generator, n_critic, draws, gamma, comm, skip_dead_gp)
     return metrics_dict(M)
 
 
@@ -173,8 +184,8 @@ class GraphedStep:
     while capturing)."""
     WARMUP = 2
 
-    def __init__(self, st, noise_generator, n_critic, comm=None):
-        self.st, self.ng, self.n_critic, self.comm = st, noise_generator, n_critic, comm
+    def __init__(self, st, noise_generator, n_critic, comm=None, skip_dead_gp=False):
+        self.st, self.ng, self.n_critic, self.comm, self.skip_dead_gp = st, noise_generator, n_critic, comm, skip_dead_gp
         self.calls = 0
         self.graph = None
         self.shape = None
@@ -187,7 +198,7 @@ class GraphedStep:
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
         with torch.cuda.graph(g):
-            self.M, _ = train_step_device(self.st, self.lr_buf, self.hr_buf, self.ng, self.n_critic, None, comm=self.comm)
+            self.M, _ = train_step_device(self.st, self.lr_buf, self.hr_buf, self.ng, self.n_critic, None, comm=self.comm, skip_dead_gp=self.skip_dead_gp)
         ops.use_current_stream()
         # capturing does not execute: undo the host mirrors it advanced, replays re-apply them
         self.blocks_per_step = self.ng._offset - off0
@@ -202,7 +213,7 @@ class GraphedStep:
         self.calls += 1
         shape = (tuple(low_res.shape), tuple(high_res.shape))
         if self.failed or self.calls <= self.WARMUP or (self.graph is not None and shape != self.shape):
-            M, _ = train_step_device(self.st, low_res, high_res, self.ng, self.n_critic, None, comm=self.comm)
+            M, _ = train_step_device(self.st, low_res, high_res, self.ng, self.n_critic, None, comm=self.comm, skip_dead_gp=self.skip_dead_gp)
             return metrics_dict(M)
         if self.graph is None:
             try:
@@ -213,7 +224,7 @@ class GraphedStep:
                 self.failed = True
                 torch.cuda.synchronize()
                 ops.use_current_stream()
-                M, _ = train_step_device(self.st, low_res, high_res, self.ng, self.n_critic, None, comm=self.comm)
+                M, _ = train_step_device(self.st, low_res, high_res, self.ng, self.n_critic, None, comm=self.comm, skip_dead_gp=self.skip_dead_gp)
                 return metrics_dict(M)
         self.lr_buf.copy_(low_res, non_blocking=True)
         self.hr_buf.copy_(high_res, non_blocking=True)
