@@ -120,7 +120,8 @@ int wdg_generator_debug_read(const wdg_generator* g, int which, float* host_out,
  * Patch order is the reference's: index = (ix * ny + iy) * ntimeseq + k (api.py:117-124); patch row p maps to
  * domain row sy+img-1-p, or img-p when sy == 0 (api.py:119). */
 
-/* Scratch needed by wdg_gather_normalise. */
+/* Scratch needed by wdg_gather_normalise (sequences of up to WDG_MAX_SEQ timesteps; api.py:22 uses 24). */
+#define WDG_MAX_SEQ 32
 int wdg_patch_scratch_bytes(int nx, int ny, int ntimeseq, int img, size_t* bytes);
 
 /* Replaces api.py:117-129: slices u10/v10 (T_total,H,W) and elevation_km (H,W) into patches, computes

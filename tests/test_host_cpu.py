@@ -102,3 +102,14 @@ def test_gan_compile_selects_training_precision():
     finally:
         ops.set_precision("fp32")
     assert ops.get_precision() == "fp32"
+
+
+def test_shard_units_covers_everything_once():
+    from wind_downscaling_gan_b200.engine import shard_units
+    for n in (0, 1, 5, 8, 100, 365):
+        for world in (1, 2, 3, 8):
+            spans = [shard_units(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1

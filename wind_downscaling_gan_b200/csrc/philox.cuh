@@ -27,17 +27,17 @@ __device__ inline float u32_to_unit(uint32_t x) {   // 23 mantissa bits -> [0, 1
   return __uint_as_float((x & 0x7fffffu) | 0x3f800000u) - 1.0f;
 }
 
-// Four standard normals of counter block `ctr`.
+// Four standard normals of counter block `ctr` (Box-Muller on the SFU: __logf / __sincosf with the angle kept in
+// [-pi, pi), where their absolute error is 2^-21.4; the radicand is clamped at 0 because __logf can come out a hair
+// positive next to u = 1).  The accurate libm forms made the input-packing kernel of the generator compute-bound.
 __device__ inline void philox_normal4(unsigned long long ctr, uint32_t k0, uint32_t k1, float (&v)[4]) {
   const U4 r = philox4x32_10(U4{(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u}, k0, k1);
-  float u1 = fmaxf(u32_to_unit(r.x), 1.0e-7f);
-  const float rad = sqrtf(-2.0f * logf(u1));
+  const float rad = sqrtf(fmaxf(-2.0f * __logf(fmaxf(u32_to_unit(r.x), 1.0e-7f)), 0.f));
   float s, c;
-  sincosf(6.283185307179586f * u32_to_unit(r.y), &s, &c);
+  __sincosf(6.283185307179586f * u32_to_unit(r.y) - 3.141592653589793f, &s, &c);
   v[0] = s * rad; v[1] = c * rad;
-  u1 = fmaxf(u32_to_unit(r.z), 1.0e-7f);
-  const float rad2 = sqrtf(-2.0f * logf(u1));
-  sincosf(6.283185307179586f * u32_to_unit(r.w), &s, &c);
+  const float rad2 = sqrtf(fmaxf(-2.0f * __logf(fmaxf(u32_to_unit(r.z), 1.0e-7f)), 0.f));
+  __sincosf(6.283185307179586f * u32_to_unit(r.w) - 3.141592653589793f, &s, &c);
   v[2] = s * rad2; v[3] = c * rad2;
 }
 

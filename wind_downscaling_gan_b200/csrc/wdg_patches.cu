@@ -44,12 +44,14 @@ __device__ __forceinline__ float load_var(const Geo& g, int var, int t, int row,
   return src[((long long)t * g.uh + r) * g.uw + c];
 }
 
-// One block per (var, ix, iy, k); thread j owns patch column j (coalesced along the domain's lon axis).
-// pass 0: partial[blk][j] = (sum x, count of non-NaN); pass 1: sum (x - mean)^2.
+// One block per (var, ix, iy, k) x timestep (blockIdx.y: a block per whole sequence left 60 blocks walking 2304 dependent
+// map -> field loads each); thread j owns patch column j (coalesced along the domain's lon axis).
+// pass 0: partial[blk][t][j] = (sum x, count of non-NaN); pass 1: sum (x - mean)^2.
 __global__ void stats_partial_kernel(Geo g, int pass, const double* __restrict__ mean, double* __restrict__ psum,
                                      double* __restrict__ pcnt) {
   const int j = threadIdx.x;
   int b = blockIdx.x;
+  const int t = blockIdx.y;
   const int k = b % g.ntimeseq; b /= g.ntimeseq;
   const int iy = b % g.ny; b /= g.ny;
   const int ix = b % g.nx; b /= g.nx;
@@ -58,17 +60,16 @@ __global__ void stats_partial_kernel(Geo g, int pass, const double* __restrict__
   const int col = g.sx[ix] + j, sy = g.sy[iy];
   const double mu = pass ? mean[j * 3 + var] : 0.0;
   double s = 0.0, c = 0.0;
-  for (int t = 0; t < g.seq; ++t)
-    for (int p = 0; p < g.img; ++p) {
-      const float x = load_var(g, var, k * g.seq + t, domain_row(sy, p, g.img), col);
-      if (x == x) {
-        const double d = (double)x - mu;
-        s += pass ? d * d : d;
-        c += 1.0;
-      }
+  for (int p = 0; p < g.img; ++p) {
+    const float x = load_var(g, var, k * g.seq + t, domain_row(sy, p, g.img), col);
+    if (x == x) {
+      const double d = (double)x - mu;
+      s += pass ? d * d : d;
+      c += 1.0;
     }
-  psum[(long long)blockIdx.x * g.img + j] = s;
-  pcnt[(long long)blockIdx.x * g.img + j] = c;
+  }
+  psum[((long long)blockIdx.x * g.seq + t) * g.img + j] = s;
+  pcnt[((long long)blockIdx.x * g.seq + t) * g.img + j] = c;
 }
 
 // Fixed-order final reduction: thread (j, var) sums its partials -> mean (pass 0) or std (pass 1).
@@ -150,7 +151,7 @@ __global__ void stitch_kernel(const float* __restrict__ pred, const int* __restr
 
 extern "C" int wdg_patch_scratch_bytes(int nx, int ny, int ntimeseq, int img, size_t* bytes) {
   if (!bytes || nx <= 0 || ny <= 0 || ntimeseq <= 0 || img <= 0) return wdg_set_error("bad argument");
-  *bytes = (size_t)2 * 3 * nx * ny * ntimeseq * img * sizeof(double);
+  *bytes = (size_t)2 * 3 * nx * ny * ntimeseq * WDG_MAX_SEQ * img * sizeof(double);   // one partial per (var, patch, timestep)
   return 0;
 }
 
@@ -187,14 +188,15 @@ static int gather_normalise_impl(Geo g, double* mean_dev, double* std_dev, float
   if (img > 1024) return wdg_set_error("img too large");
   cudaStream_t stream = (cudaStream_t)stream_;
   if (g.ntimeseq <= 0) return wdg_set_error("time window shorter than one sequence");
+  if (seq > WDG_MAX_SEQ) return wdg_set_error("sequence length above WDG_MAX_SEQ");
   const int bpv = nx * ny * g.ntimeseq;
   double* psum = (double*)scratch_dev;
-  double* pcnt = psum + (size_t)3 * bpv * img;
+  double* pcnt = psum + (size_t)3 * bpv * seq * img;
   const int threads = (img + 31) / 32 * 32;
   for (int pass = 0; pass < 2; ++pass) {
-    stats_partial_kernel<<<3 * bpv, threads, 0, stream>>>(g, pass, mean_dev, psum, pcnt);
+    stats_partial_kernel<<<dim3(3 * bpv, seq), threads, 0, stream>>>(g, pass, mean_dev, psum, pcnt);
     CKP(cudaGetLastError());
-    stats_final_kernel<<<(img * 3 + 127) / 128, 128, 0, stream>>>(img, bpv, pass, psum, pcnt, pass ? std_dev : mean_dev);
+    stats_final_kernel<<<(img * 3 + 127) / 128, 128, 0, stream>>>(img, bpv * seq, pass, psum, pcnt, pass ? std_dev : mean_dev);
     CKP(cudaGetLastError());
   }
   const long long total = (long long)bpv * seq * img * img;
