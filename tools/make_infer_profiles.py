@@ -1,8 +1,8 @@
 """Regenerates the inference-path files under profiles/ from raw captures in gpurun_out/:
-  launches_r1.csv   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv  python bench.py --steps 2 --warmup 3 --no-cpu-baseline
-  prof_r1.ncu-rep   ncu --set full --clock-control none --import-source on -c 17            python bench.py --steps 1 --warmup 1 --no-cpu-baseline
-  bench_r1.json / bench_ref_r1.json   python bench.py [--impl reference]
-Usage: python tools/make_infer_profiles.py"""
+  launches_<tag>.csv   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv  python bench.py --steps 2 --warmup 3 --no-cpu-baseline
+  prof_<tag>.ncu-rep  ncu --set full --clock-control none --import-source on -c 17            python bench.py --steps 1 --warmup 1 --no-cpu-baseline
+  bench_<tag>.json / bench_ref_<tag>.json   python bench.py [--impl reference]
+Usage: python tools/make_infer_profiles.py [tag]   (tag = r1, r2, ...: the round the captures belong to; default r2)"""
 import collections
 import csv
 import io
@@ -13,6 +13,7 @@ import shutil
 import subprocess
 import sys
 
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r2"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 STAGES = ["pack_input", "conv8x8s2", "conv4x4s2"] + ["convlstm"] * 8 + ["conv3x3", "convT2x2s2", "border_fix", "border_fix",
@@ -25,7 +26,7 @@ def clean(n):
 
 
 def launch_list():
-    rows = list(csv.reader(open(os.path.join(G, "launches_r1.csv"), errors="replace")))
+    rows = list(csv.reader(open(os.path.join(G, f"launches_{TAG}.csv"), errors="replace")))
     hdr, agg = None, collections.OrderedDict()
     for r in rows:
         if "Kernel Name" in r:
@@ -43,24 +44,24 @@ def launch_list():
             a[0] += 1
             a[1] += v
     tot = sum(v[1] for v in agg.values())
-    out = ["# r1 launch list (ncu --metrics gpu__time_duration.sum --clock-control none -c 400, `bench.py --steps 2 --warmup 3 --no-cpu-baseline`)\n",
-           "Per-launch times are cold-cache and serialised: compare SHARES with the CUDA-event stage shares of profiles/r1_bench_n1.json, not absolutes.",
+    out = [f"# {TAG} launch list (ncu --metrics gpu__time_duration.sum --clock-control none -c 400, `bench.py --steps 2 --warmup 3 --no-cpu-baseline`)\n",
+           "Per-launch times are cold-cache and serialised: compare SHARES with the CUDA-event stage shares of profiles/" + TAG + "_bench_n1.json, not absolutes.",
            "conv_umma_kernel<BN,EPI>: EPI 0 = bias/LeakyReLU/BN affine, 1 = ConvLSTM gates. halo_conv_kernel<BN,NCHUNK,NTAP,TPS,EPI>: <128,3,8,2,1> = 8x8 s2 conv,",
            "<64,3,16,4,0> = fused upsample + 5x5 transposed conv, <16,1,9,3,2> = final 3x3 conv in super-pixel form.\n",
            "| kernel | launches | total us | share |", "|---|---|---|---|"]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f"| {k} | {v[0]} | {v[1]:.1f} | {v[1] / tot:.3f} |")
-    open(os.path.join(P, "r1_launch_list.md"), "w").write("\n".join(out) + "\n")
-    shutil.copy(os.path.join(G, "launches_r1.csv"), os.path.join(P, "r1_launches.csv"))
+    open(os.path.join(P, f"{TAG}_launch_list.md"), "w").write("\n".join(out) + "\n")
+    shutil.copy(os.path.join(G, f"launches_{TAG}.csv"), os.path.join(P, f"{TAG}_launches.csv"))
 
 
 def ncu_tables():
-    rep = os.path.join(G, "prof_r1.ncu-rep")
+    rep = os.path.join(G, f"prof_{TAG}.ncu-rep")
     md = subprocess.run([sys.executable, os.path.join(P, "summarize_ncu.py"), rep], capture_output=True, text=True).stdout
-    head = ("# r1 — ncu `--set full --clock-control none --import-source on -c 17` of one generator forward (bench.py workload: 64 sequences x 8\n"
+    head = (f"# {TAG} — ncu `--set full --clock-control none --import-source on -c 17` of one generator forward (bench.py workload: 64 sequences x 8\n"
             "timesteps = 512 fields), B200.  Kernel order = launch order of the forward (pack, 8x8 s2, 4x4 s2, 8 ConvLSTM steps, 3x3, convT 2x2,\n"
             "edge lines, border GEMM, fused upsample conv, final conv).  Cold first forward: use the ratios, not the absolute times.\n\n")
-    open(os.path.join(P, "r1_ncu_kernels.md"), "w").write(head + md.replace("(anonymous namespace)::", ""))
+    open(os.path.join(P, f"{TAG}_ncu_kernels.md"), "w").write(head + md.replace("(anonymous namespace)::", ""))
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -85,16 +86,16 @@ def ncu_tables():
             out[st] = {"dram_bytes_per_launch": sum(b for _, b in lst), "kernel": " + ".join(k for k, _ in lst)}
         else:
             out[st] = {"dram_bytes_per_launch": lst[0][1], "kernel": lst[0][0]}
-    out["_source"] = "ncu --set full --clock-control none (profiles/r1_ncu_kernels.md), bench.py workload, per launch"
-    json.dump(out, open(os.path.join(P, "r1_traffic.json"), "w"), indent=1)
+    out["_source"] = "ncu --set full --clock-control none (profiles/" + TAG + "_ncu_kernels.md), bench.py workload, per launch"
+    json.dump(out, open(os.path.join(P, f"{TAG}_traffic.json"), "w"), indent=1)
 
 
 def main():
     launch_list()
     ncu_tables()
-    shutil.copy(os.path.join(G, "bench_r1.json"), os.path.join(P, "r1_bench_n1.json"))
-    if os.path.exists(os.path.join(G, "bench_ref_r1.json")):
-        shutil.copy(os.path.join(G, "bench_ref_r1.json"), os.path.join(P, "r1_bench_reference_arm.json"))
+    shutil.copy(os.path.join(G, f"bench_{TAG}.json"), os.path.join(P, f"{TAG}_bench_n1.json"))
+    if os.path.exists(os.path.join(G, f"bench_ref_{TAG}.json")):
+        shutil.copy(os.path.join(G, f"bench_ref_{TAG}.json"), os.path.join(P, f"{TAG}_bench_reference_arm.json"))
     print("profiles/ (inference) refreshed")
 
 
