@@ -283,6 +283,63 @@ int wdg_adam_dev(float* w, float* m, float* v, const float* g, long long n, cons
                  void* stream);
 int wdg_sn_update(float* w, float* u, int R, int C, void* scratch, void* stream);
 
+/* ---- the WGAN critic as a handle (reference gan/models.py:76-142 `make_discriminator`, tf_utils.py:7-32; train step
+ * ganbase.py:21-94).  What a reference-side binding calls in place of `discriminator([low_res, high_res], training=...)`,
+ * `reg_tape.gradient(score, interpolated)` (ganbase.py:35: backward to the image only), `disc_tape.gradient(loss,
+ * trainable_weights)` (:46: backward to the weights) and `gen_tape.gradient` through the critic (:60).
+ *
+ * wdg_critic_create takes make_discriminator's hyper-parameters (models.py:76-84; batch_size is not needed).  It only builds
+ * the layer plan, so it works without a device; sizes differing -> the reference's NotImplementedError text (models.py:89-91).
+ * ckpt_topology = 0: the graph the current reference code builds (the `i > 1` shortcut of models.py:127 never triggers);
+ * ckpt_topology = 1: the graph the shipped weights-55.ckpt/discriminator.index was written from -- the same plus the shortcut
+ * convolution + LayerNorm + add of tf_utils.py:15-32 around the last 7x7 stage (at 96 px: 6x6, stride 11, pad 4).
+ *
+ * Variables: ONE caller-owned flat fp32 device buffer of wdg_critic_num_floats() floats; variable i lives at
+ * weight_info's `offset` (floats, 256-byte aligned, padding must stay zero).  Names/shapes/layouts are the checkpoint's
+ * (`layer_with_weights-N/...`, Conv2D HWIO).  The trainable variables come first (wdg_critic_num_trainable_floats());
+ * a gradient buffer has that size and the same offsets, so the optimiser step and the data-parallel all-reduce of a whole
+ * model are one launch / one collective over a flat range.
+ *
+ * forward: low_res (B,T,S,S,Cl), high_res (B,T,S,S,Ch) fp32 device -> score (B,1).  training != 0 reproduces what Keras does
+ * in a training-mode call: every SpectralNormalization wrapper runs one power iteration and rewrites its kernel and sn_u
+ * IN PLACE in vars_dev (TFA 0.14), then the call reads a snapshot of the variables kept in its context.  context_dev
+ * (wdg_critic_context_bytes) keeps what this call's backward needs; several contexts may be alive at once (ganbase.py:41-46
+ * differentiates two calls together).  scratch_dev (wdg_critic_scratch_bytes) is transient and may be shared by all calls
+ * on one stream.  Sizes depend on wdg_train_set_precision's mode at the time of the call; keep it unchanged between a
+ * forward and its backward.  backward: dscore (B,1) = dLoss/dscore; grads_dev (trainable floats, may be NULL) receives
+ * dLoss/dvariables, d_high_res_dev ((B,T,S,S,Ch), may be NULL) dLoss/dhigh_res.  A context can be differentiated once
+ * (the backward overwrites the saved gate activations). */
+typedef struct wdg_critic wdg_critic;
+int wdg_critic_create(wdg_critic** out, int low_res_size, int high_res_size, int low_res_channels, int high_res_channels,
+                      int n_timesteps, int feature_channels, int ckpt_topology);
+void wdg_critic_destroy(wdg_critic* c);
+int wdg_critic_num_weights(const wdg_critic* c);
+int wdg_critic_weight_info(const wdg_critic* c, int index, const char** name, int64_t* dims, int* ndim, int64_t* offset,
+                           int* trainable);
+int64_t wdg_critic_num_floats(const wdg_critic* c);
+int64_t wdg_critic_num_trainable_floats(const wdg_critic* c);
+int wdg_critic_context_bytes(const wdg_critic* c, int B, int T, int training, size_t* bytes);
+int wdg_critic_scratch_bytes(const wdg_critic* c, int B, int T, size_t* bytes);
+/* One training-mode call's effect on the variables without the forward pass (all SpectralNormalization wrappers). */
+int wdg_critic_sn_update(wdg_critic* c, float* vars_dev, void* scratch_dev, size_t scratch_bytes, void* stream);
+int wdg_critic_forward(wdg_critic* c, float* vars_dev, const float* low_res_dev, const float* high_res_dev, float* score_dev,
+                       int B, int T, int training, void* context_dev, size_t context_bytes, void* scratch_dev,
+                       size_t scratch_bytes, void* stream);
+int wdg_critic_backward(wdg_critic* c, const float* vars_dev, void* context_dev, int B, int T, int training,
+                        const float* dscore_dev, float* grads_dev, float* d_high_res_dev, void* scratch_dev,
+                        size_t scratch_bytes, void* stream);
+int wdg_critic_backward_input(wdg_critic* c, const float* vars_dev, void* context_dev, int B, int T, int training,
+                              const float* dscore_dev, float* d_high_res_dev, void* scratch_dev, size_t scratch_bytes,
+                              void* stream);
+int wdg_critic_backward_weights(wdg_critic* c, const float* vars_dev, void* context_dev, int B, int T, int training,
+                                const float* dscore_dev, float* grads_dev, void* scratch_dev, size_t scratch_bytes,
+                                void* stream);
+
+/* ---- host helper of the TensorFlow checkpoint-V2 reader / writer (tf_checkpoint.py; ganbase.py:132-140): CRC-32C
+ * (Castagnoli) of `n` bytes, continuing from `crc` (0 to start).  TensorFlow stores mask(crc) = rotr(crc, 15) + 0xa282ead8
+ * in SSTable block trailers and BundleEntryProto.crc32c. */
+uint32_t wdg_crc32c(uint32_t crc, const void* data, size_t n);
+
 /* ---- on-device evaluation metrics (reference gan/metrics.py).  real / fake: fp32 [B,T,H,W,C].
  * wdg_metrics_pointwise: out[5][B] = wind_speed_weighted_rmse (metrics.py:32-45), wind_speed_rmse (:81-91),
  * angular_cosine_distance (:97-105), opposite_cosine_similarity (:108-111), extreme_weighted_rmse (:66-73), all in

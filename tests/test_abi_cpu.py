@@ -71,6 +71,69 @@ def test_tf_checkpoint_bundle_roundtrip(tmp_path):
     assert idx["layer_with_weights-1/gamma/.ATTRIBUTES/VARIABLE_VALUE"]["shape"] == [5]
 
 
+def test_crc32c_reproduces_the_reference_checkpoint_trailers():
+    """CRC-32C + TensorFlow's mask against every block trailer of the reference's own weights-55.ckpt/*.index
+    (tests/golden/ckpt_crc.json, make_ckpt_crc.py) and the standard check value."""
+    import json
+    import os
+    from wind_downscaling_gan_b200.tf_checkpoint import crc32c, masked_crc32c
+    assert crc32c(b"123456789") == 0xE3069283
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ckpt_crc.json")))
+    n = 0
+    for model in ("generator", "discriminator"):
+        for blk in gold[model]["blocks"]:
+            assert masked_crc32c(bytes.fromhex(blk["bytes_and_type"])) == blk["stored_masked_crc32c"], (model, blk["kind"])
+            n += 1
+    assert n == 6
+
+
+def test_written_bundle_carries_tensorflow_header_and_checksums(tmp_path):
+    """What TensorFlow's BundleReader checks: header proto identical to the one in the reference's index files, a valid
+    masked crc32c behind every block and in every entry; a flipped data byte is detected on read."""
+    import json
+    import os
+    import struct
+    import numpy as np
+    from wind_downscaling_gan_b200.tf_checkpoint import _block, _varint, masked_crc32c, read_bundle, read_index, write_bundle
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ckpt_crc.json")))
+    rng = np.random.default_rng(0)
+    t = {"layer_with_weights-0/layer/w": rng.standard_normal((8, 8, 23, 128)).astype(np.float32),
+         "layer_with_weights-4/cell/bias": rng.standard_normal(512).astype(np.float32)}
+    prefix = str(tmp_path / "generator")
+    write_bundle(prefix, t)
+    b = open(prefix + ".index", "rb").read()
+    foot, q = b[-48:], 0
+    spans = []
+    for _ in range(2):
+        off, q = _varint(foot, q)
+        size, q = _varint(foot, q)
+        spans.append((off, size))
+    for _, h in _block(b, *spans[1]):
+        off, r = _varint(h, 0)
+        size, r = _varint(h, r)
+        spans.append((off, size))
+        header = [v for k, v in _block(b, off, size) if k == b""][0]
+        assert header.hex() == gold["generator"]["header_proto"] == gold["discriminator"]["header_proto"]
+    assert len(spans) == 3
+    for off, size in spans:
+        assert b[off + size] == 0 and struct.unpack("<I", b[off + size + 1:off + size + 5])[0] == masked_crc32c(b[off:off + size + 1])
+    raw = open(prefix + ".data-00000-of-00001", "rb").read()
+    for key, e in read_index(prefix + ".index").items():
+        assert e["crc32c"] == masked_crc32c(raw[e["offset"]:e["offset"] + e["size"]]), key
+    back = read_bundle(prefix)
+    assert all(np.array_equal(back[k], t[k]) for k in t)
+    bad = bytearray(raw)
+    bad[1000] ^= 0x10
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(bad))
+    with pytest.raises(ValueError, match="crc32c"):
+        read_bundle(prefix)
+    bad_index = bytearray(b)
+    bad_index[40] ^= 1
+    open(prefix + ".index", "wb").write(bytes(bad_index))
+    with pytest.raises(ValueError, match="crc32c"):
+        read_index(prefix + ".index")
+
+
 def test_philox_known_answers(lib):
     """Philox4x32-10 block function against the Random123 known-answer vectors (Salmon et al., SC'11)."""
     import ctypes as C

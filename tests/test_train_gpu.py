@@ -249,3 +249,45 @@ def test_skipping_the_dead_gradient_penalty_passes_changes_nothing():
     assert ma == mb
     assert all(np.array_equal(ga[k], gb[k]) for k in ga) and all(np.array_equal(da[k], db[k]) for k in da)
     assert lb < la
+
+
+def test_train_step_updates_the_compiled_metrics():
+    """ganbase.py:71-72, :82-93 with the metric set of api.py:76-84: every step updates the five generator metrics with
+    (high_res, recomputed fake) and the two score metrics with (D(real), D(fake)); the dict carries their running means as
+    g_<name> / <name>.  Checked against oracle/metrics.py on the recomputed tensors of each step."""
+    from oracle import metrics as om
+    from oracle.critic import synthetic_critic_weights
+    from oracle.generator import synthetic_generator_weights
+    from wind_downscaling_gan_b200.data.data_generator import FlexibleNoiseGenerator
+    from wind_downscaling_gan_b200.gan import metrics, train
+    from wind_downscaling_gan_b200.gan.ganbase import GAN
+    from wind_downscaling_gan_b200.gan.models import make_discriminator, make_generator
+    B, T, S = 2, 2, 32
+    gen, disc = make_generator(S, 3, 20, 2, T), make_discriminator(S, S, 3, 2, T)
+    gen.set_weights(synthetic_generator_weights(7))
+    disc.set_weights(synthetic_critic_weights(8, size=S))
+    gan = GAN(gen, disc, FlexibleNoiseGenerator((B, T, S, S, 20), std=0.1, random_seed=1))
+    gan.use_cuda_graph = False
+    gan.compile(generator_optimizer=train.generator_optimizer(),
+                generator_metrics=[metrics.AngularCosineDistance(), metrics.LogSpectralDistance(), metrics.WeightedRMSEForExtremes(),
+                                   metrics.WindSpeedWeightedRMSE(), metrics.SpatialKS()],
+                discriminator_optimizer=train.discriminator_optimizer(), discriminator_loss=train.discriminator_loss,
+                metrics=[metrics.discriminator_score_fake(), metrics.discriminator_score_real()])
+    fns = {"g_acd": om.angular_cosine_distance, "g_lsd": om.log_spectral_distance, "g_extreme_rmse": om.extreme_weighted_rmse,
+           "g_ws_weighted_rmse": om.wind_speed_weighted_rmse, "g_spatial_ks": om.spatially_convolved_ks_stat}
+    acc = {k: [] for k in list(fns) + ["d_real", "d_fake"]}
+    for step in range(2):
+        _, lr, hr = data(B, T, S, 20 + step)
+        m = gan.train_step((lr, hr))
+        fake, s_real, s_fake = (t.cpu().numpy() for t in gan._last_recompute)
+        for k, fn in fns.items():
+            acc[k] += list(np.asarray(fn(hr, fake), np.float64).ravel())
+        acc["d_real"] += list(s_real.ravel())
+        acc["d_fake"] += list(s_fake.ravel())
+        assert set(m) >= {"g_loss", "g_disc_loss", "g_reco_loss", "d_loss", "d_gradient_pen", "g_gradient_param", "d_gradient_param"} | set(acc)
+        for k, v in acc.items():
+            assert abs(m[k] - np.mean(v)) <= 1e-4 * max(1.0, abs(np.mean(v))), (step, k, m[k], np.mean(v))
+    t = gan.test_step((lr, hr))
+    assert {"loss", "d_real", "d_fake"} <= set(t)
+    with pytest.raises(NotImplementedError):
+        gan.train_step((lr, hr, np.ones(B, np.float32)))

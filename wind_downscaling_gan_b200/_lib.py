@@ -99,6 +99,16 @@ def _declare(lib):
         "wdg_rng_advance": [vp, C.c_uint64, vp],
         "wdg_uniform_state": [vp, ll, vp, vp],
         "wdg_noise_normal": [vp, ll, f, C.c_uint64, C.c_uint64, vp],
+        "wdg_critic_create": [C.POINTER(vp), i, i, i, i, i, i, i],
+        "wdg_critic_num_weights": [vp],
+        "wdg_critic_weight_info": [vp, i, C.POINTER(C.c_char_p), i64p, ip, i64p, ip],
+        "wdg_critic_context_bytes": [vp, i, i, i, C.POINTER(sz)],
+        "wdg_critic_scratch_bytes": [vp, i, i, C.POINTER(sz)],
+        "wdg_critic_sn_update": [vp, vp, vp, sz, vp],
+        "wdg_critic_forward": [vp, vp, vp, vp, vp, i, i, i, vp, sz, vp, sz, vp],
+        "wdg_critic_backward": [vp, vp, vp, i, i, i, vp, vp, vp, vp, sz, vp],
+        "wdg_critic_backward_input": [vp, vp, vp, i, i, i, vp, vp, vp, sz, vp],
+        "wdg_critic_backward_weights": [vp, vp, vp, i, i, i, vp, vp, vp, sz, vp],
         "wdg_metrics_pointwise_scratch": [i, C.POINTER(sz)],
         "wdg_metrics_pointwise": [vp, vp, i, ll, i, vp, vp, vp],
         "wdg_metric_lsd": [vp, vp, i, i, i, i, i, vp, vp, vp],
@@ -114,6 +124,13 @@ def _declare(lib):
     lib.wdg_philox4x32_10.restype = None
     lib.wdg_generator_destroy.argtypes = [vp]
     lib.wdg_generator_destroy.restype = None
+    lib.wdg_crc32c.argtypes = [C.c_uint32, vp, sz]
+    lib.wdg_crc32c.restype = C.c_uint32
+    lib.wdg_critic_destroy.argtypes = [vp]
+    lib.wdg_critic_destroy.restype = None
+    for name in ("wdg_critic_num_floats", "wdg_critic_num_trainable_floats"):
+        getattr(lib, name).argtypes = [vp]
+        getattr(lib, name).restype = C.c_int64
     del fp
 
 

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _lib, tiling
 from .data.data_generator import FlexibleNoiseGenerator
-from .gan import train
+from .gan import metrics, train
 from .gan.ganbase import GAN
 from .gan.models import make_discriminator, make_generator
 from .grid import GridDataset, from_xarray, nearest_index
@@ -104,9 +104,11 @@ def get_network(weights_path=None):
                                        high_res_channels=NB_OUTPUTS, n_timesteps=SEQUENCE_LENGTH)
     noise_shape = (BATCH_SIZE, SEQUENCE_LENGTH, IMG_SIZE, IMG_SIZE, NOISE_CHANNELS)
     gan = GAN(generator, discriminator, noise_generator=FlexibleNoiseGenerator(noise_shape, std=NOISE_STD))
-    gan.compile(generator_optimizer=train.generator_optimizer(), generator_metrics=[],
+    gan.compile(generator_optimizer=train.generator_optimizer(),
+                generator_metrics=[metrics.AngularCosineDistance(), metrics.LogSpectralDistance(),
+                                   metrics.WeightedRMSEForExtremes(), metrics.WindSpeedWeightedRMSE(), metrics.SpatialKS()],
                 discriminator_optimizer=train.discriminator_optimizer(), discriminator_loss=train.discriminator_loss,
-                metrics=[])
+                metrics=[metrics.discriminator_score_fake(), metrics.discriminator_score_real()])
     path = Path(weights_path) if weights_path is not None else WEIGHTS_PATH
     try:
         gan.load_weights(path)

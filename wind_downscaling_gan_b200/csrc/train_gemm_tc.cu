@@ -670,16 +670,34 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const P p, int n
 // ---- library arena for the packed B operands (weights): a 64 MB ring, allocated on first use.  Calls are ordered
 // by the single stream the training ops run on; a packed copy is only read by the GEMM launched right after it.
 constexpr size_t ARENA_BYTES = 64ull << 20;
-char* g_arena = nullptr;
-size_t g_arena_off = 0;
+constexpr int MAX_DEVICES = 64;
+char* g_arena[MAX_DEVICES] = {};       // one ring per device (allocated on that device at first use)
+size_t g_arena_off[MAX_DEVICES] = {};
+int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d >= 0 && d < MAX_DEVICES ? d : 0;
+}
 void* arena_get(size_t bytes) {
-  if (!g_arena && cudaMalloc(&g_arena, ARENA_BYTES) != cudaSuccess) return nullptr;
+  const int d = current_device();
+  if (!g_arena[d] && cudaMalloc(&g_arena[d], ARENA_BYTES) != cudaSuccess) return nullptr;
   bytes = (bytes + 1023) & ~(size_t)1023;
   if (bytes > ARENA_BYTES) return nullptr;
-  if (g_arena_off + bytes > ARENA_BYTES) g_arena_off = 0;
-  void* p = g_arena + g_arena_off;
-  g_arena_off += bytes;
+  if (g_arena_off[d] + bytes > ARENA_BYTES) g_arena_off[d] = 0;
+  void* p = g_arena[d] + g_arena_off[d];
+  g_arena_off[d] += bytes;
   return p;
+}
+// SM count of the current device (the grid / split-K heuristics size their waves with it)
+int sm_count_now() {
+  static int cached[MAX_DEVICES] = {};
+  const int d = current_device();
+  if (!cached[d]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n <= 0) n = 148;
+    cached[d] = n;
+  }
+  return cached[d];
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -699,12 +717,13 @@ EncodeTiledFn get_encode_fn() {
 
 template <class P, int BN, int OP>
 cudaError_t launch_one(const P& p, long long M, int N, long long K, int splits, long long k_per_split, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[MAX_DEVICES] = {};      // the attribute is per device: set it once on each one used
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<P, BN, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)TcCfg<BN>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   CUtensorMap tm;
   memset(&tm, 0, sizeof tm);
@@ -744,7 +763,7 @@ int pick_bn(int N) {
 int pick_bn_grid(int N, long long M, int splits) {
   int bn = pick_bn(N);
   const long long mt = (M + TILE_M - 1) / TILE_M;
-  while (bn > 32 && mt * ((N + bn - 1) / bn) * splits < 148) bn /= 2;
+  while (bn > 32 && mt * ((N + bn - 1) / bn) * splits < sm_count_now()) bn /= 2;
   return bn;
 }
 
@@ -799,7 +818,7 @@ void wdg_tc_wgrad_plan(const ConvGeo& g, int op, int* splits_out, long long* kps
   const long long M = (long long)g.kh * g.kw * g.Ci, K = (long long)g.N * g.Ho * g.Wo;
   const int BN = pick_bn(g.Co), KB = op == OP_BF16 ? 64 : 32;
   const long long tiles = ((M + TILE_M - 1) / TILE_M) * ((g.Co + BN - 1) / BN);
-  long long splits = (4 * 148 + tiles - 1) / tiles;
+  long long splits = (4ll * sm_count_now() + tiles - 1) / tiles;
   const long long max_splits = (K + 4 * KB - 1) / (4 * KB);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

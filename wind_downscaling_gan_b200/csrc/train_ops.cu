@@ -13,6 +13,7 @@
 
 #include "../../include/wdg.h"
 #include "train_direct.cuh"
+#include "train_sparse_stride.cuh"
 #include "train_geo.cuh"
 
 namespace {
@@ -1057,6 +1058,12 @@ static int direct_bwd_weight(const ConvGeo& g, const float* x, const float* dy, 
 
 extern "C" int wdg_conv2d_fwd_act(const float* x, const float* w, const float* bias, float* y, const int* geo, int accumulate,
                                   float alpha, void* stream) {
+  if (wdg_sparse::applies(make_geo(geo))) {   // stride > kernel (critic shortcut conv): exact fp32 direct kernel, every mode
+    const ConvGeo g = make_geo(geo);
+    wdg_sparse::fwd_kernel<<<blocks_for((long long)g.N * g.Ho * g.Wo * g.Co), 256, 0, (cudaStream_t)stream>>>(g, x, w, bias, y, accumulate, alpha);
+    CKT(cudaGetLastError());
+    return 0;
+  }
   if (direct_ok(make_geo(geo), DIRECT_FWD)) return direct_fwd(make_geo(geo), x, w, bias, y, accumulate, alpha, (cudaStream_t)stream);
   if (g_train_precision)
     return wdg_tc_conv2d_fwd(make_geo(geo), x, w, bias, y, accumulate, alpha, g_train_precision, (cudaStream_t)stream);
@@ -1072,6 +1079,11 @@ extern "C" int wdg_conv2d_fwd(const float* x, const float* w, const float* bias,
 
 extern "C" int wdg_conv2d_bwd_data(const float* dy, const float* w, float* dx, const int* geo, int accumulate, void* stream) {
   const ConvGeo gg = make_geo(geo);
+  if (wdg_sparse::applies(gg)) {
+    wdg_sparse::bwd_data_kernel<<<blocks_for((long long)gg.N * gg.H * gg.W * gg.Ci), 256, 0, (cudaStream_t)stream>>>(gg, dy, w, dx, accumulate);
+    CKT(cudaGetLastError());
+    return 0;
+  }
   if (direct_ok(gg, DIRECT_BWD_DATA)) return direct_bwd_data(gg, dy, w, dx, accumulate, (cudaStream_t)stream);
   if (g_train_precision) return wdg_tc_conv2d_bwd_data(gg, dy, w, dx, accumulate, g_train_precision, (cudaStream_t)stream);
   if (gg.stride > 1 && gg.kh >= gg.stride && gg.kw >= gg.stride) {
@@ -1095,9 +1107,19 @@ extern "C" int wdg_conv2d_bwd_data(const float* dy, const float* w, float* dx, c
   return 0;
 }
 
+static int sm_count_now() {      // split-K heuristic of the fp32 backward-weight GEMM: about four CTAs per SM
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  return n;
+}
 extern "C" int wdg_conv2d_bwd_weight_scratch(const int* geo, size_t* bytes, int* splits_out) {
   const ConvGeo g = make_geo(geo);
   const long long M = (long long)g.kh * g.kw * g.Ci, K = (long long)g.N * g.Ho * g.Wo;
+  if (wdg_sparse::applies(g)) {   // no split-K partials
+    if (splits_out) *splits_out = 1;
+    if (bytes) *bytes = 0;
+    return 0;
+  }
   if (direct_ok(g, DIRECT_BWD_WEIGHT)) {
     const long long sl = direct_slabs(g);
     if (splits_out) *splits_out = (int)sl;
@@ -1112,7 +1134,7 @@ extern "C" int wdg_conv2d_bwd_weight_scratch(const int* geo, size_t* bytes, int*
     return 0;
   }
   const long long tiles = g.Co <= 16 ? ((M + 127) / 128) * ((g.Co + 15) / 16) : ((M + 63) / 64) * ((g.Co + 63) / 64);
-  long long splits = (4 * 148 + tiles - 1) / tiles;
+  long long splits = (4ll * sm_count_now() + tiles - 1) / tiles;
   const long long max_splits = (K + 255) / 256;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -1125,6 +1147,12 @@ extern "C" int wdg_conv2d_bwd_weight(const float* x, const float* dy, float* dw,
                                      int accumulate, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int splits = 1;
+  if (wdg_sparse::applies(make_geo(geo))) {
+    const ConvGeo g = make_geo(geo);
+    wdg_sparse::bwd_weight_kernel<<<blocks_for((long long)g.kh * g.kw * g.Ci * g.Co), 256, 0, stream>>>(g, x, dy, dw, accumulate);
+    CKT(cudaGetLastError());
+    return 0;
+  }
   wdg_conv2d_bwd_weight_scratch(geo, nullptr, &splits);
   if (direct_ok(make_geo(geo), DIRECT_BWD_WEIGHT)) return direct_bwd_weight(make_geo(geo), x, dy, dw, (float*)scratch, accumulate, stream);
   BwdWeightProblem p{make_geo(geo), x, dy, (float*)scratch, 0};

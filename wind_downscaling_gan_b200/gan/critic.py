@@ -9,33 +9,12 @@ from .models import _glorot_uniform, _orthogonal
 LW = "layer_with_weights-%d/"
 
 
-def critic_weight_shapes(size, lr_ch, hr_ch, F):
-    """Variable name -> shape of the graph `make_discriminator` builds (current code: no shortcut branch)."""
-    from ..train.nets import critic_plan
-    convs, dense_idx, flat = critic_plan(size, F)
-    s = {}
-    s[(LW % 0) + "cell/kernel"] = (3, 3, hr_ch, 4 * hr_ch)
-    s[(LW % 0) + "cell/recurrent_kernel"] = (3, 3, hr_ch, 4 * hr_ch)
-    s[(LW % 0) + "cell/bias"] = (4 * hr_ch,)
-    s[(LW % 1) + "cell/kernel"] = (3, 3, lr_ch + hr_ch, 4 * F)
-    s[(LW % 1) + "cell/recurrent_kernel"] = (3, 3, F, 4 * F)
-    s[(LW % 1) + "cell/bias"] = (4 * F,)
-    for i, cin in ((2, hr_ch), (3, F)):
-        s[(LW % i) + "layer/w"] = (3, 3, cin, F)
-        s[(LW % i) + "layer/layer/bias"] = (F,)
-        s[(LW % i) + "layer/sn_u"] = (1, F)
-    for i in (4, 5):
-        s[(LW % i) + "gamma"] = (F,)
-        s[(LW % i) + "beta"] = (F,)
-    for e in convs:
-        s[(LW % e["idx"]) + "layer/w"] = (e["k"], e["k"], e["cin"], e["cout"])
-        s[(LW % e["idx"]) + "layer/layer/bias"] = (e["cout"],)
-        s[(LW % e["idx"]) + "layer/sn_u"] = (1, e["cout"])
-        s[(LW % e["ln"]) + "gamma"] = (e["cout"],)
-        s[(LW % e["ln"]) + "beta"] = (e["cout"],)
-    s[(LW % dense_idx) + "layer/kernel"] = (flat, 1)
-    s[(LW % dense_idx) + "layer/bias"] = (1,)
-    return s
+def critic_weight_shapes(size, lr_ch, hr_ch, F, ckpt_topology=False):
+    """Variable name -> shape of the graph `make_discriminator` builds, read from the `wdg_critic` handle's own table
+    (csrc/wdg_critic.cu walks models.py:93-140).  ckpt_topology: the graph the shipped discriminator checkpoint was
+    written from (shortcut branch of tf_utils.py:15-32 around the last 7x7 stage)."""
+    from ..train.nets import CriticHandle
+    return CriticHandle.get(size, lr_ch, hr_ch, F, ckpt_topology).shapes()
 
 
 class Critic:
@@ -44,7 +23,7 @@ class Critic:
     name = "discriminator"
 
     def __init__(self, low_res_size, high_res_size, low_res_channels, high_res_channels, n_timesteps, batch_size=None,
-                 feature_channels=16, seed=None):
+                 feature_channels=16, seed=None, ckpt_topology=False):
         if low_res_size != high_res_size:
             raise NotImplementedError("The discriminator assumes that the low res and high res images have the same size."
                                       "Perhaps you should upsample your low res image first?")
@@ -54,11 +33,24 @@ class Critic:
         self.output_names = ["score"]
         self.optimizer = self.compiled_loss = self.compiled_metrics = None
         self.metrics = []
-        self._shapes = critic_weight_shapes(high_res_size, low_res_channels, high_res_channels, feature_channels)
         self._dev = None
         self._before_read = None     # hooks of an owning GAN, see gan/models.py
         self._after_write = None
-        rng = np.random.default_rng(seed)
+        self._seed = seed
+        self._set_topology(ckpt_topology)
+
+    def _handle(self):
+        from ..train.nets import CriticHandle
+        return CriticHandle.get(self.image_size, self.low_res_channels, self.high_res_channels, self.feature_channels,
+                                self.ckpt_topology)
+
+    def _set_topology(self, ckpt_topology):
+        """(Re)builds the variable table and the Keras-default initial values for one of the two graph revisions."""
+        self.ckpt_topology = bool(ckpt_topology)
+        self._shapes = critic_weight_shapes(self.image_size, self.low_res_channels, self.high_res_channels,
+                                            self.feature_channels, self.ckpt_topology)
+        self._dev = None
+        rng = np.random.default_rng(self._seed)
         w = {}
         for name, shp in self._shapes.items():
             leaf = name.rsplit("/", 1)[1]
@@ -108,19 +100,35 @@ class Critic:
         return {k: v.copy() for k, v in self._w.items()}
 
     def save_weights(self, filepath, *args, **kwargs):
+        """ganbase.py:134 (`<dir>/discriminator`): TensorFlow checkpoint-V2 bundle, see Generator.save_weights."""
+        from ..tf_checkpoint import write_bundle
         filepath = str(filepath)
         os.makedirs(os.path.dirname(filepath) or ".", exist_ok=True)
-        np.savez(filepath + ".npz", **self.get_weights())
+        write_bundle(filepath, self.get_weights())
 
     def load_weights(self, filepath, *args, **kwargs):
         filepath = str(filepath)
+        if os.path.exists(filepath + ".index"):
+            from ..tf_checkpoint import read_bundle, select_model_variables
+            tensors = read_bundle(filepath)
+            try:
+                sel = select_model_variables(tensors, self._shapes, "discriminator")
+            except ValueError:
+                # the checkpoint was written by the other revision of make_discriminator (the reference ships a critic
+                # checkpoint WITH the shortcut branch its current code never builds, SURVEY F6): adopt that graph
+                other = critic_weight_shapes(self.image_size, self.low_res_channels, self.high_res_channels,
+                                             self.feature_channels, not self.ckpt_topology)
+                sel = select_model_variables(tensors, other, "discriminator")      # raises if neither graph matches
+                print(f"  discriminator checkpoint has the {'shortcut' if not self.ckpt_topology else 'current-code'} "
+                      "topology: rebuilding the critic with it")
+                self._set_topology(not self.ckpt_topology)
+                if self._after_write is not None:
+                    self._after_write()
+            self.set_weights(sel)
+            return
         if os.path.exists(filepath + ".npz"):
             with np.load(filepath + ".npz") as z:
                 self.set_weights({k: z[k] for k in z.files})
-            return
-        if os.path.exists(filepath + ".index"):
-            from ..tf_checkpoint import read_bundle, select_model_variables
-            self.set_weights(select_model_variables(read_bundle(filepath), self._shapes, "discriminator"))
             return
         raise FileNotFoundError(filepath)
 
@@ -130,14 +138,14 @@ class Critic:
 
     def __call__(self, inputs, training=False, mask=None):
         """`discriminator([low_res, high_res], training=False)` -> score (B, 1) CUDA tensor."""
-        from ..train.nets import CriticNet, to_device
+        from ..train.nets import CriticNet
         from ..train.step import _dev
         from ..train import ops as _ops
         _ops.use_current_stream()
         if self._before_read is not None:
             self._before_read()
         if self._dev is None:
-            self._dev = to_device(self._w)
+            self._dev = self._handle().pack(self._w)
         low_res, high_res = _dev(inputs[0]), _dev(inputs[1])
         if tuple(low_res.shape[:-1]) != tuple(high_res.shape[:-1]):
             raise ValueError("low_resolution_image and high_resolution_image must share (B, T, H, W)")

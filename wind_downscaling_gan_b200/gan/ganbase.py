@@ -32,12 +32,20 @@ class GAN:
     def compile(self, generator_optimizer, discriminator_optimizer, generator_loss=None, generator_metrics=None,
                 discriminator_loss=None, **kwargs):
         self.metrics = list(kwargs.get("metrics") or [])
-        if kwargs.get("train_precision"):          # extension: arithmetic of the training convolution GEMMs
-            from ..train import ops as _train_ops
-            _train_ops.set_precision(kwargs["train_precision"])
+        # extension: arithmetic of THIS model's training convolution GEMMs ("fp32" | "tf32" | "bf16").  The library
+        # switch is process-wide, so the model re-asserts its own choice at the start of every train_step / test_step.
+        self.train_precision = kwargs.get("train_precision") or getattr(self, "train_precision", None)
+        self._assert_precision()
         self.generator.compile(generator_optimizer, generator_loss, metrics=generator_metrics)
         if self.discriminator is not None:
             self.discriminator.compile(discriminator_optimizer, discriminator_loss)
+
+    def _assert_precision(self):
+        if getattr(self, "train_precision", None):
+            from ..train import ops as _train_ops
+            if _train_ops.get_precision() != self.train_precision:
+                _train_ops.set_precision(self.train_precision)
+                self._graphed = None          # a captured step replays the arithmetic it was captured with
 
     def call(self, inputs, training=None, mask=None):
         """ganbase.py:126-130: draw noise for the batch and run the generator."""
@@ -71,9 +79,17 @@ class GAN:
         """ganbase.py:21-94.  data = (low_res, high_res[, sample_weight]); `draws` optionally replaces the random
         tensors (parity tests): per critic iteration [G noise, eps (B,), noise on real, noise on fake], then
         G noise for the generator update and for the metric recompute.  `comm` (train/dist.py Comm): data-parallel
-        training, `data` being this rank's shard of the global batch."""
+        training, `data` being this rank's shard of the global batch.
+
+        Returns the reference's dict (:75-93): the seven logged scalars, then `result()` of every compiled metric object
+        (`metrics=` of compile under its own name -- d_real / d_fake running means in api.py:84 -- and every generator
+        metric as `g_<name>`), all of them updated first with this step's inference-mode recompute (:71-72)."""
         from .. import _lib
         from ..train.step import GraphedStep, train_step
+        if len(data) > 2 and data[2] is not None:
+            raise NotImplementedError("sample_weight is not supported by the CUDA train_step (the reference never passes one: "
+                                      "its generators yield (low_res, high_res) pairs)")
+        self._assert_precision()
         st = self._state()
         before = _lib.calls
         if draws is None and self.use_cuda_graph:
@@ -81,14 +97,44 @@ class GAN:
             # eagerly and size every buffer
             if self._graphed is None or self._graphed.comm is not comm:
                 self._graphed = GraphedStep(st, self.noise_generator, self._n_critic, comm, self.skip_dead_gradient_penalty)
-            out = self._graphed(data[0], data[1])
+            out, extras = self._graphed(data[0], data[1])
             if self._graphed.graph is None or self._graphed.calls == GraphedStep.WARMUP + 1:
                 self._last_step_calls = _lib.calls - before      # launches of one step, counted while it ran eagerly / was captured
         else:
-            out = train_step(st, data[0], data[1], self.noise_generator, self._n_critic, draws, comm=comm,
-                             skip_dead_gp=self.skip_dead_gradient_penalty)
+            out, extras = train_step(st, data[0], data[1], self.noise_generator, self._n_critic, draws, comm=comm,
+                                     skip_dead_gp=self.skip_dead_gradient_penalty)
             self._last_step_calls = _lib.calls - before
+        self._last_recompute = extras      # (generated images, D(real), D(generated)) of the inference-mode recompute
+        self._update_metrics(out, data[1], extras)
         return out
+
+    def _update_metrics(self, out, high_res, extras):
+        """ganbase.py:71-72, :82-93.  With a data-parallel `comm` each rank's metric objects see its own shard."""
+        gen_metrics = list(getattr(self.generator, "metrics", None) or [])
+        if not gen_metrics and not self.metrics:
+            return
+        fake, s_real, s_fake = extras
+        for metric in gen_metrics:
+            metric.update_state(high_res, fake)
+        if self.metrics:
+            s_real, s_fake = s_real.detach().cpu().numpy(), s_fake.detach().cpu().numpy()
+            for metric in self.metrics:
+                metric.update_state(s_real, s_fake)
+        self._collect_metrics(out, gen_metrics)
+
+    def _collect_metrics(self, out, gen_metrics=()):
+        for metric in self.metrics:
+            result = metric.result()
+            if isinstance(result, dict):
+                out.update(result)
+            else:
+                out[metric.name] = result
+        for metric in gen_metrics:
+            result = metric.result()
+            if isinstance(result, dict):
+                out.update(result)
+            else:
+                out[f'g_{metric.name}'] = result
 
     def launches_per_step(self):
         """Library entry points the last train_step called (each launches at least one kernel): bench.py's gpu_launches."""
@@ -97,7 +143,10 @@ class GAN:
     def test_step(self, data, draws=None):
         """ganbase.py:96-113."""
         from ..train.step import test_step
-        return test_step(self._state(), data[0], data[1], self.noise_generator, draws)
+        self._assert_precision()
+        out = test_step(self._state(), data[0], data[1], self.noise_generator, draws)
+        self._collect_metrics(out)          # :105-111: results of the compiled metrics (test_step does not update them)
+        return out
 
     def sync_weights(self):
         """Copies the trained fp32 device weights back into the model handles.  Called automatically (lazily) before a

@@ -169,23 +169,25 @@ class Generator(_NativeModel):
         return out
 
     def save_weights(self, filepath, *args, **kwargs):
-        """Counterpart of ganbase.py:133 (`<dir>/generator`): written as `<filepath>.npz`
-        keyed by the checkpoint variable names."""
+        """Counterpart of ganbase.py:133 (`<dir>/generator`): a TensorFlow checkpoint-V2 bundle `<filepath>.index` +
+        `<filepath>.data-00000-of-00001` keyed `<variable>/.ATTRIBUTES/VARIABLE_VALUE` like the reference's own
+        checkpoints (tf_checkpoint.write_bundle: TensorFlow's header and crc32c checksums)."""
+        from ..tf_checkpoint import write_bundle
         filepath = str(filepath)
         os.makedirs(os.path.dirname(filepath) or ".", exist_ok=True)
-        np.savez(filepath + ".npz", **self.get_weights())
+        write_bundle(filepath, self.get_weights())
 
     def load_weights(self, filepath, *args, **kwargs):
-        """Counterpart of ganbase.py:139.  Accepts `<filepath>.npz`; a TF-checkpoint-V2 prefix
-        (`<filepath>.index` + data shard) is read with the bundle reader when present."""
+        """Counterpart of ganbase.py:139: reads the TF-checkpoint-V2 prefix `<filepath>.index` + data shard (the
+        reference's format and what save_weights writes); `<filepath>.npz` (round-1 exports) is still accepted."""
         filepath = str(filepath)
-        if os.path.exists(filepath + ".npz"):
-            with np.load(filepath + ".npz") as z:
-                self.set_weights({k: z[k] for k in z.files})
-            return
         if os.path.exists(filepath + ".index"):
             from ..tf_checkpoint import read_bundle, select_model_variables
             self.set_weights(select_model_variables(read_bundle(filepath), self._shapes, "generator"))
+            return
+        if os.path.exists(filepath + ".npz"):
+            with np.load(filepath + ".npz") as z:
+                self.set_weights({k: z[k] for k in z.files})
             return
         raise FileNotFoundError(filepath)
 
@@ -360,11 +362,13 @@ def make_generator(image_size: int, in_channels: int, noise_channels: int, out_c
 
 
 def make_discriminator(low_res_size: int, high_res_size: int, low_res_channels: int, high_res_channels: int,
-                       n_timesteps: int, batch_size: int = None, feature_channels: int = 16):
-    """Same signature as the reference's `make_discriminator` (models.py:76-84)."""
+                       n_timesteps: int, batch_size: int = None, feature_channels: int = 16, ckpt_topology: bool = False):
+    """Same signature as the reference's `make_discriminator` (models.py:76-84).  ckpt_topology (extension): build the
+    graph revision the shipped weights-55.ckpt/discriminator was written from (shortcut branch); loading
+    such a checkpoint switches to it automatically."""
     if low_res_size != high_res_size:
         raise NotImplementedError("The discriminator assumes that the low res and high res images have the same size."
                                   "Perhaps you should upsample your low res image first?")  # models.py:89-91
     from .critic import Critic
     return Critic(low_res_size, high_res_size, low_res_channels, high_res_channels, n_timesteps, batch_size,
-                  feature_channels)
+                  feature_channels, ckpt_topology=ckpt_topology)

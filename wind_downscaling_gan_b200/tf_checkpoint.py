@@ -3,7 +3,16 @@ the format `GAN.save_weights` / `load_weights` use in the reference (ganbase.py:
 
 The index is a LevelDB-style SSTable with uncompressed, prefix-compressed blocks whose values are
 `BundleEntryProto` messages (dtype, shape, shard, offset, size); tensor bytes are little-endian,
-row-major in the data shard.  Pure Python, no TensorFlow.  (SURVEY.md Appendix B.)
+row-major in the data shard.  No TensorFlow needed.  (SURVEY.md Appendix B.)
+
+Checksums are TensorFlow's: every SSTable block is followed by a 1-byte compression type and
+`mask(crc32c(block + type))`, every BundleEntryProto carries `mask(crc32c(tensor bytes))` (field 6, fixed32), with
+mask(c) = rotr(c, 15) + 0xa282ead8.  The CRC routine (csrc/wdg_crc32c.cu) reproduces all six block trailers of the
+reference's own `weights-55.ckpt/*.index` files (tests/test_abi_cpu.py).  The reader verifies both kinds; the writer
+emits both, plus the BundleHeaderProto TensorFlow writes (num_shards 1, little endian, version producer 1), so
+`tf.train.load_checkpoint(prefix)` / BundleReader accept the files.  NOT written: the `_CHECKPOINTABLE_OBJECT_GRAPH`
+entry Keras' object-based `load_weights` matches layers with -- a TensorFlow user restores by key
+(`reader.get_tensor("layer_with_weights-0/layer/w/.ATTRIBUTES/VARIABLE_VALUE")`).
 """
 import os
 import struct
@@ -11,6 +20,25 @@ import struct
 import numpy as np
 
 _DTYPES = {1: np.float32, 2: np.float64, 3: np.int32, 9: np.int64}
+
+
+def crc32c(data):
+    from . import _lib
+    b = bytes(data)
+    return int(_lib.lib().wdg_crc32c(0, b, len(b)))
+
+
+def masked_crc32c(data):
+    c = crc32c(data)
+    return (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def _check_block(b, off, size, path):
+    stored = struct.unpack("<I", b[off + size + 1:off + size + 5])[0]
+    if b[off + size] != 0:
+        raise ValueError(f"{path}: compressed SSTable block (type {b[off + size]}) is not supported")
+    if stored != masked_crc32c(b[off:off + size + 1]):
+        raise ValueError(f"{path}: SSTable block at {off} fails its crc32c check (corrupt index)")
 
 
 def _varint(b, p):
@@ -76,9 +104,11 @@ def read_index(path):
     ioff, p = _varint(foot, p)
     isize, p = _varint(foot, p)
     entries = {}
+    _check_block(b, ioff, isize, path)
     for _, handle in _block(b, ioff, isize):
         off, q = _varint(handle, 0)
         size, q = _varint(handle, q)
+        _check_block(b, off, size, path)
         for key, val in _block(b, off, size):
             if key == b"":
                 continue  # BundleHeaderProto
@@ -87,7 +117,8 @@ def read_index(path):
             for dim in _proto(d.get(2, [b""])[0]).get(2, []):
                 shape.append(_proto(dim).get(1, [0])[0])
             entries[key.decode()] = {"dtype": int(d.get(1, [0])[0]), "shape": shape, "shard": int(d.get(3, [0])[0]),
-                                     "offset": int(d.get(4, [0])[0]), "size": int(d.get(5, [0])[0])}
+                                     "offset": int(d.get(4, [0])[0]), "size": int(d.get(5, [0])[0]),
+                                     "crc32c": struct.unpack("<I", d[6][0])[0] if 6 in d else None}
     return entries
 
 
@@ -105,14 +136,16 @@ def read_bundle(prefix):
                 continue
             f.seek(e["offset"])
             raw = f.read(e["size"])
+            if e["crc32c"] is not None and e["crc32c"] != masked_crc32c(raw):
+                raise ValueError(f"{data_path}: tensor {key} fails its crc32c check")
             a = np.frombuffer(raw, dtype=np.dtype(_DTYPES[e["dtype"]]).newbyteorder("<")).reshape(e["shape"])
             out[key[:-len("/.ATTRIBUTES/VARIABLE_VALUE")]] = a.astype(_DTYPES[e["dtype"]])
     return out
 
 
 def write_bundle(prefix, tensors):
-    """Writes {name: float32 ndarray} as a single-shard checkpoint-V2 bundle readable by read_bundle
-    (one uncompressed data block; enough for round-trip tests and for exporting weights)."""
+    """Writes {name: float32 ndarray} as a single-shard checkpoint-V2 bundle: TensorFlow's header, per-tensor and
+    per-block masked crc32c (one uncompressed data block)."""
     prefix = str(prefix)
 
     def venc(x):
@@ -135,10 +168,12 @@ def write_bundle(prefix, tensors):
         a = np.ascontiguousarray(tensors[name], dtype="<f4")
         shape = b"".join(field(2, 2, venc(len(field(1, 0, venc(d)))) + field(1, 0, venc(d))) for d in a.shape)
         entry = field(1, 0, venc(1)) + field(2, 2, venc(len(shape)) + shape) + field(4, 0, venc(len(data))) + \
-            field(5, 0, venc(a.nbytes))
+            field(5, 0, venc(a.nbytes)) + field(6, 5, struct.pack("<I", masked_crc32c(a.tobytes())))
         items.append(((name + "/.ATTRIBUTES/VARIABLE_VALUE").encode(), entry))
         data += a.tobytes()
-    items.insert(0, (b"", field(1, 0, venc(1))))  # header: num_shards = 1
+    # BundleHeaderProto as TensorFlow writes it (bytes 08 01 1a 02 08 01 in the reference's index files):
+    # num_shards = 1, endianness LITTLE (default, omitted), version { producer: 1 }
+    items.insert(0, (b"", field(1, 0, venc(1)) + field(3, 2, venc(2) + field(1, 0, venc(1)))))
 
     def make_block(kvs):
         blk = bytearray()
@@ -147,15 +182,18 @@ def write_bundle(prefix, tensors):
         restarts = struct.pack("<I", 0) + struct.pack("<I", 1)
         return bytes(blk) + restarts
 
+    def trailer(blk):                      # compression type 0 + masked crc32c over block and type byte
+        return b"\x00" + struct.pack("<I", masked_crc32c(blk + b"\x00"))
+
     dblock = make_block(items)
-    out = bytearray(dblock) + b"\x00" + b"\x00\x00\x00\x00"          # type 0 (no compression) + crc (unchecked)
+    out = bytearray(dblock) + trailer(dblock)
     handle = venc(0) + venc(len(dblock))
     iblock = make_block([(items[-1][0] + b"\xff", handle)])
     ioff = len(out)
-    out += iblock + b"\x00" + b"\x00\x00\x00\x00"
+    out += iblock + trailer(iblock)
     mblock = make_block([])
     moff = len(out)
-    out += mblock + b"\x00" + b"\x00\x00\x00\x00"
+    out += mblock + trailer(mblock)
     foot = venc(moff) + venc(len(mblock)) + venc(ioff) + venc(len(iblock))
     foot += b"\x00" * (40 - len(foot)) + struct.pack("<Q", 0xDB4775248B80FB57)
     out += foot

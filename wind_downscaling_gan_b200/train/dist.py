@@ -47,6 +47,9 @@ class Comm:
         """Sums the gradient tensors over ranks through ONE flat bucket (a single collective)."""
         if self.world == 1:
             return grads
+        if getattr(grads, "flat", None) is not None and not skip:
+            self._all_reduce(grads.flat)          # the model's gradients already live in one flat buffer (train/nets.py FlatVars)
+            return grads
         names = [n for n in grads if n not in skip]
         if not names:
             return grads

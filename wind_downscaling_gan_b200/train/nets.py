@@ -367,120 +367,138 @@ class GenNet:
 
 
 # =============================================================================================== critic
-def critic_plan(size, F):
-    """Shapes of the pyramid built by models.py:111-136 (current code: the `i > 1` shortcut never triggers)."""
-    convs, idx, s, c = [], 6, size, 2 * F
-    while s >= 16:
-        so = (s + 2 - 7) // 3 + 1
-        convs.append(dict(idx=idx, ln=idx + 1, k=7, stride=3, pad=1, cin=c, cout=2 * c, size_in=s, size_out=so))
-        s, c, idx = so, 2 * c, idx + 2
-    i = 0
-    while s >= 4:
-        so = (s + 2 - 7) // 3 + 1
-        if so < 1:
-            raise ValueError("invalid image size for the critic")
-        convs.append(dict(idx=idx, ln=idx + 1, k=7, stride=3, pad=1, cin=c, cout=2 * c, size_in=s, size_out=so))
-        s, c, idx = so, 2 * c, idx + 2
-        i += 1
-    if i > 1:
-        raise NotImplementedError("shortcut branch (models.py:127-130) is unreachable for valid sizes")
-    while s > 2:
-        so = (s - 3) // 2 + 1
-        convs.append(dict(idx=idx, ln=idx + 1, k=3, stride=2, pad=0, cin=c, cout=2 * c, size_in=s, size_out=so))
-        s, c, idx = so, 2 * c, idx + 2
-    return convs, idx, s * s * c
+class FlatVars(dict):
+    """Checkpoint variable name -> view into ONE flat fp32 device buffer laid out by the `wdg_critic` handle (trainable
+    variables first, `sn_u` vectors after them; include/wdg.h).  `.flat` is the whole buffer, `.handle` the CriticHandle."""
+
+    def __init__(self, handle, flat, names):
+        super().__init__()
+        self.handle, self.flat = handle, flat
+        for name in names:
+            shape, off, _ = handle.table[name]
+            self[name] = flat[off:off + int(np.prod(shape))].view(*shape)
+
+
+class CriticHandle:
+    """`wdg_critic*` (csrc/wdg_critic.cu): layer plan + variable table of `make_discriminator` (models.py:76-142)."""
+
+    _cache = {}
+
+    def __init__(self, size, lr_ch, hr_ch, n_timesteps, F, ckpt_topology):
+        import ctypes as C
+        from .. import _lib
+        self.key = (size, lr_ch, hr_ch, F, bool(ckpt_topology))
+        h = C.c_void_p()
+        rc = _lib.lib().wdg_critic_create(C.byref(h), size, size, lr_ch, hr_ch, n_timesteps, F, int(bool(ckpt_topology)))
+        if rc != 0:
+            raise ValueError(_lib.lib().wdg_last_error().decode())
+        self.h = h
+        self.table = {}                       # name -> (shape, offset in floats, trainable), creation order
+        for i in range(_lib.lib().wdg_critic_num_weights(h)):
+            name, dims, nd, off, tr = C.c_char_p(), (C.c_int64 * 4)(), C.c_int(), C.c_int64(), C.c_int()
+            _lib.check(_lib.lib().wdg_critic_weight_info(h, i, C.byref(name), dims, C.byref(nd), C.byref(off), C.byref(tr)))
+            self.table[name.value.decode()] = (tuple(int(d) for d in dims[:nd.value]), int(off.value), bool(tr.value))
+        self.n_total = int(_lib.lib().wdg_critic_num_floats(h))
+        self.n_train = int(_lib.lib().wdg_critic_num_trainable_floats(h))
+        self.size, self.lr_ch, self.hr_ch, self.F, self.ckpt_topology = size, lr_ch, hr_ch, F, bool(ckpt_topology)
+
+    @classmethod
+    def get(cls, size, lr_ch, hr_ch, F, ckpt_topology=False, n_timesteps=24):
+        key = (size, lr_ch, hr_ch, F, bool(ckpt_topology))
+        if key not in cls._cache:
+            cls._cache[key] = cls(size, lr_ch, hr_ch, n_timesteps, F, ckpt_topology)
+        return cls._cache[key]
+
+    @classmethod
+    def for_weights(cls, weights, size):
+        """The handle whose variable table matches a name -> array dict (either topology)."""
+        F = weights[(LW % 2) + "layer/w"].shape[-1]
+        hr_ch = weights[(LW % 0) + "cell/kernel"].shape[2]
+        lr_ch = weights[(LW % 1) + "cell/kernel"].shape[2] - hr_ch
+        for topo in (False, True):
+            h = cls.get(size, lr_ch, hr_ch, F, topo)
+            if set(h.table) == set(weights) and all(tuple(weights[n].shape) == h.table[n][0] for n in h.table):
+                return h
+        raise ValueError("critic weights match neither the current-code nor the checkpoint (shortcut) topology at size %d" % size)
+
+    def shapes(self):
+        return {n: s for n, (s, _, _) in self.table.items()}
+
+    def trainable(self):
+        return [n for n, (_, _, tr) in self.table.items() if tr]
+
+    def pack(self, weights):
+        """name -> numpy / tensor dict -> FlatVars on the current device."""
+        flat = torch.zeros(self.n_total, dtype=torch.float32, device="cuda")
+        fv = FlatVars(self, flat, list(self.table))
+        for n, v in fv.items():
+            src = weights[n]
+            v.copy_(src if isinstance(src, torch.Tensor) else torch.as_tensor(np.asarray(src, np.float32)))
+        return fv
+
+    def grads(self, flat):
+        return FlatVars(self, flat, self.trainable())
 
 
 class CriticNet:
+    """One differentiable call of the critic on the `wdg_critic` handle: forward keeps a context buffer, backward
+    consumes it.  `weights`: FlatVars (used in place) or a name -> CUDA tensor dict (packed; the spectral-norm update of a
+    training-mode call is written back into its tensors, as the in-place Keras wrapper would)."""
+
     def __init__(self, weights, size):
-        self.w = weights
-        self.F = weights[(LW % 2) + "layer/w"].shape[-1]
-        self.convs, self.dense_idx, self.flat = critic_plan(size, self.F)
-        self.sn_layers = [2, 3] + [e["idx"] for e in self.convs]
+        if isinstance(weights, FlatVars):
+            self.vars, self._writeback = weights, None
+        else:
+            self.vars, self._writeback = CriticHandle.for_weights(weights, size).pack(weights), weights
+        self.h = self.vars.handle
+        self.w = self.vars
+
+    def _write_back(self):
+        if self._writeback is not None:
+            for n, v in self.vars.items():
+                self._writeback[n].copy_(v)
+
+    def _scratch(self, B, T):
+        import ctypes as C
+        from .. import _lib
+        nb = C.c_size_t()
+        _lib.check(_lib.lib().wdg_critic_scratch_bytes(self.h.h, B, T, C.byref(nb)))
+        return ops.scratch(nb.value, "critic"), nb.value
 
     def spectral_norm_step(self):
         """What a training-mode call does to the critic's VARIABLES (one power iteration per wrapped layer), without the
         forward pass."""
-        for i in self.sn_layers:
-            sn_step(self.w, i)
+        from .. import _lib
+        sc, nb = self._scratch(1, 1)
+        _lib.check(_lib.lib().wdg_critic_sn_update(self.h.h, ops._p(self.vars.flat), ops._p(sc), nb, ops._s()))
+        self._write_back()
 
     def forward(self, low_res, high_res, training):
         """[B,T,S,S,3], [B,T,S,S,2] -> score [B,1]."""
-        w, F = self.w, self.F
-        B, T, S = low_res.shape[:3]
-        N = B * T
-        if training:
-            for i in self.sn_layers:
-                sn_step(w, i)
-            # every training-mode call reads the variables at their current value (later in-place SN updates of the
-            # shared tensors must not leak into this call's backward): snapshot them
-            w = {k: (v.clone() if k.endswith(("/w", "kernel", "bias", "gamma", "beta")) else v) for k, v in w.items()}
-        cl, ch = low_res.shape[-1], high_res.shape[-1]
-        hr_in = high_res.reshape(N, S, S, ch).contiguous()
-        mix_in = ops.empty(N, S, S, cl + ch)                                                   # models.py:100
-        ops.axpby(View(mix_in, cl, cl + ch, 0), full(low_res.reshape(N, S, S, cl)))
-        ops.axpby(View(mix_in, ch, cl + ch, cl), full(hr_in))
-        L = {}
-        L["lstm_hr"] = ConvLSTM(w[(LW % 0) + "cell/kernel"], w[(LW % 0) + "cell/recurrent_kernel"], w[(LW % 0) + "cell/bias"])
-        h1 = L["lstm_hr"].forward(hr_in, B, T)                                                 # :93
-        L["c_hr"] = Conv(w[(LW % 2) + "layer/w"], w[(LW % 2) + "layer/layer/bias"], 1, 1)      # :94-96
-        a_hr = L["c_hr"].forward(full(h1), N, S, S)
-        x = ops.empty(N, S, S, 2 * F)                                                          # :108
-        L["ln_hr"] = LayerNorm(w, 4)
-        L["ln_hr"].forward(a_hr.t, View(x, F, 2 * F, 0))                                       # :97
-        L["lstm_mix"] = ConvLSTM(w[(LW % 1) + "cell/kernel"], w[(LW % 1) + "cell/recurrent_kernel"], w[(LW % 1) + "cell/bias"])
-        h2 = L["lstm_mix"].forward(mix_in, B, T)                                               # :101
-        L["c_mix"] = Conv(w[(LW % 3) + "layer/w"], w[(LW % 3) + "layer/layer/bias"], 1, 1)     # :102-104
-        a_mix = L["c_mix"].forward(full(h2), N, S, S)
-        L["ln_mix"] = LayerNorm(w, 5)
-        L["ln_mix"].forward(a_mix.t, View(x, F, 2 * F, F))                                     # :105
-        cur, size = x, S
-        for n, e in enumerate(self.convs):                                                     # :111-136
-            c = Conv(w[(LW % e["idx"]) + "layer/w"], w[(LW % e["idx"]) + "layer/layer/bias"], e["stride"], e["pad"])
-            a = c.forward(full(cur), N, size, size)
-            ln = LayerNorm(w, e["ln"])
-            cur = ln.forward(a.t).t
-            L["pc%d" % n], L["pln%d" % n] = c, ln
-            size = e["size_out"]
-        D = self.flat
+        import ctypes as C
+        from .. import _lib
+        B, T = low_res.shape[:2]
+        low_res, high_res = low_res.contiguous(), high_res.contiguous()
+        nb = C.c_size_t()
+        _lib.check(_lib.lib().wdg_critic_context_bytes(self.h.h, B, T, int(bool(training)), C.byref(nb)))
+        self.ctx = torch.empty(nb.value, dtype=torch.uint8, device="cuda")
+        sc, sb = self._scratch(B, T)
         score = ops.empty(B, 1)
-        dk, db_ = w[(LW % self.dense_idx) + "layer/kernel"], w[(LW % self.dense_idx) + "layer/bias"]
-        ops.dense_mean_fwd(cur, dk, db_, score, B, T, D)                                       # :137-140
-        self.L, self.dims, self.flat_act, self.w_used = L, (B, T, S, N, cl, ch), cur, w
+        _lib.check(_lib.lib().wdg_critic_forward(self.h.h, ops._p(self.vars.flat), ops._p(low_res), ops._p(high_res), ops._p(score),
+                                                 B, T, int(bool(training)), ops._p(self.ctx), nb.value, ops._p(sc), sb, ops._s()))
+        self.dims = (B, T, int(bool(training)), tuple(high_res.shape))
+        if training:
+            self._write_back()
         return score
 
     def backward(self, dscore, need_weight_grads=True, need_input_grad=False):
-        """dscore [B,1].  Returns (weight grads dict or {}, d high_res [B,T,S,S,ch] or None)."""
-        w, F, L = self.w_used, self.F, self.L
-        B, T, S, N, cl, ch = self.dims
-        g = {}
-        nw = need_weight_grads
-        D = self.flat
-        dk = w[(LW % self.dense_idx) + "layer/kernel"]
-        dflat = torch.empty_like(self.flat_act)
-        ddk, ddb = ops.empty(*dk.shape), ops.empty(1)
-        ops.dense_mean_bwd(dscore, self.flat_act, dk, dflat, ddk, ddb, B, T, D)
-        g[(LW % self.dense_idx) + "layer/kernel"], g[(LW % self.dense_idx) + "layer/bias"] = ddk, ddb
-        d = dflat
-        for n in range(len(self.convs) - 1, -1, -1):
-            e = self.convs[n]
-            da, gb = L["pln%d" % n].backward(full(d), ALPHA)
-            g.update(gb)
-            dxv, dw, db = L["pc%d" % n].backward(da, need_dw=nw, act_done=True)
-            g[(LW % e["idx"]) + "layer/w"], g[(LW % e["idx"]) + "layer/layer/bias"] = dw, db
-            d = dxv.t
-        # d: [N,S,S,2F] gradient of the concat(hr, mix)
-        d_hr_in = ops.zeros(N, S, S, ch) if need_input_grad else None
-        for tag, ln_i, conv_i, lstm_i, off in (("hr", 4, 2, 0, 0), ("mix", 5, 3, 1, F)):
-            da, gb = L["ln_" + tag].backward(View(d, F, 2 * F, off), ALPHA)
-            g.update(gb)
-            dh, dw, db = L["c_" + tag].backward(da, need_dw=nw, act_done=True)
-            g[(LW % conv_i) + "layer/w"], g[(LW % conv_i) + "layer/layer/bias"] = dw, db
-            dx, dK, dR, dbl = L["lstm_" + tag].backward(dh.t, need_dx=need_input_grad, need_dw=nw)
-            g[(LW % lstm_i) + "cell/kernel"], g[(LW % lstm_i) + "cell/recurrent_kernel"], g[(LW % lstm_i) + "cell/bias"] = dK, dR, dbl
-            if need_input_grad:
-                if tag == "hr":
-                    ops.axpby(full(d_hr_in), full(d_hr_in), 1.0, full(dx), 1.0)
-                else:
-                    ops.axpby(full(d_hr_in), full(d_hr_in), 1.0, View(dx, ch, cl + ch, cl), 1.0)
-        return (g if need_weight_grads else {}), (d_hr_in.view(B, T, S, S, ch) if need_input_grad else None)
+        """dscore [B,1].  Returns (weight grads: FlatVars name -> view of one flat buffer, or {}; d high_res or None)."""
+        from .. import _lib
+        B, T, training, hr_shape = self.dims
+        gflat = ops.zeros(self.h.n_train) if need_weight_grads else None
+        dhr = torch.empty(hr_shape, dtype=torch.float32, device="cuda") if need_input_grad else None
+        sc, sb = self._scratch(B, T)
+        _lib.check(_lib.lib().wdg_critic_backward(self.h.h, ops._p(self.vars.flat), ops._p(self.ctx), B, T, training,
+                                                  ops._p(dscore.contiguous()), ops._p(gflat), ops._p(dhr), ops._p(sc), sb, ops._s()))
+        self.ctx = None
+        return (self.h.grads(gflat) if need_weight_grads else {}), dhr

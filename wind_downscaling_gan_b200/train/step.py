@@ -26,10 +26,13 @@ class TrainState:
     def __init__(self, generator, discriminator, g_opt, d_opt):
         self.generator, self.discriminator = generator, discriminator
         self.g = to_device(generator.get_weights())
-        self.d = to_device(discriminator.get_weights())
+        # critic: ONE flat variable buffer laid out by the wdg_critic handle (trainable variables first), so its Adam
+        # step is one launch and its gradient all-reduce one collective over a contiguous range
+        self.d = discriminator._handle().pack(discriminator.get_weights())
         self.g_opt, self.d_opt = g_opt, d_opt
         self.g_slots = {n: (torch.zeros_like(self.g[n]), torch.zeros_like(self.g[n])) for n in trainable_names(self.g)}
-        self.d_slots = {n: (torch.zeros_like(self.d[n]), torch.zeros_like(self.d[n])) for n in trainable_names(self.d)}
+        nt = self.d.handle.n_train
+        self.d_m, self.d_v = torch.zeros(nt, dtype=torch.float32, device="cuda"), torch.zeros(nt, dtype=torch.float32, device="cuda")
         self.size = generator.image_size
         # device-resident optimizer clocks: [0] generator, [1] critic
         self.steps = torch.tensor([g_opt.iterations, d_opt.iterations], dtype=torch.int32, device="cuda")
@@ -52,6 +55,13 @@ def adam_apply(st, which, weights, slots, grads, opt):
         ops.adam_dev(weights[n], m, v, g, st.lr_t[which:which + 1], opt.beta_1, opt.beta_2, opt.epsilon)
 
 
+def adam_apply_flat(st, which, w_flat, m_flat, v_flat, g_flat, opt):
+    """Same update over a whole model held in one flat buffer: one launch (padding between variables stays 0)."""
+    opt.iterations += 1
+    ops.adam_lr(st.lr_t[which:which + 1], st.steps[which:which + 1], opt.lr, opt.beta_1, opt.beta_2)
+    ops.adam_dev(w_flat[:g_flat.numel()], m_flat, v_flat, g_flat, st.lr_t[which:which + 1], opt.beta_1, opt.beta_2, opt.epsilon)
+
+
 def _mean_sq_into(grads, out):
     """out[0] = mean over tensors of mean(g^2) (ganbase.py:79-81), reduced on the device."""
     per = ops.empty(len(grads))
@@ -62,7 +72,9 @@ def _mean_sq_into(grads, out):
 
 def train_step_device(st, low_res, high_res, noise_generator, n_critic=3, draws=None, gamma=100.0, comm=None,
                       skip_dead_gp=False):
-    """One WGAN step on this rank's share of the batch; returns the metrics as a device tensor (order METRIC_KEYS).
+    """One WGAN step on this rank's share of the batch; returns the metrics as a device tensor (order METRIC_KEYS) and the
+    tensors of the inference-mode recompute (ganbase.py:64-66: generated images, critic scores of real and generated) that
+    the compiled metric objects are updated with (:71-72).
     With a communicator (train/dist.py) the gradients are all-reduced after every backward pass and BatchNorm
     statistics are synchronised, so `world` ranks x local batch reproduce the reference's single process at the global
     batch.
@@ -125,13 +137,12 @@ def train_step_device(st, low_res, high_res, noise_generator, n_critic=3, draws=
         # d_loss = -(mean(real) - mean(fake)) + gradient_reg                          # :44-45, train.py:11-12
         g1, _ = d_real.backward(const(-1.0 / Bg))
         g2, _ = d_fake.backward(const(1.0 / Bg))
-        d_grads = {}
-        for n in g1:
-            ops.axpby(ops.full(g1[n]), ops.full(g1[n]), 1.0, ops.full(g2[n]), 1.0)
-            d_grads[n] = g1[n]
+        f1, f2 = g1.flat.view(-1, 64), g2.flat.view(-1, 64)                           # both backward passes, every variable
+        ops.axpby(ops.full(f1), ops.full(f1), 1.0, ops.full(f2), 1.0)
+        d_grads = g1
         if comm is not None:
             comm.allreduce_grads(d_grads)
-        adam_apply(st, 1, st.d, st.d_slots, d_grads, st.d_opt)                        # :46-47
+        adam_apply_flat(st, 1, st.d.flat, st.d_m, st.d_v, d_grads.flat, st.d_opt)     # :46-47
     # gradient penalty of the LAST critic iteration (:36-37; a constant for the weights): gamma * mean((norm - 1)^2)
     nm1 = ops.empty(B, out_ch)
     ops.axpby(ops.full(nm1), ops.full(norms), 1.0, ops.full(torch.ones_like(norms)), -1.0)
@@ -161,7 +172,7 @@ def train_step_device(st, low_res, high_res, noise_generator, n_critic=3, draws=
         comm.allreduce_sum(M)
         ops.axpby(ops.full(M), ops.full(M), 1.0 / comm.world)
     st.dirty = True
-    return M, fake_m
+    return M, (fake_m, s_real, s_fake)
 
 
 def metrics_dict(M):
@@ -172,9 +183,9 @@ def metrics_dict(M):
 
 
 def train_step(st, low_res, high_res, noise_generator, n_critic=3, draws=None, gamma=100.0, comm=None, skip_dead_gp=False):
-    """Eager form: runs the step and reads the metrics back (one device -> host copy)."""
-    M, _ = train_step_device(st, _dev(low_res), _dev(high_res), noise_generator, n_critic, draws, gamma, comm, skip_dead_gp)
-    return metrics_dict(M)
+    """Eager form: runs the step and reads the metrics back (one device -> host copy).  Returns (dict, recompute tensors)."""
+    M, extras = train_step_device(st, _dev(low_res), _dev(high_res), noise_generator, n_critic, draws, gamma, comm, skip_dead_gp)
+    return metrics_dict(M), extras
 
 
 class GraphedStep:
@@ -198,7 +209,8 @@ class GraphedStep:
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
         with torch.cuda.graph(g):
-            self.M, _ = train_step_device(self.st, self.lr_buf, self.hr_buf, self.ng, self.n_critic, None, comm=self.comm, skip_dead_gp=self.skip_dead_gp)
+            self.M, self.extras = train_step_device(self.st, self.lr_buf, self.hr_buf, self.ng, self.n_critic, None, comm=self.comm,
+                                                    skip_dead_gp=self.skip_dead_gp)
         ops.use_current_stream()
         # capturing does not execute: undo the host mirrors it advanced, replays re-apply them
         self.blocks_per_step = self.ng._offset - off0
@@ -213,8 +225,8 @@ class GraphedStep:
         self.calls += 1
         shape = (tuple(low_res.shape), tuple(high_res.shape))
         if self.failed or self.calls <= self.WARMUP or (self.graph is not None and shape != self.shape):
-            M, _ = train_step_device(self.st, low_res, high_res, self.ng, self.n_critic, None, comm=self.comm, skip_dead_gp=self.skip_dead_gp)
-            return metrics_dict(M)
+            M, extras = train_step_device(self.st, low_res, high_res, self.ng, self.n_critic, None, comm=self.comm, skip_dead_gp=self.skip_dead_gp)
+            return metrics_dict(M), extras
         if self.graph is None:
             try:
                 self._capture(low_res, high_res)
@@ -224,8 +236,8 @@ class GraphedStep:
                 self.failed = True
                 torch.cuda.synchronize()
                 ops.use_current_stream()
-                M, _ = train_step_device(self.st, low_res, high_res, self.ng, self.n_critic, None, comm=self.comm, skip_dead_gp=self.skip_dead_gp)
-                return metrics_dict(M)
+                M, extras = train_step_device(self.st, low_res, high_res, self.ng, self.n_critic, None, comm=self.comm, skip_dead_gp=self.skip_dead_gp)
+                return metrics_dict(M), extras
         self.lr_buf.copy_(low_res, non_blocking=True)
         self.hr_buf.copy_(high_res, non_blocking=True)
         self.graph.replay()
@@ -233,7 +245,7 @@ class GraphedStep:
         self.st.g_opt.iterations += self.iters_per_step[0]
         self.st.d_opt.iterations += self.iters_per_step[1]
         self.st.dirty = True
-        return metrics_dict(self.M)
+        return metrics_dict(self.M), self.extras
 
 
 def test_step(st, x, y, noise_generator, draws=None):
