@@ -254,3 +254,29 @@ def test_error_behaviour(mk):
     after = gen.get_weights()
     assert not np.array_equal(before["layer_with_weights-0/layer/sn_u"], after["layer_with_weights-0/layer/sn_u"])
     assert not np.array_equal(before["layer_with_weights-1/moving_mean"], after["layer_with_weights-1/moving_mean"])
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("B,T,S", [(3, 8, 96), (64, 8, 96), (1, 24, 32)])
+def test_persistent_convlstm_equals_per_step_launches(mk, precision, B, T, S, monkeypatch):
+    """All T ConvLSTM steps run in ONE cooperative launch (step counters in global memory order the recurrent half of step
+    t after every tile of step t-1; the input half overlaps).  Same tiles, same K order, same arithmetic as one launch
+    per step (WDG_NO_LSTM_PERSIST=1): outputs bit-identical, repeatedly (a stale h_{t-1} read would show up as noise)."""
+    import torch
+    from oracle.generator import synthetic_generator_weights
+    w = synthetic_generator_weights(2)
+    image, noise = inputs(B, T, S, 21)
+    image, noise = torch.from_numpy(image).cuda(), torch.from_numpy(noise).cuda()
+    gen = mk(S, 3, 20, 2, T)
+    gen.set_weights(w)
+    gen.set_precision(precision)
+    outs = [gen.forward_device(image, noise).clone() for _ in range(3)]
+    assert gen.launches_per_forward() == 10
+    monkeypatch.setenv("WDG_NO_LSTM_PERSIST", "1")
+    ref_gen = mk(S, 3, 20, 2, T)
+    ref_gen.set_weights(w)
+    ref_gen.set_precision(precision)
+    ref = ref_gen.forward_device(image, noise)
+    assert ref_gen.launches_per_forward() == 9 + T
+    for o in outs:
+        assert torch.equal(o, ref)

@@ -55,8 +55,13 @@ struct EpiParams {
   void* h_out;                       // act_t, pixel (n,y,x) channel c at n*h_sn + h_off + (y*h_pitch+x)*F + c
   long long h_sn, h_off;
   int h_pitch;                       // pixels per row of the (zero-ring padded) h image
-  int first_step;                    // c_{t-1} = 0: skip the state read
   int F;
+  long long h_step;                  // elements between consecutive timesteps of the h image sequence
+  // Persistent time loop (ConvParams::t_begin .. t_end in ONE launch): every (tile, epilogue warp) that has stored its
+  // part of h_t adds 1 to sync_flags[t]; the TMA producer waits for sync_total arrivals on sync_flags[t-1] before it
+  // fetches the first h_{t-1} operand of step t.  NULL: one step per launch (the kernel boundary orders the steps).
+  unsigned long long* sync_flags;
+  unsigned int sync_total;
   // ---- EPI_LSTM16_FWD / EPI_LSTM16_BWD: one recurrent step of the critic's 16-filter ConvLSTM2D in the TRAINING
   //      path (fp32 tensors, pixel-major [n][H][W][C]; train_lstm16.cu).  FWD (BN = 64 = [i|f|c~|o] x 16): acc =
   //      recurrent conv of h_{t-1}; t_gates holds the input conv + bias of this step and receives the activated gates;
@@ -77,6 +82,8 @@ struct ConvParams {
   int tiles_x, tiles_y, tiles_n;
   int n_tiles_N;               // number of BN-wide column tiles
   int num_kb;
+  int num_kb_first;            // EPI_LSTM: K-blocks of step t = 0 (h_0 = 0: input half only)
+  int t_begin, t_end;          // EPI_LSTM: timesteps run by this launch; KBlock::o3 is relative to t (x_t: 0, h_{t-1}: -1)
   int n_coord;                 // TMA coordinate (3 or 4) that carries the image index
   int ntile_coord;             // TMA coordinate that additionally receives the N-tile index (-1: none)
   EpiParams ep;
@@ -136,6 +143,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int t_begin = (EPI == EPI_LSTM) ? p.t_begin : 0, t_end = (EPI == EPI_LSTM) ? p.t_end : 1;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   const int total_tiles = m_tiles * p.n_tiles_N;
 
@@ -167,30 +175,43 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // ===================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles_N;
-      const int m_tile = tile / p.n_tiles_N;
-      const int tx = m_tile % p.tiles_x;
-      const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-      const int tn = m_tile / (p.tiles_x * p.tiles_y);
-      const int n0 = tn * p.tile_n;
-      const int b0 = 0 + (p.ntile_coord == 0 ? n_tile : 0);
-      const int b1 = tx * p.tile_w + (p.ntile_coord == 1 ? n_tile : 0);
-      const int b2 = ty * p.tile_h + (p.ntile_coord == 2 ? n_tile : 0);
-      const int b3 = (p.n_coord == 3 ? n0 : 0) + (p.ntile_coord == 3 ? n_tile : 0);
-      const int b4 = (p.n_coord == 4 ? n0 : 0);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const KBlock k = p.kb[kb];
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (elect_one()) {
-          const uint32_t a_bytes = k.half ? (A_STAGE_BYTES / 2) : A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], a_bytes + Cfg::B_STAGE_BYTES);
-          const CUtensorMap* tm = (k.src == 0) ? &tmA0 : ((k.src == 1) ? &tmA1 : &tmA2);
-          tma_load_5d(smA + stage * A_STAGE_BYTES, tm, &full_bar[stage], b0 + k.o0, b1 + k.o1, b2 + k.o2, b3 + k.o3, b4);
-          tma_load_2d(smB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * P::KB_ELEMS, n_tile * BN);
+    for (int t = t_begin; t < t_end; ++t) {
+      const int nkb = (EPI == EPI_LSTM && t == 0) ? p.num_kb_first : p.num_kb;
+      // the input half of step t (x_t) does not depend on step t-1: it is fetched, and multiplied, while other CTAs
+      // still finish step t-1; only the first h_{t-1} operand waits for every tile of that step
+      bool h_ready = (EPI != EPI_LSTM) || p.ep.sync_flags == nullptr || t == t_begin;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles_N;
+        const int m_tile = tile / p.n_tiles_N;
+        const int tx = m_tile % p.tiles_x;
+        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+        const int tn = m_tile / (p.tiles_x * p.tiles_y);
+        const int n0 = tn * p.tile_n;
+        const int b0 = 0 + (p.ntile_coord == 0 ? n_tile : 0);
+        const int b1 = tx * p.tile_w + (p.ntile_coord == 1 ? n_tile : 0);
+        const int b2 = ty * p.tile_h + (p.ntile_coord == 2 ? n_tile : 0);
+        const int b3 = (p.n_coord == 3 ? n0 : 0) + (p.ntile_coord == 3 ? n_tile : 0) + (EPI == EPI_LSTM ? t : 0);
+        const int b4 = (p.n_coord == 4 ? n0 : 0);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const KBlock k = p.kb[kb];
+          if constexpr (EPI == EPI_LSTM) {
+            if (!h_ready && k.src == 1) {
+              flag_wait(p.ep.sync_flags + (t - 1), p.ep.sync_total);
+              fence_proxy_async_global();      // h_{t-1} was written through the generic proxy, TMA reads it through the async one
+              h_ready = true;
+            }
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
+            const uint32_t a_bytes = k.half ? (A_STAGE_BYTES / 2) : A_STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], a_bytes + Cfg::B_STAGE_BYTES);
+            const CUtensorMap* tm = (k.src == 0) ? &tmA0 : ((k.src == 1) ? &tmA1 : &tmA2);
+            tma_load_5d(smA + stage * A_STAGE_BYTES, tm, &full_bar[stage], b0 + k.o0, b1 + k.o1, b2 + k.o2, b3 + k.o3, b4);
+            tma_load_2d(smB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * P::KB_ELEMS, n_tile * BN);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -200,11 +221,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+    const int nkb = (EPI == EPI_LSTM && t == 0) ? p.num_kb_first : p.num_kb;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      for (int kb = 0; kb < nkb; ++kb) {
         const int half = p.kb[kb].half;
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -219,12 +242,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             P::mma(d_tmem, da + 6, db + 6, idesc, 1u);
           }
           umma_commit(&empty_bar[stage]);                        // frees the smem slot once these MMAs have read it
-          if (kb == p.num_kb - 1) umma_commit(&tfull_bar[as]);   // accumulator complete -> epilogue
+          if (kb == nkb - 1) umma_commit(&tfull_bar[as]);        // accumulator complete -> epilogue
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
+    }
     }
   } else {
     // ===================================================== epilogue (warps 2..5)
@@ -235,6 +259,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int ln = row / (p.tile_w * p.tile_h);
     int as = 0;
     uint32_t aphase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles_N;
       const int m_tile = tile / p.n_tiles_N;
@@ -431,14 +456,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const float* bias = sm_bias + n_tile * 256 + s * 16;
             float* cptr = e.c_state + pix * e.F + ch0;
             float cprev[16];
-            if (e.first_step) {
+            if (t == 0) {                      // c_{-1} = 0: skip the state read
 #pragma unroll
               for (int i = 0; i < 16; ++i) cprev[i] = 0.f;
             } else {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float4 t = reinterpret_cast<const float4*>(cptr)[i];
-                cprev[4 * i] = t.x; cprev[4 * i + 1] = t.y; cprev[4 * i + 2] = t.z; cprev[4 * i + 3] = t.w;
+                const float4 cv = reinterpret_cast<const float4*>(cptr)[i];
+                cprev[4 * i] = cv.x; cprev[4 * i + 1] = cv.y; cprev[4 * i + 2] = cv.z; cprev[4 * i + 3] = cv.w;
               }
             }
             float cn[16], hn[16];
@@ -454,14 +479,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               reinterpret_cast<float4*>(cptr)[i] = make_float4(cn[4 * i], cn[4 * i + 1], cn[4 * i + 2], cn[4 * i + 3]);
-            P::store16(reinterpret_cast<act_t*>(e.h_out) + (long long)n * e.h_sn + e.h_off + ((long long)y * e.h_pitch + x) * e.F + ch0, hn);
+            P::store16(reinterpret_cast<act_t*>(e.h_out) + (long long)n * e.h_sn + e.h_off + t * e.h_step +
+                           ((long long)y * e.h_pitch + x) * e.F + ch0, hn);
           }
+        }
+        if (e.sync_flags != nullptr && t + 1 < t_end) {      // publish this warp's part of h_t to the other CTAs' TMA loads
+          __threadfence();
+          fence_proxy_async_global();
+          __syncwarp();
+          if (lane == 0) flag_arrive(e.sync_flags + t);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
+    }
     }
   }
 

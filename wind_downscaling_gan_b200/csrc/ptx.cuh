@@ -59,6 +59,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ------------------------------------------------- grid-wide step flags (persistent kernels: global-memory counters)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void flag_arrive(unsigned long long* flag) {
+  asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(flag) : "memory");
+}
+// Every lane of the calling warp polls (one broadcast transaction per round) until `flag` has reached `target`.
+// Bounded: a protocol bug (or CTAs that are not co-resident) traps instead of hanging the GPU box.
+__device__ __forceinline__ void flag_wait(const unsigned long long* flag, unsigned long long target) {
+  uint32_t spins = 0;
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= target) break;
+    __nanosleep(32);
+    if (++spins > (1u << 24)) {
+      printf("wdg: step flag wait timed out (block %d, have %llu of %llu)\n", (int)blockIdx.x, v, target);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

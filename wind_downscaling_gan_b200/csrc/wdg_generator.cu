@@ -14,6 +14,7 @@
 
 #include "../../include/wdg.h"
 #include "conv_umma.cuh"
+#include "conv_umma2.cuh"
 #include "halo_conv.cuh"
 #include "stencil_kernels.cuh"
 
@@ -116,7 +117,15 @@ struct Plan {
   uint8_t *xpad, *res4, *hseq, *g5, *catp, *edgeE, *g9;   // act_t buffers (bf16 or tf32-in-fp32), addressed in bytes
   float *cstate, *deltaD;
   ConvLaunch L0, L2, L5, L7, LE, L9;
-  std::vector<ConvLaunch> LS;  // one per timestep
+  std::vector<ConvLaunch> LS;  // ConvLSTM, one launch per timestep (fallback)
+  ConvLaunch LSP;              // ConvLSTM, all timesteps in ONE persistent cooperative launch (conv_umma.cuh: sync_flags)
+  bool lstm_persist = false;
+  unsigned long long* lstm_flags = nullptr;   // [T] step counters in the workspace
+  // the same launch on CTA pairs (conv_umma2.cuh: tcgen05.mma.cta_group::2, B tile split over the two SMs of a TPC)
+  bool lstm_pair = false;
+  CUtensorMap tmB_half;        // B boxes of 128 weight rows
+  ConvParams pair_p;
+  int pair_grid = 0;
   bool use_halo = false;       // halo-reuse kernels (halo_conv.cuh) for the 8x8 s2 conv and the fused upsample conv
   CUtensorMap hA, hB, h0A, h0B, h11A, h11B, h5A, h5B;
   HaloParams hp, h0p, h11p, h5p;
@@ -487,7 +496,7 @@ extern "C" int wdg_generator_finalize(wdg_generator* g) {
 
 // ------------------------------------------------------------- workspace
 struct WsLayout {
-  size_t xpad, res4, hseq, cstate, g5, catp, edgeE, deltaD, g9, total;
+  size_t xpad, res4, hseq, cstate, g5, catp, edgeE, deltaD, g9, flags, total;
 };
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
@@ -504,6 +513,7 @@ static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
   L.edgeE = take(N * 4 * (S + 8) * (F / 4 + 128) * E);
   L.deltaD = take(N * S * 192 * 4);
   L.g9 = take(N * (S + 2) * (S + 8) * (F / 8) * E);   // zero ring: 1 row above/below, one 4-pixel super-pixel left/right
+  L.flags = take((size_t)T * sizeof(unsigned long long));   // step counters of the persistent ConvLSTM launch
   L.total = o;
   return L;
 }
@@ -557,12 +567,55 @@ static void affine_epi(EpiParams& e, const float* bias, const float* sc, const f
   e.out_mul = 1; e.group_cols = 1 << 30; e.lrelu = lrelu; e.out_f32 = 0;
 }
 
+// ---- CTA-pair ConvLSTM launch (conv_umma2.cuh): clusters of 2, cooperative (the step flags need every CTA resident)
+template <int PREC>
+static int lstm_pair_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attrs, int grid, cudaStream_t stream) {
+  auto kern = lstm_pair_kernel<PREC>;
+  static bool done[64] = {};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !done[dev]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::SMEM_BYTES));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+  }
+  std::memset(cfg, 0, sizeof *cfg);
+  cfg->gridDim = dim3(grid);
+  cfg->blockDim = dim3(192);
+  cfg->dynamicSmemBytes = PairCfg::SMEM_BYTES;
+  cfg->stream = stream;
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative;
+  attrs[1].val.cooperative = 1;
+  cfg->attrs = attrs;
+  cfg->numAttrs = 2;
+  return 0;
+}
+static int lstm_pair_max_clusters(const wdg_generator* g, int* n) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attrs[2];
+  *n = 0;
+  if (g->prec == PREC_TF32) {
+    if (lstm_pair_config<PREC_TF32>(&cfg, attrs, 2 * g->sm_count, nullptr)) return 1;
+    cfg.numAttrs = 1;       // the occupancy query takes the cluster shape only
+    CK(cudaOccupancyMaxActiveClusters(n, lstm_pair_kernel<PREC_TF32>, &cfg));
+  } else {
+    if (lstm_pair_config<PREC_BF16>(&cfg, attrs, 2 * g->sm_count, nullptr)) return 1;
+    cfg.numAttrs = 1;
+    CK(cudaOccupancyMaxActiveClusters(n, lstm_pair_kernel<PREC_BF16>, &cfg));
+  }
+  return 0;
+}
+template <int PREC>
+static int launch_lstm_pair(const Plan& pl, cudaStream_t stream);
+
 static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
   const WsLayout L = ws_layout(g, B, T);
   pl.xpad = ws + L.xpad;
   pl.res4 = ws + L.res4; pl.hseq = ws + L.hseq;
   pl.cstate = (float*)(ws + L.cstate); pl.g5 = ws + L.g5; pl.catp = ws + L.catp;
   pl.edgeE = ws + L.edgeE; pl.deltaD = (float*)(ws + L.deltaD); pl.g9 = ws + L.g9;
+  pl.lstm_flags = (unsigned long long*)(ws + L.flags);
   const uint64_t N = (uint64_t)B * T, S = g->S, S2 = S / 2, S4 = S / 4, F = g->F, CP = g->CP;
   const int esz = g->esz();
   const uint32_t kbe = (uint32_t)g->kbe();       // elements per K-block
@@ -676,20 +729,47 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       std::memset(&c.p, 0, sizeof c.p);
       c.tmA[0] = tmX; c.tmA[1] = tmH; c.tmA[2] = tmX; c.tmB = tmB;
       set_tiles(c.p, (int)S4, (int)S4, B, 8, 8, 2, (int)(4 * F / 256), 4);
-      c.p.num_kb = t == 0 ? nk : 2 * nk;
+      // K axis: input half (x_t: time offset 0) then recurrent half (h_{t-1}: time offset -1); step 0 runs the first only
+      c.p.num_kb = 2 * nk; c.p.num_kb_first = nk;
+      c.p.t_begin = t; c.p.t_end = t + 1;
       for (int kb = 0; kb < c.p.num_kb; ++kb) {
         KBlock& k = c.p.kb[kb];
         const int kk = kb % nk, tap = kk / cpk;
         k.src = kb < nk ? 0 : 1; k.half = 0;
         k.o0 = (int16_t)((kk % cpk) * kbe); k.o1 = (int16_t)(tap % 3 - 1); k.o2 = (int16_t)(tap / 3 - 1);
-        k.o3 = (int16_t)(kb < nk ? t : t - 1);
+        k.o3 = (int16_t)(kb < nk ? 0 : -1);
       }
       EpiParams& e = c.p.ep;
       std::memset(&e, 0, sizeof e);
       e.bias = g->biasL; e.c_state = pl.cstate; e.h_out = at(pl.hseq, (SP + 1) * F);
-      e.h_sn = (long long)T * SP * SP * F; e.h_off = (long long)t * SP * SP * F; e.h_pitch = (int)SP;
-      e.first_step = t == 0; e.F = (int)F;
+      e.h_sn = (long long)T * SP * SP * F; e.h_off = 0; e.h_step = (long long)SP * SP * F; e.h_pitch = (int)SP;
+      e.F = (int)F;
       c.bn = 256; c.epi = EPI_LSTM; c.grid = grid_for(c.p);
+    }
+    // All T steps in one cooperative launch: no launch / prologue / drain between steps, and the input half of step
+    // t+1 overlaps the tail of step t (north_star: the recurrence stays inside one resident kernel).
+    pl.LSP = pl.LS[0];
+    pl.LSP.p.t_begin = 0; pl.LSP.p.t_end = T;
+    pl.LSP.p.ep.sync_flags = pl.lstm_flags;
+    pl.LSP.p.ep.sync_total = 4u * (unsigned)(pl.LSP.p.tiles_x * pl.LSP.p.tiles_y * pl.LSP.p.tiles_n * pl.LSP.p.n_tiles_N);
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, g->device);
+    pl.lstm_persist = T > 1 && coop && pl.LSP.grid <= sms && !getenv("WDG_NO_LSTM_PERSIST");
+    // CTA-pair form of the same launch (WDG_LSTM_PAIR=0 keeps the single-CTA kernel)
+    static const int pair_env = getenv("WDG_LSTM_PAIR") ? atoi(getenv("WDG_LSTM_PAIR")) : 1;
+    pl.lstm_pair = false;
+    if (pl.lstm_persist && pair_env) {
+      uint32_t bb2[2] = {kbe, 128};
+      if (tmap(&pl.tmB_half, g->BL, 2, bd, bs, bb2)) return 1;
+      pl.pair_p = pl.LSP.p;
+      const int m_tiles = pl.pair_p.tiles_x * pl.pair_p.tiles_y * pl.pair_p.tiles_n;
+      const int pair_tiles = ((m_tiles + 1) / 2) * pl.pair_p.n_tiles_N;
+      int max_clusters = 0;
+      if (lstm_pair_max_clusters(g, &max_clusters)) return 1;
+      const int pairs = pair_tiles < max_clusters ? pair_tiles : max_clusters;
+      pl.pair_grid = 2 * pairs;
+      pl.pair_p.ep.sync_total = 8u * (unsigned)pair_tiles;
+      pl.lstm_pair = pairs > 0;
     }
   }
   // ---------------- L5: 3x3 same 128 -> 64 on hseq (c, x, y, n)
@@ -878,7 +958,7 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
     }
   }
   pl.B = B; pl.T = T;
-  pl.launches = 1 + 2 + T + 2 + 2 + 1 + 1;
+  pl.launches = 1 + 2 + (pl.lstm_persist ? 1 : T) + 2 + 2 + 1 + 1;   // kernels (the step-counter memset of the persistent ConvLSTM is not one)
   return 0;
 }
 
@@ -937,6 +1017,24 @@ static int launch_conv_t(const ConvLaunch& c, int device, cudaStream_t stream) {
   CK(cudaGetLastError());
   return 0;
 }
+// Cooperative launch: every CTA of the grid is resident at once (the persistent ConvLSTM's CTAs wait for each other).
+template <int BN, int EPI, int PREC>
+static int launch_conv_coop(const ConvLaunch& c, int device, cudaStream_t stream) {
+  auto kern = conv_umma_kernel<BN, EPI, PREC, 0>;
+  using Cfg = ConvCfg<BN, 0>;
+  ENSURE_SMEM(kern, device, Cfg::SMEM_BYTES);
+  void* args[5] = {(void*)&c.tmA[0], (void*)&c.tmA[1], (void*)&c.tmA[2], (void*)&c.tmB, (void*)&c.p};
+  CK(cudaLaunchCooperativeKernel((const void*)kern, dim3(c.grid), dim3(192), args, Cfg::SMEM_BYTES, stream));
+  return 0;
+}
+template <int PREC>
+static int launch_lstm_pair(const Plan& pl, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attrs[2];
+  if (lstm_pair_config<PREC>(&cfg, attrs, pl.pair_grid, stream)) return 1;
+  CK(cudaLaunchKernelEx(&cfg, lstm_pair_kernel<PREC>, pl.LSP.tmA[0], pl.LSP.tmA[1], pl.tmB_half, pl.pair_p));
+  return 0;
+}
 template <int PREC>
 static int launch_conv(const ConvLaunch& c, int device, cudaStream_t stream) {
   if (c.epi == EPI_LSTM) return launch_conv_t<256, EPI_LSTM, PREC>(c, device, stream);
@@ -988,8 +1086,15 @@ static int run_plan_t(wdg_generator* g, const Plan& pl, const float* image_dev, 
   mark();
   if (launch_conv<PREC>(pl.L2, dev, stream)) return 1;
   mark();
-  for (int t = 0; t < pl.T; ++t)
-    if (launch_conv<PREC>(pl.LS[t], dev, stream)) return 1;
+  if (pl.lstm_persist) {
+    CK(cudaMemsetAsync(pl.lstm_flags, 0, (size_t)pl.T * sizeof(unsigned long long), stream));
+    if (pl.lstm_pair) {
+      if (launch_lstm_pair<PREC>(pl, stream)) return 1;
+    } else if (launch_conv_coop<256, EPI_LSTM, PREC>(pl.LSP, dev, stream)) return 1;
+  } else {
+    for (int t = 0; t < pl.T; ++t)
+      if (launch_conv<PREC>(pl.LS[t], dev, stream)) return 1;
+  }
   mark();
   if (pl.use_halo5) {
     if (launch_halo<64, NC128, 9, 3, HEPI_AFFINE, PREC>(pl.h5A, pl.h5B, pl.h5p, pl.h5grid, dev, stream)) return 1;
