@@ -249,6 +249,9 @@ class Dist:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
         torch.cuda.set_device(self.local_rank)
+        # page-locked host buffers of the e2e legs are first touched on the NUMA node of this rank's GPU
+        from wind_downscaling_gan_b200.hostmem import bind_to_gpu_numa_node
+        self.numa = bind_to_gpu_numa_node(self.local_rank) if os.environ.get("WDG_BIND_NUMA", "1") != "0" else None
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
@@ -407,7 +410,7 @@ def run_inference(args):
                            "tolerance": tol[args.precision]},
                 "e2e": main["e2e"], "e2e_host_noise": main["e2e_host_noise"],
                 "gpu_launches": gen.launches_per_forward() * args.steps,
-                "clocks": main["clocks"], "roofline": inference_roofline(main, peaks, D.world),
+                "clocks": main["clocks"], "host_numa": D.numa, "roofline": inference_roofline(main, peaks, D.world),
                 other: {"dtype": other, "value": side["value"], "ms_per_step": side["ms_per_step"], "e2e": side["e2e"],
                         "e2e_host_noise": side["e2e_host_noise"], "tolerance": tol[other], "clocks": side["clocks"],
                         "roofline": {k: side_roof[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "peak_source", "whole_forward")},

@@ -56,6 +56,8 @@ def main():
     from wind_downscaling_gan_b200 import api, engine
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    from wind_downscaling_gan_b200.hostmem import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(torch.cuda.current_device())      # page-locked result buffers on the GPU's own NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
@@ -119,6 +121,7 @@ def main():
                             "note": "generator forward alone (noise drawn in-kernel) on the resident batch of this run"},
             "api_over_kernel": value / (world * kernel_rate),
             "d2h_bytes_total": int(np.prod(eng.out_shape)) * 4 * units,
+            "host_numa": numa,
             "path": "engine.downscale_series: resident coarse inputs -> device regrid+gather/normalise per window -> generator "
                     "(in-kernel noise) -> device stitch -> page-locked host maps (copy stream, overlapped)",
             "timing": "wall clock around engine.run() on every rank, max over ranks"}), flush=True)

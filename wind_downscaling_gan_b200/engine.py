@@ -201,12 +201,18 @@ def downscaler_from_era5(era5, raster_topo, network, range_lon=None, range_lat=N
 
 
 def downscale_series(era5, raster_topo, range_lon=None, range_lat=None, overlap_factor=0.05, network=None, members=1,
-                     rank=0, world=1, high_res_template=None, windows_per_forward=None):
+                     rank=0, world=1, high_res_template=None, windows_per_forward=None, bind_numa=None):
     """`downscale()` once per 24-hour window of `era5` (and `members` noise draws per window), back to back on this GPU.
     With world > 1 (one process per GPU) the windows -- or, for a single window, the members -- are split contiguously
     over the ranks and this call computes rank's share.  Returns (engine, units, result) where `units` lists the
-    (window, member range) this rank computed and `result` is engine.run()'s page-locked tensor."""
+    (window, member range) this rank computed and `result` is engine.run()'s page-locked tensor.  bind_numa (default: on
+    when world > 1): restrict the process to the CPUs of its GPU's NUMA node first, so the page-locked result buffers of
+    the ranks are spread over the sockets instead of piling onto one (hostmem.py)."""
     from . import api
+    if bind_numa if bind_numa is not None else world > 1:
+        import torch
+        from .hostmem import bind_to_gpu_numa_node
+        bind_to_gpu_numa_node(torch.cuda.current_device())
     network = network if network is not None else api.get_network()
     eng = downscaler_from_era5(era5, raster_topo, network, range_lon, range_lat, overlap_factor, high_res_template,
                                windows_per_forward)
