@@ -16,8 +16,16 @@
 //
 // Positions whose window crosses an image row/edge compute garbage and are masked by the epilogue.
 // Warp roles: 0 = A producer, 1 = MMA issuer (+TMEM alloc), 2-5 = epilogue, 6 = B producer.
+//
+// PAIR = true: two CTAs on the two SMs of a TPC (cluster of 2) work on two consecutive passes with ONE
+// tcgen05.mma.cta_group::2 per (tile, tap, K slice) (M = 256: tile t of both passes).  CTA rank r loads the A chunk of
+// pass 2*pp + r and rows [r*BN/2, (r+1)*BN/2) of every weight block; each SM's tensor core reads its own A and both B
+// halves, each half served by one SM's shared memory for both.  N = 128 MMAs read 8 KB of operands per 64 cycles in
+// the single-CTA form -- the whole 128 B/clk port, before any TMA write -- and 6 KB in pair form.  Barrier protocol as in
+// conv_umma2.cuh (loads complete on the leader's barriers, commits are multicast, remote tempty arrives).
 #pragma once
 #include "conv_umma.cuh"
+#include "conv_umma2.cuh"
 
 namespace wdg {
 
@@ -70,11 +78,13 @@ struct HaloCfg {
   static_assert(2 * H_TILES * BN <= 512, "accumulators exceed TMEM");
 };
 
-template <int BN, int NCHUNK, int NTAP, int TPS, int EPI, int PREC>
+template <int BN, int NCHUNK, int NTAP, int TPS, int EPI, int PREC, bool PAIR = false>
 __global__ void __launch_bounds__(224, 1)
 halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ HaloParams p) {
-  using Cfg = HaloCfg<BN, NCHUNK, TPS>;
+  using Cfg = HaloCfg<PAIR ? BN / 2 : BN, NCHUNK, TPS>;     // PAIR: this CTA's half of every weight block
+  constexpr int BROWS = PAIR ? BN / 2 : BN;                 // weight rows per tap in this CTA's shared memory
+  static_assert(!PAIR || (BN % 32 == 0), "pair form: each half of B must be whole 16-row groups");
   using P = Prec<PREC>;
   using act_t = typename P::act_t;
   constexpr int BSTAGES = Cfg::BSTAGES;
@@ -101,18 +111,29 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int TMEM_COLS = (2 * H_TILES * BN <= 256) ? 256 : 512;     // the pair's accumulators span the full BN columns
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  // work items: passes (single CTA) or pairs of consecutive passes (PAIR); this CTA's pass of item i is first + i*step
+  const int n_items = PAIR ? (p.num_passes + 1) / 2 : p.num_passes;
+  const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto pass_of = [&](int item) { return PAIR ? 2 * item + (int)rank : item; };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int i = 0; i < H_ABUFS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < BSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], PAIR ? 8 : 4); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc2<TMEM_COLS>(tmem_slot);
+    else tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -121,14 +142,21 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ================================================= A producer: ring over (pass, chunk)
     int ab = 0;
     uint32_t phase = 0;
-    for (int pass = blockIdx.x; pass < p.num_passes; pass += gridDim.x) {
-      const int f0 = pass * (H_TILES * TILE_M);
+    for (int item = item0; item < n_items; item += item_step) {
+      const int f0 = pass_of(item) * (H_TILES * TILE_M);       // beyond the last pass (odd count, PAIR): TMA zero-fills
       for (int c = 0; c < NCHUNK; ++c) {
         mbar_wait(&a_empty[ab], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&a_full[ab], 2 * p.box_rows * 128);
-          tma_load_2d(smA + ab * H_A_BYTES, &tmA, &a_full[ab], c * P::KB_ELEMS, f0);
-          tma_load_2d(smA + ab * H_A_BYTES + p.box_rows * 128, &tmA, &a_full[ab], c * P::KB_ELEMS, f0 + p.box_rows);
+          if constexpr (PAIR) {
+            const uint32_t bar0 = mapa_u32(smem_u32(&a_full[ab]), 0);
+            if (leader) mbar_arrive_expect_tx(&a_full[ab], 2 * 2 * p.box_rows * 128);     // both CTAs' boxes
+            tma2_load_2d(smA + ab * H_A_BYTES, &tmA, bar0, c * P::KB_ELEMS, f0);
+            tma2_load_2d(smA + ab * H_A_BYTES + p.box_rows * 128, &tmA, bar0, c * P::KB_ELEMS, f0 + p.box_rows);
+          } else {
+            mbar_arrive_expect_tx(&a_full[ab], 2 * p.box_rows * 128);
+            tma_load_2d(smA + ab * H_A_BYTES, &tmA, &a_full[ab], c * P::KB_ELEMS, f0);
+            tma_load_2d(smA + ab * H_A_BYTES + p.box_rows * 128, &tmA, &a_full[ab], c * P::KB_ELEMS, f0 + p.box_rows);
+          }
         }
         __syncwarp();
         if (++ab == H_ABUFS) { ab = 0; phase ^= 1; }
@@ -138,14 +166,22 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ================================================= B producer: ring over (pass, stage of TPS K-blocks)
     int stage = 0;
     uint32_t phase = 0;
-    for (int pass = blockIdx.x; pass < p.num_passes; pass += gridDim.x) {
+    for (int item = item0; item < n_items; item += item_step) {
       for (int g = 0; g < NCHUNK * NTAP / TPS; ++g) {
         mbar_wait(&b_empty[stage], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&b_full[stage], Cfg::B_STAGE_BYTES);
+          if constexpr (PAIR) {
+            const uint32_t bar0 = mapa_u32(smem_u32(&b_full[stage]), 0);
+            if (leader) mbar_arrive_expect_tx(&b_full[stage], 2 * Cfg::B_STAGE_BYTES);    // both halves
 #pragma unroll
-          for (int j = 0; j < TPS; ++j)
-            tma_load_2d(smB + stage * Cfg::B_STAGE_BYTES + j * BN * 128, &tmB, &b_full[stage], (g * TPS + j) * P::KB_ELEMS, 0);
+            for (int j = 0; j < TPS; ++j)
+              tma2_load_2d(smB + stage * Cfg::B_STAGE_BYTES + j * BROWS * 128, &tmB, bar0, (g * TPS + j) * P::KB_ELEMS, (int)rank * BROWS);
+          } else {
+            mbar_arrive_expect_tx(&b_full[stage], Cfg::B_STAGE_BYTES);
+#pragma unroll
+            for (int j = 0; j < TPS; ++j)
+              tma_load_2d(smB + stage * Cfg::B_STAGE_BYTES + j * BN * 128, &tmB, &b_full[stage], (g * TPS + j) * P::KB_ELEMS, 0);
+          }
         }
         __syncwarp();
         if (++stage == BSTAGES) { stage = 0; phase ^= 1; }
@@ -153,11 +189,11 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ================================================= MMA issuer
-    constexpr uint32_t idesc = P::idesc(TILE_M, BN);
+    constexpr uint32_t idesc = P::idesc(PAIR ? 2 * TILE_M : TILE_M, BN);
     int stage = 0, ab = 0;
     uint32_t bphase = 0, aphase = 0, tphase = 0;
     int as = 0;
-    for (int pass = blockIdx.x; pass < p.num_passes; pass += gridDim.x) {
+    for (int item = item0; item < n_items && leader; item += item_step) {      // PAIR: the leader issues for both CTAs
       mbar_wait(&tempty[as], tphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * (H_TILES * BN);
@@ -176,19 +212,31 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint32_t shift_rows = (uint32_t)p.tap_shift[tap];
               const uint32_t kmask = p.kmask[tap];
               const int first_k = __ffs((int)kmask) - 1;     // the first MMA of a tile overwrites the accumulator
-              const uint64_t db = b_desc0 + (uint64_t)(j * BN * 8);                          // BN rows * 128 B >> 4
+              const uint64_t db = b_desc0 + (uint64_t)(j * BROWS * 8);                       // rows * 128 B >> 4
 #pragma unroll
               for (int t = 0; t < H_TILES; ++t) {
                 const uint64_t da = a_desc0 + (uint64_t)((t * TILE_M + shift_rows) * 8);     // rows * 128 B >> 4
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  if (kmask & (1u << k)) P::mma(d_tmem + t * BN, da + 2 * k, db + 2 * k, idesc, (c | tap) ? 1u : (k != first_k ? 1u : 0u));
+                  if (kmask & (1u << k)) {
+                    const uint32_t acc = (c | tap) ? 1u : (k != first_k ? 1u : 0u);
+                    if constexpr (PAIR) umma2<PREC>(d_tmem + t * BN, da + 2 * k, db + 2 * k, idesc, acc);
+                    else P::mma(d_tmem + t * BN, da + 2 * k, db + 2 * k, idesc, acc);
+                  }
               }
             }
-            umma_commit(&b_empty[stage]);
-            if (g == NTAP / TPS - 1) {
-              umma_commit(&a_empty[ab]);
-              if (c == NCHUNK - 1) umma_commit(&tfull[as]);
+            if constexpr (PAIR) {
+              umma2_commit_both(&b_empty[stage]);
+              if (g == NTAP / TPS - 1) {
+                umma2_commit_both(&a_empty[ab]);
+                if (c == NCHUNK - 1) umma2_commit_both(&tfull[as]);
+              }
+            } else {
+              umma_commit(&b_empty[stage]);
+              if (g == NTAP / TPS - 1) {
+                umma_commit(&a_empty[ab]);
+                if (c == NCHUNK - 1) umma_commit(&tfull[as]);
+              }
             }
           }
           __syncwarp();
@@ -205,7 +253,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int per_img = p.pw * p.ph;
     int as = 0;
     uint32_t tphase = 0;
-    for (int pass = blockIdx.x; pass < p.num_passes; pass += gridDim.x) {
+    for (int item = item0; item < n_items; item += item_step) {
+      const int pass = pass_of(item);
       mbar_wait(&tfull[as], tphase);
       tc_fence_after();
 #pragma unroll 1
@@ -295,16 +344,21 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));     // the leader's barrier
+        else mbar_arrive(&tempty[as]);
+      }
       if (++as == 2) { as = 0; tphase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();      // neither CTA leaves (or frees TMEM) while the other may still address it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc2<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 

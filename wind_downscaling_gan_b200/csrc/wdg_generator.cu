@@ -130,6 +130,10 @@ struct Plan {
   CUtensorMap hA, hB, h0A, h0B, h11A, h11B, h5A, h5B;
   HaloParams hp, h0p, h11p, h5p;
   int hgrid = 0, h0grid = 0, h11grid = 0, h5grid = 0;
+  // CTA-pair form (halo_conv.cuh PAIR) of the two big halo kernels: B boxes of BN/2 rows, clusters of 2
+  bool halo_pair = false;
+  CUtensorMap hB_half, h0B_half;
+  int hgrid_pair = 0, h0grid_pair = 0;
   bool use_halo11 = false;     // final 3x3 conv on the tensor cores (super-pixel form)
   bool use_halo5 = false;      // 3x3 conv on the (zero-ring padded) hidden-state sequence with halo reuse
   int launches = 0;
@@ -676,6 +680,10 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       h.out1 = at(pl.catp, (2 * PW + 2) * ci + F / 4); h.o1_sn = PW * PW * ci; h.o1_sy = PW * ci; h.o1_sx = ci;
       h.out2 = nullptr;
       pl.h0grid = h.num_passes < sms ? h.num_passes : sms;
+      uint32_t bbh[2] = {kbe, 64};
+      if (tmap(&pl.h0B_half, g->B0, 2, bd, bs, bbh)) return 1;
+      const int pairs = (h.num_passes + 1) / 2;
+      pl.h0grid_pair = 2 * (pairs < sms / 2 ? pairs : sms / 2);
     }
     pl.use_halo = fits;
   }
@@ -927,6 +935,12 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       h.bias = g->bias9; h.scale = g->sc9; h.shift = g->sh9; h.out = at(pl.g9, (G9X + 4) * G9C);
       h.up_sn = G9Y * G9X * G9C; h.up_sy = G9X * G9C;
       pl.hgrid = h.num_passes < sms ? h.num_passes : sms;
+      uint32_t bbh[2] = {kbe, 32};
+      if (tmap(&pl.hB_half, g->B9h, 2, bd, bs, bbh)) return 1;
+      const int pairs = (h.num_passes + 1) / 2;
+      pl.hgrid_pair = 2 * (pairs < sms / 2 ? pairs : sms / 2);
+      static const int halo_pair_env = getenv("WDG_HALO_PAIR") ? atoi(getenv("WDG_HALO_PAIR")) : 1;
+      pl.halo_pair = halo_pair_env != 0;
     }
     // ---------------- L11: final 3x3 conv on the tensor cores, super-pixel form (halo_conv.cuh, HEPI_FINAL; bf16 only)
     const long long SPW = G9X / 4;                              // super-pixels per padded row
@@ -1056,6 +1070,24 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Hal
   return 0;
 }
 
+// CTA-pair form: clusters of 2 (the two SMs of a TPC), one tcgen05.mma.cta_group::2 per pair of passes
+template <int BN, int NCHUNK, int NTAP, int TPS, int EPI, int PREC>
+static int launch_halo_pair(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const HaloParams& hp, int grid, int device,
+                            cudaStream_t stream) {
+  auto kern = halo_conv_kernel<BN, NCHUNK, NTAP, TPS, EPI, PREC, true>;
+  constexpr int smem = HaloCfg<BN / 2, NCHUNK, TPS>::SMEM;
+  ENSURE_SMEM(kern, device, smem);
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof cfg);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(224); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB_half, hp));
+  return 0;
+}
+
 // noise_dev == nullptr: the noise is drawn inside the packing kernel from `ns` (std, key, first counter block)
 template <int PREC>
 static int run_plan_t(wdg_generator* g, const Plan& pl, const float* image_dev, const float* noise_dev, const NoiseSpec& ns,
@@ -1081,7 +1113,9 @@ static int run_plan_t(wdg_generator* g, const Plan& pl, const float* image_dev, 
   CK(cudaGetLastError());
   mark();
   if (pl.use_halo) {
-    if (launch_halo<128, NC192, 8, 2, HEPI_AFFINE, PREC>(pl.h0A, pl.h0B, pl.h0p, pl.h0grid, dev, stream)) return 1;
+    if (pl.halo_pair) {
+      if (launch_halo_pair<128, NC192, 8, 2, HEPI_AFFINE, PREC>(pl.h0A, pl.h0B_half, pl.h0p, pl.h0grid_pair, dev, stream)) return 1;
+    } else if (launch_halo<128, NC192, 8, 2, HEPI_AFFINE, PREC>(pl.h0A, pl.h0B, pl.h0p, pl.h0grid, dev, stream)) return 1;
   } else if (launch_conv<PREC>(pl.L0, dev, stream)) return 1;
   mark();
   if (launch_conv<PREC>(pl.L2, dev, stream)) return 1;
@@ -1112,7 +1146,9 @@ static int run_plan_t(wdg_generator* g, const Plan& pl, const float* image_dev, 
   }
   mark();
   if (pl.use_halo) {
-    if (launch_halo<64, NC160, 16, 4, HEPI_UPCONV, PREC>(pl.hA, pl.hB, pl.hp, pl.hgrid, dev, stream)) return 1;
+    if (pl.halo_pair) {
+      if (launch_halo_pair<64, NC160, 16, 4, HEPI_UPCONV, PREC>(pl.hA, pl.hB_half, pl.hp, pl.hgrid_pair, dev, stream)) return 1;
+    } else if (launch_halo<64, NC160, 16, 4, HEPI_UPCONV, PREC>(pl.hA, pl.hB, pl.hp, pl.hgrid, dev, stream)) return 1;
   } else if (launch_conv<PREC>(pl.L9, dev, stream)) return 1;
   mark();
   bool done11 = false;
