@@ -57,9 +57,12 @@ struct EpiParams {
   int h_pitch;                       // pixels per row of the (zero-ring padded) h image
   int F;
   long long h_step;                  // elements between consecutive timesteps of the h image sequence
-  // Persistent time loop (ConvParams::t_begin .. t_end in ONE launch): every (tile, epilogue warp) that has stored its
-  // part of h_t adds 1 to sync_flags[t]; the TMA producer waits for sync_total arrivals on sync_flags[t-1] before it
-  // fetches the first h_{t-1} operand of step t.  NULL: one step per launch (the kernel boundary orders the steps).
+  // Persistent time loop (ConvParams::t_begin .. t_end in ONE launch).  The recurrent half of a tile at step t reads
+  // h_{t-1} of its own images only (3x3 halo, all channels), so the dependency is tracked per (step, image group of
+  // tile_n images): every (tile, epilogue warp) that has stored its part of h_t adds 1 to sync_flags[t * tiles_n + tn]; the
+  // TMA producer waits for sync_total (= every tile of that image group) arrivals on sync_flags[(t-1) * tiles_n + tn]
+  // before it fetches the tile's first h_{t-1} operand.  No grid-wide barrier: CTAs drift through the (t, tile) schedule and
+  // only neighbours in it ever wait for each other.  NULL: one step per launch (the kernel boundary orders the steps).
   unsigned long long* sync_flags;
   unsigned int sync_total;
   // ---- EPI_LSTM16_FWD / EPI_LSTM16_BWD: one recurrent step of the critic's 16-filter ConvLSTM2D in the TRAINING
@@ -177,10 +180,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint32_t phase = 0;
     for (int t = t_begin; t < t_end; ++t) {
       const int nkb = (EPI == EPI_LSTM && t == 0) ? p.num_kb_first : p.num_kb;
-      // the input half of step t (x_t) does not depend on step t-1: it is fetched, and multiplied, while other CTAs
-      // still finish step t-1; only the first h_{t-1} operand waits for every tile of that step
-      bool h_ready = (EPI != EPI_LSTM) || p.ep.sync_flags == nullptr || t == t_begin;
+      // the input half of step t (x_t) does not depend on step t-1: it is fetched, and multiplied, while the tiles of
+      // step t-1 that this tile's recurrent half needs are still being finished elsewhere
+      const bool h_sync = (EPI == EPI_LSTM) && p.ep.sync_flags != nullptr && t > t_begin;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        bool h_ready = !h_sync;
         const int n_tile = tile % p.n_tiles_N;
         const int m_tile = tile / p.n_tiles_N;
         const int tx = m_tile % p.tiles_x;
@@ -196,7 +200,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const KBlock k = p.kb[kb];
           if constexpr (EPI == EPI_LSTM) {
             if (!h_ready && k.src == 1) {
-              flag_wait(p.ep.sync_flags + (t - 1), p.ep.sync_total);
+              flag_wait(p.ep.sync_flags + (long long)(t - 1) * p.tiles_n + tn, p.ep.sync_total);
               fence_proxy_async_global();      // h_{t-1} was written through the generic proxy, TMA reads it through the async one
               h_ready = true;
             }
@@ -487,7 +491,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           __threadfence();
           fence_proxy_async_global();
           __syncwarp();
-          if (lane == 0) flag_arrive(e.sync_flags + t);
+          if (lane == 0) flag_arrive(e.sync_flags + (long long)t * p.tiles_n + tn);
         }
       }
       tc_fence_before();

@@ -14,7 +14,7 @@
 // Barriers: every TMA load (both CTAs) completes on the LEADER's `full` barrier (cp.async.bulk.tensor ... cta_group::2 with the
 // mbarrier address mapped to rank 0); tcgen05.commit.cta_group::2.multicast arrives on the `empty` (stage free) and `tfull`
 // (accumulator ready) barriers of BOTH CTAs; the peer's epilogue warps release a TMEM stage with a remote arrive on the
-// leader's `tempty` barrier.  Time loop and step flags: as in conv_umma.cuh (sync_flags).
+// leader's `tempty` barrier.  Time loop and per-image-group step flags: as in conv_umma.cuh (sync_flags).
 #pragma once
 #include "conv_umma.cuh"
 
@@ -158,7 +158,7 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint32_t phase = 0;
     for (int t = t_begin; t < t_end; ++t) {
       const int nkb = t == 0 ? p.num_kb_first : p.num_kb;
-      bool h_ready = p.ep.sync_flags == nullptr || t == t_begin;
+      const bool h_sync = p.ep.sync_flags != nullptr && t > t_begin;
       for (int pt = pair; pt < total_pair_tiles; pt += n_pairs) {
         const int n_tile = pt % p.n_tiles_N;
         const int m_tile = 2 * (pt / p.n_tiles_N) + (int)rank;       // beyond m_tiles (odd count): TMA zero-fills, epilogue masks
@@ -166,10 +166,11 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int ty = (m_tile / p.tiles_x) % p.tiles_y;
         const int tn = m_tile / (p.tiles_x * p.tiles_y);
         const int b1 = tx * p.tile_w, b2 = ty * p.tile_h, b4 = tn * p.tile_n;
+        bool h_ready = !h_sync || tn >= p.tiles_n;          // (a padding tile of an odd tile count reads zeros only)
         for (int kb = 0; kb < nkb; ++kb) {
           const KBlock k = p.kb[kb];
           if (!h_ready && k.src == 1) {
-            flag_wait(p.ep.sync_flags + (t - 1), p.ep.sync_total);
+            flag_wait(p.ep.sync_flags + (long long)(t - 1) * p.tiles_n + tn, p.ep.sync_total);
             fence_proxy_async_global();
             h_ready = true;
           }
@@ -284,11 +285,11 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                            ((long long)y * e.h_pitch + x) * e.F + ch0, hn);
           }
         }
-        if (e.sync_flags != nullptr && t + 1 < t_end) {
+        if (e.sync_flags != nullptr && t + 1 < t_end && tn < p.tiles_n) {
           __threadfence();
           fence_proxy_async_global();
           __syncwarp();
-          if (lane == 0) flag_arrive(e.sync_flags + t);
+          if (lane == 0) flag_arrive(e.sync_flags + (long long)t * p.tiles_n + tn);
         }
         tc_fence_before();
         __syncwarp();

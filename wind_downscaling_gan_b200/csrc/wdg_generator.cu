@@ -132,8 +132,8 @@ struct Plan {
   int hgrid = 0, h0grid = 0, h11grid = 0, h5grid = 0;
   // CTA-pair form (halo_conv.cuh PAIR) of the two big halo kernels: B boxes of BN/2 rows, clusters of 2
   bool halo_pair = false;
-  CUtensorMap hB_half, h0B_half;
-  int hgrid_pair = 0, h0grid_pair = 0;
+  CUtensorMap hB_half, h0B_half, h5B_half;
+  int hgrid_pair = 0, h0grid_pair = 0, h5grid_pair = 0;
   bool use_halo11 = false;     // final 3x3 conv on the tensor cores (super-pixel form)
   bool use_halo5 = false;      // 3x3 conv on the (zero-ring padded) hidden-state sequence with halo reuse
   int launches = 0;
@@ -517,7 +517,7 @@ static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
   L.edgeE = take(N * 4 * (S + 8) * (F / 4 + 128) * E);
   L.deltaD = take(N * S * 192 * 4);
   L.g9 = take(N * (S + 2) * (S + 8) * (F / 8) * E);   // zero ring: 1 row above/below, one 4-pixel super-pixel left/right
-  L.flags = take((size_t)T * sizeof(unsigned long long));   // step counters of the persistent ConvLSTM launch
+  L.flags = take((size_t)T * ((B + 1) / 2) * sizeof(unsigned long long));   // (step, image pair) counters of the persistent ConvLSTM launch
   L.total = o;
   return L;
 }
@@ -759,7 +759,7 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
     pl.LSP = pl.LS[0];
     pl.LSP.p.t_begin = 0; pl.LSP.p.t_end = T;
     pl.LSP.p.ep.sync_flags = pl.lstm_flags;
-    pl.LSP.p.ep.sync_total = 4u * (unsigned)(pl.LSP.p.tiles_x * pl.LSP.p.tiles_y * pl.LSP.p.tiles_n * pl.LSP.p.n_tiles_N);
+    pl.LSP.p.ep.sync_total = 4u * (unsigned)(pl.LSP.p.tiles_x * pl.LSP.p.tiles_y * pl.LSP.p.n_tiles_N);   // per image group: 4 epilogue warps per tile
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, g->device);
     pl.lstm_persist = T > 1 && coop && pl.LSP.grid <= sms && !getenv("WDG_NO_LSTM_PERSIST");
@@ -776,7 +776,6 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       if (lstm_pair_max_clusters(g, &max_clusters)) return 1;
       const int pairs = pair_tiles < max_clusters ? pair_tiles : max_clusters;
       pl.pair_grid = 2 * pairs;
-      pl.pair_p.ep.sync_total = 8u * (unsigned)pair_tiles;
       pl.lstm_pair = pairs > 0;
     }
   }
@@ -823,6 +822,10 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       h.out1 = pl.g5; h.o1_sn = (long long)S4 * S4 * (F / 2); h.o1_sy = (long long)S4 * (F / 2); h.o1_sx = F / 2;
       h.out2 = nullptr;
       pl.h5grid = h.num_passes < sms ? h.num_passes : sms;
+      uint32_t bbh[2] = {kbe, 32};
+      if (tmap(&pl.h5B_half, g->B5h, 2, bd, bs, bbh)) return 1;
+      const int pairs5 = (h.num_passes + 1) / 2;
+      pl.h5grid_pair = 2 * (pairs5 < sms / 2 ? pairs5 : sms / 2);
     }
   }
   // ---------------- L7: ConvT 2x2 s2 on concat(g5, res4) -> g7 [N][S2][S2][32] (pixel shuffle)
@@ -1121,7 +1124,7 @@ static int run_plan_t(wdg_generator* g, const Plan& pl, const float* image_dev, 
   if (launch_conv<PREC>(pl.L2, dev, stream)) return 1;
   mark();
   if (pl.lstm_persist) {
-    CK(cudaMemsetAsync(pl.lstm_flags, 0, (size_t)pl.T * sizeof(unsigned long long), stream));
+    CK(cudaMemsetAsync(pl.lstm_flags, 0, (size_t)pl.T * pl.LSP.p.tiles_n * sizeof(unsigned long long), stream));
     if (pl.lstm_pair) {
       if (launch_lstm_pair<PREC>(pl, stream)) return 1;
     } else if (launch_conv_coop<256, EPI_LSTM, PREC>(pl.LSP, dev, stream)) return 1;
@@ -1131,7 +1134,9 @@ static int run_plan_t(wdg_generator* g, const Plan& pl, const float* image_dev, 
   }
   mark();
   if (pl.use_halo5) {
-    if (launch_halo<64, NC128, 9, 3, HEPI_AFFINE, PREC>(pl.h5A, pl.h5B, pl.h5p, pl.h5grid, dev, stream)) return 1;
+    if (pl.halo_pair) {
+      if (launch_halo_pair<64, NC128, 9, 3, HEPI_AFFINE, PREC>(pl.h5A, pl.h5B_half, pl.h5p, pl.h5grid_pair, dev, stream)) return 1;
+    } else if (launch_halo<64, NC128, 9, 3, HEPI_AFFINE, PREC>(pl.h5A, pl.h5B, pl.h5p, pl.h5grid, dev, stream)) return 1;
   } else if (launch_conv<PREC>(pl.L5, dev, stream)) return 1;
   mark();
   if (launch_conv<PREC>(pl.L7, dev, stream)) return 1;
