@@ -90,24 +90,31 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
                : "memory");
 }
 
+template <int BN_>
 struct PairCfg {
-  static constexpr int BN = 256;                       // accumulator columns (4 gates x 64 channels)
+  static constexpr int BN = BN_;                       // accumulator columns (EPI_LSTM: 256 = 4 gates x 64 channels)
   static constexpr int B_HALF_BYTES = (BN / 2) * 128;  // this CTA's half of the B tile
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;   // 32 KB
-  static constexpr int STAGES = 6;
-  static constexpr int TMEM_COLS = 512;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;   // 32 KB (BN 256) / 24 KB (BN 128)
+  static constexpr int STAGES = BN >= 256 ? 6 : 8;
+  static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int VEC_COLS = 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + VEC_COLS * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 3 * VEC_COLS * 4;
+  static_assert(BN == 128 || BN == 256, "pair kernel is instantiated for 128 / 256 accumulator columns");
 };
 
-template <int PREC>
+// EPI_LSTM (BN 256): the persistent ConvLSTM.  EPI_AFFINE (BN 128): bias -> LeakyReLU -> folded BatchNorm convolution layers
+// with the same K-block / tile description as conv_umma_kernel (the 4x4 stride-2 convolution: its N = 128 MMAs read 8 KB of
+// operands per 64 cycles in the single-CTA kernel -- the whole shared-memory port -- and 6 KB here).
+template <int BN, int EPI, int PREC>
 __global__ void __launch_bounds__(192, 1)
-lstm_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
+conv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvParams p) {
-  using Cfg = PairCfg;
+  static_assert(EPI == EPI_LSTM || EPI == EPI_AFFINE, "pair kernel epilogues: ConvLSTM gates, affine");
+  static_assert(EPI != EPI_LSTM || BN == 256, "LSTM epilogue expects 4 gates x 64 channels");
+  using Cfg = PairCfg<BN>;
   using P = Prec<PREC>;
   using act_t = typename P::act_t;
-  constexpr int STAGES = Cfg::STAGES, BN = Cfg::BN;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // identical offsets in both CTAs (the pair's MMAs and multicast commits address both by the leader's offsets)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -120,7 +127,12 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // leader only: 8 epilogue warps of the pair drained the TMEM stage
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* sm_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
-  for (int i = threadIdx.x; i < p.n_tiles_N * BN && i < Cfg::VEC_COLS; i += blockDim.x) sm_bias[i] = p.ep.bias[i];
+  float* sm_scale = sm_bias + Cfg::VEC_COLS;
+  float* sm_shift = sm_scale + Cfg::VEC_COLS;
+  for (int i = threadIdx.x; i < p.n_tiles_N * BN && i < Cfg::VEC_COLS; i += blockDim.x) {
+    sm_bias[i] = p.ep.bias[i];
+    if constexpr (EPI == EPI_AFFINE) { sm_scale[i] = p.ep.scale[i]; sm_shift[i] = p.ep.shift[i]; }
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -129,7 +141,7 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   const int total_pair_tiles = ((m_tiles + 1) >> 1) * p.n_tiles_N;
-  const int t_begin = p.t_begin, t_end = p.t_end;
+  const int t_begin = (EPI == EPI_LSTM) ? p.t_begin : 0, t_end = (EPI == EPI_LSTM) ? p.t_end : 1;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX);
@@ -157,15 +169,20 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     for (int t = t_begin; t < t_end; ++t) {
-      const int nkb = t == 0 ? p.num_kb_first : p.num_kb;
-      const bool h_sync = p.ep.sync_flags != nullptr && t > t_begin;
+      const int nkb = (EPI == EPI_LSTM && t == 0) ? p.num_kb_first : p.num_kb;
+      const bool h_sync = (EPI == EPI_LSTM) && p.ep.sync_flags != nullptr && t > t_begin;
       for (int pt = pair; pt < total_pair_tiles; pt += n_pairs) {
         const int n_tile = pt % p.n_tiles_N;
         const int m_tile = 2 * (pt / p.n_tiles_N) + (int)rank;       // beyond m_tiles (odd count): TMA zero-fills, epilogue masks
         const int tx = m_tile % p.tiles_x;
         const int ty = (m_tile / p.tiles_x) % p.tiles_y;
         const int tn = m_tile / (p.tiles_x * p.tiles_y);
-        const int b1 = tx * p.tile_w, b2 = ty * p.tile_h, b4 = tn * p.tile_n;
+        const int n0 = tn * p.tile_n;
+        const int b0 = (p.ntile_coord == 0 ? n_tile : 0);
+        const int b1 = tx * p.tile_w + (p.ntile_coord == 1 ? n_tile : 0);
+        const int b2 = ty * p.tile_h + (p.ntile_coord == 2 ? n_tile : 0);
+        const int b3 = (p.n_coord == 3 ? n0 : 0) + (p.ntile_coord == 3 ? n_tile : 0) + (EPI == EPI_LSTM ? t : 0);
+        const int b4 = (p.n_coord == 4 ? n0 : 0);
         bool h_ready = !h_sync || tn >= p.tiles_n;          // (a padding tile of an odd tile count reads zeros only)
         for (int kb = 0; kb < nkb; ++kb) {
           const KBlock k = p.kb[kb];
@@ -178,7 +195,7 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           if (elect_one()) {
             const uint32_t full0 = mapa_u32(smem_u32(&full_bar[stage]), 0);
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);     // both CTAs' A tile + B half
-            tma2_load_5d(smA + stage * A_STAGE_BYTES, k.src == 0 ? &tmX : &tmH, full0, k.o0, b1 + k.o1, b2 + k.o2, t + k.o3, b4);
+            tma2_load_5d(smA + stage * A_STAGE_BYTES, k.src == 0 ? &tmX : &tmH, full0, b0 + k.o0, b1 + k.o1, b2 + k.o2, b3 + k.o3, b4);
             tma2_load_2d(smB + stage * Cfg::B_HALF_BYTES, &tmB, full0, kb * P::KB_ELEMS, n_tile * BN + (int)rank * (BN / 2));
           }
           __syncwarp();
@@ -195,7 +212,7 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       int as = 0;
       uint32_t aphase = 0;
       for (int t = t_begin; t < t_end; ++t) {
-        const int nkb = t == 0 ? p.num_kb_first : p.num_kb;
+        const int nkb = (EPI == EPI_LSTM && t == 0) ? p.num_kb_first : p.num_kb;
         for (int pt = pair; pt < total_pair_tiles; pt += n_pairs) {
           mbar_wait(&tempty_bar[as], aphase ^ 1);
           tc_fence_after();
@@ -244,6 +261,25 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+        if constexpr (EPI == EPI_AFFINE) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[2][16];
+            tmem_ld16(taddr + c0, r[0]);
+            tmem_ld16(taddr + c0 + 16, r[1]);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                const int col = n_tile * BN + c0 + 16 * g;
+                const long long off = (long long)n * e.out_sn + (long long)y * e.out_sy + (long long)x * e.out_sx + e.out_c0 + col;
+                float v[16];
+                affine16(r[g], sm_bias + col, sm_scale + col, sm_shift + col, e.lrelu != 0, v);
+                P::store16(reinterpret_cast<act_t*>(e.out) + off, v);
+              }
+            }
+          }
+        } else {
         const long long pix = ((long long)n * p.H + y) * p.W + x;
 #pragma unroll 1
         for (int s = 0; s < 4; ++s) {
@@ -290,6 +326,7 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           fence_proxy_async_global();
           __syncwarp();
           if (lane == 0) flag_arrive(e.sync_flags + (long long)t * p.tiles_n + tn);
+        }
         }
         tc_fence_before();
         __syncwarp();

@@ -123,6 +123,9 @@ struct Plan {
   unsigned long long* lstm_flags = nullptr;   // [T] step counters in the workspace
   // the same launch on CTA pairs (conv_umma2.cuh: tcgen05.mma.cta_group::2, B tile split over the two SMs of a TPC)
   bool lstm_pair = false;
+  bool l2_pair = false;        // 4x4 stride-2 convolution on CTA pairs (conv_pair_kernel<128, EPI_AFFINE>)
+  CUtensorMap l2B_half;
+  int l2_pair_grid = 0;
   CUtensorMap tmB_half;        // B boxes of 128 weight rows
   ConvParams pair_p;
   int pair_grid = 0;
@@ -574,18 +577,18 @@ static void affine_epi(EpiParams& e, const float* bias, const float* sc, const f
 // ---- CTA-pair ConvLSTM launch (conv_umma2.cuh): clusters of 2, cooperative (the step flags need every CTA resident)
 template <int PREC>
 static int lstm_pair_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attrs, int grid, cudaStream_t stream) {
-  auto kern = lstm_pair_kernel<PREC>;
+  auto kern = conv_pair_kernel<256, EPI_LSTM, PREC>;
   static bool done[64] = {};
   int dev = 0;
   CK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !done[dev]) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::SMEM_BYTES));
     if (dev >= 0 && dev < 64) done[dev] = true;
   }
   std::memset(cfg, 0, sizeof *cfg);
   cfg->gridDim = dim3(grid);
   cfg->blockDim = dim3(192);
-  cfg->dynamicSmemBytes = PairCfg::SMEM_BYTES;
+  cfg->dynamicSmemBytes = PairCfg<256>::SMEM_BYTES;
   cfg->stream = stream;
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
@@ -602,11 +605,11 @@ static int lstm_pair_max_clusters(const wdg_generator* g, int* n) {
   if (g->prec == PREC_TF32) {
     if (lstm_pair_config<PREC_TF32>(&cfg, attrs, 2 * g->sm_count, nullptr)) return 1;
     cfg.numAttrs = 1;       // the occupancy query takes the cluster shape only
-    CK(cudaOccupancyMaxActiveClusters(n, lstm_pair_kernel<PREC_TF32>, &cfg));
+    CK(cudaOccupancyMaxActiveClusters(n, conv_pair_kernel<256, EPI_LSTM, PREC_TF32>, &cfg));
   } else {
     if (lstm_pair_config<PREC_BF16>(&cfg, attrs, 2 * g->sm_count, nullptr)) return 1;
     cfg.numAttrs = 1;
-    CK(cudaOccupancyMaxActiveClusters(n, lstm_pair_kernel<PREC_BF16>, &cfg));
+    CK(cudaOccupancyMaxActiveClusters(n, conv_pair_kernel<256, EPI_LSTM, PREC_BF16>, &cfg));
   }
   return 0;
 }
@@ -713,6 +716,12 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       }
     affine_epi(c.p.ep, g->bias2, g->sc2, g->sh2, pl.res4, (long long)S4 * S4 * F, (long long)S4 * F, F, 0, 1);
     c.bn = 128; c.epi = EPI_AFFINE; c.shallow = (shallow_mask >> 2) & 1; c.grid = grid_for(c.p, c.shallow ? 2 : 1);
+    static const int l2_pair_env = getenv("WDG_CONV_PAIR") ? atoi(getenv("WDG_CONV_PAIR")) : 1;
+    uint32_t bbh[2] = {kbe, 64};
+    if (tmap(&pl.l2B_half, g->B2, 2, bd, bs, bbh)) return 1;
+    const int m_tiles = c.p.tiles_x * c.p.tiles_y * c.p.tiles_n, pair_tiles = ((m_tiles + 1) / 2) * c.p.n_tiles_N;
+    pl.l2_pair_grid = 2 * (pair_tiles < sms / 2 ? pair_tiles : sms / 2);
+    pl.l2_pair = l2_pair_env != 0 && pl.l2_pair_grid > 0;
   }
   // ---------------- ConvLSTM steps: A maps over (c, x, y, t, b) of res4 (x_t) and hseq (h_{t-1})
   {
@@ -1044,12 +1053,28 @@ static int launch_conv_coop(const ConvLaunch& c, int device, cudaStream_t stream
   CK(cudaLaunchCooperativeKernel((const void*)kern, dim3(c.grid), dim3(192), args, Cfg::SMEM_BYTES, stream));
   return 0;
 }
+// CTA-pair convolution (conv_umma2.cuh), plain cluster launch
+template <int BN, int EPI, int PREC>
+static int launch_conv_pair(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmB_half, const ConvParams& p, int grid,
+                            int device, cudaStream_t stream) {
+  auto kern = conv_pair_kernel<BN, EPI, PREC>;
+  ENSURE_SMEM(kern, device, PairCfg<BN>::SMEM_BYTES);
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof cfg);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = PairCfg<BN>::SMEM_BYTES; cfg.stream = stream;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, kern, tmA0, tmA1, tmB_half, p));
+  return 0;
+}
 template <int PREC>
 static int launch_lstm_pair(const Plan& pl, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attrs[2];
   if (lstm_pair_config<PREC>(&cfg, attrs, pl.pair_grid, stream)) return 1;
-  CK(cudaLaunchKernelEx(&cfg, lstm_pair_kernel<PREC>, pl.LSP.tmA[0], pl.LSP.tmA[1], pl.tmB_half, pl.pair_p));
+  CK(cudaLaunchKernelEx(&cfg, conv_pair_kernel<256, EPI_LSTM, PREC>, pl.LSP.tmA[0], pl.LSP.tmA[1], pl.tmB_half, pl.pair_p));
   return 0;
 }
 template <int PREC>
@@ -1121,7 +1146,9 @@ static int run_plan_t(wdg_generator* g, const Plan& pl, const float* image_dev, 
     } else if (launch_halo<128, NC192, 8, 2, HEPI_AFFINE, PREC>(pl.h0A, pl.h0B, pl.h0p, pl.h0grid, dev, stream)) return 1;
   } else if (launch_conv<PREC>(pl.L0, dev, stream)) return 1;
   mark();
-  if (launch_conv<PREC>(pl.L2, dev, stream)) return 1;
+  if (pl.l2_pair) {
+    if (launch_conv_pair<128, EPI_AFFINE, PREC>(pl.L2.tmA[0], pl.L2.tmA[1], pl.l2B_half, pl.L2.p, pl.l2_pair_grid, dev, stream)) return 1;
+  } else if (launch_conv<PREC>(pl.L2, dev, stream)) return 1;
   mark();
   if (pl.lstm_persist) {
     CK(cudaMemsetAsync(pl.lstm_flags, 0, (size_t)pl.T * pl.LSP.p.tiles_n * sizeof(unsigned long long), stream));
