@@ -12,8 +12,10 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "wind_downscaling_gan_b200", "csrc", "libwdg.so")
-PATTERNS = [("tcgen05.mma", r"\bUTC[A-Z]*MMA\b"), ("TMA load", r"\bUTMALDG\b"), ("tcgen05.ld", r"\bLDTM\b"),
-            ("tcgen05.commit/barrier", r"\bUTCBAR\b"), ("TMEM alloc", r"\bUTCATOMSWS\b"), ("mbarrier", r"\bSYNCS\b"),
+PATTERNS = [("tcgen05.mma", r"\bUTC[A-Z]*MMA\b"), ("of which cta_group::2", r"\bUTC[A-Z]*MMA\.2CTA\b"), ("TMA load", r"\bUTMALDG\b"),
+            ("tcgen05.ld", r"\bLDTM\b"),
+            ("tcgen05.commit/barrier", r"\bUTCBAR\b"), ("TMEM alloc", r"\bUTCATOMSWS\b"), ("cluster barrier", r"\bUCGABAR_ARV\b"),
+            ("mbarrier", r"\bSYNCS\b"),
             ("legacy HMMA", r"\bHMMA\b"), ("FFMA", r"\bFFMA\b")]
 
 
@@ -35,14 +37,15 @@ def main():
     print("# SASS opcode summary of libwdg.so (sm_100a), round 2\n")
     print(f"`cuobjdump -sass {os.path.relpath(LIB, ROOT)}`: {len(names)} kernels, {len(rows)} of them issue tcgen05 / TMA instructions.")
     print("Template arguments of the inference kernels end in the operand precision: `0` = bf16 (`kind::f16`), `1` = tf32 "
-          "(`kind::tf32`); both kinds assemble to `UTCHMMA` (the kind lives in the instruction descriptor).\n")
+          "(`kind::tf32`); both kinds assemble to `UTCHMMA` (the kind lives in the instruction descriptor).  `conv_pair_kernel` and "
+          "`halo_conv_kernel<..., true>` are the CTA-pair kernels: `UTCHMMA.2CTA`, `UTMALDG.2CTA`, `UTCBAR.2CTA.MULTICAST`.\n")
     print("| whole library | " + " | ".join(k for k, _ in PATTERNS) + " |")
     print("|---|" + "---|" * len(PATTERNS))
     print("| all kernels | " + " | ".join(str(total[k]) for k, _ in PATTERNS) + " |\n")
-    print("| kernel | " + " | ".join(k for k, _ in PATTERNS[:5]) + " |")
-    print("|---|" + "---|" * 5)
+    print("| kernel | " + " | ".join(k for k, _ in PATTERNS[:7]) + " |")
+    print("|---|" + "---|" * 7)
     for short, c in sorted(rows, key=lambda r: r[0]):
-        print(f"| `{short}` | " + " | ".join(str(c[k]) for k, _ in PATTERNS[:5]) + " |")
+        print(f"| `{short}` | " + " | ".join(str(c[k]) for k, _ in PATTERNS[:7]) + " |")
 
 
 if __name__ == "__main__":
