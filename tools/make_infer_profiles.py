@@ -47,7 +47,9 @@ def launch_list():
     out = [f"# {TAG} launch list (ncu --metrics gpu__time_duration.sum --clock-control none -c 400, `bench.py --steps 2 --warmup 3 --no-cpu-baseline`)\n",
            "Per-launch times are cold-cache and serialised: compare SHARES with the CUDA-event stage shares of profiles/" + TAG + "_bench_n1.json, not absolutes.",
            "conv_umma_kernel<BN,EPI>: EPI 0 = bias/LeakyReLU/BN affine, 1 = ConvLSTM gates. halo_conv_kernel<BN,NCHUNK,NTAP,TPS,EPI>: <128,3,8,2,1> = 8x8 s2 conv,",
-           "<64,3,16,4,0> = fused upsample + 5x5 transposed conv, <16,1,9,3,2> = final 3x3 conv in super-pixel form.\n",
+           "<64,3,16,4,0> = fused upsample + 5x5 transposed conv, <16,1,9,3,2> = final 3x3 conv in super-pixel form; a trailing `true` = CTA-pair form.",
+           "conv_pair_kernel<BN,EPI,PREC>: CTA-pair (tcgen05.mma.cta_group::2) implicit GEMM: <256,1> = all ConvLSTM steps in one persistent launch,",
+           "<128,0> = 4x4 s2 conv.\n",
            "| kernel | launches | total us | share |", "|---|---|---|---|"]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f"| {k} | {v[0]} | {v[1]:.1f} | {v[1] / tot:.3f} |")
@@ -58,9 +60,10 @@ def launch_list():
 def ncu_tables():
     rep = os.path.join(G, f"prof_{TAG}.ncu-rep")
     md = subprocess.run([sys.executable, os.path.join(P, "summarize_ncu.py"), rep], capture_output=True, text=True).stdout
-    head = (f"# {TAG} — ncu `--set full --clock-control none --import-source on -c 17` of one generator forward (bench.py workload: 64 sequences x 8\n"
-            "timesteps = 512 fields), B200.  Kernel order = launch order of the forward (pack, 8x8 s2, 4x4 s2, 8 ConvLSTM steps, 3x3, convT 2x2,\n"
-            "edge lines, border GEMM, fused upsample conv, final conv).  Cold first forward: use the ratios, not the absolute times.\n\n")
+    head = (f"# {TAG} — ncu `--set full --clock-control none --import-source on` of the generator forward (bench.py workload: 64 sequences x 8\n"
+            "timesteps = 512 fields), B200.  Kernel order = launch order of the forward (pack, 8x8 s2, 4x4 s2, ConvLSTM -- all 8 steps in one\n"
+            "persistent launch --, 3x3, convT 2x2, edge lines, border GEMM, fused upsample conv, final conv).  Cold first forward: use the ratios,\n"
+            "not the absolute times.\n\n")
     open(os.path.join(P, f"{TAG}_ncu_kernels.md"), "w").write(head + md.replace("(anonymous namespace)::", ""))
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -73,15 +76,35 @@ def ncu_tables():
         for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             t += float(r[col[m]].replace(",", "")) * scale.get(units[col[m]], 1.0)
         return t
-    assert len(data) >= len(STAGES), len(data)
+    # first forward of the capture: from the first input-packing kernel to the one before the next
+    names = [clean(r[col["Kernel Name"]]) for r in data]
+    starts = [i for i, n in enumerate(names) if n.startswith("pack_input")]
+    assert starts, names[:5]
+    fwd = list(range(starts[0], starts[1] if len(starts) > 1 else len(data)))
+
+    def stage_of(name, seen):
+        if name.startswith("pack_input"): return "pack_input"
+        if name.startswith("halo_conv_kernel<128"): return "conv8x8s2"
+        if name.startswith(("conv_pair_kernel<256", "conv_umma_kernel<256")): return "convlstm"
+        if name.startswith("conv_pair_kernel<128"): return "conv4x4s2"
+        if name.startswith("conv_umma_kernel<128"): return "convT2x2s2" if "conv4x4s2" in seen else "conv4x4s2"
+        if re.match(r"halo_conv_kernel<64, [24], 9, 3", name): return "conv3x3"
+        if name.startswith(("edge_lines", "conv_umma_kernel<48")): return "border_fix"
+        if re.match(r"halo_conv_kernel<64, [35], 16, 4", name): return "upconvT5x5"
+        if name.startswith(("halo_conv_kernel<16", "final_conv3x3")): return "conv3x3_out"
+        return None
     per = collections.OrderedDict()
-    for i, st in enumerate(STAGES):
-        per.setdefault(st, []).append((clean(data[i][col["Kernel Name"]]), dram(data[i])))
+    for i in fwd:
+        st = stage_of(names[i], per)
+        if st is not None:
+            per.setdefault(st, []).append((names[i], dram(data[i])))
     out = collections.OrderedDict()
     for st, lst in per.items():
-        if st == "convlstm":
+        if st == "convlstm" and len(lst) > 1:
             later = [b for _, b in lst[1:]]
             out[st] = {"dram_bytes_per_launch": sum(later) / len(later), "kernel": lst[0][0] + " (steps t>0)"}
+        elif st == "convlstm":
+            out[st] = {"dram_bytes_per_launch": lst[0][1], "kernel": lst[0][0] + " (all T steps in one persistent launch)"}
         elif st == "border_fix":
             out[st] = {"dram_bytes_per_launch": sum(b for _, b in lst), "kernel": " + ".join(k for k, _ in lst)}
         else:

@@ -595,7 +595,11 @@ static int lstm_pair_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attrs,
   attrs[1].id = cudaLaunchAttributeCooperative;
   attrs[1].val.cooperative = 1;
   cfg->attrs = attrs;
-  cfg->numAttrs = 2;
+  // WDG_LSTM_COOP=0 (profiling only): Nsight Compute refuses the cooperative + cluster launch (LaunchFailed); without the
+  // attribute the grid (<= one CTA per SM) is still fully resident on an otherwise idle GPU, which is what ncu's serialised
+  // replay provides.  The bounded flag wait traps instead of hanging if that ever does not hold.
+  static const int coop = getenv("WDG_LSTM_COOP") ? atoi(getenv("WDG_LSTM_COOP")) : 1;
+  cfg->numAttrs = coop ? 2 : 1;
   return 0;
 }
 static int lstm_pair_max_clusters(const wdg_generator* g, int* n) {
@@ -1049,6 +1053,12 @@ static int launch_conv_coop(const ConvLaunch& c, int device, cudaStream_t stream
   auto kern = conv_umma_kernel<BN, EPI, PREC, 0>;
   using Cfg = ConvCfg<BN, 0>;
   ENSURE_SMEM(kern, device, Cfg::SMEM_BYTES);
+  static const int coop = getenv("WDG_LSTM_COOP") ? atoi(getenv("WDG_LSTM_COOP")) : 1;     // see lstm_pair_config
+  if (!coop) {
+    kern<<<c.grid, 192, Cfg::SMEM_BYTES, stream>>>(c.tmA[0], c.tmA[1], c.tmA[2], c.tmB, c.p);
+    CK(cudaGetLastError());
+    return 0;
+  }
   void* args[5] = {(void*)&c.tmA[0], (void*)&c.tmA[1], (void*)&c.tmA[2], (void*)&c.tmB, (void*)&c.p};
   CK(cudaLaunchCooperativeKernel((const void*)kern, dim3(c.grid), dim3(192), args, Cfg::SMEM_BYTES, stream));
   return 0;
