@@ -307,7 +307,7 @@ def measure_inference(D, gen, precision, args, image_p, noise_p, out_p, image_d,
                 stage_ms[k] = stage_ms.get(k, 0.0) + v / args.steps
         gen.set_profiling(False)
     res = {"precision": precision, "ms_per_step": ms_step, "value": D.world * FIELDS_PER_STEP / (ms_step * 1e-3),
-           "clocks": clocks, "stage_ms": stage_ms}
+           "clocks": clocks, "stage_ms": stage_ms, "lstm_launches": gen.launches_per_forward() - 9}
     # end to end, the reference's call pattern: host image in, noise drawn on the device, host result out
     ng = FlexibleNoiseGenerator((B, T, S, S, CNOISE), std=0.1, random_seed=7 + D.rank)
     for _ in range(2):
@@ -340,7 +340,8 @@ def inference_roofline(res, peaks, world):
     total = sum(res["stage_ms"].values())
     stages = {}
     for name, ms in res["stage_ms"].items():
-        launches = T if name == "convlstm" else (2 if name == "border_fix" else 1)
+        # ConvLSTM: all T steps in one persistent launch (or one per step with WDG_NO_LSTM_PERSIST=1)
+        launches = res.get("lstm_launches", T) if name == "convlstm" else (2 if name == "border_fix" else 1)
         ent = {"ms_per_step": ms, "launches_per_step": launches, "share": ms / total}
         if name in STAGE_MMAC and name != "conv3x3_out":
             tf = 2 * STAGE_MMAC[name] * 1e6 * FIELDS_PER_STEP / (ms * 1e-3) / 1e12

@@ -38,6 +38,7 @@ struct HaloParams {
   int tap_shift[16];     // row shift of each tap
   int box_rows;          // rows per A TMA box (two boxes per chunk; <= H_BOX_ROWS): 2 * box_rows >= 256 + max tap shift
   unsigned char kmask[16];   // per tap: bit k set = the k-th 16-element K slice of the tap has non-zero weights (issue its MMA)
+  unsigned char kskip_tail;  // K slices of the LAST channel chunk that are pure padding (zero activations and weights): not issued
   const float* bias;     // [BN] (HEPI_UPCONV: [16])
   const float* scale;
   const float* shift;
@@ -210,7 +211,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < TPS; ++j) {
               const int tap = g * TPS + j;
               const uint32_t shift_rows = (uint32_t)p.tap_shift[tap];
-              const uint32_t kmask = p.kmask[tap];
+              const uint32_t kmask = p.kmask[tap] & ~((c == NCHUNK - 1) ? (uint32_t)p.kskip_tail : 0u);
               const int first_k = __ffs((int)kmask) - 1;     // the first MMA of a tile overwrites the accumulator
               const uint64_t db = b_desc0 + (uint64_t)(j * BROWS * 8);                       // rows * 128 B >> 4
 #pragma unroll

@@ -948,6 +948,12 @@ static int build_plan(wdg_generator* g, Plan& pl, int B, int T, uint8_t* ws) {
       h.num_passes = (int)((flat + H_TILES * TILE_M - 1) / (H_TILES * TILE_M));
       h.n_img = (int)N; h.pw = (int)PW; h.ph = (int)PW; h.S = (int)S; h.delta = pl.deltaD; h.box_rows = H_BOX_ROWS;
       for (int tap = 0; tap < 16; ++tap) { h.tap_shift[tap] = (tap / 4) * (int)PW + tap % 4; h.kmask[tap] = 0xF; }
+      // 160 input channels in chunks of kbe: the last bf16 chunk (channels 128..191) is half padding -- zero weights and
+      // zero activations -- so its upper two 16-channel K slices are never issued (1/6 of the layer's MMAs; exact)
+      {
+        const int used = (int)(I9 - (uint64_t)(nch9 - 1) * kbe), per_slice = (int)kbe / 4, slices = (used + per_slice - 1) / per_slice;
+        h.kskip_tail = (unsigned char)(0xF & ~((1u << slices) - 1u));
+      }
       h.bias = g->bias9; h.scale = g->sc9; h.shift = g->sh9; h.out = at(pl.g9, (G9X + 4) * G9C);
       h.up_sn = G9Y * G9X * G9C; h.up_sy = G9X * G9C;
       pl.hgrid = h.num_passes < sms ? h.num_passes : sms;
