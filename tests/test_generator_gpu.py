@@ -122,13 +122,15 @@ def test_pipelined_host_path_is_bitwise_equal(mk):
 
 
 @pytest.mark.parametrize("precision", ["bf16", "tf32"])
-def test_in_kernel_noise_equals_materialised_noise(mk, precision):
+@pytest.mark.parametrize("B", [37, 64])
+def test_in_kernel_noise_equals_materialised_noise(mk, precision, B):
     """Noise drawn inside the packing kernel (wdg_generator_forward_gen_noise) == the FlexibleNoiseGenerator tensor fed
-    through forward(), bit for bit, on the device entry point and on the pipelined host entry point (chunk offsets)."""
+    through forward(), bit for bit, on the device entry point and on the pipelined host entry point, whose pieces
+    (B = 37: 8 | 21 | 8, B = 64: 8 | 16 | 32 | 8 sequences) each start at their own counter offset."""
     import torch
     from oracle.generator import synthetic_generator_weights
     from wind_downscaling_gan_b200.data.data_generator import FlexibleNoiseGenerator
-    B, T, S = 37, 2, 32
+    T, S = 2, 32
     gen = mk(S, 3, 20, 2, T).set_precision(precision)
     gen.set_weights(synthetic_generator_weights(4))
     image, _ = inputs(B, T, S, 8)

@@ -162,8 +162,11 @@ struct wdg_generator {
       *w11, *b11;
   // plans: [0] = the bound (B, T); [1], [2] = chunk / tail plans used by the pipelined host entry point.
   // Every plan owns a disjoint region of the caller's workspace, so the zero rings of its padded buffers stay zero.
-  Plan plans[5];   // full batch, chunk, tail, short last piece, chunk minus the short piece
-  int chunk_B = 0, tail_B = 0;
+  Plan plans[1];   // [0] = the bound (B, T)
+  // host pipeline (predict_host*): the batch is cut into pieces, each with its own plan (one per distinct size)
+  std::map<int, Plan> piece_plans;
+  std::vector<int> sched_host, sched_dev;   // piece sizes: host-supplied noise (H2D-bound) / noise drawn on the device
+  int max_piece = 0;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev_h2d[2] = {}, ev_fwd[2] = {}, ev_d2h[2] = {};
   FinalConvW<16, 2> w11h;      // final 3x3 conv weights, passed by value (constant bank)
@@ -525,36 +528,70 @@ static WsLayout ws_layout(const wdg_generator* g, int B, int T) {
   return L;
 }
 
-// The pipelined host entry point splits B into chunks of CHUNK_B sequences (plus a tail); each plan gets its own region.
-static const int CHUNK_B = 16;
-// With host-resident noise the pipeline is bound by the H2D copies, and what it adds to them is the forward + D2H of the
-// LAST piece: when the batch divides into whole chunks the last chunk is issued as (chunk - SHORT_B) + SHORT_B sequences
-// (measured: 8.72 -> 8.4 ms per 64 sequences).  Device-generated noise keeps whole chunks (compute-bound: larger is better).
-static const int SHORT_B = 4;
-static bool short_piece(int chunk_B, int tail_B) { return chunk_B >= 3 * SHORT_B && tail_B == 0; }
-static void chunking(int B, int* chunk_B, int* tail_B) {
+// The pipelined host entry point cuts B into pieces; every distinct piece size gets its own plan and workspace region.
+// H2D copy of piece i+1 | forward of piece i | D2H copy of piece i-1 run on three streams.
+//  * host-supplied noise (434 MB per 512 fields): the pipeline is bound by the H2D copies; what it adds to them is the
+//    forward + D2H of the LAST piece, so: uniform chunks of CHUNK_B and a short last piece (measured 8.72 -> 8.4 ms / 64 seq);
+//  * noise drawn on the device: compute-bound.  step = H2D(first piece) + sum of forwards + D2H(last piece), and a forward
+//    costs ~0.2 ms + 0.027 ms per sequence (profiles/r2_batch_sweep.json), so: a small head (its copy is all that is exposed),
+//    pieces that double while the copy engine stays ahead of the SMs (a piece's H2D must finish before its predecessor's
+//    forward does: 17.7 us per sequence copied vs >= 27 us computed), large middle pieces, a small tail.
+//    B = 64: 8 | 16 | 32 | 8.
+// WDG_CHUNK_B=n forces uniform chunks of n for both (tuning / tests).
+static const int CHUNK_B = 16, SHORT_B = 4, HEAD_B = 8, BIG_B = 32;
+struct Schedules { std::vector<int> host, dev; };
+static Schedules make_schedules(int B) {
+  Schedules S;
   int cb = CHUNK_B;
-  if (const char* e = getenv("WDG_CHUNK_B")) {   // tuning knob of the host pipeline (sequences per chunk)
+  bool forced = false;
+  if (const char* e = getenv("WDG_CHUNK_B")) {
     const int v = atoi(e);
-    if (v > 0) cb = v;
+    if (v > 0) { cb = v; forced = true; }
   }
-  if (B >= 2 * cb) { *chunk_B = cb; *tail_B = B % cb; }
-  else { *chunk_B = 0; *tail_B = 0; }
+  if (B < 2 * cb) return S;                       // small batch: one piece, no pipeline
+  for (int b = 0; b < B; b += cb) S.host.push_back(B - b < cb ? B - b : cb);
+  if (B % cb == 0 && cb >= 3 * SHORT_B) { S.host.back() = cb - SHORT_B; S.host.push_back(SHORT_B); }
+  if (forced) {
+    for (int b = 0; b < B; b += cb) S.dev.push_back(B - b < cb ? B - b : cb);
+    return S;
+  }
+  S.dev.push_back(HEAD_B);
+  int rem = B - 2 * HEAD_B, next = 2 * HEAD_B;
+  while (rem > 0) {
+    int take = next < rem ? next : rem;
+    if (rem - take < HEAD_B) take = rem;          // no sliver before the tail
+    S.dev.push_back(take);
+    rem -= take;
+    if (next < BIG_B) next *= 2;
+  }
+  S.dev.push_back(HEAD_B);
+  return S;
+}
+static std::vector<int> distinct_sizes(const Schedules& S) {
+  std::vector<int> v;
+  for (const std::vector<int>* l : {&S.host, &S.dev})
+    for (int n : *l) {
+      bool seen = false;
+      for (int m : v) seen = seen || m == n;
+      if (!seen) v.push_back(n);
+    }
+  return v;
 }
 
 extern "C" int wdg_generator_workspace_bytes(const wdg_generator* g, int B, int T, size_t* bytes) {
   if (!g || !bytes || B <= 0 || T <= 0) return fail("bad argument");
-  int cb, tb;
-  chunking(B, &cb, &tb);
-  *bytes = ws_layout(g, B, T).total + (cb ? ws_layout(g, cb, T).total : 0) + (tb ? ws_layout(g, tb, T).total : 0);
-  if (short_piece(cb, tb)) *bytes += ws_layout(g, SHORT_B, T).total + ws_layout(g, cb - SHORT_B, T).total;
+  *bytes = ws_layout(g, B, T).total;
+  for (int n : distinct_sizes(make_schedules(B))) *bytes += ws_layout(g, n, T).total;
   return 0;
 }
 
 extern "C" int wdg_generator_io_bytes(const wdg_generator* g, int B, int T, size_t* bytes) {
   if (!g || !bytes || B <= 0 || T <= 0) return fail("bad argument");
-  const size_t px = (size_t)B * T * g->S * g->S;
-  *bytes = align_up(px * g->cin * 4, 256) + align_up(px * g->cnoise * 4, 256) + align_up(px * g->cout * 4, 256);
+  int mp = 0;
+  for (int n : distinct_sizes(make_schedules(B))) mp = n > mp ? n : mp;
+  const int seqs = 2 * mp > B ? 2 * mp : B;        // double-buffered staging of the largest piece, or the whole batch
+  const size_t px = (size_t)seqs * T * g->S * g->S;
+  *bytes = align_up(px * g->cin * 4, 256) + align_up(px * g->cnoise * 4, 256) + align_up(px * g->cout * 4, 256) + 1024;
   return 0;
 }
 
@@ -1010,21 +1047,15 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
   CK(cudaMemsetAsync(workspace_dev, 0, need, stream));
   uint8_t* ws = (uint8_t*)workspace_dev;
   for (auto& pl : g->plans) pl.B = 0;
-  chunking(B, &g->chunk_B, &g->tail_B);
+  g->piece_plans.clear();
+  const Schedules S = make_schedules(B);
+  g->sched_host = S.host; g->sched_dev = S.dev; g->max_piece = 0;
   if (build_plan(g, g->plans[0], B, T, ws)) return 1;
   ws += ws_layout(g, B, T).total;
-  if (g->chunk_B) {
-    if (build_plan(g, g->plans[1], g->chunk_B, T, ws)) return 1;
-    ws += ws_layout(g, g->chunk_B, T).total;
-  }
-  if (g->tail_B) {
-    if (build_plan(g, g->plans[2], g->tail_B, T, ws)) return 1;
-    ws += ws_layout(g, g->tail_B, T).total;
-  }
-  if (short_piece(g->chunk_B, g->tail_B)) {
-    if (build_plan(g, g->plans[3], SHORT_B, T, ws)) return 1;
-    ws += ws_layout(g, SHORT_B, T).total;
-    if (build_plan(g, g->plans[4], g->chunk_B - SHORT_B, T, ws)) return 1;
+  for (int n : distinct_sizes(S)) {
+    if (build_plan(g, g->piece_plans[n], n, T, ws)) return 1;
+    ws += ws_layout(g, n, T).total;
+    g->max_piece = n > g->max_piece ? n : g->max_piece;
   }
   return 0;
 }
@@ -1279,9 +1310,9 @@ extern "C" int wdg_generator_stage_ms(wdg_generator* g, float* ms, int n) {
   return 0;
 }
 
-// Host-buffer entry point.  For B >= 2*CHUNK_B the batch is cut into chunks of CHUNK_B sequences and pipelined over
-// three streams: H2D copy of chunk i+1 | forward of chunk i | D2H copy of chunk i-1 (double-buffered staging), so the
-// step costs ~max(PCIe, compute) instead of their sum.  Sequences are independent, so chunking does not change results.
+// Host-buffer entry point.  For B >= 2*CHUNK_B the batch is cut into pieces (make_schedules) and pipelined over three
+// streams: H2D copy of piece i+1 | forward of piece i | D2H copy of piece i-1 (double-buffered staging), so the step
+// costs ~max(PCIe, compute) instead of their sum.  Sequences are independent, so the cut does not change results.
 static int predict_host_impl(wdg_generator* g, const float* image_host, const float* noise_host, float noise_std,
                              uint64_t noise_seed, uint64_t noise_offset, float* out_host, void* io_dev, void* stream_) {
   if (!g || !image_host || !out_host || !io_dev) return fail("null argument");
@@ -1291,7 +1322,8 @@ static int predict_host_impl(wdg_generator* g, const float* image_host, const fl
   const size_t seq_px = (size_t)full.T * g->S * g->S;
   const size_t s_img = seq_px * g->cin * 4, s_noise = seq_px * g->cnoise * 4, s_out = seq_px * g->cout * 4;
   uint8_t* io = (uint8_t*)io_dev;
-  if (!g->chunk_B) {
+  const std::vector<int>& sched = noise_host ? g->sched_host : g->sched_dev;
+  if (sched.empty()) {
     const size_t b_img = full.B * s_img, b_noise = full.B * s_noise, b_out = full.B * s_out;
     float* d_img = (float*)io;
     float* d_noise = (float*)(io + align_up(b_img, 256));
@@ -1314,19 +1346,15 @@ static int predict_host_impl(wdg_generator* g, const float* image_host, const fl
       CK(cudaEventCreateWithFlags(&g->ev_d2h[i], cudaEventDisableTiming));
     }
   }
-  const int cb = g->chunk_B;
+  const int cb = g->max_piece;                   // staging slots are sized for the largest piece
   const size_t slot = align_up(cb * s_img, 256) + align_up(cb * s_noise, 256) + align_up(cb * s_out, 256);
   // order the side streams after whatever the caller queued on `stream`
   CK(cudaEventRecord(g->ev_fwd[0], stream));
   CK(cudaStreamWaitEvent(g->copy_in, g->ev_fwd[0], 0));
-  const bool split_last = noise_host && g->plans[3].B > 0;
-  int i = 0;
-  for (int b0 = 0, nb = 0; b0 < full.B; b0 += nb, ++i) {
-    nb = full.B - b0 < cb ? full.B - b0 : cb;
-    const Plan* plp = nb == cb ? &g->plans[1] : &g->plans[2];
-    if (split_last && full.B - b0 == cb) { nb = cb - SHORT_B; plp = &g->plans[4]; }
-    else if (split_last && full.B - b0 == SHORT_B) { plp = &g->plans[3]; }
-    const Plan& pl = *plp;
+  int b0 = 0;
+  for (int i = 0; i < (int)sched.size(); b0 += sched[i], ++i) {
+    const int nb = sched[i];
+    const Plan& pl = g->piece_plans.at(nb);
     const int buf = i & 1;
     float* d_img = (float*)(io + buf * slot);
     float* d_noise = (float*)(io + buf * slot + align_up(cb * s_img, 256));
