@@ -255,6 +255,14 @@ int wdg_lstm16_fwd_step(float* gates, const float* h_prev, const float* packed, 
                         int N, int H, int W, void* stream);
 int wdg_lstm16_bwd_step(const float* dz_next, const float* packed, float* gates_s, const float* c_prev, const float* c_cur,
                         const float* dh, float* dc, int N, int H, int W, void* stream);
+/* Cells with F = 128 filters (the generator's ConvLSTM2D, models.py:45), tensor-core training modes: the same fused forward
+ * step (t >= 1) -- TMA-fed tcgen05 recurrent convolution (K = 9 x 128, N = 512) with the gate math in the TMEM epilogue.
+ * wdg_lstm128_pack: R [3][3][128][512] -> packed (WDG_LSTM128_PACK_FLOATS floats, tf32).  gates [N,H,W,512]: input
+ * convolution + bias of the step in, activated gates out (reference gate order i, f, c~, o); h_out rounded to tf32. */
+#define WDG_LSTM128_PACK_FLOATS (512 * 36 * 32)
+int wdg_lstm128_pack(const float* R, float* packed, void* stream);
+int wdg_lstm128_fwd_step(float* gates, const float* h_prev, const float* packed, const float* c_prev, float* c_out, float* h_out,
+                         int N, int H, int W, void* stream);
 /* Generator block Concatenate([a, b]) -> UpSampling2D(2, bilinear) -> Conv2DTranspose(16, 5x5, same) + bias -> LeakyReLU(0.2)
  * (models.py:60-64) in ONE fused pass for the training forward (tensor-core modes): a [N,h,h,32], b [N,h,h,128] dense fp32
  * -> out [N,2h,2h,16] dense fp32 (pre-BatchNorm).  w is the layer's kernel [5][5][16][160]; the 4x4 phase weights and the

@@ -83,6 +83,8 @@ def _declare(lib):
         "wdg_round_tf32": [vp, ll, vp],
         "wdg_lstm16_fwd_step": [vp, vp, vp, vp, vp, vp, i, i, i, vp],
         "wdg_lstm16_bwd_step": [vp, vp, vp, vp, vp, vp, vp, i, i, i, vp],
+        "wdg_lstm128_pack": [vp, vp, vp],
+        "wdg_lstm128_fwd_step": [vp, vp, vp, vp, vp, vp, i, i, i, vp],
         "wdg_upconv5x5_workspace_bytes": [ll, i, C.POINTER(sz)],
         "wdg_upconv5x5_fwd": [vp, vp, vp, vp, vp, ll, i, vp, sz, vp],
         "wdg_upsample2x_fwd": [vp, vp, ll, i, i, i, vp],

@@ -22,7 +22,7 @@ constexpr int MAX_KB = 80;
 constexpr int TILE_M = 128;
 constexpr int A_STAGE_BYTES = TILE_M * 128;
 
-enum { EPI_AFFINE = 0, EPI_LSTM = 1, EPI_UPCONV = 2, EPI_LSTM16_FWD = 3, EPI_LSTM16_BWD = 4 };
+enum { EPI_AFFINE = 0, EPI_LSTM = 1, EPI_UPCONV = 2, EPI_LSTM16_FWD = 3, EPI_LSTM16_BWD = 4, EPI_LSTM128_FWD = 5 };
 
 struct KBlock {        // one slice of the GEMM K axis
   int8_t src;          // which A tensor map (0..2)
@@ -71,6 +71,10 @@ struct EpiParams {
   //      writes c_t and h_t (h_t rounded to tf32: it is only ever a GEMM operand).  BWD (BN = 16): acc = recurrent
   //      part of dL/dh_s carried from step s + 1; applies the gate backward of step s in place over t_gates (dz,
   //      rounded to tf32) and updates the carried dL/dc.
+  //      EPI_LSTM128_FWD (BN = 256 = [i|f|c~|o] x 64 channels of N tile n; train_lstm16.cu): the same forward step for the
+  //      generator's 128-filter cell (models.py:45): t_gates is [pix][4 * t_F] in the reference's gate-major order
+  //      (column gate * t_F + channel), t_c_prev / t_c / t_h are [pix][t_F].
+  int t_F;
   float* t_gates;                    // [pix][64]
   const float* t_c_prev;             // [pix][16] c_{s-1} (NULL: zero)
   float* t_c;                        // FWD: c_t out; BWD: c_s in
@@ -137,7 +141,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   float* sm_scale = sm_bias + Cfg::VEC_COLS;
   float* sm_shift = sm_scale + Cfg::VEC_COLS;
   {
-    const int ncols = (EPI == EPI_UPCONV) ? 16 : ((EPI == EPI_LSTM16_FWD || EPI == EPI_LSTM16_BWD) ? 0 : p.n_tiles_N * BN);
+    const int ncols = (EPI == EPI_UPCONV) ? 16 : ((EPI == EPI_LSTM16_FWD || EPI == EPI_LSTM16_BWD || EPI == EPI_LSTM128_FWD) ? 0 : p.n_tiles_N * BN);
     for (int i = threadIdx.x; i < ncols && i < Cfg::VEC_COLS; i += blockDim.x) {
       sm_bias[i] = p.ep.bias[i];
       if constexpr (EPI == EPI_AFFINE || EPI == EPI_UPCONV) { sm_scale[i] = p.ep.scale[i]; sm_shift[i] = p.ep.shift[i]; }
@@ -401,6 +405,53 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             g4[12 + q] = make_float4(go[0], go[1], go[2], go[3]);
             c4[q] = make_float4(cn[0], cn[1], cn[2], cn[3]);
             h4[q] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          }
+        }
+      } else if constexpr (EPI == EPI_LSTM128_FWD) {
+        static_assert(EPI != EPI_LSTM128_FWD || BN == 256, "LSTM128 forward expects 4 gates x 64 channels per N tile");
+        const EpiParams& e = p.ep;
+        const long long pix = ((long long)n * p.H + y) * p.W + x;
+        const int Ft = e.t_F;
+#pragma unroll 1
+        for (int s = 0; s < 4; ++s) {
+          uint32_t zi[16], zf[16], zc[16], zo[16];
+          tmem_ld16(taddr + 0 * 64 + s * 16, zi);
+          tmem_ld16(taddr + 1 * 64 + s * 16, zf);
+          tmem_ld16(taddr + 2 * 64 + s * 16, zc);
+          tmem_ld16(taddr + 3 * 64 + s * 16, zo);
+          tmem_ld_wait();
+          if (valid) {
+            const int ch0 = n_tile * 64 + s * 16;
+            float* gp = e.t_gates + pix * 4 * Ft + ch0;          // gate g of this channel block at gp + g * Ft
+            const float4* cp4 = reinterpret_cast<const float4*>(e.t_c_prev + pix * Ft + ch0);
+            float4* c4 = reinterpret_cast<float4*>(e.t_c + pix * Ft + ch0);
+            float4* h4 = reinterpret_cast<float4*>(e.t_h + pix * Ft + ch0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4* gi4 = reinterpret_cast<float4*>(gp) + q;
+              float4* gf4 = reinterpret_cast<float4*>(gp + Ft) + q;
+              float4* gc4 = reinterpret_cast<float4*>(gp + 2 * Ft) + q;
+              float4* go4 = reinterpret_cast<float4*>(gp + 3 * Ft) + q;
+              const float4 xi = *gi4, xf = *gf4, xc = *gc4, xo = *go4, cp = cp4[q];
+              const float xi_[4] = {xi.x, xi.y, xi.z, xi.w}, xf_[4] = {xf.x, xf.y, xf.z, xf.w};
+              const float xc_[4] = {xc.x, xc.y, xc.z, xc.w}, xo_[4] = {xo.x, xo.y, xo.z, xo.w}, cp_[4] = {cp.x, cp.y, cp.z, cp.w};
+              float gi[4], gf[4], gc[4], go[4], cn[4], hn[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                gi[k] = hard_sigmoid(__uint_as_float(zi[4 * q + k]) + xi_[k]);
+                gf[k] = hard_sigmoid(__uint_as_float(zf[4 * q + k]) + xf_[k]);
+                gc[k] = tanhf(__uint_as_float(zc[4 * q + k]) + xc_[k]);
+                go[k] = hard_sigmoid(__uint_as_float(zo[4 * q + k]) + xo_[k]);
+                cn[k] = gf[k] * cp_[k] + gi[k] * gc[k];
+                hn[k] = __uint_as_float(to_tf32(go[k] * tanhf(cn[k])));
+              }
+              *gi4 = make_float4(gi[0], gi[1], gi[2], gi[3]);
+              *gf4 = make_float4(gf[0], gf[1], gf[2], gf[3]);
+              *gc4 = make_float4(gc[0], gc[1], gc[2], gc[3]);
+              *go4 = make_float4(go[0], go[1], go[2], go[3]);
+              c4[q] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+              h4[q] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            }
           }
         }
       } else if constexpr (EPI == EPI_LSTM16_BWD) {

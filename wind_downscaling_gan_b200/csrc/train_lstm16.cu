@@ -55,6 +55,17 @@ __global__ void pack_lstm16_kernel(const float* __restrict__ R, float* __restric
   }
 }
 
+// 128-filter cell, forward B operand: [512 rows][36 K-blocks x 32]: row = n_tile*256 + gate*64 + cc  <->  recurrent-kernel
+// column gate*128 + n_tile*64 + cc; K-block = tap*4 + chunk, element j = input channel chunk*32 + j.
+__global__ void pack_lstm128_kernel(const float* __restrict__ R, float* __restrict__ Bf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 512 * 36 * 32) return;
+  const int row = i / (36 * 32), kb = (i / 32) % 36, j = i % 32;
+  const int n_tile = row / 256, gate = (row % 256) / 64, cc = row % 64;
+  const int tap = kb / 4, ci = (kb % 4) * 32 + j;
+  Bf[i] = __uint_as_float(to_tf32(R[((long long)tap * 128 + ci) * 512 + gate * 128 + n_tile * 64 + cc]));
+}
+
 __global__ void round_tf32_kernel(float* __restrict__ x, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] = __uint_as_float(to_tf32(x[i]));
@@ -79,10 +90,10 @@ int sm_count() {
   return sms;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int NSTAGE = 3>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvParams& p, cudaStream_t stream) {
-  auto kern = conv_umma_kernel<BN, EPI, PREC_TF32, 3>;
-  using Cfg = ConvCfg<BN, 3>;
+  auto kern = conv_umma_kernel<BN, EPI, PREC_TF32, NSTAGE>;
+  using Cfg = ConvCfg<BN, NSTAGE>;
   static bool done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -90,7 +101,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, c
     CKL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     if (dev >= 0 && dev < 64) done[dev] = true;
   }
-  const int total = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int total = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_N;
   const int cap = sm_count() * Cfg::CTAS_PER_SM;
   kern<<<total < cap ? total : cap, 192, Cfg::SMEM_BYTES, stream>>>(a0, a1, a0, b, p);
   CKL(cudaGetLastError());
@@ -159,4 +170,46 @@ extern "C" int wdg_lstm16_bwd_step(const float* dz_next, const float* packed, fl
   }
   p.ep.t_gates = gates_s; p.ep.t_c_prev = c_prev; p.ep.t_c = const_cast<float*>(c_cur); p.ep.t_dh = dh; p.ep.t_dc = dc;
   return launch<16, EPI_LSTM16_BWD>(tmA, tmA, tmB, p, (cudaStream_t)stream);
+}
+
+// ---- the generator's 128-filter ConvLSTM2D (models.py:45) in the training path: one launch per timestep t >= 1 of the
+// inference engine's TMA-fed tcgen05 kernel (K = 9 taps x 128 channels, N = 512 = two tiles of [i|f|c~|o] x 64) with the
+// gate math in the TMEM epilogue.  The unfused step was a gather-fed GEMM at M = B*576 rows (94 us, latency-bound) that
+// read-modify-wrote the 512-channel pre-activations plus a gate kernel that read them again.
+extern "C" int wdg_lstm128_pack(const float* R, float* packed, void* stream) {
+  if (!R || !packed) return wdg_set_error("null argument");
+  pack_lstm128_kernel<<<(512 * 36 * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(R, packed);
+  CKL(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int wdg_lstm128_fwd_step(float* gates, const float* h_prev, const float* packed, const float* c_prev, float* c_out,
+                                    float* h_out, int N, int H, int W, void* stream) {
+  if (!gates || !h_prev || !packed || !c_prev || !c_out || !h_out || N <= 0 || H <= 0 || W <= 0) return wdg_set_error("bad argument");
+  constexpr uint64_t F = 128;
+  CUtensorMap tmA, tmB;
+  const uint64_t dims[5] = {F, (uint64_t)W, (uint64_t)H, (uint64_t)N, 1};
+  const uint64_t str[4] = {F, (uint64_t)W * F, (uint64_t)H * W * F, (uint64_t)N * H * W * F};
+  const uint32_t box[5] = {32, 8, 8, 2, 1};
+  if (wdg_make_tmap(&tmA, h_prev, 5, dims, str, box, 128, 4)) return 1;
+  const uint64_t bd[2] = {36 * 32, 512}, bs[1] = {36 * 32};
+  const uint32_t bb[2] = {32, 256};
+  if (wdg_make_tmap(&tmB, packed, 2, bd, bs, bb, 128, 4)) return 1;
+  ConvParams p;
+  std::memset(&p, 0, sizeof p);
+  p.H = H; p.W = W; p.N = N;
+  p.tile_w = 8; p.tile_h = 8; p.tile_n = 2;
+  p.tiles_x = (W + 7) / 8; p.tiles_y = (H + 7) / 8; p.tiles_n = (N + 1) / 2;
+  p.n_tiles_N = 2;
+  p.n_coord = 3;
+  p.ntile_coord = -1;
+  p.num_kb = 36;
+  for (int kb = 0; kb < 36; ++kb) {
+    KBlock& k = p.kb[kb];
+    const int tap = kb / 4;
+    k.src = 0; k.half = 0; k.o0 = (int16_t)((kb % 4) * 32); k.o1 = (int16_t)(tap % 3 - 1); k.o2 = (int16_t)(tap / 3 - 1); k.o3 = 0;
+  }
+  p.ep.t_F = (int)F;
+  p.ep.t_gates = gates; p.ep.t_c_prev = c_prev; p.ep.t_c = c_out; p.ep.t_h = h_out;
+  return launch<256, EPI_LSTM128_FWD, 0>(tmA, tmA, tmB, p, (cudaStream_t)stream);
 }

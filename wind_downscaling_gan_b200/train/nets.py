@@ -171,9 +171,18 @@ class ConvLSTM:
         small = F in ops.SMALL_LSTM_FILTERS and tuple(self.R.shape[:2]) == (3, 3)
         fused16 = F == 16 and tuple(self.R.shape[:2]) == (3, 3) and ops.lstm16_fused()
         packed = ops.lstm16_pack(self.R) if fused16 else None
+        fused128 = F == 128 and tuple(self.R.shape[:2]) == (3, 3) and ops.lstm128_fused()
+        packed128 = ops.lstm128_pack(self.R) if fused128 and T > 1 else None
         for t in range(T):
             if small:      # recurrent conv + gates in one bandwidth-bound pass (critic high-resolution branch)
                 ops.lstm_small_fwd(gates[t], hs[t - 1] if t > 0 else None, self.R, cs[t - 1] if t > 0 else None, cs[t], hs[t])
+                continue
+            if fused128:   # generator cell: recurrent conv (tcgen05, K = 1152, N = 512) + gates in ONE launch per step
+                if t == 0:
+                    ops.lstm_gates_fwd(gates[0], None, cs[0], hs[0])
+                    ops.round_tf32(hs[0])
+                else:
+                    ops.lstm128_fwd_step(gates[t], hs[t - 1], packed128, cs[t - 1], cs[t], hs[t])
                 continue
             if fused16:    # critic mixed branch: recurrent conv (tcgen05) + gates in ONE launch per step
                 if t == 0:

@@ -220,6 +220,24 @@ def lstm16_bwd_step(dz_next, packed, gates_s, c_prev, c_cur, dh, dc):
     _lib.check(_lib.lib().wdg_lstm16_bwd_step(_p(dz_next), _p(packed), _p(gates_s), _p(c_prev), _p(c_cur), _p(dh), _p(dc), N, H, W, _s()))
 
 
+def lstm128_pack(R):
+    """R [3,3,128,512] -> packed forward operand of the fused recurrent steps of the 128-filter cell (tf32)."""
+    packed = torch.empty(512 * 36 * 32, dtype=F32, device="cuda")
+    _lib.check(_lib.lib().wdg_lstm128_pack(_p(R), _p(packed), _s()))
+    return packed
+
+
+def lstm128_fwd_step(gates, h_prev, packed, c_prev, c_out, h_out):
+    N, H, W, _ = c_out.shape
+    _lib.check(_lib.lib().wdg_lstm128_fwd_step(_p(gates), _p(h_prev), _p(packed), _p(c_prev), _p(c_out), _p(h_out), N, H, W, _s()))
+
+
+def lstm128_fused():
+    """The generator's 128-filter cell runs its forward recurrent steps as fused tcgen05 launches in the tensor-core modes."""
+    import os
+    return get_precision() != "fp32" and not os.environ.get("WDG_NO_LSTM128")
+
+
 def upconv_fused():
     """The generator's concat -> bilinear x2 -> 5x5 transposed conv block runs as the fused tcgen05 kernel in the tensor-core
     training modes."""
