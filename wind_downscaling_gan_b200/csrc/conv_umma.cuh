@@ -174,6 +174,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // everything above overlapped the previous kernel's tail; its data is needed from here on
+  pdl_launch_dependents();
 
   // Producer and MMA loops are executed by the WHOLE warp (warp-uniform control flow, so addresses and
   // descriptors stay in uniform registers); only the TMA / tcgen05 instructions themselves are issued by

@@ -163,6 +163,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   cluster_sync_all();          // barriers of BOTH CTAs initialised before any remote arrive / TMA completion
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================================================== TMA producer (both CTAs)

@@ -137,6 +137,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   // Producer / MMA loops run warp-uniformly; one elected lane issues the TMA / tcgen05 instructions.
   if (warp == 0) {

@@ -80,6 +80,14 @@ __device__ __forceinline__ void flag_wait(const unsigned long long* flag, unsign
   }
 }
 
+// ------------------------------------------------- programmatic dependent launch (PDL)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream
+// is still running: its prologue (barrier init, TMEM allocation, tensor-map prefetch, per-column vectors -> smem) overlaps
+// the predecessor's tail.  pdl_wait() blocks until the predecessor grid has COMPLETED and its memory is visible -- it must
+// precede every access to data the predecessor produced or still reads; without the launch attribute it returns at once.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -1063,6 +1063,41 @@ extern "C" int wdg_generator_bind(wdg_generator* g, int B, int T, void* workspac
 // ---------------------------------------------------------------- launch
 static bool fused_noise_ok(const wdg_generator* g) { return g->cin == 3 && g->cnoise == 20 && g->CP == 24; }
 
+// One launch path for the tcgen05 kernels of the forward: optional cluster of 2 (CTA-pair kernels), cooperative launch
+// (persistent ConvLSTM) and programmatic dependent launch (the kernel's prologue overlaps its predecessor's tail; every
+// kernel calls griddepcontrol.wait before it touches dependent data).  WDG_PDL=0 turns the last off.  If the driver rejects
+// an attribute combination, PDL is dropped for the rest of the process and the launch is retried.
+static int g_pdl = -1;
+template <typename Kern, typename... Args>
+static int launch_ex(Kern kern, int grid, int block, size_t smem, cudaStream_t stream, bool cluster2, bool coop, Args... args) {
+  if (g_pdl < 0) g_pdl = getenv("WDG_PDL") ? atoi(getenv("WDG_PDL")) : 1;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cudaLaunchAttribute attrs[3];
+    int n = 0;
+    if (cluster2) {
+      attrs[n].id = cudaLaunchAttributeClusterDimension;
+      attrs[n].val.clusterDim.x = 2; attrs[n].val.clusterDim.y = 1; attrs[n].val.clusterDim.z = 1;
+      ++n;
+    }
+    if (coop) { attrs[n].id = cudaLaunchAttributeCooperative; attrs[n].val.cooperative = 1; ++n; }
+    const bool pdl = g_pdl != 0;
+    if (pdl) { attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; attrs[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.attrs = attrs; cfg.numAttrs = n;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+    if (e == cudaSuccess) return 0;
+    if (pdl && (e == cudaErrorInvalidValue || e == cudaErrorNotSupported)) {
+      cudaGetLastError();
+      g_pdl = 0;
+      continue;
+    }
+    return fail(std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(e));
+  }
+  return fail("cudaLaunchKernelEx failed");
+}
+
 // The opt-in shared-memory size is a per-device function attribute: set it once per (kernel, device).  `done` must be
 // a static of the CALLER's template instantiation (one per kernel), hence the macro.
 #define ENSURE_SMEM(kern, device, smem)                                                              \
@@ -1080,9 +1115,7 @@ static int launch_conv_t(const ConvLaunch& c, int device, cudaStream_t stream) {
   auto kern = conv_umma_kernel<BN, EPI, PREC, NSTAGE>;
   using Cfg = ConvCfg<BN, NSTAGE>;
   ENSURE_SMEM(kern, device, Cfg::SMEM_BYTES);
-  kern<<<c.grid, 192, Cfg::SMEM_BYTES, stream>>>(c.tmA[0], c.tmA[1], c.tmA[2], c.tmB, c.p);
-  CK(cudaGetLastError());
-  return 0;
+  return launch_ex(kern, c.grid, 192, Cfg::SMEM_BYTES, stream, false, false, c.tmA[0], c.tmA[1], c.tmA[2], c.tmB, c.p);
 }
 // Cooperative launch: every CTA of the grid is resident at once (the persistent ConvLSTM's CTAs wait for each other).
 template <int BN, int EPI, int PREC>
@@ -1091,14 +1124,7 @@ static int launch_conv_coop(const ConvLaunch& c, int device, cudaStream_t stream
   using Cfg = ConvCfg<BN, 0>;
   ENSURE_SMEM(kern, device, Cfg::SMEM_BYTES);
   static const int coop = getenv("WDG_LSTM_COOP") ? atoi(getenv("WDG_LSTM_COOP")) : 1;     // see lstm_pair_config
-  if (!coop) {
-    kern<<<c.grid, 192, Cfg::SMEM_BYTES, stream>>>(c.tmA[0], c.tmA[1], c.tmA[2], c.tmB, c.p);
-    CK(cudaGetLastError());
-    return 0;
-  }
-  void* args[5] = {(void*)&c.tmA[0], (void*)&c.tmA[1], (void*)&c.tmA[2], (void*)&c.tmB, (void*)&c.p};
-  CK(cudaLaunchCooperativeKernel((const void*)kern, dim3(c.grid), dim3(192), args, Cfg::SMEM_BYTES, stream));
-  return 0;
+  return launch_ex(kern, c.grid, 192, Cfg::SMEM_BYTES, stream, false, coop != 0, c.tmA[0], c.tmA[1], c.tmA[2], c.tmB, c.p);
 }
 // CTA-pair convolution (conv_umma2.cuh), plain cluster launch
 template <int BN, int EPI, int PREC>
@@ -1106,23 +1132,15 @@ static int launch_conv_pair(const CUtensorMap& tmA0, const CUtensorMap& tmA1, co
                             int device, cudaStream_t stream) {
   auto kern = conv_pair_kernel<BN, EPI, PREC>;
   ENSURE_SMEM(kern, device, PairCfg<BN>::SMEM_BYTES);
-  cudaLaunchConfig_t cfg;
-  std::memset(&cfg, 0, sizeof cfg);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = PairCfg<BN>::SMEM_BYTES; cfg.stream = stream;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, kern, tmA0, tmA1, tmB_half, p));
-  return 0;
+  return launch_ex(kern, grid, 192, PairCfg<BN>::SMEM_BYTES, stream, true, false, tmA0, tmA1, tmB_half, p);
 }
 template <int PREC>
 static int launch_lstm_pair(const Plan& pl, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attrs[2];
-  if (lstm_pair_config<PREC>(&cfg, attrs, pl.pair_grid, stream)) return 1;
-  CK(cudaLaunchKernelEx(&cfg, conv_pair_kernel<256, EPI_LSTM, PREC>, pl.LSP.tmA[0], pl.LSP.tmA[1], pl.tmB_half, pl.pair_p));
-  return 0;
+  if (lstm_pair_config<PREC>(&cfg, attrs, pl.pair_grid, stream)) return 1;     // sets the shared-memory attribute; numAttrs == 2: cooperative
+  return launch_ex(conv_pair_kernel<256, EPI_LSTM, PREC>, pl.pair_grid, 192, PairCfg<256>::SMEM_BYTES, stream, true, cfg.numAttrs == 2,
+                   pl.LSP.tmA[0], pl.LSP.tmA[1], pl.tmB_half, pl.pair_p);
 }
 template <int PREC>
 static int launch_conv(const ConvLaunch& c, int device, cudaStream_t stream) {
@@ -1140,9 +1158,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const Hal
   auto kern = halo_conv_kernel<BN, NCHUNK, NTAP, TPS, EPI, PREC>;
   constexpr int smem = HaloCfg<BN, NCHUNK, TPS>::SMEM;
   ENSURE_SMEM(kern, device, smem);
-  kern<<<grid, 224, smem, stream>>>(tmA, tmB, hp);
-  CK(cudaGetLastError());
-  return 0;
+  return launch_ex(kern, grid, 224, smem, stream, false, false, tmA, tmB, hp);
 }
 
 // CTA-pair form: clusters of 2 (the two SMs of a TPC), one tcgen05.mma.cta_group::2 per pair of passes
@@ -1152,15 +1168,7 @@ static int launch_halo_pair(const CUtensorMap& tmA, const CUtensorMap& tmB_half,
   auto kern = halo_conv_kernel<BN, NCHUNK, NTAP, TPS, EPI, PREC, true>;
   constexpr int smem = HaloCfg<BN / 2, NCHUNK, TPS>::SMEM;
   ENSURE_SMEM(kern, device, smem);
-  cudaLaunchConfig_t cfg;
-  std::memset(&cfg, 0, sizeof cfg);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(224); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB_half, hp));
-  return 0;
+  return launch_ex(kern, grid, 224, smem, stream, true, false, tmA, tmB_half, hp);
 }
 
 // noise_dev == nullptr: the noise is drawn inside the packing kernel from `ns` (std, key, first counter block)
@@ -1176,6 +1184,8 @@ static int run_plan_t(wdg_generator* g, const Plan& pl, const float* image_dev, 
   const int dev = g->device;
   int stage_i = 0;
   auto mark = [&]() { if (g->profiling && profile) cudaEventRecord(g->ev[stage_i++], stream); };
+  // step counters of the persistent ConvLSTM: cleared here, not next to its launch, so that the kernel chain stays unbroken
+  if (pl.lstm_persist) CK(cudaMemsetAsync(pl.lstm_flags, 0, (size_t)pl.T * pl.LSP.p.tiles_n * sizeof(unsigned long long), stream));
   mark();
   if (noise_dev) {
     pack_input_s2d_kernel<PREC><<<(unsigned)(N * S), 128, (size_t)S * (g->cin + g->cnoise) * sizeof(float), stream>>>(
@@ -1198,7 +1208,6 @@ static int run_plan_t(wdg_generator* g, const Plan& pl, const float* image_dev, 
   } else if (launch_conv<PREC>(pl.L2, dev, stream)) return 1;
   mark();
   if (pl.lstm_persist) {
-    CK(cudaMemsetAsync(pl.lstm_flags, 0, (size_t)pl.T * pl.LSP.p.tiles_n * sizeof(unsigned long long), stream));
     if (pl.lstm_pair) {
       if (launch_lstm_pair<PREC>(pl, stream)) return 1;
     } else if (launch_conv_coop<256, EPI_LSTM, PREC>(pl.LSP, dev, stream)) return 1;
