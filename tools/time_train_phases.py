@@ -32,7 +32,6 @@ gen.forward(lr, nz, True)
 timed("G backward", lambda: gen.backward(torch.ones_like(fake)), n=1)
 d = CriticNet(dw, S)
 timed("D forward (training)", lambda: d.forward(lr, hr, True))
-d.forward(lr, hr, True)
-timed("D backward input only", lambda: d.backward(ones, False, True), n=1)
-d.forward(lr, hr, True)
-timed("D backward weights only", lambda: d.backward(ones, True, False), n=1)
+# a context is consumed by its backward (wdg_critic_backward): time forward + backward pairs, subtract the forward above
+timed("D forward + backward input only", lambda: (d.forward(lr, hr, True), d.backward(ones, False, True)), n=1)
+timed("D forward + backward weights only", lambda: (d.forward(lr, hr, True), d.backward(ones, True, False)), n=1)
