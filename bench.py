@@ -153,12 +153,25 @@ def cpu_model_name():
 
 
 # ============================================================================================ CPU legs (the oracle port)
+_AFFINITY0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+
+
+def _all_host_cores():
+    """The CPU legs use every core the process started with (the GPU legs may have bound it to one NUMA node)."""
+    if _AFFINITY0 is not None:
+        try:
+            os.sched_setaffinity(0, _AFFINITY0)
+        except OSError:
+            pass
+    return len(_AFFINITY0) if _AFFINITY0 else (os.cpu_count() or 1)
+
+
 def cpu_port_fields_per_s(steps, warmup):
     """Times the CPU restatement of the reference generator graph on all host threads."""
     import torch
     from oracle.generator import synthetic_generator_weights
     from oracle.torch_port import TorchGenerator
-    cores = os.cpu_count() or 1
+    cores = _all_host_cores()
     torch.set_num_threads(cores)
     gen = TorchGenerator(synthetic_generator_weights(0), torch.float32)
     rng = np.random.default_rng(1)
@@ -184,7 +197,7 @@ def cpu_port_train_samples_per_s(steps, warmup, Bc=1, Tc=4):
     from oracle.critic import synthetic_critic_weights
     from oracle.generator import synthetic_generator_weights
     tt.DT = torch.float32
-    cores = os.cpu_count() or 1
+    cores = _all_host_cores()
     torch.set_num_threads(cores)
     rng = np.random.default_rng(0)
     lr = rng.standard_normal((Bc, Tc, S, S, 3)).astype(np.float32)
@@ -461,7 +474,20 @@ def run_training(args):
         sampler.start()
     ms_step = D.timed(step_resident, args.steps)
     clocks = sampler.stop() if D.rank == 0 else None
-    ar_ms = comm.collective_ms() / args.steps if comm is not None else 0.0
+    # The timed steps replay ONE CUDA graph: the collectives are nodes of it and no Python-side event brackets them.  Their
+    # device time is measured on two extra EAGER steps of the same model (CUDA events around every NCCL call).
+    ar_ms, ar_calls = 0.0, 0
+    if comm is not None:
+        graph_was = gan.use_cuda_graph
+        gan.use_cuda_graph = False
+        gan.train_step((lr_d, hr_d), comm=comm)
+        comm.reset_timers()
+        for _ in range(2):
+            gan.train_step((lr_d, hr_d), comm=comm)
+        ar_calls = len(comm._events) // 2
+        ar_ms = comm.collective_ms() / 2
+        comm.timing = False
+        gan.use_cuda_graph = graph_was
     launches = gan.launches_per_step() if hasattr(gan, "launches_per_step") else None
     step_e2e()
     ms_e2e = D.timed(step_e2e, args.steps)
@@ -501,7 +527,10 @@ def run_training(args):
                         "api": "GAN.train_step((low_res, high_res)) with pinned host batches; metrics dict read back"},
                 "gpu_launches": launches * args.steps if launches else None,
                 "collective": {"allreduce_ms_per_step": ar_ms, "share_of_step": ar_ms / ms_step if ms_step else None,
-                               "note": "device time of the NCCL collectives (gradient buckets + BatchNorm statistics), CUDA events on the launch stream"},
+                               "nccl_calls_per_step": ar_calls,
+                               "note": "device time of the NCCL collectives (flat gradient buffers + BatchNorm statistics), CUDA events "
+                                       "around every call on the launch stream, measured on 2 eager steps after the timed "
+                                       "CUDA-graph region (inside the graph they are nodes no event brackets)"},
                 "dead_gradient_penalty_skipped": {"value": D.world * TB / (ms_skip * 1e-3), "unit": "samples/s", "ms_per_step": ms_skip,
                                                   "note": "GAN(..., skip_dead_gradient_penalty=True): same weights and metrics bit for bit; NOT the headline"},
                 "cuda_graph": bool(getattr(gan, "_graphed", None) is not None and gan._graphed.graph is not None),
