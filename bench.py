@@ -294,8 +294,19 @@ class Dist:
         return self.max_over_ranks(ev0.elapsed_time(ev1)) / steps
 
     def close(self):
+        """Tear the process group down; never hang on it.  (Seen once at N = 2: destroy_process_group() did not return
+        after a run that mixed CUDA-graph-captured and eager NCCL calls on one communicator -- the JSON line was already
+        out.)  All ranks meet at a barrier, flush, and a watchdog ends the process if the teardown stalls."""
         if self.world > 1:
+            import gc
+            import threading
+            sys.stdout.flush()
+            sys.stderr.flush()
+            self.barrier()
+            gc.collect()
+            threading.Timer(15.0, lambda: os._exit(0)).start()
             self.dist.destroy_process_group()
+            os._exit(0)
 
 
 # ============================================================================================ inference

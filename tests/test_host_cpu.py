@@ -113,3 +113,34 @@ def test_shard_units_covers_everything_once():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_numa_binding_is_a_noop_without_topology_information(monkeypatch):
+    """hostmem.bind_to_gpu_numa_node: parses sysfs cpulists, never widens the affinity mask, and does nothing when the box
+    does not say which node a GPU sits on (this container: no GPU at all)."""
+    import os
+    from wind_downscaling_gan_b200 import hostmem
+    before = os.sched_getaffinity(0)
+    rep = hostmem.bind_to_gpu_numa_node(0)
+    assert rep["bound"] is False and rep["numa_node"] is None and os.sched_getaffinity(0) == before
+    # a node whose CPU list covers this process: binding keeps the intersection only
+    monkeypatch.setattr(hostmem, "gpu_numa_node", lambda i: 0)
+    some = set(sorted(before)[:max(1, len(before) // 2)])
+    monkeypatch.setattr(hostmem, "node_cpus", lambda n: some | {10_000})
+    try:
+        rep = hostmem.bind_to_gpu_numa_node(0)
+        assert os.sched_getaffinity(0) == some and rep["bound"] == (some != before) and rep["cpus_on_node"] == len(some)
+    finally:
+        os.sched_setaffinity(0, before)
+
+
+def test_numa_cpulist_parsing(monkeypatch):
+    import builtins
+    import io
+    from wind_downscaling_gan_b200 import hostmem
+    real_open = builtins.open
+    monkeypatch.setattr(builtins, "open", lambda p, *a, **k: io.StringIO("0-3,8,10-11\n") if str(p).endswith("node7/cpulist")
+                        else real_open(p, *a, **k))
+    assert hostmem.node_cpus(7) == {0, 1, 2, 3, 8, 10, 11}
+    monkeypatch.undo()
+    assert hostmem.node_cpus(123456) == set()
