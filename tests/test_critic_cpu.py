@@ -99,3 +99,25 @@ def test_save_weights_writes_checkpoint_bundles(tmp_path):
     d2.load_weights(tmp_path / "ck" / "discriminator")
     a, b = d.get_weights(), d2.get_weights()
     assert all(np.array_equal(a[k], b[k]) for k in a)
+
+
+def test_buffer_sizes_are_host_arithmetic():
+    """context / scratch sizes come from the same allocation walk the kernels' launcher uses; no device needed, and the
+    process-wide training precision is not touched by asking."""
+    from wind_downscaling_gan_b200 import _lib
+    from wind_downscaling_gan_b200.train.nets import CriticHandle
+    L = _lib.lib()
+    h = CriticHandle.get(96, 3, 2, 16, True)
+    before = L.wdg_train_get_precision()
+    ctx_t, ctx_i, scr = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    assert L.wdg_critic_context_bytes(h.h, 8, 24, 1, C.byref(ctx_t)) == 0
+    assert L.wdg_critic_context_bytes(h.h, 8, 24, 0, C.byref(ctx_i)) == 0
+    assert L.wdg_critic_scratch_bytes(h.h, 8, 24, C.byref(scr)) == 0
+    assert L.wdg_train_get_precision() == before
+    px = 8 * 24 * 96 * 96
+    # gates of the 16-filter cell alone are px * 64 floats; the training context additionally snapshots the variables
+    assert ctx_i.value > px * 64 * 4 and ctx_t.value - ctx_i.value >= h.n_train * 4
+    assert scr.value > px * 16 * 4 and scr.value % 256 == 0 or scr.value > 0
+    small = C.c_size_t()
+    assert L.wdg_critic_context_bytes(h.h, 1, 2, 1, C.byref(small)) == 0 and small.value < ctx_t.value
+    assert L.wdg_critic_context_bytes(h.h, 0, 2, 1, C.byref(small)) != 0

@@ -41,6 +41,9 @@ static inline BwdClass make_bwd_class(const ConvGeo& g, int ry, int rx) {
   return c;
 }
 
+// split-K scratch of wdg_conv2d_bwd_weight for a given arithmetic mode (train_ops.cu)
+int wdg_wgrad_scratch_for_mode(const int* geo, int mode, size_t* bytes, int* splits_out);
+
 // tcgen05 paths (train_gemm_tc.cu).  op: 1 = tf32 operands, 2 = bf16 operands; fp32 accumulation in TMEM.
 // alpha: slope of the LeakyReLU applied to the final value (1 = linear)
 int wdg_tc_conv2d_fwd(const ConvGeo& g, const float* x, const float* w, const float* bias, float* y, int accumulate, float alpha,

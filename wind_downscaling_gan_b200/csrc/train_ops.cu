@@ -1112,7 +1112,9 @@ static int sm_count_now() {      // split-K heuristic of the fp32 backward-weigh
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   return n;
 }
-extern "C" int wdg_conv2d_bwd_weight_scratch(const int* geo, size_t* bytes, int* splits_out) {
+// Split-K plan / scratch of the backward-weight GEMM in arithmetic `mode` (0 fp32, 1 tf32, 2 bf16).  Also called by
+// wdg_critic.cu, which sizes its scratch for every mode without touching the process-wide setting.
+int wdg_wgrad_scratch_for_mode(const int* geo, int mode, size_t* bytes, int* splits_out) {
   const ConvGeo g = make_geo(geo);
   const long long M = (long long)g.kh * g.kw * g.Ci, K = (long long)g.N * g.Ho * g.Wo;
   if (wdg_sparse::applies(g)) {   // no split-K partials
@@ -1126,9 +1128,9 @@ extern "C" int wdg_conv2d_bwd_weight_scratch(const int* geo, size_t* bytes, int*
     if (bytes) *bytes = (size_t)(sl * M * g.Co * sizeof(float));
     return 0;
   }
-  if (g_train_precision) {
+  if (mode) {
     int sp; long long kps;
-    wdg_tc_wgrad_plan(g, g_train_precision, &sp, &kps);
+    wdg_tc_wgrad_plan(g, mode, &sp, &kps);
     if (splits_out) *splits_out = sp;
     if (bytes) *bytes = (size_t)((long long)sp * M * g.Co * sizeof(float));
     return 0;
@@ -1141,6 +1143,10 @@ extern "C" int wdg_conv2d_bwd_weight_scratch(const int* geo, size_t* bytes, int*
   if (splits_out) *splits_out = (int)splits;
   if (bytes) *bytes = (size_t)(splits * M * g.Co * sizeof(float));
   return 0;
+}
+
+extern "C" int wdg_conv2d_bwd_weight_scratch(const int* geo, size_t* bytes, int* splits_out) {
+  return wdg_wgrad_scratch_for_mode(geo, g_train_precision, bytes, splits_out);
 }
 
 extern "C" int wdg_conv2d_bwd_weight(const float* x, const float* dy, float* dw, const int* geo, void* scratch,

@@ -252,12 +252,10 @@ size_t op_scratch_bytes(const wdg_critic* c, int B, int T) {
   auto colsum = [&](int C) { up((size_t)512 * (C > 32 ? C : 32) * 4); };
   auto ln_bwd = [&](long long rows, int C) { up(((size_t)rows * C + (size_t)512 * (C > 32 ? C : 32)) * 4); };
   auto sn = [&](const ConvSpec& e) { up(((size_t)e.k * e.k * e.cin + 64 * (size_t)e.cout + 4) * 4); };
-  const int saved = wdg_train_get_precision();
-  auto wgrad = [&](const Geo& g) {
+  auto wgrad = [&](const Geo& g) {      // every arithmetic mode: a buffer sized now stays valid if the caller switches precision
     for (int mode = 0; mode < 3; ++mode) {
-      wdg_train_set_precision(mode);
       size_t b = 0;
-      wdg_conv2d_bwd_weight_scratch(g.v, &b, nullptr);
+      wdg_wgrad_scratch_for_mode(g.v, mode, &b, nullptr);
       up(b);
     }
   };
@@ -275,7 +273,6 @@ size_t op_scratch_bytes(const wdg_critic* c, int B, int T) {
     wgrad(lstm_geo(N, c->size, l->cin, 4 * l->F));
     wgrad(lstm_geo(N, c->size, l->F, 4 * l->F));
   }
-  wdg_train_set_precision(saved);
   return (m + 255) & ~(size_t)255;
 }
 
