@@ -101,6 +101,13 @@ int wdg_generator_predict_host(wdg_generator* g, const float* image_host, const 
 int wdg_generator_predict_host_gen_noise(wdg_generator* g, const float* image_host, float noise_std, uint64_t noise_seed,
                                          uint64_t noise_offset, float* out_host, void* io_dev, void* stream);
 
+/* The piece sizes (sequences) predict_host / predict_host_gen_noise cut a batch of B sequences into: H2D of piece i+1,
+ * forward of piece i and D2H of piece i-1 overlap on three streams.  host_noise != 0: the H2D-bound schedule of
+ * predict_host (uniform chunks, short last piece); 0: the compute-bound one of predict_host_gen_noise (small head and tail,
+ * doubling pieces in between).  Returns the number of pieces (0: the batch is run in one piece) and writes up to
+ * `capacity` of them; -1 on a bad argument.  Host arithmetic only. */
+int wdg_generator_pipeline_schedule(int B, int host_noise, int* pieces, int capacity);
+
 /* Number of kernels one forward() launches for the bound plan (bench.py's gpu_launches). */
 int wdg_generator_launches_per_forward(const wdg_generator* g);
 

@@ -144,3 +144,25 @@ def test_philox_known_answers(lib):
     assert ph([0] * 4, [0] * 2) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
     assert ph([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert ph([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_host_pipeline_schedules(lib, monkeypatch):
+    """The pieces predict_host* cuts a batch into (csrc/wdg_generator.cu: make_schedules): cover the batch exactly, the
+    device-noise schedule starts and ends small, the host-noise one ends with the short piece."""
+    def sched(B, host):
+        buf = (ctypes.c_int * 32)()
+        n = lib.wdg_generator_pipeline_schedule(B, host, buf, 32)
+        return [buf[i] for i in range(n)]
+    monkeypatch.delenv("WDG_CHUNK_B", raising=False)
+    assert sched(64, 0) == [8, 16, 32, 8] and sched(64, 1) == [16, 16, 16, 12, 4]
+    assert sched(37, 0) == [8, 21, 8] and sched(37, 1) == [16, 16, 5]
+    assert sched(32, 0) == [8, 16, 8] and sched(31, 0) == [] and sched(16, 1) == []
+    for B in range(32, 300, 7):
+        for host in (0, 1):
+            p = sched(B, host)
+            assert sum(p) == B and min(p) >= 1, (B, host, p)
+        d = sched(B, 0)
+        assert d[0] == 8 and d[-1] == 8 and max(d) <= 39
+    monkeypatch.setenv("WDG_CHUNK_B", "8")
+    assert sched(24, 0) == [8, 8, 8] and sched(20, 1) == [8, 8, 4]
+    assert lib.wdg_generator_pipeline_schedule(0, 0, None, 0) == -1

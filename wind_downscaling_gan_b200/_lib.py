@@ -40,6 +40,7 @@ def _declare(lib):
         "wdg_generator_predict_host": [vp, vp, vp, vp, vp, vp],
         "wdg_generator_predict_host_gen_noise": [vp, vp, C.c_float, C.c_uint64, C.c_uint64, vp, vp, vp],
         "wdg_generator_launches_per_forward": [vp],
+        "wdg_generator_pipeline_schedule": [i, i, C.POINTER(i), i],
         "wdg_generator_debug_read": [vp, i, vp, C.c_int64],
         "wdg_generator_profile": [vp, i],
         "wdg_generator_stage_ms": [vp, vp, i],

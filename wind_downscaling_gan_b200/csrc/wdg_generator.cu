@@ -578,6 +578,15 @@ static std::vector<int> distinct_sizes(const Schedules& S) {
   return v;
 }
 
+// Introspection (host arithmetic only): the piece sizes predict_host* cuts a batch of B sequences into.
+extern "C" int wdg_generator_pipeline_schedule(int B, int host_noise, int* pieces, int capacity) {
+  if (B <= 0 || (!pieces && capacity > 0)) return -1;
+  const Schedules S = make_schedules(B);
+  const std::vector<int>& v = host_noise ? S.host : S.dev;
+  for (int i = 0; i < (int)v.size() && i < capacity; ++i) pieces[i] = v[i];
+  return (int)v.size();
+}
+
 extern "C" int wdg_generator_workspace_bytes(const wdg_generator* g, int B, int T, size_t* bytes) {
   if (!g || !bytes || B <= 0 || T <= 0) return fail("bad argument");
   *bytes = ws_layout(g, B, T).total;
