@@ -61,6 +61,25 @@ TRAIN_FLOP_PER_SAMPLE = 1.0e12
 TRAIN_WORKLOAD = f"WGAN train_step, batch {TB} per GPU x {TT} timesteps x {S}x{S} (BASELINE configs[3])"
 
 
+TOLERANCE = {"bf16": "rel-L2 <= 1e-2 vs float64 oracle (bf16 operands, fp32 accumulate)",
+             "tf32": "rel-L2 <= 1e-3 vs float64 oracle (tf32 operands, fp32 accumulate, fp32 output conv)"}
+
+
+def infer_config(world, precision):
+    """The `config` object of the inference line -- identical in the b200 arm and the reference arm."""
+    return {"workload": WORKLOAD, "fields_per_step_per_gpu": FIELDS_PER_STEP,
+            "weights": "synthetic, seed 0, non-trivial BN stats",
+            "parallelism": f"independent sequences x{world}, no collective",
+            "l2": "inputs 434 MB + >1.6 GB activations per step exceed the 126 MB L2",
+            "tolerance": TOLERANCE[precision]}
+
+
+def train_config(world):
+    return {"workload": TRAIN_WORKLOAD,
+            "parallelism": f"data parallel x{world}: NCCL gradient all-reduce (4 per step) + synchronised BatchNorm",
+            "l2": "activations of one step (> 10 GB) exceed the 126 MB L2"}
+
+
 def stage_bytes(esz):
     """Algorithmic HBM bytes per field of the bandwidth-bound stages (esz = bytes per activation element)."""
     return {"pack_input": 96 * 96 * 23 * 4 + 102 * 102 * 24 * esz,
@@ -230,7 +249,7 @@ def run_reference(args):
         line = {"impl": "reference", "metric": "wgan_train_samples_per_sec", "value": v, "unit": "samples/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": 1e3 * sum(times) / len(times),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": TRAIN_WORKLOAD},
+                "config": train_config(int(os.environ.get("WORLD_SIZE", "1"))),
                 "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                                  "sample": sample + f"; torch-CPU fp32 autograd restatement of ganbase.py:21-94 on {cores} threads "
                                                     f"({cpu_model_name()}); TensorFlow 2.4.3 not installable"},
@@ -244,7 +263,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "generator_fields_per_sec", "value": v, "unit": "fields/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": infer_config(int(os.environ.get("WORLD_SIZE", "1")), args.precision),
             "cpu_baseline": {"value": v, "unit": "fields/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "fields/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -428,11 +448,7 @@ def run_inference(args):
         line = {"metric": "generator_fields_per_sec", "value": main["value"], "unit": "fields/s", "n_gpus": D.world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": WORKLOAD, "fields_per_step_per_gpu": FIELDS_PER_STEP,
-                           "weights": "synthetic, seed 0, non-trivial BN stats",
-                           "parallelism": f"independent sequences x{D.world}, no collective",
-                           "l2": "inputs 434 MB + >1.6 GB activations per step exceed the 126 MB L2",
-                           "tolerance": tol[args.precision]},
+                "config": infer_config(D.world, args.precision),
                 "e2e": main["e2e"], "e2e_host_noise": main["e2e_host_noise"],
                 "gpu_launches": gen.launches_per_forward() * args.steps,
                 "clocks": main["clocks"], "host_numa": D.numa, "roofline": inference_roofline(main, peaks, D.world),
@@ -530,9 +546,7 @@ def run_training(args):
         line = {"metric": "wgan_train_samples_per_sec", "value": samples, "unit": "samples/s", "n_gpus": D.world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
-                "config": {"workload": TRAIN_WORKLOAD,
-                           "parallelism": f"data parallel x{D.world}: NCCL gradient all-reduce (4 per step) + synchronised BatchNorm",
-                           "l2": "activations of one step (> 10 GB) exceed the 126 MB L2"},
+                "config": train_config(D.world),
                 "e2e": {"value": D.world * TB / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(lr_p.numel() * 4 + hr_p.numel() * 4), "d2h_bytes_per_step": 64,
                         "api": "GAN.train_step((low_res, high_res)) with pinned host batches; metrics dict read back"},
